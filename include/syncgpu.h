@@ -1,0 +1,169 @@
+/*
+ * syncgpu.h -- C ABI of libsyncgpu.so, the B200 (sm_100a) implementation of the
+ * oatk/syncasm hot path: closed-syncmer extraction, syncmer counting and the arc
+ * tally of the sparse de Bruijn graph.
+ *
+ * The boundary is what the reference's own functions for this path would bind
+ * if its host code stayed in C and called a device library (INTEGRATION.md shows
+ * the stub a maintainer would add to reference syncmer.c / syncasm.c):
+ *
+ *   reference function (file:line)                    entry point here
+ *   ------------------------------------------------  -------------------------
+ *   sr_read + sr_read_analysis_thread                 sg_batch_set_reads_*,
+ *     (syncmer.c:487-556, 243-421), kmer_hash64         sg_extract,
+ *     (syncmer.c:175-226)                               sg_extract_sizes / _download
+ *   sr_db_stat counting part (syncmer.c:867-987)      sg_stat
+ *   collect_syncmer_from_reads + process_kmer_cluster sg_count,
+ *     (syncmer.c:1397-1451, 1270-1393)                  sg_count_sizes / _download
+ *   make_syncmer_graph arc tally (syncasm.c:236-282)  sg_arcs
+ *
+ * Plain pointers and sizes only; no C++ or torch types. All functions return 0
+ * or a negative SG_E_* code and never call exit(). There is no CPU fallback:
+ * without a CUDA device every compute call fails with SG_E_CUDA.
+ *
+ * Threading: a context and the batches made from it belong to one host thread
+ * at a time. One context per GPU; one process per GPU for multi-GPU runs.
+ */
+#ifndef SYNCGPU_H
+#define SYNCGPU_H
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SG_OK              0
+#define SG_E_CUDA         -1   /* a CUDA runtime call failed (sg_last_error has the text) */
+#define SG_E_ARG          -2   /* bad argument (k/s out of range, NULL pointer, state) */
+#define SG_E_NOMEM        -3   /* host or device allocation failed */
+#define SG_E_LIMIT        -4   /* reference limits exceeded: > 2^32-1 reads, read > 2^31-1 bases (syncmer.h:43-45) */
+#define SG_E_KSIZE        -5   /* k too large for the shared-memory window of the scan kernel */
+#define SG_E_SMER_CONFLICT -6  /* identical k-mers with different s-mer codes (reference exits, syncmer.c:1370-1376) */
+#define SG_E_EMPTY        -7   /* no syncmers in the batch (reference returns NULL, syncmer.c:1414-1417) */
+#define SG_E_STATE        -8   /* call order violated (e.g. sg_count before sg_extract) */
+
+typedef struct sg_ctx sg_ctx;
+typedef struct sg_batch sg_batch;
+
+/* ---- context ---- */
+int sg_ctx_create(int device, sg_ctx **out);
+void sg_ctx_destroy(sg_ctx *ctx);
+/* launch everything on this cudaStream_t (NULL = the legacy default stream) */
+int sg_ctx_set_stream(sg_ctx *ctx, void *cuda_stream);
+int sg_ctx_sync(sg_ctx *ctx);
+const char *sg_strerror(int code);
+const char *sg_last_error(sg_ctx *ctx);
+/* number of kernels launched by this context since creation (bench.py's gpu_launches) */
+uint64_t sg_ctx_launches(sg_ctx *ctx);
+/* per-stage device time of the most recent call, CUDA events on the context's stream */
+enum { SG_T_ENCODE = 0, SG_T_SCAN, SG_T_KMERHASH, SG_T_PLACE, SG_T_SORT, SG_T_GROUP, SG_T_STAT, SG_T_ARCS, SG_T_PACK, SG_T_N };
+int sg_ctx_enable_timing(sg_ctx *ctx, int on);
+int sg_ctx_timings(sg_ctx *ctx, float *ms /* SG_T_N */, uint32_t *launches /* SG_T_N */);
+
+/* ---- a batch of reads and everything derived from it (device resident) ---- */
+int sg_batch_create(sg_ctx *ctx, sg_batch **out);
+void sg_batch_destroy(sg_batch *b);
+/* bases: all reads back to back, 1 byte per base as in the FASTA/FASTQ record;
+ * off: n_reads+1 byte offsets into bases. Host version copies (bases need not be
+ * pinned; pinned makes the copy asynchronous). Device version borrows the
+ * pointers, which must stay valid until the batch is destroyed or reset; the
+ * bases pointer must be 16-byte aligned. */
+int sg_batch_set_reads_host(sg_batch *b, const char *bases, const uint64_t *off, uint64_t n_reads);
+int sg_batch_set_reads_device(sg_batch *b, const void *d_bases, const uint64_t *d_off, uint64_t n_reads, uint64_t total_bases);
+/* read ids of this batch start here (sid = sid_base + index); default 0 */
+int sg_batch_set_sid_base(sg_batch *b, uint64_t sid_base);
+
+/* a2-a4: homopolymer compression, 2-bit packing, closed-syncmer selection and
+ * MurmurHash64A of every selected k-mer. Asynchronous on the context stream. */
+int sg_extract(sg_batch *b, int k, int s);
+
+typedef struct {
+    uint64_t n_reads;
+    uint64_t n_syncmers;      /* sum of sr_t.n */
+    uint64_t hoco_bases;      /* sum of sr_t.hoco_l */
+    uint64_t hoco_s_bytes;    /* size of the packed download buffer (reads 16-byte aligned) */
+    uint64_t ho_rl_bytes;     /* size of the run-length download buffer (reads 16-byte aligned) */
+    uint64_t n_ambiguous;     /* total entries of all sr_t.n_nucl */
+    uint64_t n_long_runs;     /* total entries of all sr_t.ho_l_rl */
+} sg_extract_sizes_t;
+int sg_extract_sizes(sg_batch *b, sg_extract_sizes_t *out);   /* synchronises */
+
+/* Host destinations; any pointer may be NULL to skip that array.
+ * Per read r (reference sr_t, syncmer.h:48-70):
+ *   hoco_s  = hoco_s_buf + hoco_s_off[r], ceil(hoco_l[r]/4) bytes
+ *   ho_rl   = ho_rl_buf  + ho_rl_off[r],  hoco_l[r] bytes
+ *   m_pos/s_mer/k_mer = arrays + scm_off[r], n_scm[r] entries
+ *   n_nucl  = the amb_pos entries whose amb_sid == r (sorted by sid, then position)
+ *   ho_l_rl = the lrl_val entries whose lrl_sid == r (sorted by sid, then hoco index) */
+typedef struct {
+    uint32_t *hoco_l;        /* n_reads */
+    uint32_t *n_scm;         /* n_reads */
+    uint64_t *hoco_s_off;    /* n_reads + 1 */
+    uint64_t *ho_rl_off;     /* n_reads + 1 */
+    uint64_t *scm_off;       /* n_reads + 1 */
+    uint8_t *hoco_s_buf;     /* hoco_s_bytes */
+    uint8_t *ho_rl_buf;      /* ho_rl_bytes */
+    uint32_t *m_pos;         /* n_syncmers: hoco start << 1 | rev */
+    uint64_t *s_mer;         /* n_syncmers: canonical s-mer << 1 | orientation */
+    uint64_t *k_mer;         /* n_syncmers: k-mer hash (after sg_count: id << 1) */
+    uint32_t *amb_sid, *amb_pos;             /* n_ambiguous */
+    uint32_t *lrl_sid, *lrl_idx, *lrl_val;   /* n_long_runs */
+} sg_extract_out_t;
+int sg_extract_download(sg_batch *b, const sg_extract_out_t *out);
+
+/* a5: the counting part of sr_db_stat. Dense multiplicity-of-multiplicity tables
+ * for distinct s-mer codes and distinct (k_mer >> 1) keys, multiplicities >= 1000
+ * summed in [1000] (reference kh_ctab_cnt with MAX_DEPTH 1000, syncmer.c:639-659),
+ * and the gap sum of consecutive syncmers on a read. Peak finding stays on the host. */
+typedef struct {
+    uint64_t n_syncmers;
+    uint64_t n_gaps;          /* pairs of consecutive syncmers on one read */
+    int64_t gap_sum;          /* sum of (p1 - p0 - k) over those pairs */
+    uint64_t smer_unique, smer_singleton;
+    uint64_t kmer_unique, kmer_singleton;
+    int64_t smer_cnts[1001];
+    int64_t kmer_cnts[1001];
+} sg_stat_t;
+int sg_stat(sg_batch *b, sg_stat_t *out);                     /* synchronises */
+
+/* a6: syncmer database. Sorts the (hash, sid, idx, rev) tuples, groups them by
+ * hash, verifies with an exact sequence comparison that a group holds one
+ * k-mer (splitting it like process_kmer_cluster when it does not), assigns
+ * dense ids in hash order and rewrites k_mer[] to id << 1. */
+int sg_count(sg_batch *b);
+typedef struct {
+    uint64_t n_syncmers;      /* occurrences */
+    uint64_t n_unique;        /* syncmer_db_t.n */
+    uint64_t n_hash_collisions; /* hash groups that had to be split */
+} sg_count_sizes_t;
+int sg_count_sizes(sg_batch *b, sg_count_sizes_t *out);       /* synchronises */
+typedef struct {
+    uint64_t *h;              /* n_unique: syncmer_t.h */
+    uint64_t *s;              /* n_unique: syncmer_t.s */
+    uint32_t *cov;            /* n_unique: syncmer_t.cov */
+    uint64_t *occ_off;        /* n_unique + 1 */
+    uint64_t *occ;            /* n_syncmers: concatenated syncmer_t.m_pos lists (sid<<32 | idx<<1 | rev) */
+    uint64_t *k_mer_id;       /* n_syncmers, read order: id << 1 (sr_t.k_mer after collect) */
+} sg_count_out_t;
+int sg_count_download(sg_batch *b, const sg_count_out_t *out);
+
+/* a7: arc tally of make_syncmer_graph. Counts canonical (v0,v1) neighbour pairs
+ * in a warp-cooperative open-addressing table, applies the coverage filters and
+ * returns arcs and their complements sorted by (v, w, comp): 4 uint64 per arc
+ * = v, w, cov, comp. Vertex ids are syncmer ids (before asmg_cleanup renumbers). */
+int sg_arcs(sg_batch *b, uint32_t min_k_cov, double min_a_cov_f, uint64_t *n_arcs);  /* synchronises */
+int sg_arcs_download(sg_batch *b, uint64_t *arcs4);
+
+/* ---- multi-GPU exchange (one process per GPU; the transport is the caller's
+ * collective, e.g. NCCL all-to-all; see oatk_b200/dist.py) ---- */
+/* partition this batch's tuples by hash range into n_parts buckets: counts[p] tuples for part p,
+ * laid out contiguously in an internal device buffer of 3 x uint64 per tuple (hash, occ, s_mer) */
+int sg_tuples_partition(sg_batch *b, int n_parts, uint64_t *counts /* host, n_parts */, void **d_tuples /* device ptr out */);
+/* replace this batch's tuple set by tuples received from the peers (device pointer, n tuples of 3 x uint64) */
+int sg_tuples_adopt(sg_batch *b, const void *d_tuples, uint64_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,70 @@
+// sg_host.h -- host-side state behind the opaque handles of include/syncgpu.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/syncgpu.h"
+
+namespace sg {
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes);     // grow-only; contents are not preserved
+    void release();
+    ~DevBuf() { release(); }
+};
+
+} // namespace sg
+
+struct sg_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    uint64_t launches = 0;
+    bool timing = false;
+    cudaEvent_t ev[SG_T_N][2];
+    bool ev_used[SG_T_N] = {};
+    uint32_t stage_launch[SG_T_N] = {};
+    void count_launch(int stage, int n);
+    void t_begin(int stage);
+    void t_end(int stage);
+};
+
+struct sg_batch {
+    sg_ctx *ctx = nullptr;
+    // input
+    const uint8_t *d_bases = nullptr;
+    const uint64_t *d_off = nullptr;
+    uint64_t n_reads = 0, total_bases = 0, sid_base = 0;
+    sg::DevBuf own_bases, own_off;
+    // state
+    bool extracted = false, counted = false, sizes_known = false;
+    int k = 0, s = 0;
+    uint64_t n_syncmers = 0, n_amb_total = 0, n_lrl_total = 0, hoco_bases = 0;
+    uint64_t h2d_bytes = 0, d2h_bytes = 0;
+    // a2-a4 device results (capacity-indexed layout, see sg_common.cuh)
+    sg::DevBuf hoff, scan_tmp, hoco_s, ho_rl, nbits, hoco_l, n_amb, n_scm, scm_off, counters;
+    uint64_t amb_cap = 0, lrl_cap = 0, rec_cap = 0;
+    sg::DevBuf amb_sid, amb_pos, lrl_sid, lrl_idx, lrl_val;
+    sg::DevBuf rec_sid, rec_idx, rec_mpos, rec_smer;
+    sg::DevBuf key, occ, m_pos, s_mer;          // read order, one entry per syncmer
+    // download staging
+    sg::DevBuf pk_hs, pk_rl, pk_hs_off, pk_rl_off;
+    std::vector<uint32_t> h_hoco_l, h_n_scm;
+    std::vector<uint64_t> h_hs_off, h_rl_off, h_scm_off;
+    // a5/a6 device results
+    sg::DevBuf kid;                              // read order: id << 1
+    sg::DevBuf skey, sval, skey_alt, sval_alt, sort_tmp;
+    sg::DevBuf socc, ssmer, flags, ids, ids_tmp;
+    sg::DevBuf scm_h, scm_s, scm_cov, scm_occ_off, status;
+    uint64_t n_unique = 0, n_collisions = 0;
+    // a7
+    sg::DevBuf arc_keys, arc_vals, arc_out;
+    uint64_t n_arcs = 0;
+};
+
+namespace sg {
+int launch_pack(sg_batch *b, cudaStream_t st);
+}

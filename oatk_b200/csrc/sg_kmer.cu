@@ -1,0 +1,62 @@
+// sg_kmer.cu -- kernel 1c: MurmurHash64A of every selected k-mer, and placement of
+// the syncmer records into read order.
+//
+// Replaces kmer_hash64 + MurmurHash64A (reference syncmer.c:175-226, 131-170):
+// the k bases starting at hoco position `start` are taken in read orientation
+// (rev = 0) or reverse-complemented (rev = 1), packed 4 per byte first base on
+// top, the unused low bits of the last byte are zero, and ceil(k/4) bytes are
+// hashed with seed 1234 as little-endian 8-byte blocks plus a <= 7-byte tail.
+//
+// Here one thread hashes one k-mer straight from the packed read: 32 bases at a
+// time are pulled out of the big-endian word stream with a funnel shift (the
+// reverse strand through a 2-bit-group reversal of the mirrored window), byte
+// swapped into the little-endian block Murmur expects, and mixed. The hash
+// chain is serial by construction (xor and multiply do not commute), so the
+// parallelism is across k-mers.
+#include "sg_common.cuh"
+#include "sg_internal.h"
+
+namespace sg {
+
+__device__ __forceinline__ uint64_t kmer_murmur(const uint32_t *hs, int64_t nwords, int64_t start, int k, int rev)
+{
+    const uint64_t M = 0xc6a4a7935bd1e995ull;
+    const uint32_t nbytes = (uint32_t) (k + 3) >> 2, nblk = nbytes >> 3;
+    uint64_t h = 1234ull ^ ((uint64_t) nbytes * M);
+    for (uint32_t j = 0; j < nblk; ++j) {
+        uint64_t w = bswap64(oriented_block(hs, nwords, start, k, rev, (int) j));
+        w *= M; w ^= w >> 47; w *= M;
+        h = (h ^ w) * M;
+    }
+    if (nbytes & 7u) {
+        const uint64_t w = bswap64(oriented_block(hs, nwords, start, k, rev, (int) nblk));
+        h = (h ^ w) * M;
+    }
+    h ^= h >> 47; h *= M; h ^= h >> 47;
+    return h;
+}
+
+__global__ void __launch_bounds__(256) kmerhash_kernel(KmerArgs A)
+{
+    const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= A.n_rec) return;
+    const uint32_t sid = A.rec_sid[i], idx = A.rec_idx[i], mp = A.rec_mpos[i];
+    const uint64_t hb = A.hoff[sid];
+    const uint32_t *hs32 = reinterpret_cast<const uint32_t *>(A.hoco_s + hb / 4);
+    const int64_t nwords = ((int64_t) A.hoco_l[sid] + 15) >> 4;
+    const uint64_t h = kmer_murmur(hs32, nwords, mp >> 1, A.k, mp & 1u);
+    const uint64_t o = A.scm_off[sid] + idx;
+    A.key[o] = h;
+    A.occ[o] = (A.sid_base + sid) << 32 | (uint64_t) idx << 1 | (mp & 1u);
+    A.m_pos[o] = mp;
+    A.s_mer[o] = A.rec_smer[i];
+}
+
+int launch_kmerhash(const KmerArgs &A, cudaStream_t st)
+{
+    if (A.n_rec == 0) return 0;
+    kmerhash_kernel<<<(unsigned) ((A.n_rec + 255) / 256), 256, 0, st>>>(A);
+    return 1;
+}
+
+} // namespace sg

@@ -1,0 +1,81 @@
+"""a2-a4 on the GPU (sg_extract through the C ABI) against the CPU oracle, bit for bit."""
+import numpy as np
+import pytest
+from oatk_b200 import synth
+from pyoracle import pack_reads
+import parity
+
+pytestmark = pytest.mark.gpu
+
+KS = [(1001, 31), (501, 31), (2001, 31), (101, 11), (301, 15), (64, 31), (33, 31), (40, 1), (12, 11), (5, 3)]
+
+
+def run_gpu(gpu_ctx, bases, off, k, s):
+    from oatk_b200 import lib
+    b = lib.Batch(gpu_ctx)
+    b.set_reads_host(bases, off)
+    b.extract(k, s)
+    f = b.extract_download()
+    b.close()
+    return f
+
+
+def check(gpu_ctx, oracle, reads, k, s):
+    bases, off = pack_reads(reads)
+    db, exp = oracle.extract(bases, off, k, s)
+    oracle.free(db)
+    got = run_gpu(gpu_ctx, bases, off, k, s)
+    d = parity.diff(got, exp, parity.EXTRACT_FIELDS)
+    if d:
+        d += parity.per_read_report(got, exp)
+    assert not d, "\n".join(d)
+    return got
+
+
+@pytest.mark.parametrize("k,s", KS)
+def test_adversarial(gpu_ctx, oracle, k, s):
+    check(gpu_ctx, oracle, synth.adversarial_reads(3, k, s), k, s)
+
+
+@pytest.mark.parametrize("k,s", [(1001, 31), (501, 31), (2001, 31)])
+def test_hifi_small(gpu_ctx, oracle, k, s):
+    reads = synth.hifi_reads(42, 500000, 300, 15000, 0.001)
+    got = check(gpu_ctx, oracle, reads, k, s)
+    if (k, s) == (1001, 31):
+        # first read of reads10k.fa as extracted by the reference
+        assert got["hoco_l"][0] == 11296 and got["n_scm"][0] == 21
+        assert (int(got["m_pos"][0]), int(got["s_mer"][0]), int(got["k_mer"][0])) == \
+            (447, 1089221421968769627, 12466468101431059233)
+
+
+def test_empty_batch(gpu_ctx):
+    from oatk_b200 import lib
+    b = lib.Batch(gpu_ctx)
+    b.set_reads_host(np.zeros(1, np.uint8), np.zeros(1, np.uint64))
+    b.extract(1001, 31)
+    z = b.extract_sizes()
+    assert z.n_reads == 0 and z.n_syncmers == 0
+
+
+def test_bad_params(gpu_ctx):
+    from oatk_b200 import lib
+    b = lib.Batch(gpu_ctx)
+    b.set_reads_host(np.frombuffer(b"ACGT", np.uint8), np.array([0, 4], np.uint64))
+    for k, s in ((31, 31), (10, 32), (10, 0), (5, 9)):
+        with pytest.raises(lib.SgError):
+            b.extract(k, s)
+
+
+def test_long_read(gpu_ctx, oracle):
+    """one read much longer than a tile: exercises the ring buffer wrap and the tile carries"""
+    rng = np.random.default_rng(11)
+    reads = [synth._rand(rng, 300000), synth._rand(rng, 70000).replace(b"AC", b"AAAAC")]
+    check(gpu_ctx, oracle, reads, 1001, 31)
+    check(gpu_ctx, oracle, reads, 2001, 31)
+
+
+def test_unaligned_offsets(gpu_ctx, oracle):
+    """reads whose raw offsets are not 16-byte aligned, of every length mod 16"""
+    rng = np.random.default_rng(5)
+    reads = [synth._rand(rng, 1200 + i) for i in range(40)]
+    check(gpu_ctx, oracle, reads, 301, 15)
