@@ -75,7 +75,7 @@ int sg_batch_set_reads_device(sg_batch *b, const void *d_bases, const uint64_t *
 int sg_batch_set_sid_base(sg_batch *b, uint64_t sid_base);
 
 /* a2-a4: homopolymer compression, 2-bit packing, closed-syncmer selection and
- * MurmurHash64A of every selected k-mer. Asynchronous on the context stream. */
+ * MurmurHash64A of every selected k-mer. Synchronises once (the syncmer count sizes what follows). */
 int sg_extract(sg_batch *b, int k, int s);
 
 typedef struct {
@@ -154,6 +154,10 @@ int sg_count_download(sg_batch *b, const sg_count_out_t *out);
  * = v, w, cov, comp. Vertex ids are syncmer ids (before asmg_cleanup renumbers). */
 int sg_arcs(sg_batch *b, uint32_t min_k_cov, double min_a_cov_f, uint64_t *n_arcs);  /* synchronises */
 int sg_arcs_download(sg_batch *b, uint64_t *arcs4);
+
+/* test hook: keep only the low `bits` bits of every k-mer hash when grouping, which forces hash
+ * collisions so that the exact-sequence split of process_kmer_cluster is exercised. 64 = off. */
+int sg_debug_set_hash_bits(sg_batch *b, int bits);
 
 /* ---- multi-GPU exchange (one process per GPU; the transport is the caller's
  * collective, e.g. NCCL all-to-all; see oatk_b200/dist.py) ---- */

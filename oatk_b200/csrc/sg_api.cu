@@ -133,7 +133,7 @@ void sg_batch_destroy(sg_batch *b)
 
 static void reset_state(sg_batch *b)
 {
-    b->extracted = b->counted = b->sizes_known = false;
+    b->extracted = b->counted = b->sizes_known = b->sorted = false;
     b->k = b->s = 0;
     b->n_syncmers = 0;
 }

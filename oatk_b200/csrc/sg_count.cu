@@ -1,0 +1,449 @@
+// sg_count.cu -- kernel group 2: the syncmer database (a6) and the counting part of
+// sr_db_stat (a5).
+//
+// Reference: collect_syncmer_from_reads + process_kmer_cluster (syncmer.c:1397-1451,
+// 1270-1393) sorts 128-bit tuples hash<<64 | sid<<32 | idx<<1 | rev, forms one
+// cluster per hash, splits a cluster by exact sequence comparison when it holds
+// more than one tuple, and numbers the resulting classes 0..U-1 in that order.
+// sr_db_stat (syncmer.c:867-987) sorts all syncmers twice to tabulate how many
+// distinct s-mer codes / k-mer keys occur once, twice, ...
+//
+// Here: the tuples exist in (sid, idx) order, so one stable radix sort by hash
+// gives the reference's order. Every tuple is then compared, 2-bit-packed word by
+// word, with its predecessor of equal hash (a warp walks 31 tuples plus one of
+// overlap and hands each lane its neighbour's words by shuffle, so every k-mer is
+// unpacked once). Equal neighbours everywhere means one class per hash; a hash
+// group with an unequal pair is re-classified serially like the reference does.
+// Ids are a prefix sum over class heads.
+#include "sg_common.cuh"
+#include "sg_internal.h"
+#include "sg_host.h"
+
+namespace sg {
+
+__global__ void __launch_bounds__(256) tuple_init_kernel(const uint64_t *key, uint64_t *skey, uint64_t *sval, uint64_t n, uint64_t hmask)
+{
+    const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { skey[i] = key[i] & hmask; sval[i] = i; }
+}
+
+__global__ void __launch_bounds__(256) tuple_gather_kernel(const uint64_t *sval, const uint64_t *occ, const uint64_t *smer,
+        uint64_t *socc, uint64_t *ssmer, uint64_t n)
+{
+    const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { const uint64_t o = sval[i]; socc[i] = occ[o]; ssmer[i] = smer[o]; }
+}
+
+struct VerifyArgs {
+    const uint64_t *skey, *sval, *socc;
+    const uint32_t *m_pos;
+    const uint64_t *hoff;
+    const uint8_t *hoco_s;
+    const uint32_t *hoco_l;
+    uint64_t sid_base, n;
+    int k;
+    uint32_t *newid;               // 1 for the first tuple of a hash group
+    uint8_t *differs;              // 1 when the tuple's k-mer differs from its predecessor of equal hash
+    unsigned long long *status;    // [1] += number of differing neighbours
+};
+
+__global__ void __launch_bounds__(256) verify_kernel(VerifyArgs A)
+{
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp = ((uint64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t e = (int64_t) (warp * 31) + lane - 1;        // lane 0 repeats the previous warp's last tuple
+    const bool ok = e >= 0 && (uint64_t) e < A.n;
+    uint64_t key = 0;
+    const uint32_t *hs = nullptr;
+    int64_t nwords = 0, start = 0;
+    int rev = 0;
+    if (ok) {
+        key = A.skey[e];
+        const uint64_t oc = A.socc[e];
+        const uint64_t sid = (oc >> 32) - A.sid_base;
+        hs = reinterpret_cast<const uint32_t *>(A.hoco_s + A.hoff[sid] / 4);
+        nwords = ((int64_t) A.hoco_l[sid] + 15) >> 4;
+        start = A.m_pos[A.sval[e]] >> 1;
+        rev = (int) (oc & 1ull);
+    }
+    const uint64_t pkey = __shfl_up_sync(SG_FULL, key, 1);
+    const bool pok = __shfl_up_sync(SG_FULL, (int) ok, 1) != 0;
+    const bool same = ok && lane > 0 && pok && pkey == key;
+    const int nblk = (A.k + 31) >> 5;
+    bool neq = false;
+    for (int j = 0; j < nblk; ++j) {
+        const uint64_t mine = ok ? oriented_block(hs, nwords, start, A.k, rev, j) : 0ull;
+        const uint64_t prev = __shfl_up_sync(SG_FULL, mine, 1);
+        neq |= same && mine != prev;
+    }
+    if (ok && lane > 0) {
+        A.newid[e] = same ? 0u : 1u;
+        A.differs[e] = neq ? 1 : 0;
+        if (neq) atomicAdd(A.status + 1, 1ull);
+    }
+}
+
+// serial re-classification of the (practically non-existent) hash groups that hold
+// more than one distinct k-mer; classes are numbered by first appearance and laid
+// out one after another, each in tuple order (syncmer.c:1283-1333, 1342-1379)
+struct SplitArgs {
+    uint64_t *skey, *sval, *socc, *ssmer;
+    uint64_t *t_val, *t_occ, *t_smer;     // scratch of the same size
+    uint32_t *cls;                        // scratch, one per tuple
+    const uint32_t *m_pos;
+    const uint64_t *hoff;
+    const uint8_t *hoco_s;
+    const uint32_t *hoco_l;
+    uint64_t sid_base, n;
+    int k;
+    uint32_t *newid;
+    const uint8_t *differs;
+    unsigned long long *status;           // [2] += groups split
+};
+
+__device__ bool same_kmer(const SplitArgs &A, uint64_t a, uint64_t b)
+{
+    const uint64_t oa = A.socc[a], ob = A.socc[b];
+    const uint64_t sa = (oa >> 32) - A.sid_base, sb = (ob >> 32) - A.sid_base;
+    const uint32_t *ha = reinterpret_cast<const uint32_t *>(A.hoco_s + A.hoff[sa] / 4);
+    const uint32_t *hb = reinterpret_cast<const uint32_t *>(A.hoco_s + A.hoff[sb] / 4);
+    const int64_t na = ((int64_t) A.hoco_l[sa] + 15) >> 4, nb = ((int64_t) A.hoco_l[sb] + 15) >> 4;
+    const int64_t pa = A.m_pos[A.sval[a]] >> 1, pb = A.m_pos[A.sval[b]] >> 1;
+    const int nblk = (A.k + 31) >> 5;
+    for (int j = 0; j < nblk; ++j)
+        if (oriented_block(ha, na, pa, A.k, (int) (oa & 1), j) != oriented_block(hb, nb, pb, A.k, (int) (ob & 1), j)) return false;
+    return true;
+}
+
+__global__ void __launch_bounds__(128) split_kernel(SplitArgs A)
+{
+    const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= A.n || (i > 0 && A.skey[i] == A.skey[i - 1])) return;      // hash-group heads only (skey is never rewritten)
+    uint64_t j = i + 1;
+    bool any = false;
+    while (j < A.n && A.skey[j] == A.skey[i]) { any |= A.differs[j] != 0; ++j; }
+    if (!any) return;
+    atomicAdd(A.status + 2, 1ull);
+    // 1. classes by first appearance; t_val[i + c] remembers the tuple that represents class c
+    uint32_t ncls = 0;
+    for (uint64_t x = i; x < j; ++x) {
+        uint32_t c = 0;
+        for (; c < ncls; ++c) if (same_kmer(A, x, A.t_val[i + c])) break;
+        if (c == ncls) A.t_val[i + ncls++] = x;
+        A.cls[x] = c;
+    }
+    // 2. stable partition by class into the scratch arrays (the representatives are no longer needed);
+    //    bit 63 of the permuted sval marks the first tuple of a class
+    uint64_t w = i;
+    for (uint32_t c = 0; c < ncls; ++c) {
+        bool first = true;
+        for (uint64_t x = i; x < j; ++x) {
+            if (A.cls[x] != c) continue;
+            A.t_occ[w] = A.socc[x];
+            A.t_smer[w] = A.ssmer[x];
+            A.t_val[w] = A.sval[x] | (first ? 1ull << 63 : 0ull);
+            first = false;
+            ++w;
+        }
+    }
+    // 3. copy back
+    for (uint64_t x = i; x < j; ++x) {
+        const uint64_t v = A.t_val[x];
+        A.sval[x] = v & ~(1ull << 63);
+        A.newid[x] = (uint32_t) (v >> 63);
+        A.socc[x] = A.t_occ[x];
+        A.ssmer[x] = A.t_smer[x];
+    }
+}
+
+struct FillArgs {
+    const uint64_t *skey, *sval, *socc, *ssmer;
+    const uint32_t *newid;
+    const uint64_t *ex;                  // exclusive scan of newid (n + 1)
+    uint64_t n;
+    uint64_t *kid;                       // read order: id << 1
+    uint64_t *scm_h, *scm_s, *occ_off;
+    unsigned long long *status;          // [0] |= s-mer conflict
+};
+
+__global__ void __launch_bounds__(256) fill_kernel(FillArgs A)
+{
+    const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= A.n) return;
+    const uint32_t head = A.newid[i];
+    const uint64_t id = A.ex[i] + head - 1;
+    A.kid[A.sval[i]] = id << 1;                                  // syncmer.c:1378
+    if (head) { A.scm_h[id] = A.skey[i]; A.scm_s[id] = A.ssmer[i]; A.occ_off[id] = i; }
+    else if (A.ssmer[i] != A.ssmer[i - 1]) atomicOr(A.status, 1ull);   // syncmer.c:1370-1376
+    if (i == A.n - 1) A.occ_off[id + 1] = A.n;
+}
+
+__global__ void __launch_bounds__(256) cov_kernel(const uint64_t *occ_off, uint32_t *cov, uint64_t u)
+{
+    const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < u) cov[i] = (uint32_t) (occ_off[i + 1] - occ_off[i]);
+}
+
+// ---- a5 ----
+__global__ void __launch_bounds__(256) run_heads_kernel(const uint64_t *k, uint64_t n, int shift, uint32_t *head)
+{
+    const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) head[i] = (i == 0 || (k[i] >> shift) != (k[i - 1] >> shift)) ? 1u : 0u;
+}
+
+// one thread per run head: length = distance to the next head, found through the scan
+__global__ void __launch_bounds__(256) run_starts_kernel(const uint32_t *head, const uint64_t *ex, uint64_t n, uint64_t *starts)
+{
+    const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (head[i]) starts[ex[i]] = i;
+    if (i == n - 1) starts[ex[n]] = n;
+}
+
+__global__ void __launch_bounds__(256) run_hist_kernel(const uint64_t *starts, uint64_t g, unsigned long long *hist /* 1001 */)
+{
+    __shared__ uint32_t h[1001];
+    for (int i = threadIdx.x; i < 1001; i += blockDim.x) h[i] = 0;
+    __syncthreads();
+    for (uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < g; i += (uint64_t) gridDim.x * blockDim.x) {
+        const uint64_t len = starts[i + 1] - starts[i];
+        atomicAdd(&h[len < 1000 ? len : 1000], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 1001; i += blockDim.x) if (h[i]) atomicAdd(hist + i, (unsigned long long) h[i]);
+}
+
+__global__ void __launch_bounds__(256) gap_kernel(const uint64_t *occ, const uint32_t *m_pos, uint64_t n, int k, unsigned long long *out /* [0]=sum (two's complement), [1]=count */)
+{
+    __shared__ long long ssum[8];
+    __shared__ unsigned long long scnt[8];
+    long long s = 0; unsigned long long c = 0;
+    for (uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t) gridDim.x * blockDim.x) {
+        const uint32_t idx = (uint32_t) (occ[i] >> 1) & 0x7FFFFFFFu;
+        if (idx == 0) continue;
+        const uint32_t p1 = m_pos[i] >> 1, p0 = m_pos[i - 1] >> 1;
+        if (p0 == 0x7FFFFFFFu || p1 == 0x7FFFFFFFu) continue;          // error-corrected entries, syncmer.c:900
+        s += (long long) p1 - (long long) p0 - k; ++c;
+    }
+    for (int d = 16; d; d >>= 1) { s += __shfl_down_sync(SG_FULL, s, d); c += __shfl_down_sync(SG_FULL, c, d); }
+    if ((threadIdx.x & 31) == 0) { ssum[threadIdx.x >> 5] = s; scnt[threadIdx.x >> 5] = c; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) { s += ssum[w]; c += scnt[w]; }
+        atomicAdd(out, (unsigned long long) s);
+        atomicAdd(out + 1, c);
+    }
+}
+
+} // namespace sg
+
+using namespace sg;
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+    ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_); return SG_E_CUDA; } } while (0)
+#define RS(buf, bytes) do { if ((buf).reserve(bytes)) { ctx->err = "device allocation of " + std::to_string((size_t)(bytes)) + " bytes failed"; return SG_E_NOMEM; } } while (0)
+#define LAUNCHED(stage, expr) do { int n_ = (expr); if (n_ < 0) return n_; ctx->count_launch(stage, n_); } while (0)
+static inline unsigned nblk(uint64_t n, unsigned t) { return (unsigned) ((n + t - 1) / t); }
+
+// sort the tuples of the batch by hash (cached until the next extract/adopt)
+static int ensure_sorted(sg_batch *b)
+{
+    sg_ctx *ctx = b->ctx;
+    if (b->sorted) return SG_OK;
+    cudaStream_t st = ctx->stream;
+    const uint64_t N = b->n_syncmers;
+    RS(b->skey, (N + 1) * 8); RS(b->sval, (N + 1) * 8); RS(b->skey_alt, (N + 1) * 8); RS(b->sval_alt, (N + 1) * 8);
+    RS(b->sort_tmp, sort_tmp_words(N) * 4);
+    RS(b->socc, (N + 1) * 8); RS(b->ssmer, (N + 1) * 8);
+    ctx->t_begin(SG_T_SORT);
+    const uint64_t hmask = b->hash_bits >= 64 ? ~0ull : ((1ull << b->hash_bits) - 1);
+    tuple_init_kernel<<<nblk(N, 256), 256, 0, st>>>((const uint64_t *) b->key.p, (uint64_t *) b->skey.p, (uint64_t *) b->sval.p, N, hmask);
+    ctx->count_launch(SG_T_SORT, 1);
+    LAUNCHED(SG_T_SORT, launch_sort_pairs((uint64_t *) b->skey.p, (uint64_t *) b->sval.p, (uint64_t *) b->skey_alt.p,
+            (uint64_t *) b->sval_alt.p, N, 0, b->hash_bits >= 64 ? 64 : ((b->hash_bits + 7) & ~7), (uint32_t *) b->sort_tmp.p, st));
+    tuple_gather_kernel<<<nblk(N, 256), 256, 0, st>>>((const uint64_t *) b->sval.p, (const uint64_t *) b->occ.p,
+            (const uint64_t *) b->s_mer.p, (uint64_t *) b->socc.p, (uint64_t *) b->ssmer.p, N);
+    ctx->count_launch(SG_T_SORT, 1);
+    ctx->t_end(SG_T_SORT);
+    CK(cudaGetLastError());
+    b->sorted = true;
+    return SG_OK;
+}
+
+// multiplicity-of-multiplicity table of a sorted key array (keys compared after >> shift)
+static int mult_table(sg_batch *b, const uint64_t *sorted, uint64_t N, int shift, unsigned long long *d_hist, uint64_t *groups)
+{
+    sg_ctx *ctx = b->ctx;
+    cudaStream_t st = ctx->stream;
+    RS(b->flags, (N + 1) * 4); RS(b->ids, (N + 2) * 8); RS(b->ids_tmp, scan_tmp_words(N) * 8);
+    RS(b->starts, (N + 2) * 8);
+    run_heads_kernel<<<nblk(N, 256), 256, 0, st>>>(sorted, N, shift, (uint32_t *) b->flags.p);
+    ctx->count_launch(SG_T_STAT, 1);
+    LAUNCHED(SG_T_STAT, launch_scan_u32_u64((const uint32_t *) b->flags.p, (uint64_t *) b->ids.p, N, (uint64_t *) b->ids_tmp.p, st));
+    uint64_t G = 0;
+    CK(cudaMemcpyAsync(&G, (uint64_t *) b->ids.p + N, 8, cudaMemcpyDeviceToHost, st));
+    run_starts_kernel<<<nblk(N, 256), 256, 0, st>>>((const uint32_t *) b->flags.p, (const uint64_t *) b->ids.p, N, (uint64_t *) b->starts.p);
+    CK(cudaStreamSynchronize(st));
+    run_hist_kernel<<<std::min<unsigned>(nblk(G, 256), 1184u), 256, 0, st>>>((const uint64_t *) b->starts.p, G, d_hist);
+    ctx->count_launch(SG_T_STAT, 2);
+    *groups = G;
+    return SG_OK;
+}
+
+extern "C" {
+
+int sg_debug_set_hash_bits(sg_batch *b, int bits)
+{
+    if (!b || bits < 1 || bits > 64) return SG_E_ARG;
+    b->hash_bits = bits;
+    b->sorted = b->counted = false;
+    return SG_OK;
+}
+
+int sg_stat(sg_batch *b, sg_stat_t *out)
+{
+    if (!b || !out) return SG_E_ARG;
+    if (!b->extracted) return SG_E_STATE;
+    sg_ctx *ctx = b->ctx;
+    cudaStream_t st = ctx->stream;
+    CK(cudaSetDevice(ctx->device));
+    memset(out, 0, sizeof(*out));
+    const uint64_t N = b->n_syncmers;
+    out->n_syncmers = N;
+    if (N == 0) return SG_E_EMPTY;                                  // "empty syncmer collection", syncmer.c:909-912
+    int rc = ensure_sorted(b);
+    if (rc) return rc;
+    ctx->t_begin(SG_T_STAT);
+    RS(b->stat_dev, (2 * 1001 + 4) * 8);
+    unsigned long long *d = (unsigned long long *) b->stat_dev.p;
+    CK(cudaMemsetAsync(d, 0, (2 * 1001 + 4) * 8, st));
+    // k-mer keys: hash with its low bit dropped (syncmer.c:896); the hash-sorted order keeps equal keys adjacent
+    uint64_t gk = 0, gs = 0;
+    rc = mult_table(b, (const uint64_t *) b->skey.p, N, 1, d + 1001, &gk);
+    if (rc) return rc;
+    // s-mer codes: a second sort, values unused
+    RS(b->skey2, (N + 1) * 8); RS(b->sval2, (N + 1) * 8);
+    CK(cudaMemcpyAsync(b->skey2.p, b->s_mer.p, N * 8, cudaMemcpyDeviceToDevice, st));
+    LAUNCHED(SG_T_STAT, launch_sort_pairs((uint64_t *) b->skey2.p, (uint64_t *) b->sval2.p, (uint64_t *) b->skey_alt.p,
+            (uint64_t *) b->sval_alt.p, N, 0, 64, (uint32_t *) b->sort_tmp.p, st));
+    rc = mult_table(b, (const uint64_t *) b->skey2.p, N, 0, d, &gs);
+    if (rc) return rc;
+    gap_kernel<<<std::min<unsigned>(nblk(N, 256), 1184u), 256, 0, st>>>((const uint64_t *) b->occ.p, (const uint32_t *) b->m_pos.p, N, b->k, d + 2002);
+    ctx->count_launch(SG_T_STAT, 1);
+    ctx->t_end(SG_T_STAT);
+    std::vector<unsigned long long> h(2 * 1001 + 4);
+    CK(cudaMemcpyAsync(h.data(), d, h.size() * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    for (int i = 0; i < 1001; ++i) { out->smer_cnts[i] = (int64_t) h[i]; out->kmer_cnts[i] = (int64_t) h[1001 + i]; }
+    out->gap_sum = (int64_t) h[2002];
+    out->n_gaps = h[2003];
+    out->smer_unique = gs; out->smer_singleton = h[1];
+    out->kmer_unique = gk; out->kmer_singleton = h[1001 + 1];
+    return SG_OK;
+}
+
+int sg_count(sg_batch *b)
+{
+    if (!b) return SG_E_ARG;
+    if (!b->extracted) return SG_E_STATE;
+    sg_ctx *ctx = b->ctx;
+    cudaStream_t st = ctx->stream;
+    CK(cudaSetDevice(ctx->device));
+    const uint64_t N = b->n_syncmers;
+    if (N == 0) return SG_E_EMPTY;                                  // reference returns NULL, syncmer.c:1414-1417
+    int rc = ensure_sorted(b);
+    if (rc) return rc;
+    ctx->t_begin(SG_T_GROUP);
+    RS(b->flags, (N + 1) * 4); RS(b->differs, N + 1); RS(b->ids, (N + 2) * 8); RS(b->ids_tmp, scan_tmp_words(N) * 8);
+    RS(b->status, 4 * 8); RS(b->kid, (N + 1) * 8);
+    unsigned long long *status = (unsigned long long *) b->status.p;
+    CK(cudaMemsetAsync(status, 0, 4 * 8, st));
+    CK(cudaMemsetAsync(b->differs.p, 0, N + 1, st));
+    {
+        // element 0 is always a head; the kernel writes flags for lanes >= 1 only
+        uint32_t one = 1;
+        CK(cudaMemcpyAsync(b->flags.p, &one, 4, cudaMemcpyHostToDevice, st));
+    }
+    VerifyArgs V;
+    V.skey = (const uint64_t *) b->skey.p; V.sval = (const uint64_t *) b->sval.p; V.socc = (const uint64_t *) b->socc.p;
+    V.m_pos = (const uint32_t *) b->m_pos.p; V.hoff = (const uint64_t *) b->hoff.p; V.hoco_s = (const uint8_t *) b->hoco_s.p;
+    V.hoco_l = (const uint32_t *) b->hoco_l.p; V.sid_base = b->sid_base; V.n = N; V.k = b->k;
+    V.newid = (uint32_t *) b->flags.p; V.differs = (uint8_t *) b->differs.p; V.status = status;
+    {
+        const uint64_t warps = (N + 30) / 31 + 1;
+        verify_kernel<<<nblk(warps * 32, 256), 256, 0, st>>>(V);
+        ctx->count_launch(SG_T_GROUP, 1);
+    }
+    unsigned long long hs[4];
+    CK(cudaMemcpyAsync(hs, status, sizeof(hs), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    b->n_collisions = 0;
+    if (hs[1]) {
+        // some hash group holds more than one k-mer: rebuild those groups the way process_kmer_cluster does
+        RS(b->cls, (N + 1) * 4);
+        SplitArgs S;
+        S.skey = (uint64_t *) b->skey.p; S.sval = (uint64_t *) b->sval.p; S.socc = (uint64_t *) b->socc.p; S.ssmer = (uint64_t *) b->ssmer.p;
+        S.t_val = (uint64_t *) b->sval_alt.p; S.t_occ = (uint64_t *) b->skey_alt.p; S.t_smer = (uint64_t *) b->ids.p;
+        S.cls = (uint32_t *) b->cls.p; S.m_pos = V.m_pos; S.hoff = V.hoff; S.hoco_s = V.hoco_s; S.hoco_l = V.hoco_l;
+        S.sid_base = b->sid_base; S.n = N; S.k = b->k; S.newid = (uint32_t *) b->flags.p; S.differs = (const uint8_t *) b->differs.p;
+        S.status = status;
+        split_kernel<<<nblk(N, 128), 128, 0, st>>>(S);
+        ctx->count_launch(SG_T_GROUP, 1);
+        CK(cudaMemcpyAsync(hs, status, sizeof(hs), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        b->n_collisions = hs[2];
+    }
+    LAUNCHED(SG_T_GROUP, launch_scan_u32_u64((const uint32_t *) b->flags.p, (uint64_t *) b->ids.p, N, (uint64_t *) b->ids_tmp.p, st));
+    uint64_t U = 0;
+    CK(cudaMemcpyAsync(&U, (uint64_t *) b->ids.p + N, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    b->n_unique = U;
+    RS(b->scm_h, (U + 1) * 8); RS(b->scm_s, (U + 1) * 8); RS(b->scm_cov, (U + 1) * 4); RS(b->scm_occ_off, (U + 2) * 8);
+    FillArgs F;
+    F.skey = (const uint64_t *) b->skey.p; F.sval = (const uint64_t *) b->sval.p; F.socc = (const uint64_t *) b->socc.p;
+    F.ssmer = (const uint64_t *) b->ssmer.p; F.newid = (const uint32_t *) b->flags.p; F.ex = (const uint64_t *) b->ids.p;
+    F.n = N; F.kid = (uint64_t *) b->kid.p; F.scm_h = (uint64_t *) b->scm_h.p; F.scm_s = (uint64_t *) b->scm_s.p;
+    F.occ_off = (uint64_t *) b->scm_occ_off.p; F.status = status;
+    fill_kernel<<<nblk(N, 256), 256, 0, st>>>(F);
+    cov_kernel<<<nblk(U, 256), 256, 0, st>>>((const uint64_t *) b->scm_occ_off.p, (uint32_t *) b->scm_cov.p, U);
+    ctx->count_launch(SG_T_GROUP, 2);
+    ctx->t_end(SG_T_GROUP);
+    CK(cudaMemcpyAsync(hs, status, sizeof(hs), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    b->counted = true;
+    if (hs[0]) { ctx->err = "identical kmers have different smers"; return SG_E_SMER_CONFLICT; }
+    return SG_OK;
+}
+
+int sg_count_sizes(sg_batch *b, sg_count_sizes_t *out)
+{
+    if (!b || !out) return SG_E_ARG;
+    if (!b->counted) return SG_E_STATE;
+    out->n_syncmers = b->n_syncmers;
+    out->n_unique = b->n_unique;
+    out->n_hash_collisions = b->n_collisions;
+    return SG_OK;
+}
+
+int sg_count_download(sg_batch *b, const sg_count_out_t *o)
+{
+    if (!b || !o) return SG_E_ARG;
+    if (!b->counted) return SG_E_STATE;
+    sg_ctx *ctx = b->ctx;
+    cudaStream_t st = ctx->stream;
+    CK(cudaSetDevice(ctx->device));
+    const uint64_t N = b->n_syncmers, U = b->n_unique;
+    if (o->h) CK(cudaMemcpyAsync(o->h, b->scm_h.p, U * 8, cudaMemcpyDeviceToHost, st));
+    if (o->s) CK(cudaMemcpyAsync(o->s, b->scm_s.p, U * 8, cudaMemcpyDeviceToHost, st));
+    if (o->cov) CK(cudaMemcpyAsync(o->cov, b->scm_cov.p, U * 4, cudaMemcpyDeviceToHost, st));
+    if (o->occ_off) CK(cudaMemcpyAsync(o->occ_off, b->scm_occ_off.p, (U + 1) * 8, cudaMemcpyDeviceToHost, st));
+    if (o->occ) CK(cudaMemcpyAsync(o->occ, b->socc.p, N * 8, cudaMemcpyDeviceToHost, st));
+    if (o->k_mer_id) CK(cudaMemcpyAsync(o->k_mer_id, b->kid.p, N * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    b->d2h_bytes += U * 28 + N * 16;
+    return SG_OK;
+}
+
+} // extern "C"

@@ -57,7 +57,9 @@ struct sg_batch {
     // a5/a6 device results
     sg::DevBuf kid;                              // read order: id << 1
     sg::DevBuf skey, sval, skey_alt, sval_alt, sort_tmp;
-    sg::DevBuf socc, ssmer, flags, ids, ids_tmp;
+    sg::DevBuf socc, ssmer, flags, ids, ids_tmp, differs, cls, starts, stat_dev, skey2, sval2;
+    bool sorted = false;
+    int hash_bits = 64;                          // < 64 only through sg_debug_set_hash_bits (tests)
     sg::DevBuf scm_h, scm_s, scm_cov, scm_occ_off, status;
     uint64_t n_unique = 0, n_collisions = 0;
     // a7

@@ -1,0 +1,100 @@
+"""a5/a6 on the GPU (sg_stat, sg_count through the C ABI) against the CPU oracle, bit for bit."""
+import numpy as np
+import pytest
+from oatk_b200 import synth
+from pyoracle import pack_reads
+import parity
+
+pytestmark = pytest.mark.gpu
+
+
+def gpu_batch(gpu_ctx, bases, off, k, s):
+    from oatk_b200 import lib
+    b = lib.Batch(gpu_ctx)
+    b.set_reads_host(bases, off)
+    b.extract(k, s)
+    return b
+
+
+def check_count(gpu_ctx, oracle, reads, k, s, hash_bits=64):
+    bases, off = pack_reads(reads)
+    db, _ = oracle.extract(bases, off, k, s)
+    exp = oracle.collect(db, len(reads), hash_bits)
+    b = gpu_batch(gpu_ctx, bases, off, k, s)
+    if hash_bits != 64:
+        b.debug_set_hash_bits(hash_bits)
+    b.count()
+    got = b.count_download()
+    d = parity.diff(got, exp, parity.SCM_FIELDS)
+    # k_mer[] as the host sees it after collect
+    f = b.extract_download(want_seq=False)
+    d += parity.diff({"k_mer_id": f["k_mer"]}, exp, ("k_mer_id",), tag="download:")
+    assert not d, "\n".join(d)
+    oracle.free(db, exp)
+    b.close()
+    return got
+
+
+@pytest.mark.parametrize("k,s", [(1001, 31), (501, 31), (101, 11), (64, 31), (33, 31)])
+def test_count_adversarial(gpu_ctx, oracle, k, s):
+    check_count(gpu_ctx, oracle, synth.adversarial_reads(3, k, s), k, s)
+
+
+def test_count_hifi(gpu_ctx, oracle):
+    reads = synth.hifi_reads(7, 200000, 400, 15000, 0.001)
+    got = check_count(gpu_ctx, oracle, reads, 1001, 31)
+    assert got["n_hash_collisions"] == 0
+    assert int(got["cov"].sum()) == len(got["occ"])
+
+
+@pytest.mark.parametrize("bits", [3, 8, 16])
+def test_forced_hash_collisions(gpu_ctx, oracle, bits):
+    """truncating the hash forces distinct k-mers into one hash group: the exact-sequence
+    split must number the classes like process_kmer_cluster (syncmer.c:1270-1393)"""
+    reads = synth.hifi_reads(9, 60000, 60, 8000, 0.002) + synth.adversarial_reads(4, 301, 15)[:20]
+    got = check_count(gpu_ctx, oracle, reads, 301, 15, hash_bits=bits)
+    assert got["n_hash_collisions"] > 0
+
+
+@pytest.mark.parametrize("k,s", [(1001, 31), (301, 15)])
+def test_stat(gpu_ctx, oracle, k, s):
+    reads = synth.hifi_reads(5, 100000, 300, 12000, 0.001) + synth.adversarial_reads(3, k, s)
+    bases, off = pack_reads(reads)
+    db, _ = oracle.extract(bases, off, k, s)
+    rc, d, i, sc, kc = oracle.stat(db)
+    assert rc == 0
+    b = gpu_batch(gpu_ctx, bases, off, k, s)
+    st = b.stat()
+    assert np.array_equal(np.array(st.smer_cnts[:], np.int64), sc)
+    assert np.array_equal(np.array(st.kmer_cnts[:], np.int64), kc)
+    assert (st.smer_unique, st.smer_singleton, st.kmer_unique, st.kmer_singleton) == (i[0], i[1], i[4], i[5])
+    assert st.gap_sum / st.n_gaps == d[1]
+    assert st.n_syncmers / len(reads) == d[0]
+    oracle.free(db)
+    b.close()
+
+
+def test_stat_then_count_order(gpu_ctx, oracle):
+    """the reference calls sr_db_stat before collect (run_syncasm.c:88-103); both orders must agree"""
+    reads = synth.hifi_reads(3, 50000, 100, 9000, 0.001)
+    bases, off = pack_reads(reads)
+    b = gpu_batch(gpu_ctx, bases, off, 501, 31)
+    s1 = b.stat()
+    b.count()
+    c1 = b.count_download()
+    b2 = gpu_batch(gpu_ctx, bases, off, 501, 31)
+    b2.count()
+    c2 = b2.count_download()
+    s2 = b2.stat()
+    assert not parity.diff(c1, c2, parity.SCM_FIELDS)
+    assert s1.kmer_cnts[:] == s2.kmer_cnts[:] and s1.smer_cnts[:] == s2.smer_cnts[:]
+
+
+def test_count_empty(gpu_ctx):
+    from oatk_b200 import lib
+    b = lib.Batch(gpu_ctx)
+    b.set_reads_host(np.frombuffer(b"ACGTACGT", np.uint8), np.array([0, 8], np.uint64))
+    b.extract(1001, 31)
+    with pytest.raises(lib.SgError) as e:
+        b.count()
+    assert e.value.code == -7
