@@ -1,0 +1,387 @@
+#!/usr/bin/env python
+"""bench.py -- HiFi bases/second through syncmer extract + count.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+A step is one pass of the hot path (sg_extract + sg_stat + sg_count = reference
+sr_read_analysis_thread + sr_db_stat + collect_syncmer_from_reads) over one batch of
+synthetic reads that is already resident in HBM: BASELINE.json configs[1], 1 M x 15 kb
+reads per GPU at k=1001 s=31. `value` is whole-job raw bases per second; `e2e` is the same
+pass through the C ABI with HOST buffers (pinned), host<->device copies inside the timed
+region. `--impl reference` times the unmodified reference (oracle/_ref/libref.so) on the
+host cores on a bounded sample of the same workload.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+K, S = 1001, 31
+READ_LEN = 15000
+ERR = 1e-3
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.path = tempfile.mktemp(prefix="clocks_", suffix=".csv")
+        self.f = open(self.path, "w")
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.FIELDS,
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is not None:
+            self.p.terminate()
+            try:
+                self.p.wait(timeout=5)
+            except Exception:
+                self.p.kill()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                c = [x.strip() for x in line.split(",")]
+                if len(c) < 9:
+                    continue
+                try:
+                    sm.append(float(c[1]))
+                    mx.append(float(c[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- reference arm
+def write_fasta(path, bases_u8, n_reads, read_len):
+    import numpy as np
+    hdr = np.frombuffer(b"".join(b">r%07d\n" % i for i in range(n_reads)), dtype=np.uint8).reshape(n_reads, 10)
+    rec = np.empty((n_reads, 10 + read_len + 1), dtype=np.uint8)
+    rec[:, :10] = hdr
+    rec[:, 10:10 + read_len] = bases_u8.reshape(n_reads, read_len)
+    rec[:, -1] = 10
+    rec.tofile(path)
+
+
+def host_sample_reads(n_reads, seed):
+    """the bench workload's generator on the CPU path: numpy, same error model (oatk_b200/synth.py)"""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    G = 50_000_000
+    genome = rng.integers(0, 4, G, dtype=np.uint8)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    out = np.empty((n_reads, READ_LEN), dtype=np.uint8)
+    start = rng.integers(0, G - READ_LEN - 64, n_reads)
+    for i in range(n_reads):
+        r = genome[start[i]:start[i] + READ_LEN].copy()
+        ne = rng.binomial(READ_LEN, ERR)
+        pos = rng.integers(0, READ_LEN, ne)
+        r[pos] = (r[pos] + rng.integers(1, 4, ne)) % 4       # substitutions only: keeps the length fixed
+        if rng.integers(0, 2):
+            r = (3 - r)[::-1]
+        out[i] = acgt[r]
+    return out.reshape(-1)
+
+
+def cpu_reference_run(bases_u8, n_reads, threads):
+    """times the unmodified reference (sr_read + sr_db_stat + collect) on a FASTA of the sample"""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pyoracle
+    if not pyoracle.have_ref():
+        pyoracle.build()
+    if not pyoracle.have_ref():
+        return None
+    R = pyoracle.Ref()
+    d = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
+    path = os.path.join(d, "bench_sample_%d.fa" % os.getpid())
+    write_fasta(path, bases_u8, n_reads, READ_LEN)
+    try:
+        t = R.time_extract_count(path, K, S, threads)
+    finally:
+        os.unlink(path)
+    tot = t["sr_read_s"] + t["sr_db_stat_s"] + t["collect_s"]
+    return {"seconds": tot, "stages": t, "bases": n_reads * READ_LEN}
+
+
+def run_reference(args):
+    rank = env_int("RANK", 0)
+    if rank != 0:
+        return 0
+    threads = os.cpu_count() or 1
+    n_reads = min(10000 * threads, 160000)
+    bases = host_sample_reads(n_reads, 1)
+    times = []
+    last = None
+    for i in range(args.warmup + args.steps):
+        r = cpu_reference_run(bases, n_reads, threads)
+        if r is None:
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libref.so missing and /root/reference absent"}))
+            return 0
+        if i >= args.warmup:
+            times.append(r["seconds"])
+        last = r
+    sec = sum(times) / len(times)
+    val = n_reads * READ_LEN / sec
+    sample = "%d x %d b reads (%.2f Gbases) per step, reference sr_read(kseq parse + extract, -t %d) + sr_db_stat + collect" % (
+        n_reads, READ_LEN, n_reads * READ_LEN / 1e9, threads)
+    line = {
+        "impl": "reference", "metric": "HiFi bases/sec syncmer-extract+count", "value": val, "unit": "bases/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": val, "unit": "bases/s", "cores": threads, "kind": "reference", "sample": sample,
+                         "stages_s": last["stages"]},
+        "e2e": {"value": val, "unit": "bases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(n_gpus, n_reads=None):
+    return {"workload": "syncmer extract+count, %s x %d b synthetic HiFi reads per GPU, k=%d s=%d (BASELINE.json configs[1])" % (
+                "1M" if n_reads in (None, 1000000) else str(n_reads), READ_LEN, K, S),
+            "k": K, "s": S, "read_len": READ_LEN, "error_rate": ERR, "genome_len": 50_000_000,
+            "reads_per_gpu": n_reads or 1000000, "parallelism": "reads sharded by record, %d GPU(s)" % n_gpus,
+            "l2": "inputs (15 GB per step) larger than L2; no flush needed"}
+
+
+# ----------------------------------------------------------------------------- our arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--reads", type=int, default=1000000, help="reads per GPU (default: the configs[1] workload)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    from oatk_b200 import lib, synth_gpu
+
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: libsyncgpu has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    W = max(args.warmup, 3)
+    n_reads = args.reads
+
+    bases, off = synth_gpu.hifi_reads_gpu(1 + rank, 50_000_000, n_reads, READ_LEN, ERR, dev)
+    total = n_reads * READ_LEN
+    torch.cuda.synchronize()
+
+    ctx = lib.Context(local)          # launches on the legacy default stream = torch's current stream
+    batch = lib.Batch(ctx)
+    batch.set_sid_base(rank * n_reads)
+    exchange = None
+    if world > 1:
+        from oatk_b200 import dist as sgdist
+        exchange = sgdist.TupleExchange(ctx, dist, rank, world)
+
+    def step():
+        batch.set_reads_device(bases.data_ptr(), off.data_ptr(), n_reads, total)
+        batch.extract(K, S)
+        if exchange is not None:
+            exchange.run(batch)
+        st = batch.stat()
+        batch.count()
+        return st
+
+    for _ in range(W):
+        step()
+    torch.cuda.synchronize()
+    sizes = batch.extract_sizes()
+    csz = batch.count_sizes()
+
+    # ---- device-resident timing ----
+    ctx.enable_timing(True)
+    ctx.timings()
+    stage_ms = {}
+    stage_launch = {}
+    sampler = ClockSampler(local) if rank == 0 else None
+    l0 = ctx.launches()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+        for name, (ms, ln) in ctx.timings().items():
+            stage_ms[name] = stage_ms.get(name, 0.0) + ms
+            stage_launch[name] = stage_launch.get(name, 0) + ln
+    e1.record()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    launches = ctx.launches() - l0
+    clocks = sampler.stop() if sampler else None
+    ms_step = e0.elapsed_time(e1) / args.steps
+    if dist is not None:
+        t = torch.tensor([ms_step], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_step = float(t.item())
+    ctx.enable_timing(False)
+    value = world * total / (ms_step * 1e-3)
+
+    # ---- end to end through the C ABI with host buffers ----
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(torch, lib, ctx, batch, bases, off, n_reads, total, sizes, csz, max(1, min(args.steps, 3)), dist, dev, world)
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
+    peak, peak_src = measured_peak()
+    # algorithmic bytes of the extract kernels: raw read + hoco_s + ho_rl written + 20 B per syncmer
+    ext_bytes = total + 1.25 * sizes.hoco_bases + 20.0 * sizes.n_syncmers
+    ext_ms = (stage_ms["encode"] + stage_ms["scan"] + stage_ms["kmerhash"]) / args.steps
+    achieved = ext_bytes / (ext_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "extract = encode_kernel + scan_kernel + kmerhash_kernel",
+                "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": ncu_traffic(), "algorithmic_bytes_per_launch": ext_bytes,
+                "bytes_per_raw_base": ext_bytes / total, "ms_per_launch": ext_ms,
+                "stage_ms": {k_: v / args.steps for k_, v in stage_ms.items()},
+                "stage_launches": {k_: v // args.steps for k_, v in stage_launch.items()},
+                "note": "integer-issue bound, not HBM bound: see DESIGN.md section 5"}
+
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        threads = os.cpu_count() or 1
+        ns = min(10000 * threads, 160000, n_reads)
+        sample = bases[:ns * READ_LEN].cpu().numpy()
+        r = cpu_reference_run(sample, ns, threads)
+        if r is not None:
+            cpu = {"value": r["bases"] / r["seconds"], "unit": "bases/s", "cores": threads, "kind": "reference",
+                   "sample": "first %d reads of the step's batch (%.2f Gbases), reference sr_read -t %d + sr_db_stat + collect, FASTA in /dev/shm" % (
+                       ns, ns * READ_LEN / 1e9, threads), "stages_s": r["stages"]}
+
+    line = {"metric": "HiFi bases/sec syncmer-extract+count", "value": value, "unit": "bases/s", "n_gpus": world,
+            "steps": args.steps, "warmup": W, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": workload_config(world, n_reads),
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+            "results": {"syncmers": int(sizes.n_syncmers), "distinct_kmers": int(csz.n_unique), "hoco_bases": int(sizes.hoco_bases)}}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+def ncu_traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu capture, if any"""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get("extract_dram_bytes_per_launch")
+        except Exception:
+            return None
+    return None
+
+
+def run_e2e(torch, lib, ctx, batch, bases, off, n_reads, total, sizes, csz, steps, dist, dev, world):
+    """host buffers in, host buffers out, through sg_batch_set_reads_host / sg_extract / sg_stat / sg_count / downloads"""
+    import numpy as np
+    pin = lambda n, dt: torch.empty(max(int(n), 1), dtype=dt, pin_memory=True)
+    h_bases = pin(total, torch.uint8)
+    h_bases.copy_(bases)
+    h_off = pin(n_reads + 1, torch.int64)
+    h_off.copy_(off)
+    N, U = sizes.n_syncmers, csz.n_unique
+    slack = 1.02
+    o = lib.ExtractOut()
+    bufs = {
+        "hoco_l": pin(n_reads, torch.int32), "n_scm": pin(n_reads, torch.int32),
+        "hoco_s_off": pin(n_reads + 1, torch.int64), "ho_rl_off": pin(n_reads + 1, torch.int64), "scm_off": pin(n_reads + 1, torch.int64),
+        "hoco_s_buf": pin(sizes.hoco_s_bytes * slack + 4096, torch.uint8), "ho_rl_buf": pin(sizes.ho_rl_bytes * slack + 4096, torch.uint8),
+        "m_pos": pin(N * slack, torch.int32), "s_mer": pin(N * slack, torch.int64), "k_mer": pin(N * slack, torch.int64),
+    }
+    for name, _ in lib.ExtractOut._fields_:
+        setattr(o, name, bufs[name].data_ptr() if name in bufs else None)
+    co = lib.CountOut()
+    cb = {"h": pin(U * slack, torch.int64), "s": pin(U * slack, torch.int64), "cov": pin(U * slack, torch.int32),
+          "occ_off": pin(U * slack + 1, torch.int64), "occ": pin(N * slack, torch.int64), "k_mer_id": None}
+    for name, _ in lib.CountOut._fields_:
+        setattr(co, name, cb[name].data_ptr() if cb.get(name) is not None else None)
+    L = lib.library()
+    torch.cuda.synchronize()
+
+    def one():
+        batch.set_reads_host_ptr(h_bases.data_ptr(), h_off.data_ptr(), n_reads)
+        batch.extract(K, S)
+        batch.stat()
+        batch.count()
+        lib._ck(ctx.h, L.sg_extract_download(batch.h, C.byref(o)), "sg_extract_download")
+        lib._ck(ctx.h, L.sg_count_download(batch.h, C.byref(co)), "sg_count_download")
+
+    one()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one()
+    torch.cuda.synchronize()
+    sec = (time.perf_counter() - t0) / steps
+    if dist is not None:
+        t = torch.tensor([sec], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        sec = float(t.item())
+    h2d = total + 8 * (n_reads + 1)
+    d2h = int(sizes.hoco_s_bytes + sizes.ho_rl_bytes + 20 * N + 8 * n_reads + 28 * U + 8 * N)
+    return {"value": world * total / sec, "unit": "bases/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": d2h,
+            "ms_per_step": sec * 1e3, "steps": steps,
+            "path": "sg_batch_set_reads_host -> sg_extract -> sg_stat -> sg_count -> sg_extract_download + sg_count_download, pinned host buffers"}
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,20 @@
+"""Builds liboatk_gpu.so: the C host layer that mirrors the reference's syncmer.h API over libsyncgpu."""
+import os
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def build(force=False):
+    srcs = [os.path.join(HERE, f) for f in sorted(os.listdir(HERE)) if f.endswith(".c")]
+    if not srcs:
+        return None
+    out = os.path.join(HERE, "liboatk_gpu.so")
+    deps = srcs + [os.path.join(HERE, f) for f in os.listdir(HERE) if f.endswith(".h")]
+    if not force and os.path.exists(out) and all(os.path.getmtime(d) <= os.path.getmtime(out) for d in deps):
+        return out
+    lib = os.path.join(HERE, "..")
+    subprocess.check_call(["gcc", "-O2", "-Wall", "-fPIC", "-shared", "-o", out] + srcs +
+                          ["-I" + os.path.join(HERE, "..", "..", "include"), "-L" + lib, "-lsyncgpu",
+                           "-Wl,-rpath,$ORIGIN/..", "-lm", "-lpthread", "-lz"])
+    return out
