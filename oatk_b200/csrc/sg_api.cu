@@ -246,7 +246,7 @@ int sg_extract(sg_batch *b, int k, int s)
     CK(cudaSetDevice(ctx->device));
     {
         ScanGeom g; size_t smem;
-        if (scan_geometry(k, s, 128, &g, &smem)) { ctx->err = "k - s + 1 exceeds the scan window"; return SG_E_KSIZE; }
+        if (scan_geometry(k, s, SYNC_SCAN_NT, &g, &smem)) { ctx->err = "k - s + 1 exceeds the scan window"; return SG_E_KSIZE; }
     }
     reset_state(b);
     b->k = k; b->s = s;

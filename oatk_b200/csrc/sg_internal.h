@@ -30,12 +30,12 @@ struct ScanArgs {
     uint32_t *rec_sid, *rec_idx, *rec_mpos;   // unordered records (one per syncmer)
     uint64_t *rec_smer;
 };
+constexpr int SYNC_SCAN_NT = 128;   // threads per CTA of the syncmer scan kernel (16 positions each)
 struct ScanGeom {
     int rch;        // ring size in chunks (power of two)
     int n_full;     // chunks fully inside every window of a thread's 16 positions
-    int J;          // top level of the sparse table (2^J <= n_full), -1 when n_full == 0
+    int T;          // top level of the radix-4 sparse table (4^T <= n_full)
 };
-
 int scan_geometry(int k, int s, int nt, ScanGeom *g, size_t *smem);
 // returns launches (>= 0) or a negative SG_E_* code
 int launch_scan(const ScanArgs &A, uint64_t n_reads, cudaStream_t st);

@@ -11,19 +11,20 @@
 //
 // One CTA per read walks it in tiles of NT*16 positions; thread t owns 16
 // consecutive positions (one 32-bit word of packed bases).
-//   1. roll both strands through the 16 bases, hash, store (hi, lo) words of m[]
-//      in a shared-memory ring that always holds the last q + tile positions
-//      (transposed [16][chunks] so that every access is bank-conflict free)
-//   2. sparse-table doubling over the per-chunk minima of the HIGH words gives
-//      every thread r0 = min over the chunks that lie fully inside the window of
-//      all its 16 positions
+//   1. roll both strands through the 16 bases and hash; only the HIGH 32 bits of
+//      each 62-bit hash are kept, in a shared-memory ring that holds the last
+//      q + tile positions, transposed [16][chunks] so every access is conflict free
+//   2. a radix-4 sparse table over the per-chunk minima gives every thread
+//      r0 = min over the chunks that lie fully inside the window of all its 16 positions
 //   3. a position is a candidate when its high word (or that of e(p)) is <= the
-//      running minimum of r0 and the thread's own earlier positions; about 2/q
-//      of all positions pass
-//   4. candidates are settled exactly: the < 32 window positions not covered by
-//      r0 are scanned on the high word; a tie on the high word (only identical
-//      s-mers in practice, i.e. tandem repeats) falls back to a full 64-bit scan
-//   5. CLOSE/OPEN bits are combined, ranked with a block scan and written as
+//      running minimum of r0 and the thread's own earlier positions: about 2/q of
+//      all positions pass
+//   4. candidates are settled by the whole warp: the < 48 window positions that r0
+//      and the running minimum do not cover are min-reduced on the high word. A tie
+//      on the high word (identical s-mers, i.e. tandem repeats; otherwise 2^-30) is
+//      resolved exactly by re-hashing just the tied positions from the packed read
+//   5. CLOSE/OPEN bits are parked per chunk; once per read (or every 32 k
+//      positions) they are combined, ranked with one block scan and written as
 //      (sid, idx, m_pos, s_mer) records; k-mer hashes follow in sg_kmer.cu
 #include "sg_common.cuh"
 #include "sg_internal.h"
@@ -31,162 +32,82 @@
 
 namespace sg {
 
-template <int NT>
+constexpr int COCAP = 2048;            // chunks of parked CLOSE/OPEN bits (32 k positions)
+constexpr uint32_t HNONE = 0xffffffffu;
+
+// Exact decision for a candidate whose high word ties with the window minimum: the
+// full 62-bit hashes of the tied positions are recomputed from the packed read and
+// compared under the reference's rules. Whole warp; rare (identical s-mers inside
+// one window), so it is kept out of line to keep the tile loop inside the I-cache.
+__device__ __noinline__ bool settle_tie(const uint32_t *ring, int RCH, const uint32_t *hs32, int nwords, int s,
+        int p, int q, bool is_open, uint32_t tgt, int lane)
+{
+    const int RM = RCH - 1;
+    const uint64_t mask = (1ull << (2 * s)) - 1;
+    auto ring_at = [&](int x) -> uint32_t { return ring[(x & 15) * RCH + ((x >> 4) & RM)]; };
+    auto m64_at = [&](int x) -> uint64_t {
+        if (x < 0 || ring_at(x) == HNONE) return SG_NONE64;
+        return hash64(smer_code_at(hs32, x, s, nwords) >> 1, mask);
+    };
+    uint32_t lo = 0xffffffffu;
+    for (int x = p - q + 1 + lane; x < p; x += 32)
+        if (ring_at(x) == tgt) lo = min(lo, (uint32_t) m64_at(x));
+    const uint64_t mo = (uint64_t) tgt << 32 | __reduce_min_sync(SG_FULL, lo);
+    const uint64_t e64 = m64_at(p - q);
+    if (is_open) return e64 <= mo;
+    const uint64_t mp = m64_at(p);
+    return mp <= mo && (mp <= e64 || mp < mo || m64_at(p - q + 1) == mp);
+}
+
+template <int NT, int S_FIXED>
 __global__ void __launch_bounds__(NT) scan_kernel(ScanArgs A, ScanGeom G)
 {
     constexpr int NW = NT / 32;
     extern __shared__ __align__(16) uint32_t smem[];
     const int RCH = G.rch, RM = RCH - 1;
-    uint32_t *ring_hi = smem;                          // [16][RCH]
-    uint32_t *ring_lo = ring_hi + 16 * RCH;            // [16][RCH]
-    uint32_t *D = ring_lo + 16 * RCH;                  // [J+1][RCH] (at least one level)
-    const int nlev = G.J >= 0 ? G.J + 1 : 1;
-    uint32_t *cflag = D + nlev * RCH;                  // [RCH]
-    uint32_t *s_scan = cflag + RCH;                    // [NW + 1]
+    uint32_t *ring = smem;                             // [16][RCH] high words of m[]
+    uint32_t *Lv = ring + 16 * RCH;                    // [T+1][RCH] radix-4 sparse table, level 0 = chunk minima
+    uint32_t *co = Lv + (G.T + 1) * RCH;               // [COCAP] Cm | Om << 16 per chunk
+    uint32_t *s_scan = co + COCAP;                     // [NW + 1]
     int *s_misc = reinterpret_cast<int *>(s_scan + NW + 1);   // [NW + 4]
 
     const uint64_t r = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int64_t H = A.hoco_l[r];
-    const int k = A.k, s = A.s, q = k - s + 1;
+    const int H = (int) A.hoco_l[r];
+    const int k = A.k, s = S_FIXED ? S_FIXED : A.s, q = k - s + 1;
     if (H < k) { if (tid == 0) A.n_scm[r] = 0; return; }
     const uint64_t hb = A.hoff[r];
     const uint32_t *hs32 = reinterpret_cast<const uint32_t *>(A.hoco_s + hb / 4);
     const uint16_t *nb16 = reinterpret_cast<const uint16_t *>(A.nbits + hb / 8);
-    const int64_t nwords = (H + 15) >> 4;
+    const int nwords = (H + 15) >> 4;
     const bool has_n = A.n_amb[r] != 0;
     const uint64_t mask = (1ull << (2 * s)) - 1;
     const int rsh = 2 * s - 2;
+    const bool small_q = q < 16;       // a thread's earlier positions fall out of the window: no running bound
+    const int n_full = G.n_full, T = G.T, W = 1 << (2 * T);
 
-    for (int i = tid; i < 16 * RCH; i += NT) { ring_hi[i] = 0xffffffffu; ring_lo[i] = 0xffffffffu; }
-    for (int i = tid; i < nlev * RCH; i += NT) D[i] = 0xffffffffu;
-    for (int i = tid; i < RCH; i += NT) cflag[i] = 0;
+    for (int i = tid; i < 16 * RCH; i += NT) ring[i] = HNONE;
+    for (int i = tid; i < (T + 1) * RCH; i += NT) Lv[i] = HNONE;
     if (tid == 0) s_misc[NW] = -1;                     // last ambiguous position seen so far
     __syncthreads();
 
-    auto ring_at = [&](int64_t x) -> int { return (int) (x & 15) * RCH + (int) ((x >> 4) & RM); };
-    auto m_at = [&](int64_t x) -> uint64_t { int a = ring_at(x); return (uint64_t) ring_hi[a] << 32 | ring_lo[a]; };
+    auto ring_at = [&](int x) -> uint32_t { return ring[(x & 15) * RCH + ((x >> 4) & RM)]; };
+    uint32_t n_emitted = 0, carryC = 0;
+    int co_base = 0;                                   // chunk index of co[0]
+    const int n_sub = (H + 1 + NT * 16 - 1) / (NT * 16);
 
-    uint32_t n_emitted = 0;
-    const int64_t n_sub = (H + 1 + NT * 16 - 1) / (NT * 16);
-    for (int64_t sub = 0; sub < n_sub; ++sub) {
-        const int64_t c = sub * NT + tid;              // my chunk
-        const int64_t P = c << 4;                      // its first position
-        const int cs = (int) (c & RM);
-        const uint32_t w0 = hoco_word(hs32, c, nwords);
-        const uint32_t nb = (has_n && c < nwords) ? nb16[c] : 0u;
-
-        // valid bases in a row ending just before my chunk
-        int64_t l0 = P;
-        if (has_n) {
-            int mine = nb ? (int) P + 31 - __clz(nb) : -1, inc = mine;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(SG_FULL, inc, d); if (lane >= d) inc = max(inc, t); }
-            if (lane == 31) s_misc[wid] = inc;
-            __syncthreads();
-            int before = s_misc[NW];
-            for (int w = 0; w < wid; ++w) before = max(before, s_misc[w]);
-            int exc = __shfl_up_sync(SG_FULL, inc, 1);
-            if (lane == 0) exc = -1;
-            before = max(before, exc);
-            l0 = P - 1 - before;
-            __syncthreads();
-            if (tid == NT - 1) s_misc[NW] = max(before, mine);
+    // ranks the parked bits of chunks [co_base, c_end) and writes their records
+    auto flush = [&](int c_end) {
+        const int nb = c_end - co_base;
+        const int cpt = (nb + NT - 1) / NT;            // chunks per thread, contiguous
+        const int j0 = min(tid * cpt, nb), j1 = min(j0 + cpt, nb);
+        uint32_t cnt = 0;
+        for (int j = j0; j < j1; ++j) {
+            const uint32_t v = co[j], pv = j ? (co[j - 1] >> 15) & 1u : carryC;
+            cnt += __popc((((v << 1) | pv) ^ (v >> 16)) & 0xffffu);
         }
-
-        // 1. hashes of my 16 positions
-        uint32_t hi[16];
-        uint32_t cmin = 0xffffffffu;
-        {
-            const uint64_t V = (uint64_t) hoco_word(hs32, c - 2, nwords) << 32 | hoco_word(hs32, c - 1, nwords);
-            uint64_t fw = V & mask, rv = rc64(V) >> (64 - 2 * s);
-            int64_t l = l0;
-            const int nvalid = (int) min((int64_t) 16, max((int64_t) 0, H - P));
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const uint32_t b = (w0 >> (30 - 2 * i)) & 3u;
-                fw = ((fw << 2) | b) & mask;
-                rv = (rv >> 2) | ((uint64_t) (3u - b) << rsh);
-                l = ((nb >> i) & 1u) ? 0 : l + 1;
-                const bool ok = i < nvalid && l >= s && fw != rv;
-                const uint64_t m = ok ? hash64(fw < rv ? fw : rv, mask) : SG_NONE64;
-                hi[i] = (uint32_t) (m >> 32);
-                ring_hi[i * RCH + cs] = hi[i];
-                ring_lo[i * RCH + cs] = (uint32_t) m;
-                cmin = min(cmin, hi[i]);
-            }
-        }
-        D[cs] = cmin;
-        __syncthreads();
-
-        // 2. sparse table over chunk minima
-        {
-            uint32_t v = cmin;
-            for (int j = 1; j <= G.J; ++j) {
-                v = min(v, D[(j - 1) * RCH + (int) ((c - (1 << (j - 1))) & RM)]);
-                D[j * RCH + cs] = v;
-                __syncthreads();
-            }
-        }
-        uint32_t R = 0xffffffffu;
-        if (G.n_full > 0)
-            R = min(D[G.J * RCH + (int) ((c - 1) & RM)], D[G.J * RCH + (int) ((c - G.n_full + (1 << G.J) - 1) & RM)]);
-
-        // valid-run length ending at position P+i
-        auto run_len = [&](int i) -> int64_t {
-            if (i < 0) return l0;
-            const uint32_t ml = nb & ((2u << i) - 1u);
-            return ml ? (int64_t) (i - (31 - __clz(ml))) : l0 + i + 1;
-        };
-        const int64_t first_cov = (G.n_full > 0 ? (c - G.n_full) : c) << 4;   // first position covered by R at i = 0
-        // for q < 16 a thread's earlier positions fall out of the window, so the running
-        // minimum is not a bound: every position is settled by scanning its (short) window
-        const bool small_q = q < 16;
-
-        // 3./4. candidates
-        uint32_t Cm = 0, Om = 0;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const int64_t p = P + i;
-            const uint32_t e_hi = ring_hi[ring_at(p - q)];
-            const bool cand_o = p <= H && p >= k && e_hi != 0xffffffffu && e_hi <= R;
-            const bool cand_c = p < H && hi[i] != 0xffffffffu && hi[i] <= R;
-            if (cand_o || cand_c) {
-                // exact minimum of the high words over m[p-q+1 .. p-1]
-                uint32_t Mhi = R;
-                for (int64_t x = p - q + 1, xe = small_q ? p : first_cov; x < xe; ++x) Mhi = min(Mhi, ring_hi[ring_at(x)]);
-                uint64_t mo = 0; bool have_mo = false;
-                auto full_min = [&]() {
-                    if (!have_mo) {
-                        mo = SG_NONE64;
-                        for (int64_t x = p - q + 1; x < p; ++x) mo = min(mo, m_at(x));
-                        have_mo = true;
-                    }
-                    return mo;
-                };
-                if (cand_o && run_len(i - 1) >= k && (p == H || !((nb >> i) & 1u))) {
-                    bool yes = e_hi < Mhi;
-                    if (!yes && e_hi == Mhi) yes = m_at(p - q) <= full_min();
-                    if (yes) Om |= 1u << i;
-                }
-                if (cand_c && run_len(i) >= k) {
-                    bool yes = hi[i] < Mhi;
-                    if (!yes && hi[i] == Mhi) {
-                        const uint64_t mp = m_at(p), mm = full_min();
-                        yes = mp <= mm && (mp <= m_at(p - q) || mp < mm || m_at(p - q + 1) == mp);
-                    }
-                    if (yes) Cm |= 1u << i;
-                }
-            }
-            if (!small_q) R = min(R, hi[i]);
-        }
-
-        // 5. combine, rank, write
-        cflag[cs] = (Cm >> 15) & 1u;
-        __syncthreads();
-        uint32_t E = (((Cm << 1) | cflag[(int) ((c - 1) & RM)]) ^ Om) & 0xffffu;
         uint32_t tot;
-        const uint32_t ex = BlockScanU32::run<NW>(__popc(E), s_scan, &tot);
+        uint32_t idx = BlockScanU32::run<NW>(cnt, s_scan, &tot);
         if (tot) {
             if (tid == 0) {
                 unsigned long long b = atomicAdd(A.rec_count, (unsigned long long) tot);
@@ -195,27 +116,188 @@ __global__ void __launch_bounds__(NT) scan_kernel(ScanArgs A, ScanGeom G)
             }
             __syncthreads();
             const uint64_t base = (uint64_t) (uint32_t) s_misc[NW + 1] | (uint64_t) (uint32_t) s_misc[NW + 2] << 32;
-            uint32_t j = ex;
-            while (E) {
-                const int i = __ffs(E) - 1;
-                E &= E - 1;
-                const int64_t t = P + i - k;           // k-mer start
-                uint64_t code;
-                if ((Om >> i) & 1u) code = smer_code_at(hs32, t + s - 1, s, nwords);          // first s-mer
-                else code = smer_code_at(hs32, t + k - 1, s, nwords) ^ 1ull;                 // last s-mer, flipped
-                const uint32_t z = (uint32_t) (((Om >> i) & 1u) ? code & 1ull : (code ^ 1ull) & 1ull);
-                const uint64_t o = base + j;
-                if (o < A.rec_cap) {
-                    A.rec_sid[o] = (uint32_t) r;
-                    A.rec_idx[o] = n_emitted + j;
-                    A.rec_mpos[o] = (uint32_t) t << 1 | z;
-                    A.rec_smer[o] = code;
+            for (int j = j0; j < j1; ++j) {
+                const uint32_t v = co[j], pv = j ? (co[j - 1] >> 15) & 1u : carryC, Om = v >> 16;
+                uint32_t E = (((v << 1) | pv) ^ Om) & 0xffffu;
+                while (E) {
+                    const int i = __ffs(E) - 1;
+                    E &= E - 1;
+                    const int t = ((co_base + j) << 4) + i - k;      // k-mer start
+                    const bool open = (Om >> i) & 1u;
+                    // OPEN: code of the first s-mer; CLOSE: code of the last s-mer with its low bit flipped
+                    const uint64_t raw = smer_code_at(hs32, open ? t + s - 1 : t + k - 1, s, nwords);
+                    const uint64_t o = base + idx;
+                    if (o < A.rec_cap) {
+                        A.rec_sid[o] = (uint32_t) r;
+                        A.rec_idx[o] = n_emitted + idx;
+                        A.rec_mpos[o] = (uint32_t) t << 1 | (uint32_t) (raw & 1ull);
+                        A.rec_smer[o] = open ? raw : raw ^ 1ull;
+                    }
+                    ++idx;
                 }
-                ++j;
             }
-            n_emitted += tot;
-            __syncthreads();
         }
+        __syncthreads();
+        if (nb) carryC = (co[nb - 1] >> 15) & 1u;
+        n_emitted += tot;
+        co_base = c_end;
+        __syncthreads();
+    };
+
+    for (int sub = 0; ; ++sub) {
+        // single call site: when the parking buffer would overflow, and once at the end of the read
+        if (sub == n_sub || sub * NT + NT - co_base > COCAP) flush(sub * NT);      // uniform: depends on sub only
+        if (sub == n_sub) break;
+        const int c = sub * NT + tid;                  // my chunk
+        const int P = c << 4;                          // its first position
+        const int cs = c & RM;
+
+        // which of my 16 positions can carry a hash: >= s valid bases in a row, inside the read
+        uint32_t vm, nb = 0;
+        int l0 = P;                                    // valid bases in a row ending just before my chunk
+        {
+            const int to = min(16, max(0, H - P));
+            if (!has_n) {
+                const int from = max(0, s - 1 - P);
+                vm = (from < to) ? ((0xffffu << from) & (0xffffu >> (16 - to))) : 0u;
+            } else {
+                nb = c < nwords ? nb16[c] : 0u;
+                int mine = nb ? P + 31 - __clz(nb) : -1, inc = mine;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(SG_FULL, inc, d); if (lane >= d) inc = max(inc, t); }
+                if (lane == 31) s_misc[wid] = inc;
+                __syncthreads();
+                int before = s_misc[NW];
+                for (int w = 0; w < wid; ++w) before = max(before, s_misc[w]);
+                int exc = __shfl_up_sync(SG_FULL, inc, 1);
+                if (lane == 0) exc = -1;
+                before = max(before, exc);
+                l0 = P - 1 - before;
+                __syncthreads();
+                if (tid == NT - 1) s_misc[NW] = max(before, mine);
+                vm = 0;
+                int l = l0;
+                for (int i = 0; i < to; ++i) { l = ((nb >> i) & 1u) ? 0 : l + 1; vm |= (uint32_t) (l >= s) << i; }
+            }
+        }
+
+        // 1. hashes of my 16 positions (4 x 4: the loop keeps the tile body inside the instruction cache)
+        uint32_t cmin = HNONE;
+        uint32_t *own = ring + cs;
+        if (vm) {
+            uint32_t w0 = hoco_word(hs32, c, nwords), vmr = vm;
+            const uint64_t V = (uint64_t) hoco_word(hs32, c - 2, nwords) << 32 | hoco_word(hs32, c - 1, nwords);
+            uint64_t fw = V & mask, rv = rc64(V) >> (64 - 2 * s);
+            uint32_t *dst = own;
+            for (int i4 = 0; i4 < 4; ++i4) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t b = w0 >> 30;
+                    w0 <<= 2;
+                    fw = ((fw << 2) | b) & mask;
+                    rv = (rv >> 2) | ((uint64_t) (3u - b) << rsh);
+                    const bool ok = (vmr & 1u) && fw != rv;
+                    vmr >>= 1;
+                    const uint32_t h = (uint32_t) (hash64(fw < rv ? fw : rv, mask) >> 32);
+                    const uint32_t hv = ok ? h : HNONE;
+                    dst[j * RCH] = hv;
+                    cmin = min(cmin, hv);
+                }
+                dst += 4 * RCH;
+            }
+        } else {
+#pragma unroll 4
+            for (int i = 0; i < 16; ++i) own[i * RCH] = HNONE;
+        }
+        Lv[cs] = cmin;
+        __syncthreads();
+
+        // 2. radix-4 sparse table over chunk minima: level t holds the minimum of 4^t chunks ending at c
+        {
+            uint32_t v = cmin;
+            for (int t = 1; t <= T; ++t) {
+                const int st = 1 << (2 * (t - 1));
+                const uint32_t *L = Lv + (t - 1) * RCH;
+                v = min(min(v, L[(c - st) & RM]), min(L[(c - 2 * st) & RM], L[(c - 3 * st) & RM]));
+                Lv[t * RCH + cs] = v;
+                __syncthreads();
+            }
+        }
+        uint32_t r0 = HNONE;
+        if (n_full > 0) {
+            const uint32_t *L = Lv + T * RCH;
+            for (int e = c - 1; e - W + 1 > c - n_full; e -= W) r0 = min(r0, L[e & RM]);
+            r0 = min(r0, L[(c - n_full + W - 1) & RM]);
+        }
+
+        // 3. candidates
+        uint32_t candC = 0, candO = 0;
+        {
+            const uint32_t mC = (P + 15 < k - 1 || P >= H) ? 0u :
+                ((0xffffu << max(0, k - 1 - P)) & (0xffffu >> (16 - min(16, H - P)))) & 0xffffu;
+            const uint32_t mO = (P + 15 < k || P > H) ? 0u :
+                ((0xffffu << max(0, k - P)) & (0xffffu >> (16 - min(16, H + 1 - P)))) & 0xffffu;
+            if (small_q) {
+                candC = mC; candO = mO;
+            } else if (mC | mO) {
+                const int d = P - q, d0 = d & 15;
+                const uint32_t *rowA = ring + ((d >> 4) & RM), *rowB = ring + (((d >> 4) + 1) & RM);
+                uint32_t R = r0;
+#pragma unroll 4
+                for (int i = 0; i < 16; ++i) {
+                    const uint32_t e = (i + d0 < 16 ? rowA : rowB)[((i + d0) & 15) * RCH];
+                    const uint32_t h = own[i * RCH];
+                    candO |= (uint32_t) (e <= R) << i;
+                    candC |= (uint32_t) (h <= R) << i;
+                    R = min(R, h);
+                }
+                candC &= mC; candO &= mO;
+            }
+        }
+
+        // 4. settle candidates, one at a time, with the whole warp
+        uint32_t Cm = 0, Om = 0;
+        {
+            uint32_t any = __ballot_sync(SG_FULL, (candC | candO) != 0);
+            while (any) {
+                const int src = __ffs(any) - 1;
+                any &= any - 1;
+                uint32_t lc = __shfl_sync(SG_FULL, candC | candO << 16, src);
+                const uint32_t lr0 = small_q ? HNONE : __shfl_sync(SG_FULL, r0, src);
+                const int lc_chunk = c - lane + src;
+                const int lP = lc_chunk << 4;
+                const int fc = small_q ? 0x7fffffff : ((n_full > 0 ? lc_chunk - n_full : lc_chunk) << 4);
+                while (lc) {
+                    const int bit = __ffs(lc) - 1;
+                    lc &= lc - 1;
+                    const int i = bit & 15, p = lP + i;
+                    const bool is_open = bit >> 4;
+                    // minimum of the high words over m[p-q+1 .. p-1]: r0 covers [fc, lP), the rest is scanned
+                    uint32_t m = lr0;
+                    for (int x = p - q + 1 + lane; x < min(fc, p); x += 32) m = min(m, ring_at(x));
+                    if (!small_q) for (int x = lP + lane; x < p; x += 32) m = min(m, ring_at(x));
+                    const uint32_t Mhi = __reduce_min_sync(SG_FULL, m);
+                    const uint32_t tgt = ring_at(is_open ? p - q : p);
+                    bool yes = tgt != HNONE && tgt < Mhi;
+                    if (tgt != HNONE && tgt == Mhi) yes = settle_tie(ring, RCH, hs32, nwords, s, p, q, is_open, tgt, lane);
+                    if (lane == src && yes) {
+                        if (has_n) {
+                            // run-length conditions that the position masks only imply for reads without N
+                            auto run_len = [&](int ii) -> int {
+                                if (ii < 0) return l0;
+                                const uint32_t ml = nb & ((2u << ii) - 1u);
+                                return ml ? ii - (31 - __clz(ml)) : l0 + ii + 1;
+                            };
+                            if (is_open) yes = run_len(i - 1) >= k && (p == H || !((nb >> i) & 1u));
+                            else yes = run_len(i) >= k;
+                        }
+                        if (yes) { if (is_open) Om |= 1u << i; else Cm |= 1u << i; }
+                    }
+                }
+            }
+        }
+        co[c - co_base] = Cm | Om << 16;
+        __syncthreads();                               // ring and table slots are reused by the next tile
     }
     if (tid == 0) A.n_scm[r] = n_emitted;
 }
@@ -225,30 +307,36 @@ int scan_geometry(int k, int s, int nt, ScanGeom *g, size_t *smem)
     const int q = k - s + 1;
     int n_full = q / 16 - 1;
     if (n_full < 0) n_full = 0;
-    int J = -1;
-    while (n_full > 0 && (2 << J) <= n_full) ++J;        // largest J with 2^J <= n_full
+    int T = 0;
+    while (n_full > 0 && (4 << (2 * T)) <= n_full) ++T;  // largest T with 4^T <= n_full
     int need = (q + 15) / 16 + nt + 2, rch = 64;
     while (rch < need) rch <<= 1;
-    const int nlev = J >= 0 ? J + 1 : 1;
-    g->rch = rch; g->n_full = n_full; g->J = J;
-    *smem = sizeof(uint32_t) * ((size_t) 32 * rch + (size_t) nlev * rch + rch + (nt / 32 + 1) + (nt / 32 + 4));
+    g->rch = rch; g->n_full = n_full; g->T = T;
+    *smem = sizeof(uint32_t) * ((size_t) 16 * rch + (size_t) (T + 1) * rch + COCAP + (nt / 32 + 1) + (nt / 32 + 4));
     return *smem <= 227 * 1024 ? 0 : SG_E_KSIZE;
 }
 
-int launch_scan(const ScanArgs &A, uint64_t n_reads, cudaStream_t st)
+template <int NT>
+static int launch_scan_nt(const ScanArgs &A, uint64_t n_reads, cudaStream_t st)
 {
-    constexpr int NT = 128;
     ScanGeom g;
     size_t smem;
     if (scan_geometry(A.k, A.s, NT, &g, &smem)) return SG_E_KSIZE;
     if (n_reads == 0) return 0;
     static bool attr_set = false;
     if (!attr_set) {
-        if (cudaFuncSetAttribute(scan_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return SG_E_CUDA;
+        if (cudaFuncSetAttribute(scan_kernel<NT, 31>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return SG_E_CUDA;
+        if (cudaFuncSetAttribute(scan_kernel<NT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return SG_E_CUDA;
         attr_set = true;
     }
-    scan_kernel<NT><<<(unsigned) n_reads, NT, smem, st>>>(A, g);
+    if (A.s == 31) scan_kernel<NT, 31><<<(unsigned) n_reads, NT, smem, st>>>(A, g);
+    else scan_kernel<NT, 0><<<(unsigned) n_reads, NT, smem, st>>>(A, g);
     return 1;
+}
+
+int launch_scan(const ScanArgs &A, uint64_t n_reads, cudaStream_t st)
+{
+    return launch_scan_nt<SYNC_SCAN_NT>(A, n_reads, st);
 }
 
 } // namespace sg
