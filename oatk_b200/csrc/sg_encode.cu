@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(NT) encode_kernel(EncodeArgs A)
     constexpr int TILE = NT * 16;
     constexpr int NW = NT / 32;
     __shared__ __align__(16) uint8_t s_code[TILE + 48];
-    __shared__ uint32_t s_pos[TILE + 48];
+    __shared__ __align__(16) uint32_t s_pos[TILE + 48];
     __shared__ uint32_t s_scan[NW + 1];
     __shared__ uint32_t s_namb;
 
@@ -111,17 +111,28 @@ __global__ void __launch_bounds__(NT) encode_kernel(EncodeArgs A)
         uint32_t tot;
         const uint32_t ex = BlockScanU32::run<NW>(cnt, s_scan, &tot);
 
-        // stage (code, raw start) of every run that starts in my chunk
+        // stage (code, raw start) of every run that starts in my chunk: 16 predicated steps, no loop
         {
-            uint32_t hl = n_stage + ex, m = M;
+            uint32_t hl = n_stage + ex;
             const uint32_t rel = (uint32_t) (g - raw0);        // wraps for bytes before the read; those are void
-            while (m) {
-                const int b = 31 - __clz(m);
-                m &= ~(1u << b);
-                const int i = 15 - (b >> 1);
-                s_code[hl] = (uint8_t) (((P >> b) & 3u) | ((NM >> b) & 1u) << 2);
-                s_pos[hl] = rel + (uint32_t) i;
-                ++hl;
+            if (fast) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    if (M & (1u << (2 * (15 - i)))) {
+                        s_code[hl] = (uint8_t) ((P >> (2 * (15 - i))) & 3u);
+                        s_pos[hl] = rel + (uint32_t) i;
+                        ++hl;
+                    }
+                }
+            } else {
+                uint32_t m = M;
+                while (m) {
+                    const int b = 31 - __clz(m);
+                    m &= ~(1u << b);
+                    s_code[hl] = (uint8_t) (((P >> b) & 3u) | ((NM >> b) & 1u) << 2);
+                    s_pos[hl] = rel + (uint32_t) (15 - (b >> 1));
+                    ++hl;
+                }
             }
         }
         const bool last = (t + 1 == ntiles);
@@ -131,35 +142,62 @@ __global__ void __launch_bounds__(NT) encode_kernel(EncodeArgs A)
         const uint32_t closed = last ? n_avail : (n_avail ? n_avail - 1 : 0);
         const uint32_t fin = last ? closed : (closed & ~15u);
 
-        // run lengths, side lists
-        for (uint32_t hl = tid; hl < fin; hl += NT) {
-            const uint32_t rl = s_pos[hl + 1] - s_pos[hl];
-            rl8[g_done + hl] = (uint8_t) (min(rl, 256u) - 1u);
-            if (rl > 255u) {
-                unsigned long long j = atomicAdd(A.lrl_count, 1ull);
-                if (j < A.lrl_cap) { A.lrl_sid[j] = sid; A.lrl_idx[j] = g_done + hl; A.lrl_val[j] = rl - 1u; }
-            }
-            if (s_code[hl] & 4u) {
-                unsigned long long j = atomicAdd(A.amb_count, 1ull);
-                if (j < A.amb_cap) { A.amb_sid[j] = sid; A.amb_pos[j] = s_pos[hl]; }
-                atomicAdd(&s_namb, 1u);
-            }
-        }
-        // 16 codes -> one big-endian 32-bit word; 16 flags -> 16 bits
+        // finalise groups of 16 hoco bases: run lengths -> 16 bytes, codes -> one big-endian word,
+        // ambiguity flags -> 16 bits; everything from vector loads of the staging arrays
         const uint32_t ngrp = (fin + 15) >> 4;
         for (uint32_t gi = tid; gi < ngrp; gi += NT) {
-            const uint4 c = *reinterpret_cast<const uint4 *>(s_code + gi * 16);
-            const uint32_t w[4] = {c.x, c.y, c.z, c.w};
+            const uint32_t e0 = gi * 16;
+            const uint32_t nval = min(16u, fin - e0);             // entries of this group that exist
+            uint32_t ps[17];
+            {
+                const uint4 *q4 = reinterpret_cast<const uint4 *>(s_pos + e0);
+                const uint4 a = q4[0], b4 = q4[1], c4 = q4[2], d4 = q4[3];
+                ps[0] = a.x; ps[1] = a.y; ps[2] = a.z; ps[3] = a.w; ps[4] = b4.x; ps[5] = b4.y; ps[6] = b4.z; ps[7] = b4.w;
+                ps[8] = c4.x; ps[9] = c4.y; ps[10] = c4.z; ps[11] = c4.w; ps[12] = d4.x; ps[13] = d4.y; ps[14] = d4.z; ps[15] = d4.w;
+                ps[16] = s_pos[e0 + 16];
+            }
+            uint32_t rl[16], big = 0;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                rl[j] = (uint32_t) j < nval ? ps[j + 1] - ps[j] - 1u : 0u;     // run length - 1
+                big |= rl[j];
+            }
+            const uint4 cw = *reinterpret_cast<const uint4 *>(s_code + e0);
+            const uint32_t w[4] = {cw.x, cw.y, cw.z, cw.w};
             uint32_t word = 0, nbw = 0;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 uint32_t x = w[j];
-                const uint32_t left = fin - gi * 16 - j * 4;          // valid entries from this 4-group on
-                if (gi * 16 + j * 4 >= fin) x = 0;
-                else if (left < 4) x &= (1u << (8 * left)) - 1u;
+                if ((uint32_t) (4 * j) >= nval) x = 0;
+                else if (nval - 4 * j < 4) x &= (1u << (8 * (nval - 4 * j))) - 1u;
                 word |= (((x & 0x03030303u) * 0x40100401u) >> 24) << (24 - 8 * j);
-                nbw |= ((((x >> 2) & 0x01010101u) * 0x00204081u >> 21) & 0xFu) << (4 * j);   // gather bit 0 of 4 bytes
+                nbw |= ((((x >> 2) & 0x01010101u) * 0x00204081u >> 21) & 0xFu) << (4 * j);   // gather bit 2 of 4 bytes
             }
+            if (big >= 255u) {
+                // a run longer than 256 saturates ho_rl and goes to the side list (syncmer.c:301-304)
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    if (rl[j] >= 255u) {
+                        unsigned long long o = atomicAdd(A.lrl_count, 1ull);
+                        if (o < A.lrl_cap) { A.lrl_sid[o] = sid; A.lrl_idx[o] = g_done + e0 + j; A.lrl_val[o] = rl[j]; }
+                        rl[j] = 255u;
+                    }
+                }
+            }
+            if (nbw) {
+                for (uint32_t mm = nbw; mm; mm &= mm - 1) {
+                    const int j = __ffs(mm) - 1;
+                    unsigned long long o = atomicAdd(A.amb_count, 1ull);
+                    if (o < A.amb_cap) { A.amb_sid[o] = sid; A.amb_pos[o] = s_pos[e0 + j]; }
+                }
+                atomicAdd(&s_namb, (uint32_t) __popc(nbw));
+            }
+            uint4 out;
+            out.x = rl[0] | rl[1] << 8 | rl[2] << 16 | rl[3] << 24;
+            out.y = rl[4] | rl[5] << 8 | rl[6] << 16 | rl[7] << 24;
+            out.z = rl[8] | rl[9] << 8 | rl[10] << 16 | rl[11] << 24;
+            out.w = rl[12] | rl[13] << 8 | rl[14] << 16 | rl[15] << 24;
+            *reinterpret_cast<uint4 *>(rl8 + g_done + e0) = out;      // capacity is padded to 64: a full store always fits
             hs32[(g_done >> 4) + gi] = bswap32(word);
             nb16[(g_done >> 4) + gi] = (uint16_t) nbw;
         }

@@ -181,29 +181,48 @@ __global__ void __launch_bounds__(NT) scan_kernel(ScanArgs A, ScanGeom G)
             }
         }
 
-        // 1. hashes of my 16 positions (4 x 4: the loop keeps the tile body inside the instruction cache)
+        // 1. hashes of my 16 positions (4 x 4: the loop keeps the tile body inside the instruction cache).
+        //    An s-mer of odd length cannot be its own reverse complement, so a chunk whose 16 positions
+        //    are all valid needs no per-position checks.
         uint32_t cmin = HNONE;
         uint32_t *own = ring + cs;
         if (vm) {
-            uint32_t w0 = hoco_word(hs32, c, nwords), vmr = vm;
+            uint32_t w0 = hoco_word(hs32, c, nwords);
             const uint64_t V = (uint64_t) hoco_word(hs32, c - 2, nwords) << 32 | hoco_word(hs32, c - 1, nwords);
             uint64_t fw = V & mask, rv = rc64(V) >> (64 - 2 * s);
             uint32_t *dst = own;
-            for (int i4 = 0; i4 < 4; ++i4) {
+            if (vm == 0xffffu && (s & 1)) {
+                for (int i4 = 0; i4 < 4; ++i4) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const uint32_t b = w0 >> 30;
-                    w0 <<= 2;
-                    fw = ((fw << 2) | b) & mask;
-                    rv = (rv >> 2) | ((uint64_t) (3u - b) << rsh);
-                    const bool ok = (vmr & 1u) && fw != rv;
-                    vmr >>= 1;
-                    const uint32_t h = (uint32_t) (hash64(fw < rv ? fw : rv, mask) >> 32);
-                    const uint32_t hv = ok ? h : HNONE;
-                    dst[j * RCH] = hv;
-                    cmin = min(cmin, hv);
+                    for (int j = 0; j < 4; ++j) {
+                        const uint32_t b = w0 >> 30;
+                        w0 <<= 2;
+                        fw = ((fw << 2) | b) & mask;
+                        rv = (rv >> 2) | ((uint64_t) (3u - b) << rsh);
+                        const uint32_t hv = (uint32_t) (hash64(fw < rv ? fw : rv, mask) >> 32);
+                        dst[j * RCH] = hv;
+                        cmin = min(cmin, hv);
+                    }
+                    dst += 4 * RCH;
                 }
-                dst += 4 * RCH;
+            } else {
+                uint32_t vmr = vm;
+                for (int i4 = 0; i4 < 4; ++i4) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint32_t b = w0 >> 30;
+                        w0 <<= 2;
+                        fw = ((fw << 2) | b) & mask;
+                        rv = (rv >> 2) | ((uint64_t) (3u - b) << rsh);
+                        const bool ok = (vmr & 1u) && fw != rv;
+                        vmr >>= 1;
+                        const uint32_t h = (uint32_t) (hash64(fw < rv ? fw : rv, mask) >> 32);
+                        const uint32_t hv = ok ? h : HNONE;
+                        dst[j * RCH] = hv;
+                        cmin = min(cmin, hv);
+                    }
+                    dst += 4 * RCH;
+                }
             }
         } else {
 #pragma unroll 4
@@ -230,56 +249,55 @@ __global__ void __launch_bounds__(NT) scan_kernel(ScanArgs A, ScanGeom G)
             r0 = min(r0, L[(c - n_full + W - 1) & RM]);
         }
 
-        // 3. candidates
-        uint32_t candC = 0, candO = 0;
-        {
-            const uint32_t mC = (P + 15 < k - 1 || P >= H) ? 0u :
-                ((0xffffu << max(0, k - 1 - P)) & (0xffffu >> (16 - min(16, H - P)))) & 0xffffu;
-            const uint32_t mO = (P + 15 < k || P > H) ? 0u :
-                ((0xffffu << max(0, k - P)) & (0xffffu >> (16 - min(16, H + 1 - P)))) & 0xffffu;
-            if (small_q) {
-                candC = mC; candO = mO;
-            } else if (mC | mO) {
-                const int d = P - q, d0 = d & 15;
-                const uint32_t *rowA = ring + ((d >> 4) & RM), *rowB = ring + (((d >> 4) + 1) & RM);
-                uint32_t R = r0;
-#pragma unroll 4
-                for (int i = 0; i < 16; ++i) {
-                    const uint32_t e = (i + d0 < 16 ? rowA : rowB)[((i + d0) & 15) * RCH];
-                    const uint32_t h = own[i * RCH];
-                    candO |= (uint32_t) (e <= R) << i;
-                    candC |= (uint32_t) (h <= R) << i;
-                    R = min(R, h);
-                }
-                candC &= mC; candO &= mO;
-            }
+        // 3. which chunks can hold a candidate at all: its own minimum (CLOSE) or the minimum of the two
+        //    chunks its leaving elements e(p) come from (OPEN) must not exceed r0. About 1 chunk in 20.
+        const uint32_t mC = (P + 15 < k - 1 || P >= H) ? 0u :
+            ((0xffffu << max(0, k - 1 - P)) & (0xffffu >> (16 - min(16, H - P)))) & 0xffffu;
+        const uint32_t mO = (P + 15 < k || P > H) ? 0u :
+            ((0xffffu << max(0, k - P)) & (0xffffu >> (16 - min(16, H + 1 - P)))) & 0xffffu;
+        bool flagged;
+        if (small_q) flagged = (mC | mO) != 0;
+        else {
+            const int cA = (P - q) >> 4;
+            const uint32_t emin = min(Lv[cA & RM], Lv[(cA + 1) & RM]);
+            flagged = (mC && cmin <= r0) || (mO && emin <= r0);
         }
 
-        // 4. settle candidates, one at a time, with the whole warp
+        // 4. the warp takes the flagged chunks one at a time: lanes 0-15 test CLOSE at position i,
+        //    lanes 16-31 test OPEN at step i against the running minimum, then the survivors are settled
         uint32_t Cm = 0, Om = 0;
         {
-            uint32_t any = __ballot_sync(SG_FULL, (candC | candO) != 0);
+            uint32_t any = __ballot_sync(SG_FULL, flagged);
             while (any) {
                 const int src = __ffs(any) - 1;
                 any &= any - 1;
-                uint32_t lc = __shfl_sync(SG_FULL, candC | candO << 16, src);
+                const int lch = c - lane + src, lP = lch << 4;
                 const uint32_t lr0 = small_q ? HNONE : __shfl_sync(SG_FULL, r0, src);
-                const int lc_chunk = c - lane + src;
-                const int lP = lc_chunk << 4;
-                const int fc = small_q ? 0x7fffffff : ((n_full > 0 ? lc_chunk - n_full : lc_chunk) << 4);
+                const uint32_t lmask = __shfl_sync(SG_FULL, mC | mO << 16, src);
+                const int fc = small_q ? 0x7fffffff : ((n_full > 0 ? lch - n_full : lch) << 4);
+                const int li = lane & 15;
+                const uint32_t h = ring[li * RCH + (lch & RM)];
+                uint32_t Rin = h;                      // inclusive prefix minimum inside each half warp
+#pragma unroll
+                for (int d = 1; d < 16; d <<= 1) { const uint32_t t = __shfl_up_sync(SG_FULL, Rin, d, 16); if (li >= d) Rin = min(Rin, t); }
+                uint32_t Rex = __shfl_up_sync(SG_FULL, Rin, 1, 16);
+                Rex = min(li == 0 ? HNONE : Rex, lr0); // r0 and the chunk's earlier positions
+                const uint32_t mine = lane < 16 ? h : ring_at(lP + li - q);
+                const bool cand = mine != HNONE && ((lmask >> lane) & 1u) && (small_q || mine <= Rex);
+                uint32_t lc = __ballot_sync(SG_FULL, cand);
                 while (lc) {
                     const int bit = __ffs(lc) - 1;
                     lc &= lc - 1;
                     const int i = bit & 15, p = lP + i;
                     const bool is_open = bit >> 4;
-                    // minimum of the high words over m[p-q+1 .. p-1]: r0 covers [fc, lP), the rest is scanned
-                    uint32_t m = lr0;
+                    // minimum of the high words over m[p-q+1 .. p-1]: Rex covers [fc, p), the rest is scanned
+                    uint32_t m = __shfl_sync(SG_FULL, Rex, bit);
+                    if (small_q) m = HNONE;
                     for (int x = p - q + 1 + lane; x < min(fc, p); x += 32) m = min(m, ring_at(x));
-                    if (!small_q) for (int x = lP + lane; x < p; x += 32) m = min(m, ring_at(x));
                     const uint32_t Mhi = __reduce_min_sync(SG_FULL, m);
-                    const uint32_t tgt = ring_at(is_open ? p - q : p);
-                    bool yes = tgt != HNONE && tgt < Mhi;
-                    if (tgt != HNONE && tgt == Mhi) yes = settle_tie(ring, RCH, hs32, nwords, s, p, q, is_open, tgt, lane);
+                    const uint32_t tgt = __shfl_sync(SG_FULL, mine, bit);
+                    bool yes = tgt < Mhi;
+                    if (tgt == Mhi) yes = settle_tie(ring, RCH, hs32, nwords, s, p, q, is_open, tgt, lane);
                     if (lane == src && yes) {
                         if (has_n) {
                             // run-length conditions that the position masks only imply for reads without N
