@@ -188,7 +188,7 @@ class Batch:
         return z
 
     def extract_download(self, want_seq=True):
-        """returns the same flat dictionary layout as oracle/pyoracle.py (unpadded, read order)"""
+        """returns one flat dictionary of unpadded arrays in read order (the layout the parity tests compare)"""
         z = self.extract_sizes()
         n, N = z.n_reads, z.n_syncmers
         a = dict(

@@ -49,6 +49,61 @@ def _nohp(rng, n):
     return ACGT[x].tobytes()
 
 
+def hash64(x, mask):
+    """the reference's invertible s-mer hash (syncmer.c:116-126) on python ints; used only to
+    plant minimisers in the adversarial reads below"""
+    x = ((x << 21) - x - 1) & mask
+    x ^= x >> 24
+    x = (x * 265) & mask
+    x ^= x >> 14
+    x = (x * 21) & mask
+    x ^= x >> 28
+    x = (x * 2147483649) & mask
+    return x
+
+
+def _smer_hashes(seq, s):
+    """hash of the canonical s-mer ending at every position of an ACGT byte string (None = none)"""
+    code = {65: 0, 67: 1, 71: 2, 84: 3}
+    mask = (1 << (2 * s)) - 1
+    fw = rv = 0
+    out = []
+    for i, ch in enumerate(seq):
+        c = code[ch]
+        fw = ((fw << 2) | c) & mask
+        rv = (rv >> 2) | ((3 - c) << (2 * (s - 1)))
+        out.append(None if i + 1 < s or fw == rv else hash64(min(fw, rv), mask))
+    return out
+
+
+def tie_rule_read(rng, k, s):
+    """A read that makes the reference's tie clause (syncmer.c:356-377) reject a CLOSE: an s-mer Y
+    occurs twice inside one window, is the window minimum, its older copy is not in the oldest
+    slot, and the element that just left the window (X) is smaller still. Returns None when
+    k - s + 1 is too small to hold the construction."""
+    q = k - s + 1
+    if q < 2 * s + 4 or s < 4:
+        return None
+    for _ in range(200):
+        cands = [_nohp(rng, s) for _ in range(400 if s > 8 else 60)]
+        hs = sorted((h[-1], c) for c in cands for h in [_smer_hashes(c, s)] if h[-1] is not None)
+        (hx, X), (hy, Y) = hs[0], hs[1]
+        if hx == hy:
+            continue
+        a = (q - 2 * s) // 3
+        b = q - 2 * s - a
+        for _ in range(300):
+            read = _nohp(rng, k) + X + _nohp(rng, a) + Y + _nohp(rng, b) + Y + _nohp(rng, k)
+            if any(read[i] == read[i + 1] for i in range(len(read) - 1)):
+                continue
+            h = _smer_hashes(read, s)
+            p = k + s + a + s + b + s - 1                      # end of the second Y
+            win = [v for v in h[p - q + 1:p] if v is not None]
+            if h[p] == hy and h[p - q] == hx and min(win) == hy and h[p - q + 1] != hy:
+                return read
+    return None
+
+
 def revcomp(b):
     t = bytes.maketrans(b"ACGTacgt", b"TGCAtgca")
     return b.translate(t)[::-1]
@@ -114,4 +169,8 @@ def adversarial_reads(seed, k, s, scale=1):
     out.append(b"\x00\x01\x02\x03" * 50 + _rand(rng, L))       # raw codes 0..3 are bases too (nt4 table)
     for _ in range(6 * scale):                                 # a few long reads with sparse errors
         out.append(_rand(rng, int(rng.integers(L, 3 * L))))
+    t = tie_rule_read(rng, k, s)                               # planted tie: the CLOSE tie clause must reject
+    if t is not None:
+        out.append(t)
+        out.append(revcomp(t))
     return out

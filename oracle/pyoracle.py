@@ -79,12 +79,16 @@ class Oracle:
         L.or_stat.argtypes = [C.c_void_p] + [C.c_void_p] * 4
         L.or_analyze_count.restype = C.c_int
         L.or_analyze_count.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.or_debug_tie_suppressed.restype = C.c_uint64
         L.or_arcs.restype = C.c_uint64
         L.or_arcs.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_double, C.c_void_p]
         self.L = L
 
     def hash64(self, x, mask):
         return self.L.or_hash64(x, mask)
+
+    def tie_suppressed(self):
+        return int(self.L.or_debug_tie_suppressed())
 
     def murmur(self, b, seed=1234):
         return self.L.or_murmur64a(b, len(b), seed)

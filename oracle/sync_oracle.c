@@ -43,6 +43,10 @@
 
 #define NONE UINT64_MAX
 
+/* how often the tie clause of CLOSE rejected a position (tests check that it is exercised) */
+static uint64_t g_tie_suppressed;
+uint64_t or_debug_tie_suppressed(void) { return g_tie_suppressed; }
+
 /* ---------- scalar pieces ---------- */
 
 /* seq_nt4_table semantics (syncmer.c:47-64): bytes 0..3 are themselves,
@@ -202,9 +206,10 @@ static void extract_read(const char *seq, uint64_t len, int k, int s, or_read_t 
                 else { uint32_t x; for (x = a; x <= b; ++x) if (m[x] < mo) mo = m[x]; }
             }
             e = p >= (uint32_t) q ? m[p - q] : NONE;
-            if (p < H && m[p] != NONE && l[p] >= (uint32_t) k && m[p] <= mo &&
-                    (m[p] <= e || m[p] < mo || m[p - q + 1] == m[p]))
-                fc[p] = 1;
+            if (p < H && m[p] != NONE && l[p] >= (uint32_t) k && m[p] <= mo) {
+                if (m[p] <= e || m[p] < mo || m[p - q + 1] == m[p]) fc[p] = 1;
+                else ++g_tie_suppressed;
+            }
             if (p >= (uint32_t) k && e != NONE && e <= mo &&
                     (p < H ? (!isn[p] && l[p] > (uint32_t) k) : l[H - 1] >= (uint32_t) k))
                 fo[p] = 1;
@@ -406,17 +411,82 @@ int or_analyze_count(int n, int start_cnt, const int64_t *cnt, int *peak_het)
     return top;
 }
 
+/* The reference tabulates multiplicities in a khashl map (int -> int, syncmer.c:558) and reads
+ * the number of singletons as the value stored under key 1 -- or, when no group has multiplicity
+ * 1, as the value of whatever slot its scan over the table visited last (kh_ctab_stat,
+ * syncmer.c:618-646). That makes the slot order observable, so the table is restated here:
+ * power-of-two capacity, Fibonacci bucket of kh_hash_uint32, linear probing, growth at 75 %
+ * load with khashl's in-place re-insertion (khashl.h:130-176, 186-211). */
+typedef struct { uint32_t key; int val; } cslot_t;
+typedef struct { uint32_t bits, count, cap; uint32_t *used; cslot_t *b; } ctab_t;
+
+static uint32_t ct_hash(uint32_t k)
+{
+    k += ~(k << 15); k ^= k >> 10; k += k << 3; k ^= k >> 6; k += ~(k << 11); k ^= k >> 16;
+    return k;
+}
+static uint32_t ct_bucket(uint32_t key, uint32_t bits) { return (ct_hash(key) * 2654435769U) >> (32 - bits); }
+#define CT_USED(u, i) ((u)[(i) >> 5] >> ((i) & 31) & 1U)
+#define CT_SET(u, i) ((u)[(i) >> 5] |= 1U << ((i) & 31))
+#define CT_CLR(u, i) ((u)[(i) >> 5] &= ~(1U << ((i) & 31)))
+
+static void ct_grow(ctab_t *t)
+{
+    uint32_t old_n = t->cap, nb = 2, n, j, *nu;
+    while ((1U << nb) < old_n + 1) ++nb;
+    n = 1U << nb;
+    nu = (uint32_t *) calloc(n < 32 ? 1 : n >> 5, 4);
+    t->b = (cslot_t *) realloc(t->b, sizeof(cslot_t) * n);
+    for (j = 0; j < old_n; ++j) {
+        cslot_t cur;
+        if (!CT_USED(t->used, j)) continue;
+        cur = t->b[j];
+        CT_CLR(t->used, j);
+        for (;;) {                       /* drop it at its new home, evicting a not-yet-moved element if one sits there */
+            uint32_t i = ct_bucket(cur.key, nb);
+            while (CT_USED(nu, i)) i = (i + 1) & (n - 1);
+            CT_SET(nu, i);
+            if (i < old_n && CT_USED(t->used, i)) {
+                cslot_t tmp = t->b[i]; t->b[i] = cur; cur = tmp;
+                CT_CLR(t->used, i);
+            } else { t->b[i] = cur; break; }
+        }
+    }
+    free(t->used);
+    t->used = nu; t->bits = nb; t->cap = n;
+}
+
+static void ct_add1(ctab_t *t, uint32_t key)
+{
+    uint32_t i, last, mask;
+    if (t->count >= (t->cap >> 1) + (t->cap >> 2)) ct_grow(t);
+    mask = t->cap - 1;
+    i = last = ct_bucket(key, t->bits);
+    while (CT_USED(t->used, i) && t->b[i].key != key) { i = (i + 1) & mask; if (i == last) break; }
+    if (!CT_USED(t->used, i)) { t->b[i].key = key; t->b[i].val = 1; CT_SET(t->used, i); ++t->count; }
+    else ++t->b[i].val;
+}
+
 /* multiplicity-of-multiplicity summary of a sorted key array */
 static void mult_table(const uint64_t *a, uint64_t n, int64_t *cnts, int *uniq, int *single, double *avg)
 {
-    uint64_t i, run = 1, u = 0, s1 = 0;
+    uint64_t i, run = 1, u = 0;
+    uint32_t j;
+    int last_val = 0, have1 = 0;
+    ctab_t t;
+    memset(&t, 0, sizeof(t));
     memset(cnts, 0, sizeof(int64_t) * 1001);
     for (i = 1; i <= n; ++i) {
         if (i < n && a[i] == a[i - 1]) { ++run; continue; }
         cnts[run < 1000 ? run : 1000] += 1;
-        s1 += run == 1; ++u; run = 1;
+        ct_add1(&t, (uint32_t) run);
+        ++u; run = 1;
     }
-    *uniq = (int) u; *single = (int) s1; *avg = (double) n / (double) u;
+    for (j = 0; j < t.cap; ++j)
+        if (CT_USED(t.used, j)) { last_val = t.b[j].val; if (t.b[j].key == 1) have1 = 1; }
+    *single = have1 ? (int) cnts[1] : last_val;
+    *uniq = (int) u; *avg = (double) n / (double) u;
+    free(t.used); free(t.b);
 }
 
 int or_stat(const or_db_t *db, double *dout, int *iout, int64_t *s_cnts, int64_t *k_cnts)

@@ -51,6 +51,7 @@ typedef struct {
     int smer_conflict;   /* 1 if identical k-mers carried different s-mer codes (reference exits) */
 } or_scm_t;
 
+uint64_t or_debug_tie_suppressed(void);
 uint64_t or_hash64(uint64_t key, uint64_t mask);                       /* syncmer.c:116-126 */
 uint64_t or_murmur64a(const void *key, uint32_t len, uint64_t seed);   /* syncmer.c:131-170 */
 uint64_t or_kmer_hash(const uint8_t *hoco_s, uint32_t start, int k, int rev); /* syncmer.c:175-226 */

@@ -1,0 +1,51 @@
+"""CPU: the C-ABI library builds for sm_100a, loads, and exports every symbol include/syncgpu.h declares.
+No compute call is made here (there is no GPU in the build container)."""
+import os
+import re
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    txt = open(os.path.join(ROOT, "include", "syncgpu.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(sg_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_everything_the_header_declares():
+    from oatk_b200 import lib
+    L = lib.library()
+    names = declared_symbols()
+    assert len(names) >= 20
+    missing = [n for n in names if not hasattr(L, n)]
+    assert missing == []
+    assert sorted(lib.SYMBOLS) == names
+
+
+def test_strerror_and_no_device_is_loud():
+    from oatk_b200 import lib
+    L = lib.library()
+    assert L.sg_strerror(0) == b"ok"
+    assert b"smers" in L.sg_strerror(-6)
+    import torch
+    if not torch.cuda.is_available():
+        with pytest.raises(lib.SgError):
+            lib.Context(0)          # no CPU fallback: creating a context without a GPU must fail
+
+
+def test_sass_is_sm100a():
+    import subprocess
+    from oatk_b200 import lib
+    out = subprocess.run(["cuobjdump", "-lelf", lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+
+
+def test_product_does_not_touch_the_oracle():
+    """the product package must not import, link or execute anything under oracle/"""
+    pkg = os.path.join(ROOT, "oatk_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".c", ".cpp")):
+                src = open(os.path.join(dp, f), errors="ignore").read()
+                assert "pyoracle" not in src and "liboracle" not in src and "sync_oracle" not in src and "libref" not in src, f
