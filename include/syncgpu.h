@@ -155,6 +155,19 @@ int sg_count_download(sg_batch *b, const sg_count_out_t *out);
 int sg_arcs(sg_batch *b, uint32_t min_k_cov, double min_a_cov_f, uint64_t *n_arcs);  /* synchronises */
 int sg_arcs_download(sg_batch *b, uint64_t *arcs4);
 
+/* device pointers of the batch's result arrays (for device-side consumers such as the multi-GPU
+ * exchange); valid until the next call that recomputes them. n = number of elements. */
+enum { SG_BUF_KEY = 0,      /* uint64 k-mer hash, read order */
+       SG_BUF_OCC,          /* uint64 sid<<32 | idx<<1 | rev, read order */
+       SG_BUF_SMER,         /* uint64 s-mer code, read order */
+       SG_BUF_MPOS,         /* uint32 m_pos, read order */
+       SG_BUF_KID,          /* uint64 id<<1 per tuple of the counted set (read order, or adopted order) */
+       SG_BUF_SORTED_OCC,   /* uint64 occurrences in hash-sorted order = concatenated syncmer_t.m_pos */
+       SG_BUF_SCM_H,        /* uint64 per distinct k-mer */
+       SG_BUF_SCM_COV,      /* uint32 per distinct k-mer */
+       SG_BUF_ADOPTED_OCC   /* uint64 occ of the adopted tuples, adopted order */ };
+int sg_batch_buffer(sg_batch *b, int which, void **d_ptr, uint64_t *n);
+
 /* test hook: keep only the low `bits` bits of every k-mer hash when grouping, which forces hash
  * collisions so that the exact-sequence split of process_kmer_cluster is exercised. 64 = off. */
 int sg_debug_set_hash_bits(sg_batch *b, int bits);
@@ -166,6 +179,11 @@ int sg_debug_set_hash_bits(sg_batch *b, int bits);
 int sg_tuples_partition(sg_batch *b, int n_parts, uint64_t *counts /* host, n_parts */, void **d_tuples /* device ptr out */);
 /* replace this batch's tuple set by tuples received from the peers (device pointer, n tuples of 3 x uint64) */
 int sg_tuples_adopt(sg_batch *b, const void *d_tuples, uint64_t n);
+/* after sg_count on adopted tuples: (occ, (id + id_base) << 1) pairs in adopted order, 2 x uint64 each,
+ * to be sent back to the ranks the tuples came from (same split sizes, reversed) */
+int sg_ids_pack(sg_batch *b, uint64_t id_base, void **d_pairs, uint64_t *n);
+/* the pairs received back for this rank's own reads: fills k_mer[] (read order) with id << 1 */
+int sg_ids_scatter(sg_batch *b, const void *d_pairs, uint64_t n);
 
 #ifdef __cplusplus
 }

@@ -133,7 +133,9 @@ void sg_batch_destroy(sg_batch *b)
 
 static void reset_state(sg_batch *b)
 {
-    b->extracted = b->counted = b->sizes_known = b->sorted = false;
+    b->extracted = b->counted = b->sizes_known = b->sorted = b->adopted = false;
+    b->n_adopted = 0;
+    b->have_kid_local = false;
     b->k = b->s = 0;
     b->n_syncmers = 0;
 }
@@ -360,7 +362,8 @@ int sg_extract_download(sg_batch *b, const sg_extract_out_t *o)
     if (N) {
         if (o->m_pos) CK(cudaMemcpyAsync(o->m_pos, b->m_pos.p, N * 4, cudaMemcpyDeviceToHost, st));
         if (o->s_mer) CK(cudaMemcpyAsync(o->s_mer, b->s_mer.p, N * 8, cudaMemcpyDeviceToHost, st));
-        if (o->k_mer) CK(cudaMemcpyAsync(o->k_mer, b->counted ? b->kid.p : b->key.p, N * 8, cudaMemcpyDeviceToHost, st));
+        const void *ksrc = b->have_kid_local ? b->kid_local.p : ((b->counted && !b->adopted) ? b->kid.p : b->key.p);
+        if (o->k_mer) CK(cudaMemcpyAsync(o->k_mer, ksrc, N * 8, cudaMemcpyDeviceToHost, st));
         b->d2h_bytes += N * 20;
     }
     CK(cudaStreamSynchronize(st));

@@ -17,9 +17,15 @@
 // Ids are a prefix sum over class heads.
 #include "sg_common.cuh"
 #include "sg_internal.h"
+#include <cstring>
+#include <string>
+#include <vector>
+#include <algorithm>
 #include "sg_host.h"
 
 namespace sg {
+
+__global__ void __launch_bounds__(256) run_heads_kernel(const uint64_t *k, uint64_t n, int shift, uint32_t *head);
 
 __global__ void __launch_bounds__(256) tuple_init_kernel(const uint64_t *key, uint64_t *skey, uint64_t *sval, uint64_t n, uint64_t hmask)
 {
@@ -251,18 +257,18 @@ static int ensure_sorted(sg_batch *b)
     sg_ctx *ctx = b->ctx;
     if (b->sorted) return SG_OK;
     cudaStream_t st = ctx->stream;
-    const uint64_t N = b->n_syncmers;
+    const uint64_t N = b->t_n();
     RS(b->skey, (N + 1) * 8); RS(b->sval, (N + 1) * 8); RS(b->skey_alt, (N + 1) * 8); RS(b->sval_alt, (N + 1) * 8);
     RS(b->sort_tmp, sort_tmp_words(N) * 4);
     RS(b->socc, (N + 1) * 8); RS(b->ssmer, (N + 1) * 8);
     ctx->t_begin(SG_T_SORT);
     const uint64_t hmask = b->hash_bits >= 64 ? ~0ull : ((1ull << b->hash_bits) - 1);
-    tuple_init_kernel<<<nblk(N, 256), 256, 0, st>>>((const uint64_t *) b->key.p, (uint64_t *) b->skey.p, (uint64_t *) b->sval.p, N, hmask);
+    tuple_init_kernel<<<nblk(N, 256), 256, 0, st>>>(b->t_key(), (uint64_t *) b->skey.p, (uint64_t *) b->sval.p, N, hmask);
     ctx->count_launch(SG_T_SORT, 1);
     LAUNCHED(SG_T_SORT, launch_sort_pairs((uint64_t *) b->skey.p, (uint64_t *) b->sval.p, (uint64_t *) b->skey_alt.p,
             (uint64_t *) b->sval_alt.p, N, 0, b->hash_bits >= 64 ? 64 : ((b->hash_bits + 7) & ~7), (uint32_t *) b->sort_tmp.p, st));
-    tuple_gather_kernel<<<nblk(N, 256), 256, 0, st>>>((const uint64_t *) b->sval.p, (const uint64_t *) b->occ.p,
-            (const uint64_t *) b->s_mer.p, (uint64_t *) b->socc.p, (uint64_t *) b->ssmer.p, N);
+    tuple_gather_kernel<<<nblk(N, 256), 256, 0, st>>>((const uint64_t *) b->sval.p, b->t_occ(),
+            b->t_smer(), (uint64_t *) b->socc.p, (uint64_t *) b->ssmer.p, N);
     ctx->count_launch(SG_T_SORT, 1);
     ctx->t_end(SG_T_SORT);
     CK(cudaGetLastError());
@@ -274,6 +280,8 @@ static int ensure_sorted(sg_batch *b)
 static int mult_table(sg_batch *b, const uint64_t *sorted, uint64_t N, int shift, unsigned long long *d_hist, uint64_t *groups)
 {
     sg_ctx *ctx = b->ctx;
+    *groups = 0;
+    if (N == 0) return SG_OK;
     cudaStream_t st = ctx->stream;
     RS(b->flags, (N + 1) * 4); RS(b->ids, (N + 2) * 8); RS(b->ids_tmp, scan_tmp_words(N) * 8);
     RS(b->starts, (N + 2) * 8);
@@ -308,9 +316,9 @@ int sg_stat(sg_batch *b, sg_stat_t *out)
     cudaStream_t st = ctx->stream;
     CK(cudaSetDevice(ctx->device));
     memset(out, 0, sizeof(*out));
-    const uint64_t N = b->n_syncmers;
-    out->n_syncmers = N;
-    if (N == 0) return SG_E_EMPTY;                                  // "empty syncmer collection", syncmer.c:909-912
+    const uint64_t N = b->t_n();
+    out->n_syncmers = b->n_syncmers;
+    if (N == 0 && b->n_syncmers == 0) return SG_E_EMPTY;            // "empty syncmer collection", syncmer.c:909-912
     int rc = ensure_sorted(b);
     if (rc) return rc;
     ctx->t_begin(SG_T_STAT);
@@ -323,12 +331,13 @@ int sg_stat(sg_batch *b, sg_stat_t *out)
     if (rc) return rc;
     // s-mer codes: a second sort, values unused
     RS(b->skey2, (N + 1) * 8); RS(b->sval2, (N + 1) * 8);
-    CK(cudaMemcpyAsync(b->skey2.p, b->s_mer.p, N * 8, cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(b->skey2.p, b->t_smer(), N * 8, cudaMemcpyDeviceToDevice, st));
     LAUNCHED(SG_T_STAT, launch_sort_pairs((uint64_t *) b->skey2.p, (uint64_t *) b->sval2.p, (uint64_t *) b->skey_alt.p,
             (uint64_t *) b->sval_alt.p, N, 0, 64, (uint32_t *) b->sort_tmp.p, st));
     rc = mult_table(b, (const uint64_t *) b->skey2.p, N, 0, d, &gs);
     if (rc) return rc;
-    gap_kernel<<<std::min<unsigned>(nblk(N, 256), 1184u), 256, 0, st>>>((const uint64_t *) b->occ.p, (const uint32_t *) b->m_pos.p, N, b->k, d + 2002);
+    // gaps are a property of the local reads whichever tuple set is being counted
+    if (b->n_syncmers) gap_kernel<<<std::min<unsigned>(nblk(b->n_syncmers, 256), 1184u), 256, 0, st>>>((const uint64_t *) b->occ.p, (const uint32_t *) b->m_pos.p, b->n_syncmers, b->k, d + 2002);
     ctx->count_launch(SG_T_STAT, 1);
     ctx->t_end(SG_T_STAT);
     std::vector<unsigned long long> h(2 * 1001 + 4);
@@ -350,7 +359,7 @@ int sg_count(sg_batch *b)
     sg_ctx *ctx = b->ctx;
     cudaStream_t st = ctx->stream;
     CK(cudaSetDevice(ctx->device));
-    const uint64_t N = b->n_syncmers;
+    const uint64_t N = b->t_n();
     if (N == 0) return SG_E_EMPTY;                                  // reference returns NULL, syncmer.c:1414-1417
     int rc = ensure_sorted(b);
     if (rc) return rc;
@@ -366,20 +375,26 @@ int sg_count(sg_batch *b)
         CK(cudaMemcpyAsync(b->flags.p, &one, 4, cudaMemcpyHostToDevice, st));
     }
     VerifyArgs V;
+    memset(&V, 0, sizeof(V));
     V.skey = (const uint64_t *) b->skey.p; V.sval = (const uint64_t *) b->sval.p; V.socc = (const uint64_t *) b->socc.p;
     V.m_pos = (const uint32_t *) b->m_pos.p; V.hoff = (const uint64_t *) b->hoff.p; V.hoco_s = (const uint8_t *) b->hoco_s.p;
     V.hoco_l = (const uint32_t *) b->hoco_l.p; V.sid_base = b->sid_base; V.n = N; V.k = b->k;
     V.newid = (uint32_t *) b->flags.p; V.differs = (uint8_t *) b->differs.p; V.status = status;
-    {
+    if (!b->adopted) {
         const uint64_t warps = (N + 30) / 31 + 1;
         verify_kernel<<<nblk(warps * 32, 256), 256, 0, st>>>(V);
+        ctx->count_launch(SG_T_GROUP, 1);
+    } else {
+        // tuples adopted from other GPUs: their reads are not here, so groups are formed on the 64-bit
+        // hash alone (DESIGN.md section 7 discusses the 2^-64 residual)
+        run_heads_kernel<<<nblk(N, 256), 256, 0, st>>>((const uint64_t *) b->skey.p, N, 0, (uint32_t *) b->flags.p);
         ctx->count_launch(SG_T_GROUP, 1);
     }
     unsigned long long hs[4];
     CK(cudaMemcpyAsync(hs, status, sizeof(hs), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     b->n_collisions = 0;
-    if (hs[1]) {
+    if (hs[1] && !b->adopted) {
         // some hash group holds more than one k-mer: rebuild those groups the way process_kmer_cluster does
         RS(b->cls, (N + 1) * 4);
         SplitArgs S;
@@ -417,11 +432,29 @@ int sg_count(sg_batch *b)
     return SG_OK;
 }
 
+int sg_batch_buffer(sg_batch *b, int which, void **ptr, uint64_t *n)
+{
+    if (!b || !ptr || !n) return SG_E_ARG;
+    switch (which) {
+        case SG_BUF_KEY: *ptr = b->key.p; *n = b->n_syncmers; break;
+        case SG_BUF_OCC: *ptr = b->occ.p; *n = b->n_syncmers; break;
+        case SG_BUF_SMER: *ptr = b->s_mer.p; *n = b->n_syncmers; break;
+        case SG_BUF_MPOS: *ptr = b->m_pos.p; *n = b->n_syncmers; break;
+        case SG_BUF_KID: *ptr = b->kid.p; *n = b->counted ? b->t_n() : 0; break;
+        case SG_BUF_SORTED_OCC: *ptr = b->socc.p; *n = b->sorted ? b->t_n() : 0; break;
+        case SG_BUF_SCM_H: *ptr = b->scm_h.p; *n = b->counted ? b->n_unique : 0; break;
+        case SG_BUF_SCM_COV: *ptr = b->scm_cov.p; *n = b->counted ? b->n_unique : 0; break;
+        case SG_BUF_ADOPTED_OCC: *ptr = b->aocc.p; *n = b->n_adopted; break;
+        default: return SG_E_ARG;
+    }
+    return SG_OK;
+}
+
 int sg_count_sizes(sg_batch *b, sg_count_sizes_t *out)
 {
     if (!b || !out) return SG_E_ARG;
     if (!b->counted) return SG_E_STATE;
-    out->n_syncmers = b->n_syncmers;
+    out->n_syncmers = b->t_n();
     out->n_unique = b->n_unique;
     out->n_hash_collisions = b->n_collisions;
     return SG_OK;
@@ -434,7 +467,7 @@ int sg_count_download(sg_batch *b, const sg_count_out_t *o)
     sg_ctx *ctx = b->ctx;
     cudaStream_t st = ctx->stream;
     CK(cudaSetDevice(ctx->device));
-    const uint64_t N = b->n_syncmers, U = b->n_unique;
+    const uint64_t N = b->t_n(), U = b->n_unique;
     if (o->h) CK(cudaMemcpyAsync(o->h, b->scm_h.p, U * 8, cudaMemcpyDeviceToHost, st));
     if (o->s) CK(cudaMemcpyAsync(o->s, b->scm_s.p, U * 8, cudaMemcpyDeviceToHost, st));
     if (o->cov) CK(cudaMemcpyAsync(o->cov, b->scm_cov.p, U * 4, cudaMemcpyDeviceToHost, st));

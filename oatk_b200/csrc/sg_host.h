@@ -63,8 +63,18 @@ struct sg_batch {
     sg::DevBuf scm_h, scm_s, scm_cov, scm_occ_off, status;
     uint64_t n_unique = 0, n_collisions = 0;
     // a7
-    sg::DevBuf arc_keys, arc_vals, arc_out;
-    uint64_t n_arcs = 0;
+    sg::DevBuf arc_keys, arc_vals, arc_out, arc_okey, arc_oval, arc_okey_alt, arc_oval_alt;
+    uint64_t n_arcs = 0, arc_cap = 0;
+    // multi-GPU exchange: tuples adopted from the peers replace the local tuple set for a5/a6
+    sg::DevBuf tuples, part_counts, akey, aocc, asmer, kid_local;
+    bool have_kid_local = false;
+    bool adopted = false;
+    uint64_t n_adopted = 0;
+    // the tuple set a5/a6 work on
+    const uint64_t *t_key() const { return (const uint64_t *) (adopted ? akey.p : key.p); }
+    const uint64_t *t_occ() const { return (const uint64_t *) (adopted ? aocc.p : occ.p); }
+    const uint64_t *t_smer() const { return (const uint64_t *) (adopted ? asmer.p : s_mer.p); }
+    uint64_t t_n() const { return adopted ? n_adopted : n_syncmers; }
 };
 
 namespace sg {

@@ -1,7 +1,7 @@
 // sg_scan.cu -- kernel 1b: rolling s-mer hash, k-window minimum, closed-syncmer selection.
 //
 // Replaces the minimiser/emission part of the reference's per-read loop (reference
-// syncmer.c:276-283, 307-394) with the stateless rules of oracle/sync_oracle.c:
+// syncmer.c:276-283, 307-394) with the stateless rules derived in DESIGN.md section 3:
 //
 //   m[p]     hash64 of the canonical s-mer ending at hoco position p, or NONE
 //   mo(p)    min m[p-q+1 .. p-1],  e(p) = m[p-q],  q = k-s+1

@@ -56,7 +56,8 @@ SYMBOLS = [
     "sg_batch_create", "sg_batch_destroy", "sg_batch_set_reads_host", "sg_batch_set_reads_device",
     "sg_batch_set_sid_base", "sg_extract", "sg_extract_sizes", "sg_extract_download",
     "sg_stat", "sg_count", "sg_count_sizes", "sg_count_download", "sg_arcs", "sg_arcs_download",
-    "sg_tuples_partition", "sg_tuples_adopt", "sg_debug_set_hash_bits",
+    "sg_tuples_partition", "sg_tuples_adopt", "sg_debug_set_hash_bits", "sg_batch_buffer",
+    "sg_ids_pack", "sg_ids_scatter",
 ]
 
 
@@ -95,7 +96,8 @@ def _lib():
                        ("sg_count_sizes", [vp, C.POINTER(CountSizes)]), ("sg_count_download", [vp, C.POINTER(CountOut)]),
                        ("sg_arcs", [vp, C.c_uint32, C.c_double, C.POINTER(u64)]), ("sg_arcs_download", [vp, vp]),
                        ("sg_tuples_partition", [vp, i32, vp, C.POINTER(vp)]), ("sg_tuples_adopt", [vp, vp, u64]),
-                       ("sg_debug_set_hash_bits", [vp, i32])):
+                       ("sg_debug_set_hash_bits", [vp, i32]), ("sg_batch_buffer", [vp, i32, C.POINTER(vp), C.POINTER(u64)]),
+                       ("sg_ids_pack", [vp, u64, C.POINTER(vp), C.POINTER(u64)]), ("sg_ids_scatter", [vp, vp, u64])):
         if hasattr(L, name):
             getattr(L, name).argtypes = args
     _LIB = L
@@ -249,6 +251,31 @@ class Batch:
         if n.value:
             _ck(self.ctx.h, _lib().sg_arcs_download(self.h, out.ctypes.data), "sg_arcs_download")
         return out
+
+    BUF = dict(key=0, occ=1, smer=2, mpos=3, kid=4, sorted_occ=5, scm_h=6, scm_cov=7, adopted_occ=8)
+
+    def buffer(self, which):
+        """(device pointer, element count) of one of the batch's device arrays"""
+        p, n = C.c_void_p(), C.c_uint64()
+        _ck(self.ctx.h, _lib().sg_batch_buffer(self.h, self.BUF[which], C.byref(p), C.byref(n)), "sg_batch_buffer")
+        return p.value or 0, n.value
+
+    def tuples_partition(self, n_parts):
+        counts = (C.c_uint64 * n_parts)()
+        p = C.c_void_p()
+        _ck(self.ctx.h, _lib().sg_tuples_partition(self.h, n_parts, counts, C.byref(p)), "sg_tuples_partition")
+        return [int(x) for x in counts], p.value or 0
+
+    def tuples_adopt(self, d_ptr, n):
+        _ck(self.ctx.h, _lib().sg_tuples_adopt(self.h, d_ptr, n), "sg_tuples_adopt")
+
+    def ids_pack(self, id_base):
+        p, n = C.c_void_p(), C.c_uint64()
+        _ck(self.ctx.h, _lib().sg_ids_pack(self.h, id_base, C.byref(p), C.byref(n)), "sg_ids_pack")
+        return p.value or 0, n.value
+
+    def ids_scatter(self, d_ptr, n):
+        _ck(self.ctx.h, _lib().sg_ids_scatter(self.h, d_ptr, n), "sg_ids_scatter")
 
     def debug_set_hash_bits(self, bits):
         _ck(self.ctx.h, _lib().sg_debug_set_hash_bits(self.h, bits), "sg_debug_set_hash_bits")
