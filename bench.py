@@ -214,7 +214,7 @@ def main():
     W = max(args.warmup, 3)
     n_reads = args.reads
 
-    bases, off = synth_gpu.hifi_reads_gpu(1 + rank, 50_000_000, n_reads, READ_LEN, ERR, dev)
+    bases, off = synth_gpu.hifi_reads_gpu(1000 + rank, 50_000_000, n_reads, READ_LEN, ERR, dev, genome_seed=1)
     total = n_reads * READ_LEN
     torch.cuda.synchronize()
 
@@ -233,6 +233,8 @@ def main():
             exchange.run(batch)
         st = batch.stat()
         batch.count()
+        if exchange is not None:
+            exchange.return_ids(batch, batch.count_sizes().n_unique)
         return st
 
     for _ in range(W):

@@ -8,11 +8,12 @@ here only to fill device memory; nothing on the measured path goes through it.
 import torch
 
 
-def hifi_reads_gpu(seed, genome_len, n_reads, read_len, err, device, chunk=16384):
+def hifi_reads_gpu(seed, genome_len, n_reads, read_len, err, device, chunk=16384, genome_seed=None):
     """returns (bases uint8 [n_reads*read_len] on device, offsets uint64-as-int64 [n_reads+1] on device)"""
     g = torch.Generator(device=device)
-    g.manual_seed(seed)
+    g.manual_seed(seed if genome_seed is None else genome_seed)      # all ranks sequence the same genome
     genome = torch.randint(0, 4, (genome_len,), dtype=torch.uint8, device=device, generator=g)
+    g.manual_seed(seed)
     lut = torch.tensor([65, 67, 71, 84], dtype=torch.uint8, device=device)
     out = torch.empty(n_reads * read_len, dtype=torch.uint8, device=device)
     for r0 in range(0, n_reads, chunk):
