@@ -1,0 +1,358 @@
+/*
+ * syncmer_gpu.c -- the reference's syncmer.h functions for the hot path, implemented
+ * over the C ABI of libsyncgpu.so (include/syncgpu.h). Host code only: it moves
+ * flat device results into the reference's data structures and prints what the
+ * reference prints. No sequence arithmetic happens here.
+ */
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+#include <pthread.h>
+#include "syncgpu.h"
+#include "syncmer_gpu.h"
+
+const unsigned char seq_nt4_table[256] = {
+#define R16(x) x, x, x, x, x, x, x, x, x, x, x, x, x, x, x, x
+    0, 1, 2, 3, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, R16(4), R16(4), R16(4),
+    4, 0, 4, 1, 4, 4, 4, 2, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 3, 3, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4,
+    4, 0, 4, 1, 4, 4, 4, 2, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 3, 3, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4,
+    R16(4), R16(4), R16(4), R16(4), R16(4), R16(4), R16(4), R16(4)
+#undef R16
+};
+const char char_nt4_table[4] = {'A', 'C', 'G', 'T'};
+
+/* one device context for the process, one live batch per sr_db_t */
+static sg_ctx *g_ctx;
+static int g_device;
+typedef struct reg_s { sr_db_t *db; sg_batch *b; struct reg_s *next; } reg_t;
+static reg_t *g_reg;
+static pthread_mutex_t g_lock = PTHREAD_MUTEX_INITIALIZER;
+
+int oatk_gpu_set_device(int device) { g_device = device; return 0; }
+
+static sg_batch *batch_of(sr_db_t *db, int create)
+{
+    reg_t *r;
+    sg_batch *b = 0;
+    pthread_mutex_lock(&g_lock);
+    for (r = g_reg; r; r = r->next) if (r->db == db) { b = r->b; break; }
+    if (!b && create) {
+        if (!g_ctx && sg_ctx_create(g_device, &g_ctx) != SG_OK) {
+            fprintf(stderr, "[E::%s] no usable CUDA device %d (libsyncgpu has no CPU path)\n", __func__, g_device);
+        } else if (sg_batch_create(g_ctx, &b) == SG_OK) {
+            r = (reg_t *) malloc(sizeof(reg_t));
+            r->db = db; r->b = b; r->next = g_reg; g_reg = r;
+        }
+    }
+    pthread_mutex_unlock(&g_lock);
+    return b;
+}
+
+static void batch_drop(sr_db_t *db)
+{
+    reg_t **pp, *r;
+    pthread_mutex_lock(&g_lock);
+    for (pp = &g_reg; (r = *pp); pp = &r->next)
+        if (r->db == db) { *pp = r->next; sg_batch_destroy(r->b); free(r); break; }
+    pthread_mutex_unlock(&g_lock);
+}
+
+void oatk_gpu_shutdown(void)
+{
+    pthread_mutex_lock(&g_lock);
+    while (g_reg) { reg_t *r = g_reg; g_reg = r->next; sg_batch_destroy(r->b); free(r); }
+    if (g_ctx) { sg_ctx_destroy(g_ctx); g_ctx = 0; }
+    pthread_mutex_unlock(&g_lock);
+}
+
+void sr_db_init(sr_db_t *sr_db, int k, int s)
+{
+    if (!sr_db) return;
+    sr_db->n = sr_db->m = 0;
+    sr_db->a = 0;
+    sr_db->k = k;
+    sr_db->s = s;
+    sr_db->stats = 0;
+}
+
+static void *dup_block(const void *src, size_t bytes)
+{
+    void *p;
+    if (!bytes) return 0;                 /* kvec semantics: an empty array is NULL */
+    p = malloc(bytes);
+    memcpy(p, src, bytes);
+    return p;
+}
+
+int sr_read_mem(sr_db_t *sr_db, const char *bases, const uint64_t *off, char **names, uint64_t n_reads)
+{
+    sg_batch *b;
+    sg_extract_sizes_t z;
+    sg_extract_out_t o;
+    int rc, k = sr_db->k, s = sr_db->s;
+    uint64_t i, ia = 0, il = 0;
+    uint32_t *hoco_l = 0, *n_scm = 0, *m_pos = 0, *amb_sid = 0, *amb_pos = 0, *lrl_sid = 0, *lrl_idx = 0, *lrl_val = 0;
+    uint64_t *hs_off = 0, *rl_off = 0, *scm_off = 0, *s_mer = 0, *k_mer = 0;
+    uint8_t *hs = 0, *rl = 0;
+
+    sr_db_clean(sr_db);
+    sr_db_init(sr_db, k, s);
+    b = batch_of(sr_db, 1);
+    if (!b) return SG_E_CUDA;
+    if ((rc = sg_batch_set_reads_host(b, bases, off, n_reads)) != SG_OK ||
+            (rc = sg_extract(b, k, s)) != SG_OK || (rc = sg_extract_sizes(b, &z)) != SG_OK) {
+        fprintf(stderr, "[E::%s] %s: %s\n", __func__, sg_strerror(rc), sg_last_error(g_ctx));
+        return rc;
+    }
+#define NEW(p, n) ((p) = malloc(sizeof(*(p)) * ((n) + 1)))
+    NEW(hoco_l, n_reads); NEW(n_scm, n_reads); NEW(hs_off, n_reads + 1); NEW(rl_off, n_reads + 1); NEW(scm_off, n_reads + 1);
+    NEW(hs, z.hoco_s_bytes); NEW(rl, z.ho_rl_bytes);
+    NEW(m_pos, z.n_syncmers); NEW(s_mer, z.n_syncmers); NEW(k_mer, z.n_syncmers);
+    NEW(amb_sid, z.n_ambiguous); NEW(amb_pos, z.n_ambiguous);
+    NEW(lrl_sid, z.n_long_runs); NEW(lrl_idx, z.n_long_runs); NEW(lrl_val, z.n_long_runs);
+#undef NEW
+    memset(&o, 0, sizeof(o));
+    o.hoco_l = hoco_l; o.n_scm = n_scm; o.hoco_s_off = hs_off; o.ho_rl_off = rl_off; o.scm_off = scm_off;
+    o.hoco_s_buf = hs; o.ho_rl_buf = rl; o.m_pos = m_pos; o.s_mer = s_mer; o.k_mer = k_mer;
+    o.amb_sid = amb_sid; o.amb_pos = amb_pos; o.lrl_sid = lrl_sid; o.lrl_idx = lrl_idx; o.lrl_val = lrl_val;
+    if ((rc = sg_extract_download(b, &o)) != SG_OK) {
+        fprintf(stderr, "[E::%s] %s: %s\n", __func__, sg_strerror(rc), sg_last_error(g_ctx));
+        goto done;
+    }
+    sr_db->a = (sr_t *) calloc(n_reads ? n_reads : 1, sizeof(sr_t));
+    sr_db->n = sr_db->m = n_reads;
+    for (i = 0; i < n_reads; ++i) {
+        sr_t *r = &sr_db->a[i];
+        uint64_t a0 = ia, l0 = il;
+        char nm[32];
+        r->sid = i;                                             /* asserted by the reference, syncmer.c:1407 */
+        if (names && names[i]) r->sname = strdup(names[i]);
+        else { snprintf(nm, sizeof(nm), "r%lu", (unsigned long) i); r->sname = strdup(nm); }
+        r->hoco_l = hoco_l[i];
+        r->hoco_s = (uint8_t *) dup_block(hs + hs_off[i], (hoco_l[i] + 3) / 4);
+        r->ho_rl = (uint8_t *) dup_block(rl + rl_off[i], hoco_l[i]);
+        while (ia < z.n_ambiguous && amb_sid[ia] == i) ++ia;
+        r->n_nucl = (uint32_t *) dup_block(amb_pos + a0, 4 * (ia - a0));
+        while (il < z.n_long_runs && lrl_sid[il] == i) ++il;
+        r->ho_l_rl = (uint32_t *) dup_block(lrl_val + l0, 4 * (il - l0));
+        r->n = n_scm[i];
+        r->m_pos = (uint32_t *) dup_block(m_pos + scm_off[i], 4 * (size_t) r->n);
+        r->s_mer = (uint64_t *) dup_block(s_mer + scm_off[i], 8 * (size_t) r->n);
+        r->k_mer = (uint64_t *) dup_block(k_mer + scm_off[i], 8 * (size_t) r->n);
+    }
+done:
+    free(hoco_l); free(n_scm); free(hs_off); free(rl_off); free(scm_off); free(hs); free(rl);
+    free(m_pos); free(s_mer); free(k_mer); free(amb_sid); free(amb_pos); free(lrl_sid); free(lrl_idx); free(lrl_val);
+    return rc;
+}
+
+int sr_db_validate(sr_db_t *sr_db)
+{
+    size_t i;
+    if (sr_db->n > MAX_RD_NUM) {
+        fprintf(stderr, "[E::%s] read number exceeds the limit %llu\n", __func__, MAX_RD_NUM);
+        return 1;
+    }
+    for (i = 0; i < sr_db->n; ++i)
+        if (sr_db->a[i].n > MAX_RD_SCM) {
+            fprintf(stderr, "[E::%s] syncmer number (%u) on read exceeds the limit %llu: %s\n", __func__,
+                    sr_db->a[i].n, MAX_RD_SCM, sr_db->a[i].sname);
+            return 2;
+        }
+    return 0;
+}
+
+/* peak finder the reference borrows from hifiasm (syncmer.c:775-865): lowest point from the left,
+ * highest peak after it, then a smaller peak on either side that is separated by a real valley */
+static int find_peaks(int n, int start_cnt, const int64_t *cnt, int *peak_het)
+{
+    int i, low, top, left = -1, right = -1;
+    int64_t vtop, vleft = -1, vright = -1, mn;
+    *peak_het = -1;
+    low = cnt[1] > 0 ? 1 : 2;
+    if (low < start_cnt) low = start_cnt;
+    for (i = low + 1; i < n && cnt[i] <= cnt[i - 1]; ++i) {}
+    low = i - 1;
+    if (low == n - 1) return -1;
+    top = low + 1; vtop = cnt[top];
+    for (i = low + 1; i < n; ++i) if (cnt[i] > vtop) vtop = cnt[i], top = i;
+    for (i = top - 1; i > low; --i)
+        if (cnt[i] >= cnt[i - 1] && cnt[i] >= cnt[i + 1] && cnt[i] > vleft) vleft = cnt[i], left = i;
+    if (left > low && left < top) {
+        for (i = left + 1, mn = vtop; i < top; ++i) if (cnt[i] < mn) mn = cnt[i];
+        if (vleft < vtop * 0.05 || mn > vleft * 0.95) vleft = -1, left = -1;
+    }
+    for (i = top + 1; i < n - 1; ++i)
+        if (cnt[i] >= cnt[i - 1] && cnt[i] >= cnt[i + 1] && cnt[i] > vright) vright = cnt[i], right = i;
+    if (right > top) {
+        for (i = top + 1, mn = vtop; i < right; ++i) if (cnt[i] < mn) mn = cnt[i];
+        if (vright < vtop * 0.05 || mn > vright * 0.95 || right > top * 2.5) vright = -1, right = -1;
+    }
+    if (right > 0) { *peak_het = top; return right; }
+    if (left > 0) *peak_het = left;
+    return top;
+}
+
+void sr_db_stat(sr_db_t *sr_db, FILE *fo, int more)
+{
+    sg_batch *b = batch_of(sr_db, 0);
+    sg_stat_t st;
+    sr_stat_t *s;
+    int rc;
+    (void) more;
+    if (!sr_db->stats) sr_db->stats = (sr_stat_t *) calloc(1, sizeof(sr_stat_t));
+    s = sr_db->stats;
+    if (!b) { fprintf(stderr, "[E::%s] the read database was not produced by sr_read_mem\n", __func__); return; }
+    rc = sg_stat(b, &st);
+    if (rc == SG_E_EMPTY) { fprintf(fo, "[M::%s] empty syncmer collection\n", __func__); return; }   /* syncmer.c:909-912 */
+    if (rc != SG_OK) { fprintf(stderr, "[E::%s] %s: %s\n", __func__, sg_strerror(rc), sg_last_error(g_ctx)); return; }
+    s->syncmer_n = st.n_syncmers;
+    s->syncmer_per_read = (double) st.n_syncmers / (double) sr_db->n;
+    s->syncmer_avg_dist = (double) st.gap_sum / (double) st.n_gaps;
+    s->smer_unique = (int) st.smer_unique; s->smer_singleton = (int) st.smer_singleton;
+    s->smer_avg_cnt = (double) st.n_syncmers / (double) st.smer_unique;
+    s->kmer_unique = (int) st.kmer_unique; s->kmer_singleton = (int) st.kmer_singleton;
+    s->kmer_avg_cnt = (double) st.n_syncmers / (double) st.kmer_unique;
+    s->smer_peak_hom = find_peaks(1001, 5, st.smer_cnts, &s->smer_peak_het);
+    s->kmer_peak_hom = find_peaks(1001, 5, st.kmer_cnts, &s->kmer_peak_het);
+    fprintf(fo, "[M::%s] number syncmers collected: %lu\n", __func__, (unsigned long) s->syncmer_n);
+    fprintf(fo, "[M::%s] number syncmers per read: %.3f\n", __func__, s->syncmer_per_read);
+    fprintf(fo, "[M::%s] average kmer space: %.3f\n", __func__, s->syncmer_avg_dist);
+    fprintf(fo, "[M::%s] number uniqe smer: %d; singletons: %d (%.3f%%)\n", __func__, s->smer_unique, s->smer_singleton,
+            (double) s->smer_singleton * 100 / s->smer_unique);
+    fprintf(fo, "[M::%s] average smer count: %.3f\n", __func__, s->smer_avg_cnt);
+    fprintf(fo, "[M::%s] smer peak_hom: %d; peak_het: %d\n", __func__, s->smer_peak_hom, s->smer_peak_het);
+    fprintf(fo, "[M::%s] number uniqe kmer: %d; singletons: %d (%.3f%%)\n", __func__, s->kmer_unique, s->kmer_singleton,
+            (double) s->kmer_singleton * 100 / s->kmer_unique);
+    fprintf(fo, "[M::%s] average kmer count: %.3f\n", __func__, s->kmer_avg_cnt);
+    fprintf(fo, "[M::%s] kmer peak_hom: %d; peak_het: %d\n", __func__, s->kmer_peak_hom, s->kmer_peak_het);
+}
+
+syncmer_db_t *collect_syncmer_from_reads(sr_db_t *sr_db)
+{
+    sg_batch *b = batch_of(sr_db, 0);
+    sg_count_sizes_t z;
+    sg_count_out_t o;
+    syncmer_db_t *db;
+    uint64_t *h, *s, *off, *occ, *kid, i, p;
+    uint32_t *cov;
+    int rc;
+    if (!b) { fprintf(stderr, "[E::%s] the read database was not produced by sr_read_mem\n", __func__); return 0; }
+    rc = sg_count(b);
+    if (rc == SG_E_EMPTY) return 0;                            /* syncmer.c:1414-1417 */
+    if (rc == SG_E_SMER_CONFLICT) {
+        fprintf(stderr, "[E::%s] identical kmers have different smers\n", __func__);   /* the reference exits here */
+        return 0;
+    }
+    if (rc != SG_OK || (rc = sg_count_sizes(b, &z)) != SG_OK) {
+        fprintf(stderr, "[E::%s] %s: %s\n", __func__, sg_strerror(rc), sg_last_error(g_ctx));
+        return 0;
+    }
+    h = malloc(8 * (z.n_unique + 1)); s = malloc(8 * (z.n_unique + 1)); cov = malloc(4 * (z.n_unique + 1));
+    off = malloc(8 * (z.n_unique + 2)); occ = malloc(8 * (z.n_syncmers + 1)); kid = malloc(8 * (z.n_syncmers + 1));
+    o.h = h; o.s = s; o.cov = cov; o.occ_off = off; o.occ = occ; o.k_mer_id = kid;
+    if ((rc = sg_count_download(b, &o)) != SG_OK) {
+        fprintf(stderr, "[E::%s] %s: %s\n", __func__, sg_strerror(rc), sg_last_error(g_ctx));
+        free(h); free(s); free(cov); free(off); free(occ); free(kid);
+        return 0;
+    }
+    db = (syncmer_db_t *) malloc(sizeof(syncmer_db_t));
+    db->n = db->m = z.n_unique;
+    db->a = (syncmer_t *) malloc(sizeof(syncmer_t) * (z.n_unique ? z.n_unique : 1));
+    db->c = (uint16_t *) malloc(sizeof(uint16_t) * (z.n_unique ? z.n_unique : 1));
+    db->h = 0;
+    for (i = 0; i < z.n_unique; ++i) {
+        syncmer_t *m = &db->a[i];
+        m->h = h[i]; m->s = s[i]; m->cov = cov[i]; m->del = 0;
+        m->m_pos = (uint64_t *) malloc(8 * (size_t) cov[i]);
+        memcpy(m->m_pos, occ + off[i], 8 * (size_t) cov[i]);
+        db->c[i] = 1;                                           /* syncmer.c:1443 */
+    }
+    /* k_mer[] now carries id << 1 (syncmer.c:1378) */
+    for (i = 0, p = 0; i < sr_db->n; ++i) {
+        sr_t *r = &sr_db->a[i];
+        if (r->n) memcpy(r->k_mer, kid + p, 8 * (size_t) r->n);
+        p += r->n;
+    }
+    free(h); free(s); free(cov); free(off); free(occ); free(kid);
+    return db;
+}
+
+int syncmer_graph_arcs(sr_db_t *sr_db, syncmer_db_t *scm_db, uint32_t min_k_cov, double min_a_cov_f, uint64_t **arcs4, uint64_t *n_arcs)
+{
+    sg_batch *b = batch_of(sr_db, 0);
+    int rc;
+    (void) scm_db;
+    *arcs4 = 0; *n_arcs = 0;
+    if (!b) return SG_E_STATE;
+    if ((rc = sg_arcs(b, min_k_cov, min_a_cov_f, n_arcs)) != SG_OK) return rc;
+    *arcs4 = (uint64_t *) malloc(32 * (*n_arcs + 1));
+    return sg_arcs_download(b, *arcs4);
+}
+
+void sr_destroy(sr_t *sr)
+{
+    if (!sr) return;
+    free(sr->sname); free(sr->hoco_s); free(sr->ho_rl); free(sr->ho_l_rl); free(sr->n_nucl);
+    free(sr->s_mer); free(sr->k_mer); free(sr->m_pos);
+}
+
+void sr_db_clean(sr_db_t *sr_db)
+{
+    size_t i;
+    if (!sr_db) return;
+    for (i = 0; i < sr_db->n; ++i) sr_destroy(&sr_db->a[i]);
+    free(sr_db->a);
+    free(sr_db->stats);
+    sr_db->a = 0; sr_db->stats = 0; sr_db->n = sr_db->m = 0;
+    batch_drop(sr_db);
+}
+
+void sr_db_destroy(sr_db_t *sr_db)
+{
+    if (!sr_db) return;
+    sr_db_clean(sr_db);
+    free(sr_db);
+}
+
+void syncmer_db_init(syncmer_db_t *scm_db)
+{
+    if (!scm_db) return;
+    scm_db->n = scm_db->m = 0; scm_db->a = 0; scm_db->c = 0; scm_db->h = 0;
+}
+
+void syncmer_db_clean(syncmer_db_t *scm_db)
+{
+    size_t i;
+    if (!scm_db) return;
+    for (i = 0; i < scm_db->n; ++i) free(scm_db->a[i].m_pos);
+    free(scm_db->a); free(scm_db->c); free(scm_db->h);
+}
+
+void syncmer_db_destroy(syncmer_db_t *scm_db)
+{
+    if (!scm_db) return;
+    syncmer_db_clean(scm_db);
+    free(scm_db);
+}
+
+static inline int hoco_base(const uint8_t *hs, uint32_t p) { return (hs[p >> 2] >> ((3 - (p & 3)) << 1)) & 3; }
+
+void get_kmer_seq(uint8_t *hoco_s, uint32_t pos, int l, uint32_t rev, uint8_t *kmer_s)
+{
+    int i;
+    for (i = 0; i < l; ++i) kmer_s[i] = (uint8_t) (rev ? 3 - hoco_base(hoco_s, pos + l - 1 - i) : hoco_base(hoco_s, pos + i));
+}
+
+void get_kmer_dna_seq(uint8_t *hoco_s, uint32_t pos, int l, uint32_t rev, char *dna_seq)
+{
+    int i;
+    for (i = 0; i < l; ++i) dna_seq[i] = char_nt4_table[rev ? 3 - hoco_base(hoco_s, pos + l - 1 - i) : hoco_base(hoco_s, pos + i)];
+}
+
+void print_hoco_seq(sr_t *sr, FILE *fo)
+{
+    uint32_t i;
+    for (i = 0; i < sr->hoco_l; ++i) fputc(char_nt4_table[hoco_base(sr->hoco_s, i)], fo);
+    fputc('\n', fo);
+}

@@ -1,0 +1,108 @@
+/*
+ * syncmer_gpu.h -- host side of the drop-in: the reference's syncmer.h interface for
+ * the hot path (reference syncmer.h:39-144), served by libsyncgpu.so.
+ *
+ * The four structs below are byte-compatible with the reference's (same member
+ * order, types and bit-fields; tests/test_host_layer.py hands them to the
+ * reference's own code to prove it), and the functions keep the reference's
+ * names, argument meaning and ownership rules:
+ *   - every per-read array is its own malloc block, NULL when empty
+ *     (sr_destroy frees them one by one, syncmer.c:1047-1058; read error
+ *     correction reallocs k_mer/m_pos/s_mer in place, syncerr.c:604-608)
+ *   - syncmer_t.m_pos is one malloc block per syncmer (syncmer.c:1359)
+ *   - sr_db_stat prints the reference's nine [M::sr_db_stat] lines
+ * The only function with a different signature is the reader: sr_read() in the
+ * reference pulls records from its sstream_t; here sr_read_mem() takes the
+ * records already in memory (INTEGRATION.md shows the 20-line sr_read() a
+ * maintainer writes on top of it inside the reference tree).
+ */
+#ifndef SYNCMER_GPU_H
+#define SYNCMER_GPU_H
+#include <stdio.h>
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef __SYNCMER_H__          /* inside the reference tree its own header provides these */
+#define uint128_t __uint128_t
+#define MAX_RD_NUM 0xFFFFFFFFULL
+#define MAX_RD_LEN 0x7FFFFFFFULL
+#define MAX_RD_SCM 0x7FFFFFFFULL
+
+typedef struct {
+    uint64_t sid;
+    char *sname;
+    uint32_t hoco_l;
+    uint8_t *hoco_s;
+    uint8_t *ho_rl;
+    uint32_t *ho_l_rl;
+    uint32_t *n_nucl;
+    uint32_t n;
+    uint32_t *m_pos;
+    uint64_t *s_mer;
+    uint64_t *k_mer;
+} sr_t;
+
+typedef struct {
+    uint64_t syncmer_n;
+    double syncmer_per_read, syncmer_avg_dist, smer_avg_cnt, kmer_avg_cnt;
+    int smer_unique, smer_singleton, smer_peak_hom, smer_peak_het;
+    int kmer_unique, kmer_singleton, kmer_peak_hom, kmer_peak_het;
+} sr_stat_t;
+
+typedef struct {
+    size_t n, m;
+    sr_t *a;
+    int k, s;
+    sr_stat_t *stats;
+} sr_db_t;
+
+typedef struct {
+    uint64_t h, s;
+    uint32_t cov:31, del:1;
+    uint64_t *m_pos;
+} syncmer_t;
+
+typedef struct {
+    size_t n, m;
+    syncmer_t *a;
+    uint16_t *c;
+    uint64_t *h;
+} syncmer_db_t;
+#endif
+
+extern const unsigned char seq_nt4_table[256];
+extern const char char_nt4_table[4];
+
+void sr_db_init(sr_db_t *sr_db, int k, int s);
+/* reads = n_reads records back to back in `bases`, off[n_reads+1]; names may be NULL.
+ * Returns 0, or a negative SG_E_* code after printing an [E::sr_read_mem] line. */
+int sr_read_mem(sr_db_t *sr_db, const char *bases, const uint64_t *off, char **names, uint64_t n_reads);
+int sr_db_validate(sr_db_t *sr_db);
+void sr_db_stat(sr_db_t *sr_db, FILE *fo, int more);
+syncmer_db_t *collect_syncmer_from_reads(sr_db_t *sr_db);
+void sr_destroy(sr_t *sr);
+void sr_db_clean(sr_db_t *sr_db);
+void sr_db_destroy(sr_db_t *sr_db);
+void syncmer_db_init(syncmer_db_t *scm_db);
+void syncmer_db_clean(syncmer_db_t *scm_db);
+void syncmer_db_destroy(syncmer_db_t *scm_db);
+void get_kmer_seq(uint8_t *hoco_s, uint32_t pos, int l, uint32_t rev, uint8_t *kmer_s);
+void get_kmer_dna_seq(uint8_t *hoco_s, uint32_t pos, int l, uint32_t rev, char *dna_seq);
+void print_hoco_seq(sr_t *sr, FILE *fo);
+
+/* arcs of make_syncmer_graph (syncasm.c:236-282) for the database just collected:
+ * 4 uint64 per arc (v, w, cov, comp), sorted by (v, w, comp); caller frees. */
+int syncmer_graph_arcs(sr_db_t *sr_db, syncmer_db_t *scm_db, uint32_t min_k_cov, double min_a_cov_f, uint64_t **arcs4, uint64_t *n_arcs);
+
+/* which GPU the layer uses (default 0), and its release */
+int oatk_gpu_set_device(int device);
+void oatk_gpu_shutdown(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

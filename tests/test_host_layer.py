@@ -1,0 +1,123 @@
+"""The C host layer (oatk_b200/host/syncmer_gpu.c) as a drop-in for the reference's syncmer.h functions:
+its structs are handed to the UNMODIFIED reference's own code (flatten helpers, make_syncmer_graph) to
+prove byte compatibility, and its printed statistics are compared line by line."""
+import ctypes as C
+import os
+import re
+import tempfile
+import numpy as np
+import pytest
+from oatk_b200 import synth
+from pyoracle import pack_reads, count_ambiguous
+import parity
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class SrDb(C.Structure):
+    _fields_ = [("n", C.c_size_t), ("m", C.c_size_t), ("a", C.c_void_p), ("k", C.c_int), ("s", C.c_int), ("stats", C.c_void_p)]
+
+
+@pytest.fixture(scope="module")
+def host():
+    from oatk_b200.host import build_host
+    L = C.CDLL(build_host.build())
+    L.sr_read_mem.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+    L.sr_db_init.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    L.sr_db_stat.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    L.sr_db_validate.argtypes = [C.c_void_p]
+    L.collect_syncmer_from_reads.restype = C.c_void_p
+    L.collect_syncmer_from_reads.argtypes = [C.c_void_p]
+    L.sr_db_clean.argtypes = [C.c_void_p]
+    L.syncmer_db_destroy.argtypes = [C.c_void_p]
+    L.syncmer_graph_arcs.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_double, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+    return L
+
+
+def stat_lines(fn, db_ptr):
+    libc = C.CDLL(None)
+    libc.fopen.restype = C.c_void_p
+    libc.fopen.argtypes = [C.c_char_p, C.c_char_p]
+    libc.fclose.argtypes = [C.c_void_p]
+    path = tempfile.mktemp()
+    fo = libc.fopen(path.encode(), b"w")
+    fn(db_ptr, fo, 0)
+    libc.fclose(fo)
+    txt = open(path).read()
+    os.unlink(path)
+    return txt.splitlines()
+
+
+@pytest.mark.parametrize("k,s", [(1001, 31), (301, 15)])
+def test_drop_in_structs_feed_the_reference(host, ref, k, s):
+    reads = synth.hifi_reads(31, 150000, 360, 15000, 0.001) + synth.adversarial_reads(3, k, s)
+    bases, off = pack_reads(reads)
+    n = len(reads)
+    db = SrDb()
+    host.sr_db_init(C.byref(db), k, s)
+    assert host.sr_read_mem(C.byref(db), bases.ctypes.data, off.ctypes.data, None, n) == 0
+    assert host.sr_db_validate(C.byref(db)) == 0
+    # 1. the reference's own flatten walks OUR sr_db_t
+    mine = ref._flat(C.addressof(db), n, count_ambiguous(bases, off))
+    rdb, theirs = ref.extract(bases, off, k, s)
+    assert parity.diff(mine, theirs, parity.EXTRACT_FIELDS) == []
+    # 2. sr_db_stat prints the reference's lines (the reference first, as run_syncasm.c does)
+    ref.L.sr_db_stat.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    exp_lines = stat_lines(ref.L.sr_db_stat, rdb)
+    got_lines = stat_lines(host.sr_db_stat, C.addressof(db))
+    assert got_lines == exp_lines
+    # 3. collect: the reference's flatten walks OUR syncmer_db_t, and k_mer[] was rewritten to id << 1
+    scm = host.collect_syncmer_from_reads(C.byref(db))
+    assert scm
+    rscm = ref.collect(rdb)
+    U, N = len(rscm["h"]), len(rscm["occ"])
+    assert ref.L.ref_scm_n(scm) == U
+    got = dict(h=np.zeros(U, np.uint64), s=np.zeros(U, np.uint64), cov=np.zeros(U, np.uint32), occ=np.zeros(N, np.uint64))
+    ref.L.ref_scm_flatten(scm, got["h"].ctypes.data, got["s"].ctypes.data, got["cov"].ctypes.data, got["occ"].ctypes.data)
+    ids = np.zeros(N + 1, np.uint64)
+    ref.L.ref_kmer_ids(C.addressof(db), ids.ctypes.data)
+    got["k_mer_id"] = ids[:N]
+    assert parity.diff(got, rscm, ("h", "s", "cov", "occ", "k_mer_id")) == []
+    # 4. the reference's make_syncmer_graph + unitigging run on OUR structs and give the reference's graph
+    g_mine = ref.L.ref_make_graph(C.addressof(db), scm, 3, 0.35)
+    g_ref = ref.graph(rdb, rscm, 3, 0.35)
+    d1, d2 = ref.graph_dump(g_mine), ref.graph_dump(g_ref)
+    for f in d1:
+        assert np.array_equal(d1[f], d2[f]), f
+    ref.unitig(g_mine)
+    ref.unitig(g_ref)
+    d1, d2 = ref.graph_dump(g_mine), ref.graph_dump(g_ref)
+    for f in d1:
+        assert np.array_equal(d1[f], d2[f]), f
+    # 5. our arc list = the reference graph's arcs mapped back to syncmer ids
+    # (make_syncmer_graph set the del flags in scm in place; the arc call does not depend on them)
+    p, na = C.c_void_p(), C.c_uint64()
+    assert host.syncmer_graph_arcs(C.byref(db), scm, 3, 0.35, C.byref(p), C.byref(na)) == 0
+    arcs = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint64)), (na.value, 4)).copy()
+    g3 = ref.graph(rdb, rscm, 3, 0.35)
+    gd = ref.graph_dump(g3)
+    first = gd["vtx_lists"][np.concatenate([[0], np.cumsum(gd["vtx_n"])[:-1]]).astype(np.int64)]
+    ra = gd["arcs"]
+    exp = np.stack([first[(ra[:, 0] >> 1).astype(np.int64)] | (ra[:, 0] & 1), first[(ra[:, 1] >> 1).astype(np.int64)] | (ra[:, 1] & 1),
+                    ra[:, 4] & 0x3FFFFFFF, (ra[:, 4] >> 31) & 1], axis=1).astype(np.uint64)
+    exp[(exp[:, 1] ^ 1) == exp[:, 0], 3] = 0            # asmg_arc_fix_symm flips comp of self-complementary arcs
+    exp = exp[np.lexsort((exp[:, 2], exp[:, 3], exp[:, 1], exp[:, 0]))]
+    assert np.array_equal(arcs, exp)
+    C.CDLL(None).free(p)
+    ref.free(g=g_mine)
+    ref.free(g=g_ref)
+    ref.free(g=g3)
+    host.syncmer_db_destroy(scm)
+    host.sr_db_clean(C.byref(db))
+    ref.free(rdb, rscm)
+
+
+def test_empty_collection(host):
+    bases, off = pack_reads([b"ACGTTGCA", b"NNNN", b""])
+    db = SrDb()
+    host.sr_db_init(C.byref(db), 1001, 31)
+    assert host.sr_read_mem(C.byref(db), bases.ctypes.data, off.ctypes.data, None, 3) == 0
+    assert stat_lines(host.sr_db_stat, C.addressof(db)) == ["[M::sr_db_stat] empty syncmer collection"]
+    assert not host.collect_syncmer_from_reads(C.byref(db))
+    host.sr_db_clean(C.byref(db))
