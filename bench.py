@@ -331,8 +331,9 @@ def ncu_traffic():
 
 
 def run_e2e(torch, lib, ctx, batch, bases, off, n_reads, total, sizes, csz, steps, dist, dev, world):
-    """host buffers in, host buffers out, through sg_batch_set_reads_host / sg_extract / sg_stat / sg_count / downloads"""
-    import numpy as np
+    """host buffers in, host buffers out through the C ABI: sg_pipe_run_host (chunked over 3 streams:
+    upload, kernels and download overlap) -> sg_stat -> sg_count -> sg_count_download on the master batch.
+    Every input byte crosses PCIe inside the timed region and every result array lands in pinned host memory."""
     pin = lambda n, dt: torch.empty(max(int(n), 1), dtype=dt, pin_memory=True)
     h_bases = pin(total, torch.uint8)
     h_bases.copy_(bases)
@@ -346,43 +347,91 @@ def run_e2e(torch, lib, ctx, batch, bases, off, n_reads, total, sizes, csz, step
         "hoco_s_off": pin(n_reads + 1, torch.int64), "ho_rl_off": pin(n_reads + 1, torch.int64), "scm_off": pin(n_reads + 1, torch.int64),
         "hoco_s_buf": pin(sizes.hoco_s_bytes * slack + 4096, torch.uint8), "ho_rl_buf": pin(sizes.ho_rl_bytes * slack + 4096, torch.uint8),
         "m_pos": pin(N * slack, torch.int32), "s_mer": pin(N * slack, torch.int64), "k_mer": pin(N * slack, torch.int64),
+        "amb_sid": pin(1024, torch.int32), "amb_pos": pin(1024, torch.int32),
+        "lrl_sid": pin(1024, torch.int32), "lrl_idx": pin(1024, torch.int32), "lrl_val": pin(1024, torch.int32),
     }
     for name, _ in lib.ExtractOut._fields_:
-        setattr(o, name, bufs[name].data_ptr() if name in bufs else None)
+        setattr(o, name, bufs[name].data_ptr())
+    caps = lib.PipeCaps(int(N * slack), bufs["hoco_s_buf"].numel(), bufs["ho_rl_buf"].numel(), 1024, 1024)
     co = lib.CountOut()
     cb = {"h": pin(U * slack, torch.int64), "s": pin(U * slack, torch.int64), "cov": pin(U * slack, torch.int32),
-          "occ_off": pin(U * slack + 1, torch.int64), "occ": pin(N * slack, torch.int64), "k_mer_id": None}
+          "occ_off": pin(U * slack + 1, torch.int64), "occ": pin(N * slack, torch.int64), "k_mer_id": pin(N * slack, torch.int64)}
     for name, _ in lib.CountOut._fields_:
-        setattr(co, name, cb[name].data_ptr() if cb.get(name) is not None else None)
+        setattr(co, name, cb[name].data_ptr())
     L = lib.library()
+    n_slots = env_int("SG_PIPE_SLOTS", 6)
+    pipe = lib.Pipe(ctx.device, n_slots)
+    chunk = env_int("SG_PIPE_CHUNK", 16384)
     torch.cuda.synchronize()
 
     def one():
-        batch.set_reads_host_ptr(h_bases.data_ptr(), h_off.data_ptr(), n_reads)
-        batch.extract(K, S)
-        batch.stat()
-        batch.count()
-        lib._ck(ctx.h, L.sg_extract_download(batch.h, C.byref(o)), "sg_extract_download")
-        lib._ck(ctx.h, L.sg_count_download(batch.h, C.byref(co)), "sg_count_download")
+        z = pipe.run_host(h_bases.data_ptr(), h_off.data_ptr(), n_reads, K, S, chunk, o, caps)
+        pipe.master.stat()
+        pipe.master.count()
+        lib._ck(pipe.ctx.h, L.sg_count_download(pipe.master.h, C.byref(co)), "sg_count_download")
+        return z
 
+    one()
     one()
     if dist is not None:
         dist.barrier()
     torch.cuda.synchronize()
+    l0 = pipe.launches()
     t0 = time.perf_counter()
     for _ in range(steps):
-        one()
+        z = one()
     torch.cuda.synchronize()
     sec = (time.perf_counter() - t0) / steps
+    launches = (pipe.launches() - l0) // steps
     if dist is not None:
         t = torch.tensor([sec], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         sec = float(t.item())
-    h2d = total + 8 * (n_reads + 1)
-    d2h = int(sizes.hoco_s_bytes + sizes.ho_rl_bytes + 20 * N + 8 * n_reads + 28 * U + 8 * N)
-    return {"value": world * total / sec, "unit": "bases/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": d2h,
-            "ms_per_step": sec * 1e3, "steps": steps,
-            "path": "sg_batch_set_reads_host -> sg_extract -> sg_stat -> sg_count -> sg_extract_download + sg_count_download, pinned host buffers"}
+    assert z.n_syncmers == N
+    h2d = total + 8 * (n_reads + n_reads // chunk + 1)
+    d2h = int(z.hoco_s_bytes + z.ho_rl_bytes + 20 * N + 8 * n_reads + 28 * U + 16 * N)
+    res = {"value": world * total / sec, "unit": "bases/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": d2h,
+           "ms_per_step": sec * 1e3, "steps": steps, "gpu_launches_per_step": int(launches), "chunk_reads": chunk, "streams": n_slots,
+           "path": "sg_pipe_run_host (chunks of %d reads over several streams) -> sg_stat -> sg_count -> sg_count_download; pinned host buffers; "
+                   "multi-GPU runs time each rank's own shard without the tuple exchange" % chunk}
+    pipe.close()
+    res["pcie"] = pcie_probe(torch, dev, h_bases)
+    return res
+
+
+def pcie_probe(torch, dev, h_src):
+    """what the host link of this box delivers (pinned memory, 1 GiB copies): the ceiling of the e2e number"""
+    n = min(h_src.numel(), 1 << 30)
+    d = torch.empty(n, dtype=torch.uint8, device=dev)
+    h_dst = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    s1, s2 = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+
+    def timed(fn, reps=3):
+        fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / reps
+
+    def h2d():
+        with torch.cuda.stream(s1):
+            d.copy_(h_src[:n], non_blocking=True)
+
+    d2 = torch.empty(n, dtype=torch.uint8, device=dev)
+
+    def d2h():
+        with torch.cuda.stream(s2):
+            h_dst.copy_(d2, non_blocking=True)
+
+    def both():
+        h2d()
+        d2h()
+
+    t_h2d, t_d2h, t_both = timed(h2d), timed(d2h), timed(both)
+    return {"h2d_gbs": n / t_h2d / 1e9, "d2h_gbs": n / t_d2h / 1e9, "duplex_each_gbs": n / t_both / 1e9,
+            "note": "e2e moves ~1 B/base up and ~1 B/base down, so its ceiling is duplex_each_gbs bases/ns"}
 
 
 if __name__ == "__main__":

@@ -155,6 +155,30 @@ int sg_count_download(sg_batch *b, const sg_count_out_t *out);
 int sg_arcs(sg_batch *b, uint32_t min_k_cov, double min_a_cov_f, uint64_t *n_arcs);  /* synchronises */
 int sg_arcs_download(sg_batch *b, uint64_t *arcs4);
 
+/* ---- host buffers at PCIe rate: the chunked copy / compute / copy pipeline ----
+ * sr_read's role (syncmer.c:487-556) for inputs that live in host memory: the reads are cut into
+ * chunks of `chunk_reads`, which flow through n_slots (stream, batch) pairs driven by one host
+ * thread each, so uploads, kernels and downloads overlap. Per-read results are written to `out`
+ * in read order exactly as sg_extract_download would (offset arrays are global); the syncmer
+ * tuples and the packed reads are appended to a device-resident master batch on which sg_stat,
+ * sg_count, sg_count_download, sg_arcs run afterwards. `bases` and the big arrays of `out` should
+ * be pinned (cudaHostAlloc / cudaHostRegister) or the copies serialise. */
+typedef struct sg_pipe sg_pipe;
+typedef struct {
+    uint64_t max_syncmers;    /* capacity of out->m_pos / s_mer / k_mer */
+    uint64_t hoco_s_bytes;    /* capacity of out->hoco_s_buf (<= total_bases/4 + 16 per read always suffices) */
+    uint64_t ho_rl_bytes;     /* capacity of out->ho_rl_buf (<= total_bases + 16 per read always suffices) */
+    uint64_t max_ambiguous, max_long_runs;
+} sg_pipe_caps_t;
+int sg_pipe_create(int device, int n_slots, sg_pipe **out);
+void sg_pipe_destroy(sg_pipe *p);
+int sg_pipe_run_host(sg_pipe *p, const char *bases, const uint64_t *off, uint64_t n_reads, int k, int s,
+        uint64_t chunk_reads, const sg_extract_out_t *out, const sg_pipe_caps_t *caps, sg_extract_sizes_t *sizes);
+sg_batch *sg_pipe_master(sg_pipe *p);
+sg_ctx *sg_pipe_ctx(sg_pipe *p);
+const char *sg_pipe_last_error(sg_pipe *p);
+uint64_t sg_pipe_launches(sg_pipe *p);
+
 /* device pointers of the batch's result arrays (for device-side consumers such as the multi-GPU
  * exchange); valid until the next call that recomputes them. n = number of elements. */
 enum { SG_BUF_KEY = 0,      /* uint64 k-mer hash, read order */

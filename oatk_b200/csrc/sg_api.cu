@@ -136,6 +136,7 @@ static void reset_state(sg_batch *b)
     b->extracted = b->counted = b->sizes_known = b->sorted = b->adopted = false;
     b->n_adopted = 0;
     b->have_kid_local = false;
+    b->pipe_fed = false;
     b->k = b->s = 0;
     b->n_syncmers = 0;
 }
@@ -334,6 +335,8 @@ int sg_extract_download(sg_batch *b, const sg_extract_out_t *o)
 {
     if (!b || !o) return SG_E_ARG;
     if (!b->extracted) return SG_E_STATE;
+    if (b->pipe_fed && (o->hoco_s_buf || o->ho_rl_buf || o->amb_sid || o->amb_pos || o->lrl_sid || o->lrl_idx || o->lrl_val))
+        return SG_E_STATE;                        // the pipeline already delivered these per chunk
     sg_ctx *ctx = b->ctx;
     cudaStream_t st = ctx->stream;
     CK(cudaSetDevice(ctx->device));

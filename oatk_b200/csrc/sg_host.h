@@ -69,6 +69,7 @@ struct sg_batch {
     sg::DevBuf tuples, part_counts, akey, aocc, asmer, kid_local;
     bool have_kid_local = false;
     bool adopted = false;
+    bool pipe_fed = false;                       // filled by sg_pipe_run_host: no ho_rl / raw reads on the device
     uint64_t n_adopted = 0;
     // the tuple set a5/a6 work on
     const uint64_t *t_key() const { return (const uint64_t *) (adopted ? akey.p : key.p); }

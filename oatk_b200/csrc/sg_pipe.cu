@@ -1,0 +1,258 @@
+// sg_pipe.cu -- the host-buffer path at full PCIe rate: reads are cut into chunks that flow
+// through n_slots independent (context, stream, batch) triples, one host thread each, so the
+// host-to-device copy of chunk i+1, the kernels of chunk i and the device-to-host copy of
+// chunk i-1 overlap. What the reference does in sr_read (syncmer.c:487-556: a batch of
+// 10 000 reads per pthread, joined per super-batch) becomes a 3-deep copy/compute/copy
+// pipeline; per-read results land in the caller's host arrays in read order, and the small
+// per-syncmer tuples (plus the 2-bit packed reads, which the exact k-mer verification of
+// sg_count needs) are appended to a device-resident master batch on which sg_stat,
+// sg_count and sg_arcs then run as usual.
+#include <cstring>
+#include <string>
+#include <vector>
+#include <thread>
+#include <mutex>
+#include <condition_variable>
+#include <algorithm>
+#include <chrono>
+#include <cstdlib>
+#include "sg_common.cuh"
+#include "sg_internal.h"
+#include "sg_host.h"
+
+namespace sg {
+
+__global__ void __launch_bounds__(256) add_offset_kernel(const uint64_t *src, uint64_t *dst, uint64_t n, uint64_t add)
+{
+    const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[i] + add;
+}
+
+} // namespace sg
+
+using namespace sg;
+
+struct sg_pipe {
+    int device = 0, n_slots = 0;
+    std::vector<sg_ctx *> ctx;
+    std::vector<sg_batch *> slot;
+    sg_ctx *mctx = nullptr;
+    sg_batch *master = nullptr;
+    std::string err;
+};
+
+static inline unsigned nblk(uint64_t n, unsigned t) { return (unsigned) ((n + t - 1) / t); }
+
+extern "C" {
+
+int sg_pipe_create(int device, int n_slots, sg_pipe **out)
+{
+    if (!out || n_slots < 1 || n_slots > 8) return SG_E_ARG;
+    *out = nullptr;
+    sg_pipe *p = new sg_pipe();
+    p->device = device; p->n_slots = n_slots;
+    int rc = sg_ctx_create(device, &p->mctx);
+    if (rc) { delete p; return rc; }
+    if ((rc = sg_batch_create(p->mctx, &p->master))) { sg_ctx_destroy(p->mctx); delete p; return rc; }
+    for (int i = 0; i < n_slots; ++i) {
+        sg_ctx *c = nullptr; sg_batch *b = nullptr;
+        cudaStream_t st;
+        if (sg_ctx_create(device, &c) || cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess || sg_batch_create(c, &b)) {
+            rc = SG_E_CUDA;
+            break;
+        }
+        sg_ctx_set_stream(c, st);
+        p->ctx.push_back(c); p->slot.push_back(b);
+    }
+    if (rc) { sg_pipe_destroy(p); return rc; }
+    *out = p;
+    return SG_OK;
+}
+
+void sg_pipe_destroy(sg_pipe *p)
+{
+    if (!p) return;
+    cudaSetDevice(p->device);
+    for (size_t i = 0; i < p->slot.size(); ++i) {
+        sg_batch_destroy(p->slot[i]);
+        cudaStream_t st = p->ctx[i]->stream;
+        sg_ctx_destroy(p->ctx[i]);
+        if (st) cudaStreamDestroy(st);
+    }
+    if (p->master) sg_batch_destroy(p->master);
+    if (p->mctx) sg_ctx_destroy(p->mctx);
+    delete p;
+}
+
+sg_batch *sg_pipe_master(sg_pipe *p) { return p ? p->master : nullptr; }
+sg_ctx *sg_pipe_ctx(sg_pipe *p) { return p ? p->mctx : nullptr; }
+const char *sg_pipe_last_error(sg_pipe *p) { return p ? p->err.c_str() : "no pipe"; }
+
+uint64_t sg_pipe_launches(sg_pipe *p)
+{
+    if (!p) return 0;
+    uint64_t n = p->mctx->launches;
+    for (auto c : p->ctx) n += c->launches;
+    return n;
+}
+
+int sg_pipe_run_host(sg_pipe *p, const char *bases, const uint64_t *off, uint64_t n_reads, int k, int s,
+        uint64_t chunk_reads, const sg_extract_out_t *out, const sg_pipe_caps_t *caps, sg_extract_sizes_t *sizes)
+{
+    if (!p || !off || !out || !caps || !sizes || chunk_reads == 0) return SG_E_ARG;
+    if (!(s > 0 && s < 32 && k > s)) return SG_E_ARG;
+    if (n_reads > 0xFFFFFFFFull) return SG_E_LIMIT;
+    cudaSetDevice(p->device);
+    const uint64_t n_chunks = (n_reads + chunk_reads - 1) / chunk_reads;
+    const uint64_t total = n_reads ? off[n_reads] - off[0] : 0;
+    sg_batch *M = p->master;
+    sg_ctx *mctx = p->mctx;
+    auto fail = [&](int rc, const std::string &what) { p->err = what; return rc; };
+
+    // master arrays: per read and per position capacities are known, per syncmer ones come from the caller
+    const uint64_t cap_pos = total + 64 * n_reads + 64, capN = caps->max_syncmers;
+    if (M->hoff.reserve((n_reads + 1) * 8) || M->hoco_s.reserve(cap_pos / 4 + 64) || M->hoco_l.reserve((n_reads + 1) * 4) ||
+            M->n_scm.reserve((n_reads + 1) * 4) || M->scm_off.reserve((n_reads + 1) * 8) || M->n_amb.reserve((n_reads + 1) * 4) ||
+            M->key.reserve((capN + 1) * 8) || M->occ.reserve((capN + 1) * 8) || M->m_pos.reserve((capN + 1) * 4) || M->s_mer.reserve((capN + 1) * 8))
+        return fail(SG_E_NOMEM, "master allocation failed");
+
+    // running totals, advanced in chunk order
+    struct Totals { uint64_t hoff = 0, hs = 0, rl = 0, scm = 0, amb = 0, lrl = 0, hoco = 0; } tot;
+    std::mutex mu;
+    std::condition_variable cv;
+    uint64_t next_chunk = 0;
+    int first_err = 0;
+    std::string first_msg;
+
+    const bool trace = getenv("SG_PIPE_TRACE") != nullptr;
+    std::vector<double> tphase(p->n_slots * 6, 0.0);
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const bool last_writes_end = true;
+    (void) last_writes_end;
+
+    auto worker = [&](int si) {
+        cudaSetDevice(p->device);
+        double *tp = &tphase[si * 6];
+        sg_batch *b = p->slot[si];
+        sg_ctx *ctx = p->ctx[si];
+        cudaStream_t st = ctx->stream;
+        for (uint64_t c = si; c < n_chunks; c += p->n_slots) {
+            const uint64_t r0 = c * chunk_reads, r1 = std::min(n_reads, r0 + chunk_reads), nr = r1 - r0;
+            int rc = SG_OK;
+            std::string msg;
+            double t0 = now();
+            std::vector<uint64_t> loff(nr + 1), l_hs(nr + 1), l_rl(nr + 1), l_scm(nr + 1);
+            for (uint64_t i = 0; i <= nr; ++i) loff[i] = off[r0 + i] - off[r0];
+            sg_batch_set_sid_base(b, r0);
+            sg_extract_sizes_t z;
+            memset(&z, 0, sizeof(z));
+            {
+                std::lock_guard<std::mutex> g(mu);
+                if (first_err) rc = first_err;
+            }
+            if (!rc) rc = sg_batch_set_reads_host(b, bases + off[r0], loff.data(), nr);
+            if (!rc) rc = sg_extract(b, k, s);
+            if (!rc) rc = sg_extract_sizes(b, &z);
+            if (rc && msg.empty()) msg = ctx->err;
+            double t1 = now(); tp[0] += t1 - t0;
+            // ---- ordered section: claim this chunk's place in every output ----
+            Totals base;
+            uint64_t hcap = 0;                             // capacity positions of this chunk (multiple of 64)
+            {
+                std::unique_lock<std::mutex> g(mu);
+                cv.wait(g, [&] { return next_chunk == c; });
+                base = tot;
+                if (!rc && !first_err) {
+                    if (tot.scm + z.n_syncmers > capN || tot.hs + z.hoco_s_bytes > caps->hoco_s_bytes ||
+                            tot.rl + z.ho_rl_bytes > caps->ho_rl_bytes || tot.amb + z.n_ambiguous > caps->max_ambiguous ||
+                            tot.lrl + z.n_long_runs > caps->max_long_runs) {
+                        rc = SG_E_NOMEM; msg = "caller capacities too small";
+                    }
+                }
+                if (!rc && !first_err) {
+                    for (uint64_t i = 0; i < nr; ++i) hcap += (loff[i + 1] - loff[i] + 63) & ~63ull;
+                    tot.hoff += hcap; tot.hs += z.hoco_s_bytes; tot.rl += z.ho_rl_bytes; tot.scm += z.n_syncmers;
+                    tot.amb += z.n_ambiguous; tot.lrl += z.n_long_runs; tot.hoco += z.hoco_bases;
+                } else if (!first_err) { first_err = rc; first_msg = msg; }
+                ++next_chunk;
+                cv.notify_all();
+            }
+            double t2 = now(); tp[1] += t2 - t1;
+            if (rc || first_err) continue;
+            // ---- append to the master batch (device to device, this slot's stream) ----
+            const uint64_t N = z.n_syncmers;
+            if (hcap) cudaMemcpyAsync((uint8_t *) M->hoco_s.p + base.hoff / 4, b->hoco_s.p, hcap / 4, cudaMemcpyDeviceToDevice, st);
+            cudaMemcpyAsync((uint32_t *) M->hoco_l.p + r0, b->hoco_l.p, nr * 4, cudaMemcpyDeviceToDevice, st);
+            cudaMemcpyAsync((uint32_t *) M->n_scm.p + r0, b->n_scm.p, nr * 4, cudaMemcpyDeviceToDevice, st);
+            cudaMemcpyAsync((uint32_t *) M->n_amb.p + r0, b->n_amb.p, nr * 4, cudaMemcpyDeviceToDevice, st);
+            add_offset_kernel<<<nblk(nr + 1, 256), 256, 0, st>>>((const uint64_t *) b->hoff.p, (uint64_t *) M->hoff.p + r0, nr + 1, base.hoff);
+            add_offset_kernel<<<nblk(nr + 1, 256), 256, 0, st>>>((const uint64_t *) b->scm_off.p, (uint64_t *) M->scm_off.p + r0, nr + 1, base.scm);
+            ctx->count_launch(SG_T_PLACE, 2);
+            if (N) {
+                cudaMemcpyAsync((uint64_t *) M->key.p + base.scm, b->key.p, N * 8, cudaMemcpyDeviceToDevice, st);
+                cudaMemcpyAsync((uint64_t *) M->occ.p + base.scm, b->occ.p, N * 8, cudaMemcpyDeviceToDevice, st);
+                cudaMemcpyAsync((uint32_t *) M->m_pos.p + base.scm, b->m_pos.p, N * 4, cudaMemcpyDeviceToDevice, st);
+                cudaMemcpyAsync((uint64_t *) M->s_mer.p + base.scm, b->s_mer.p, N * 8, cudaMemcpyDeviceToDevice, st);
+            }
+            // ---- this chunk's slice of the caller's arrays ----
+            sg_extract_out_t o = *out;
+            if (o.hoco_l) o.hoco_l += r0;
+            if (o.n_scm) o.n_scm += r0;
+            // offset arrays go through chunk-local copies: entry nr of one chunk is entry 0 of the next
+            o.hoco_s_off = l_hs.data(); o.ho_rl_off = l_rl.data(); o.scm_off = l_scm.data();
+            if (o.hoco_s_buf) o.hoco_s_buf += base.hs;
+            if (o.ho_rl_buf) o.ho_rl_buf += base.rl;
+            if (o.m_pos) o.m_pos += base.scm;
+            if (o.s_mer) o.s_mer += base.scm;
+            if (o.k_mer) o.k_mer += base.scm;
+            if (o.amb_sid) o.amb_sid += base.amb;
+            if (o.amb_pos) o.amb_pos += base.amb;
+            if (o.lrl_sid) o.lrl_sid += base.lrl;
+            if (o.lrl_idx) o.lrl_idx += base.lrl;
+            if (o.lrl_val) o.lrl_val += base.lrl;
+            double t3 = now(); tp[2] += t3 - t2;
+            rc = sg_extract_download(b, &o);              // synchronises this slot's stream
+            double t4 = now(); tp[3] += t4 - t3;
+            if (!rc) {
+                // chunk-local offsets and read ids -> global; only the last chunk writes the closing entry
+                const uint64_t ne = nr + (r1 == n_reads ? 1 : 0);
+                for (uint64_t i = 0; i < ne; ++i) {
+                    if (out->hoco_s_off) out->hoco_s_off[r0 + i] = l_hs[i] + base.hs;
+                    if (out->ho_rl_off) out->ho_rl_off[r0 + i] = l_rl[i] + base.rl;
+                    if (out->scm_off) out->scm_off[r0 + i] = l_scm[i] + base.scm;
+                }
+                for (uint64_t i = 0; i < z.n_ambiguous && o.amb_sid; ++i) o.amb_sid[i] += (uint32_t) r0;
+                for (uint64_t i = 0; i < z.n_long_runs && o.lrl_sid; ++i) o.lrl_sid[i] += (uint32_t) r0;
+            } else {
+                std::lock_guard<std::mutex> g(mu);
+                if (!first_err) { first_err = rc; first_msg = ctx->err; }
+            }
+            tp[4] += now() - t4;
+        }
+        cudaStreamSynchronize(st);
+    };
+
+    std::vector<std::thread> th;
+    for (int i = 0; i < p->n_slots; ++i) th.emplace_back(worker, i);
+    for (auto &t : th) t.join();
+    if (trace)
+        for (int i = 0; i < p->n_slots; ++i)
+            fprintf(stderr, "[sg_pipe] slot %d: upload+extract %.1f ms, ordered wait %.1f, append enqueue %.1f, download %.1f, fix-up %.1f\n", i,
+                    tphase[i * 6] * 1e3, tphase[i * 6 + 1] * 1e3, tphase[i * 6 + 2] * 1e3, tphase[i * 6 + 3] * 1e3, tphase[i * 6 + 4] * 1e3);
+    if (first_err) return fail(first_err, first_msg);
+    if (cudaDeviceSynchronize() != cudaSuccess) return fail(SG_E_CUDA, cudaGetErrorString(cudaGetLastError()));
+
+    // the master batch now looks like the result of one big sg_extract
+    M->d_bases = nullptr; M->d_off = nullptr;
+    M->n_reads = n_reads; M->total_bases = total; M->sid_base = 0;
+    M->k = k; M->s = s;
+    M->n_syncmers = tot.scm; M->n_amb_total = tot.amb; M->n_lrl_total = tot.lrl; M->hoco_bases = tot.hoco;
+    M->extracted = true; M->counted = M->sorted = M->adopted = M->sizes_known = M->have_kid_local = false;
+    M->pipe_fed = true;
+    sizes->n_reads = n_reads; sizes->n_syncmers = tot.scm; sizes->hoco_bases = tot.hoco;
+    sizes->hoco_s_bytes = tot.hs; sizes->ho_rl_bytes = tot.rl; sizes->n_ambiguous = tot.amb; sizes->n_long_runs = tot.lrl;
+    (void) mctx;
+    return SG_OK;
+}
+
+} // extern "C"

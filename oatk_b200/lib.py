@@ -43,6 +43,10 @@ class CountSizes(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("n_syncmers", "n_unique", "n_hash_collisions")]
 
 
+class PipeCaps(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("max_syncmers", "hoco_s_bytes", "ho_rl_bytes", "max_ambiguous", "max_long_runs")]
+
+
 class CountOut(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("h", "s", "cov", "occ_off", "occ", "k_mer_id")]
 
@@ -58,6 +62,7 @@ SYMBOLS = [
     "sg_stat", "sg_count", "sg_count_sizes", "sg_count_download", "sg_arcs", "sg_arcs_download",
     "sg_tuples_partition", "sg_tuples_adopt", "sg_debug_set_hash_bits", "sg_batch_buffer",
     "sg_ids_pack", "sg_ids_scatter",
+    "sg_pipe_create", "sg_pipe_destroy", "sg_pipe_run_host", "sg_pipe_master", "sg_pipe_ctx", "sg_pipe_last_error", "sg_pipe_launches",
 ]
 
 
@@ -100,6 +105,18 @@ def _lib():
                        ("sg_ids_pack", [vp, u64, C.POINTER(vp), C.POINTER(u64)]), ("sg_ids_scatter", [vp, vp, u64])):
         if hasattr(L, name):
             getattr(L, name).argtypes = args
+    L.sg_pipe_create.argtypes = [i32, i32, C.POINTER(vp)]
+    L.sg_pipe_destroy.argtypes = [vp]
+    L.sg_pipe_destroy.restype = None
+    L.sg_pipe_run_host.argtypes = [vp, vp, vp, u64, i32, i32, u64, C.POINTER(ExtractOut), C.POINTER(PipeCaps), C.POINTER(ExtractSizes)]
+    L.sg_pipe_master.restype = vp
+    L.sg_pipe_master.argtypes = [vp]
+    L.sg_pipe_ctx.restype = vp
+    L.sg_pipe_ctx.argtypes = [vp]
+    L.sg_pipe_last_error.restype = C.c_char_p
+    L.sg_pipe_last_error.argtypes = [vp]
+    L.sg_pipe_launches.restype = u64
+    L.sg_pipe_launches.argtypes = [vp]
     _LIB = L
     return L
 
@@ -304,3 +321,55 @@ def _unpad(buf, off, lens):
     idx = np.arange(tot, dtype=np.int64) - np.repeat(starts, lens) + np.repeat(off[:-1].astype(np.int64), lens)
     out[:] = buf[idx]
     return out
+
+
+class _Borrowed:
+    """a handle owned by someone else (the pipeline's master context / batch)"""
+
+    def __init__(self, h, device=0):
+        self.h = C.c_void_p(h)
+        self.device = device
+
+
+class Pipe:
+    """sg_pipe_*: host buffers in, host buffers out, chunked over several streams"""
+
+    def __init__(self, device=0, n_slots=3):
+        h = C.c_void_p()
+        rc = _lib().sg_pipe_create(device, n_slots, C.byref(h))
+        if rc != 0:
+            raise SgError(rc, "sg_pipe_create")
+        self.h = h
+        self.device = device
+        ctx = Context.__new__(Context)
+        ctx.h = C.c_void_p(_lib().sg_pipe_ctx(h))
+        ctx.device = device
+        ctx.close = lambda: None
+        self.ctx = ctx
+        m = Batch.__new__(Batch)
+        m.ctx = ctx
+        m.h = C.c_void_p(_lib().sg_pipe_master(h))
+        m._keep = None
+        m.close = lambda: None
+        self.master = m
+
+    def run_host(self, bases_ptr, off_ptr, n_reads, k, s, chunk_reads, out, caps):
+        z = ExtractSizes()
+        rc = _lib().sg_pipe_run_host(self.h, bases_ptr, off_ptr, n_reads, k, s, chunk_reads, C.byref(out), C.byref(caps), C.byref(z))
+        if rc != 0:
+            raise SgError(rc, "sg_pipe_run_host", _lib().sg_pipe_last_error(self.h).decode())
+        return z
+
+    def launches(self):
+        return int(_lib().sg_pipe_launches(self.h))
+
+    def close(self):
+        if self.h:
+            _lib().sg_pipe_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
