@@ -12,11 +12,15 @@
 //              for plain ACGT/acgt; anything else (N, IUPAC, U, bytes 0..3, tile
 //              edges) takes an exact per-byte path
 //   run starts 2-bit packed codes XOR their 1-base shift -> start mask
-//   scan       block prefix sum of start counts = hoco index
-//   stage      (code, raw start) per hoco base into shared memory
-//   finalise   run length = next start - this start; 16 codes -> one 32-bit word,
-//              16 N flags -> one 16-bit word, coalesced stores; the open last run
-//              and an incomplete group of 16 are carried into the next tile
+//   scan       block prefix sum of start counts = hoco index, block prefix maximum
+//              of "latest start" = where the run before my chunk began
+//   close      every start closes the run before it (length = distance between
+//              starts) with one byte store into shared memory and shifts its 2-bit
+//              code into a register; the thread's codes are then OR-ed into the
+//              shared big-endian word stream with at most two shared atomics
+//   flush      finished groups of 16 entries leave as one 32-bit code word, one
+//              128-bit store of run lengths and 16 N flags; the open last run and an
+//              incomplete group stay staged for the next tile
 #include "sg_common.cuh"
 #include "sg_internal.h"
 
@@ -52,13 +56,17 @@ __global__ void __launch_bounds__(NT) encode_kernel(EncodeArgs A)
 {
     constexpr int TILE = NT * 16;
     constexpr int NW = NT / 32;
-    __shared__ __align__(16) uint8_t s_code[TILE + 48];
-    __shared__ __align__(16) uint32_t s_pos[TILE + 48];
-    __shared__ uint32_t s_scan[NW + 1];
+    constexpr int NWORD = TILE / 16 + 4;               // staged 16-entry groups (tile + carry)
+    __shared__ __align__(16) uint8_t s_rl_arr[TILE + 64];   // run length - 1 per staged hoco entry; [-16, 0) is scratch
+    __shared__ uint32_t s_w[NWORD];                    // 2-bit codes, 16 per word, first entry in bits 31:30
+    __shared__ uint32_t s_nbw[NWORD / 2 + 2];          // ambiguity flags, entry e -> bit e & 31 of word e >> 5
+    __shared__ uint32_t s_cnt[NW];
+    __shared__ int s_last[NW];
     __shared__ uint32_t s_namb;
+    uint8_t *s_rl = s_rl_arr + 16;
 
     const uint64_t r = blockIdx.x;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint64_t raw0 = A.off[r], raw1 = A.off[r + 1];
     const uint32_t len = (uint32_t) (raw1 - raw0);
     const uint64_t hb = A.hoff[r];                      // capacity offset, multiple of 64
@@ -69,9 +77,23 @@ __global__ void __launch_bounds__(NT) encode_kernel(EncodeArgs A)
     uint8_t *rl8 = A.ho_rl + hb;
     const uint32_t sid = (uint32_t) r;
 
-    uint32_t n_stage = 0;        // staged entries carried from the previous tile (uniform)
+    uint32_t n_stage = 0;        // staged entries carried from the previous tile, the open run last (uniform)
     uint32_t g_done = 0;         // hoco entries already written (uniform, multiple of 16)
+    int carry_last = -1;         // raw position of the latest run start seen so far (uniform)
+    for (int i = tid; i < NWORD; i += NT) s_w[i] = 0;
+    for (int i = tid; i < NWORD / 2 + 2; i += NT) s_nbw[i] = 0;
     if (tid == 0) s_namb = 0;
+    __syncthreads();
+
+    // a run longer than 256 saturates ho_rl and goes to the side list (syncmer.c:301-304)
+    auto close_run = [&](uint32_t e, uint32_t rl1) {
+        if (rl1 >= 255u) {
+            unsigned long long o = atomicAdd(A.lrl_count, 1ull);
+            if (o < A.lrl_cap) { A.lrl_sid[o] = sid; A.lrl_idx[o] = g_done + e; A.lrl_val[o] = rl1; }
+            rl1 = 255u;
+        }
+        s_rl[(int) e] = (uint8_t) rl1;
+    };
 
     for (uint32_t t = 0; t < ntiles; ++t) {
         const uint64_t g = a0 + (uint64_t) t * TILE + (uint64_t) tid * 16;   // global byte index of my chunk
@@ -107,21 +129,46 @@ __global__ void __launch_bounds__(NT) encode_kernel(EncodeArgs A)
             if (pc >= 4) M |= 0x40000000u;
             if (!fast) M = (M | NM | (NM >> 2) | (VM >> 2)) & ~VM;
         }
+        const int rel = (int) (uint32_t) (g - raw0);   // wraps for bytes before the read; those are void
         const uint32_t cnt = __popc(M);
-        uint32_t tot;
-        const uint32_t ex = BlockScanU32::run<NW>(cnt, s_scan, &tot);
+        const int mylast = M ? rel + 15 - ((__ffs(M) - 1) >> 1) : -1;
 
-        // stage (code, raw start) of every run that starts in my chunk: 16 predicated steps, no loop
+        // block scan: hoco index of my first start, and the raw position of the latest start before my chunk
+        uint32_t inc = cnt;
+        int lmax = mylast;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t a = __shfl_up_sync(SG_FULL, inc, d);
+            const int bq = __shfl_up_sync(SG_FULL, lmax, d);
+            if (lane >= d) { inc += a; lmax = max(lmax, bq); }
+        }
+        if (lane == 31) { s_cnt[wid] = inc; s_last[wid] = lmax; }
+        __syncthreads();
+        uint32_t ex = inc - cnt, tot = 0;
+        int prev = __shfl_up_sync(SG_FULL, lmax, 1), blast = carry_last;
+        if (lane == 0) prev = -1;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+            const uint32_t c = s_cnt[w];
+            const int l = s_last[w];
+            if (w < wid) { ex += c; prev = max(prev, l); }
+            tot += c; blast = max(blast, l);
+        }
+        prev = max(prev, carry_last);
+
+        // every run start closes the run before it (run length = distance between starts) and
+        // appends its code; 16 predicated steps, everything in registers but the byte store
         {
-            uint32_t hl = n_stage + ex;
-            const uint32_t rel = (uint32_t) (g - raw0);        // wraps for bytes before the read; those are void
+            uint32_t e = n_stage + ex, CP = 0;
             if (fast) {
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                     if (M & (1u << (2 * (15 - i)))) {
-                        s_code[hl] = (uint8_t) ((P >> (2 * (15 - i))) & 3u);
-                        s_pos[hl] = rel + (uint32_t) i;
-                        ++hl;
+                        const uint32_t rl1 = (uint32_t) (rel + i - prev - 1);
+                        if (rl1 >= 255u) close_run(e - 1, rl1); else s_rl[(int) e - 1] = (uint8_t) rl1;
+                        prev = rel + i;
+                        CP = CP * 4u + ((P >> (2 * (15 - i))) & 3u);
+                        ++e;
                     }
                 }
             } else {
@@ -129,87 +176,53 @@ __global__ void __launch_bounds__(NT) encode_kernel(EncodeArgs A)
                 while (m) {
                     const int b = 31 - __clz(m);
                     m &= ~(1u << b);
-                    s_code[hl] = (uint8_t) (((P >> b) & 3u) | ((NM >> b) & 1u) << 2);
-                    s_pos[hl] = rel + (uint32_t) (15 - (b >> 1));
-                    ++hl;
+                    const int i = 15 - (b >> 1);
+                    close_run(e - 1, (uint32_t) (rel + i - prev - 1));   // entry -1 of the read lands in scratch
+                    prev = rel + i;
+                    CP = CP * 4u + ((P >> b) & 3u);
+                    if ((NM >> b) & 1u) {
+                        atomicOr(&s_nbw[e >> 5], 1u << (e & 31));
+                        unsigned long long o = atomicAdd(A.amb_count, 1ull);
+                        if (o < A.amb_cap) { A.amb_sid[o] = sid; A.amb_pos[o] = (uint32_t) (rel + i); }
+                        atomicAdd(&s_namb, 1u);
+                    }
+                    ++e;
                 }
+            }
+            if (cnt) {
+                // my cnt codes sit in the low 2*cnt bits of CP: drop them at bit 2*(n_stage+ex) of the big-endian stream
+                const uint32_t bitpos = 2u * (n_stage + ex);
+                const uint64_t v = ((uint64_t) CP << (64 - 2 * cnt)) >> (bitpos & 31u);
+                atomicOr(&s_w[bitpos >> 5], (uint32_t) (v >> 32));
+                if ((uint32_t) v) atomicOr(&s_w[(bitpos >> 5) + 1], (uint32_t) v);
             }
         }
         const bool last = (t + 1 == ntiles);
         const uint32_t n_avail = n_stage + tot;
-        if (last && tid == 0) s_pos[n_avail] = len;
+        if (last && tid == 0 && n_avail) close_run(n_avail - 1, (uint32_t) ((int) len - blast - 1));
         __syncthreads();
-        const uint32_t closed = last ? n_avail : (n_avail ? n_avail - 1 : 0);
-        const uint32_t fin = last ? closed : (closed & ~15u);
+        const uint32_t fin = last ? n_avail : (n_avail ? ((n_avail - 1) & ~15u) : 0);
 
-        // finalise groups of 16 hoco bases: run lengths -> 16 bytes, codes -> one big-endian word,
-        // ambiguity flags -> 16 bits; everything from vector loads of the staging arrays
+        // write the finished groups of 16: one code word, 16 run-length bytes, 16 flags
         const uint32_t ngrp = (fin + 15) >> 4;
         for (uint32_t gi = tid; gi < ngrp; gi += NT) {
-            const uint32_t e0 = gi * 16;
-            const uint32_t nval = min(16u, fin - e0);             // entries of this group that exist
-            uint32_t ps[17];
-            {
-                const uint4 *q4 = reinterpret_cast<const uint4 *>(s_pos + e0);
-                const uint4 a = q4[0], b4 = q4[1], c4 = q4[2], d4 = q4[3];
-                ps[0] = a.x; ps[1] = a.y; ps[2] = a.z; ps[3] = a.w; ps[4] = b4.x; ps[5] = b4.y; ps[6] = b4.z; ps[7] = b4.w;
-                ps[8] = c4.x; ps[9] = c4.y; ps[10] = c4.z; ps[11] = c4.w; ps[12] = d4.x; ps[13] = d4.y; ps[14] = d4.z; ps[15] = d4.w;
-                ps[16] = s_pos[e0 + 16];
-            }
-            uint32_t rl[16], big = 0;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                rl[j] = (uint32_t) j < nval ? ps[j + 1] - ps[j] - 1u : 0u;     // run length - 1
-                big |= rl[j];
-            }
-            const uint4 cw = *reinterpret_cast<const uint4 *>(s_code + e0);
-            const uint32_t w[4] = {cw.x, cw.y, cw.z, cw.w};
-            uint32_t word = 0, nbw = 0;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                uint32_t x = w[j];
-                if ((uint32_t) (4 * j) >= nval) x = 0;
-                else if (nval - 4 * j < 4) x &= (1u << (8 * (nval - 4 * j))) - 1u;
-                word |= (((x & 0x03030303u) * 0x40100401u) >> 24) << (24 - 8 * j);
-                nbw |= ((((x >> 2) & 0x01010101u) * 0x00204081u >> 21) & 0xFu) << (4 * j);   // gather bit 2 of 4 bytes
-            }
-            if (big >= 255u) {
-                // a run longer than 256 saturates ho_rl and goes to the side list (syncmer.c:301-304)
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    if (rl[j] >= 255u) {
-                        unsigned long long o = atomicAdd(A.lrl_count, 1ull);
-                        if (o < A.lrl_cap) { A.lrl_sid[o] = sid; A.lrl_idx[o] = g_done + e0 + j; A.lrl_val[o] = rl[j]; }
-                        rl[j] = 255u;
-                    }
-                }
-            }
-            if (nbw) {
-                for (uint32_t mm = nbw; mm; mm &= mm - 1) {
-                    const int j = __ffs(mm) - 1;
-                    unsigned long long o = atomicAdd(A.amb_count, 1ull);
-                    if (o < A.amb_cap) { A.amb_sid[o] = sid; A.amb_pos[o] = s_pos[e0 + j]; }
-                }
-                atomicAdd(&s_namb, (uint32_t) __popc(nbw));
-            }
-            uint4 out;
-            out.x = rl[0] | rl[1] << 8 | rl[2] << 16 | rl[3] << 24;
-            out.y = rl[4] | rl[5] << 8 | rl[6] << 16 | rl[7] << 24;
-            out.z = rl[8] | rl[9] << 8 | rl[10] << 16 | rl[11] << 24;
-            out.w = rl[12] | rl[13] << 8 | rl[14] << 16 | rl[15] << 24;
-            *reinterpret_cast<uint4 *>(rl8 + g_done + e0) = out;      // capacity is padded to 64: a full store always fits
-            hs32[(g_done >> 4) + gi] = bswap32(word);
-            nb16[(g_done >> 4) + gi] = (uint16_t) nbw;
+            hs32[(g_done >> 4) + gi] = bswap32(s_w[gi]);
+            nb16[(g_done >> 4) + gi] = (uint16_t) (s_nbw[gi >> 1] >> (16 * (gi & 1)));
+            *reinterpret_cast<uint4 *>(rl8 + g_done + 16 * gi) = *reinterpret_cast<const uint4 *>(s_rl + 16 * gi);
         }
-        // carry the tail (open run and incomplete group) to the front
+        // what stays staged: the open run and an incomplete group (at most 16 entries, one word)
         const uint32_t n_carry = n_avail - fin;
-        uint8_t cc = 0; uint32_t cp = 0;
-        if ((uint32_t) tid < n_carry) { cc = s_code[fin + tid]; cp = s_pos[fin + tid]; }
+        const uint32_t cw = s_w[fin >> 4], cn = (s_nbw[fin >> 5] >> (fin & 16u)) & 0xffffu;
+        uint8_t cb = 0;
+        if ((uint32_t) tid < n_carry) cb = s_rl[fin + tid];
         __syncthreads();
-        if ((uint32_t) tid < n_carry) { s_code[tid] = cc; s_pos[tid] = cp; }
-        __syncthreads();
+        if ((uint32_t) tid < n_carry) s_rl[tid] = cb;
+        for (int i = tid; i < NWORD; i += NT) s_w[i] = (i == 0 && n_carry) ? cw : 0u;
+        for (int i = tid; i < NWORD / 2 + 2; i += NT) s_nbw[i] = (i == 0 && n_carry) ? cn : 0u;
         n_stage = n_carry;
         g_done += fin;
+        carry_last = blast;
+        // the two barriers of the next tile's scan order these writes before anybody stages again
     }
     if (tid == 0) {
         A.hoco_l[r] = g_done;
@@ -220,7 +233,7 @@ __global__ void __launch_bounds__(NT) encode_kernel(EncodeArgs A)
 int launch_encode(const EncodeArgs &A, uint64_t n_reads, cudaStream_t st)
 {
     if (n_reads == 0) return 0;
-    encode_kernel<256><<<(unsigned) n_reads, 256, 0, st>>>(A);
+    encode_kernel<128><<<(unsigned) n_reads, 128, 0, st>>>(A);
     return 1;
 }
 

@@ -1,0 +1,71 @@
+/*
+ * graph_gpu.h -- host side of rows a7-a9: the reference's graph.h / syncasm.h interface
+ * for building the syncmer graph and merging unitigs (reference graph.h:39-96,
+ * syncasm.h:51-64, 94-97). Structs are byte-compatible with the reference's.
+ *
+ * The arc tally runs on the GPU (sg_arcs); what is left is small (a few 10^4 vertices
+ * after the coverage filter) and order-sensitive, so it stays on the host:
+ *   make_syncmer_graph        syncasm.c:203-299   vertices + arcs -> asmg_finalize -> index
+ *   asmg_finalize             graph.c:250-263     cleanup, sort, index, symmetry repair, link ids
+ *   asmg_unitigging           graph.c:905-1105    three ordered walks, singletons, arc remap, list expansion
+ *   process_mergeable_unitigs syncasm.c:1048-1061
+ */
+#ifndef GRAPH_GPU_H
+#define GRAPH_GPU_H
+#include "syncmer_gpu.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef __GRAPH_H__
+typedef struct {
+    uint64_t v, w;
+    uint64_t ln, ls;
+    uint32_t cov:30, del:1, comp:1;
+    uint64_t link_id;
+} asmg_arc_t;
+
+typedef struct {
+    uint64_t n;
+    uint64_t *a;
+    char *seq;
+    uint64_t len;
+    uint32_t cov:30, del:1, circ:1;
+} asmg_vtx_t;
+
+typedef struct {
+    uint64_t n_vtx, m_vtx;
+    asmg_vtx_t *vtx;
+    uint64_t n_arc, m_arc;
+    asmg_arc_t *arc;
+    uint64_t *idx_p;
+    uint64_t *idx_n;
+} asmg_t;
+#endif
+
+#ifndef __SYNCASM_H__
+typedef struct {
+    syncmer_db_t *scm_db;      /* borrowed */
+    asmg_t *utg_asmg;
+    uint128_t *scm_u;          /* scm_id[49] | scm_rev[1] | utg_id[42] | utg_pos[36], sorted */
+    uint128_t **idx_u;         /* n_scm + 1 pointers into scm_u */
+} scg_t;
+#endif
+
+void asmg_destroy(asmg_t *g);
+void asmg_arc_sort(asmg_t *g);
+void asmg_arc_index(asmg_t *g);
+void asmg_shrink_link_id(asmg_t *g);
+void asmg_finalize(asmg_t *g, int do_cleanup);
+asmg_t *asmg_unitigging(asmg_t *g);
+
+scg_t *make_syncmer_graph(sr_db_t *sr_db, syncmer_db_t *scm_db, uint32_t min_k_cov, double min_a_cov_f);
+void process_mergeable_unitigs(scg_t *g);
+void scg_destroy(scg_t *g);
+void scg_stat(scg_t *scg, FILE *fo, uint64_t *stats);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

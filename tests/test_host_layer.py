@@ -113,6 +113,43 @@ def test_drop_in_structs_feed_the_reference(host, ref, k, s):
     ref.free(rdb, rscm)
 
 
+@pytest.mark.parametrize("k,s,mkc", [(1001, 31, 3), (301, 15, 2), (501, 31, 30)])
+def test_graph_layer_matches_reference(host, ref, k, s, mkc):
+    """a7-a9 of the host layer (make_syncmer_graph over the device arc tally, asmg_finalize,
+    asmg_unitigging) against the reference's graph.c / syncasm.c on the same reads"""
+    host.make_syncmer_graph.restype = C.c_void_p
+    host.make_syncmer_graph.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_double]
+    host.process_mergeable_unitigs.argtypes = [C.c_void_p]
+    host.scg_destroy.argtypes = [C.c_void_p]
+    # 60x coverage of a small genome (so that -c 30 leaves a graph) plus the adversarial reads
+    reads = synth.hifi_reads(77, 60000, 240 if mkc < 30 else 400, 15000, 0.002) + synth.adversarial_reads(3, k, s) * 2
+    bases, off = pack_reads(reads)
+    db = SrDb()
+    host.sr_db_init(C.byref(db), k, s)
+    assert host.sr_read_mem(C.byref(db), bases.ctypes.data, off.ctypes.data, None, len(reads)) == 0
+    scm = host.collect_syncmer_from_reads(C.byref(db))
+    rdb, _ = ref.extract(bases, off, k, s)
+    rscm = ref.collect(rdb)
+    for a in (0.35, 0.0):
+        g_mine = host.make_syncmer_graph(C.byref(db), scm, mkc, a)
+        g_ref = ref.graph(rdb, rscm, mkc, a)
+        assert g_mine and g_ref
+        d1, d2 = ref.graph_dump(g_mine), ref.graph_dump(g_ref)      # the reference's dump walks OUR scg_t
+        for f in d1:
+            assert np.array_equal(d1[f], d2[f]), ("graph", f, a)
+        assert len(d1["arcs"]) > 0
+        host.process_mergeable_unitigs(g_mine)
+        ref.unitig(g_ref)
+        d1, d2 = ref.graph_dump(g_mine), ref.graph_dump(g_ref)
+        for f in d1:
+            assert np.array_equal(d1[f], d2[f]), ("unitigs", f, a)
+        host.scg_destroy(g_mine)
+        ref.free(g=g_ref)
+    host.syncmer_db_destroy(scm)
+    host.sr_db_clean(C.byref(db))
+    ref.free(rdb, rscm)
+
+
 def test_empty_collection(host):
     bases, off = pack_reads([b"ACGTTGCA", b"NNNN", b""])
     db = SrDb()
