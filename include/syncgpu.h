@@ -42,6 +42,7 @@ extern "C" {
 #define SG_E_SMER_CONFLICT -6  /* identical k-mers with different s-mer codes (reference exits, syncmer.c:1370-1376) */
 #define SG_E_EMPTY        -7   /* no syncmers in the batch (reference returns NULL, syncmer.c:1414-1417) */
 #define SG_E_STATE        -8   /* call order violated (e.g. sg_count before sg_extract) */
+#define SG_E_COLLISION    -9   /* multi-GPU only: two different k-mers of different GPUs share a 64-bit hash */
 
 typedef struct sg_ctx sg_ctx;
 typedef struct sg_batch sg_batch;
@@ -132,6 +133,12 @@ int sg_stat(sg_batch *b, sg_stat_t *out);                     /* synchronises */
  * k-mer (splitting it like process_kmer_cluster when it does not), assigns
  * dense ids in hash order and rewrites k_mer[] to id << 1. */
 int sg_count(sg_batch *b);
+/* How sg_count decides that two tuples of equal hash are the same k-mer. 0 (default): equal hash and
+ * equal 64-bit fingerprint (a second, independent hash of the same packed k-mer, computed by
+ * sg_extract); a group with differing fingerprints is then split by exact sequence comparison like
+ * process_kmer_cluster. 1: the packed k-mers themselves are compared for every tuple, as the
+ * reference does (syncmer.c:1283-1333). Same results unless two different k-mers agree in all 128 bits. */
+int sg_batch_set_exact_verify(sg_batch *b, int on);
 typedef struct {
     uint64_t n_syncmers;      /* occurrences */
     uint64_t n_unique;        /* syncmer_db_t.n */
@@ -199,9 +206,9 @@ int sg_debug_set_hash_bits(sg_batch *b, int bits);
 /* ---- multi-GPU exchange (one process per GPU; the transport is the caller's
  * collective, e.g. NCCL all-to-all; see oatk_b200/dist.py) ---- */
 /* partition this batch's tuples by hash range into n_parts buckets: counts[p] tuples for part p,
- * laid out contiguously in an internal device buffer of 3 x uint64 per tuple (hash, occ, s_mer) */
+ * laid out contiguously in an internal device buffer of 4 x uint64 per tuple (hash, occ, s_mer, fingerprint) */
 int sg_tuples_partition(sg_batch *b, int n_parts, uint64_t *counts /* host, n_parts */, void **d_tuples /* device ptr out */);
-/* replace this batch's tuple set by tuples received from the peers (device pointer, n tuples of 3 x uint64) */
+/* replace this batch's tuple set by tuples received from the peers (device pointer, n tuples of 4 x uint64) */
 int sg_tuples_adopt(sg_batch *b, const void *d_tuples, uint64_t n);
 /* after sg_count on adopted tuples: (occ, (id + id_base) << 1) pairs in adopted order, 2 x uint64 each,
  * to be sent back to the ranks the tuples came from (same split sizes, reversed) */

@@ -68,6 +68,7 @@ const char *sg_strerror(int code)
         case SG_E_SMER_CONFLICT: return "identical kmers have different smers";
         case SG_E_EMPTY: return "empty syncmer collection";
         case SG_E_STATE: return "call order violated";
+        case SG_E_COLLISION: return "64-bit k-mer hash collision across GPUs";
     }
     return "unknown error";
 }
@@ -272,7 +273,7 @@ int sg_extract(sg_batch *b, int k, int s)
         if (attempt == 3) { ctx->err = "side-list capacity did not converge"; return SG_E_NOMEM; }
     }
     const uint64_t N = b->n_syncmers;
-    RS(b->key, (N + 1) * 8); RS(b->occ, (N + 1) * 8); RS(b->m_pos, (N + 1) * 4); RS(b->s_mer, (N + 1) * 8);
+    RS(b->key, (N + 1) * 8); RS(b->occ, (N + 1) * 8); RS(b->m_pos, (N + 1) * 4); RS(b->s_mer, (N + 1) * 8); RS(b->fp, (N + 1) * 8);
     ctx->t_begin(SG_T_KMERHASH);
     KmerArgs K;
     K.hoff = (const uint64_t *) b->hoff.p; K.hoco_s = (const uint8_t *) b->hoco_s.p; K.hoco_l = (const uint32_t *) b->hoco_l.p;
@@ -280,6 +281,7 @@ int sg_extract(sg_batch *b, int k, int s)
     K.rec_sid = (const uint32_t *) b->rec_sid.p; K.rec_idx = (const uint32_t *) b->rec_idx.p; K.rec_mpos = (const uint32_t *) b->rec_mpos.p;
     K.rec_smer = (const uint64_t *) b->rec_smer.p; K.scm_off = (const uint64_t *) b->scm_off.p;
     K.sid_base = b->sid_base;
+    K.fp = (uint64_t *) b->fp.p;
     K.key = (uint64_t *) b->key.p; K.occ = (uint64_t *) b->occ.p; K.m_pos = (uint32_t *) b->m_pos.p; K.s_mer = (uint64_t *) b->s_mer.p;
     LAUNCHED(SG_T_KMERHASH, launch_kmerhash(K, st));
     ctx->t_end(SG_T_KMERHASH);

@@ -139,20 +139,20 @@ __global__ void __launch_bounds__(256) part_key_kernel(const uint64_t *key, uint
 }
 
 __global__ void __launch_bounds__(256) part_gather_kernel(const uint64_t *pkey, const uint64_t *pval, const uint64_t *key, const uint64_t *occ,
-        const uint64_t *smer, uint64_t n, uint64_t *tuples, unsigned long long *counts)
+        const uint64_t *smer, const uint64_t *fp, uint64_t n, uint64_t *tuples, unsigned long long *counts)
 {
     const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint64_t o = pval[i];
-    tuples[3 * i + 0] = key[o]; tuples[3 * i + 1] = occ[o]; tuples[3 * i + 2] = smer[o];
+    tuples[4 * i + 0] = key[o]; tuples[4 * i + 1] = occ[o]; tuples[4 * i + 2] = smer[o]; tuples[4 * i + 3] = fp[o];
     if (i == n - 1 || pkey[i + 1] != pkey[i]) atomicMax(counts + pkey[i], (unsigned long long) (i + 1));   // end offset of this part
 }
 
-__global__ void __launch_bounds__(256) adopt_kernel(const uint64_t *tuples, uint64_t n, uint64_t *key, uint64_t *occ, uint64_t *smer)
+__global__ void __launch_bounds__(256) adopt_kernel(const uint64_t *tuples, uint64_t n, uint64_t *key, uint64_t *occ, uint64_t *smer, uint64_t *fp)
 {
     const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    key[i] = tuples[3 * i]; occ[i] = tuples[3 * i + 1]; smer[i] = tuples[3 * i + 2];
+    key[i] = tuples[4 * i]; occ[i] = tuples[4 * i + 1]; smer[i] = tuples[4 * i + 2]; fp[i] = tuples[4 * i + 3];
 }
 
 // ids coming back from the GPU that owns the hash range: pairs (occ, id << 1) for occurrences on local reads
@@ -266,7 +266,7 @@ int sg_tuples_partition(sg_batch *b, int n_parts, uint64_t *counts, void **d_tup
     const uint64_t N = b->n_syncmers;
     RS(b->skey, (N + 1) * 8); RS(b->sval, (N + 1) * 8); RS(b->skey_alt, (N + 1) * 8); RS(b->sval_alt, (N + 1) * 8);
     RS(b->sort_tmp, sort_tmp_words(std::max<uint64_t>(N, 1)) * 4);
-    RS(b->tuples, (N + 1) * 24);
+    RS(b->tuples, (N + 1) * 32);
     RS(b->status, 4 * 8);
     RS(b->part_counts, 257 * 8);
     CK(cudaMemsetAsync(b->part_counts.p, 0, 257 * 8, st));
@@ -277,7 +277,7 @@ int sg_tuples_partition(sg_batch *b, int n_parts, uint64_t *counts, void **d_tup
         LAUNCHED(SG_T_SORT, launch_sort_pairs((uint64_t *) b->skey.p, (uint64_t *) b->sval.p, (uint64_t *) b->skey_alt.p,
                 (uint64_t *) b->sval_alt.p, N, 0, 8, (uint32_t *) b->sort_tmp.p, st));
         part_gather_kernel<<<nblk(N, 256), 256, 0, st>>>((const uint64_t *) b->skey.p, (const uint64_t *) b->sval.p,
-                (const uint64_t *) b->key.p, (const uint64_t *) b->occ.p, (const uint64_t *) b->s_mer.p, N,
+                (const uint64_t *) b->key.p, (const uint64_t *) b->occ.p, (const uint64_t *) b->s_mer.p, (const uint64_t *) b->fp.p, N,
                 (uint64_t *) b->tuples.p, (unsigned long long *) b->part_counts.p);
         ctx->count_launch(SG_T_SORT, 1);
     }
@@ -304,9 +304,9 @@ int sg_tuples_adopt(sg_batch *b, const void *d_tuples, uint64_t n)
     cudaStream_t st = ctx->stream;
     CK(cudaSetDevice(ctx->device));
     // keep the local read-order arrays for the id write-back; the tuple set being counted is replaced
-    RS(b->akey, (n + 1) * 8); RS(b->aocc, (n + 1) * 8); RS(b->asmer, (n + 1) * 8);
+    RS(b->akey, (n + 1) * 8); RS(b->aocc, (n + 1) * 8); RS(b->asmer, (n + 1) * 8); RS(b->afp, (n + 1) * 8);
     if (n) {
-        adopt_kernel<<<nblk(n, 256), 256, 0, st>>>((const uint64_t *) d_tuples, n, (uint64_t *) b->akey.p, (uint64_t *) b->aocc.p, (uint64_t *) b->asmer.p);
+        adopt_kernel<<<nblk(n, 256), 256, 0, st>>>((const uint64_t *) d_tuples, n, (uint64_t *) b->akey.p, (uint64_t *) b->aocc.p, (uint64_t *) b->asmer.p, (uint64_t *) b->afp.p);
         ctx->count_launch(SG_T_SORT, 1);
     }
     CK(cudaGetLastError());
@@ -324,7 +324,7 @@ int sg_ids_pack(sg_batch *b, uint64_t id_base, void **d_pairs, uint64_t *n)
     cudaStream_t st = ctx->stream;
     CK(cudaSetDevice(ctx->device));
     const uint64_t N = b->n_adopted;
-    RS(b->tuples, (N + 1) * 24);
+    RS(b->tuples, (N + 1) * 32);
     if (N) {
         pair_pack_kernel<<<nblk(N, 256), 256, 0, st>>>((const uint64_t *) b->aocc.p, (const uint64_t *) b->kid.p, N, id_base, (uint64_t *) b->tuples.p);
         ctx->count_launch(SG_T_GROUP, 1);

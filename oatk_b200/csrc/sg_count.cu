@@ -33,11 +33,24 @@ __global__ void __launch_bounds__(256) tuple_init_kernel(const uint64_t *key, ui
     if (i < n) { skey[i] = key[i] & hmask; sval[i] = i; }
 }
 
-__global__ void __launch_bounds__(256) tuple_gather_kernel(const uint64_t *sval, const uint64_t *occ, const uint64_t *smer,
-        uint64_t *socc, uint64_t *ssmer, uint64_t n)
+__global__ void __launch_bounds__(256) tuple_gather_kernel(const uint64_t *sval, const uint64_t *occ, const uint64_t *smer, const uint64_t *fp,
+        uint64_t *socc, uint64_t *ssmer, uint64_t *sfp, uint64_t n)
 {
     const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) { const uint64_t o = sval[i]; socc[i] = occ[o]; ssmer[i] = smer[o]; }
+    if (i < n) { const uint64_t o = sval[i]; socc[i] = occ[o]; ssmer[i] = smer[o]; sfp[i] = fp[o]; }
+}
+
+// default group test: a tuple continues its predecessor's class when hash AND fingerprint agree
+__global__ void __launch_bounds__(256) verify_fp_kernel(const uint64_t *skey, const uint64_t *sfp, uint64_t n, uint32_t *newid,
+        uint8_t *differs, unsigned long long *status)
+{
+    const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const bool same = i > 0 && skey[i] == skey[i - 1];
+    const bool neq = same && sfp[i] != sfp[i - 1];
+    newid[i] = same ? 0u : 1u;
+    differs[i] = neq ? 1 : 0;
+    if (neq) atomicAdd(status + 1, 1ull);
 }
 
 struct VerifyArgs {
@@ -260,7 +273,7 @@ static int ensure_sorted(sg_batch *b)
     const uint64_t N = b->t_n();
     RS(b->skey, (N + 1) * 8); RS(b->sval, (N + 1) * 8); RS(b->skey_alt, (N + 1) * 8); RS(b->sval_alt, (N + 1) * 8);
     RS(b->sort_tmp, sort_tmp_words(N) * 4);
-    RS(b->socc, (N + 1) * 8); RS(b->ssmer, (N + 1) * 8);
+    RS(b->socc, (N + 1) * 8); RS(b->ssmer, (N + 1) * 8); RS(b->sfp, (N + 1) * 8);
     ctx->t_begin(SG_T_SORT);
     const uint64_t hmask = b->hash_bits >= 64 ? ~0ull : ((1ull << b->hash_bits) - 1);
     tuple_init_kernel<<<nblk(N, 256), 256, 0, st>>>(b->t_key(), (uint64_t *) b->skey.p, (uint64_t *) b->sval.p, N, hmask);
@@ -268,7 +281,7 @@ static int ensure_sorted(sg_batch *b)
     LAUNCHED(SG_T_SORT, launch_sort_pairs((uint64_t *) b->skey.p, (uint64_t *) b->sval.p, (uint64_t *) b->skey_alt.p,
             (uint64_t *) b->sval_alt.p, N, 0, b->hash_bits >= 64 ? 64 : ((b->hash_bits + 7) & ~7), (uint32_t *) b->sort_tmp.p, st));
     tuple_gather_kernel<<<nblk(N, 256), 256, 0, st>>>((const uint64_t *) b->sval.p, b->t_occ(),
-            b->t_smer(), (uint64_t *) b->socc.p, (uint64_t *) b->ssmer.p, N);
+            b->t_smer(), b->t_fp(), (uint64_t *) b->socc.p, (uint64_t *) b->ssmer.p, (uint64_t *) b->sfp.p, N);
     ctx->count_launch(SG_T_SORT, 1);
     ctx->t_end(SG_T_SORT);
     CK(cudaGetLastError());
@@ -299,6 +312,14 @@ static int mult_table(sg_batch *b, const uint64_t *sorted, uint64_t N, int shift
 }
 
 extern "C" {
+
+int sg_batch_set_exact_verify(sg_batch *b, int on)
+{
+    if (!b) return SG_E_ARG;
+    b->exact_verify = on != 0;
+    b->counted = false;
+    return SG_OK;
+}
 
 int sg_debug_set_hash_bits(sg_batch *b, int bits)
 {
@@ -380,21 +401,23 @@ int sg_count(sg_batch *b)
     V.m_pos = (const uint32_t *) b->m_pos.p; V.hoff = (const uint64_t *) b->hoff.p; V.hoco_s = (const uint8_t *) b->hoco_s.p;
     V.hoco_l = (const uint32_t *) b->hoco_l.p; V.sid_base = b->sid_base; V.n = N; V.k = b->k;
     V.newid = (uint32_t *) b->flags.p; V.differs = (uint8_t *) b->differs.p; V.status = status;
-    if (!b->adopted) {
+    if (b->exact_verify && !b->adopted) {
         const uint64_t warps = (N + 30) / 31 + 1;
         verify_kernel<<<nblk(warps * 32, 256), 256, 0, st>>>(V);
         ctx->count_launch(SG_T_GROUP, 1);
     } else {
-        // tuples adopted from other GPUs: their reads are not here, so groups are formed on the 64-bit
-        // hash alone (DESIGN.md section 7 discusses the 2^-64 residual)
-        run_heads_kernel<<<nblk(N, 256), 256, 0, st>>>((const uint64_t *) b->skey.p, N, 0, (uint32_t *) b->flags.p);
+        // hash + independent 64-bit fingerprint (also what travels with tuples adopted from other GPUs,
+        // whose reads are not here)
+        verify_fp_kernel<<<nblk(N, 256), 256, 0, st>>>((const uint64_t *) b->skey.p, (const uint64_t *) b->sfp.p, N,
+                (uint32_t *) b->flags.p, (uint8_t *) b->differs.p, status);
         ctx->count_launch(SG_T_GROUP, 1);
     }
     unsigned long long hs[4];
     CK(cudaMemcpyAsync(hs, status, sizeof(hs), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     b->n_collisions = 0;
-    if (hs[1] && !b->adopted) {
+    if (hs[1] && b->adopted) { ctx->err = "64-bit hash collision between k-mers of different GPUs: count this input on one GPU"; return SG_E_COLLISION; }
+    if (hs[1]) {
         // some hash group holds more than one k-mer: rebuild those groups the way process_kmer_cluster does
         RS(b->cls, (N + 1) * 4);
         SplitArgs S;

@@ -161,14 +161,32 @@ __global__ void __launch_bounds__(NT) encode_kernel(EncodeArgs A)
         {
             uint32_t e = n_stage + ex, CP = 0;
             if (fast) {
+                // branch-free steps: selects and one predicated byte store each; runs of 256+ are rare and
+                // are only noticed here (big), then pushed to the side list by a second pass
+                uint32_t big = 0;
+                const int prev0 = prev;
+                const uint32_t e0 = e;
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                    if (M & (1u << (2 * (15 - i)))) {
-                        const uint32_t rl1 = (uint32_t) (rel + i - prev - 1);
-                        if (rl1 >= 255u) close_run(e - 1, rl1); else s_rl[(int) e - 1] = (uint8_t) rl1;
-                        prev = rel + i;
-                        CP = CP * 4u + ((P >> (2 * (15 - i))) & 3u);
-                        ++e;
+                    const bool st = (M >> (2 * (15 - i))) & 1u;
+                    const uint32_t rl1 = (uint32_t) (rel + i - prev - 1);
+                    if (st) s_rl[(int) e - 1] = (uint8_t) min(rl1, 255u);
+                    big |= st ? rl1 : 0u;
+                    prev = st ? rel + i : prev;
+                    CP = st ? CP * 4u + ((P >> (2 * (15 - i))) & 3u) : CP;
+                    e += st;
+                }
+                if (big >= 255u) {
+                    int pv = prev0;
+                    uint32_t ee = e0, m = M;
+                    while (m) {
+                        const int b = 31 - __clz(m);
+                        m &= ~(1u << b);
+                        const int i = 15 - (b >> 1);
+                        const uint32_t rl1 = (uint32_t) (rel + i - pv - 1);
+                        if (rl1 >= 255u) close_run(ee - 1, rl1);
+                        pv = rel + i;
+                        ++ee;
                     }
                 }
             } else {

@@ -49,7 +49,7 @@ struct sg_batch {
     uint64_t amb_cap = 0, lrl_cap = 0, rec_cap = 0;
     sg::DevBuf amb_sid, amb_pos, lrl_sid, lrl_idx, lrl_val;
     sg::DevBuf rec_sid, rec_idx, rec_mpos, rec_smer;
-    sg::DevBuf key, occ, m_pos, s_mer;          // read order, one entry per syncmer
+    sg::DevBuf key, occ, m_pos, s_mer, fp;      // read order, one entry per syncmer (fp: second hash)
     // download staging
     sg::DevBuf pk_hs, pk_rl, pk_hs_off, pk_rl_off;
     std::vector<uint32_t> h_hoco_l, h_n_scm;
@@ -59,6 +59,7 @@ struct sg_batch {
     sg::DevBuf skey, sval, skey_alt, sval_alt, sort_tmp;
     sg::DevBuf socc, ssmer, flags, ids, ids_tmp, differs, cls, starts, stat_dev, skey2, sval2;
     bool sorted = false;
+    bool exact_verify = false;                   // sg_batch_set_exact_verify: compare packed k-mers instead of fingerprints
     int hash_bits = 64;                          // < 64 only through sg_debug_set_hash_bits (tests)
     sg::DevBuf scm_h, scm_s, scm_cov, scm_occ_off, status;
     uint64_t n_unique = 0, n_collisions = 0;
@@ -66,7 +67,7 @@ struct sg_batch {
     sg::DevBuf arc_keys, arc_vals, arc_out, arc_okey, arc_oval, arc_okey_alt, arc_oval_alt;
     uint64_t n_arcs = 0, arc_cap = 0;
     // multi-GPU exchange: tuples adopted from the peers replace the local tuple set for a5/a6
-    sg::DevBuf tuples, part_counts, akey, aocc, asmer, kid_local;
+    sg::DevBuf tuples, part_counts, akey, aocc, asmer, afp, kid_local, sfp;
     bool have_kid_local = false;
     bool adopted = false;
     bool pipe_fed = false;                       // filled by sg_pipe_run_host: no ho_rl / raw reads on the device
@@ -75,6 +76,7 @@ struct sg_batch {
     const uint64_t *t_key() const { return (const uint64_t *) (adopted ? akey.p : key.p); }
     const uint64_t *t_occ() const { return (const uint64_t *) (adopted ? aocc.p : occ.p); }
     const uint64_t *t_smer() const { return (const uint64_t *) (adopted ? asmer.p : s_mer.p); }
+    const uint64_t *t_fp() const { return (const uint64_t *) (adopted ? afp.p : fp.p); }
     uint64_t t_n() const { return adopted ? n_adopted : n_syncmers; }
 };
 

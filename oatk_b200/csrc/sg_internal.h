@@ -52,6 +52,7 @@ struct KmerArgs {
     uint64_t sid_base;
     // ordered outputs (read order)
     uint64_t *key;               // k-mer hash
+    uint64_t *fp;                // independent second hash of the same k-mer
     uint64_t *occ;               // sid << 32 | idx << 1 | rev
     uint32_t *m_pos;
     uint64_t *s_mer;

@@ -18,21 +18,29 @@
 
 namespace sg {
 
-__device__ __forceinline__ uint64_t kmer_murmur(const uint32_t *hs, int64_t nwords, int64_t start, int k, int rev)
+// Besides the reference's MurmurHash64A, a second, independent 64-bit hash of the same oriented
+// words (multiply-xorshift chain with other constants, over the big-endian blocks). Hash and
+// fingerprint together decide "same k-mer" in sg_count's default mode; see DESIGN.md section 8.
+__device__ __forceinline__ uint64_t kmer_murmur(const uint32_t *hs, int64_t nwords, int64_t start, int k, int rev, uint64_t *fp_out)
 {
-    const uint64_t M = 0xc6a4a7935bd1e995ull;
+    const uint64_t M = 0xc6a4a7935bd1e995ull, F = 0x9e3779b97f4a7c15ull;
     const uint32_t nbytes = (uint32_t) (k + 3) >> 2, nblk = nbytes >> 3;
-    uint64_t h = 1234ull ^ ((uint64_t) nbytes * M);
+    uint64_t h = 1234ull ^ ((uint64_t) nbytes * M), f = 0x243f6a8885a308d3ull ^ (uint64_t) k;
     for (uint32_t j = 0; j < nblk; ++j) {
-        uint64_t w = bswap64(oriented_block(hs, nwords, start, k, rev, (int) j));
+        const uint64_t be = oriented_block(hs, nwords, start, k, rev, (int) j);
+        uint64_t w = bswap64(be);
         w *= M; w ^= w >> 47; w *= M;
         h = (h ^ w) * M;
+        f = (f ^ be) * F; f ^= f >> 32;
     }
     if (nbytes & 7u) {
-        const uint64_t w = bswap64(oriented_block(hs, nwords, start, k, rev, (int) nblk));
-        h = (h ^ w) * M;
+        const uint64_t be = oriented_block(hs, nwords, start, k, rev, (int) nblk);
+        h = (h ^ bswap64(be)) * M;
+        f = (f ^ be) * F; f ^= f >> 32;
     }
     h ^= h >> 47; h *= M; h ^= h >> 47;
+    f *= 0xd6e8feb86659fd93ull; f ^= f >> 29;
+    *fp_out = f;
     return h;
 }
 
@@ -44,9 +52,11 @@ __global__ void __launch_bounds__(256) kmerhash_kernel(KmerArgs A)
     const uint64_t hb = A.hoff[sid];
     const uint32_t *hs32 = reinterpret_cast<const uint32_t *>(A.hoco_s + hb / 4);
     const int64_t nwords = ((int64_t) A.hoco_l[sid] + 15) >> 4;
-    const uint64_t h = kmer_murmur(hs32, nwords, mp >> 1, A.k, mp & 1u);
+    uint64_t fp;
+    const uint64_t h = kmer_murmur(hs32, nwords, mp >> 1, A.k, mp & 1u, &fp);
     const uint64_t o = A.scm_off[sid] + idx;
     A.key[o] = h;
+    A.fp[o] = fp;
     A.occ[o] = (A.sid_base + sid) << 32 | (uint64_t) idx << 1 | (mp & 1u);
     A.m_pos[o] = mp;
     A.s_mer[o] = A.rec_smer[i];

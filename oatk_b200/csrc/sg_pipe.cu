@@ -113,7 +113,7 @@ int sg_pipe_run_host(sg_pipe *p, const char *bases, const uint64_t *off, uint64_
     const uint64_t cap_pos = total + 64 * n_reads + 64, capN = caps->max_syncmers;
     if (M->hoff.reserve((n_reads + 1) * 8) || M->hoco_s.reserve(cap_pos / 4 + 64) || M->hoco_l.reserve((n_reads + 1) * 4) ||
             M->n_scm.reserve((n_reads + 1) * 4) || M->scm_off.reserve((n_reads + 1) * 8) || M->n_amb.reserve((n_reads + 1) * 4) ||
-            M->key.reserve((capN + 1) * 8) || M->occ.reserve((capN + 1) * 8) || M->m_pos.reserve((capN + 1) * 4) || M->s_mer.reserve((capN + 1) * 8))
+            M->key.reserve((capN + 1) * 8) || M->occ.reserve((capN + 1) * 8) || M->m_pos.reserve((capN + 1) * 4) || M->s_mer.reserve((capN + 1) * 8) || M->fp.reserve((capN + 1) * 8))
         return fail(SG_E_NOMEM, "master allocation failed");
 
     // running totals, advanced in chunk order
@@ -193,6 +193,7 @@ int sg_pipe_run_host(sg_pipe *p, const char *bases, const uint64_t *off, uint64_
                 cudaMemcpyAsync((uint64_t *) M->occ.p + base.scm, b->occ.p, N * 8, cudaMemcpyDeviceToDevice, st);
                 cudaMemcpyAsync((uint32_t *) M->m_pos.p + base.scm, b->m_pos.p, N * 4, cudaMemcpyDeviceToDevice, st);
                 cudaMemcpyAsync((uint64_t *) M->s_mer.p + base.scm, b->s_mer.p, N * 8, cudaMemcpyDeviceToDevice, st);
+                cudaMemcpyAsync((uint64_t *) M->fp.p + base.scm, b->fp.p, N * 8, cudaMemcpyDeviceToDevice, st);
             }
             // ---- this chunk's slice of the caller's arrays ----
             sg_extract_out_t o = *out;

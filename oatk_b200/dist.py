@@ -1,7 +1,7 @@
 """Multi-GPU plumbing for the syncmer counter: one process per GPU, torch.distributed for transport.
 
 The path shards by read (contiguous blocks, so sid = global read index). Extraction needs no
-communication. Counting needs every occurrence of a k-mer on one GPU, so the (hash, occ, s_mer)
+communication. Counting needs every occurrence of a k-mer on one GPU, so the (hash, occ, s_mer, fingerprint)
 tuples are range-partitioned on the hash and exchanged with ONE all-to-all over NVLink; each GPU
 then owns a contiguous hash range and its local hash order is the reference's global order
 restricted to that range. Dense ids are local ranks plus the number of distinct k-mers on the
@@ -80,9 +80,9 @@ class TupleExchange:
         counts, ptr = batch.tuples_partition(self.world)
         self.send_counts = counts
         self.recv_counts = exchange_counts(self.dist, counts, self.device)
-        rows = tensor_from_ptr(ptr, sum(counts) * 3, self.device)
-        got = exchange_rows(self.dist, rows, counts, self.recv_counts, 3)
-        self.bytes_sent = (sum(counts) - counts[self.rank]) * 24
+        rows = tensor_from_ptr(ptr, sum(counts) * 4, self.device)
+        got = exchange_rows(self.dist, rows, counts, self.recv_counts, 4)
+        self.bytes_sent = (sum(counts) - counts[self.rank]) * 32
         batch.tuples_adopt(got.data_ptr(), sum(self.recv_counts))
         torch.cuda.current_stream().synchronize()      # `got` may be freed once the adopt kernel has read it
         return sum(self.recv_counts)

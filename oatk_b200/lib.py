@@ -61,7 +61,7 @@ SYMBOLS = [
     "sg_batch_set_sid_base", "sg_extract", "sg_extract_sizes", "sg_extract_download",
     "sg_stat", "sg_count", "sg_count_sizes", "sg_count_download", "sg_arcs", "sg_arcs_download",
     "sg_tuples_partition", "sg_tuples_adopt", "sg_debug_set_hash_bits", "sg_batch_buffer",
-    "sg_ids_pack", "sg_ids_scatter",
+    "sg_ids_pack", "sg_ids_scatter", "sg_batch_set_exact_verify",
     "sg_pipe_create", "sg_pipe_destroy", "sg_pipe_run_host", "sg_pipe_master", "sg_pipe_ctx", "sg_pipe_last_error", "sg_pipe_launches",
 ]
 
@@ -102,7 +102,7 @@ def _lib():
                        ("sg_arcs", [vp, C.c_uint32, C.c_double, C.POINTER(u64)]), ("sg_arcs_download", [vp, vp]),
                        ("sg_tuples_partition", [vp, i32, vp, C.POINTER(vp)]), ("sg_tuples_adopt", [vp, vp, u64]),
                        ("sg_debug_set_hash_bits", [vp, i32]), ("sg_batch_buffer", [vp, i32, C.POINTER(vp), C.POINTER(u64)]),
-                       ("sg_ids_pack", [vp, u64, C.POINTER(vp), C.POINTER(u64)]), ("sg_ids_scatter", [vp, vp, u64])):
+                       ("sg_ids_pack", [vp, u64, C.POINTER(vp), C.POINTER(u64)]), ("sg_ids_scatter", [vp, vp, u64]), ("sg_batch_set_exact_verify", [vp, i32])):
         if hasattr(L, name):
             getattr(L, name).argtypes = args
     L.sg_pipe_create.argtypes = [i32, i32, C.POINTER(vp)]
@@ -293,6 +293,9 @@ class Batch:
 
     def ids_scatter(self, d_ptr, n):
         _ck(self.ctx.h, _lib().sg_ids_scatter(self.h, d_ptr, n), "sg_ids_scatter")
+
+    def set_exact_verify(self, on=True):
+        _ck(self.ctx.h, _lib().sg_batch_set_exact_verify(self.h, 1 if on else 0), "sg_batch_set_exact_verify")
 
     def debug_set_hash_bits(self, bits):
         _ck(self.ctx.h, _lib().sg_debug_set_hash_bits(self.h, bits), "sg_debug_set_hash_bits")

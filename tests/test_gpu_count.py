@@ -23,8 +23,16 @@ def check_count(gpu_ctx, oracle, reads, k, s, hash_bits=64):
     b = gpu_batch(gpu_ctx, bases, off, k, s)
     if hash_bits != 64:
         b.debug_set_hash_bits(hash_bits)
+    # both group tests: packed k-mers compared for every tuple (the reference's way), then the default
+    # hash + fingerprint test with exact comparison only inside groups whose fingerprints differ
+    b.set_exact_verify(True)
+    b.count()
+    exact = b.count_download()
+    assert not parity.diff(exact, exp, parity.SCM_FIELDS)
+    b.set_exact_verify(False)
     b.count()
     got = b.count_download()
+    assert got["n_hash_collisions"] == exact["n_hash_collisions"]
     d = parity.diff(got, exp, parity.SCM_FIELDS)
     # k_mer[] as the host sees it after collect
     f = b.extract_download(want_seq=False)

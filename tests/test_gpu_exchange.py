@@ -25,7 +25,7 @@ def test_partition_adopt_count(gpu_ctx, oracle, world):
     N = sum(counts)
     assert N == len(exp["occ"])
     dev = torch.device("cuda", 0)
-    rows = sgdist.tensor_from_ptr(ptr, N * 3, dev).clone().view(-1, 3)
+    rows = sgdist.tensor_from_ptr(ptr, N * 4, dev).clone().view(-1, 4)
     # every part holds exactly the keys of its range, in (sid, idx) order
     keys = rows[:, 0].contiguous()
     part = sgdist.range_part(keys, world).numpy()
