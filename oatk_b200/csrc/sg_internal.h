@@ -30,7 +30,7 @@ struct ScanArgs {
     uint32_t *rec_sid, *rec_idx, *rec_mpos;   // unordered records (one per syncmer)
     uint64_t *rec_smer;
 };
-constexpr int SYNC_SCAN_NT = 128;   // threads per CTA of the syncmer scan kernel (16 positions each)
+constexpr int SYNC_SCAN_NT = 64;    // threads per CTA of the syncmer scan kernel (16 positions each)
 struct ScanGeom {
     int rch;        // ring size in chunks (power of two)
     int n_full;     // chunks fully inside every window of a thread's 16 positions

@@ -32,7 +32,7 @@
 
 namespace sg {
 
-constexpr int COCAP = 2048;            // chunks of parked CLOSE/OPEN bits (32 k positions)
+constexpr int COCAP = 1024;            // chunks of parked CLOSE/OPEN bits (16 k positions)
 constexpr uint32_t HNONE = 0xffffffffu;
 
 // Exact decision for a candidate whose high word ties with the window minimum: the
@@ -251,10 +251,13 @@ __global__ void __launch_bounds__(NT) scan_kernel(ScanArgs A, ScanGeom G)
 
         // 3. which chunks can hold a candidate at all: its own minimum (CLOSE) or the minimum of the two
         //    chunks its leaving elements e(p) come from (OPEN) must not exceed r0. About 1 chunk in 20.
-        const uint32_t mC = (P + 15 < k - 1 || P >= H) ? 0u :
-            ((0xffffu << max(0, k - 1 - P)) & (0xffffu >> (16 - min(16, H - P)))) & 0xffffu;
-        const uint32_t mO = (P + 15 < k || P > H) ? 0u :
-            ((0xffffu << max(0, k - P)) & (0xffffu >> (16 - min(16, H + 1 - P)))) & 0xffffu;
+        uint32_t mC = 0xffffu, mO = 0xffffu;           // positions that may close / open at all
+        if (P < k || P + 16 > H) {                     // only the first and last chunks of a read are partial
+            mC = (P + 15 < k - 1 || P >= H) ? 0u :
+                ((0xffffu << max(0, k - 1 - P)) & (0xffffu >> (16 - min(16, H - P)))) & 0xffffu;
+            mO = (P + 15 < k || P > H) ? 0u :
+                ((0xffffu << max(0, k - P)) & (0xffffu >> (16 - min(16, H + 1 - P)))) & 0xffffu;
+        }
         bool flagged;
         if (small_q) flagged = (mC | mO) != 0;
         else {

@@ -79,3 +79,25 @@ def test_unaligned_offsets(gpu_ctx, oracle):
     rng = np.random.default_rng(5)
     reads = [synth._rand(rng, 1200 + i) for i in range(40)]
     check(gpu_ctx, oracle, reads, 301, 15)
+
+
+def test_large_k_and_the_window_limit(gpu_ctx, oracle):
+    """k far above the default still fits the shared-memory window; beyond the limit the call fails loudly"""
+    from oatk_b200 import lib
+    rng = np.random.default_rng(2)
+    reads = [synth._rand(rng, 60000), synth._rand(rng, 9000), synth._rand(rng, 45000)]
+    check(gpu_ctx, oracle, reads, 8001, 31)
+    check(gpu_ctx, oracle, reads, 20001, 25)
+    b = lib.Batch(gpu_ctx)
+    bases, off = pack_reads(reads)
+    b.set_reads_host(bases, off)
+    with pytest.raises(lib.SgError) as e:
+        b.extract(60001, 31)
+    assert e.value.code == -5
+
+
+def test_many_tiny_reads(gpu_ctx, oracle):
+    rng = np.random.default_rng(4)
+    reads = [synth._rand(rng, int(n)) for n in rng.integers(0, 200, 20000)]
+    check(gpu_ctx, oracle, reads, 64, 31)
+    check(gpu_ctx, oracle, reads, 1001, 31)
