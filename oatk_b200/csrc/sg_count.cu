@@ -22,6 +22,7 @@
 #include <vector>
 #include <algorithm>
 #include "sg_host.h"
+#include "sg_table.cuh"
 
 namespace sg {
 
@@ -232,6 +233,32 @@ __global__ void __launch_bounds__(256) run_hist_kernel(const uint64_t *starts, u
     for (int i = threadIdx.x; i < 1001; i += blockDim.x) if (h[i]) atomicAdd(hist + i, (unsigned long long) h[i]);
 }
 
+// multiplicity of every distinct key through the warp-cooperative table
+__global__ void __launch_bounds__(256) key_tally_kernel(const uint64_t *keys, uint64_t n, uint64_t *tk, uint32_t *tv, uint64_t nslot_mask)
+{
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp0 = ((uint64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nwarp = ((uint64_t) gridDim.x * blockDim.x) >> 5;
+    for (uint64_t base = warp0 * 32; base < n; base += nwarp * 32)
+        table_add_warp(tk, tv, nslot_mask, base + lane < n ? keys[base + lane] : EMPTY_KEY, lane);
+}
+
+// multiplicity-of-multiplicity histogram over the occupied slots; hist[1001] counts the distinct keys
+__global__ void __launch_bounds__(256) slot_hist_kernel(const uint64_t *tk, const uint32_t *tv, uint64_t nslots, unsigned long long *hist)
+{
+    __shared__ uint32_t h[1002];
+    for (int i = threadIdx.x; i < 1002; i += blockDim.x) h[i] = 0;
+    __syncthreads();
+    for (uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < nslots; i += (uint64_t) gridDim.x * blockDim.x) {
+        if (tk[i] == EMPTY_KEY) continue;
+        const uint32_t c = tv[i];
+        atomicAdd(&h[c < 1000 ? c : 1000], 1u);
+        atomicAdd(&h[1001], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 1002; i += blockDim.x) if (h[i]) atomicAdd(hist + i, (unsigned long long) h[i]);
+}
+
 __global__ void __launch_bounds__(256) gap_kernel(const uint64_t *occ, const uint32_t *m_pos, uint64_t n, int k, unsigned long long *out /* [0]=sum (two's complement), [1]=count */)
 {
     __shared__ long long ssum[8];
@@ -350,13 +377,24 @@ int sg_stat(sg_batch *b, sg_stat_t *out)
     uint64_t gk = 0, gs = 0;
     rc = mult_table(b, (const uint64_t *) b->skey.p, N, 1, d + 1001, &gk);
     if (rc) return rc;
-    // s-mer codes: a second sort, values unused
-    RS(b->skey2, (N + 1) * 8); RS(b->sval2, (N + 1) * 8);
-    CK(cudaMemcpyAsync(b->skey2.p, b->t_smer(), N * 8, cudaMemcpyDeviceToDevice, st));
-    LAUNCHED(SG_T_STAT, launch_sort_pairs((uint64_t *) b->skey2.p, (uint64_t *) b->sval2.p, (uint64_t *) b->skey_alt.p,
-            (uint64_t *) b->sval_alt.p, N, 0, 64, (uint32_t *) b->sort_tmp.p, st));
-    rc = mult_table(b, (const uint64_t *) b->skey2.p, N, 0, d, &gs);
-    if (rc) return rc;
+    // s-mer codes: no order is needed, only how often each distinct code occurs -> hash table
+    // (the reference sorts all syncmers a second time for this, syncmer.c:916-926)
+    if (N) {
+        uint64_t nslots = 1024;
+        while (nslots < 2 * N) nslots <<= 1;
+        RS(b->arc_keys, nslots * 8); RS(b->arc_vals, nslots * 4);
+        RS(b->stat_dev2, 1002 * 8);
+        CK(cudaMemsetAsync(b->arc_keys.p, 0xff, nslots * 8, st));
+        CK(cudaMemsetAsync(b->arc_vals.p, 0, nslots * 4, st));
+        CK(cudaMemsetAsync(b->stat_dev2.p, 0, 1002 * 8, st));
+        key_tally_kernel<<<std::min<unsigned>(nblk(N, 256), 148u * 16u), 256, 0, st>>>(b->t_smer(), N, (uint64_t *) b->arc_keys.p,
+                (uint32_t *) b->arc_vals.p, nslots - 1);
+        slot_hist_kernel<<<std::min<unsigned>(nblk(nslots, 256), 148u * 16u), 256, 0, st>>>((const uint64_t *) b->arc_keys.p,
+                (const uint32_t *) b->arc_vals.p, nslots, (unsigned long long *) b->stat_dev2.p);
+        ctx->count_launch(SG_T_STAT, 2);
+        CK(cudaMemcpyAsync(d, b->stat_dev2.p, 1001 * 8, cudaMemcpyDeviceToDevice, st));
+        CK(cudaMemcpyAsync(&gs, (unsigned long long *) b->stat_dev2.p + 1001, 8, cudaMemcpyDeviceToHost, st));
+    }
     // gaps are a property of the local reads whichever tuple set is being counted
     if (b->n_syncmers) gap_kernel<<<std::min<unsigned>(nblk(b->n_syncmers, 256), 1184u), 256, 0, st>>>((const uint64_t *) b->occ.p, (const uint32_t *) b->m_pos.p, b->n_syncmers, b->k, d + 2002);
     ctx->count_launch(SG_T_STAT, 1);

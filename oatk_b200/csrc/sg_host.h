@@ -57,7 +57,7 @@ struct sg_batch {
     // a5/a6 device results
     sg::DevBuf kid;                              // read order: id << 1
     sg::DevBuf skey, sval, skey_alt, sval_alt, sort_tmp;
-    sg::DevBuf socc, ssmer, flags, ids, ids_tmp, differs, cls, starts, stat_dev, skey2, sval2;
+    sg::DevBuf socc, ssmer, flags, ids, ids_tmp, differs, cls, starts, stat_dev, stat_dev2, skey2, sval2;
     bool sorted = false;
     bool exact_verify = false;                   // sg_batch_set_exact_verify: compare packed k-mers instead of fingerprints
     int hash_bits = 64;                          // < 64 only through sg_debug_set_hash_bits (tests)
