@@ -1,0 +1,106 @@
+// sg_hash31.cuh -- s = 31: canonical 31-mer of a position and its hash64, in a left-aligned frame.
+//
+// The reference hashes x (62 bits) with hash64(x, 2^62 - 1) (reference syncmer.c:116-126). Here the
+// value is kept as X = x << 2 in a 64-bit pair (hi:lo): multiplications mod 2^64 are then
+// multiplications mod 2^62 of x with no masking, and only the right shifts have to keep the two
+// alignment bits clear. The result is bit-identical: hashA(x << 2) == hash64(x) << 2
+// (tests/test_hash31.py restates both on the CPU).
+//
+// Cost model measured on B200 (tools/microbench/int_pipes.cu): LOP3/SHF/ISETP/SEL/VIMNMX issue at
+// 0.5 warp-instructions per clock per SM sub-partition on the ALU pipe, IMAD at 0.5 on the FMA pipe
+// (concurrently with the ALU pipe), IMAD.WIDE and IMAD.HI at 0.25. The instruction selection below
+// splits the work ~40 ALU cycles / ~36 FMA cycles per position: the high-word right shifts of the
+// three xor-shifts run as IMAD.HI by a power of two held in a register (kernel parameter, so ptxas
+// cannot turn it back into a shift).
+#pragma once
+#include <stdint.h>
+
+namespace sg {
+
+// 2^(32-24), 2^(32-14), 2^(32-28): multipliers that turn "x >> n" into the high word of a product
+struct H31Consts { uint32_t p8, p18, p4; };
+__host__ __device__ inline H31Consts h31_consts() { return H31Consts{1u << 8, 1u << 18, 1u << 4}; }
+
+// (hi:lo) >> 32 after a left shift by n < 32: the top word of a two-word window
+__device__ __forceinline__ uint32_t h31_shf_l(uint32_t lo, uint32_t hi, uint32_t n) { return __funnelshift_l(lo, hi, n); }
+
+// (hi:lo) *= c, + add  (mod 2^64): IMAD.WIDE + IMAD
+__device__ __forceinline__ void h31_mul(uint32_t &hi, uint32_t &lo, uint32_t c, uint64_t add)
+{
+    const uint64_t w = (uint64_t) lo * c + add;
+    hi = hi * c + (uint32_t) (w >> 32);
+    lo = (uint32_t) w;
+}
+
+// X ^= X >> N with the alignment bits kept clear; pw = 2^(32-N)
+template <int N>
+__device__ __forceinline__ void h31_xorshift(uint32_t &hi, uint32_t &lo, uint32_t pw)
+{
+    const uint32_t t = __umulhi(hi, pw);                       // hi >> N on the FMA pipe
+    const uint32_t u = __funnelshift_r(lo, hi, N);
+    lo ^= u & 0xfffffffcu;
+    hi ^= t;
+}
+
+// hash64 of x = X >> 2, returned as the top 32 bits of hash << 2 (i.e. hash >> 30)
+__device__ __forceinline__ uint32_t h31_hash_top(uint32_t hi, uint32_t lo, const H31Consts &K)
+{
+    h31_mul(hi, lo, 0x1fffffu, 0xfffffffffffffffcull);         // x = (x << 21) - x - 1
+    h31_xorshift<24>(hi, lo, K.p8);
+    h31_mul(hi, lo, 265u, 0);                                  // x = x + (x << 3) + (x << 8)
+    h31_xorshift<14>(hi, lo, K.p18);
+    h31_mul(hi, lo, 21u, 0);                                   // x = x + (x << 2) + (x << 4)
+    h31_xorshift<28>(hi, lo, K.p4);
+    return hi * 0x80000001u + __umulhi(lo, 0x80000001u);       // x += x << 31: only the top word is needed
+}
+
+// the same for a full 64-bit result (hash << 2)
+__device__ __forceinline__ uint64_t h31_hash_full(uint32_t hi, uint32_t lo)
+{
+    uint64_t x = (uint64_t) hi << 32 | lo;
+    x = x * 0x1fffffull - 4ull;
+    x ^= (x >> 24) & ~3ull;
+    x *= 265ull;
+    x ^= (x >> 14) & ~3ull;
+    x *= 21ull;
+    x ^= (x >> 28) & ~3ull;
+    x *= 0x80000001ull;
+    return x;
+}
+
+// Canonical 31-mer ending at position J (0..15) of the sixteen bases of word w0; a, b are the two
+// words before it (32 bases), ra/rb/rc the reverse-complement words of w0/b/a. All words hold their
+// first base in bits 31:30. Returns the smaller strand left-aligned in (hi:lo), low two bits clear.
+// A 31-mer cannot equal its reverse complement (odd length), so the strands never tie.
+template <int J>
+__device__ __forceinline__ void h31_canon(uint32_t a, uint32_t b, uint32_t w0, uint32_t ra, uint32_t rb, uint32_t rc,
+        uint32_t &hi, uint32_t &lo)
+{
+    uint32_t fh, fl;
+    if (J < 14) { fh = h31_shf_l(b, a, 2 * J + 4); fl = h31_shf_l(w0, b, 2 * J + 4); }
+    else if (J == 14) { fh = b; fl = w0; }
+    else { fh = h31_shf_l(w0, b, 2); fl = w0 << 2; }
+    const uint32_t rh = J == 15 ? ra : h31_shf_l(rb, ra, 30 - 2 * J);
+    const uint32_t rl = J == 15 ? rb : h31_shf_l(rc, rb, 30 - 2 * J);
+    // the two junk bits below the 62 compared ones cannot decide the order: the strands differ above them
+    const bool lt = ((uint64_t) fh << 32 | fl) < ((uint64_t) rh << 32 | rl);
+    hi = lt ? fh : rh;
+    lo = (lt ? fl : rl) & 0xfffffffcu;
+}
+
+// run-time position (the slow, checked path): same as h31_canon<J>
+__device__ __forceinline__ void h31_canon_rt(int j, uint32_t a, uint32_t b, uint32_t w0, uint32_t ra, uint32_t rb, uint32_t rc,
+        uint32_t &hi, uint32_t &lo)
+{
+    const uint32_t n = 2u * j + 4u;                            // 4..34
+    const bool far = n >= 32u;
+    const uint32_t x0 = far ? b : a, x1 = far ? w0 : b, x2 = far ? 0u : w0;
+    const uint32_t fh = h31_shf_l(x1, x0, n & 31u), fl = h31_shf_l(x2, x1, n & 31u);
+    const uint32_t m = 30u - 2u * j;                           // 30..0
+    const uint32_t rh = h31_shf_l(rb, ra, m), rl = h31_shf_l(rc, rb, m);
+    const bool lt = ((uint64_t) fh << 32 | (fl & 0xfffffffcu)) < ((uint64_t) rh << 32 | (rl & 0xfffffffcu));
+    hi = lt ? fh : rh;
+    lo = (lt ? fl : rl) & 0xfffffffcu;
+}
+
+} // namespace sg

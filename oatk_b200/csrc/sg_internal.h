@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include "sg_hash31.cuh"
 
 namespace sg {
 
@@ -35,6 +36,7 @@ struct ScanGeom {
     int rch;        // ring size in chunks (power of two)
     int n_full;     // chunks fully inside every window of a thread's 16 positions
     int T;          // top level of the radix-4 sparse table (4^T <= n_full)
+    H31Consts h31;  // shift multipliers of the s = 31 hash (kept as parameters: see sg_hash31.cuh)
 };
 int scan_geometry(int k, int s, int nt, ScanGeom *g, size_t *smem);
 // returns launches (>= 0) or a negative SG_E_* code

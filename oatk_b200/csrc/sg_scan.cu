@@ -27,6 +27,7 @@
 //      positions) they are combined, ranked with one block scan and written as
 //      (sid, idx, m_pos, s_mer) records; k-mer hashes follow in sg_kmer.cu
 #include "sg_common.cuh"
+#include "sg_hash31.cuh"
 #include "sg_internal.h"
 #include "../../include/syncgpu.h"
 
@@ -49,10 +50,14 @@ __device__ __noinline__ bool settle_tie(const uint32_t *ring, int RCH, const uin
         if (x < 0 || ring_at(x) == HNONE) return SG_NONE64;
         return hash64(smer_code_at(hs32, x, s, nwords) >> 1, mask);
     };
-    uint32_t lo = 0xffffffffu;
+    // positions whose ring word equals tgt are the only ones that can hold the window minimum; the ring
+    // word is a monotone function of the hash (its top bits, clamped below NONE), so the full hashes decide
+    uint64_t best = SG_NONE64;
     for (int x = p - q + 1 + lane; x < p; x += 32)
-        if (ring_at(x) == tgt) lo = min(lo, (uint32_t) m64_at(x));
-    const uint64_t mo = (uint64_t) tgt << 32 | __reduce_min_sync(SG_FULL, lo);
+        if (ring_at(x) == tgt) best = min(best, m64_at(x));
+    const uint32_t bh = (uint32_t) (best >> 32), mh = __reduce_min_sync(SG_FULL, bh);
+    const uint32_t ml = __reduce_min_sync(SG_FULL, bh == mh ? (uint32_t) best : 0xffffffffu);
+    const uint64_t mo = (uint64_t) mh << 32 | ml;
     const uint64_t e64 = m64_at(p - q);
     if (is_open) return e64 <= mo;
     const uint64_t mp = m64_at(p);
@@ -186,7 +191,29 @@ __global__ void __launch_bounds__(NT) scan_kernel(ScanArgs A, ScanGeom G)
         //    are all valid needs no per-position checks.
         uint32_t cmin = HNONE;
         uint32_t *own = ring + cs;
-        if (vm) {
+        if (vm && S_FIXED == 31) {
+            // s = 31: every position is extracted straight from the three words around it (no rolling
+            // dependency between positions) and hashed in the left-aligned frame of sg_hash31.cuh. The ring
+            // word is hash >> 30 clamped below NONE. An odd s-mer cannot be its own reverse complement.
+            const uint32_t a = hoco_word(hs32, c - 2, nwords), b = hoco_word(hs32, c - 1, nwords), w0 = hoco_word(hs32, c, nwords);
+            const uint32_t ra = rev2(~w0), rb = rev2(~b), rc = rev2(~a);
+            if (vm == 0xffffu) {
+#define SG_H31_POS(J) { uint32_t hi, lo; h31_canon<J>(a, b, w0, ra, rb, rc, hi, lo); \
+                        const uint32_t hv = min(h31_hash_top(hi, lo, G.h31), 0xfffffffeu); own[(J) * RCH] = hv; cmin = min(cmin, hv); }
+                SG_H31_POS(0) SG_H31_POS(1) SG_H31_POS(2) SG_H31_POS(3) SG_H31_POS(4) SG_H31_POS(5) SG_H31_POS(6) SG_H31_POS(7)
+                SG_H31_POS(8) SG_H31_POS(9) SG_H31_POS(10) SG_H31_POS(11) SG_H31_POS(12) SG_H31_POS(13) SG_H31_POS(14) SG_H31_POS(15)
+#undef SG_H31_POS
+            } else {
+#pragma unroll 1
+                for (int j = 0; j < 16; ++j) {
+                    uint32_t hi, lo;
+                    h31_canon_rt(j, a, b, w0, ra, rb, rc, hi, lo);
+                    const uint32_t hv = ((vm >> j) & 1u) ? min(h31_hash_top(hi, lo, G.h31), 0xfffffffeu) : HNONE;
+                    own[j * RCH] = hv;
+                    cmin = min(cmin, hv);
+                }
+            }
+        } else if (vm) {
             uint32_t w0 = hoco_word(hs32, c, nwords);
             const uint64_t V = (uint64_t) hoco_word(hs32, c - 2, nwords) << 32 | hoco_word(hs32, c - 1, nwords);
             uint64_t fw = V & mask, rv = rc64(V) >> (64 - 2 * s);
@@ -332,7 +359,7 @@ int scan_geometry(int k, int s, int nt, ScanGeom *g, size_t *smem)
     while (n_full > 0 && (4 << (2 * T)) <= n_full) ++T;  // largest T with 4^T <= n_full
     int need = (q + 15) / 16 + nt + 2, rch = 64;
     while (rch < need) rch <<= 1;
-    g->rch = rch; g->n_full = n_full; g->T = T;
+    g->rch = rch; g->n_full = n_full; g->T = T; g->h31 = h31_consts();
     *smem = sizeof(uint32_t) * ((size_t) 16 * rch + (size_t) (T + 1) * rch + COCAP + (nt / 32 + 1) + (nt / 32 + 4));
     return *smem <= 227 * 1024 ? 0 : SG_E_KSIZE;
 }
