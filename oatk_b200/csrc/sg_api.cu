@@ -215,13 +215,14 @@ static int run_extract(sg_batch *b, uint64_t rec_cap_hint)
     LAUNCHED(SG_T_ENCODE, launch_capacity_offsets(b->d_off, (uint64_t *) b->hoff.p, n, (uint64_t *) b->scan_tmp.p, st));
     EncodeArgs E;
     E.bases = b->d_bases; E.off = b->d_off; E.hoff = (const uint64_t *) b->hoff.p;
+    E.n_reads = n; E.work = reinterpret_cast<unsigned int *>(cnt + 4);
     E.hoco_s = (uint8_t *) b->hoco_s.p; E.ho_rl = (uint8_t *) b->ho_rl.p; E.nbits = (uint8_t *) b->nbits.p;
     E.hoco_l = (uint32_t *) b->hoco_l.p; E.n_amb = (uint32_t *) b->n_amb.p;
     E.amb_count = cnt + 0; E.lrl_count = cnt + 1;
     E.amb_cap = b->amb_cap; E.lrl_cap = b->lrl_cap;
     E.amb_sid = (uint32_t *) b->amb_sid.p; E.amb_pos = (uint32_t *) b->amb_pos.p;
     E.lrl_sid = (uint32_t *) b->lrl_sid.p; E.lrl_idx = (uint32_t *) b->lrl_idx.p; E.lrl_val = (uint32_t *) b->lrl_val.p;
-    LAUNCHED(SG_T_ENCODE, launch_encode(E, n, st));
+    LAUNCHED(SG_T_ENCODE, launch_encode(E, st));
     ctx->t_end(SG_T_ENCODE);
 
     ctx->t_begin(SG_T_SCAN);
@@ -229,11 +230,12 @@ static int run_extract(sg_batch *b, uint64_t rec_cap_hint)
     S.hoff = (const uint64_t *) b->hoff.p; S.hoco_s = (const uint8_t *) b->hoco_s.p; S.nbits = (const uint8_t *) b->nbits.p;
     S.hoco_l = (const uint32_t *) b->hoco_l.p; S.n_amb = (const uint32_t *) b->n_amb.p;
     S.k = b->k; S.s = b->s;
+    S.n_reads = n; S.work = reinterpret_cast<unsigned int *>(cnt + 3);
     S.n_scm = (uint32_t *) b->n_scm.p;
     S.rec_count = cnt + 2; S.rec_cap = rec_cap;
     S.rec_sid = (uint32_t *) b->rec_sid.p; S.rec_idx = (uint32_t *) b->rec_idx.p; S.rec_mpos = (uint32_t *) b->rec_mpos.p;
     S.rec_smer = (uint64_t *) b->rec_smer.p;
-    LAUNCHED(SG_T_SCAN, launch_scan(S, n, st));
+    LAUNCHED(SG_T_SCAN, launch_scan(S, st));
     ctx->t_end(SG_T_SCAN);
 
     ctx->t_begin(SG_T_PLACE);
@@ -250,7 +252,7 @@ int sg_extract(sg_batch *b, int k, int s)
     CK(cudaSetDevice(ctx->device));
     {
         ScanGeom g; size_t smem;
-        if (scan_geometry(k, s, SYNC_SCAN_NT, &g, &smem)) { ctx->err = "k - s + 1 exceeds the scan window"; return SG_E_KSIZE; }
+        if (scan_geometry(k, s, &g, &smem)) { ctx->err = "k - s + 1 exceeds the scan window"; return SG_E_KSIZE; }
     }
     reset_state(b);
     b->k = k; b->s = s;

@@ -7,24 +7,31 @@
 // character is never compressed, is stored as A with ho_rl 0 and its RAW index
 // goes to n_nucl (:316-322).
 //
-// One CTA per read, walking the read in tiles of NT*16 raw bytes. Per tile:
-//   classify   16 bytes per thread from one aligned 128-bit load, SIMD-in-register
-//              for plain ACGT/acgt; anything else (N, IUPAC, U, bytes 0..3, tile
-//              edges) takes an exact per-byte path
-//   run starts 2-bit packed codes XOR their 1-base shift -> start mask
-//   scan       block prefix sum of start counts = hoco index, block prefix maximum
-//              of "latest start" = where the run before my chunk began
-//   close      every start closes the run before it (length = distance between
-//              starts) with one byte store into shared memory and shifts its 2-bit
-//              code into a register; the thread's codes are then OR-ed into the
-//              shared big-endian word stream with at most two shared atomics
-//   flush      finished groups of 16 entries leave as one 32-bit code word, one
-//              128-bit store of run lengths and 16 N flags; the open last run and an
-//              incomplete group stay staged for the next tile
+// One WARP per read (reads are handed out through an atomic counter, the grid is
+// persistent), no block-wide barriers. The warp walks the read in tiles of 1024
+// raw bytes; lane l owns 32 consecutive bytes (two aligned 128-bit loads, issued
+// one tile ahead). Per tile:
+//   classify   four bytes at a time in registers: codes from bits 1-2 of the ASCII
+//              byte, validity by re-deriving the three bits that separate ACGT/acgt
+//              from everything else; anything else (N, IUPAC, U, bytes 0..3) sends
+//              the lane through an exact per-byte path
+//   run starts 2-bit packed codes XOR their one-base shift -> start mask; warp
+//              prefix sum of the start counts = hoco index of the lane's first run
+//   stage      every start stores ONE 16-bit entry {code of the new run, length - 1
+//              of the run it closes} into a warp-private shared array: 32 unrolled
+//              steps of predicate / length / byte-merge / pointer bump
+//   emit       finished groups of 16 entries leave as one 128-bit store of run
+//              lengths, one 32-bit word of codes and 16 N flags; the open last run
+//              and an incomplete group stay staged for the next tile
+#include <algorithm>
 #include "sg_common.cuh"
 #include "sg_internal.h"
 
 namespace sg {
+
+constexpr int ENC_WARPS = 8;
+constexpr int ENC_TILE = 1024;                 // raw bytes per warp and tile
+constexpr int ENC_SLOTS = ENC_TILE + 64;       // staged 16-bit entries per warp (tile + carry + slack)
 
 __device__ __forceinline__ int base_code_slow(uint32_t ch)
 {
@@ -38,220 +45,267 @@ __device__ __forceinline__ int base_code_slow(uint32_t ch)
     return 4;
 }
 
-// four ASCII bytes -> 8 bits of packed codes (first byte in bits 7:6); `bad`
-// collects any byte that is not one of ACGTacgt
+// four ASCII bytes -> their codes 0..3 in the same byte lanes; `bad` collects any byte that is not
+// one of ACGTacgt. A=0x41 C=0x43 G=0x47 T=0x54: bits 2:1 give the code (Gray-decoded), bit 5 is the
+// case, and the other bits must read 0 1 . t 0 . . !t with t = "is T".
 __device__ __forceinline__ uint32_t classify4(uint32_t w, uint32_t &bad)
 {
     const uint32_t K = 0x01010101u;
-    uint32_t a = w >> 1, b = w >> 2;
-    uint32_t c1 = b & K, c0 = (a ^ b) & K;
-    uint32_t t = c0 & c1, o = c0 | c1, n = c1 & ~c0;
-    uint32_t expect = 0x41414141u + t * 17u + o * 2u + n * 4u;   // 'A','C','G','T' per byte
-    bad |= (w & 0xDFDFDFDFu) ^ expect;
-    return ((c0 + 2u * c1) * 0x40100401u) >> 24;
+    const uint32_t c1 = (w >> 2) & K, c0 = ((w >> 1) ^ (w >> 2)) & K;
+    const uint32_t t17 = (c0 & c1) * 17u;                 // T: bit 4 set, bit 0 clear
+    bad |= ((w ^ t17) & 0xD9D9D9D9u) ^ 0x41414141u;
+    return c0 + 2u * c1;
 }
+// codes in byte lanes -> 8 bits, first byte in bits 7:6
+__device__ __forceinline__ uint32_t pack4(uint32_t cc) { return ((cc & 0x03030303u) * 0x40100401u) >> 24; }
 
-template <int NT>
-__global__ void __launch_bounds__(NT) encode_kernel(EncodeArgs A)
+__global__ void __launch_bounds__(32 * ENC_WARPS) encode_kernel(EncodeArgs A)
 {
-    constexpr int TILE = NT * 16;
-    constexpr int NW = NT / 32;
-    constexpr int NWORD = TILE / 16 + 4;               // staged 16-entry groups (tile + carry)
-    __shared__ __align__(16) uint8_t s_rl_arr[TILE + 64];   // run length - 1 per staged hoco entry; [-16, 0) is scratch
-    __shared__ uint32_t s_w[NWORD];                    // 2-bit codes, 16 per word, first entry in bits 31:30
-    __shared__ uint32_t s_nbw[NWORD / 2 + 2];          // ambiguity flags, entry e -> bit e & 31 of word e >> 5
-    __shared__ uint32_t s_cnt[NW];
-    __shared__ int s_last[NW];
-    __shared__ uint32_t s_namb;
-    uint8_t *s_rl = s_rl_arr + 16;
+    __shared__ __align__(16) uint16_t s_ent_all[ENC_WARPS][ENC_SLOTS];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint16_t *ent = s_ent_all[wid];
+    uint32_t *ent32 = reinterpret_cast<uint32_t *>(ent);
+    const uint32_t lt_mask = (1u << lane) - 1u;
 
-    const uint64_t r = blockIdx.x;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const uint64_t raw0 = A.off[r], raw1 = A.off[r + 1];
-    const uint32_t len = (uint32_t) (raw1 - raw0);
-    const uint64_t hb = A.hoff[r];                      // capacity offset, multiple of 64
-    const uint64_t a0 = raw0 & ~15ull;
-    const uint32_t ntiles = (uint32_t) ((raw1 - a0 + TILE - 1) / TILE);
-    uint32_t *hs32 = reinterpret_cast<uint32_t *>(A.hoco_s + hb / 4);
-    uint16_t *nb16 = reinterpret_cast<uint16_t *>(A.nbits + hb / 8);
-    uint8_t *rl8 = A.ho_rl + hb;
-    const uint32_t sid = (uint32_t) r;
+    for (;;) {
+        unsigned int r32 = 0;
+        if (lane == 0) r32 = atomicAdd(A.work, 1u);
+        r32 = __shfl_sync(SG_FULL, r32, 0);
+        if ((uint64_t) r32 >= A.n_reads) break;
+        const uint64_t r = r32;
+        const uint32_t sid = r32;
+        const uint64_t raw0 = A.off[r], raw1 = A.off[r + 1];
+        const int len = (int) (raw1 - raw0);
+        const uint64_t hb = A.hoff[r];                      // capacity offset, multiple of 64
+        const uint64_t a0 = raw0 & ~15ull;
+        const int ntiles = (int) ((raw1 - a0 + ENC_TILE - 1) / ENC_TILE);
+        uint32_t *hs32 = reinterpret_cast<uint32_t *>(A.hoco_s + hb / 4);
+        uint16_t *nb16 = reinterpret_cast<uint16_t *>(A.nbits + hb / 8);
+        uint4 *rl128 = reinterpret_cast<uint4 *>(A.ho_rl + hb);
 
-    uint32_t n_stage = 0;        // staged entries carried from the previous tile, the open run last (uniform)
-    uint32_t g_done = 0;         // hoco entries already written (uniform, multiple of 16)
-    int carry_last = -1;         // raw position of the latest run start seen so far (uniform)
-    for (int i = tid; i < NWORD; i += NT) s_w[i] = 0;
-    for (int i = tid; i < NWORD / 2 + 2; i += NT) s_nbw[i] = 0;
-    if (tid == 0) s_namb = 0;
-    __syncthreads();
+        uint32_t n_stage = 0;        // staged entries carried from the previous tile, the open run last (uniform)
+        uint32_t g_done = 0;         // hoco entries already written (uniform, multiple of 16)
+        int lastpos = -1;            // read position of the latest run start seen so far (uniform)
+        uint32_t last_cc = 5;        // code of the last byte of the previous tile: 0..3, 4 ambiguous, 5 outside (uniform)
+        uint32_t n_amb = 0;          // ambiguous characters seen by this lane
+        bool any_n = false;          // the staged entries may carry N flags (uniform)
 
-    // a run longer than 256 saturates ho_rl and goes to the side list (syncmer.c:301-304)
-    auto close_run = [&](uint32_t e, uint32_t rl1) {
-        if (rl1 >= 255u) {
+        auto load_chunk = [&](int t, uint4 &q0, uint4 &q1) {
+            const uint64_t g = a0 + (uint64_t) t * ENC_TILE + (uint64_t) lane * 32;
+            q0 = make_uint4(0, 0, 0, 0); q1 = q0;
+            if (t < ntiles && g < raw1 && g + 32 > raw0) {
+                q0 = __ldg(reinterpret_cast<const uint4 *>(A.bases + g));
+                if (g + 16 < raw1) q1 = __ldg(reinterpret_cast<const uint4 *>(A.bases + g + 16));
+            }
+        };
+        // a run of 256 or more saturates ho_rl and goes to the side list (syncmer.c:301-304)
+        auto side_list = [&](uint32_t idx, uint32_t rl1) {
             unsigned long long o = atomicAdd(A.lrl_count, 1ull);
-            if (o < A.lrl_cap) { A.lrl_sid[o] = sid; A.lrl_idx[o] = g_done + e; A.lrl_val[o] = rl1; }
-            rl1 = 255u;
-        }
-        s_rl[(int) e] = (uint8_t) rl1;
-    };
+            if (o < A.lrl_cap) { A.lrl_sid[o] = sid; A.lrl_idx[o] = idx; A.lrl_val[o] = rl1; }
+        };
 
-    for (uint32_t t = 0; t < ntiles; ++t) {
-        const uint64_t g = a0 + (uint64_t) t * TILE + (uint64_t) tid * 16;   // global byte index of my chunk
-        uint32_t P = 0, NM = 0, VM = 0;    // packed codes; ambiguous / void masks (bit 2*(15-i) for byte i)
-        bool fast = false;
-        if (g < raw1 && g + 16 > raw0) {
-            const uint4 q = __ldg(reinterpret_cast<const uint4 *>(A.bases + g));
+        uint4 nq0, nq1;
+        load_chunk(0, nq0, nq1);
+        for (int t = 0; t < ntiles; ++t) {
+            const uint4 q0 = nq0, q1 = nq1;
+            load_chunk(t + 1, nq0, nq1);                   // in flight while this tile is processed
+            const int rel = (int) (int64_t) (a0 + (uint64_t) t * ENC_TILE + (uint64_t) lane * 32 - raw0);   // read position of my first byte
+            const uint32_t w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+            uint32_t cc[8];
             uint32_t bad = 0;
-            uint32_t p0 = classify4(q.x, bad), p1 = classify4(q.y, bad), p2 = classify4(q.z, bad), p3 = classify4(q.w, bad);
-            if (bad == 0 && g >= raw0 && g + 16 <= raw1) {
-                P = p0 << 24 | p1 << 16 | p2 << 8 | p3;
-                fast = true;
-            } else {
-                const uint32_t w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const uint32_t bit = 1u << (2 * (15 - i));
-                    if (g + i < raw0 || g + i >= raw1) { VM |= bit; continue; }
-                    int c = base_code_slow((w[i >> 2] >> (8 * (i & 3))) & 0xFFu);
-                    if (c == 4) NM |= bit; else P |= (uint32_t) c << (2 * (15 - i));
+            for (int j = 0; j < 8; ++j) cc[j] = classify4(w[j], bad);
+            const bool inside = rel >= 0 && rel + 32 <= len;
+            // valid positions of my chunk: [vlo, vhi)
+            const int vlo = min(32, max(0, -rel)), vhi = max(0, min(32, len - rel));
+            uint32_t NM0 = 0, NM1 = 0;                     // ambiguous positions, bit 2*(15-i) like the start masks
+            if (!inside || bad) {
+                // exact per-byte codes (also fixes U, raw 0..3) for the valid bytes; everything else becomes 0
+                bad = 0;
+#pragma unroll 1
+                for (int j = 0; j < 8; ++j) {
+                    uint32_t cw = 0, wj = 0;
+                    // runtime-indexed register arrays go through select chains (no local memory)
+#pragma unroll
+                    for (int jj = 0; jj < 8; ++jj) if (jj == j) wj = w[jj];
+                    for (int b = 0; b < 4; ++b) {
+                        const int i = 4 * j + b;
+                        if (i < vlo || i >= vhi) continue;
+                        const int c = base_code_slow((wj >> (8 * b)) & 0xffu);
+                        if (c == 4) {
+                            cw |= 4u << (8 * b);               // N flag rides in bit 2 of the code byte; the code itself is A
+                            if (i < 16) NM0 |= 1u << (2 * (15 - i)); else NM1 |= 1u << (2 * (31 - i));
+                            unsigned long long o = atomicAdd(A.amb_count, 1ull);
+                            if (o < A.amb_cap) { A.amb_sid[o] = sid; A.amb_pos[o] = (uint32_t) (rel + i); }
+                            ++n_amb;
+                        } else cw |= (uint32_t) c << (8 * b);
+                    }
+#pragma unroll
+                    for (int jj = 0; jj < 8; ++jj) if (jj == j) cc[jj] = cw;
                 }
             }
-        } else {
-            VM = 0x55555555u;
-        }
-        // code of the byte in front of my chunk: 0..3, 4 = ambiguous, 5 = outside the read
-        int pc = 5;
-        if (g > raw0 && g <= raw1) pc = base_code_slow(__ldg(A.bases + g - 1));
-        uint32_t M;
-        {
-            uint32_t D = P ^ ((P >> 2) | ((uint32_t) (pc & 3) << 30));
-            M = (D | (D >> 1)) & 0x55555555u;
-            if (pc >= 4) M |= 0x40000000u;
-            if (!fast) M = (M | NM | (NM >> 2) | (VM >> 2)) & ~VM;
-        }
-        const int rel = (int) (uint32_t) (g - raw0);   // wraps for bytes before the read; those are void
-        const uint32_t cnt = __popc(M);
-        const int mylast = M ? rel + 15 - ((__ffs(M) - 1) >> 1) : -1;
+            if (__any_sync(SG_FULL, (NM0 | NM1) != 0)) any_n = true;
 
-        // block scan: hoco index of my first start, and the raw position of the latest start before my chunk
-        uint32_t inc = cnt;
-        int lmax = mylast;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t a = __shfl_up_sync(SG_FULL, inc, d);
-            const int bq = __shfl_up_sync(SG_FULL, lmax, d);
-            if (lane >= d) { inc += a; lmax = max(lmax, bq); }
-        }
-        if (lane == 31) { s_cnt[wid] = inc; s_last[wid] = lmax; }
-        __syncthreads();
-        uint32_t ex = inc - cnt, tot = 0;
-        int prev = __shfl_up_sync(SG_FULL, lmax, 1), blast = carry_last;
-        if (lane == 0) prev = -1;
-#pragma unroll
-        for (int w = 0; w < NW; ++w) {
-            const uint32_t c = s_cnt[w];
-            const int l = s_last[w];
-            if (w < wid) { ex += c; prev = max(prev, l); }
-            tot += c; blast = max(blast, l);
-        }
-        prev = max(prev, carry_last);
-
-        // every run start closes the run before it (run length = distance between starts) and
-        // appends its code; 16 predicated steps, everything in registers but the byte store
-        {
-            uint32_t e = n_stage + ex, CP = 0;
-            if (fast) {
-                // branch-free steps: selects and one predicated byte store each; runs of 256+ are rare and
-                // are only noticed here (big), then pushed to the side list by a second pass
-                uint32_t big = 0;
-                const int prev0 = prev;
-                const uint32_t e0 = e;
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const bool st = (M >> (2 * (15 - i))) & 1u;
-                    const uint32_t rl1 = (uint32_t) (rel + i - prev - 1);
-                    if (st) s_rl[(int) e - 1] = (uint8_t) min(rl1, 255u);
-                    big |= st ? rl1 : 0u;
-                    prev = st ? rel + i : prev;
-                    CP = st ? CP * 4u + ((P >> (2 * (15 - i))) & 3u) : CP;
-                    e += st;
-                }
-                if (big >= 255u) {
-                    int pv = prev0;
-                    uint32_t ee = e0, m = M;
-                    while (m) {
-                        const int b = 31 - __clz(m);
-                        m &= ~(1u << b);
-                        const int i = 15 - (b >> 1);
-                        const uint32_t rl1 = (uint32_t) (rel + i - pv - 1);
-                        if (rl1 >= 255u) close_run(ee - 1, rl1);
-                        pv = rel + i;
-                        ++ee;
-                    }
-                }
-            } else {
-                uint32_t m = M;
-                while (m) {
-                    const int b = 31 - __clz(m);
-                    m &= ~(1u << b);
-                    const int i = 15 - (b >> 1);
-                    close_run(e - 1, (uint32_t) (rel + i - prev - 1));   // entry -1 of the read lands in scratch
-                    prev = rel + i;
-                    CP = CP * 4u + ((P >> b) & 3u);
-                    if ((NM >> b) & 1u) {
-                        atomicOr(&s_nbw[e >> 5], 1u << (e & 31));
-                        unsigned long long o = atomicAdd(A.amb_count, 1ull);
-                        if (o < A.amb_cap) { A.amb_sid[o] = sid; A.amb_pos[o] = (uint32_t) (rel + i); }
-                        atomicAdd(&s_namb, 1u);
-                    }
-                    ++e;
+            // packed codes: positions 0..15 in P0, 16..31 in P1, first position in bits 31:30
+            const uint32_t P0 = pack4(cc[0]) << 24 | pack4(cc[1]) << 16 | pack4(cc[2]) << 8 | pack4(cc[3]);
+            const uint32_t P1 = pack4(cc[4]) << 24 | pack4(cc[5]) << 16 | pack4(cc[6]) << 8 | pack4(cc[7]);
+            // code of the byte in front of my chunk: 0..3, 4 = ambiguous, 5 = outside the read
+            uint32_t mylastc = (NM1 & 1u) ? 4u : (P1 & 3u);
+            if (rel + 31 < 0 || rel + 31 >= len) mylastc = 5u;
+            uint32_t pc = __shfl_up_sync(SG_FULL, mylastc, 1);
+            if (lane == 0) pc = last_cc;
+            last_cc = __shfl_sync(SG_FULL, mylastc, 31);
+            uint32_t M0, M1;
+            {
+                const uint32_t D0 = P0 ^ ((P0 >> 2) | (pc & 3u) << 30), D1 = P1 ^ ((P1 >> 2) | P0 << 30);
+                M0 = (D0 | (D0 >> 1)) & 0x55555555u;
+                M1 = (D1 | (D1 >> 1)) & 0x55555555u;
+                if (pc >= 4u) M0 |= 0x40000000u;
+                if (!inside || (NM0 | NM1)) {
+                    // void positions never start a run, the first valid position always does; an ambiguous
+                    // character is its own run and so is whatever follows it
+                    const uint64_t all = 0x5555555555555555ull;
+                    const uint64_t keep = (vhi > vlo) ? ((all >> (2 * vlo)) & ~(vhi < 32 ? all >> (2 * vhi) : 0ull)) : 0ull;
+                    const uint64_t NM = (uint64_t) NM0 << 32 | NM1;
+                    uint64_t M = (uint64_t) M0 << 32 | M1;
+                    M |= NM | (NM >> 2);
+                    if (vlo > 0 && vlo < 32) M |= 1ull << (2 * (31 - vlo));
+                    M &= keep;
+                    M0 = (uint32_t) (M >> 32); M1 = (uint32_t) M;
                 }
             }
+            const uint32_t cnt = __popc(M0) + __popc(M1);
+            // read position of my last start, and of the latest start in front of my chunk
+            int mylast = -1;
+            if (M1) mylast = rel + 31 - ((__ffs(M1) - 1) >> 1);
+            else if (M0) mylast = rel + 15 - ((__ffs(M0) - 1) >> 1);
+            const uint32_t has = __ballot_sync(SG_FULL, cnt != 0);
+            const uint32_t below = has & lt_mask;
+            int prev = __shfl_sync(SG_FULL, mylast, below ? 31 - __clz(below) : 0);
+            if (!below) prev = lastpos;
+            if (has) lastpos = __shfl_sync(SG_FULL, mylast, 31 - __clz(has));
+            // hoco index of my first start
+            uint32_t inc = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const uint32_t a = __shfl_up_sync(SG_FULL, inc, d); if (lane >= d) inc += a; }
+            const uint32_t tot = __shfl_sync(SG_FULL, inc, 31);
+            uint32_t e = n_stage + inc - cnt;              // slot of my first start
+
             if (cnt) {
-                // my cnt codes sit in the low 2*cnt bits of CP: drop them at bit 2*(n_stage+ex) of the big-endian stream
-                const uint32_t bitpos = 2u * (n_stage + ex);
-                const uint64_t v = ((uint64_t) CP << (64 - 2 * cnt)) >> (bitpos & 31u);
-                atomicOr(&s_w[bitpos >> 5], (uint32_t) (v >> 32));
-                if ((uint32_t) v) atomicOr(&s_w[(bitpos >> 5) + 1], (uint32_t) v);
+                if (rel + 31 - prev < 255) {
+                    // fast: no run that closes in my chunk can reach 256. nb = -(position of the latest start
+                    // relative to my chunk), so a start at i closes a run of length - 1 = i - 1 + nb.
+                    uint16_t *pe = ent + e;
+                    int nb = rel - prev;
+#define SG_ENC_STEP(I, MW, CW) { \
+                        const bool st = (MW >> (2 * (15 - ((I) & 15)))) & 1u; \
+                        const uint32_t v = __byte_perm((uint32_t) (nb + (I) - 1), CW, 0x0040 | ((4 + ((I) & 3)) << 4)); \
+                        if (st) { *pe = (uint16_t) v; ++pe; nb = -(I); } }
+                    SG_ENC_STEP(0, M0, cc[0]) SG_ENC_STEP(1, M0, cc[0]) SG_ENC_STEP(2, M0, cc[0]) SG_ENC_STEP(3, M0, cc[0])
+                    SG_ENC_STEP(4, M0, cc[1]) SG_ENC_STEP(5, M0, cc[1]) SG_ENC_STEP(6, M0, cc[1]) SG_ENC_STEP(7, M0, cc[1])
+                    SG_ENC_STEP(8, M0, cc[2]) SG_ENC_STEP(9, M0, cc[2]) SG_ENC_STEP(10, M0, cc[2]) SG_ENC_STEP(11, M0, cc[2])
+                    SG_ENC_STEP(12, M0, cc[3]) SG_ENC_STEP(13, M0, cc[3]) SG_ENC_STEP(14, M0, cc[3]) SG_ENC_STEP(15, M0, cc[3])
+                    SG_ENC_STEP(16, M1, cc[4]) SG_ENC_STEP(17, M1, cc[4]) SG_ENC_STEP(18, M1, cc[4]) SG_ENC_STEP(19, M1, cc[4])
+                    SG_ENC_STEP(20, M1, cc[5]) SG_ENC_STEP(21, M1, cc[5]) SG_ENC_STEP(22, M1, cc[5]) SG_ENC_STEP(23, M1, cc[5])
+                    SG_ENC_STEP(24, M1, cc[6]) SG_ENC_STEP(25, M1, cc[6]) SG_ENC_STEP(26, M1, cc[6]) SG_ENC_STEP(27, M1, cc[6])
+                    SG_ENC_STEP(28, M1, cc[7]) SG_ENC_STEP(29, M1, cc[7]) SG_ENC_STEP(30, M1, cc[7]) SG_ENC_STEP(31, M1, cc[7])
+#undef SG_ENC_STEP
+                } else {
+                    // a long run may close here: exact lengths, saturation and the side list
+                    int pv = prev;
+                    for (int i = 0; i < 32; ++i) {
+                        const uint32_t MW = i < 16 ? M0 : M1;
+                        if (!((MW >> (2 * (15 - (i & 15)))) & 1u)) continue;
+                        uint32_t rl1 = (uint32_t) (rel + i - pv - 1);
+                        if (rl1 >= 255u) { if (g_done + e > 0) side_list(g_done + e - 1, rl1); rl1 = 255u; }
+                        uint32_t cw = 0;
+#pragma unroll
+                        for (int jj = 0; jj < 8; ++jj) if (jj == (i >> 2)) cw = cc[jj];
+                        ent[e] = (uint16_t) (rl1 | ((cw >> (8 * (i & 3))) & 0xffu) << 8);
+                        pv = rel + i;
+                        ++e;
+                    }
+                }
             }
-        }
-        const bool last = (t + 1 == ntiles);
-        const uint32_t n_avail = n_stage + tot;
-        if (last && tid == 0 && n_avail) close_run(n_avail - 1, (uint32_t) ((int) len - blast - 1));
-        __syncthreads();
-        const uint32_t fin = last ? n_avail : (n_avail ? ((n_avail - 1) & ~15u) : 0);
+            const bool last = (t + 1 == ntiles);
+            const uint32_t n_avail = n_stage + tot;
+            __syncwarp();
+            if (last && lane == 0 && n_avail) {
+                // the end of the read closes the last run
+                uint32_t rl1 = (uint32_t) (len - lastpos - 1);
+                if (rl1 >= 255u) { side_list(g_done + n_avail - 1, rl1); rl1 = 255u; }
+                ent[n_avail] = (uint16_t) rl1;
+            }
+            __syncwarp();
+            const uint32_t fin = last ? n_avail : (n_avail ? ((n_avail - 1) & ~15u) : 0);
 
-        // write the finished groups of 16: one code word, 16 run-length bytes, 16 flags
-        const uint32_t ngrp = (fin + 15) >> 4;
-        for (uint32_t gi = tid; gi < ngrp; gi += NT) {
-            hs32[(g_done >> 4) + gi] = bswap32(s_w[gi]);
-            nb16[(g_done >> 4) + gi] = (uint16_t) (s_nbw[gi >> 1] >> (16 * (gi & 1)));
-            *reinterpret_cast<uint4 *>(rl8 + g_done + 16 * gi) = *reinterpret_cast<const uint4 *>(s_rl + 16 * gi);
+            // emit the finished groups of 16: slot e = {low byte: length - 1 of entry e-1, high byte: code of entry e}
+            const uint32_t ngrp = (fin + 15) >> 4;
+            for (uint32_t gi = lane; gi < ngrp; gi += 32) {
+                const uint4 A0 = *reinterpret_cast<const uint4 *>(ent32 + 8 * gi), A1 = *reinterpret_cast<const uint4 *>(ent32 + 8 * gi + 4);
+                const uint32_t W8 = ent32[8 * gi + 8];
+                const uint32_t W[9] = {A0.x, A0.y, A0.z, A0.w, A1.x, A1.y, A1.z, A1.w, W8};
+                uint32_t R[4], C[4];
+#pragma unroll
+                for (int m = 0; m < 4; ++m) {
+                    C[m] = __byte_perm(W[2 * m], W[2 * m + 1], 0x7531);                    // codes of entries 4m .. 4m+3
+                    const uint32_t x = __byte_perm(W[2 * m], W[2 * m + 1], 0x0642);        // lengths of 4m, 4m+1, 4m+2
+                    R[m] = __byte_perm(x, W[2 * m + 2], 0x4210);                           // and 4m+3 from the next word
+                }
+                uint32_t code = pack4(C[0]) | pack4(C[1]) << 8 | pack4(C[2]) << 16 | pack4(C[3]) << 24;
+                uint32_t nflag = 0;
+                if (any_n) {
+#pragma unroll
+                    for (int m = 0; m < 4; ++m) nflag |= ((((C[m] >> 2) & 0x01010101u) * 0x10204080u) >> 28) << (4 * m);   // bytes 0..3 -> bits 0..3
+                }
+                const uint32_t left = fin - 16 * gi;       // entries of this group that exist (>= 16 except in the last group of a read)
+                if (left < 16) {
+                    // keep the unused tail of the last word clean: bases beyond hoco_l read as zero
+                    uint32_t keepc = 0;
+                    for (uint32_t i = 0; i < left; ++i) keepc |= 3u << (2 * (3 - (i & 3)) + 8 * (i >> 2));
+                    code &= keepc;
+                    nflag &= (1u << left) - 1u;
+#pragma unroll
+                    for (int m = 0; m < 4; ++m)
+                        for (int b = 0; b < 4; ++b) if ((uint32_t) (4 * m + b) >= left) R[m] &= ~(0xffu << (8 * b));
+                }
+                const uint32_t go = (g_done >> 4) + gi;
+                hs32[go] = code;
+                nb16[go] = (uint16_t) nflag;
+                rl128[go] = make_uint4(R[0], R[1], R[2], R[3]);
+            }
+            // what stays staged: the open run and an incomplete group (at most 16 entries)
+            const uint32_t n_carry = n_avail - fin;
+            uint16_t cv = 0;
+            if ((uint32_t) lane < n_carry) cv = ent[fin + lane];
+            __syncwarp();
+            if ((uint32_t) lane < n_carry) ent[lane] = cv;
+            n_stage = n_carry;
+            g_done += fin;
+            __syncwarp();
         }
-        // what stays staged: the open run and an incomplete group (at most 16 entries, one word)
-        const uint32_t n_carry = n_avail - fin;
-        const uint32_t cw = s_w[fin >> 4], cn = (s_nbw[fin >> 5] >> (fin & 16u)) & 0xffffu;
-        uint8_t cb = 0;
-        if ((uint32_t) tid < n_carry) cb = s_rl[fin + tid];
-        __syncthreads();
-        if ((uint32_t) tid < n_carry) s_rl[tid] = cb;
-        for (int i = tid; i < NWORD; i += NT) s_w[i] = (i == 0 && n_carry) ? cw : 0u;
-        for (int i = tid; i < NWORD / 2 + 2; i += NT) s_nbw[i] = (i == 0 && n_carry) ? cn : 0u;
-        n_stage = n_carry;
-        g_done += fin;
-        carry_last = blast;
-        // the two barriers of the next tile's scan order these writes before anybody stages again
-    }
-    if (tid == 0) {
-        A.hoco_l[r] = g_done;
-        A.n_amb[r] = s_namb;
+        n_amb = __reduce_add_sync(SG_FULL, n_amb);
+        if (lane == 0) {
+            A.hoco_l[r] = g_done;
+            A.n_amb[r] = n_amb;
+        }
     }
 }
 
-int launch_encode(const EncodeArgs &A, uint64_t n_reads, cudaStream_t st)
+int launch_encode(const EncodeArgs &A, cudaStream_t st)
 {
-    if (n_reads == 0) return 0;
-    encode_kernel<128><<<(unsigned) n_reads, 128, 0, st>>>(A);
+    if (A.n_reads == 0) return 0;
+    static int ctas_per_sm = 0, n_sm = 0;
+    if (!ctas_per_sm) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+        if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, encode_kernel, 32 * ENC_WARPS, 0) != cudaSuccess) return -1;
+        if (ctas_per_sm < 1) return -1;
+    }
+    const uint64_t want = (A.n_reads + ENC_WARPS - 1) / ENC_WARPS;
+    const unsigned grid = (unsigned) std::min<uint64_t>(want, (uint64_t) n_sm * ctas_per_sm);
+    encode_kernel<<<grid, 32 * ENC_WARPS, 0, st>>>(A);
     return 1;
 }
 

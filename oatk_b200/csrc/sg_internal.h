@@ -10,6 +10,8 @@ struct EncodeArgs {
     const uint8_t *bases;        // all reads back to back
     const uint64_t *off;         // n_reads + 1 raw offsets
     const uint64_t *hoff;        // n_reads + 1 capacity offsets (multiples of 64)
+    uint64_t n_reads;
+    unsigned int *work;          // zeroed before the launch: next read to hand to a warp
     uint8_t *hoco_s, *ho_rl, *nbits;
     uint32_t *hoco_l;            // per read
     uint32_t *n_amb;             // per read: ambiguous characters
@@ -18,29 +20,31 @@ struct EncodeArgs {
     uint32_t *amb_sid, *amb_pos;
     uint32_t *lrl_sid, *lrl_idx, *lrl_val;
 };
-int launch_encode(const EncodeArgs &A, uint64_t n_reads, cudaStream_t st);
+int launch_encode(const EncodeArgs &A, cudaStream_t st);
 
 struct ScanArgs {
     const uint64_t *hoff;
     const uint8_t *hoco_s, *nbits;
     const uint32_t *hoco_l, *n_amb;
     int k, s;
+    uint64_t n_reads;
+    unsigned int *work;          // zeroed before the launch: next read to hand to a warp
     uint32_t *n_scm;             // per read: syncmers emitted
     unsigned long long *rec_count;
     uint64_t rec_cap;
     uint32_t *rec_sid, *rec_idx, *rec_mpos;   // unordered records (one per syncmer)
     uint64_t *rec_smer;
 };
-constexpr int SYNC_SCAN_NT = 64;    // threads per CTA of the syncmer scan kernel (16 positions each)
+constexpr int SYNC_SCAN_WARPS = 2;  // warps per CTA of the syncmer scan kernel (one read per warp, 16 positions per lane and tile)
 struct ScanGeom {
-    int rch;        // ring size in chunks (power of two)
-    int n_full;     // chunks fully inside every window of a thread's 16 positions
-    int T;          // top level of the radix-4 sparse table (4^T <= n_full)
+    int rch;        // ring size in chunks of 16 positions (power of two, >= window + one tile)
+    int n_full;     // chunks fully inside every window of a lane's 16 positions
+    int logB;       // chunk minima are prefix/suffix-min scanned in blocks of 2^logB lanes (2^logB <= n_full)
     H31Consts h31;  // shift multipliers of the s = 31 hash (kept as parameters: see sg_hash31.cuh)
 };
-int scan_geometry(int k, int s, int nt, ScanGeom *g, size_t *smem);
+int scan_geometry(int k, int s, ScanGeom *g, size_t *smem_per_warp);
 // returns launches (>= 0) or a negative SG_E_* code
-int launch_scan(const ScanArgs &A, uint64_t n_reads, cudaStream_t st);
+int launch_scan(const ScanArgs &A, cudaStream_t st);
 
 struct KmerArgs {
     const uint64_t *hoff;
