@@ -56,6 +56,13 @@ __device__ __forceinline__ uint32_t classify4(uint32_t w, uint32_t &bad)
     bad |= ((w ^ t17) & 0xD9D9D9D9u) ^ 0x41414141u;
     return c0 + 2u * c1;
 }
+// validity word of four bytes (zero byte = one of ACGTacgt), not accumulated
+__device__ __forceinline__ uint32_t invalid4(uint32_t w)
+{
+    const uint32_t K = 0x01010101u;
+    const uint32_t t17 = ((w >> 2) & ((w >> 1) ^ (w >> 2)) & K) * 17u;
+    return ((w ^ t17) & 0xD9D9D9D9u) ^ 0x41414141u;
+}
 // codes in byte lanes -> 8 bits, first byte in bits 7:6
 __device__ __forceinline__ uint32_t pack4(uint32_t cc) { return ((cc & 0x03030303u) * 0x40100401u) >> 24; }
 
@@ -119,7 +126,17 @@ __global__ void __launch_bounds__(32 * ENC_WARPS) encode_kernel(EncodeArgs A)
             // valid positions of my chunk: [vlo, vhi)
             const int vlo = min(32, max(0, -rel)), vhi = max(0, min(32, len - rel));
             uint32_t NM0 = 0, NM1 = 0;                     // ambiguous positions, bit 2*(15-i) like the start masks
-            if (!inside || bad) {
+            if (!inside) {
+                // chunk at the head or tail of the read: only the bytes inside the read decide whether it is plain ACGT
+                bad = 0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int lo = max(vlo - 4 * j, 0), hi = min(vhi - 4 * j, 4);       // valid bytes [lo, hi) of word j
+                    const uint32_t bm = hi > lo ? (0xffffffffu >> (8 * (4 - hi + lo))) << (8 * lo) : 0u;
+                    bad |= invalid4(w[j]) & bm;
+                }
+            }
+            if (bad) {
                 // exact per-byte codes (also fixes U, raw 0..3) for the valid bytes; everything else becomes 0
                 bad = 0;
 #pragma unroll 1

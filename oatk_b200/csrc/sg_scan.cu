@@ -31,6 +31,7 @@
 //      emissions are queued in a 64-entry list and written out as (sid, idx, m_pos, s_mer) records
 //      when the list fills or the read ends; k-mer hashes follow in sg_kmer.cu
 #include <algorithm>
+#include <cuda_pipeline.h>
 #include "sg_common.cuh"
 #include "sg_hash31.cuh"
 #include "sg_internal.h"
@@ -68,23 +69,28 @@ __device__ __noinline__ bool settle_tie(const uint32_t *ring, int RCH, const uin
     return mp <= mo && (mp <= e64 || mp < mo || m64_at(p - q + 1) == mp);
 }
 
-template <int S_FIXED, int RCH_FIXED>
+template <int S_FIXED, int RCH_FIXED, int LOGB_FIXED>
 __global__ void __launch_bounds__(32 * SYNC_SCAN_WARPS) scan_kernel(ScanArgs A, ScanGeom G)
 {
     extern __shared__ __align__(16) uint32_t smem[];
     const int RCH = RCH_FIXED ? RCH_FIXED : G.rch, RM = RCH - 1;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    uint32_t *ring = smem + (size_t) wid * (18 * RCH + 2 * LISTCAP);   // [16][RCH] keys of m[]
+    uint32_t *ring = smem + (size_t) wid * (18 * RCH + 2 * LISTCAP + 64);   // [16][RCH] keys of m[]
     uint32_t *Lv0 = ring + 16 * RCH;                   // [RCH] chunk minima
     uint32_t *sfxA = Lv0 + RCH;                        // [RCH] suffix minimum of the chunk's block from the chunk on
     uint32_t *list_c = sfxA + RCH;                     // [LISTCAP] chunk index
     uint32_t *list_e = list_c + LISTCAP;               // [LISTCAP] E | Om << 16
+    uint32_t *wbuf = list_e + LISTCAP;                 // [2][32] packed words of the next tile, filled by cp.async
 
     const int k = A.k, s = S_FIXED ? S_FIXED : A.s, q = k - s + 1;
     const uint64_t mask = (1ull << (2 * s)) - 1;
     const int rsh = 2 * s - 2;
     const bool small_q = q < 16;       // a thread's earlier positions fall out of the window: no running bound
-    const int n_full = G.n_full, logB = G.logB, B = 1 << logB;
+    const int n_full = G.n_full, logB = LOGB_FIXED >= 0 ? LOGB_FIXED : G.logB, B = 1 << logB;
+    // tile-invariant per lane: my place in my block of B chunks, and how many whole blocks lie between the
+    // block that holds the first chunk of my window (c - n_full) and my own block
+    const int lb = lane & (B - 1);
+    const int n_between = n_full > 0 ? ((lane >> logB) - ((lane - n_full) >> logB) - 1) : 0;
     auto ring_at = [&](int x) -> uint32_t { return ring[(x & 15) * RCH + ((x >> 4) & RM)]; };
 
     for (;;) {
@@ -109,8 +115,14 @@ __global__ void __launch_bounds__(32 * SYNC_SCAN_WARPS) scan_kernel(ScanArgs A, 
         int last_n = -1;                                   // last ambiguous position seen so far
         uint32_t prev30 = 0, prev31 = 0;                   // the two words in front of the tile
         const int n_tiles = (H + 1 + 511) >> 9;
-        // raw (still byte-swapped) word of the next tile: loaded a tile ahead, converted only when it is used
-        uint32_t w_next = lane < nwords ? __ldg(hs32 + lane) : 0u;
+        // the packed word of the next tile travels global -> shared with cp.async one tile ahead, so no
+        // register waits on it while the current tile is hashed
+        auto fetch_word = [&](int cw, int slot) {
+            if (cw < nwords) __pipeline_memcpy_async(wbuf + 32 * slot + lane, hs32 + cw, 4);
+            else wbuf[32 * slot + lane] = 0u;
+            __pipeline_commit();
+        };
+        fetch_word(lane, 0);
 
         // writes the records of the queued chunks
         auto flush = [&]() {
@@ -156,8 +168,9 @@ __global__ void __launch_bounds__(32 * SYNC_SCAN_WARPS) scan_kernel(ScanArgs A, 
             const int c = (tl << 5) + lane;                // my chunk
             const int P = c << 4;                          // its first position
             const int cs = c & RM;
-            const uint32_t w0 = bswap32(w_next);
-            w_next = c + 32 < nwords ? __ldg(hs32 + c + 32) : 0u;   // in flight while this tile is hashed
+            __pipeline_wait_prior(0);
+            const uint32_t w0 = bswap32(wbuf[32 * (tl & 1) + lane]);
+            fetch_word(c + 32, (tl + 1) & 1);
             uint32_t wb = __shfl_up_sync(SG_FULL, w0, 1), wa = __shfl_up_sync(SG_FULL, w0, 2);
             if (lane == 0) { wb = prev31; wa = prev30; }
             if (lane == 1) wa = prev31;
@@ -238,21 +251,25 @@ __global__ void __launch_bounds__(32 * SYNC_SCAN_WARPS) scan_kernel(ScanArgs A, 
 
             // 2. minimum over the n_full whole chunks in front of mine: prefix / suffix minima inside blocks of B lanes
             uint32_t pfx = cmin, sfx = cmin;
-            for (int d = 1; d < B; d <<= 1) {
-                const uint32_t up = __shfl_up_sync(SG_FULL, pfx, d), dn = __shfl_down_sync(SG_FULL, sfx, d);
-                if ((lane & (B - 1)) >= d) pfx = min(pfx, up);
-                if ((lane & (B - 1)) + d < B) sfx = min(sfx, dn);
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                if (d < B) {
+                    const uint32_t up = __shfl_up_sync(SG_FULL, pfx, d), dn = __shfl_down_sync(SG_FULL, sfx, d);
+                    if (lb >= d) pfx = min(pfx, up);
+                    if (lb + d < B) sfx = min(sfx, dn);
+                }
             }
             Lv0[cs] = cmin;
             sfxA[cs] = sfx;
             uint32_t pex = __shfl_up_sync(SG_FULL, pfx, 1);                // my block's chunks in front of me
-            if ((lane & (B - 1)) == 0) pex = HNONE;
+            if (lb == 0) pex = HNONE;
             __syncwarp();
             uint32_t r0 = HNONE;
             if (n_full > 0) {
-                const int sc = c - n_full;
-                r0 = min(pex, sfxA[sc & RM]);
-                for (int bk = (sc >> logB) + 1; bk < (c >> logB); ++bk) r0 = min(r0, sfxA[(bk << logB) & RM]);
+                int sl = (c - n_full) & RM;                                  // first chunk of my window
+                r0 = min(pex, sfxA[sl]);
+                sl &= ~(B - 1);                                              // its block; block totals sit at block starts
+                for (int j = 0; j < n_between; ++j) { sl = (sl + B) & RM; r0 = min(r0, sfxA[sl]); }
             }
 
             // 3. which chunks can hold a candidate at all
@@ -359,14 +376,14 @@ int scan_geometry(int k, int s, ScanGeom *g, size_t *smem_per_warp)
     int rch = 64;
     while (rch < need) rch <<= 1;
     g->rch = rch; g->n_full = n_full; g->logB = logB; g->h31 = h31_consts();
-    *smem_per_warp = sizeof(uint32_t) * ((size_t) 18 * rch + 2 * LISTCAP);
+    *smem_per_warp = sizeof(uint32_t) * ((size_t) 18 * rch + 2 * LISTCAP + 64);
     return *smem_per_warp <= 227 * 1024 ? 0 : SG_E_KSIZE;
 }
 
-template <int S_FIXED, int RCH_FIXED>
+template <int S_FIXED, int RCH_FIXED, int LOGB_FIXED>
 static int launch_scan_t(const ScanArgs &A, const ScanGeom &g, size_t smem_per_warp, cudaStream_t st)
 {
-    auto kern = scan_kernel<S_FIXED, RCH_FIXED>;
+    auto kern = scan_kernel<S_FIXED, RCH_FIXED, LOGB_FIXED>;
     static int ctas_per_sm = 0, n_sm = 0;
     static size_t smem_set = 0;
     int warps = SYNC_SCAN_WARPS;
@@ -394,12 +411,13 @@ int launch_scan(const ScanArgs &A, cudaStream_t st)
     if (scan_geometry(A.k, A.s, &g, &spw)) return SG_E_KSIZE;
     if (A.n_reads == 0) return 0;
     if (A.s == 31) {
-        if (g.rch == 64) return launch_scan_t<31, 64>(A, g, spw, st);
-        if (g.rch == 128) return launch_scan_t<31, 128>(A, g, spw, st);
-        if (g.rch == 256) return launch_scan_t<31, 256>(A, g, spw, st);
-        return launch_scan_t<31, 0>(A, g, spw, st);
+        // the shapes of the benchmark sweep (k = 501, 1001, 2001) get compile-time ring and block sizes
+        if (g.rch == 64 && g.logB == 4) return launch_scan_t<31, 64, 4>(A, g, spw, st);
+        if (g.rch == 128 && g.logB == 5) return launch_scan_t<31, 128, 5>(A, g, spw, st);
+        if (g.rch == 256 && g.logB == 5) return launch_scan_t<31, 256, 5>(A, g, spw, st);
+        return launch_scan_t<31, 0, -1>(A, g, spw, st);
     }
-    return launch_scan_t<0, 0>(A, g, spw, st);
+    return launch_scan_t<0, 0, -1>(A, g, spw, st);
 }
 
 } // namespace sg
