@@ -377,7 +377,7 @@ def run_e2e(torch, lib, ctx, batch, bases, off, n_reads, total, sizes, csz, step
     L = lib.library()
     n_slots = env_int("SG_PIPE_SLOTS", 6)
     pipe = lib.Pipe(ctx.device, n_slots)
-    chunk = env_int("SG_PIPE_CHUNK", 16384)
+    chunk = env_int("SG_PIPE_CHUNK", 4096)
     torch.cuda.synchronize()
 
     def one():

@@ -32,10 +32,21 @@ __global__ void __launch_bounds__(256) add_offset_kernel(const uint64_t *src, ui
 
 using namespace sg;
 
+// per slot: two device input buffers, so the upload of the slot's next chunk (on its own stream) runs
+// while the current chunk is computed and downloaded
+struct SlotIn {
+    cudaStream_t up = nullptr;
+    cudaEvent_t ready[2] = {nullptr, nullptr};
+    DevBuf bases[2], off[2];
+    uint64_t *h_off[2] = {nullptr, nullptr};       // pinned chunk-local offsets
+    size_t h_off_cap = 0;
+};
+
 struct sg_pipe {
     int device = 0, n_slots = 0;
     std::vector<sg_ctx *> ctx;
     std::vector<sg_batch *> slot;
+    std::vector<SlotIn *> in;
     sg_ctx *mctx = nullptr;
     sg_batch *master = nullptr;
     std::string err;
@@ -63,6 +74,11 @@ int sg_pipe_create(int device, int n_slots, sg_pipe **out)
         }
         sg_ctx_set_stream(c, st);
         p->ctx.push_back(c); p->slot.push_back(b);
+        SlotIn *si = new SlotIn();
+        p->in.push_back(si);
+        if (cudaStreamCreateWithFlags(&si->up, cudaStreamNonBlocking) != cudaSuccess ||
+                cudaEventCreateWithFlags(&si->ready[0], cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventCreateWithFlags(&si->ready[1], cudaEventDisableTiming) != cudaSuccess) { rc = SG_E_CUDA; break; }
     }
     if (rc) { sg_pipe_destroy(p); return rc; }
     *out = p;
@@ -78,6 +94,11 @@ void sg_pipe_destroy(sg_pipe *p)
         cudaStream_t st = p->ctx[i]->stream;
         sg_ctx_destroy(p->ctx[i]);
         if (st) cudaStreamDestroy(st);
+    }
+    for (SlotIn *si : p->in) {
+        if (si->up) cudaStreamDestroy(si->up);
+        for (int j = 0; j < 2; ++j) { if (si->ready[j]) cudaEventDestroy(si->ready[j]); if (si->h_off[j]) cudaFreeHost(si->h_off[j]); }
+        delete si;
     }
     if (p->master) sg_batch_destroy(p->master);
     if (p->mctx) sg_ctx_destroy(p->mctx);
@@ -136,21 +157,49 @@ int sg_pipe_run_host(sg_pipe *p, const char *bases, const uint64_t *off, uint64_
         sg_batch *b = p->slot[si];
         sg_ctx *ctx = p->ctx[si];
         cudaStream_t st = ctx->stream;
-        for (uint64_t c = si; c < n_chunks; c += p->n_slots) {
+        SlotIn *in = p->in[si];
+        // chunk-local offsets live in pinned memory so that their copy is asynchronous too
+        if (in->h_off_cap < chunk_reads + 1) {
+            for (int j = 0; j < 2; ++j) {
+                if (in->h_off[j]) cudaFreeHost(in->h_off[j]);
+                in->h_off[j] = nullptr;
+                cudaMallocHost((void **) &in->h_off[j], (chunk_reads + 1) * sizeof(uint64_t));
+            }
+            in->h_off_cap = chunk_reads + 1;
+        }
+        // uploads chunk c into input buffer j on the slot's upload stream
+        auto upload = [&](uint64_t c, int j) -> int {
             const uint64_t r0 = c * chunk_reads, r1 = std::min(n_reads, r0 + chunk_reads), nr = r1 - r0;
-            int rc = SG_OK;
+            const uint64_t nb = off[r1] - off[r0];
+            if (!in->h_off[j] || in->bases[j].reserve(nb + 64) || in->off[j].reserve((nr + 1) * sizeof(uint64_t))) return SG_E_NOMEM;
+            for (uint64_t i = 0; i <= nr; ++i) in->h_off[j][i] = off[r0 + i] - off[r0];
+            if (nb && cudaMemcpyAsync(in->bases[j].p, bases + off[r0], nb, cudaMemcpyHostToDevice, in->up) != cudaSuccess) return SG_E_CUDA;
+            if (cudaMemcpyAsync(in->off[j].p, in->h_off[j], (nr + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, in->up) != cudaSuccess) return SG_E_CUDA;
+            if (cudaEventRecord(in->ready[j], in->up) != cudaSuccess) return SG_E_CUDA;
+            b->h2d_bytes += nb + (nr + 1) * sizeof(uint64_t);
+            return SG_OK;
+        };
+        int cur = 0;
+        int up_rc = (uint64_t) si < n_chunks ? upload(si, 0) : SG_OK;
+        for (uint64_t c = si; c < n_chunks; c += p->n_slots, cur ^= 1) {
+            const uint64_t r0 = c * chunk_reads, r1 = std::min(n_reads, r0 + chunk_reads), nr = r1 - r0;
+            int rc = up_rc;
             std::string msg;
+            if (rc) msg = "upload failed";
             double t0 = now();
-            std::vector<uint64_t> loff(nr + 1), l_hs(nr + 1), l_rl(nr + 1), l_scm(nr + 1);
-            for (uint64_t i = 0; i <= nr; ++i) loff[i] = off[r0 + i] - off[r0];
+            std::vector<uint64_t> l_hs(nr + 1), l_rl(nr + 1), l_scm(nr + 1);
+            const uint64_t *loff = in->h_off[cur];
             sg_batch_set_sid_base(b, r0);
             sg_extract_sizes_t z;
             memset(&z, 0, sizeof(z));
             {
                 std::lock_guard<std::mutex> g(mu);
-                if (first_err) rc = first_err;
+                if (first_err && !rc) rc = first_err;
             }
-            if (!rc) rc = sg_batch_set_reads_host(b, bases + off[r0], loff.data(), nr);
+            if (!rc && cudaStreamWaitEvent(st, in->ready[cur], 0) != cudaSuccess) rc = SG_E_CUDA;
+            if (!rc) rc = sg_batch_set_reads_device(b, in->bases[cur].p, (const uint64_t *) in->off[cur].p, nr, off[r1] - off[r0]);
+            // the slot's next chunk starts to travel now: its buffer was last read by the extract of two rounds ago
+            if (!rc && c + p->n_slots < n_chunks) up_rc = upload(c + p->n_slots, cur ^ 1);
             if (!rc) rc = sg_extract(b, k, s);
             if (!rc) rc = sg_extract_sizes(b, &z);
             if (rc && msg.empty()) msg = ctx->err;
@@ -230,6 +279,7 @@ int sg_pipe_run_host(sg_pipe *p, const char *bases, const uint64_t *off, uint64_
             }
             tp[4] += now() - t4;
         }
+        cudaStreamSynchronize(in->up);
         cudaStreamSynchronize(st);
     };
 

@@ -48,9 +48,9 @@ constexpr int LISTCAP = 64;            // queued chunks with emissions (a tile a
 __device__ __noinline__ bool settle_tie(const uint32_t *ring, int RCH, const uint32_t *hs32, int nwords, int s,
         int p, int q, bool is_open, uint32_t tgt, int lane)
 {
-    const int RM = RCH - 1;
+    const int RM = RCH - 1, RS = RCH + 2;
     const uint64_t mask = (1ull << (2 * s)) - 1;
-    auto ring_at = [&](int x) -> uint32_t { return ring[(x & 15) * RCH + ((x >> 4) & RM)]; };
+    auto ring_at = [&](int x) -> uint32_t { return ring[(x & 15) * RS + ((x >> 4) & RM)]; };
     auto m64_at = [&](int x) -> uint64_t {
         if (x < 0 || ring_at(x) == HNONE) return SG_NONE64;
         return hash64(smer_code_at(hs32, x, s, nwords) >> 1, mask);
@@ -73,10 +73,12 @@ template <int S_FIXED, int RCH_FIXED, int LOGB_FIXED>
 __global__ void __launch_bounds__(32 * SYNC_SCAN_WARPS) scan_kernel(ScanArgs A, ScanGeom G)
 {
     extern __shared__ __align__(16) uint32_t smem[];
-    const int RCH = RCH_FIXED ? RCH_FIXED : G.rch, RM = RCH - 1;
+    // ring rows are RCH + 2 words apart: a chunk's 16 positions (one column) and 32 consecutive positions
+    // (two columns) then fall into distinct banks, like the 32 chunks of a tile (one row)
+    const int RCH = RCH_FIXED ? RCH_FIXED : G.rch, RM = RCH - 1, RS = RCH + 2;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    uint32_t *ring = smem + (size_t) wid * (18 * RCH + 2 * LISTCAP + 64);   // [16][RCH] keys of m[]
-    uint32_t *Lv0 = ring + 16 * RCH;                   // [RCH] chunk minima
+    uint32_t *ring = smem + (size_t) wid * (16 * RS + 2 * RCH + 2 * LISTCAP + 64);   // [16][RS] keys of m[]
+    uint32_t *Lv0 = ring + 16 * RS;                    // [RCH] chunk minima
     uint32_t *sfxA = Lv0 + RCH;                        // [RCH] suffix minimum of the chunk's block from the chunk on
     uint32_t *list_c = sfxA + RCH;                     // [LISTCAP] chunk index
     uint32_t *list_e = list_c + LISTCAP;               // [LISTCAP] E | Om << 16
@@ -91,7 +93,7 @@ __global__ void __launch_bounds__(32 * SYNC_SCAN_WARPS) scan_kernel(ScanArgs A, 
     // block that holds the first chunk of my window (c - n_full) and my own block
     const int lb = lane & (B - 1);
     const int n_between = n_full > 0 ? ((lane >> logB) - ((lane - n_full) >> logB) - 1) : 0;
-    auto ring_at = [&](int x) -> uint32_t { return ring[(x & 15) * RCH + ((x >> 4) & RM)]; };
+    auto ring_at = [&](int x) -> uint32_t { return ring[(x & 15) * RS + ((x >> 4) & RM)]; };
 
     for (;;) {
         unsigned int r32 = 0;
@@ -107,7 +109,7 @@ __global__ void __launch_bounds__(32 * SYNC_SCAN_WARPS) scan_kernel(ScanArgs A, 
         const int nwords = (H + 15) >> 4;
         const bool has_n = A.n_amb[r] != 0;
 
-        for (int i = lane; i < 18 * RCH; i += 32) ring[i] = HNONE;      // ring, Lv0, sfxA
+        for (int i = lane; i < 16 * RS + 2 * RCH; i += 32) ring[i] = HNONE;      // ring, Lv0, sfxA
         __syncwarp();
 
         uint32_t n_emitted = 0, carryC = 0;
@@ -212,7 +214,7 @@ __global__ void __launch_bounds__(32 * SYNC_SCAN_WARPS) scan_kernel(ScanArgs A, 
                 const uint32_t ra = rev2(~w0), rb = rev2(~wb), rc = rev2(~wa);
                 if (vm == 0xffffu) {
 #define SG_H31_POS(J) { uint32_t hi, lo; h31_canon<J>(wa, wb, w0, ra, rb, rc, hi, lo); \
-                        const uint32_t hv = min(h31_hash_top(hi, lo, G.h31), 0xfffffffeu); own[(J) * RCH] = hv; cmin = min(cmin, hv); }
+                        const uint32_t hv = min(h31_hash_top(hi, lo, G.h31), 0xfffffffeu); own[(J) * RS] = hv; cmin = min(cmin, hv); }
                     SG_H31_POS(0) SG_H31_POS(1) SG_H31_POS(2) SG_H31_POS(3) SG_H31_POS(4) SG_H31_POS(5) SG_H31_POS(6) SG_H31_POS(7)
                     SG_H31_POS(8) SG_H31_POS(9) SG_H31_POS(10) SG_H31_POS(11) SG_H31_POS(12) SG_H31_POS(13) SG_H31_POS(14) SG_H31_POS(15)
 #undef SG_H31_POS
@@ -222,7 +224,7 @@ __global__ void __launch_bounds__(32 * SYNC_SCAN_WARPS) scan_kernel(ScanArgs A, 
                         uint32_t hi, lo;
                         h31_canon_rt(j, wa, wb, w0, ra, rb, rc, hi, lo);
                         const uint32_t hv = ((vm >> j) & 1u) ? min(h31_hash_top(hi, lo, G.h31), 0xfffffffeu) : HNONE;
-                        own[j * RCH] = hv;
+                        own[j * RS] = hv;
                         cmin = min(cmin, hv);
                     }
                 }
@@ -241,12 +243,12 @@ __global__ void __launch_bounds__(32 * SYNC_SCAN_WARPS) scan_kernel(ScanArgs A, 
                     vmr >>= 1;
                     const uint32_t h = (uint32_t) (hash64(fw < rv ? fw : rv, mask) >> 32);
                     const uint32_t hv = ok ? h : HNONE;
-                    own[j * RCH] = hv;
+                    own[j * RS] = hv;
                     cmin = min(cmin, hv);
                 }
             } else {
 #pragma unroll 4
-                for (int i = 0; i < 16; ++i) own[i * RCH] = HNONE;
+                for (int i = 0; i < 16; ++i) own[i * RS] = HNONE;
             }
 
             // 2. minimum over the n_full whole chunks in front of mine: prefix / suffix minima inside blocks of B lanes
@@ -300,7 +302,7 @@ __global__ void __launch_bounds__(32 * SYNC_SCAN_WARPS) scan_kernel(ScanArgs A, 
                     const uint32_t lmask = __shfl_sync(SG_FULL, mC | mO << 16, src);
                     const int fc = small_q ? 0x7fffffff : ((n_full > 0 ? lch - n_full : lch) << 4);
                     const int li = lane & 15;
-                    const uint32_t h = ring[li * RCH + (lch & RM)];
+                    const uint32_t h = ring[li * RS + (lch & RM)];
                     uint32_t Rin = h;                      // inclusive prefix minimum inside each half warp
 #pragma unroll
                     for (int d = 1; d < 16; d <<= 1) { const uint32_t t = __shfl_up_sync(SG_FULL, Rin, d, 16); if (li >= d) Rin = min(Rin, t); }
@@ -376,7 +378,7 @@ int scan_geometry(int k, int s, ScanGeom *g, size_t *smem_per_warp)
     int rch = 64;
     while (rch < need) rch <<= 1;
     g->rch = rch; g->n_full = n_full; g->logB = logB; g->h31 = h31_consts();
-    *smem_per_warp = sizeof(uint32_t) * ((size_t) 18 * rch + 2 * LISTCAP + 64);
+    *smem_per_warp = sizeof(uint32_t) * ((size_t) 16 * (rch + 2) + 2 * rch + 2 * LISTCAP + 64);
     return *smem_per_warp <= 227 * 1024 ? 0 : SG_E_KSIZE;
 }
 
