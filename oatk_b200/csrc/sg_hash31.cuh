@@ -8,16 +8,17 @@
 //
 // Cost model measured on B200 (tools/microbench/int_pipes.cu): LOP3/SHF/ISETP/SEL/VIMNMX issue at
 // 0.5 warp-instructions per clock per SM sub-partition on the ALU pipe, IMAD at 0.5 on the FMA pipe
-// (concurrently with the ALU pipe), IMAD.WIDE and IMAD.HI at 0.25. The instruction selection below
-// splits the work ~40 ALU cycles / ~36 FMA cycles per position: the high-word right shifts of the
-// three xor-shifts run as IMAD.HI by a power of two held in a register (kernel parameter, so ptxas
-// cannot turn it back into a shift).
+// (concurrently with the ALU pipe); IMAD.WIDE and IMAD.HI run at 0.25 AND take an ALU slot each
+// ("3 LOP3 + 1 IMAD.HI" sustains 0.46, not 0.67). The ALU pipe is what bounds this code, so the
+// selection below minimises ALU slots: three IMAD.WIDE + IMAD for the multiplications, plain shifts
+// for the xor-shifts, one 32-bit compare for the strand (see h31_canon).
 #pragma once
 #include <stdint.h>
 
 namespace sg {
 
 // 2^(32-24), 2^(32-14), 2^(32-28): multipliers that turn "x >> n" into the high word of a product
+// (kept for the microbenchmarks that compare both instruction selections)
 struct H31Consts { uint32_t p8, p18, p4; };
 __host__ __device__ inline H31Consts h31_consts() { return H31Consts{1u << 8, 1u << 18, 1u << 4}; }
 
@@ -36,7 +37,12 @@ __device__ __forceinline__ void h31_mul(uint32_t &hi, uint32_t &lo, uint32_t c, 
 template <int N>
 __device__ __forceinline__ void h31_xorshift(uint32_t &hi, uint32_t &lo, uint32_t pw)
 {
-    const uint32_t t = __umulhi(hi, pw);                       // hi >> N on the FMA pipe
+#ifdef SG_H31_FMA_SHIFTS
+    const uint32_t t = __umulhi(hi, pw);                       // hi >> N on the FMA pipe (costs an ALU slot as well)
+#else
+    (void) pw;
+    const uint32_t t = hi >> N;
+#endif
     const uint32_t u = __funnelshift_r(lo, hi, N);
     lo ^= u & 0xfffffffcu;
     hi ^= t;
@@ -71,7 +77,9 @@ __device__ __forceinline__ uint64_t h31_hash_full(uint32_t hi, uint32_t lo)
 // Canonical 31-mer ending at position J (0..15) of the sixteen bases of word w0; a, b are the two
 // words before it (32 bases), ra/rb/rc the reverse-complement words of w0/b/a. All words hold their
 // first base in bits 31:30. Returns the smaller strand left-aligned in (hi:lo), low two bits clear.
-// A 31-mer cannot equal its reverse complement (odd length), so the strands never tie.
+// The middle base of a 31-mer pairs with itself under reverse complement and comp(x) != x, and that
+// base lies among the top 16 bases of both strands: the HIGH WORDS of the two strands always differ,
+// so one 32-bit compare orders them exactly.
 template <int J>
 __device__ __forceinline__ void h31_canon(uint32_t a, uint32_t b, uint32_t w0, uint32_t ra, uint32_t rb, uint32_t rc,
         uint32_t &hi, uint32_t &lo)
@@ -82,9 +90,8 @@ __device__ __forceinline__ void h31_canon(uint32_t a, uint32_t b, uint32_t w0, u
     else { fh = h31_shf_l(w0, b, 2); fl = w0 << 2; }
     const uint32_t rh = J == 15 ? ra : h31_shf_l(rb, ra, 30 - 2 * J);
     const uint32_t rl = J == 15 ? rb : h31_shf_l(rc, rb, 30 - 2 * J);
-    // the two junk bits below the 62 compared ones cannot decide the order: the strands differ above them
-    const bool lt = ((uint64_t) fh << 32 | fl) < ((uint64_t) rh << 32 | rl);
-    hi = lt ? fh : rh;
+    const bool lt = fh < rh;
+    hi = min(fh, rh);
     lo = (lt ? fl : rl) & 0xfffffffcu;
 }
 
@@ -98,7 +105,7 @@ __device__ __forceinline__ void h31_canon_rt(int j, uint32_t a, uint32_t b, uint
     const uint32_t fh = h31_shf_l(x1, x0, n & 31u), fl = h31_shf_l(x2, x1, n & 31u);
     const uint32_t m = 30u - 2u * j;                           // 30..0
     const uint32_t rh = h31_shf_l(rb, ra, m), rl = h31_shf_l(rc, rb, m);
-    const bool lt = ((uint64_t) fh << 32 | (fl & 0xfffffffcu)) < ((uint64_t) rh << 32 | (rl & 0xfffffffcu));
+    const bool lt = fh < rh;
     hi = lt ? fh : rh;
     lo = (lt ? fl : rl) & 0xfffffffcu;
 }

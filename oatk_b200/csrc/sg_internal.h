@@ -35,7 +35,7 @@ struct ScanArgs {
     uint32_t *rec_sid, *rec_idx, *rec_mpos;   // unordered records (one per syncmer)
     uint64_t *rec_smer;
 };
-constexpr int SYNC_SCAN_WARPS = 2;  // warps per CTA of the syncmer scan kernel (one read per warp, 16 positions per lane and tile)
+constexpr int SYNC_SCAN_WARPS = 4;  // warps per CTA of the syncmer scan kernel (one read per warp, 16 positions per lane and tile)
 struct ScanGeom {
     int rch;        // ring size in chunks of 16 positions (power of two, >= window + one tile)
     int n_full;     // chunks fully inside every window of a lane's 16 positions

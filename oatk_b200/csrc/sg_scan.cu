@@ -39,20 +39,21 @@
 
 namespace sg {
 
-constexpr uint32_t HNONE = 0xffffffffu;
+constexpr uint32_t HNONE = 0xffffffffu;  // "no hash" among chunk minima (32-bit)
+constexpr uint32_t KNONE = 0xffffu;      // "no hash" among the per-position keys (15 significant bits in 16)
 constexpr int LISTCAP = 64;            // queued chunks with emissions (a tile adds at most 32)
 
 // Exact decision for a candidate whose key ties with the window minimum: the full 62-bit hashes of
 // the tied positions are recomputed from the packed read and compared under the reference's rules.
 // Whole warp; rare, so it is kept out of line to keep the tile loop inside the instruction cache.
-__device__ __noinline__ bool settle_tie(const uint32_t *ring, int RCH, const uint32_t *hs32, int nwords, int s,
+__device__ __noinline__ bool settle_tie(const uint16_t *ring, int RCH, const uint32_t *hs32, int nwords, int s,
         int p, int q, bool is_open, uint32_t tgt, int lane)
 {
-    const int RM = RCH - 1, RS = RCH + 2;
+    const int RM = RCH - 1, RS = RCH + 4;
     const uint64_t mask = (1ull << (2 * s)) - 1;
     auto ring_at = [&](int x) -> uint32_t { return ring[(x & 15) * RS + ((x >> 4) & RM)]; };
     auto m64_at = [&](int x) -> uint64_t {
-        if (x < 0 || ring_at(x) == HNONE) return SG_NONE64;
+        if (x < 0 || ring_at(x) == KNONE) return SG_NONE64;
         return hash64(smer_code_at(hs32, x, s, nwords) >> 1, mask);
     };
     // positions whose key equals tgt are the only ones that can hold the window minimum; the key is a
@@ -70,15 +71,16 @@ __device__ __noinline__ bool settle_tie(const uint32_t *ring, int RCH, const uin
 }
 
 template <int S_FIXED, int RCH_FIXED, int LOGB_FIXED>
-__global__ void __launch_bounds__(32 * SYNC_SCAN_WARPS) scan_kernel(ScanArgs A, ScanGeom G)
+__global__ void __launch_bounds__(32 * SYNC_SCAN_WARPS, 8) scan_kernel(ScanArgs A, ScanGeom G)
 {
     extern __shared__ __align__(16) uint32_t smem[];
-    // ring rows are RCH + 2 words apart: a chunk's 16 positions (one column) and 32 consecutive positions
+    // ring rows are RCH + 4 keys apart: a chunk's 16 positions (one column) and 32 consecutive positions
     // (two columns) then fall into distinct banks, like the 32 chunks of a tile (one row)
-    const int RCH = RCH_FIXED ? RCH_FIXED : G.rch, RM = RCH - 1, RS = RCH + 2;
+    const int RCH = RCH_FIXED ? RCH_FIXED : G.rch, RM = RCH - 1, RS = RCH + 4;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    uint32_t *ring = smem + (size_t) wid * (16 * RS + 2 * RCH + 2 * LISTCAP + 64);   // [16][RS] keys of m[]
-    uint32_t *Lv0 = ring + 16 * RS;                    // [RCH] chunk minima
+    uint32_t *wbase = smem + (size_t) wid * (8 * RS + 2 * RCH + 2 * LISTCAP + 64);
+    uint16_t *ring = reinterpret_cast<uint16_t *>(wbase);   // [16][RS] 15-bit keys of m[]
+    uint32_t *Lv0 = wbase + 8 * RS;                    // [RCH] chunk minima (32-bit)
     uint32_t *sfxA = Lv0 + RCH;                        // [RCH] suffix minimum of the chunk's block from the chunk on
     uint32_t *list_c = sfxA + RCH;                     // [LISTCAP] chunk index
     uint32_t *list_e = list_c + LISTCAP;               // [LISTCAP] E | Om << 16
@@ -88,6 +90,10 @@ __global__ void __launch_bounds__(32 * SYNC_SCAN_WARPS) scan_kernel(ScanArgs A, 
     const uint64_t mask = (1ull << (2 * s)) - 1;
     const int rsh = 2 * s - 2;
     const bool small_q = q < 16;       // a thread's earlier positions fall out of the window: no running bound
+    // per-position keys: the top 15 bits of the hash (a monotone map, so "<" on keys implies "<" on hashes and
+    // equal keys go to the exact path); chunk minima keep 32 bits (s = 31) or the key itself (other s)
+    const int kshift = max(0, 2 * s - 15);
+    auto to_key = [&](uint32_t cm) -> uint32_t { return S_FIXED == 31 ? cm >> 17 : min(cm, 0x7fffu); };
     const int n_full = G.n_full, logB = LOGB_FIXED >= 0 ? LOGB_FIXED : G.logB, B = 1 << logB;
     // tile-invariant per lane: my place in my block of B chunks, and how many whole blocks lie between the
     // block that holds the first chunk of my window (c - n_full) and my own block
@@ -109,7 +115,7 @@ __global__ void __launch_bounds__(32 * SYNC_SCAN_WARPS) scan_kernel(ScanArgs A, 
         const int nwords = (H + 15) >> 4;
         const bool has_n = A.n_amb[r] != 0;
 
-        for (int i = lane; i < 16 * RS + 2 * RCH; i += 32) ring[i] = HNONE;      // ring, Lv0, sfxA
+        for (int i = lane; i < 8 * RS + 2 * RCH; i += 32) wbase[i] = HNONE;      // ring (all keys NONE), Lv0, sfxA
         __syncwarp();
 
         uint32_t n_emitted = 0, carryC = 0;
@@ -206,26 +212,27 @@ __global__ void __launch_bounds__(32 * SYNC_SCAN_WARPS) scan_kernel(ScanArgs A, 
 
             // 1. keys of my 16 positions
             uint32_t cmin = HNONE;
-            uint32_t *own = ring + cs;
+            uint16_t *own = ring + cs;
             if (vm && S_FIXED == 31) {
                 // s = 31: every position is extracted straight from the three words around it (no rolling
                 // dependency between positions) and hashed in the left-aligned frame of sg_hash31.cuh.
                 // An odd s-mer cannot be its own reverse complement.
                 const uint32_t ra = rev2(~w0), rb = rev2(~wb), rc = rev2(~wa);
                 if (vm == 0xffffu) {
-#define SG_H31_POS(J) { uint32_t hi, lo; h31_canon<J>(wa, wb, w0, ra, rb, rc, hi, lo); \
-                        const uint32_t hv = min(h31_hash_top(hi, lo, G.h31), 0xfffffffeu); own[(J) * RS] = hv; cmin = min(cmin, hv); }
-                    SG_H31_POS(0) SG_H31_POS(1) SG_H31_POS(2) SG_H31_POS(3) SG_H31_POS(4) SG_H31_POS(5) SG_H31_POS(6) SG_H31_POS(7)
-                    SG_H31_POS(8) SG_H31_POS(9) SG_H31_POS(10) SG_H31_POS(11) SG_H31_POS(12) SG_H31_POS(13) SG_H31_POS(14) SG_H31_POS(15)
-#undef SG_H31_POS
+#define SG_H31_PAIR(J) { uint32_t hi, lo, hi2, lo2; h31_canon<J>(wa, wb, w0, ra, rb, rc, hi, lo); h31_canon<(J) + 1>(wa, wb, w0, ra, rb, rc, hi2, lo2); \
+                        const uint32_t hv = h31_hash_top(hi, lo, G.h31), hv2 = h31_hash_top(hi2, lo2, G.h31); \
+                        own[(J) * RS] = (uint16_t) (hv >> 17); own[((J) + 1) * RS] = (uint16_t) (hv2 >> 17); cmin = min(cmin, min(hv, hv2)); }
+                    SG_H31_PAIR(0) SG_H31_PAIR(2) SG_H31_PAIR(4) SG_H31_PAIR(6) SG_H31_PAIR(8) SG_H31_PAIR(10) SG_H31_PAIR(12) SG_H31_PAIR(14)
+#undef SG_H31_PAIR
                 } else {
 #pragma unroll 1
                     for (int j = 0; j < 16; ++j) {
                         uint32_t hi, lo;
                         h31_canon_rt(j, wa, wb, w0, ra, rb, rc, hi, lo);
-                        const uint32_t hv = ((vm >> j) & 1u) ? min(h31_hash_top(hi, lo, G.h31), 0xfffffffeu) : HNONE;
-                        own[j * RS] = hv;
-                        cmin = min(cmin, hv);
+                        const bool ok = (vm >> j) & 1u;
+                        const uint32_t hv = h31_hash_top(hi, lo, G.h31);
+                        own[j * RS] = (uint16_t) (ok ? hv >> 17 : KNONE);
+                        if (ok) cmin = min(cmin, hv);
                     }
                 }
             } else if (vm) {
@@ -241,14 +248,13 @@ __global__ void __launch_bounds__(32 * SYNC_SCAN_WARPS) scan_kernel(ScanArgs A, 
                     rv = (rv >> 2) | ((uint64_t) (3u - b) << rsh);
                     const bool ok = (vmr & 1u) && fw != rv;
                     vmr >>= 1;
-                    const uint32_t h = (uint32_t) (hash64(fw < rv ? fw : rv, mask) >> 32);
-                    const uint32_t hv = ok ? h : HNONE;
-                    own[j * RS] = hv;
-                    cmin = min(cmin, hv);
+                    const uint32_t h = (uint32_t) (hash64(fw < rv ? fw : rv, mask) >> kshift);
+                    own[j * RS] = (uint16_t) (ok ? h : KNONE);
+                    if (ok) cmin = min(cmin, h);
                 }
             } else {
 #pragma unroll 4
-                for (int i = 0; i < 16; ++i) own[i * RS] = HNONE;
+                for (int i = 0; i < 16; ++i) own[i * RS] = (uint16_t) KNONE;
             }
 
             // 2. minimum over the n_full whole chunks in front of mine: prefix / suffix minima inside blocks of B lanes
@@ -298,7 +304,7 @@ __global__ void __launch_bounds__(32 * SYNC_SCAN_WARPS) scan_kernel(ScanArgs A, 
                     const int src = __ffs(any) - 1;
                     any &= any - 1;
                     const int lch = c - lane + src, lP = lch << 4;
-                    const uint32_t lr0 = small_q ? HNONE : __shfl_sync(SG_FULL, r0, src);
+                    const uint32_t lr0 = small_q ? KNONE : to_key(__shfl_sync(SG_FULL, r0, src));
                     const uint32_t lmask = __shfl_sync(SG_FULL, mC | mO << 16, src);
                     const int fc = small_q ? 0x7fffffff : ((n_full > 0 ? lch - n_full : lch) << 4);
                     const int li = lane & 15;
@@ -307,9 +313,9 @@ __global__ void __launch_bounds__(32 * SYNC_SCAN_WARPS) scan_kernel(ScanArgs A, 
 #pragma unroll
                     for (int d = 1; d < 16; d <<= 1) { const uint32_t t = __shfl_up_sync(SG_FULL, Rin, d, 16); if (li >= d) Rin = min(Rin, t); }
                     uint32_t Rex = __shfl_up_sync(SG_FULL, Rin, 1, 16);
-                    Rex = min(li == 0 ? HNONE : Rex, lr0); // r0 and the chunk's earlier positions
+                    Rex = min(li == 0 ? KNONE : Rex, lr0); // r0 and the chunk's earlier positions
                     const uint32_t mine = lane < 16 ? h : ring_at(lP + li - q);
-                    const bool cand = mine != HNONE && ((lmask >> lane) & 1u) && (small_q || mine <= Rex);
+                    const bool cand = mine != KNONE && ((lmask >> lane) & 1u) && (small_q || mine <= Rex);
                     uint32_t lc = __ballot_sync(SG_FULL, cand);
                     while (lc) {
                         const int bit = __ffs(lc) - 1;
@@ -318,7 +324,7 @@ __global__ void __launch_bounds__(32 * SYNC_SCAN_WARPS) scan_kernel(ScanArgs A, 
                         const bool is_open = bit >> 4;
                         // minimum of the keys over m[p-q+1 .. p-1]: Rex covers [fc, p), the rest is scanned
                         uint32_t m = __shfl_sync(SG_FULL, Rex, bit);
-                        if (small_q) m = HNONE;
+                        if (small_q) m = KNONE;
                         for (int x = p - q + 1 + lane; x < min(fc, p); x += 32) m = min(m, ring_at(x));
                         const uint32_t Mhi = __reduce_min_sync(SG_FULL, m);
                         const uint32_t tgt = __shfl_sync(SG_FULL, mine, bit);
@@ -378,7 +384,7 @@ int scan_geometry(int k, int s, ScanGeom *g, size_t *smem_per_warp)
     int rch = 64;
     while (rch < need) rch <<= 1;
     g->rch = rch; g->n_full = n_full; g->logB = logB; g->h31 = h31_consts();
-    *smem_per_warp = sizeof(uint32_t) * ((size_t) 16 * (rch + 2) + 2 * rch + 2 * LISTCAP + 64);
+    *smem_per_warp = sizeof(uint32_t) * ((size_t) 8 * (rch + 4) + 2 * rch + 2 * LISTCAP + 64);
     return *smem_per_warp <= 227 * 1024 ? 0 : SG_E_KSIZE;
 }
 

@@ -88,11 +88,12 @@ def test_large_k_and_the_window_limit(gpu_ctx, oracle):
     reads = [synth._rand(rng, 60000), synth._rand(rng, 9000), synth._rand(rng, 45000)]
     check(gpu_ctx, oracle, reads, 8001, 31)
     check(gpu_ctx, oracle, reads, 20001, 25)
+    check(gpu_ctx, oracle, reads, 40001, 31)      # one warp per CTA, ring of 4096 chunks
     b = lib.Batch(gpu_ctx)
     bases, off = pack_reads(reads)
     b.set_reads_host(bases, off)
     with pytest.raises(lib.SgError) as e:
-        b.extract(60001, 31)
+        b.extract(200001, 31)
     assert e.value.code == -5
 
 

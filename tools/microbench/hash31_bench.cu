@@ -1,4 +1,4 @@
-#if VARIANT == 10
+#if VARIANT >= 10
 #include "../../oatk_b200/csrc/sg_hash31.cuh"
 #else
 #include "hash31.cuh"
@@ -7,18 +7,22 @@
 #include <vector>
 using namespace sg;
 __device__ __forceinline__ uint32_t rev2(uint32_t x){ x = __brev(x); return ((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1); }
-#if VARIANT == 9
+#if VARIANT == 9 || VARIANT == 12
 __device__ __forceinline__ uint64_t hash64(uint64_t x, uint64_t mask)
 {
     x = ((x << 21) - x - 1) & mask; x ^= x >> 24; x = (x * 265) & mask; x ^= x >> 14; x = (x * 21) & mask; x ^= x >> 28; x = (x + (x << 31)) & mask; return x;
 }
 #endif
-#if VARIANT == 10
+#if VARIANT >= 10
 template <int J> __device__ __forceinline__ void one(uint32_t a, uint32_t b, uint32_t w0, uint32_t ra, uint32_t rb, uint32_t rc, uint32_t *dst, int RCH, uint32_t &cmin, const H31Consts &K)
 {
     uint32_t hi, lo;
     h31_canon<J>(a, b, w0, ra, rb, rc, hi, lo);
+#if VARIANT == 12
+    uint32_t hv = (uint32_t) (hash64(((uint64_t) hi << 32 | lo) >> 2, (1ull << 62) - 1) >> 32);
+#else
     uint32_t hv = min(h31_hash_top(hi, lo, K), 0xfffffffeu);
+#endif
     dst[J * RCH] = hv; cmin = min(cmin, hv);
 }
 #else
@@ -33,11 +37,11 @@ template <int J> __device__ __forceinline__ void one(uint32_t a, uint32_t b, uin
 __global__ void __launch_bounds__(64) tk(const uint32_t *in, uint32_t *out, H31Consts K, int n)
 {
     __shared__ uint32_t ring[16 * 128]; __shared__ uint64_t s_m4; 
-#if VARIANT != 10
+#if VARIANT < 10
  if (threadIdx.x == 0) s_m4 = K.m4;
 #endif
  __syncthreads(); 
-#if VARIANT != 10
+#if VARIANT < 10
  K.m4 = *(volatile uint64_t *) &s_m4;
 #endif
 
@@ -46,7 +50,23 @@ __global__ void __launch_bounds__(64) tk(const uint32_t *in, uint32_t *out, H31C
         int c = ((it * 64 + threadIdx.x) & 1023) + 2;
         uint32_t a = __ldg(in + c - 2), b = __ldg(in + c - 1), w0 = __ldg(in + c);
         uint32_t *dst = ring + threadIdx.x + (it & 1) * 64; uint32_t cmin = 0xffffffffu;
-#if VARIANT == 9
+#if VARIANT == 11
+        {
+            uint64_t V = (uint64_t) a << 32 | b;
+            uint64_t fw = V << 2, rv = ((uint64_t) rev2(~(uint32_t) V) << 32 | rev2(~(uint32_t) (V >> 32))) & ~3ull;
+            for (int i4 = 0; i4 < 4; ++i4) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t bb = w0 >> 30; w0 <<= 2;
+                    fw = (fw << 2) | (bb << 2); rv = ((rv >> 2) & ~3ull) | ((uint64_t) (3u - bb) << 62);
+                    const uint64_t x = fw < rv ? fw : rv;
+                    const uint32_t hv = min(h31_hash_top((uint32_t) (x >> 32), (uint32_t) x, K), 0xfffffffeu);
+                    dst[j * 128] = hv; cmin = min(cmin, hv);
+                }
+                dst += 4 * 128;
+            }
+        }
+#elif VARIANT == 9
         const uint64_t mask = (1ull << 62) - 1;
         uint64_t V = (uint64_t) a << 32 | b;
         uint64_t fw = V & mask, rv = ((uint64_t) rev2(~(uint32_t) V) << 32 | rev2(~(uint32_t) (V >> 32))) >> 2;
@@ -79,7 +99,7 @@ int main()
     cudaMalloc(&in, 4096 * 4); cudaMalloc(&out, (size_t) nblk * 64 * 4);
     std::vector<uint32_t> h(4096); uint32_t x = 12345; for (auto &v : h) { x = x * 1664525u + 1013904223u; v = x; }
     cudaMemcpy(in, h.data(), 4096 * 4, cudaMemcpyHostToDevice);
-#if VARIANT == 10
+#if VARIANT >= 10
     H31Consts K = h31_consts();
 #else
     H31Consts K = {1u << 8, 1u << 18, 1u << 4, 0, 0xfffffffffffffffcull};

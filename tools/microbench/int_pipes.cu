@@ -30,6 +30,11 @@ __global__ void __launch_bounds__(256) k(uint32_t *out, uint32_t p, uint32_t q)
                 if (OP == 9) { asm volatile("{.reg .pred pp; setp.lt.u32 pp, %0, %1; selp.u32 %0, %1, %2, pp;}" : "+r"(x[i]) : "r"(y[i]), "r"(p)); asm volatile("{.reg .pred pp; setp.lt.u32 pp, %0, %1; selp.u32 %0, %1, %2, pp;}" : "+r"(y[i]) : "r"(x[i]), "r"(q)); }
                 if (OP == 10) { asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[i]) : "r"(q), "r"(p)); asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(y[i]) : "r"(q), "r"(p)); }
                 if (OP == 11) { float fx = __uint_as_float(x[i]), fy = __uint_as_float(y[i]); asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(fx) : "f"(1.0001f), "f"(0.5f)); asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(fy) : "f"(0.9999f), "f"(0.25f)); x[i] = __float_as_uint(fx); y[i] = __float_as_uint(fy); }
+                if (OP == 13) { asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[i]) : "r"(q), "r"(p)); asm volatile("lop3.b32 %0, %0, %1, %2, 0x78;" : "+r"(x[i]) : "r"(p), "r"(q)); asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[i]) : "r"(q), "r"(p)); asm volatile("mul.hi.u32 %0, %0, %1;" : "+r"(y[i]) : "r"(q)); }
+                if (OP == 14) { uint64_t w; asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[i]) : "r"(q), "r"(p)); asm volatile("lop3.b32 %0, %0, %1, %2, 0x78;" : "+r"(x[i]) : "r"(p), "r"(q)); asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[i]) : "r"(q), "r"(p)); asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(w) : "r"(y[i]), "r"(q)); y[i] = (uint32_t) (w >> 32); }
+                if (OP == 15) { asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[i]) : "r"(q), "r"(p)); asm volatile("lop3.b32 %0, %0, %1, %2, 0x78;" : "+r"(x[i]) : "r"(p), "r"(q)); asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(y[i]) : "r"(q), "r"(p)); asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(y[i]) : "r"(p), "r"(q)); }
+                if (OP == 16) { asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[i]) : "r"(q), "r"(p)); asm volatile("lop3.b32 %0, %0, %1, %2, 0x78;" : "+r"(x[i]) : "r"(p), "r"(q)); asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[i]) : "r"(q), "r"(p)); asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(y[i]) : "r"(q), "r"(p)); }
+                if (OP == 17) { asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[i]) : "r"(y[i]), "r"(p)); asm volatile("shf.r.clamp.b32 %0, %0, %1, 7;" : "+r"(y[i]) : "r"(x[i])); asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[i]) : "r"(y[i]), "r"(p)); asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(y[i]) : "r"(q), "r"(x[i])); }
                 if (OP == 12) { float fy = __uint_as_float(y[i]); asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[i]) : "r"(q), "r"(p)); asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(fy) : "f"(0.9999f), "f"(0.25f)); y[i] = __float_as_uint(fy); }
             }
         }
@@ -58,6 +63,7 @@ int main()
     run<0>("SHF", out, 2); run<1>("LOP3", out, 2); run<7>("IADD", out, 2); run<8>("VIMNMX", out, 2); run<9>("ISETP+SEL", out, 4);
     run<2>("IMAD", out, 2); run<3>("IMAD.HI", out, 2); run<4>("IMAD.WIDE (+LOP3)", out, 4);
     run<5>("SHF + IMAD", out, 2); run<10>("LOP3 + IMAD", out, 2); run<6>("LOP3 + IMAD.HI", out, 2);
+    run<13>("3 LOP3 + 1 IMAD.HI", out, 4); run<14>("3 LOP3 + 1 IMAD.WIDE", out, 4); run<15>("2 LOP3 + 2 IMAD", out, 4); run<16>("3 LOP3 + 1 IMAD", out, 4); run<17>("LOP3 SHF LOP3 IMAD dependent regs", out, 4);
     run<11>("FFMA", out, 2); run<12>("LOP3 + FFMA", out, 2);
     printf("err %d\n", (int) cudaGetLastError());
     return 0;
