@@ -193,7 +193,10 @@ def main():
     ap.add_argument("--reads", type=int, default=1000000, help="reads per GPU (default: the configs[1] workload)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--k", type=int, default=K, help="k-mer size (configs[4] sweep: 501, 1001, 2001)")
+    ap.add_argument("--err", type=float, default=ERR, help="per-base error rate of the synthetic reads")
     args = ap.parse_args()
+    globals()["K"], globals()["ERR"] = args.k, args.err
     if args.impl == "reference":
         return run_reference(args)
 
