@@ -202,6 +202,11 @@ int sg_batch_buffer(sg_batch *b, int which, void **d_ptr, uint64_t *n);
 /* test hook: keep only the low `bits` bits of every k-mer hash when grouping, which forces hash
  * collisions so that the exact-sequence split of process_kmer_cluster is exercised. 64 = off. */
 int sg_debug_set_hash_bits(sg_batch *b, int bits);
+/* tests only: the sort of sg_count/sg_stat runs radix passes over hash bits [low_bits, 64) and repairs the
+ * rare runs that differ below (default 24; 0 = sort on all 64 bits). sg_debug_sort_info reports how many
+ * out-of-order pairs the last sort repaired and whether it fell back to the full sort. */
+int sg_debug_set_sort_low_bits(sg_batch *b, int low_bits);
+int sg_debug_sort_info(sg_batch *b, uint64_t *repairs, int *fell_back);
 
 /* ---- multi-GPU exchange (one process per GPU; the transport is the caller's
  * collective, e.g. NCCL all-to-all; see oatk_b200/dist.py) ---- */

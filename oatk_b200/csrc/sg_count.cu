@@ -34,6 +34,57 @@ __global__ void __launch_bounds__(256) tuple_init_kernel(const uint64_t *key, ui
     if (i < n) { skey[i] = key[i] & hmask; sval[i] = i; }
 }
 
+// ---- partial sort + repair ------------------------------------------------------------------
+// The k-mer hashes are uniform 64-bit values, so five radix passes over bits 24..63 already put almost
+// every tuple in its final place: what is left are the few runs that agree on those 40 bits and differ
+// below (expected N^2 / 2^41 pairs, a few hundred at 21 M tuples). sort_detect_kernel lists the adjacent
+// pairs that are out of order inside such a run, sort_repair_kernel insertion-sorts each listed run once
+// (stable: strict comparisons, and the radix passes kept the input order inside a run). Anything the
+// small fixed buffers cannot hold is reported, and the caller then sorts on all 64 bits instead.
+constexpr uint32_t SORT_FIX_CAP = 8192;       // listed pairs
+constexpr uint64_t SORT_FIX_MAXRUN = 4096;    // longest run a single thread is allowed to repair
+
+__global__ void __launch_bounds__(256) sort_detect_kernel(const uint64_t *k, uint64_t n, int SORT_LOW_BITS, uint32_t *fix /* [0] count, [1] overflow, [2..] positions */)
+{
+    const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i + 1 >= n) return;
+    const uint64_t a = k[i], b = k[i + 1];
+    if ((a >> SORT_LOW_BITS) == (b >> SORT_LOW_BITS) && a > b) {
+        const uint32_t o = atomicAdd(&fix[0], 1u);
+        if (o < SORT_FIX_CAP) fix[2 + o] = (uint32_t) i; else fix[1] = 1u;
+    }
+}
+
+__global__ void __launch_bounds__(128) sort_repair_kernel(uint64_t *k, uint64_t *v, uint64_t n, int SORT_LOW_BITS, uint32_t *fix)
+{
+    const uint32_t cnt = min(fix[0], SORT_FIX_CAP);
+    for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < cnt; e += gridDim.x * blockDim.x) {
+        const uint64_t i = fix[2 + e];
+        const uint64_t top = k[i] >> SORT_LOW_BITS;
+        // walk to the start of the run; the run belongs to its FIRST out-of-order pair
+        uint64_t s0 = i;
+        bool owner = true;
+        while (s0 > 0 && (k[s0 - 1] >> SORT_LOW_BITS) == top) {
+            if (k[s0 - 1] > k[s0]) { owner = false; break; }
+            --s0;
+            if (i - s0 > SORT_FIX_MAXRUN) { fix[1] = 1u; owner = false; break; }
+        }
+        if (!owner) continue;
+        uint64_t s1 = i + 1;
+        while (s1 + 1 < n && (k[s1 + 1] >> SORT_LOW_BITS) == top) {
+            ++s1;
+            if (s1 - s0 > SORT_FIX_MAXRUN) { fix[1] = 1u; owner = false; break; }
+        }
+        if (!owner) continue;
+        for (uint64_t a = s0 + 1; a <= s1; ++a) {          // stable insertion sort of [s0, s1]
+            const uint64_t kk = k[a], vv = v[a];
+            uint64_t b = a;
+            while (b > s0 && k[b - 1] > kk) { k[b] = k[b - 1]; v[b] = v[b - 1]; --b; }
+            k[b] = kk; v[b] = vv;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) tuple_gather_kernel(const uint64_t *sval, const uint64_t *occ, const uint64_t *smer, const uint64_t *fp,
         uint64_t *socc, uint64_t *ssmer, uint64_t *sfp, uint64_t n)
 {
@@ -303,10 +354,28 @@ static int ensure_sorted(sg_batch *b)
     RS(b->socc, (N + 1) * 8); RS(b->ssmer, (N + 1) * 8); RS(b->sfp, (N + 1) * 8);
     ctx->t_begin(SG_T_SORT);
     const uint64_t hmask = b->hash_bits >= 64 ? ~0ull : ((1ull << b->hash_bits) - 1);
-    tuple_init_kernel<<<nblk(N, 256), 256, 0, st>>>(b->t_key(), (uint64_t *) b->skey.p, (uint64_t *) b->sval.p, N, hmask);
-    ctx->count_launch(SG_T_SORT, 1);
-    LAUNCHED(SG_T_SORT, launch_sort_pairs((uint64_t *) b->skey.p, (uint64_t *) b->sval.p, (uint64_t *) b->skey_alt.p,
-            (uint64_t *) b->sval_alt.p, N, 0, b->hash_bits >= 64 ? 64 : ((b->hash_bits + 7) & ~7), (uint32_t *) b->sort_tmp.p, st));
+    RS(b->sort_fix, (SORT_FIX_CAP + 2) * 4);
+    const int SORT_LOW_BITS = b->sort_low_bits;              // 24 unless a test moves it (multiple of 8)
+    bool full = b->hash_bits < 64 || SORT_LOW_BITS == 0;     // truncated hashes (tests) collide by design
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        tuple_init_kernel<<<nblk(N, 256), 256, 0, st>>>(b->t_key(), (uint64_t *) b->skey.p, (uint64_t *) b->sval.p, N, hmask);
+        ctx->count_launch(SG_T_SORT, 1);
+        LAUNCHED(SG_T_SORT, launch_sort_pairs((uint64_t *) b->skey.p, (uint64_t *) b->sval.p, (uint64_t *) b->skey_alt.p,
+                (uint64_t *) b->sval_alt.p, N, full ? 0 : SORT_LOW_BITS, b->hash_bits >= 64 ? 64 : ((b->hash_bits + 7) & ~7), (uint32_t *) b->sort_tmp.p, st));
+        if (full) break;
+        CK(cudaMemsetAsync(b->sort_fix.p, 0, 8, st));
+        sort_detect_kernel<<<nblk(N, 256), 256, 0, st>>>((const uint64_t *) b->skey.p, N, SORT_LOW_BITS, (uint32_t *) b->sort_fix.p);
+        sort_repair_kernel<<<8, 128, 0, st>>>((uint64_t *) b->skey.p, (uint64_t *) b->sval.p, N, SORT_LOW_BITS, (uint32_t *) b->sort_fix.p);
+        ctx->count_launch(SG_T_SORT, 2);
+        uint32_t hf[2];
+        CK(cudaMemcpyAsync(hf, b->sort_fix.p, sizeof(hf), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        b->n_sort_repairs = hf[0];
+        b->sort_fell_back = false;
+        if (hf[1] == 0 && hf[0] <= SORT_FIX_CAP) break;
+        b->sort_fell_back = true;
+        full = true;                                          // too many or too long runs: sort on all 64 bits
+    }
     tuple_gather_kernel<<<nblk(N, 256), 256, 0, st>>>((const uint64_t *) b->sval.p, b->t_occ(),
             b->t_smer(), b->t_fp(), (uint64_t *) b->socc.p, (uint64_t *) b->ssmer.p, (uint64_t *) b->sfp.p, N);
     ctx->count_launch(SG_T_SORT, 1);
@@ -345,6 +414,22 @@ int sg_batch_set_exact_verify(sg_batch *b, int on)
     if (!b) return SG_E_ARG;
     b->exact_verify = on != 0;
     b->counted = false;
+    return SG_OK;
+}
+
+int sg_debug_set_sort_low_bits(sg_batch *b, int bits)
+{
+    if (!b || bits < 0 || bits > 56 || (bits & 7)) return SG_E_ARG;
+    b->sort_low_bits = bits;
+    b->sorted = b->counted = false;
+    return SG_OK;
+}
+
+int sg_debug_sort_info(sg_batch *b, uint64_t *repairs, int *fell_back)
+{
+    if (!b) return SG_E_ARG;
+    if (repairs) *repairs = b->n_sort_repairs;
+    if (fell_back) *fell_back = b->sort_fell_back ? 1 : 0;
     return SG_OK;
 }
 

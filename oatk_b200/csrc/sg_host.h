@@ -56,7 +56,10 @@ struct sg_batch {
     std::vector<uint64_t> h_hs_off, h_rl_off, h_scm_off;
     // a5/a6 device results
     sg::DevBuf kid;                              // read order: id << 1
-    sg::DevBuf skey, sval, skey_alt, sval_alt, sort_tmp;
+    sg::DevBuf skey, sval, skey_alt, sval_alt, sort_tmp, sort_fix;
+    int sort_low_bits = 24;                      // radix passes skip these low hash bits, a repair pass handles them (0: full sort)
+    bool sort_fell_back = false;
+    uint64_t n_sort_repairs = 0;                 // out-of-order pairs the repair pass saw
     sg::DevBuf socc, ssmer, flags, ids, ids_tmp, differs, cls, starts, stat_dev, stat_dev2, skey2, sval2;
     bool sorted = false;
     bool exact_verify = false;                   // sg_batch_set_exact_verify: compare packed k-mers instead of fingerprints

@@ -106,3 +106,27 @@ def test_count_empty(gpu_ctx):
     with pytest.raises(lib.SgError) as e:
         b.count()
     assert e.value.code == -7
+
+
+@pytest.mark.parametrize("low_bits,expect", [(24, "repair-or-clean"), (48, "repair"), (56, "fallback"), (0, "full")])
+def test_partial_sort_and_repair(gpu_ctx, oracle, low_bits, expect):
+    """sg_count sorts on the top 64 - low_bits hash bits and repairs the runs that differ below; moving the split
+    makes the repair pass (and, past its buffers, the fall-back to the full sort) do real work"""
+    from oatk_b200 import lib
+    reads = synth.hifi_reads(11, 100000, 300, 15000, 0.001) + synth.adversarial_reads(5, 101, 11)
+    bases, off = pack_reads(reads)
+    db, _ = oracle.extract(bases, off, 101, 11)
+    exp = oracle.collect(db, len(reads), 64)
+    b = gpu_batch(gpu_ctx, bases, off, 101, 11)
+    b.debug_set_sort_low_bits(low_bits)
+    b.count()
+    got = b.count_download()
+    repairs, fell_back = b.debug_sort_info()
+    d = parity.diff(got, exp, parity.SCM_FIELDS)
+    assert not d, "\n".join(d)
+    if expect == "repair":
+        assert repairs > 0 and not fell_back
+    elif expect == "fallback":
+        assert fell_back
+    oracle.free(db, exp)
+    b.close()
