@@ -1,0 +1,367 @@
+/*
+ * consensus_gpu.c -- row f1 of SURVEY.md section 8: unitig sequences and the GFA text.
+ *
+ * What the reference computes (syncasm.c:477-582 calc_syncmer_overlap, :888-1001
+ * scg_syncmer_consensus, :1004-1046 scg_unitig_consensus, :630-670 utg_avg_cov,
+ * :716-823 scg_consensus), restated from its behaviour:
+ *
+ *   offset(m1, m2)  For two syncmers that follow each other on a unitig: over all reads that
+ *                   carry both as NEIGHBOURS in the right relative orientation, the difference
+ *                   of their hoco start positions; the most frequent value wins. Ties go to the
+ *                   value met first when the reference walks its khashl table in slot order, and
+ *                   that table keeps its capacity while one unitig is processed -- so the table
+ *                   below reproduces khashl 0.1's bucket function, probing, growth rule and its
+ *                   in-place kick-out rehash.
+ *   bases(m, from)  hoco bases [from, k) of a syncmer from its first occurrence that was not
+ *                   error-corrected; every hoco base is written 1 + lround(mean run length - 1)
+ *                   times, the mean taken over all such occurrences (0..255 from ho_rl, longer
+ *                   runs from the ho_l_rl side list). A negative `from` pads with N.
+ *   unitig          offsets accumulate into positions; a syncmer that starts before the end of
+ *                   what is already written is skipped unless it is the last one that does.
+ *   coverage        mean of the single-copy syncmers' coverages inside [Q1-1.5 IQR, Q3+1.5 IQR]
+ *                   (all syncmers when none is single copy).
+ *   GFA             H line, one S line per unitig (LN, KC = (int64)(len*cov), SC %.3f), two L
+ *                   lines per arc with the overlap in bases and EC = arc coverage.
+ *
+ * Everything here runs on the host over the caller's sr_db_t / scg_t (the structs of
+ * syncmer_gpu.h / graph_gpu.h): graphs after the coverage filter hold a few 10^4 syncmers.
+ */
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+#include <float.h>
+#include <assert.h>
+#include "graph_gpu.h"
+
+/* test probes: how often the offset vote was decided by slot order, and how often a vote table grew past
+ * its first four buckets (tests/test_consensus_cpu.py makes sure both paths are exercised) */
+static uint64_t dbg_vote_ties, dbg_table_growths;
+void oatk_consensus_debug_counts(uint64_t *out) { out[0] = dbg_vote_ties; out[1] = dbg_table_growths; }
+
+/* ---------------------------------------------------------------- int -> count, khashl slot order */
+typedef struct { int key, val; } ovl_cell_t;
+typedef struct {
+    uint32_t bits, count;
+    uint32_t *used;            /* one bit per bucket */
+    ovl_cell_t *cell;          /* NULL until the first insertion */
+} ovl_tab_t;
+
+static inline uint32_t ot_words(uint32_t n_buckets) { return n_buckets < 32 ? 1 : n_buckets >> 5; }
+static inline int ot_used(const uint32_t *u, uint32_t i) { return (u[i >> 5] >> (i & 31)) & 1u; }
+static inline void ot_set(uint32_t *u, uint32_t i) { u[i >> 5] |= 1u << (i & 31); }
+static inline void ot_unset(uint32_t *u, uint32_t i) { u[i >> 5] &= ~(1u << (i & 31)); }
+/* khashl.h:82 with the identity hash the reference gives this map (syncasm.c:63) */
+static inline uint32_t ot_bucket(int key, uint32_t bits) { return (uint32_t) key * 2654435769u >> (32 - bits); }
+
+static void ot_clear(ovl_tab_t *t)
+{
+    if (t->used) { memset(t->used, 0, ot_words(1u << t->bits) * sizeof(uint32_t)); t->count = 0; }
+}
+
+static void ot_free(ovl_tab_t *t) { free(t->used); free(t->cell); memset(t, 0, sizeof(*t)); }
+
+/* growth to the next power of two >= want (at least 4), moving the cells inside the same array the
+ * way khashl does it (khashl.h:144-187): walk the old buckets in order, drop each cell at its new
+ * home and carry on with whatever old cell was sitting there */
+static void ot_grow(ovl_tab_t *t, uint32_t want)
+{
+    uint32_t j = 0, x = want, old_n = t->cell ? 1u << t->bits : 0u, new_bits, new_n, mask;
+    while ((x >>= 1) != 0) ++j;
+    if (want & (want - 1)) ++j;
+    new_bits = j > 2 ? j : 2;
+    new_n = 1u << new_bits;
+    if (t->count > (new_n >> 1) + (new_n >> 2)) return;
+    if (old_n) ++dbg_table_growths;
+    uint32_t *nu = (uint32_t *) calloc(ot_words(new_n), sizeof(uint32_t));
+    if (old_n < new_n) t->cell = (ovl_cell_t *) realloc(t->cell, new_n * sizeof(ovl_cell_t));
+    mask = new_n - 1;
+    for (j = 0; j != old_n; ++j) {
+        if (!ot_used(t->used, j)) continue;
+        ovl_cell_t c = t->cell[j];
+        ot_unset(t->used, j);
+        for (;;) {
+            uint32_t i = ot_bucket(c.key, new_bits);
+            while (ot_used(nu, i)) i = (i + 1) & mask;
+            ot_set(nu, i);
+            if (i < old_n && ot_used(t->used, i)) {
+                ovl_cell_t tmp = t->cell[i]; t->cell[i] = c; c = tmp;
+                ot_unset(t->used, i);
+            } else { t->cell[i] = c; break; }
+        }
+    }
+    if (old_n > new_n) t->cell = (ovl_cell_t *) realloc(t->cell, new_n * sizeof(ovl_cell_t));
+    free(t->used);
+    t->used = nu; t->bits = new_bits;
+}
+
+static void ot_count(ovl_tab_t *t, int key)
+{
+    uint32_t n = t->cell ? 1u << t->bits : 0u;
+    if (t->count >= (n >> 1) + (n >> 2)) { ot_grow(t, n + 1); n = 1u << t->bits; }
+    const uint32_t mask = n - 1;
+    uint32_t i = ot_bucket(key, t->bits), first = i;
+    while (ot_used(t->used, i) && t->cell[i].key != key) { i = (i + 1) & mask; if (i == first) break; }
+    if (!ot_used(t->used, i)) { t->cell[i].key = key; t->cell[i].val = 1; ot_set(t->used, i); ++t->count; }
+    else ++t->cell[i].val;
+}
+
+/* the value with the highest count; among equals the first in slot order */
+static int ot_mode(const ovl_tab_t *t)
+{
+    int best = 0, best_n = 0, tied = 0;
+    if (!t->cell) return 0;
+    for (uint32_t i = 0, n = 1u << t->bits; i < n; ++i) {
+        if (!ot_used(t->used, i)) continue;
+        if (t->cell[i].val > best_n) { best_n = t->cell[i].val; best = t->cell[i].key; tied = 0; }
+        else if (t->cell[i].val == best_n) tied = 1;
+    }
+    dbg_vote_ties += tied;
+    return best;
+}
+
+/* ---------------------------------------------------------------- distance between two neighbours */
+static inline int occ_is_corrected(const sr_db_t *db, uint64_t occ)
+{
+    return (int) (db->a[occ >> 32].k_mer[occ >> 1 & MAX_RD_SCM] & 1);
+}
+static inline int64_t occ_start(const sr_db_t *db, uint64_t occ)
+{
+    return (int64_t) (db->a[occ >> 32].m_pos[occ >> 1 & MAX_RD_SCM] >> 1);
+}
+
+/* m1 (strand rc1) is followed by m2 (strand rc2): hoco distance between their starts */
+static int neighbour_offset(const sr_db_t *db, const syncmer_t *m1, uint64_t rc1, const syncmer_t *m2, uint64_t rc2, ovl_tab_t *shared)
+{
+    ovl_tab_t local = {0, 0, 0, 0}, *t = shared ? shared : &local;
+    const uint64_t *o1 = m1->m_pos, *o2 = m2->m_pos;
+    const uint64_t n1 = m1->cov, n2 = m2->cov;
+    assert(n1 > 0 && n2 > 0);
+    ot_clear(t);
+    uint64_t j0 = 0;                                  /* first occurrence of m2 on a read >= the current one */
+    for (uint64_t a = 0; a < n1; ++a) {
+        const uint64_t read = o1[a] >> 32, i1 = o1[a] >> 1 & MAX_RD_SCM, s1 = o1[a] & 1;
+        if (occ_is_corrected(db, o1[a])) continue;
+        while (j0 < n2 && (o2[j0] >> 32) < read) ++j0;
+        for (uint64_t b = j0; b < n2 && (o2[b] >> 32) == read; ++b) {
+            const uint64_t i2 = o2[b] >> 1 & MAX_RD_SCM, s2 = o2[b] & 1;
+            if (occ_is_corrected(db, o2[b])) continue;
+            /* read walks the pair forwards (m2 right after m1, both on the asked strands) or backwards */
+            if (i1 == i2 + 1 && s1 != rc1 && s2 != rc2) ot_count(t, (int) (occ_start(db, o1[a]) - occ_start(db, o2[b])));
+            else if (i1 + 1 == i2 && s1 == rc1 && s2 == rc2) ot_count(t, (int) (occ_start(db, o2[b]) - occ_start(db, o1[a])));
+        }
+    }
+    const int d = ot_mode(t);
+    if (!shared) ot_free(&local);
+    return d;
+}
+
+/* ---------------------------------------------------------------- growing text buffer */
+typedef struct { size_t l, m; char *s; } txt_t;
+static inline void txt_put(txt_t *t, int c)
+{
+    if (t->l + 1 > t->m) { t->m = t->m ? t->m << 1 : 256; t->s = (char *) realloc(t->s, t->m); }
+    t->s[t->l++] = (char) c;
+}
+
+/* ---------------------------------------------------------------- bases of one syncmer */
+static int64_t syncmer_text(const sr_db_t *db, const syncmer_t *m, int rev, int64_t from, txt_t *out, int hoco_only)
+{
+    const int w = db->k;
+    assert(from < w);
+    int64_t written = from < 0 ? -from : 0;
+    for (; from < 0; ++from) txt_put(out, 'N');
+    const uint64_t l = (uint64_t) (w - from);
+    written += (int64_t) l;
+
+    /* the first occurrence that read error correction left alone supplies the bases */
+    uint32_t i;
+    const sr_t *s = 0;
+    uint64_t p = 0, r = 0;
+    for (i = 0; i < m->cov; ++i) {
+        if (occ_is_corrected(db, m->m_pos[i])) continue;
+        s = &db->a[m->m_pos[i] >> 32];
+        p = s->m_pos[m->m_pos[i] >> 1 & MAX_RD_SCM];
+        r = (p & 1) ^ (uint64_t) rev;
+        p >>= 1;
+        break;
+    }
+    if (i == m->cov) {                                 /* every copy was corrected away: N (reference :925-931) */
+        for (uint64_t j = 0; j < l; ++j) txt_put(out, 'N');
+        return written;
+    }
+    if (!r) p += (uint64_t) from;
+    uint8_t *code = (uint8_t *) malloc(l);
+    get_kmer_seq(s->hoco_s, (uint32_t) p, (int) l, (uint32_t) r, code);
+    if (hoco_only) {
+        for (uint64_t j = 0; j < l; ++j) txt_put(out, char_nt4_table[code[j]]);
+        free(code);
+        return written;
+    }
+    /* summed run lengths - 1 per hoco base over the uncorrected occurrences, in the syncmer's orientation */
+    uint64_t *tot = (uint64_t *) calloc(l, sizeof(uint64_t));
+    uint32_t copies = 0;
+    for (i = 0; i < m->cov; ++i) {
+        if (occ_is_corrected(db, m->m_pos[i])) continue;
+        const sr_t *t = &db->a[m->m_pos[i] >> 32];
+        uint64_t q = t->m_pos[m->m_pos[i] >> 1 & MAX_RD_SCM];
+        const uint64_t rr = (q & 1) ^ (uint64_t) rev;
+        q >>= 1;
+        if (!rr) q += (uint64_t) from;
+        uint32_t side = 0;                             /* entries of the long-run list in front of q */
+        if (t->ho_l_rl) for (uint64_t j = 0; j < q; ++j) side += t->ho_rl[j] == 255;
+        for (uint64_t j = 0; j < l; ++j) {
+            uint32_t rl = t->ho_rl[q + j];
+            if (rl == 255) rl = t->ho_l_rl[side++];
+            tot[rr ? l - 1 - j : j] += rl;
+        }
+        ++copies;
+    }
+    for (uint64_t j = 0; j < l; ++j) {
+        const long extra = lround((double) tot[j] / copies);
+        for (long e = 0; e <= extra; ++e) txt_put(out, char_nt4_table[code[j]]);
+        written += extra;
+    }
+    free(tot);
+    free(code);
+    return written;
+}
+
+/* ---------------------------------------------------------------- bases of a chain of syncmers */
+static int64_t chain_text(const sr_db_t *db, const uint64_t *v, uint64_t n, const syncmer_t *scm, txt_t *out, int hoco_only)
+{
+    if (n == 0) return 0;
+    const int w = db->k;
+    ovl_tab_t tab = {0, 0, 0, 0};                      /* one table per chain: its capacity carries over (reference :1011-1041) */
+    int64_t *pos = (int64_t *) malloc(n * sizeof(int64_t));
+    pos[0] = 0;
+    for (uint64_t i = 1; i < n; ++i)
+        pos[i] = pos[i - 1] + neighbour_offset(db, &scm[v[i - 1] >> 1], v[i - 1] & 1, &scm[v[i] >> 1], v[i] & 1, &tab);
+    int64_t end = 0, len = 0;
+    for (uint64_t i = 0; i < n; ++i) {
+        while (i + 1 < n && pos[i + 1] <= end) ++i;     /* the next one still starts inside what is written: skip ahead */
+        len += syncmer_text(db, &scm[v[i] >> 1], (int) (v[i] & 1), end - pos[i], out, hoco_only);
+        end = pos[i] + w;
+    }
+    free(pos);
+    ot_free(&tab);
+    assert(len >= 0 && (uint64_t) len == out->l);
+    return len;
+}
+
+/* ---------------------------------------------------------------- unitig coverage */
+static int dbl_cmp(const void *a, const void *b)
+{
+    const double x = *(const double *) a, y = *(const double *) b;
+    return (x > y) - (x < y);
+}
+
+static double quantile_sorted(const double *a, int n, double q)
+{
+    if (n == 1) return a[0];
+    double whole;
+    const double frac = modf(q * (n - 1), &whole);
+    const int i = (int) lround(whole);
+    return i == n - 1 ? a[i] : a[i] + (a[i + 1] - a[i]) * frac;
+}
+
+static double iqr_mean_sorted(const double *a, int n)
+{
+    if (n == 0) return 0.;
+    double q1 = quantile_sorted(a, n, 0.25), q3 = quantile_sorted(a, n, 0.75);
+    const double iqr = q3 - q1;
+    q1 -= 1.5 * iqr; q3 += 1.5 * iqr;
+    double sum = 0.;
+    int kept = 0;
+    for (int i = 0; i < n; ++i) if (a[i] >= q1 && a[i] <= q3) { sum += a[i]; ++kept; }
+    return kept ? sum / kept : 0.;
+}
+
+static double unitig_coverage(const scg_t *g, const asmg_vtx_t *u)
+{
+    if (u->del) return 0.;
+    const syncmer_t *scm = g->scm_db->a;
+    double *c = (double *) calloc(u->n ? u->n : 1, sizeof(double));
+    uint64_t i, first;
+    for (i = 0; i < u->n; ++i) {                        /* syncmers that sit on exactly one unitig */
+        const uint64_t id = u->a[i] >> 1;
+        if (g->idx_u[id + 1] - g->idx_u[id] == 1) c[i] = scm[id].cov;
+    }
+    qsort(c, u->n, sizeof(double), dbl_cmp);
+    for (first = 0; first < u->n && c[first] < DBL_EPSILON; ++first) {}
+    if (first == u->n) {
+        for (i = 0; i < u->n; ++i) c[i] = scm[u->a[i] >> 1].cov;
+        qsort(c, u->n, sizeof(double), dbl_cmp);
+        first = 0;
+    }
+    const double avg = iqr_mean_sorted(c + first, (int) (u->n - first));
+    free(c);
+    return avg;
+}
+
+/* ---------------------------------------------------------------- the graph as GFA */
+static asmg_arc_t *arc_vw(asmg_t *g, uint64_t v, uint64_t w)
+{
+    asmg_arc_t *a = &g->arc[g->idx_p[v]];
+    for (uint64_t i = 0, n = g->idx_n[v]; i < n; ++i) if (a[i].w == w) return &a[i];
+    return 0;
+}
+
+void scg_consensus(sr_db_t *sr_db, scg_t *scg, int hoco_seq, int save_seq, FILE *fo)
+{
+    const int w = sr_db->k;
+    const syncmer_t *scm = scg->scm_db->a;
+    asmg_t *G = scg->utg_asmg;
+    txt_t t = {0, 0, 0};
+    uint64_t i;
+
+    for (i = 0; i < G->n_arc; ++i) G->arc[i].ls = 0;    /* graph.h:283-295 */
+    for (i = 0; i < G->n_vtx; ++i) { free(G->vtx[i].seq); G->vtx[i].seq = 0; G->vtx[i].len = 0; }
+
+    if (fo) fprintf(fo, "H\tVN:Z:1.0\n");
+    for (i = 0; i < G->n_vtx; ++i) {
+        asmg_vtx_t *u = &G->vtx[i];
+        if (u->del) continue;
+        t.l = 0;
+        const int64_t l = chain_text(sr_db, u->a, u->n, scm, &t, hoco_seq);
+        const double cov = u->cov ? u->cov : unitig_coverage(scg, u);
+        u->cov = cov;                                   /* the bit-field keeps the integer part, the text the double */
+        u->len = (uint64_t) l;
+        if (save_seq) {
+            u->seq = (char *) malloc((size_t) l + 1);
+            memcpy(u->seq, t.s, (size_t) l);
+            u->seq[l] = 0;
+        }
+        if (fo) fprintf(fo, "S\tu%lu\t%.*s\tLN:i:%ld\tKC:i:%ld\tSC:f:%.3f\n", (unsigned long) i, (int) l, t.s ? t.s : "", (long) l, (long) (int64_t) (l * cov), cov);
+    }
+    for (i = 0; i < G->n_arc; ++i) {
+        asmg_arc_t *a = &G->arc[i];
+        if (a->del || a->comp) continue;
+        int64_t l;
+        if (a->ln > 0) {                                /* the two unitigs share ln syncmers: their length in bases */
+            const asmg_vtx_t *u = &G->vtx[a->v >> 1];
+            t.l = 0;
+            l = chain_text(sr_db, (a->v & 1) ? u->a : &u->a[u->n - a->ln], a->ln, scm, &t, hoco_seq);
+        } else {                                        /* they abut: overlap of the two end syncmers */
+            const asmg_vtx_t *u = &G->vtx[a->v >> 1];
+            uint64_t z = a->v & 1;
+            const uint64_t x = u->a[(u->n - 1) * (!z)] ^ z;
+            u = &G->vtx[a->w >> 1];
+            z = a->w & 1;
+            const uint64_t y = u->a[(u->n - 1) * z] ^ z;
+            l = neighbour_offset(sr_db, &scm[x >> 1], x & 1, &scm[y >> 1], y & 1, 0);
+            if (l < w) {
+                t.l = 0;
+                l = syncmer_text(sr_db, &scm[x >> 1], (int) (x & 1), l, &t, hoco_seq);
+            } else l = 0;
+        }
+        if ((uint64_t) l > G->vtx[a->v >> 1].len) l = (int64_t) G->vtx[a->v >> 1].len;
+        if ((uint64_t) l > G->vtx[a->w >> 1].len) l = (int64_t) G->vtx[a->w >> 1].len;
+        a->ls = (uint64_t) l;
+        arc_vw(G, a->w ^ 1, a->v ^ 1)->ls = (uint64_t) l;
+        if (fo) {
+            fprintf(fo, "L\tu%lu\t%c\tu%lu\t%c\t%ldM\tEC:i:%u\n", (unsigned long) (a->v >> 1), "+-"[a->v & 1], (unsigned long) (a->w >> 1), "+-"[a->w & 1], (long) l, (unsigned) a->cov);
+            fprintf(fo, "L\tu%lu\t%c\tu%lu\t%c\t%ldM\tEC:i:%u\n", (unsigned long) (a->w >> 1), "-+"[a->w & 1], (unsigned long) (a->v >> 1), "-+"[a->v & 1], (long) l, (unsigned) a->cov);
+        }
+    }
+    free(t.s);
+}

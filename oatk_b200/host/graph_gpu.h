@@ -9,6 +9,7 @@
  *   asmg_finalize             graph.c:250-263     cleanup, sort, index, symmetry repair, link ids
  *   asmg_unitigging           graph.c:905-1105    three ordered walks, singletons, arc remap, list expansion
  *   process_mergeable_unitigs syncasm.c:1048-1061
+ *   scg_consensus             syncasm.c:716-823   unitig sequences, overlaps, GFA (consensus_gpu.c)
  */
 #ifndef GRAPH_GPU_H
 #define GRAPH_GPU_H
@@ -64,6 +65,10 @@ scg_t *make_syncmer_graph(sr_db_t *sr_db, syncmer_db_t *scm_db, uint32_t min_k_c
 void process_mergeable_unitigs(scg_t *g);
 void scg_destroy(scg_t *g);
 void scg_stat(scg_t *scg, FILE *fo, uint64_t *stats);
+/* row f1 (consensus_gpu.c): unitig sequences, arc overlaps and the GFA text (reference syncasm.c:716-823).
+ * hoco_seq: write homopolymer-compressed bases; save_seq: keep each unitig's sequence in vtx[i].seq;
+ * fo may be NULL (lengths, coverages and overlaps are still filled in) */
+void scg_consensus(sr_db_t *sr_db, scg_t *scg, int hoco_seq, int save_seq, FILE *fo);
 
 #ifdef __cplusplus
 }

@@ -218,6 +218,16 @@ int ref_write_gfa(sr_db_t *db, scg_t *g, const char *path)
     return 0;
 }
 
+/* the same with the reference's switches: hoco_seq (homopolymer-compressed text), save_seq */
+int ref_write_gfa2(sr_db_t *db, scg_t *g, int hoco_seq, int save_seq, const char *path)
+{
+    FILE *fo = fopen(path, "w");
+    if (!fo) return 1;
+    scg_consensus(db, g, hoco_seq, save_seq, fo);
+    fclose(fo);
+    return 0;
+}
+
 /* ---- CPU baseline timing: the reference's own sr_read -> sr_db_stat -> collect,
  *      called in the order run_syncasm.c does. t[0..2] = seconds per stage,
  *      t[3] = raw bases read, t[4] = syncmers, t[5] = distinct k-mers ---- */

@@ -49,6 +49,45 @@ def stat_lines(fn, db_ptr):
     return txt.splitlines()
 
 
+def _libc():
+    libc = C.CDLL(None)
+    libc.fopen.restype = C.c_void_p
+    libc.fopen.argtypes = [C.c_char_p, C.c_char_p]
+    libc.fclose.argtypes = [C.c_void_p]
+    return libc
+
+
+def gfa_text(host, db_ptr, g):
+    host.scg_consensus.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    host.scg_consensus.restype = None
+    libc = _libc()
+    path = tempfile.mktemp()
+    fo = libc.fopen(path.encode(), b"w")
+    host.scg_consensus(db_ptr, g, 0, 0, fo)
+    libc.fclose(fo)
+    txt = open(path, "rb").read()
+    os.unlink(path)
+    return txt
+
+
+def ref_gfa_text(ref, rdb, g):
+    ref.L.ref_write_gfa.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p]
+    path = tempfile.mktemp()
+    assert ref.L.ref_write_gfa(rdb, g, path.encode()) == 0
+    txt = open(path, "rb").read()
+    os.unlink(path)
+    return txt
+
+
+def first_diff(a, b):
+    la, lb = a.split(b"\n"), b.split(b"\n")
+    for i, (x, y) in enumerate(zip(la, lb)):
+        if x != y:
+            j = next((t for t in range(min(len(x), len(y))) if x[t] != y[t]), min(len(x), len(y)))
+            return "line %d col %d: %r vs %r" % (i, j, x[max(0, j - 20):j + 20], y[max(0, j - 20):j + 20])
+    return "line counts %d vs %d" % (len(la), len(lb))
+
+
 @pytest.mark.parametrize("k,s", [(1001, 31), (301, 15)])
 def test_drop_in_structs_feed_the_reference(host, ref, k, s):
     reads = synth.hifi_reads(31, 150000, 360, 15000, 0.001) + synth.adversarial_reads(3, k, s)
@@ -143,6 +182,14 @@ def test_graph_layer_matches_reference(host, ref, k, s, mkc):
         d1, d2 = ref.graph_dump(g_mine), ref.graph_dump(g_ref)
         for f in d1:
             assert np.array_equal(d1[f], d2[f]), ("unitigs", f, a)
+        # f1: the GFA text (unitig consensus, overlaps, coverages) of our layer against the reference's scg_consensus
+        mine_gfa, ref_gfa = gfa_text(host, C.addressof(db), g_mine), ref_gfa_text(ref, rdb, g_ref)
+        assert mine_gfa.count(b"\nS\t") > 0
+        assert mine_gfa == ref_gfa, ("gfa", a, first_diff(mine_gfa, ref_gfa))
+        # and the lengths / overlaps it leaves in the graph
+        d1, d2 = ref.graph_dump(g_mine), ref.graph_dump(g_ref)
+        for f in d1:
+            assert np.array_equal(d1[f], d2[f]), ("after consensus", f, a)
         host.scg_destroy(g_mine)
         ref.free(g=g_ref)
     host.syncmer_db_destroy(scm)
