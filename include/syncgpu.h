@@ -208,6 +208,15 @@ int sg_debug_set_hash_bits(sg_batch *b, int bits);
 int sg_debug_set_sort_low_bits(sg_batch *b, int low_bits);
 int sg_debug_sort_info(sg_batch *b, uint64_t *repairs, int *fell_back);
 
+/* multi-GPU statistics: after the tuple exchange every rank holds a share of the occurrences of an s-mer code,
+ * so the s-mer part of sg_stat is per rank. sg_smer_counts_pack exposes the distinct codes of this rank's tuples
+ * with their local counts (2 x uint64 per code, device memory owned by the batch, valid until the next sg_stat /
+ * merge); after an all-gather, sg_smer_counts_merge adds the pairs of all ranks up and overwrites the smer_*
+ * fields of `out` with the global tables (reference sr_db_stat, syncmer.c:916-926). k-mer tables and gap sums of
+ * the ranks simply add up. */
+int sg_smer_counts_pack(sg_batch *b, void **d_pairs, uint64_t *n);
+int sg_smer_counts_merge(sg_batch *b, const void *d_pairs, uint64_t n, sg_stat_t *out);
+
 /* ---- multi-GPU exchange (one process per GPU; the transport is the caller's
  * collective, e.g. NCCL all-to-all; see oatk_b200/dist.py) ---- */
 /* partition this batch's tuples by hash range into n_parts buckets: counts[p] tuples for part p,

@@ -310,6 +310,36 @@ __global__ void __launch_bounds__(256) slot_hist_kernel(const uint64_t *tk, cons
     for (int i = threadIdx.x; i < 1002; i += blockDim.x) if (h[i]) atomicAdd(hist + i, (unsigned long long) h[i]);
 }
 
+// ---- multi-GPU: s-mer multiplicities need every occurrence of a code in one table -----------------
+// the occupied slots of a tally table as (code, count) pairs
+__global__ void __launch_bounds__(256) slot_pack_kernel(const uint64_t *tk, const uint32_t *tv, uint64_t nslots, uint64_t *pairs, unsigned long long *n_out)
+{
+    for (uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < nslots; i += (uint64_t) gridDim.x * blockDim.x) {
+        if (tk[i] == EMPTY_KEY) continue;
+        const unsigned long long o = atomicAdd(n_out, 1ull);
+        pairs[2 * o] = tk[i];
+        pairs[2 * o + 1] = tv[i];
+    }
+}
+// add the pairs of all ranks into one table
+__global__ void __launch_bounds__(256) pair_tally_kernel(const uint64_t *pairs, uint64_t n, uint64_t *tk, uint32_t *tv, uint64_t nslot_mask)
+{
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp0 = ((uint64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nwarp = ((uint64_t) gridDim.x * blockDim.x) >> 5;
+    for (uint64_t base = warp0 * 32; base < n; base += nwarp * 32) {
+        const bool ok = base + lane < n;
+        const uint64_t key = ok ? pairs[2 * (base + lane)] : EMPTY_KEY;
+        const uint32_t cnt = ok ? (uint32_t) pairs[2 * (base + lane) + 1] : 0u;
+        uint32_t work = __ballot_sync(SG_FULL, ok);
+        while (work) {
+            const int src = __ffs(work) - 1;
+            work &= work - 1;
+            table_add(tk, tv, nslot_mask, __shfl_sync(SG_FULL, key, src), __shfl_sync(SG_FULL, cnt, src), lane);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) gap_kernel(const uint64_t *occ, const uint32_t *m_pos, uint64_t n, int k, unsigned long long *out /* [0]=sum (two's complement), [1]=count */)
 {
     __shared__ long long ssum[8];
@@ -469,6 +499,7 @@ int sg_stat(sg_batch *b, sg_stat_t *out)
         while (nslots < 2 * N) nslots <<= 1;
         RS(b->arc_keys, nslots * 8); RS(b->arc_vals, nslots * 4);
         RS(b->stat_dev2, 1002 * 8);
+        b->smer_slots = nslots;
         CK(cudaMemsetAsync(b->arc_keys.p, 0xff, nslots * 8, st));
         CK(cudaMemsetAsync(b->arc_vals.p, 0, nslots * 4, st));
         CK(cudaMemsetAsync(b->stat_dev2.p, 0, 1002 * 8, st));
@@ -493,6 +524,56 @@ int sg_stat(sg_batch *b, sg_stat_t *out)
     out->n_gaps = h[2003];
     out->smer_unique = gs; out->smer_singleton = h[1];
     out->kmer_unique = gk; out->kmer_singleton = h[1001 + 1];
+    return SG_OK;
+}
+
+int sg_smer_counts_pack(sg_batch *b, void **d_pairs, uint64_t *n)
+{
+    if (!b || !d_pairs || !n) return SG_E_ARG;
+    if (!b->smer_slots) return SG_E_STATE;                          // sg_stat builds the table
+    sg_ctx *ctx = b->ctx;
+    cudaStream_t st = ctx->stream;
+    CK(cudaSetDevice(ctx->device));
+    RS(b->smer_pairs, (b->smer_slots / 2 + 1) * 16);                // load factor <= 0.5
+    RS(b->status, 4 * 8);
+    CK(cudaMemsetAsync(b->status.p, 0, 8, st));
+    slot_pack_kernel<<<std::min<unsigned>(nblk(b->smer_slots, 256), 148u * 16u), 256, 0, st>>>((const uint64_t *) b->arc_keys.p,
+            (const uint32_t *) b->arc_vals.p, b->smer_slots, (uint64_t *) b->smer_pairs.p, (unsigned long long *) b->status.p);
+    ctx->count_launch(SG_T_STAT, 1);
+    unsigned long long c = 0;
+    CK(cudaMemcpyAsync(&c, b->status.p, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    *d_pairs = b->smer_pairs.p;
+    *n = c;
+    return SG_OK;
+}
+
+int sg_smer_counts_merge(sg_batch *b, const void *d_pairs, uint64_t n, sg_stat_t *out)
+{
+    if (!b || !out || (!d_pairs && n)) return SG_E_ARG;
+    sg_ctx *ctx = b->ctx;
+    cudaStream_t st = ctx->stream;
+    CK(cudaSetDevice(ctx->device));
+    uint64_t nslots = 1024;
+    while (nslots < 2 * n) nslots <<= 1;
+    RS(b->arc_keys, nslots * 8); RS(b->arc_vals, nslots * 4); RS(b->stat_dev2, 1002 * 8);
+    b->smer_slots = 0;                                              // the local table is gone
+    CK(cudaMemsetAsync(b->arc_keys.p, 0xff, nslots * 8, st));
+    CK(cudaMemsetAsync(b->arc_vals.p, 0, nslots * 4, st));
+    CK(cudaMemsetAsync(b->stat_dev2.p, 0, 1002 * 8, st));
+    if (n) pair_tally_kernel<<<std::min<unsigned>(nblk(n, 256), 148u * 16u), 256, 0, st>>>((const uint64_t *) d_pairs, n, (uint64_t *) b->arc_keys.p,
+            (uint32_t *) b->arc_vals.p, nslots - 1);
+    slot_hist_kernel<<<std::min<unsigned>(nblk(nslots, 256), 148u * 16u), 256, 0, st>>>((const uint64_t *) b->arc_keys.p,
+            (const uint32_t *) b->arc_vals.p, nslots, (unsigned long long *) b->stat_dev2.p);
+    ctx->count_launch(SG_T_STAT, 2);
+    unsigned long long h[1002];
+    CK(cudaMemcpyAsync(h, b->stat_dev2.p, sizeof(h), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    for (int i = 0; i < 1001; ++i) out->smer_cnts[i] = (int64_t) h[i];
+    out->smer_unique = h[1001];
+    out->smer_singleton = h[1];
     return SG_OK;
 }
 

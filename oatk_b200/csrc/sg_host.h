@@ -66,6 +66,8 @@ struct sg_batch {
     int hash_bits = 64;                          // < 64 only through sg_debug_set_hash_bits (tests)
     sg::DevBuf scm_h, scm_s, scm_cov, scm_occ_off, status;
     uint64_t n_unique = 0, n_collisions = 0;
+    sg::DevBuf smer_pairs;                       // multi-GPU: (s-mer code, local count) pairs of the last sg_stat
+    uint64_t smer_slots = 0;                     // slots of the s-mer tally table left by sg_stat (0: none)
     // a7
     sg::DevBuf arc_keys, arc_vals, arc_out, arc_okey, arc_oval, arc_okey_alt, arc_oval_alt;
     uint64_t n_arcs = 0, arc_cap = 0;

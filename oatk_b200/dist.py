@@ -87,6 +87,31 @@ class TupleExchange:
         torch.cuda.current_stream().synchronize()      # `got` may be freed once the adopt kernel has read it
         return sum(self.recv_counts)
 
+    def global_stat(self, batch, st):
+        """sr_db_stat's tables over ALL reads from the per-rank sg_stat results: k-mer tables and gap sums add up
+        (every k-mer lives on one rank), s-mer codes are all-gathered as (code, local count) pairs and merged"""
+        dev = self.device
+        ptr, n = batch.smer_counts_pack()
+        mine = tensor_from_ptr(ptr, n * 2, dev)
+        ns = [torch.empty(1, dtype=torch.int64, device=dev) for _ in range(self.world)]
+        self.dist.all_gather(ns, torch.tensor([n], dtype=torch.int64, device=dev))
+        ns = [int(x.item()) for x in ns]
+        pad = torch.zeros(2 * max(max(ns), 1), dtype=torch.int64, device=dev)
+        pad[:2 * n] = mine
+        parts = [torch.empty_like(pad) for _ in range(self.world)]
+        self.dist.all_gather(parts, pad)
+        allp = torch.cat([p[:2 * m] for p, m in zip(parts, ns)]) if sum(ns) else torch.empty(0, dtype=torch.int64, device=dev)
+        batch.smer_counts_merge(allp.data_ptr() if allp.numel() else None, sum(ns), st)
+        torch.cuda.current_stream().synchronize()
+        kc = torch.tensor(list(st.kmer_cnts), dtype=torch.int64, device=dev)
+        misc = torch.tensor([st.gap_sum, st.n_gaps, st.kmer_unique, st.kmer_singleton, st.n_syncmers], dtype=torch.int64, device=dev)
+        self.dist.all_reduce(kc)
+        self.dist.all_reduce(misc)
+        for i, v in enumerate(kc.tolist()):
+            st.kmer_cnts[i] = v
+        st.gap_sum, st.n_gaps, st.kmer_unique, st.kmer_singleton, st.n_syncmers = (int(x) for x in misc.tolist())
+        return st
+
     def return_ids(self, batch, n_unique):
         """after sg_count: global ids back to the ranks that hold the reads"""
         base, all_counts = id_base(self.dist, n_unique, self.rank, self.world, self.device)

@@ -61,7 +61,7 @@ SYMBOLS = [
     "sg_batch_set_sid_base", "sg_extract", "sg_extract_sizes", "sg_extract_download",
     "sg_stat", "sg_count", "sg_count_sizes", "sg_count_download", "sg_arcs", "sg_arcs_download",
     "sg_tuples_partition", "sg_tuples_adopt", "sg_debug_set_hash_bits", "sg_debug_set_sort_low_bits", "sg_debug_sort_info", "sg_batch_buffer",
-    "sg_ids_pack", "sg_ids_scatter", "sg_batch_set_exact_verify",
+    "sg_ids_pack", "sg_ids_scatter", "sg_batch_set_exact_verify", "sg_smer_counts_pack", "sg_smer_counts_merge",
     "sg_pipe_create", "sg_pipe_destroy", "sg_pipe_run_host", "sg_pipe_master", "sg_pipe_ctx", "sg_pipe_last_error", "sg_pipe_launches",
 ]
 
@@ -103,7 +103,8 @@ def _lib():
                        ("sg_tuples_partition", [vp, i32, vp, C.POINTER(vp)]), ("sg_tuples_adopt", [vp, vp, u64]),
                        ("sg_debug_set_hash_bits", [vp, i32]), ("sg_debug_set_sort_low_bits", [vp, i32]),
                        ("sg_debug_sort_info", [vp, C.POINTER(u64), C.POINTER(i32)]), ("sg_batch_buffer", [vp, i32, C.POINTER(vp), C.POINTER(u64)]),
-                       ("sg_ids_pack", [vp, u64, C.POINTER(vp), C.POINTER(u64)]), ("sg_ids_scatter", [vp, vp, u64]), ("sg_batch_set_exact_verify", [vp, i32])):
+                       ("sg_ids_pack", [vp, u64, C.POINTER(vp), C.POINTER(u64)]), ("sg_smer_counts_pack", [vp, C.POINTER(vp), C.POINTER(u64)]),
+                       ("sg_smer_counts_merge", [vp, vp, u64, vp]), ("sg_ids_scatter", [vp, vp, u64]), ("sg_batch_set_exact_verify", [vp, i32])):
         if hasattr(L, name):
             getattr(L, name).argtypes = args
     L.sg_pipe_create.argtypes = [i32, i32, C.POINTER(vp)]
@@ -300,6 +301,15 @@ class Batch:
 
     def debug_set_hash_bits(self, bits):
         _ck(self.ctx.h, _lib().sg_debug_set_hash_bits(self.h, bits), "sg_debug_set_hash_bits")
+
+    def smer_counts_pack(self):
+        p, n = C.c_void_p(), C.c_uint64(0)
+        _ck(self.ctx.h, _lib().sg_smer_counts_pack(self.h, C.byref(p), C.byref(n)), "sg_smer_counts_pack")
+        return p.value, int(n.value)
+
+    def smer_counts_merge(self, d_ptr, n, stat):
+        _ck(self.ctx.h, _lib().sg_smer_counts_merge(self.h, d_ptr, n, C.byref(stat)), "sg_smer_counts_merge")
+        return stat
 
     def debug_set_sort_low_bits(self, bits):
         _ck(self.ctx.h, _lib().sg_debug_set_sort_low_bits(self.h, bits), "sg_debug_set_sort_low_bits")

@@ -34,6 +34,7 @@ def main():
     ex = sgdist.TupleExchange(ctx, dist, rank, world)
     ex.run(b)
     st = b.stat()
+    gst = ex.global_stat(b, b.stat())          # every rank ends up with the whole-input tables
     b.count()
     got = b.count_download()
     base, allc = ex.return_ids(b, len(got["h"]))
@@ -65,7 +66,11 @@ def main():
         checks = {"h": np.array_equal(H, exp["h"]), "cov": np.array_equal(COV.astype(np.uint32), exp["cov"]),
                   "occ": np.array_equal(OCC, exp["occ"]), "k_mer_id": np.array_equal(KID, exp["k_mer_id"]),
                   "kmer_cnts": np.array_equal(kc.cpu().numpy(), kcx),
-                  "avg_dist": gaps[0].item() / gaps[1].item() == d[1]}
+                  "avg_dist": gaps[0].item() / gaps[1].item() == d[1],
+                  "global_kmer_cnts": np.array_equal(np.array(gst.kmer_cnts[:], np.int64), kcx),
+                  "global_smer_cnts": np.array_equal(np.array(gst.smer_cnts[:], np.int64), sc),
+                  "global_smer_unique": int(gst.smer_unique) == int(np.sum(sc)),
+                  "global_gaps": gst.gap_sum / gst.n_gaps == d[1]}
         ok = all(checks.values())
         print("MULTIGPU_PARITY", "OK" if ok else "FAIL", checks, "world", world, "distinct", len(exp["h"]), "per-rank", allc)
     dist.barrier()
