@@ -181,6 +181,16 @@ int sg_pipe_create(int device, int n_slots, sg_pipe **out);
 void sg_pipe_destroy(sg_pipe *p);
 int sg_pipe_run_host(sg_pipe *p, const char *bases, const uint64_t *off, uint64_t n_reads, int k, int s,
         uint64_t chunk_reads, const sg_extract_out_t *out, const sg_pipe_caps_t *caps, sg_extract_sizes_t *sizes);
+/* The same pipeline, handing every chunk to the caller instead of filling flat arrays: `fn` is called once per
+ * chunk of reads [r0, r0 + n_reads) with chunk-local arrays (offsets start at 0, amb_sid / lrl_sid count reads
+ * from r0) that live in pinned staging memory and are valid only during the call. Calls for different chunks
+ * may run concurrently on different threads; a non-zero return value stops the run and is returned. This is
+ * what the reference-API layer uses to build its per-read malloc blocks while later chunks are still in flight.
+ * `bases` may be ordinary pageable memory in both forms (it is staged through pinned buffers by the slot
+ * threads); pinned input goes straight to the copy engine. */
+typedef int (*sg_pipe_chunk_fn)(void *user, uint64_t r0, uint64_t n_reads, const sg_extract_out_t *chunk, const sg_extract_sizes_t *sizes);
+int sg_pipe_run_host_cb(sg_pipe *p, const char *bases, const uint64_t *off, uint64_t n_reads, int k, int s,
+        uint64_t chunk_reads, sg_pipe_chunk_fn fn, void *user, sg_extract_sizes_t *sizes);
 sg_batch *sg_pipe_master(sg_pipe *p);
 sg_ctx *sg_pipe_ctx(sg_pipe *p);
 const char *sg_pipe_last_error(sg_pipe *p);

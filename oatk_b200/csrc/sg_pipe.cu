@@ -40,6 +40,22 @@ struct SlotIn {
     DevBuf bases[2], off[2];
     uint64_t *h_off[2] = {nullptr, nullptr};       // pinned chunk-local offsets
     size_t h_off_cap = 0;
+    char *h_bases[2] = {nullptr, nullptr};         // pinned copy of a chunk when the caller's reads are pageable
+    size_t h_bases_cap[2] = {0, 0};
+    // pinned result staging of the callback form (one chunk)
+    void *stage[16] = {};
+    size_t stage_cap[16] = {};
+    void *staged(int i, size_t bytes)
+    {
+        if (stage_cap[i] < bytes) {
+            if (stage[i]) cudaFreeHost(stage[i]);
+            stage[i] = nullptr; stage_cap[i] = 0;
+            const size_t want = bytes + bytes / 4 + 4096;
+            if (cudaMallocHost(&stage[i], want) != cudaSuccess) return nullptr;
+            stage_cap[i] = want;
+        }
+        return stage[i];
+    }
 };
 
 struct sg_pipe {
@@ -97,7 +113,12 @@ void sg_pipe_destroy(sg_pipe *p)
     }
     for (SlotIn *si : p->in) {
         if (si->up) cudaStreamDestroy(si->up);
-        for (int j = 0; j < 2; ++j) { if (si->ready[j]) cudaEventDestroy(si->ready[j]); if (si->h_off[j]) cudaFreeHost(si->h_off[j]); }
+        for (int j = 0; j < 2; ++j) {
+            if (si->ready[j]) cudaEventDestroy(si->ready[j]);
+            if (si->h_off[j]) cudaFreeHost(si->h_off[j]);
+            if (si->h_bases[j]) cudaFreeHost(si->h_bases[j]);
+        }
+        for (int j = 0; j < 16; ++j) if (si->stage[j]) cudaFreeHost(si->stage[j]);
         delete si;
     }
     if (p->master) sg_batch_destroy(p->master);
@@ -117,10 +138,10 @@ uint64_t sg_pipe_launches(sg_pipe *p)
     return n;
 }
 
-int sg_pipe_run_host(sg_pipe *p, const char *bases, const uint64_t *off, uint64_t n_reads, int k, int s,
-        uint64_t chunk_reads, const sg_extract_out_t *out, const sg_pipe_caps_t *caps, sg_extract_sizes_t *sizes)
+static int pipe_run(sg_pipe *p, const char *bases, const uint64_t *off, uint64_t n_reads, int k, int s,
+        uint64_t chunk_reads, const sg_extract_out_t *out, const sg_pipe_caps_t *caps, sg_pipe_chunk_fn cb, void *cb_user, sg_extract_sizes_t *sizes)
 {
-    if (!p || !off || !out || !caps || !sizes || chunk_reads == 0) return SG_E_ARG;
+    if (!p || !off || (!cb && (!out || !caps)) || !sizes || chunk_reads == 0) return SG_E_ARG;
     if (!(s > 0 && s < 32 && k > s)) return SG_E_ARG;
     if (n_reads > 0xFFFFFFFFull) return SG_E_LIMIT;
     cudaSetDevice(p->device);
@@ -130,8 +151,19 @@ int sg_pipe_run_host(sg_pipe *p, const char *bases, const uint64_t *off, uint64_
     sg_ctx *mctx = p->mctx;
     auto fail = [&](int rc, const std::string &what) { p->err = what; return rc; };
 
+    // pageable reads are staged through pinned per-slot buffers by the slot threads (the driver would do
+    // the same, serially and synchronously)
+    bool in_pinned = true;
+    if (total) {
+        cudaPointerAttributes pa;
+        if (cudaPointerGetAttributes(&pa, bases) != cudaSuccess) { cudaGetLastError(); in_pinned = false; }
+        else in_pinned = pa.type == cudaMemoryTypeHost || pa.type == cudaMemoryTypeManaged;
+    }
     // master arrays: per read and per position capacities are known, per syncmer ones come from the caller
-    const uint64_t cap_pos = total + 64 * n_reads + 64, capN = caps->max_syncmers;
+    // (callback form: 2 closed syncmers per window is the expectation; room for 16, never more than one per base)
+    const uint64_t qwin = (uint64_t) (k - s + 1);
+    const uint64_t cap_pos = total + 64 * n_reads + 64;
+    const uint64_t capN = cb ? std::min<uint64_t>(total + n_reads, 16 * (total / qwin + n_reads)) + 1024 : caps->max_syncmers;
     if (M->hoff.reserve((n_reads + 1) * 8) || M->hoco_s.reserve(cap_pos / 4 + 64) || M->hoco_l.reserve((n_reads + 1) * 4) ||
             M->n_scm.reserve((n_reads + 1) * 4) || M->scm_off.reserve((n_reads + 1) * 8) || M->n_amb.reserve((n_reads + 1) * 4) ||
             M->key.reserve((capN + 1) * 8) || M->occ.reserve((capN + 1) * 8) || M->m_pos.reserve((capN + 1) * 4) || M->s_mer.reserve((capN + 1) * 8) || M->fp.reserve((capN + 1) * 8))
@@ -173,7 +205,19 @@ int sg_pipe_run_host(sg_pipe *p, const char *bases, const uint64_t *off, uint64_
             const uint64_t nb = off[r1] - off[r0];
             if (!in->h_off[j] || in->bases[j].reserve(nb + 64) || in->off[j].reserve((nr + 1) * sizeof(uint64_t))) return SG_E_NOMEM;
             for (uint64_t i = 0; i <= nr; ++i) in->h_off[j][i] = off[r0 + i] - off[r0];
-            if (nb && cudaMemcpyAsync(in->bases[j].p, bases + off[r0], nb, cudaMemcpyHostToDevice, in->up) != cudaSuccess) return SG_E_CUDA;
+            const char *src = bases + off[r0];
+            if (!in_pinned && nb) {
+                if (in->h_bases_cap[j] < nb) {
+                    if (in->h_bases[j]) cudaFreeHost(in->h_bases[j]);
+                    in->h_bases[j] = nullptr; in->h_bases_cap[j] = 0;
+                    if (cudaMallocHost((void **) &in->h_bases[j], nb + nb / 8 + 4096) != cudaSuccess) return SG_E_NOMEM;
+                    in->h_bases_cap[j] = nb + nb / 8 + 4096;
+                }
+                // the buffer was last read by the upload of two rounds ago, which the extract of that chunk waited for
+                memcpy(in->h_bases[j], src, nb);
+                src = in->h_bases[j];
+            }
+            if (nb && cudaMemcpyAsync(in->bases[j].p, src, nb, cudaMemcpyHostToDevice, in->up) != cudaSuccess) return SG_E_CUDA;
             if (cudaMemcpyAsync(in->off[j].p, in->h_off[j], (nr + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, in->up) != cudaSuccess) return SG_E_CUDA;
             if (cudaEventRecord(in->ready[j], in->up) != cudaSuccess) return SG_E_CUDA;
             b->h2d_bytes += nb + (nr + 1) * sizeof(uint64_t);
@@ -212,9 +256,9 @@ int sg_pipe_run_host(sg_pipe *p, const char *bases, const uint64_t *off, uint64_
                 cv.wait(g, [&] { return next_chunk == c; });
                 base = tot;
                 if (!rc && !first_err) {
-                    if (tot.scm + z.n_syncmers > capN || tot.hs + z.hoco_s_bytes > caps->hoco_s_bytes ||
+                    if (tot.scm + z.n_syncmers > capN || (!cb && (tot.hs + z.hoco_s_bytes > caps->hoco_s_bytes ||
                             tot.rl + z.ho_rl_bytes > caps->ho_rl_bytes || tot.amb + z.n_ambiguous > caps->max_ambiguous ||
-                            tot.lrl + z.n_long_runs > caps->max_long_runs) {
+                            tot.lrl + z.n_long_runs > caps->max_long_runs))) {
                         rc = SG_E_NOMEM; msg = "caller capacities too small";
                     }
                 }
@@ -243,6 +287,31 @@ int sg_pipe_run_host(sg_pipe *p, const char *bases, const uint64_t *off, uint64_
                 cudaMemcpyAsync((uint32_t *) M->m_pos.p + base.scm, b->m_pos.p, N * 4, cudaMemcpyDeviceToDevice, st);
                 cudaMemcpyAsync((uint64_t *) M->s_mer.p + base.scm, b->s_mer.p, N * 8, cudaMemcpyDeviceToDevice, st);
                 cudaMemcpyAsync((uint64_t *) M->fp.p + base.scm, b->fp.p, N * 8, cudaMemcpyDeviceToDevice, st);
+            }
+            if (cb) {
+                // ---- callback form: the chunk lands in this slot's pinned staging and is handed over ----
+                sg_extract_out_t o;
+                memset(&o, 0, sizeof(o));
+                o.hoco_l = (uint32_t *) in->staged(0, (nr + 1) * 4); o.n_scm = (uint32_t *) in->staged(1, (nr + 1) * 4);
+                o.hoco_s_off = (uint64_t *) in->staged(2, (nr + 2) * 8); o.ho_rl_off = (uint64_t *) in->staged(3, (nr + 2) * 8);
+                o.scm_off = (uint64_t *) in->staged(4, (nr + 2) * 8);
+                o.hoco_s_buf = (uint8_t *) in->staged(5, z.hoco_s_bytes + 64); o.ho_rl_buf = (uint8_t *) in->staged(6, z.ho_rl_bytes + 64);
+                o.m_pos = (uint32_t *) in->staged(7, (N + 1) * 4); o.s_mer = (uint64_t *) in->staged(8, (N + 1) * 8); o.k_mer = (uint64_t *) in->staged(9, (N + 1) * 8);
+                o.amb_sid = (uint32_t *) in->staged(10, (z.n_ambiguous + 1) * 4); o.amb_pos = (uint32_t *) in->staged(11, (z.n_ambiguous + 1) * 4);
+                o.lrl_sid = (uint32_t *) in->staged(12, (z.n_long_runs + 1) * 4); o.lrl_idx = (uint32_t *) in->staged(13, (z.n_long_runs + 1) * 4);
+                o.lrl_val = (uint32_t *) in->staged(14, (z.n_long_runs + 1) * 4);
+                bool ok = true;
+                for (int j = 0; j < 15; ++j) ok = ok && in->stage[j];
+                double t3 = now(); tp[2] += t3 - t2;
+                rc = ok ? sg_extract_download(b, &o) : SG_E_NOMEM;
+                double t4 = now(); tp[3] += t4 - t3;
+                if (!rc) rc = cb(cb_user, r0, nr, &o, &z);
+                if (rc) {
+                    std::lock_guard<std::mutex> g(mu);
+                    if (!first_err) { first_err = rc; first_msg = rc == SG_E_NOMEM ? "pinned staging allocation failed" : ctx->err; }
+                }
+                tp[4] += now() - t4;
+                continue;
             }
             // ---- this chunk's slice of the caller's arrays ----
             sg_extract_out_t o = *out;
@@ -304,6 +373,19 @@ int sg_pipe_run_host(sg_pipe *p, const char *bases, const uint64_t *off, uint64_
     sizes->hoco_s_bytes = tot.hs; sizes->ho_rl_bytes = tot.rl; sizes->n_ambiguous = tot.amb; sizes->n_long_runs = tot.lrl;
     (void) mctx;
     return SG_OK;
+}
+
+int sg_pipe_run_host(sg_pipe *p, const char *bases, const uint64_t *off, uint64_t n_reads, int k, int s,
+        uint64_t chunk_reads, const sg_extract_out_t *out, const sg_pipe_caps_t *caps, sg_extract_sizes_t *sizes)
+{
+    return pipe_run(p, bases, off, n_reads, k, s, chunk_reads, out, caps, nullptr, nullptr, sizes);
+}
+
+int sg_pipe_run_host_cb(sg_pipe *p, const char *bases, const uint64_t *off, uint64_t n_reads, int k, int s,
+        uint64_t chunk_reads, sg_pipe_chunk_fn fn, void *user, sg_extract_sizes_t *sizes)
+{
+    if (!fn) return SG_E_ARG;
+    return pipe_run(p, bases, off, n_reads, k, s, chunk_reads, nullptr, nullptr, fn, user, sizes);
 }
 
 } // extern "C"

@@ -31,11 +31,13 @@
 #include <math.h>
 #include <float.h>
 #include <assert.h>
+#include <pthread.h>
+#include <unistd.h>
 #include "graph_gpu.h"
 
 /* test probes: how often the offset vote was decided by slot order, and how often a vote table grew past
  * its first four buckets (tests/test_consensus_cpu.py makes sure both paths are exercised) */
-static uint64_t dbg_vote_ties, dbg_table_growths;
+static uint64_t dbg_vote_ties, dbg_table_growths;   /* bumped with relaxed atomics: unitigs are processed in parallel */
 void oatk_consensus_debug_counts(uint64_t *out) { out[0] = dbg_vote_ties; out[1] = dbg_table_growths; }
 
 /* ---------------------------------------------------------------- int -> count, khashl slot order */
@@ -71,7 +73,7 @@ static void ot_grow(ovl_tab_t *t, uint32_t want)
     new_bits = j > 2 ? j : 2;
     new_n = 1u << new_bits;
     if (t->count > (new_n >> 1) + (new_n >> 2)) return;
-    if (old_n) ++dbg_table_growths;
+    if (old_n) __atomic_fetch_add(&dbg_table_growths, 1, __ATOMIC_RELAXED);
     uint32_t *nu = (uint32_t *) calloc(ot_words(new_n), sizeof(uint32_t));
     if (old_n < new_n) t->cell = (ovl_cell_t *) realloc(t->cell, new_n * sizeof(ovl_cell_t));
     mask = new_n - 1;
@@ -115,7 +117,7 @@ static int ot_mode(const ovl_tab_t *t)
         if (t->cell[i].val > best_n) { best_n = t->cell[i].val; best = t->cell[i].key; tied = 0; }
         else if (t->cell[i].val == best_n) tied = 1;
     }
-    dbg_vote_ties += tied;
+    if (tied) __atomic_fetch_add(&dbg_vote_ties, 1, __ATOMIC_RELAXED);
     return best;
 }
 
@@ -306,54 +308,118 @@ static asmg_arc_t *arc_vw(asmg_t *g, uint64_t v, uint64_t w)
     return 0;
 }
 
+/* Unitigs (and arcs) are independent of each other, so their texts and overlaps are computed by a few worker
+ * threads that pull indices from a shared counter; the results are then written out in index order, which is
+ * all the reference's single loop guarantees. */
+typedef struct {
+    sr_db_t *db; scg_t *scg; int hoco;
+    char **text; int64_t *len; double *cov;            /* per unitig */
+    int64_t *ovl;                                       /* per arc */
+    uint64_t next;                                      /* shared work counter */
+    int phase;
+} cons_job_t;
+
+static int64_t arc_overlap(cons_job_t *J, const asmg_arc_t *a, txt_t *t)
+{
+    const sr_db_t *db = J->db;
+    const syncmer_t *scm = J->scg->scm_db->a;
+    asmg_t *G = J->scg->utg_asmg;
+    const int w = db->k;
+    int64_t l;
+    if (a->ln > 0) {                                    /* the two unitigs share ln syncmers: their length in bases */
+        const asmg_vtx_t *u = &G->vtx[a->v >> 1];
+        t->l = 0;
+        l = chain_text(db, (a->v & 1) ? u->a : &u->a[u->n - a->ln], a->ln, scm, t, J->hoco);
+    } else {                                            /* they abut: overlap of the two end syncmers */
+        const asmg_vtx_t *u = &G->vtx[a->v >> 1];
+        uint64_t z = a->v & 1;
+        const uint64_t x = u->a[(u->n - 1) * (!z)] ^ z;
+        u = &G->vtx[a->w >> 1];
+        z = a->w & 1;
+        const uint64_t y = u->a[(u->n - 1) * z] ^ z;
+        l = neighbour_offset(db, &scm[x >> 1], x & 1, &scm[y >> 1], y & 1, 0);
+        if (l < w) {
+            t->l = 0;
+            l = syncmer_text(db, &scm[x >> 1], (int) (x & 1), l, t, J->hoco);
+        } else l = 0;
+    }
+    return l;
+}
+
+static void *cons_worker(void *arg)
+{
+    cons_job_t *J = (cons_job_t *) arg;
+    asmg_t *G = J->scg->utg_asmg;
+    txt_t t = {0, 0, 0};
+    for (;;) {
+        const uint64_t i = __atomic_fetch_add(&J->next, 1, __ATOMIC_RELAXED);
+        if (J->phase == 0) {
+            if (i >= G->n_vtx) break;
+            asmg_vtx_t *u = &G->vtx[i];
+            if (u->del) continue;
+            t.l = 0;
+            J->len[i] = chain_text(J->db, u->a, u->n, J->scg->scm_db->a, &t, J->hoco);
+            J->cov[i] = u->cov ? u->cov : unitig_coverage(J->scg, u);
+            J->text[i] = (char *) malloc((size_t) J->len[i] + 1);
+            memcpy(J->text[i], t.s, (size_t) J->len[i]);
+            J->text[i][J->len[i]] = 0;
+        } else {
+            if (i >= G->n_arc) break;
+            const asmg_arc_t *a = &G->arc[i];
+            if (a->del || a->comp) continue;
+            J->ovl[i] = arc_overlap(J, a, &t);
+        }
+    }
+    free(t.s);
+    return 0;
+}
+
+static void cons_run(cons_job_t *J, int phase, uint64_t n_items)
+{
+    long nt = sysconf(_SC_NPROCESSORS_ONLN);
+    pthread_t th[16];
+    if (nt > 16) nt = 16;
+    if (nt < 1 || n_items < 4) nt = 1;
+    J->phase = phase; J->next = 0;
+    if (nt == 1) { cons_worker(J); return; }
+    for (long i = 0; i < nt; ++i) pthread_create(&th[i], 0, cons_worker, J);
+    for (long i = 0; i < nt; ++i) pthread_join(th[i], 0);
+}
+
 void scg_consensus(sr_db_t *sr_db, scg_t *scg, int hoco_seq, int save_seq, FILE *fo)
 {
-    const int w = sr_db->k;
-    const syncmer_t *scm = scg->scm_db->a;
     asmg_t *G = scg->utg_asmg;
-    txt_t t = {0, 0, 0};
     uint64_t i;
+    cons_job_t J;
 
     for (i = 0; i < G->n_arc; ++i) G->arc[i].ls = 0;    /* graph.h:283-295 */
     for (i = 0; i < G->n_vtx; ++i) { free(G->vtx[i].seq); G->vtx[i].seq = 0; G->vtx[i].len = 0; }
 
+    memset(&J, 0, sizeof(J));
+    J.db = sr_db; J.scg = scg; J.hoco = hoco_seq;
+    J.text = (char **) calloc(G->n_vtx ? G->n_vtx : 1, sizeof(char *));
+    J.len = (int64_t *) calloc(G->n_vtx ? G->n_vtx : 1, sizeof(int64_t));
+    J.cov = (double *) calloc(G->n_vtx ? G->n_vtx : 1, sizeof(double));
+    J.ovl = (int64_t *) calloc(G->n_arc ? G->n_arc : 1, sizeof(int64_t));
+
+    cons_run(&J, 0, G->n_vtx);
     if (fo) fprintf(fo, "H\tVN:Z:1.0\n");
     for (i = 0; i < G->n_vtx; ++i) {
         asmg_vtx_t *u = &G->vtx[i];
         if (u->del) continue;
-        t.l = 0;
-        const int64_t l = chain_text(sr_db, u->a, u->n, scm, &t, hoco_seq);
-        const double cov = u->cov ? u->cov : unitig_coverage(scg, u);
+        const int64_t l = J.len[i];
+        const double cov = J.cov[i];
         u->cov = cov;                                   /* the bit-field keeps the integer part, the text the double */
         u->len = (uint64_t) l;
-        if (save_seq) {
-            u->seq = (char *) malloc((size_t) l + 1);
-            memcpy(u->seq, t.s, (size_t) l);
-            u->seq[l] = 0;
-        }
-        if (fo) fprintf(fo, "S\tu%lu\t%.*s\tLN:i:%ld\tKC:i:%ld\tSC:f:%.3f\n", (unsigned long) i, (int) l, t.s ? t.s : "", (long) l, (long) (int64_t) (l * cov), cov);
+        if (fo) fprintf(fo, "S\tu%lu\t%.*s\tLN:i:%ld\tKC:i:%ld\tSC:f:%.3f\n", (unsigned long) i, (int) l, J.text[i], (long) l, (long) (int64_t) (l * cov), cov);
+        if (save_seq) u->seq = J.text[i]; else free(J.text[i]);
     }
+    /* overlaps are clipped to the unitig lengths, which are all known now */
+    cons_run(&J, 1, G->n_arc);
     for (i = 0; i < G->n_arc; ++i) {
         asmg_arc_t *a = &G->arc[i];
         if (a->del || a->comp) continue;
-        int64_t l;
-        if (a->ln > 0) {                                /* the two unitigs share ln syncmers: their length in bases */
-            const asmg_vtx_t *u = &G->vtx[a->v >> 1];
-            t.l = 0;
-            l = chain_text(sr_db, (a->v & 1) ? u->a : &u->a[u->n - a->ln], a->ln, scm, &t, hoco_seq);
-        } else {                                        /* they abut: overlap of the two end syncmers */
-            const asmg_vtx_t *u = &G->vtx[a->v >> 1];
-            uint64_t z = a->v & 1;
-            const uint64_t x = u->a[(u->n - 1) * (!z)] ^ z;
-            u = &G->vtx[a->w >> 1];
-            z = a->w & 1;
-            const uint64_t y = u->a[(u->n - 1) * z] ^ z;
-            l = neighbour_offset(sr_db, &scm[x >> 1], x & 1, &scm[y >> 1], y & 1, 0);
-            if (l < w) {
-                t.l = 0;
-                l = syncmer_text(sr_db, &scm[x >> 1], (int) (x & 1), l, &t, hoco_seq);
-            } else l = 0;
-        }
+        int64_t l = J.ovl[i];
         if ((uint64_t) l > G->vtx[a->v >> 1].len) l = (int64_t) G->vtx[a->v >> 1].len;
         if ((uint64_t) l > G->vtx[a->w >> 1].len) l = (int64_t) G->vtx[a->w >> 1].len;
         a->ls = (uint64_t) l;
@@ -363,5 +429,5 @@ void scg_consensus(sr_db_t *sr_db, scg_t *scg, int hoco_seq, int save_seq, FILE 
             fprintf(fo, "L\tu%lu\t%c\tu%lu\t%c\t%ldM\tEC:i:%u\n", (unsigned long) (a->w >> 1), "-+"[a->w & 1], (unsigned long) (a->v >> 1), "-+"[a->v & 1], (long) l, (unsigned) a->cov);
         }
     }
-    free(t.s);
+    free(J.text); free(J.len); free(J.cov); free(J.ovl);
 }

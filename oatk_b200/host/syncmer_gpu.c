@@ -24,8 +24,9 @@ const char char_nt4_table[4] = {'A', 'C', 'G', 'T'};
 /* one device context for the process, one live batch per sr_db_t */
 static sg_ctx *g_ctx;
 static int g_device;
-typedef struct reg_s { sr_db_t *db; sg_batch *b; struct reg_s *next; } reg_t;
+typedef struct reg_s { sr_db_t *db; sg_batch *b; sg_pipe *pipe; struct reg_s *next; } reg_t;
 static reg_t *g_reg;
+static sg_pipe *g_spare;          /* a released pipeline (device buffers, pinned staging, streams) waits here for the next sr_read_mem */
 static pthread_mutex_t g_lock = PTHREAD_MUTEX_INITIALIZER;
 
 int oatk_gpu_set_device(int device) { g_device = device; return 0; }
@@ -41,11 +42,22 @@ static sg_batch *batch_of(sr_db_t *db, int create)
             fprintf(stderr, "[E::%s] no usable CUDA device %d (libsyncgpu has no CPU path)\n", __func__, g_device);
         } else if (sg_batch_create(g_ctx, &b) == SG_OK) {
             r = (reg_t *) malloc(sizeof(reg_t));
-            r->db = db; r->b = b; r->next = g_reg; g_reg = r;
+            r->db = db; r->b = b; r->pipe = 0; r->next = g_reg; g_reg = r;
         }
     }
     pthread_mutex_unlock(&g_lock);
     return b;
+}
+
+/* whose error text to print */
+static sg_ctx *ctx_of(sr_db_t *db)
+{
+    reg_t *r;
+    sg_ctx *c = g_ctx;
+    pthread_mutex_lock(&g_lock);
+    for (r = g_reg; r; r = r->next) if (r->db == db && r->pipe) { c = sg_pipe_ctx(r->pipe); break; }
+    pthread_mutex_unlock(&g_lock);
+    return c;
 }
 
 static void batch_drop(sr_db_t *db)
@@ -53,14 +65,21 @@ static void batch_drop(sr_db_t *db)
     reg_t **pp, *r;
     pthread_mutex_lock(&g_lock);
     for (pp = &g_reg; (r = *pp); pp = &r->next)
-        if (r->db == db) { *pp = r->next; sg_batch_destroy(r->b); free(r); break; }
+        if (r->db == db) {
+            *pp = r->next;
+            if (r->pipe) { if (g_spare) sg_pipe_destroy(g_spare); g_spare = r->pipe; }
+            else sg_batch_destroy(r->b);
+            free(r);
+            break;
+        }
     pthread_mutex_unlock(&g_lock);
 }
 
 void oatk_gpu_shutdown(void)
 {
     pthread_mutex_lock(&g_lock);
-    while (g_reg) { reg_t *r = g_reg; g_reg = r->next; sg_batch_destroy(r->b); free(r); }
+    while (g_reg) { reg_t *r = g_reg; g_reg = r->next; if (r->pipe) sg_pipe_destroy(r->pipe); else sg_batch_destroy(r->b); free(r); }
+    if (g_spare) { sg_pipe_destroy(g_spare); g_spare = 0; }
     if (g_ctx) { sg_ctx_destroy(g_ctx); g_ctx = 0; }
     pthread_mutex_unlock(&g_lock);
 }
@@ -84,65 +103,67 @@ static void *dup_block(const void *src, size_t bytes)
     return p;
 }
 
+/* the pipeline of libsyncgpu hands over one chunk of reads at a time (chunk-local arrays in pinned staging);
+ * this turns it into the reference's per-read malloc blocks. Runs on the pipeline's slot threads, one chunk per
+ * call, disjoint read ranges. */
+typedef struct { sr_db_t *db; char **names; } fill_t;
+
+static int fill_chunk(void *user, uint64_t r0, uint64_t nr, const sg_extract_out_t *c, const sg_extract_sizes_t *z)
+{
+    fill_t *f = (fill_t *) user;
+    uint64_t i, ia = 0, il = 0;
+    for (i = 0; i < nr; ++i) {
+        sr_t *r = &f->db->a[r0 + i];
+        const uint64_t a0 = ia, l0 = il;
+        char nm[32];
+        r->sid = r0 + i;                                        /* asserted by the reference, syncmer.c:1407 */
+        if (f->names && f->names[r0 + i]) r->sname = strdup(f->names[r0 + i]);
+        else { snprintf(nm, sizeof(nm), "r%lu", (unsigned long) (r0 + i)); r->sname = strdup(nm); }
+        r->hoco_l = c->hoco_l[i];
+        r->hoco_s = (uint8_t *) dup_block(c->hoco_s_buf + c->hoco_s_off[i], (c->hoco_l[i] + 3) / 4);
+        r->ho_rl = (uint8_t *) dup_block(c->ho_rl_buf + c->ho_rl_off[i], c->hoco_l[i]);
+        while (ia < z->n_ambiguous && c->amb_sid[ia] == i) ++ia;
+        r->n_nucl = (uint32_t *) dup_block(c->amb_pos + a0, 4 * (ia - a0));
+        while (il < z->n_long_runs && c->lrl_sid[il] == i) ++il;
+        r->ho_l_rl = (uint32_t *) dup_block(c->lrl_val + l0, 4 * (il - l0));
+        r->n = c->n_scm[i];
+        r->m_pos = (uint32_t *) dup_block(c->m_pos + c->scm_off[i], 4 * (size_t) r->n);
+        r->s_mer = (uint64_t *) dup_block(c->s_mer + c->scm_off[i], 8 * (size_t) r->n);
+        r->k_mer = (uint64_t *) dup_block(c->k_mer + c->scm_off[i], 8 * (size_t) r->n);
+    }
+    return 0;
+}
+
+#define SR_READ_SLOTS 6
+#define SR_READ_CHUNK 4096
+
 int sr_read_mem(sr_db_t *sr_db, const char *bases, const uint64_t *off, char **names, uint64_t n_reads)
 {
-    sg_batch *b;
+    sg_pipe *pipe = 0;
     sg_extract_sizes_t z;
-    sg_extract_out_t o;
+    fill_t f;
+    reg_t *r;
     int rc, k = sr_db->k, s = sr_db->s;
-    uint64_t i, ia = 0, il = 0;
-    uint32_t *hoco_l = 0, *n_scm = 0, *m_pos = 0, *amb_sid = 0, *amb_pos = 0, *lrl_sid = 0, *lrl_idx = 0, *lrl_val = 0;
-    uint64_t *hs_off = 0, *rl_off = 0, *scm_off = 0, *s_mer = 0, *k_mer = 0;
-    uint8_t *hs = 0, *rl = 0;
 
     sr_db_clean(sr_db);
     sr_db_init(sr_db, k, s);
-    b = batch_of(sr_db, 1);
-    if (!b) return SG_E_CUDA;
-    if ((rc = sg_batch_set_reads_host(b, bases, off, n_reads)) != SG_OK ||
-            (rc = sg_extract(b, k, s)) != SG_OK || (rc = sg_extract_sizes(b, &z)) != SG_OK) {
-        fprintf(stderr, "[E::%s] %s: %s\n", __func__, sg_strerror(rc), sg_last_error(g_ctx));
-        return rc;
+    pthread_mutex_lock(&g_lock);
+    pipe = g_spare; g_spare = 0;
+    pthread_mutex_unlock(&g_lock);
+    if (!pipe && sg_pipe_create(g_device, SR_READ_SLOTS, &pipe) != SG_OK) {
+        fprintf(stderr, "[E::%s] no usable CUDA device %d (libsyncgpu has no CPU path)\n", __func__, g_device);
+        return SG_E_CUDA;
     }
-#define NEW(p, n) ((p) = malloc(sizeof(*(p)) * ((n) + 1)))
-    NEW(hoco_l, n_reads); NEW(n_scm, n_reads); NEW(hs_off, n_reads + 1); NEW(rl_off, n_reads + 1); NEW(scm_off, n_reads + 1);
-    NEW(hs, z.hoco_s_bytes); NEW(rl, z.ho_rl_bytes);
-    NEW(m_pos, z.n_syncmers); NEW(s_mer, z.n_syncmers); NEW(k_mer, z.n_syncmers);
-    NEW(amb_sid, z.n_ambiguous); NEW(amb_pos, z.n_ambiguous);
-    NEW(lrl_sid, z.n_long_runs); NEW(lrl_idx, z.n_long_runs); NEW(lrl_val, z.n_long_runs);
-#undef NEW
-    memset(&o, 0, sizeof(o));
-    o.hoco_l = hoco_l; o.n_scm = n_scm; o.hoco_s_off = hs_off; o.ho_rl_off = rl_off; o.scm_off = scm_off;
-    o.hoco_s_buf = hs; o.ho_rl_buf = rl; o.m_pos = m_pos; o.s_mer = s_mer; o.k_mer = k_mer;
-    o.amb_sid = amb_sid; o.amb_pos = amb_pos; o.lrl_sid = lrl_sid; o.lrl_idx = lrl_idx; o.lrl_val = lrl_val;
-    if ((rc = sg_extract_download(b, &o)) != SG_OK) {
-        fprintf(stderr, "[E::%s] %s: %s\n", __func__, sg_strerror(rc), sg_last_error(g_ctx));
-        goto done;
-    }
+    /* sr_db_stat / collect / the arc tally work on the pipeline's device-resident master batch */
+    pthread_mutex_lock(&g_lock);
+    r = (reg_t *) malloc(sizeof(reg_t));
+    r->db = sr_db; r->b = sg_pipe_master(pipe); r->pipe = pipe; r->next = g_reg; g_reg = r;
+    pthread_mutex_unlock(&g_lock);
     sr_db->a = (sr_t *) calloc(n_reads ? n_reads : 1, sizeof(sr_t));
     sr_db->n = sr_db->m = n_reads;
-    for (i = 0; i < n_reads; ++i) {
-        sr_t *r = &sr_db->a[i];
-        uint64_t a0 = ia, l0 = il;
-        char nm[32];
-        r->sid = i;                                             /* asserted by the reference, syncmer.c:1407 */
-        if (names && names[i]) r->sname = strdup(names[i]);
-        else { snprintf(nm, sizeof(nm), "r%lu", (unsigned long) i); r->sname = strdup(nm); }
-        r->hoco_l = hoco_l[i];
-        r->hoco_s = (uint8_t *) dup_block(hs + hs_off[i], (hoco_l[i] + 3) / 4);
-        r->ho_rl = (uint8_t *) dup_block(rl + rl_off[i], hoco_l[i]);
-        while (ia < z.n_ambiguous && amb_sid[ia] == i) ++ia;
-        r->n_nucl = (uint32_t *) dup_block(amb_pos + a0, 4 * (ia - a0));
-        while (il < z.n_long_runs && lrl_sid[il] == i) ++il;
-        r->ho_l_rl = (uint32_t *) dup_block(lrl_val + l0, 4 * (il - l0));
-        r->n = n_scm[i];
-        r->m_pos = (uint32_t *) dup_block(m_pos + scm_off[i], 4 * (size_t) r->n);
-        r->s_mer = (uint64_t *) dup_block(s_mer + scm_off[i], 8 * (size_t) r->n);
-        r->k_mer = (uint64_t *) dup_block(k_mer + scm_off[i], 8 * (size_t) r->n);
-    }
-done:
-    free(hoco_l); free(n_scm); free(hs_off); free(rl_off); free(scm_off); free(hs); free(rl);
-    free(m_pos); free(s_mer); free(k_mer); free(amb_sid); free(amb_pos); free(lrl_sid); free(lrl_idx); free(lrl_val);
+    f.db = sr_db; f.names = names;
+    rc = sg_pipe_run_host_cb(pipe, bases, off, n_reads, k, s, SR_READ_CHUNK, fill_chunk, &f, &z);
+    if (rc != SG_OK) fprintf(stderr, "[E::%s] %s: %s\n", __func__, sg_strerror(rc), sg_pipe_last_error(pipe));
     return rc;
 }
 
@@ -205,7 +226,7 @@ void sr_db_stat(sr_db_t *sr_db, FILE *fo, int more)
     if (!b) { fprintf(stderr, "[E::%s] the read database was not produced by sr_read_mem\n", __func__); return; }
     rc = sg_stat(b, &st);
     if (rc == SG_E_EMPTY) { fprintf(fo, "[M::%s] empty syncmer collection\n", __func__); return; }   /* syncmer.c:909-912 */
-    if (rc != SG_OK) { fprintf(stderr, "[E::%s] %s: %s\n", __func__, sg_strerror(rc), sg_last_error(g_ctx)); return; }
+    if (rc != SG_OK) { fprintf(stderr, "[E::%s] %s: %s\n", __func__, sg_strerror(rc), sg_last_error(ctx_of(sr_db))); return; }
     s->syncmer_n = st.n_syncmers;
     s->syncmer_per_read = (double) st.n_syncmers / (double) sr_db->n;
     s->syncmer_avg_dist = (double) st.gap_sum / (double) st.n_gaps;
@@ -245,14 +266,14 @@ syncmer_db_t *collect_syncmer_from_reads(sr_db_t *sr_db)
         return 0;
     }
     if (rc != SG_OK || (rc = sg_count_sizes(b, &z)) != SG_OK) {
-        fprintf(stderr, "[E::%s] %s: %s\n", __func__, sg_strerror(rc), sg_last_error(g_ctx));
+        fprintf(stderr, "[E::%s] %s: %s\n", __func__, sg_strerror(rc), sg_last_error(ctx_of(sr_db)));
         return 0;
     }
     h = malloc(8 * (z.n_unique + 1)); s = malloc(8 * (z.n_unique + 1)); cov = malloc(4 * (z.n_unique + 1));
     off = malloc(8 * (z.n_unique + 2)); occ = malloc(8 * (z.n_syncmers + 1)); kid = malloc(8 * (z.n_syncmers + 1));
     o.h = h; o.s = s; o.cov = cov; o.occ_off = off; o.occ = occ; o.k_mer_id = kid;
     if ((rc = sg_count_download(b, &o)) != SG_OK) {
-        fprintf(stderr, "[E::%s] %s: %s\n", __func__, sg_strerror(rc), sg_last_error(g_ctx));
+        fprintf(stderr, "[E::%s] %s: %s\n", __func__, sg_strerror(rc), sg_last_error(ctx_of(sr_db)));
         free(h); free(s); free(cov); free(off); free(occ); free(kid);
         return 0;
     }
