@@ -206,7 +206,7 @@ static int run_extract(sg_batch *b, uint64_t rec_cap_hint)
     const uint64_t q = (uint64_t) (b->k - b->s + 1);
     uint64_t rec_cap = std::max<uint64_t>(rec_cap_hint, 4 * (b->total_bases / q + n) + 1024);
     b->rec_cap = rec_cap;
-    RS(b->rec_sid, rec_cap * 4); RS(b->rec_idx, rec_cap * 4); RS(b->rec_mpos, rec_cap * 4); RS(b->rec_smer, rec_cap * 8);
+    RS(b->rec_sid, rec_cap * 4); RS(b->rec_idx, rec_cap * 4); RS(b->rec_mpos, rec_cap * 4);
 
     CK(cudaMemsetAsync(b->counters.p, 0, 8 * sizeof(unsigned long long), st));
     unsigned long long *cnt = (unsigned long long *) b->counters.p;
@@ -234,7 +234,6 @@ static int run_extract(sg_batch *b, uint64_t rec_cap_hint)
     S.n_scm = (uint32_t *) b->n_scm.p;
     S.rec_count = cnt + 2; S.rec_cap = rec_cap;
     S.rec_sid = (uint32_t *) b->rec_sid.p; S.rec_idx = (uint32_t *) b->rec_idx.p; S.rec_mpos = (uint32_t *) b->rec_mpos.p;
-    S.rec_smer = (uint64_t *) b->rec_smer.p;
     LAUNCHED(SG_T_SCAN, launch_scan(S, st));
     ctx->t_end(SG_T_SCAN);
 
@@ -279,9 +278,9 @@ int sg_extract(sg_batch *b, int k, int s)
     ctx->t_begin(SG_T_KMERHASH);
     KmerArgs K;
     K.hoff = (const uint64_t *) b->hoff.p; K.hoco_s = (const uint8_t *) b->hoco_s.p; K.hoco_l = (const uint32_t *) b->hoco_l.p;
-    K.k = k; K.n_rec = N;
+    K.k = k; K.s = s; K.n_rec = N;
     K.rec_sid = (const uint32_t *) b->rec_sid.p; K.rec_idx = (const uint32_t *) b->rec_idx.p; K.rec_mpos = (const uint32_t *) b->rec_mpos.p;
-    K.rec_smer = (const uint64_t *) b->rec_smer.p; K.scm_off = (const uint64_t *) b->scm_off.p;
+    K.scm_off = (const uint64_t *) b->scm_off.p;
     K.sid_base = b->sid_base;
     K.fp = (uint64_t *) b->fp.p;
     K.key = (uint64_t *) b->key.p; K.occ = (uint64_t *) b->occ.p; K.m_pos = (uint32_t *) b->m_pos.p; K.s_mer = (uint64_t *) b->s_mer.p;

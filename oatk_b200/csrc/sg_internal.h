@@ -32,8 +32,7 @@ struct ScanArgs {
     uint32_t *n_scm;             // per read: syncmers emitted
     unsigned long long *rec_count;
     uint64_t rec_cap;
-    uint32_t *rec_sid, *rec_idx, *rec_mpos;   // unordered records (one per syncmer)
-    uint64_t *rec_smer;
+    uint32_t *rec_sid, *rec_idx, *rec_mpos;   // unordered records (one per syncmer): read, rank on the read, start << 1 | open
 };
 constexpr int SYNC_SCAN_WARPS = 4;  // warps per CTA of the syncmer scan kernel (one read per warp, 16 positions per lane and tile)
 struct ScanGeom {
@@ -50,10 +49,9 @@ struct KmerArgs {
     const uint64_t *hoff;
     const uint8_t *hoco_s;
     const uint32_t *hoco_l;
-    int k;
+    int k, s;
     uint64_t n_rec;
     const uint32_t *rec_sid, *rec_idx, *rec_mpos;
-    const uint64_t *rec_smer;
     const uint64_t *scm_off;     // n_reads + 1: exclusive scan of n_scm
     uint64_t sid_base;
     // ordered outputs (read order)

@@ -48,10 +48,17 @@ __global__ void __launch_bounds__(256) kmerhash_kernel(KmerArgs A)
 {
     const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= A.n_rec) return;
-    const uint32_t sid = A.rec_sid[i], idx = A.rec_idx[i], mp = A.rec_mpos[i];
+    const uint32_t sid = A.rec_sid[i], idx = A.rec_idx[i], rec = A.rec_mpos[i];
     const uint64_t hb = A.hoff[sid];
     const uint32_t *hs32 = reinterpret_cast<const uint32_t *>(A.hoco_s + hb / 4);
     const int64_t nwords = ((int64_t) A.hoco_l[sid] + 15) >> 4;
+    // the scan kernel says where the k-mer starts and which rule selected it. OPEN: code of the first s-mer;
+    // CLOSE: code of the last s-mer with its low bit flipped (reference syncmer.c:325-338, 356-377); the strand
+    // bit of that s-mer orients the k-mer
+    const int64_t t = rec >> 1;
+    const bool open = rec & 1u;
+    const uint64_t raw = smer_code_at(hs32, open ? t + A.s - 1 : t + A.k - 1, A.s, nwords);
+    const uint32_t mp = (uint32_t) t << 1 | (uint32_t) (raw & 1ull);
     uint64_t fp;
     const uint64_t h = kmer_murmur(hs32, nwords, mp >> 1, A.k, mp & 1u, &fp);
     const uint64_t o = A.scm_off[sid] + idx;
@@ -59,7 +66,7 @@ __global__ void __launch_bounds__(256) kmerhash_kernel(KmerArgs A)
     A.fp[o] = fp;
     A.occ[o] = (A.sid_base + sid) << 32 | (uint64_t) idx << 1 | (mp & 1u);
     A.m_pos[o] = mp;
-    A.s_mer[o] = A.rec_smer[i];
+    A.s_mer[o] = open ? raw : raw ^ 1ull;
 }
 
 int launch_kmerhash(const KmerArgs &A, cudaStream_t st)

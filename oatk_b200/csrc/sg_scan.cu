@@ -28,8 +28,8 @@
 //      s-mers, i.e. tandem repeats; otherwise 2^-30) is resolved exactly by re-hashing only the tied
 //      positions from the packed read
 //   5. CLOSE/OPEN bits of a tile are combined in registers (E = ((C << 1) | carry) ^ O), chunks with
-//      emissions are queued in a 64-entry list and written out as (sid, idx, m_pos, s_mer) records
-//      when the list fills or the read ends; k-mer hashes follow in sg_kmer.cu
+//      emissions are queued in a 64-entry list and written out as (sid, idx, start << 1 | open)
+//      records when the list fills or the read ends; s-mer codes and k-mer hashes follow in sg_kmer.cu
 #include <algorithm>
 #include <cuda_pipeline.h>
 #include "sg_common.cuh"
@@ -115,7 +115,9 @@ __global__ void __launch_bounds__(32 * SYNC_SCAN_WARPS, 8) scan_kernel(ScanArgs 
         const int nwords = (H + 15) >> 4;
         const bool has_n = A.n_amb[r] != 0;
 
-        for (int i = lane; i < 8 * RS + 2 * RCH; i += 32) wbase[i] = HNONE;      // ring (all keys NONE), Lv0, sfxA
+        // chunk minima in front of the read must say "no hash"; the position ring needs no clearing: every
+        // position a window can reach (>= 0) is written, hash or NONE, by the tile that holds it
+        for (int i = lane; i < 2 * RCH; i += 32) Lv0[i] = HNONE;                 // Lv0, sfxA
         __syncwarp();
 
         uint32_t n_emitted = 0, carryC = 0;
@@ -152,16 +154,13 @@ __global__ void __launch_bounds__(32 * SYNC_SCAN_WARPS, 8) scan_kernel(ScanArgs 
                 while (E) {
                     const int i = __ffs(E) - 1;
                     E &= E - 1;
-                    const int t = (int) (cj << 4) + i - k;                // k-mer start
-                    const bool open = (Om >> i) & 1u;
-                    // OPEN: code of the first s-mer; CLOSE: code of the last s-mer with its low bit flipped
-                    const uint64_t raw = smer_code_at(hs32, open ? t + s - 1 : t + k - 1, s, nwords);
+                    const uint32_t t = (uint32_t) ((int) (cj << 4) + i - k);   // k-mer start
                     const uint64_t o = b + idx;
+                    // the s-mer code and the strand bit follow in kmerhash_kernel (one thread per syncmer, no divergence)
                     if (o < A.rec_cap) {
                         A.rec_sid[o] = (uint32_t) r;
                         A.rec_idx[o] = n_emitted + done + idx;
-                        A.rec_mpos[o] = (uint32_t) t << 1 | (uint32_t) (raw & 1ull);
-                        A.rec_smer[o] = open ? raw : raw ^ 1ull;
+                        A.rec_mpos[o] = t << 1 | ((Om >> i) & 1u);             // bit 0: emitted by OPEN (first s-mer) or CLOSE (last s-mer)
                     }
                     ++idx;
                 }
