@@ -228,6 +228,34 @@ int ref_write_gfa2(sr_db_t *db, scg_t *g, int hoco_seq, int save_seq, const char
     return 0;
 }
 
+/* the reference's reader alone (sstream_open / sstream_read, the loop of sr_read with its -D rule): every record's
+ * name and sequence, flat. Arrays are malloc()ed; the caller frees them. */
+int ref_parse_files(char **files, int n_files, size_t mD, char **bases_out, uint64_t **off_out, char **names_out, uint64_t **name_off_out, uint64_t *n_out)
+{
+    sstream_t *ss = sstream_open(files, n_files);
+    size_t nb = 0, mb = 1 << 16, nn = 0, mn = 1 << 12, n = 0, m = 1024, D = 0;
+    char *bases = malloc(mb), *names = malloc(mn);
+    uint64_t *off = malloc((m + 1) * 8), *noff = malloc((m + 1) * 8);
+    int l;
+    off[0] = noff[0] = 0;
+    if (mD == 0) mD = SIZE_MAX;
+    while ((l = sstream_read(ss)) >= 0) {
+        const char *nm = ss->s->ks->name.s, *sq = ss->s->ks->seq.s;
+        size_t ln = strlen(nm);
+        while (nb + l + 1 > mb) { mb *= 2; bases = realloc(bases, mb); }
+        while (nn + ln + 1 > mn) { mn *= 2; names = realloc(names, mn); }
+        if (n + 2 > m) { m *= 2; off = realloc(off, (m + 1) * 8); noff = realloc(noff, (m + 1) * 8); }
+        memcpy(bases + nb, sq, l); nb += l;
+        memcpy(names + nn, nm, ln); nn += ln;
+        ++n; off[n] = nb; noff[n] = nn;
+        D += l;
+        if (D >= mD) break;
+    }
+    sstream_close(ss);
+    *bases_out = bases; *off_out = off; *names_out = names; *name_off_out = noff; *n_out = n;
+    return 0;
+}
+
 /* ---- CPU baseline timing: the reference's own sr_read -> sr_db_stat -> collect,
  *      called in the order run_syncasm.c does. t[0..2] = seconds per stage,
  *      t[3] = raw bases read, t[4] = syncmers, t[5] = distinct k-mers ---- */
