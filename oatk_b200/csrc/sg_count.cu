@@ -503,7 +503,9 @@ int sg_stat(sg_batch *b, sg_stat_t *out)
         CK(cudaMemsetAsync(b->arc_keys.p, 0xff, nslots * 8, st));
         CK(cudaMemsetAsync(b->arc_vals.p, 0, nslots * 4, st));
         CK(cudaMemsetAsync(b->stat_dev2.p, 0, 1002 * 8, st));
-        key_tally_kernel<<<std::min<unsigned>(nblk(N, 256), 148u * 16u), 256, 0, st>>>(b->t_smer(), N, (uint64_t *) b->arc_keys.p,
+        // in k-mer hash order the occurrences of one k-mer (hence of its s-mer code) are neighbours: the warps merge
+        // them with one match_any before touching the table
+        key_tally_kernel<<<std::min<unsigned>(nblk(N, 256), 148u * 16u), 256, 0, st>>>((const uint64_t *) b->ssmer.p, N, (uint64_t *) b->arc_keys.p,
                 (uint32_t *) b->arc_vals.p, nslots - 1);
         slot_hist_kernel<<<std::min<unsigned>(nblk(nslots, 256), 148u * 16u), 256, 0, st>>>((const uint64_t *) b->arc_keys.p,
                 (const uint32_t *) b->arc_vals.p, nslots, (unsigned long long *) b->stat_dev2.p);
