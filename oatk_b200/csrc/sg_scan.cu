@@ -71,7 +71,7 @@ __device__ __noinline__ bool settle_tie(const uint16_t *ring, int RCH, const uin
 }
 
 template <int S_FIXED, int RCH_FIXED, int LOGB_FIXED>
-__global__ void __launch_bounds__(32 * SYNC_SCAN_WARPS, 8) scan_kernel(ScanArgs A, ScanGeom G)
+__global__ void __launch_bounds__(32 * SYNC_SCAN_WARPS, 6) scan_kernel(ScanArgs A, ScanGeom G)
 {
     extern __shared__ __align__(16) uint32_t smem[];
     // ring rows are RCH + 4 keys apart: a chunk's 16 positions (one column) and 32 consecutive positions
