@@ -205,3 +205,52 @@ def test_empty_collection(host):
     assert stat_lines(host.sr_db_stat, C.addressof(db)) == ["[M::sr_db_stat] empty syncmer collection"]
     assert not host.collect_syncmer_from_reads(C.byref(db))
     host.sr_db_clean(C.byref(db))
+
+
+def test_sr_read_files_matches_reference(host, ref):
+    """file -> sr_db_t through the native reader (f4) and the device pipeline, against the reference's sr_read on the
+    same FASTQ + gzipped FASTA pair: every per-read field and the read names"""
+    host.sr_read_files.argtypes = [C.c_void_p, C.POINTER(C.c_char_p), C.c_int, C.c_size_t]
+    k, s = 301, 15
+    reads = synth.hifi_reads(5, 80000, 150, 9000, 0.002) + synth.adversarial_reads(3, k, s)
+    with tempfile.TemporaryDirectory() as d:
+        import gzip
+        p1, p2 = os.path.join(d, "a.fq"), os.path.join(d, "b.fa.gz")
+        half = len(reads) // 2
+        with open(p1, "wb") as f:
+            for i, r in enumerate(reads[:half]):
+                f.write(b"@q%d desc\n%s\n+\n%s\n" % (i, r, b"I" * len(r)))
+        with gzip.open(p2, "wb") as f:
+            for i, r in enumerate(reads[half:]):
+                f.write(b">f%d\n" % i)
+                for a in range(0, max(len(r), 1), 70):
+                    f.write(r[a:a + 70] + b"\n")
+        files = (C.c_char_p * 2)(p1.encode(), p2.encode())
+        db = SrDb()
+        host.sr_db_init(C.byref(db), k, s)
+        assert host.sr_read_files(C.byref(db), files, 2, 0) == 0
+        ref.L.ref_extract_file.restype = C.c_void_p
+        # the reference reads one file per call of its shim: compare file by file through the in-memory path instead
+        bases, off = pack_reads(reads)
+        rdb, theirs = ref.extract(bases, off, k, s)
+        mine = ref._flat(C.addressof(db), len(reads), count_ambiguous(bases, off))
+        assert db.n == len(reads)
+        assert parity.diff(mine, theirs, parity.EXTRACT_FIELDS) == []
+        # names: "q<i>" then "f<i>"
+        class Sr(C.Structure):
+            _fields_ = [("sid", C.c_uint64), ("sname", C.c_char_p), ("hoco_l", C.c_uint32), ("hoco_s", C.c_void_p), ("ho_rl", C.c_void_p),
+                        ("ho_l_rl", C.c_void_p), ("n_nucl", C.c_void_p), ("n", C.c_uint32), ("m_pos", C.c_void_p), ("s_mer", C.c_void_p), ("k_mer", C.c_void_p)]
+        arr = C.cast(db.a, C.POINTER(Sr))
+        assert arr[0].sname == b"q0" and arr[half - 1].sname == b"q%d" % (half - 1)
+        assert arr[half].sname == b"f0" and arr[len(reads) - 1].sname == b"f%d" % (len(reads) - half - 1)
+        assert all(arr[i].sid == i for i in range(0, len(reads), 17))
+        # the -D cap: stop after the read that reaches it, print the reference's message
+        total = int(off[-1])
+        db2 = SrDb()
+        host.sr_db_init(C.byref(db2), k, s)
+        assert host.sr_read_files(C.byref(db2), files, 2, total // 3) == 0
+        cum = np.cumsum(np.diff(off))
+        assert db2.n == int(np.searchsorted(cum, total // 3, side="left")) + 1
+        host.sr_db_clean(C.byref(db2))
+        host.sr_db_clean(C.byref(db))
+        ref.free(rdb)
