@@ -44,6 +44,42 @@ __device__ __forceinline__ uint64_t kmer_murmur(const uint32_t *hs, int64_t nwor
     return h;
 }
 
+// The same for a k-mer whose 32-base windows all lie inside the read's words (every k-mer but those within two
+// words of a read end): the three-word window slides by two words per block, so each block costs two loads, no
+// bounds checks and no re-conversion of the word it shares with its neighbour.
+__device__ __forceinline__ uint64_t kmer_murmur_interior(const uint32_t *hs, int64_t start, int k, int rev, uint64_t *fp_out)
+{
+    const uint64_t M = 0xc6a4a7935bd1e995ull, F = 0x9e3779b97f4a7c15ull;
+    const uint32_t nbytes = (uint32_t) (k + 3) >> 2, nblk = nbytes >> 3;
+    uint64_t h = 1234ull ^ ((uint64_t) nbytes * M), f = 0x243f6a8885a308d3ull ^ (uint64_t) k;
+    const int64_t p0 = rev ? start + k - 32 : start;                // first window; later ones are 32 bases further on / back
+    const int sh = (int) (p0 & 15) * 2;
+    const uint32_t *w = hs + (p0 >> 4);
+    uint32_t a = bswap32(__ldg(w)), b = bswap32(__ldg(w + 1)), c = bswap32(__ldg(w + 2));
+    const uint32_t nall = nblk + ((nbytes & 7u) ? 1u : 0u);
+    for (uint32_t j = 0; j < nall; ++j) {
+        uint64_t be = (uint64_t) __funnelshift_l(b, a, sh) << 32 | __funnelshift_l(c, b, sh);
+        if (rev) be = rc64(be);
+        // next window: two words on (forward) or two words back (reverse); one word is shared
+        if (j + 1 < nall) {
+            if (!rev) { w += 2; a = c; b = bswap32(__ldg(w + 1)); c = bswap32(__ldg(w + 2)); }
+            else { w -= 2; c = a; a = bswap32(__ldg(w)); b = bswap32(__ldg(w + 1)); }
+        }
+        const int left = k - 32 * (int) j;                            // bases of the k-mer in this block
+        if (left < 32) be &= ~0ull << (64 - 2 * left);
+        if (j < nblk) {
+            uint64_t x = bswap64(be);
+            x *= M; x ^= x >> 47; x *= M;
+            h = (h ^ x) * M;
+        } else h = (h ^ bswap64(be)) * M;                             // the <= 7-byte tail is mixed in unhashed
+        f = (f ^ be) * F; f ^= f >> 32;
+    }
+    h ^= h >> 47; h *= M; h ^= h >> 47;
+    f *= 0xd6e8feb86659fd93ull; f ^= f >> 29;
+    *fp_out = f;
+    return h;
+}
+
 __global__ void __launch_bounds__(256) kmerhash_kernel(KmerArgs A)
 {
     const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
@@ -60,7 +96,10 @@ __global__ void __launch_bounds__(256) kmerhash_kernel(KmerArgs A)
     const uint64_t raw = smer_code_at(hs32, open ? t + A.s - 1 : t + A.k - 1, A.s, nwords);
     const uint32_t mp = (uint32_t) t << 1 | (uint32_t) (raw & 1ull);
     uint64_t fp;
-    const uint64_t h = kmer_murmur(hs32, nwords, mp >> 1, A.k, mp & 1u, &fp);
+    // windows reach from word (start - 32) >> 4 (reverse, last block) to word ((start + k + 31) >> 4) + 2 at most
+    const bool interior = t >= 32 && ((t + A.k + 31) >> 4) + 3 <= nwords;
+    const uint64_t h = interior ? kmer_murmur_interior(hs32, t, A.k, (int) (mp & 1u), &fp)
+                                : kmer_murmur(hs32, nwords, mp >> 1, A.k, mp & 1u, &fp);
     const uint64_t o = A.scm_off[sid] + idx;
     A.key[o] = h;
     A.fp[o] = fp;

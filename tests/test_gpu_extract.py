@@ -37,6 +37,14 @@ def test_adversarial(gpu_ctx, oracle, k, s):
     check(gpu_ctx, oracle, synth.adversarial_reads(3, k, s), k, s)
 
 
+@pytest.mark.parametrize("k,s", [(63, 31), (95, 21), (127, 31), (96, 31), (1023, 31)])
+def test_kmer_block_shapes(gpu_ctx, oracle, k, s):
+    """k-mer lengths around multiples of 32 bases: a last 8-byte Murmur block that is not full of bases, no tail,
+    a tail of every size class (the interior fast path of kmerhash_kernel and the checked one)"""
+    reads = synth.hifi_reads(9, 60000, 40, 6000, 0.002) + synth.adversarial_reads(3, k, s)
+    check(gpu_ctx, oracle, reads, k, s)
+
+
 @pytest.mark.parametrize("k,s", [(1001, 31), (501, 31), (2001, 31)])
 def test_hifi_small(gpu_ctx, oracle, k, s):
     reads = synth.hifi_reads(42, 500000, 300, 15000, 0.001)
