@@ -1,0 +1,444 @@
+/*
+ * syncerr_gpu.c -- row f2 of SURVEY.md section 8: read error correction on the all-syncmer graph.
+ *
+ * What the reference does (syncerr.c:679-757 find_error_syncmers, :342-612 the per-read pass, :144-288 the
+ * graph search, :769-817 update_syncmer_db, :819-943 the driver; levdist.c:75-113, 156-225, 265-310 the
+ * wavefront edit distance it searches with), restated from its behaviour:
+ *
+ *   suspects   a syncmer is suspect when its coverage is below err_mer_c, or -- below max_err_c -- when on one
+ *              of its two sides it has arcs but none with coverage >= err_arc_c and >= max_arc_f * min(cov, cov');
+ *              suspects are flagged in the database AND removed from the graph (vertex and all its arcs)
+ *   blocks     on a read, trusted syncmers (not suspect, not already corrected) are anchors. A stretch of
+ *              untrusted ones together with its flanking anchors is an error block; the anchor that closes a block
+ *              must start at least 10 bases after the end of the syncmer before the block's first bad one. Blocks at
+ *              the head of a read are searched backwards from their right anchor (reverse complement), blocks at
+ *              the tail have no sink, and the bases after the last syncmer form one more tail block.
+ *   search     depth-first over the graph from the left anchor: every arc appends the part of the next k-mer that
+ *              does not overlap the current one to a candidate sequence, which is aligned to the read's bases of
+ *              the block by a wavefront edit distance that is RESUMED from the parent's state (extension mode,
+ *              band bw = max(6, ceil(0.02 * length))). A path counts when its score (edit distance plus unaligned
+ *              target bases) is within the band and it ends in the sink (any vertex for tail blocks). The best one
+ *              wins; a second one with the same score makes the block ambiguous (different bases: AMBISEQ,
+ *              different syncmers: AMBISNQ). At most 10 000 search leaves.
+ *   rewrite    only a SUCCESS replaces the block's syncmers by the path's inner vertices: k_mer = id << 1 | 1 and
+ *              m_pos = 0xFFFFFFFE | strand (the "corrected" marker 0x7FFFFFFF as position). Everything else is kept.
+ *   database   coverages and occurrence lists are rebuilt from the reads; a syncmer without any forward-strand
+ *              occurrence left is flagged deleted (:811-812).
+ *
+ * The per-read pass is independent per read and runs on worker threads like the reference's kt_for; it only
+ * reads the graph. Host code: it walks pointer-rich structures (per-read arrays, per-vertex strings).
+ */
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+#include <assert.h>
+#include <pthread.h>
+#include <unistd.h>
+#include "graph_gpu.h"
+
+#define EC_FAILURE 0
+#define EC_SUCCESS 1
+#define EC_AMBISNQ 2
+#define EC_AMBISEQ 3
+#define EC_MAX_LEAVES 10000
+#define EC_MIN_BLOCK 10          /* bases: shorter blocks are left alone (their flanking syncmers overlap) */
+#define EC_MIN_BAND 6
+#define NO_SINK UINT64_MAX
+#define ID_MASK 0xFFFFFFFFFFFFFFFEULL
+
+/* ---------------------------------------------------------------- wavefront edit distance, resumable */
+typedef struct { int32_t d, k; } wdiag_t;   /* diagonal = query pos - target pos; k = last target index reached on it */
+typedef struct {
+    const char *ts, *qs;
+    int32_t tl, ql, bw;
+    int32_t score, t_end, q_end;            /* t_end/q_end: aligned lengths when an end was reached, else 0 */
+    wdiag_t *a;
+    size_t n, m;
+} wave_t;
+
+static inline int32_t wave_slide(const wave_t *w, const wdiag_t *p)
+{
+    int32_t k = p->k;
+    const int32_t last = (w->ql - p->d < w->tl ? w->ql - p->d : w->tl) - 1;
+    const char *t = w->ts + 1, *q = w->qs + p->d + 1;
+    while (k < last && t[k] == q[k]) ++k;
+    return k;
+}
+
+/* one more edit: slide every diagonal, stop if one reaches the end of target or query, else open the next wave.
+ * Returns the new number of diagonals, or -1 when an end was reached (t_end/q_end then hold the last indices). */
+static int wave_step(wave_t *w, int32_t n, int32_t *t_end, int32_t *q_end)
+{
+    wdiag_t *a = w->a, *b = w->a + n + 2;
+    const int32_t tl = w->tl, ql = w->ql, bw = w->bw;
+    int32_t j, st = 0, en = n + 2;
+    *t_end = *q_end = -1;
+    for (j = 0; j < n; ++j) {
+        wdiag_t *p = &a[j];
+        int32_t k = p->k;
+        if (k >= tl || k + p->d >= ql) continue;
+        k = wave_slide(w, p);
+        if (k + p->d == ql - 1 || k == tl - 1) { *t_end = k; *q_end = k + p->d; return -1; }
+        p->k = k;
+    }
+    b[0].d = a[0].d - 1; b[0].k = a[0].k + 1;
+    b[1].d = a[0].d; b[1].k = ((n == 1 || a[0].k > a[1].k) ? a[0].k : a[1].k) + 1;
+    for (j = 1; j < n - 1; ++j) {
+        int32_t k = a[j - 1].k;
+        if (a[j].k + 1 > k) k = a[j].k + 1;
+        if (a[j + 1].k + 1 > k) k = a[j + 1].k + 1;
+        b[j + 1].d = a[j].d; b[j + 1].k = k;
+    }
+    if (n >= 2) { b[n].d = a[n - 1].d; b[n].k = a[n - 2].k > a[n - 1].k + 1 ? a[n - 2].k : a[n - 1].k + 1; }
+    b[n + 1].d = a[n - 1].d + 1; b[n + 1].k = a[n - 1].k;
+    if (bw < 0 || n < bw + bw + 1) {
+        if (b[0].d < -tl) ++st;
+        if (b[n + 1].d > ql) --en;
+    } else {                                            /* fixed band in extension mode (levdist.c:99-113) */
+        int32_t lo = -bw, hi = bw;
+        if (lo < -tl) lo = -tl;
+        if (hi < ql) hi = ql;                           /* sic: the reference widens, it does not clip */
+        while (b[st].d < lo) ++st;
+        while (b[en - 1].d > hi) --en;
+    }
+    memmove(a, &b[st], (size_t) (en - st) * sizeof(*a));
+    return en - st;
+}
+
+static void wave_run(wave_t *w)
+{
+    int32_t s = w->score, n = (int32_t) w->n, t_end = w->t_end, q_end = w->q_end, na;
+    if (w->m < 2 * (size_t) (w->tl + w->ql + 2)) {
+        w->m = 2 * (size_t) (w->tl + w->ql + 2);
+        w->a = (wdiag_t *) realloc(w->a, w->m * sizeof(wdiag_t));
+    }
+    for (;;) {
+        na = wave_step(w, n, &t_end, &q_end);
+        if (na < 0) break;
+        ++s;
+        n = na;
+        if (w->bw >= 0 && s > w->bw) break;
+    }
+    w->t_end = t_end + 1; w->q_end = q_end + 1;
+    w->score = s; w->n = (size_t) n;
+}
+
+/* ---------------------------------------------------------------- small vectors */
+typedef struct { size_t l, m; char *s; } str_t;
+typedef struct { size_t n, m; uint64_t *a; } v64_t;
+typedef struct { size_t n, m; uint32_t *a; } v32_t;
+
+static inline void str_room(str_t *s, size_t extra)
+{
+    if (s->l + extra + 1 >= s->m) { s->m = (s->l + extra + 2) * 2; s->s = (char *) realloc(s->s, s->m); }
+}
+static inline void str_add(str_t *s, const char *p, size_t l) { str_room(s, l); memcpy(s->s + s->l, p, l); s->l += l; s->s[s->l] = 0; }
+static inline char comp_base(char c)
+{
+    switch (c) { case 'A': return 'T'; case 'C': return 'G'; case 'G': return 'C'; case 'T': return 'A'; }
+    return c;                                           /* the graph's strings hold ACGT (and N for syncmers without a copy) */
+}
+static inline void str_add_rc(str_t *s, const char *p, size_t l)
+{
+    str_room(s, l);
+    for (size_t i = 0; i < l; ++i) s->s[s->l + i] = comp_base(p[l - 1 - i]);
+    s->l += l; s->s[s->l] = 0;
+}
+static inline void v64_push(v64_t *v, uint64_t x) { if (v->n == v->m) { v->m = v->m ? v->m * 2 : 16; v->a = (uint64_t *) realloc(v->a, v->m * 8); } v->a[v->n++] = x; }
+static inline void v32_push(v32_t *v, uint32_t x) { if (v->n == v->m) { v->m = v->m ? v->m * 2 : 16; v->a = (uint32_t *) realloc(v->a, v->m * 4); } v->a[v->n++] = x; }
+static inline void v64_copy(v64_t *d, const v64_t *s) { if (d->m < s->n) { d->m = s->n; d->a = (uint64_t *) realloc(d->a, d->m * 8); } d->n = s->n; if (s->n) memcpy(d->a, s->a, s->n * 8); }
+
+/* ---------------------------------------------------------------- graph search */
+typedef struct {
+    int status, leaves, best, second;                   /* best / second best score so far */
+    str_t cand, best_seq;
+    v64_t path, best_path;
+} search_t;
+
+static void search_from(const asmg_t *G, search_t *S, uint64_t sink, wave_t *w)
+{
+    if (S->leaves >= EC_MAX_LEAVES) return;
+    const size_t l0 = S->cand.l, n0 = S->path.n, d0 = w->n;
+    const uint64_t from = S->path.a[n0 - 1];
+    const asmg_arc_t *arc = &G->arc[G->idx_p[from]];
+    const uint64_t n_arc = G->idx_n[from];
+    const int32_t t_end0 = w->t_end, q_end0 = w->q_end, s0 = w->score;
+    wdiag_t *saved = (wdiag_t *) malloc((d0 ? d0 : 1) * sizeof(wdiag_t));
+    memcpy(saved, w->a, d0 * sizeof(wdiag_t));
+
+    for (uint64_t i = 0; i < n_arc; ++i) {
+        const asmg_arc_t *e = &arc[i];
+        if (e->del) continue;
+        const uint64_t v = e->w;
+        const int ov = (int) e->ls, vl = (int) G->vtx[v >> 1].len;
+        const char *vs = G->vtx[v >> 1].seq;
+        v64_push(&S->path, v);
+        if (v & 1) str_add_rc(&S->cand, vs, (size_t) (vl - ov));
+        else str_add(&S->cand, vs + ov, (size_t) (vl - ov));
+        w->qs = S->cand.s; w->ql = (int32_t) S->cand.l;
+        wave_run(w);
+        const int score = w->score + w->tl - w->t_end;   /* unaligned target bases count as edits */
+        if (score <= w->bw && (sink == NO_SINK || sink == v)) {
+            S->status = EC_SUCCESS;
+            if (score <= S->best) {
+                if (w->t_end > t_end0) S->second = S->best;   /* a real alternative, not an extension of its parent */
+                S->best = score;
+                /* tail blocks: a last vertex that is only partly covered by the read is not part of the answer */
+                if (sink == NO_SINK && w->q_end < w->ql) --S->path.n;
+                if (S->best == S->second) {
+                    if ((size_t) w->q_end != S->best_seq.l || strncmp(S->cand.s, S->best_seq.s ? S->best_seq.s : "", (size_t) w->q_end)) S->status = EC_AMBISEQ;
+                    if (S->status == EC_SUCCESS) {
+                        int same = S->path.n == S->best_path.n;
+                        for (size_t j = 0; same && j < S->path.n; ++j) same = S->path.a[j] == S->best_path.a[j];
+                        if (!same) S->status = EC_AMBISNQ;
+                    }
+                }
+                S->best_seq.l = 0;
+                str_add(&S->best_seq, S->cand.s, (size_t) w->q_end);
+                v64_copy(&S->best_path, &S->path);
+            } else if (score < S->second) S->second = score;
+        }
+        if (w->score <= w->bw && w->ql - vl <= w->tl + w->bw && ((sink != NO_SINK && sink != v) || w->t_end < w->tl))
+            search_from(G, S, sink, w);
+        else ++S->leaves;
+        /* back to the state in front of this arc */
+        S->path.n = n0; S->cand.l = l0;
+        w->t_end = t_end0; w->q_end = q_end0; w->score = s0; w->n = d0;
+        memcpy(w->a, saved, d0 * sizeof(wdiag_t));
+    }
+    free(saved);
+}
+
+/* ---------------------------------------------------------------- one read */
+typedef struct {
+    wave_t w; search_t S; str_t seq; v64_t kk; v32_t pp;
+    long stats[11];                                     /* tail blocks, their 4 outcomes, middle blocks, their 4 outcomes, too short */
+} ec_worker_t;
+
+static void correct_read(sr_db_t *db, const scg_t *g, double max_edist, uint64_t rid, ec_worker_t *W)
+{
+    const asmg_t *G = g->utg_asmg;
+    const syncmer_t *scm = g->scm_db->a;
+    sr_t *sr = &db->a[rid];
+    const int ksz = db->k, n = (int) sr->n;
+    const uint64_t *K = sr->k_mer;
+    const uint32_t *P = sr->m_pos;
+    int beg = -1, end, updated = 1;
+    W->kk.n = 0; W->pp.n = 0;
+
+    for (;;) {
+        uint32_t from = beg < 1 ? 0 : (P[beg - 1] >> 1) + (uint32_t) ksz;
+        from += EC_MIN_BLOCK;
+        for (end = beg + 1; end < n; ++end)
+            if (!scm[K[end] >> 1].del && !(K[end] & 1) && (P[end] >> 1) >= from) break;    /* the next anchor */
+
+        if (beg >= 0 || end < n) {
+            uint64_t src, sink;
+            int l, rev, res;
+            uint32_t at;
+            if (beg < 0) {                              /* head of the read: search backwards from the first anchor */
+                beg = end;
+                src = (K[beg] & ID_MASK) | (uint64_t) !(P[beg] & 1);
+                at = 0; sink = NO_SINK; l = (int) (P[beg] >> 1); rev = 1;
+            } else {
+                --beg;                                  /* the anchor in front of the block */
+                src = (K[beg] & ID_MASK) | (P[beg] & 1);
+                at = (P[beg] >> 1) + (uint32_t) ksz;
+                if (end >= n) { sink = NO_SINK; l = (int) sr->hoco_l - (int) at; }
+                else { sink = (K[end] & ID_MASK) | (P[end] & 1); l = (int) (P[end] >> 1) - (int) at; }
+                rev = 0;
+            }
+            assert(l >= 0);
+            if (W->seq.m < (size_t) l + 1) { W->seq.m = (size_t) l + 1; W->seq.s = (char *) realloc(W->seq.s, W->seq.m); }
+            get_kmer_dna_seq(sr->hoco_s, at, l, (uint32_t) rev, W->seq.s);
+            W->seq.l = (size_t) l;
+            if (l >= EC_MIN_BLOCK) {
+                wave_t *w = &W->w;
+                w->ts = W->seq.s; w->tl = l; w->score = 0; w->qs = 0; w->ql = 0;
+                w->bw = (int32_t) ceil(l * max_edist);
+                if (w->bw < EC_MIN_BAND) w->bw = EC_MIN_BAND;
+                if (w->m < (size_t) l * 4) { w->m = (size_t) l * 4; w->a = (wdiag_t *) realloc(w->a, w->m * sizeof(wdiag_t)); }
+                w->n = 1; w->a[0].d = 0; w->a[0].k = -1;
+                search_t *S = &W->S;
+                S->status = EC_FAILURE; S->leaves = 0; S->best = S->second = INT32_MAX;
+                S->cand.l = 0; S->best_seq.l = 0; S->path.n = 0; S->best_path.n = 0;
+                v64_push(&S->path, src);
+                search_from(G, S, sink, w);
+                res = S->status;
+                if (res) assert(src == S->best_path.a[0] && (sink == NO_SINK || sink == S->best_path.a[S->best_path.n - 1]));
+                if (sink == NO_SINK) { ++W->stats[0]; ++W->stats[1 + res]; }
+                else { ++W->stats[5]; ++W->stats[6 + res]; }
+            } else { res = EC_FAILURE; ++W->stats[10]; }
+
+            if (res == EC_SUCCESS) {                    /* the path's inner vertices replace the block */
+                const v64_t *bp = &W->S.best_path;
+                const int np = (int) bp->n;
+                int j;
+                if (rev) {
+                    for (j = np - 1; j > 0; --j) { v64_push(&W->kk, (bp->a[j] & ID_MASK) | 1); v32_push(&W->pp, 0xFFFFFFFFu ^ (uint32_t) (bp->a[j] & 1)); }
+                } else {
+                    for (j = 1; j < np - 1; ++j) { v64_push(&W->kk, (bp->a[j] & ID_MASK) | 1); v32_push(&W->pp, 0xFFFFFFFEu | (uint32_t) (bp->a[j] & 1)); }
+                    if (sink == NO_SINK && np > 1) { v64_push(&W->kk, (bp->a[j] & ID_MASK) | 1); v32_push(&W->pp, 0xFFFFFFFEu | (uint32_t) (bp->a[j] & 1)); }
+                }
+            } else if (rev) {                           /* keep what the read had */
+                for (int j = 0; j < beg; ++j) { v64_push(&W->kk, K[j]); v32_push(&W->pp, P[j]); }
+            } else if (beg + 1 < n) {
+                for (int j = beg + 1; j < end; ++j) { v64_push(&W->kk, K[j]); v32_push(&W->pp, P[j]); }
+            }
+        } else updated = 0;                             /* not a single anchor on this read */
+
+        /* the run of anchors that follows; note that the reference tests the flag of K[end] here, not of K[beg] (:579) */
+        for (beg = end + 1; beg < n; ++beg)
+            if (scm[K[beg] >> 1].del || (K[end] & 1)) break;
+        if (beg > n) break;
+        for (int j = end; j < beg; ++j) { v64_push(&W->kk, K[j]); v32_push(&W->pp, P[j]); }
+    }
+
+    if (updated) {
+        const size_t nc = W->kk.n;
+        sr->k_mer = (uint64_t *) realloc(sr->k_mer, nc * sizeof(uint64_t));
+        sr->m_pos = (uint32_t *) realloc(sr->m_pos, nc * sizeof(uint32_t));
+        sr->s_mer = (uint64_t *) realloc(sr->s_mer, nc * sizeof(uint64_t));
+        if (nc) { memcpy(sr->k_mer, W->kk.a, nc * sizeof(uint64_t)); memcpy(sr->m_pos, W->pp.a, nc * sizeof(uint32_t)); }
+        for (size_t j = 0; j < nc; ++j) sr->s_mer[j] = scm[sr->k_mer[j] >> 1].s;
+        sr->n = (uint32_t) nc;
+    }
+}
+
+/* ---------------------------------------------------------------- suspects */
+static void drop_arc(asmg_t *G, uint64_t v, uint64_t w)
+{
+    asmg_arc_t *a = &G->arc[G->idx_p[v]];
+    for (uint64_t i = 0, n = G->idx_n[v]; i < n; ++i) if (a[i].w == w) a[i].del = 1;
+}
+static void drop_vertex(asmg_t *G, uint64_t id)
+{
+    G->vtx[id].del = 1;
+    for (int side = 0; side < 2; ++side) {
+        const uint64_t v = id << 1 | (uint64_t) side;
+        asmg_arc_t *a = &G->arc[G->idx_p[v]];
+        for (uint64_t i = 0, n = G->idx_n[v]; i < n; ++i) { a[i].del = 1; drop_arc(G, a[i].w ^ 1, v ^ 1); }
+    }
+}
+
+int64_t find_error_syncmers(scg_t *g, uint32_t err_mer_c, uint32_t max_err_c, uint32_t err_arc_c, double max_arc_f, int del_err)
+{
+    asmg_t *G = g->utg_asmg;
+    syncmer_t *scm = g->scm_db->a;
+    const size_t n_scm = g->scm_db->n;
+    for (size_t i = 0; i < n_scm; ++i) {
+        if (scm[i].del || scm[i].cov >= max_err_c) continue;
+        if (scm[i].cov < err_mer_c) { scm[i].del = 1; continue; }
+        int side_ok[2] = {-1, -1};                      /* -1: no live arc on that side */
+        for (int side = 0; side < 2; ++side) {
+            const uint64_t v = (uint64_t) i << 1 | (uint64_t) side;
+            const asmg_arc_t *a = &G->arc[G->idx_p[v]];
+            const uint64_t na = G->idx_n[v];
+            uint64_t live = 0;
+            for (uint64_t j = 0; j < na; ++j) live += !a[j].del;
+            if (!live) continue;
+            side_ok[side] = 0;
+            for (uint64_t j = 0; j < na; ++j) {
+                if (a[j].del) continue;
+                const uint32_t cw = scm[a[j].w >> 1].cov, cv = scm[i].cov;
+                if (a[j].cov >= err_arc_c && a[j].cov >= (cv < cw ? cv : cw) * max_arc_f) { side_ok[side] = 1; break; }
+            }
+        }
+        if (!side_ok[0] || !side_ok[1]) scm[i].del = 1;
+    }
+    int64_t n_err = 0;
+    uint32_t max_c = 0;
+    for (size_t i = 0; i < n_scm; ++i) if (scm[i].del) { if (scm[i].cov > max_c) max_c = scm[i].cov; ++n_err; }
+    if (del_err) for (size_t i = 0; i < n_scm; ++i) if (scm[i].del) drop_vertex(G, i);
+    fprintf(stderr, "[M::%s] error syncmer candidates: num = %ld, max_c = %u\n", __func__, (long) n_err, max_c);
+    return n_err;
+}
+
+/* ---------------------------------------------------------------- database after the rewrite */
+static void rebuild_syncmer_db(sr_db_t *db, syncmer_db_t *S)
+{
+    syncmer_t *scm = S->a;
+    free(S->c); S->c = 0;
+    free(S->h); S->h = 0;
+    for (size_t i = 0; i < S->n; ++i) scm[i].cov = 0;
+    for (size_t r = 0; r < db->n; ++r)
+        for (uint32_t j = 0; j < db->a[r].n; ++j) ++scm[db->a[r].k_mer[j] >> 1].cov;
+    for (size_t i = 0; i < S->n; ++i) {
+        free(scm[i].m_pos);
+        scm[i].m_pos = (uint64_t *) malloc((scm[i].cov ? scm[i].cov : 1) * sizeof(uint64_t));
+        scm[i].cov = 0;
+    }
+    uint32_t *fwd = (uint32_t *) calloc(S->n ? S->n : 1, sizeof(uint32_t));
+    for (size_t r = 0; r < db->n; ++r) {
+        const sr_t *sr = &db->a[r];
+        for (uint32_t j = 0; j < sr->n; ++j) {
+            const uint64_t id = sr->k_mer[j] >> 1;
+            scm[id].m_pos[scm[id].cov++] = sr->sid << 32 | (uint64_t) j << 1 | (sr->m_pos[j] & 1);
+            if (!(sr->m_pos[j] & 1)) ++fwd[id];
+        }
+    }
+    for (size_t i = 0; i < S->n; ++i) scm[i].del = !fwd[i];   /* syncerr.c:805-812 */
+    free(fwd);
+}
+
+/* ---------------------------------------------------------------- driver */
+typedef struct { sr_db_t *db; scg_t *g; double max_edist; uint64_t *next; ec_worker_t W; pthread_t th; } ec_job_t;
+
+static void *ec_job(void *arg)
+{
+    ec_job_t *J = (ec_job_t *) arg;
+    for (;;) {
+        const uint64_t r = __atomic_fetch_add(J->next, 1, __ATOMIC_RELAXED);
+        if (r >= J->db->n) break;
+        correct_read(J->db, J->g, J->max_edist, r, &J->W);
+    }
+    return 0;
+}
+
+void read_error_correction(sr_db_t *sr_db, scg_t *g, double max_edist, uint32_t err_mer_c, uint32_t max_err_c,
+        uint32_t err_arc_c, double max_arc_f, int n_threads, FILE *fo, int verbose)
+{
+    (void) fo;                                          /* the corrected-read FASTA is a debugging aid of the reference */
+    if (n_threads <= 0) n_threads = 1;
+    if (n_threads > 64) n_threads = 64;
+    find_error_syncmers(g, err_mer_c, max_err_c, err_arc_c, max_arc_f, 1);
+
+    ec_job_t *J = (ec_job_t *) calloc((size_t) n_threads, sizeof(ec_job_t));
+    uint64_t next = 0;
+    for (int t = 0; t < n_threads; ++t) { J[t].db = sr_db; J[t].g = g; J[t].max_edist = max_edist; J[t].next = &next; }
+    if (n_threads == 1) ec_job(&J[0]);
+    else {
+        for (int t = 0; t < n_threads; ++t) pthread_create(&J[t].th, 0, ec_job, &J[t]);
+        for (int t = 0; t < n_threads; ++t) pthread_join(J[t].th, 0);
+    }
+    long stats[11] = {0};
+    for (int t = 0; t < n_threads; ++t) for (int j = 0; j < 11; ++j) stats[j] += J[t].W.stats[j];
+
+    rebuild_syncmer_db(sr_db, g->scm_db);
+
+    fprintf(stderr, "[M::%s] Error Correction Summary Results\n", __func__);
+    fprintf(stderr, "[M::%s] total number of error blocks : %ld\n", __func__, stats[0] + stats[5] + stats[10]);
+    fprintf(stderr, "[M::%s]                - uncorrected : %ld\n", __func__, stats[1] + stats[6]);
+    fprintf(stderr, "[M::%s]                  - corrected : %ld\n", __func__, stats[2] + stats[7]);
+    fprintf(stderr, "[M::%s]             - ambiguous seqs : %ld\n", __func__, stats[3] + stats[8]);
+    fprintf(stderr, "[M::%s]             - ambiguous path : %ld\n", __func__, stats[4] + stats[9]);
+    if (verbose) {
+        fprintf(stderr, "[M::%s] error blocks in the tail end : %ld\n", __func__, stats[0]);
+        fprintf(stderr, "[M::%s]                - uncorrected : %ld\n", __func__, stats[1]);
+        fprintf(stderr, "[M::%s]                  - corrected : %ld\n", __func__, stats[2]);
+        fprintf(stderr, "[M::%s]             - ambiguous seqs : %ld\n", __func__, stats[3]);
+        fprintf(stderr, "[M::%s]             - ambiguous path : %ld\n", __func__, stats[4]);
+        fprintf(stderr, "[M::%s]   error blocks in the middle : %ld\n", __func__, stats[5]);
+        fprintf(stderr, "[M::%s]                - uncorrected : %ld\n", __func__, stats[6]);
+        fprintf(stderr, "[M::%s]                  - corrected : %ld\n", __func__, stats[7]);
+        fprintf(stderr, "[M::%s]             - ambiguous seqs : %ld\n", __func__, stats[8]);
+        fprintf(stderr, "[M::%s]             - ambiguous path : %ld\n", __func__, stats[9]);
+        fprintf(stderr, "[M::%s]      error blocks overlapped : %ld\n", __func__, stats[10]);
+    }
+    for (int t = 0; t < n_threads; ++t) {
+        ec_worker_t *W = &J[t].W;
+        free(W->w.a); free(W->S.cand.s); free(W->S.best_seq.s); free(W->S.path.a); free(W->S.best_path.a);
+        free(W->seq.s); free(W->kk.a); free(W->pp.a);
+    }
+    free(J);
+}

@@ -228,6 +228,14 @@ int ref_write_gfa2(sr_db_t *db, scg_t *g, int hoco_seq, int save_seq, const char
     return 0;
 }
 
+/* read error correction of the reference on its own structures (run_syncasm.c:126), and what it leaves behind */
+void ref_read_ec(sr_db_t *db, scg_t *g, double max_edist, uint32_t err_mer_c, uint32_t max_err_c, uint32_t err_arc_c, double max_arc_f, int n_threads)
+{
+    read_error_correction(db, g, max_edist, err_mer_c, max_err_c, err_arc_c, max_arc_f, n_threads, 0, 0);
+}
+void ref_scm_flags(syncmer_db_t *s, uint8_t *del) { size_t i; for (i = 0; i < s->n; ++i) del[i] = s->a[i].del; }
+uint64_t ref_scm_total_cov(syncmer_db_t *s) { size_t i; uint64_t t = 0; for (i = 0; i < s->n; ++i) t += s->a[i].cov; return t; }
+
 /* the reference's reader alone (sstream_open / sstream_read, the loop of sr_read with its -D rule): every record's
  * name and sequence, flat. Arrays are malloc()ed; the caller frees them. */
 int ref_parse_files(char **files, int n_files, size_t mD, char **bases_out, uint64_t **off_out, char **names_out, uint64_t **name_off_out, uint64_t *n_out)

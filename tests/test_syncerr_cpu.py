@@ -1,0 +1,82 @@
+"""f2 on the CPU: read error correction of the host layer (oatk_b200/host/syncerr_gpu.c) against the reference's
+read_error_correction on identical structures: two pipelines are built by the UNMODIFIED reference (reads ->
+syncmer database -> all-syncmer graph -> hoco consensus), one is corrected by the reference, the other by our
+code, and every per-read array and the rebuilt syncmer database must agree. Needs oracle/_ref/libref.so; no GPU."""
+import ctypes as C
+import numpy as np
+import pytest
+from oatk_b200 import synth
+from pyoracle import pack_reads, count_ambiguous
+
+
+@pytest.fixture(scope="module")
+def host():
+    from oatk_b200.host import build_host
+    try:
+        L = C.CDLL(build_host.build())
+    except OSError as e:
+        pytest.skip("host layer not loadable: %s" % e)
+    L.read_error_correction.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_uint32, C.c_uint32, C.c_uint32, C.c_double, C.c_int, C.c_void_p, C.c_int]
+    L.read_error_correction.restype = None
+    return L
+
+
+def _pipeline(ref, bases, off, k, s):
+    rdb, _ = ref.extract(bases, off, k, s)
+    rscm = ref.collect(rdb)
+    g = ref.graph(rdb, rscm, 0, 0.0)                      # all syncmers: vertex id == syncmer id
+    ref.L.ref_write_gfa2.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_char_p]
+    assert ref.L.ref_write_gfa2(rdb, g, 1, 1, b"/dev/null") == 0      # hoco consensus saved in the graph (run_syncasm.c:118)
+    return rdb, rscm, g
+
+
+def _state(ref, rdb, rscm, n, n_n):
+    f = ref._flat(rdb, n, n_n)
+    S = rscm["_handle"]
+    U = int(ref.L.ref_scm_n(S))
+    ref.L.ref_scm_total_cov.restype = C.c_uint64
+    ref.L.ref_scm_total_cov.argtypes = [C.c_void_p]
+    N = int(ref.L.ref_scm_total_cov(S))
+    d = dict(h=np.zeros(U, np.uint64), s=np.zeros(U, np.uint64), cov=np.zeros(U, np.uint32), occ=np.zeros(N + 1, np.uint64), dele=np.zeros(U, np.uint8))
+    ref.L.ref_scm_flatten(S, d["h"].ctypes.data, d["s"].ctypes.data, d["cov"].ctypes.data, d["occ"].ctypes.data)
+    ref.L.ref_scm_flags.argtypes = [C.c_void_p, C.c_void_p]
+    ref.L.ref_scm_flags(S, d["dele"].ctypes.data)
+    d["occ"] = d["occ"][:N]
+    for key in ("n_scm", "m_pos", "s_mer", "k_mer"):
+        d["read_" + key] = f[key]
+    return d
+
+
+CASES = [
+    # k, s, genome, reads, read length, error rate, seed, min_k_cov, threads
+    (301, 15, 40000, 200, 9000, 0.004, 3, 8, 1),
+    (301, 15, 40000, 200, 9000, 0.004, 3, 8, 4),
+    (1001, 31, 60000, 300, 15000, 0.002, 7, 10, 2),
+    (101, 11, 20000, 250, 4000, 0.01, 11, 6, 3),
+    (63, 9, 15000, 300, 3000, 0.02, 5, 5, 2),
+]
+
+
+@pytest.mark.parametrize("k,s,G,n,L,err,seed,mkc,threads", CASES)
+def test_read_error_correction_matches_reference(host, ref, k, s, G, n, L, err, seed, mkc, threads):
+    reads = synth.hifi_reads(seed, G, n, L, err) + synth.adversarial_reads(3, k, s)
+    bases, off = pack_reads(reads)
+    n_n = count_ambiguous(bases, off)
+    a = _pipeline(ref, bases, off, k, s)
+    b = _pipeline(ref, bases, off, k, s)
+    before = _state(ref, a[0], a[1], len(reads), n_n)
+    ref.L.ref_read_ec.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_uint32, C.c_uint32, C.c_uint32, C.c_double, C.c_int]
+    ref.L.ref_read_ec(a[0], a[2], 0.02, mkc, mkc * 10, mkc, 0.35, threads)
+    host.read_error_correction(b[0], b[2], 0.02, mkc, mkc * 10, mkc, 0.35, threads, None, 0)
+    want = _state(ref, a[0], a[1], len(reads), n_n)
+    got = _state(ref, b[0], b[1], len(reads), n_n)
+    assert not np.array_equal(want["read_k_mer"], before["read_k_mer"]), "the case corrects nothing"
+    for key in want:
+        assert np.array_equal(got[key], want[key]), key
+    # the graphs were pruned the same way (suspect vertices and their arcs)
+    d1, d2 = ref.graph_dump(a[2]), ref.graph_dump(b[2])
+    for f in d1:
+        assert np.array_equal(d1[f], d2[f]), f
+    for x in (a, b):
+        ref.free(g=x[2])
+        ref.free(x[0], x[1])
