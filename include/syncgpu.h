@@ -218,6 +218,14 @@ int sg_debug_set_hash_bits(sg_batch *b, int bits);
 int sg_debug_set_sort_low_bits(sg_batch *b, int low_bits);
 int sg_debug_sort_info(sg_batch *b, uint64_t *repairs, int *fell_back);
 
+/* After read error correction has rewritten the reads' syncmer lists on the host (reference syncerr.c:592-606, 769-817):
+ * replace the batch's per-syncmer arrays (read order: k_mer = id << 1 | corrected, m_pos, s_mer; scm_off = n_reads + 1
+ * offsets) and the per-k-mer coverages, so that the second sr_db_stat (keys = ids, corrected entries skipped in the gap
+ * sum, syncmer.c:896-902) and the arc tally of the final graph run on the corrected lists. sg_count is not valid on
+ * such a batch (the ids exist). */
+int sg_batch_set_lists_host(sg_batch *b, uint64_t n_reads, const uint64_t *scm_off, const uint64_t *k_mer, const uint32_t *m_pos,
+        const uint64_t *s_mer, const uint32_t *cov, uint64_t n_unique);
+
 /* multi-GPU statistics: after the tuple exchange every rank holds a share of the occurrences of an s-mer code,
  * so the s-mer part of sg_stat is per rank. sg_smer_counts_pack exposes the distinct codes of this rank's tuples
  * with their local counts (2 x uint64 per code, device memory owned by the batch, valid until the next sg_stat /

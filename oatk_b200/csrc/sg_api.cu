@@ -138,6 +138,7 @@ static void reset_state(sg_batch *b)
     b->n_adopted = 0;
     b->have_kid_local = false;
     b->pipe_fed = false;
+    b->keys_are_ids = false;
     b->k = b->s = 0;
     b->n_syncmers = 0;
 }

@@ -385,7 +385,7 @@ static int ensure_sorted(sg_batch *b)
     ctx->t_begin(SG_T_SORT);
     const uint64_t hmask = b->hash_bits >= 64 ? ~0ull : ((1ull << b->hash_bits) - 1);
     RS(b->sort_fix, (SORT_FIX_CAP + 2) * 4);
-    const int SORT_LOW_BITS = b->sort_low_bits;              // 24 unless a test moves it (multiple of 8)
+    const int SORT_LOW_BITS = b->keys_are_ids ? 0 : b->sort_low_bits;   // 24 unless a test moves it (multiple of 8); dense ids: all bits
     bool full = b->hash_bits < 64 || SORT_LOW_BITS == 0;     // truncated hashes (tests) collide by design
     for (int attempt = 0; attempt < 2; ++attempt) {
         tuple_init_kernel<<<nblk(N, 256), 256, 0, st>>>(b->t_key(), (uint64_t *) b->skey.p, (uint64_t *) b->sval.p, N, hmask);
@@ -579,10 +579,44 @@ int sg_smer_counts_merge(sg_batch *b, const void *d_pairs, uint64_t n, sg_stat_t
     return SG_OK;
 }
 
+int sg_batch_set_lists_host(sg_batch *b, uint64_t n_reads, const uint64_t *scm_off, const uint64_t *k_mer, const uint32_t *m_pos,
+        const uint64_t *s_mer, const uint32_t *cov, uint64_t n_unique)
+{
+    if (!b || !scm_off || (n_reads && scm_off[n_reads] && (!k_mer || !m_pos || !s_mer)) || (n_unique && !cov)) return SG_E_ARG;
+    if (n_reads > 0xFFFFFFFFull) return SG_E_LIMIT;
+    sg_ctx *ctx = b->ctx;
+    cudaStream_t st = ctx->stream;
+    CK(cudaSetDevice(ctx->device));
+    const uint64_t N = n_reads ? scm_off[n_reads] : 0;
+    RS(b->key, (N + 1) * 8); RS(b->kid, (N + 1) * 8); RS(b->occ, (N + 1) * 8); RS(b->m_pos, (N + 1) * 4); RS(b->s_mer, (N + 1) * 8); RS(b->fp, (N + 1) * 8);
+    RS(b->scm_cov, (n_unique + 1) * 4);
+    std::vector<uint64_t> occ(N);
+    for (uint64_t r = 0; r < n_reads; ++r)
+        for (uint64_t i = scm_off[r], j = 0; i < scm_off[r + 1]; ++i, ++j)
+            occ[i] = (b->sid_base + r) << 32 | j << 1 | (m_pos[i] & 1u);
+    if (N) {
+        CK(cudaMemcpyAsync(b->key.p, k_mer, N * 8, cudaMemcpyHostToDevice, st));     // sr_db_stat keys on k_mer >> 1 = the id (syncmer.c:896)
+        CK(cudaMemcpyAsync(b->kid.p, k_mer, N * 8, cudaMemcpyHostToDevice, st));     // the arc tally drops the low bit as well
+        CK(cudaMemcpyAsync(b->occ.p, occ.data(), N * 8, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(b->m_pos.p, m_pos, N * 4, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(b->s_mer.p, s_mer, N * 8, cudaMemcpyHostToDevice, st));
+        CK(cudaMemsetAsync(b->fp.p, 0, N * 8, st));
+    }
+    if (n_unique) CK(cudaMemcpyAsync(b->scm_cov.p, cov, n_unique * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));
+    b->h2d_bytes += N * 36 + n_unique * 4;
+    b->n_reads = n_reads; b->n_syncmers = N; b->n_unique = n_unique;
+    b->extracted = true; b->counted = true; b->sorted = false; b->adopted = false; b->sizes_known = false; b->have_kid_local = false;
+    b->keys_are_ids = true;
+    b->smer_slots = 0;
+    return SG_OK;
+}
+
 int sg_count(sg_batch *b)
 {
     if (!b) return SG_E_ARG;
     if (!b->extracted) return SG_E_STATE;
+    if (b->keys_are_ids) return SG_E_STATE;                         // the ids exist already (sg_batch_set_lists_host)
     sg_ctx *ctx = b->ctx;
     cudaStream_t st = ctx->stream;
     CK(cudaSetDevice(ctx->device));

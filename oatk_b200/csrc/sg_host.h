@@ -59,6 +59,7 @@ struct sg_batch {
     sg::DevBuf skey, sval, skey_alt, sval_alt, sort_tmp, sort_fix;
     int sort_low_bits = 24;                      // radix passes skip these low hash bits, a repair pass handles them (0: full sort)
     bool sort_fell_back = false;
+    bool keys_are_ids = false;                   // sg_batch_set_lists_host: key[] holds id << 1 | corrected, not hashes
     uint64_t n_sort_repairs = 0;                 // out-of-order pairs the repair pass saw
     sg::DevBuf socc, ssmer, flags, ids, ids_tmp, differs, cls, starts, stat_dev, stat_dev2, skey2, sval2;
     bool sorted = false;

@@ -369,6 +369,7 @@ static int pipe_run(sg_pipe *p, const char *bases, const uint64_t *off, uint64_t
     M->n_syncmers = tot.scm; M->n_amb_total = tot.amb; M->n_lrl_total = tot.lrl; M->hoco_bases = tot.hoco;
     M->extracted = true; M->counted = M->sorted = M->adopted = M->sizes_known = M->have_kid_local = false;
     M->pipe_fed = true;
+    M->keys_are_ids = false;
     sizes->n_reads = n_reads; sizes->n_syncmers = tot.scm; sizes->hoco_bases = tot.hoco;
     sizes->hoco_s_bytes = tot.hs; sizes->ho_rl_bytes = tot.rl; sizes->n_ambiguous = tot.amb; sizes->n_long_runs = tot.lrl;
     (void) mctx;

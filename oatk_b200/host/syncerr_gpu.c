@@ -415,6 +415,7 @@ void read_error_correction(sr_db_t *sr_db, scg_t *g, double max_edist, uint32_t 
     for (int t = 0; t < n_threads; ++t) for (int j = 0; j < 11; ++j) stats[j] += J[t].W.stats[j];
 
     rebuild_syncmer_db(sr_db, g->scm_db);
+    oatk_gpu_update_lists(sr_db, g->scm_db);            /* the device-resident lists follow the host's */
 
     fprintf(stderr, "[M::%s] Error Correction Summary Results\n", __func__);
     fprintf(stderr, "[M::%s] total number of error blocks : %ld\n", __func__, stats[0] + stats[5] + stats[10]);

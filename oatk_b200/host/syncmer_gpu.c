@@ -311,6 +311,36 @@ int syncmer_graph_arcs(sr_db_t *sr_db, syncmer_db_t *scm_db, uint32_t min_k_cov,
     return sg_arcs_download(b, *arcs4);
 }
 
+/* read error correction rewrote the syncmer lists of the reads and the coverages of the database on the host: bring
+ * the device-resident batch behind this sr_db_t up to date, so that the second sr_db_stat and the arc tally of the
+ * final graph (both on the device) see the corrected lists. A database that was not produced by sr_read_mem has no
+ * batch and nothing to refresh. */
+int oatk_gpu_update_lists(sr_db_t *sr_db, syncmer_db_t *scm_db)
+{
+    sg_batch *b = batch_of(sr_db, 0);
+    uint64_t i, N = 0, *off, *km, *sm;
+    uint32_t *mp, *cov;
+    int rc;
+    if (!b) return 0;
+    off = (uint64_t *) malloc(8 * (sr_db->n + 1));
+    off[0] = 0;
+    for (i = 0; i < sr_db->n; ++i) { N += sr_db->a[i].n; off[i + 1] = N; }
+    km = (uint64_t *) malloc(8 * (N + 1)); sm = (uint64_t *) malloc(8 * (N + 1)); mp = (uint32_t *) malloc(4 * (N + 1));
+    cov = (uint32_t *) malloc(4 * (scm_db->n + 1));
+    for (i = 0; i < sr_db->n; ++i) {
+        const sr_t *r = &sr_db->a[i];
+        if (!r->n) continue;
+        memcpy(km + off[i], r->k_mer, 8 * (size_t) r->n);
+        memcpy(sm + off[i], r->s_mer, 8 * (size_t) r->n);
+        memcpy(mp + off[i], r->m_pos, 4 * (size_t) r->n);
+    }
+    for (i = 0; i < scm_db->n; ++i) cov[i] = scm_db->a[i].cov;
+    rc = sg_batch_set_lists_host(b, sr_db->n, off, km, mp, sm, cov, scm_db->n);
+    if (rc != SG_OK) fprintf(stderr, "[E::%s] %s: %s\n", __func__, sg_strerror(rc), sg_last_error(ctx_of(sr_db)));
+    free(off); free(km); free(sm); free(mp); free(cov);
+    return rc;
+}
+
 void sr_destroy(sr_t *sr)
 {
     if (!sr) return;

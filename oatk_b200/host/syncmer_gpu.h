@@ -99,6 +99,8 @@ void print_hoco_seq(sr_t *sr, FILE *fo);
 int syncmer_graph_arcs(sr_db_t *sr_db, syncmer_db_t *scm_db, uint32_t min_k_cov, double min_a_cov_f, uint64_t **arcs4, uint64_t *n_arcs);
 
 /* which GPU the layer uses (default 0), and its release */
+/* after read_error_correction (called by it): refresh the device-resident batch from the corrected host lists */
+int oatk_gpu_update_lists(sr_db_t *sr_db, syncmer_db_t *scm_db);
 int oatk_gpu_set_device(int device);
 void oatk_gpu_shutdown(void);
 

@@ -61,7 +61,7 @@ SYMBOLS = [
     "sg_batch_set_sid_base", "sg_extract", "sg_extract_sizes", "sg_extract_download",
     "sg_stat", "sg_count", "sg_count_sizes", "sg_count_download", "sg_arcs", "sg_arcs_download",
     "sg_tuples_partition", "sg_tuples_adopt", "sg_debug_set_hash_bits", "sg_debug_set_sort_low_bits", "sg_debug_sort_info", "sg_batch_buffer",
-    "sg_ids_pack", "sg_ids_scatter", "sg_batch_set_exact_verify", "sg_smer_counts_pack", "sg_smer_counts_merge",
+    "sg_ids_pack", "sg_ids_scatter", "sg_batch_set_exact_verify", "sg_smer_counts_pack", "sg_smer_counts_merge", "sg_batch_set_lists_host",
     "sg_pipe_create", "sg_pipe_destroy", "sg_pipe_run_host", "sg_pipe_run_host_cb", "sg_pipe_master", "sg_pipe_ctx", "sg_pipe_last_error", "sg_pipe_launches",
 ]
 

@@ -254,3 +254,58 @@ def test_sr_read_files_matches_reference(host, ref):
         host.sr_db_clean(C.byref(db2))
         host.sr_db_clean(C.byref(db))
         ref.free(rdb)
+
+
+@pytest.mark.parametrize("k,s,G,n,L,err,mkc", [(1001, 31, 60000, 300, 15000, 0.002, 10), (301, 15, 40000, 240, 9000, 0.004, 8)])
+def test_default_pipeline_with_error_correction(host, ref, k, s, G, n, L, err, mkc):
+    """run_syncasm.c:79-166 with read error correction on (the default): reads -> statistics -> database -> all-syncmer
+    graph -> hoco consensus -> read error correction -> statistics again -> final graph -> unitigs -> GFA, through the host
+    layer (device: extraction, counting, both statistics passes, both arc tallies) and through the unmodified reference"""
+    for f, a in (("make_syncmer_graph", [C.c_void_p, C.c_void_p, C.c_uint32, C.c_double]), ("process_mergeable_unitigs", [C.c_void_p]),
+                 ("scg_destroy", [C.c_void_p]), ("scg_consensus", [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+                 ("read_error_correction", [C.c_void_p, C.c_void_p, C.c_double, C.c_uint32, C.c_uint32, C.c_uint32, C.c_double, C.c_int, C.c_void_p, C.c_int])):
+        getattr(host, f).argtypes = a
+    host.make_syncmer_graph.restype = C.c_void_p
+    host.scg_consensus.restype = None
+    host.read_error_correction.restype = None
+    reads = synth.hifi_reads(13, G, n, L, err) + synth.adversarial_reads(3, k, s)
+    bases, off = pack_reads(reads)
+    # ---- ours
+    db = SrDb()
+    host.sr_db_init(C.byref(db), k, s)
+    assert host.sr_read_mem(C.byref(db), bases.ctypes.data, off.ctypes.data, None, len(reads)) == 0
+    stat1 = stat_lines(host.sr_db_stat, C.addressof(db))
+    scm = host.collect_syncmer_from_reads(C.byref(db))
+    g = host.make_syncmer_graph(C.byref(db), scm, 0, 0.0)
+    host.scg_consensus(C.byref(db), g, 1, 1, None)
+    host.read_error_correction(C.byref(db), g, 0.02, mkc, mkc * 10, mkc, 0.35, 4, None, 0)
+    stat2 = stat_lines(host.sr_db_stat, C.addressof(db))
+    host.scg_destroy(g)
+    g = host.make_syncmer_graph(C.byref(db), scm, mkc, 0.35)
+    assert g
+    host.process_mergeable_unitigs(g)
+    mine_gfa = gfa_text(host, C.addressof(db), g)
+    # ---- the reference
+    rdb, _ = ref.extract(bases, off, k, s)
+    ref.L.sr_db_stat.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    rstat1 = stat_lines(ref.L.sr_db_stat, rdb)
+    rscm = ref.collect(rdb)
+    rg = ref.graph(rdb, rscm, 0, 0.0)
+    ref.L.ref_write_gfa2.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_char_p]
+    assert ref.L.ref_write_gfa2(rdb, rg, 1, 1, b"/dev/null") == 0
+    ref.L.ref_read_ec.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_uint32, C.c_uint32, C.c_uint32, C.c_double, C.c_int]
+    ref.L.ref_read_ec(rdb, rg, 0.02, mkc, mkc * 10, mkc, 0.35, 2)
+    rstat2 = stat_lines(ref.L.sr_db_stat, rdb)
+    ref.free(g=rg)
+    rg = ref.graph(rdb, rscm, mkc, 0.35)
+    ref.unitig(rg)
+    want_gfa = ref_gfa_text(ref, rdb, rg)
+    assert stat1 == rstat1
+    assert stat2 == rstat2 and stat2 != stat1          # error correction changed the counts, and both sides agree on how
+    assert mine_gfa.count(b"\nS\t") > 0
+    assert mine_gfa == want_gfa, first_diff(mine_gfa, want_gfa)
+    host.scg_destroy(g)
+    host.syncmer_db_destroy(scm)
+    host.sr_db_clean(C.byref(db))
+    ref.free(g=rg)
+    ref.free(rdb, rscm)
