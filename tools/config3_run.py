@@ -39,6 +39,7 @@ def main():
     ap.add_argument("--c", type=int, default=30)
     ap.add_argument("--a", type=float, default=0.35)
     ap.add_argument("--threads", type=int, default=os.cpu_count() or 1)
+    ap.add_argument("--ec", action="store_true", help="with read error correction (the reference's default); without: --no-read-ec")
     args = ap.parse_args()
 
     reads = synth.hifi_reads(2, args.genome, args.reads, args.len, args.err)
@@ -64,6 +65,8 @@ def main():
     H.scg_consensus.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     H.scg_consensus.restype = None
     H.scg_destroy.argtypes = [C.c_void_p]
+    H.read_error_correction.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_uint32, C.c_uint32, C.c_uint32, C.c_double, C.c_int, C.c_void_p, C.c_int]
+    H.read_error_correction.restype = None
     H.syncmer_db_destroy.argtypes = [C.c_void_p]
     H.sr_db_clean.argtypes = [C.c_void_p]
 
@@ -91,6 +94,20 @@ def main():
         scm = H.collect_syncmer_from_reads(C.byref(db))
         t["collect_s"] = time.perf_counter() - t0
         assert scm
+        if args.ec:
+            t0 = time.perf_counter()
+            g = H.make_syncmer_graph(C.byref(db), scm, 0, 0.0)
+            H.scg_consensus(C.byref(db), g, 1, 1, None)
+            t["ec_graph_consensus_s"] = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            H.read_error_correction(C.byref(db), g, 0.02, args.c, args.c * 10, args.c, args.a, args.threads, None, 0)
+            t["read_ec_s"] = time.perf_counter() - t0
+            nul = libc.fopen(b"/dev/null", b"w")
+            t0 = time.perf_counter()
+            H.sr_db_stat(C.byref(db), nul, 0)
+            t["sr_db_stat2_s"] = time.perf_counter() - t0
+            libc.fclose(nul)
+            H.scg_destroy(g)
         t0 = time.perf_counter()
         g = H.make_syncmer_graph(C.byref(db), scm, args.c, args.a)
         t["graph_s"] = time.perf_counter() - t0
@@ -129,6 +146,22 @@ def main():
     t0 = time.perf_counter()
     rscm = R.L.ref_collect(rdb)
     t_ref["collect_s"] = time.perf_counter() - t0
+    if args.ec:
+        R.L.ref_write_gfa2.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_char_p]
+        R.L.ref_read_ec.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_uint32, C.c_uint32, C.c_uint32, C.c_double, C.c_int]
+        t0 = time.perf_counter()
+        g = R.L.ref_make_graph(rdb, rscm, 0, 0.0)
+        assert R.L.ref_write_gfa2(rdb, g, 1, 1, b"/dev/null") == 0
+        t_ref["ec_graph_consensus_s"] = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        R.L.ref_read_ec(rdb, g, 0.02, args.c, args.c * 10, args.c, args.a, args.threads)
+        t_ref["read_ec_s"] = time.perf_counter() - t0
+        nul = libc.fopen(b"/dev/null", b"w")
+        t0 = time.perf_counter()
+        R.L.sr_db_stat(rdb, nul, 0)
+        t_ref["sr_db_stat2_s"] = time.perf_counter() - t0
+        libc.fclose(nul)
+        R.L.ref_scg_free(g)
     t0 = time.perf_counter()
     g = R.L.ref_make_graph(rdb, rscm, args.c, args.a)
     t_ref["graph_s"] = time.perf_counter() - t0
@@ -142,8 +175,8 @@ def main():
     t_ref["total_s"] = sum(t_ref.values())
 
     a, b = open(p_ours, "rb").read(), open(p_ref, "rb").read()
-    line = {"config": "BASELINE.json configs[2] (--no-read-ec): %d x %d b reads of a %d b genome, k=%d s=%d -c %d -a %.2f" % (
-                args.reads, args.len, args.genome, args.k, args.s, args.c, args.a),
+    line = {"config": "BASELINE.json configs[2] (%s): %d x %d b reads of a %d b genome, k=%d s=%d -c %d -a %.2f" % (
+                "default: with read error correction" if args.ec else "--no-read-ec", args.reads, args.len, args.genome, args.k, args.s, args.c, args.a),
             "raw_bases": total, "gfa_identical": a == b, "gfa_md5": hashlib.md5(a).hexdigest(), "gfa_md5_reference": hashlib.md5(b).hexdigest(),
             "gfa_S_lines": a.count(b"\nS\t"), "gfa_L_lines": a.count(b"\nL\t"), "gfa_bytes": len(a),
             "ours_s": t_ours, "reference_s": t_ref, "reference_threads": args.threads,
