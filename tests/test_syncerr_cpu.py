@@ -80,3 +80,33 @@ def test_read_error_correction_matches_reference(host, ref, k, s, G, n, L, err, 
     for x in (a, b):
         ref.free(g=x[2])
         ref.free(x[0], x[1])
+
+
+def test_randomised_inputs_with_repeats(host, ref):
+    """random genome sizes, read lengths, error rates and coverage thresholds, half of the cases with a planted repeat
+    (two contexts around one shared segment: alternative paths, ambiguous blocks)"""
+    rng = np.random.default_rng(0)
+    ref.L.ref_read_ec.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_uint32, C.c_uint32, C.c_uint32, C.c_double, C.c_int]
+    bad = []
+    for it in range(10):
+        k, s = [(301, 15), (101, 11), (63, 9), (501, 31), (41, 7)][it % 5]
+        G, L, n = int(rng.integers(8000, 50000)), int(rng.integers(2000, 12000)), int(rng.integers(60, 300))
+        err, mkc = float(rng.choice([0.002, 0.005, 0.01, 0.02])), int(rng.integers(3, 12))
+        reads = synth.hifi_reads(100 + it, G, n, L, err)
+        if it % 2:
+            rep = reads[0][:min(len(reads[0]), 3000)]
+            reads += [rep + synth.hifi_reads(500 + it, 5000, 1, 3000, 0)[0] for _ in range(mkc + 2)]
+            reads += [synth.hifi_reads(600 + it, 5000, 1, 3000, 0)[0] + rep for _ in range(mkc + 2)]
+        bases, off = pack_reads(reads)
+        n_n = count_ambiguous(bases, off)
+        a, b = _pipeline(ref, bases, off, k, s), _pipeline(ref, bases, off, k, s)
+        ref.L.ref_read_ec(a[0], a[2], 0.02, mkc, mkc * 10, mkc, 0.35, 2)
+        host.read_error_correction(b[0], b[2], 0.02, mkc, mkc * 10, mkc, 0.35, 3, None, 0)
+        want, got = _state(ref, a[0], a[1], len(reads), n_n), _state(ref, b[0], b[1], len(reads), n_n)
+        diff = [x for x in want if not np.array_equal(got[x], want[x])]
+        if diff:
+            bad.append((it, k, s, G, L, n, err, mkc, diff))
+        for x in (a, b):
+            ref.free(g=x[2])
+            ref.free(x[0], x[1])
+    assert not bad, bad
