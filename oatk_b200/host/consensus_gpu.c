@@ -44,8 +44,10 @@ void oatk_consensus_debug_counts(uint64_t *out) { out[0] = dbg_vote_ties; out[1]
 typedef struct { int key, val; } ovl_cell_t;
 typedef struct {
     uint32_t bits, count;
-    uint32_t *used;            /* one bit per bucket */
-    ovl_cell_t *cell;          /* NULL until the first insertion */
+    int live;                  /* 0: logically no table yet (khashl's keys == NULL), whatever storage is kept below */
+    uint32_t alloc;            /* buckets the storage below can hold */
+    uint32_t *used, *spare;    /* one bit per bucket; spare is the zeroed bitmap the next growth fills */
+    ovl_cell_t *cell;
 } ovl_tab_t;
 
 static inline uint32_t ot_words(uint32_t n_buckets) { return n_buckets < 32 ? 1 : n_buckets >> 5; }
@@ -55,27 +57,42 @@ static inline void ot_unset(uint32_t *u, uint32_t i) { u[i >> 5] &= ~(1u << (i &
 /* khashl.h:82 with the identity hash the reference gives this map (syncasm.c:63) */
 static inline uint32_t ot_bucket(int key, uint32_t bits) { return (uint32_t) key * 2654435769u >> (32 - bits); }
 
+/* kh_clear: same capacity, no entries */
 static void ot_clear(ovl_tab_t *t)
 {
-    if (t->used) { memset(t->used, 0, ot_words(1u << t->bits) * sizeof(uint32_t)); t->count = 0; }
+    if (t->live) { memset(t->used, 0, ot_words(1u << t->bits) * sizeof(uint32_t)); t->count = 0; }
 }
+/* a table as kh_init leaves it (no buckets at all), keeping the storage for the next use */
+static void ot_fresh(ovl_tab_t *t) { t->live = 0; t->bits = 0; t->count = 0; }
 
-static void ot_free(ovl_tab_t *t) { free(t->used); free(t->cell); memset(t, 0, sizeof(*t)); }
+static void ot_free(ovl_tab_t *t) { free(t->used); free(t->spare); free(t->cell); memset(t, 0, sizeof(*t)); }
+
+static void ot_reserve(ovl_tab_t *t, uint32_t buckets)
+{
+    if (buckets <= t->alloc) return;
+    uint32_t *u = (uint32_t *) calloc(ot_words(buckets), sizeof(uint32_t)), *sp = (uint32_t *) calloc(ot_words(buckets), sizeof(uint32_t));
+    if (t->live) memcpy(u, t->used, ot_words(1u << t->bits) * sizeof(uint32_t));
+    free(t->used); free(t->spare);
+    t->used = u; t->spare = sp;
+    t->cell = (ovl_cell_t *) realloc(t->cell, buckets * sizeof(ovl_cell_t));
+    t->alloc = buckets;
+}
 
 /* growth to the next power of two >= want (at least 4), moving the cells inside the same array the
  * way khashl does it (khashl.h:144-187): walk the old buckets in order, drop each cell at its new
  * home and carry on with whatever old cell was sitting there */
 static void ot_grow(ovl_tab_t *t, uint32_t want)
 {
-    uint32_t j = 0, x = want, old_n = t->cell ? 1u << t->bits : 0u, new_bits, new_n, mask;
+    uint32_t j = 0, x = want, old_n = t->live ? 1u << t->bits : 0u, new_bits, new_n, mask;
     while ((x >>= 1) != 0) ++j;
     if (want & (want - 1)) ++j;
     new_bits = j > 2 ? j : 2;
     new_n = 1u << new_bits;
     if (t->count > (new_n >> 1) + (new_n >> 2)) return;
     if (old_n) __atomic_fetch_add(&dbg_table_growths, 1, __ATOMIC_RELAXED);
-    uint32_t *nu = (uint32_t *) calloc(ot_words(new_n), sizeof(uint32_t));
-    if (old_n < new_n) t->cell = (ovl_cell_t *) realloc(t->cell, new_n * sizeof(ovl_cell_t));
+    ot_reserve(t, new_n);
+    uint32_t *nu = t->spare;
+    memset(nu, 0, ot_words(new_n) * sizeof(uint32_t));
     mask = new_n - 1;
     for (j = 0; j != old_n; ++j) {
         if (!ot_used(t->used, j)) continue;
@@ -91,14 +108,13 @@ static void ot_grow(ovl_tab_t *t, uint32_t want)
             } else { t->cell[i] = c; break; }
         }
     }
-    if (old_n > new_n) t->cell = (ovl_cell_t *) realloc(t->cell, new_n * sizeof(ovl_cell_t));
-    free(t->used);
-    t->used = nu; t->bits = new_bits;
+    t->spare = t->used; t->used = nu;
+    t->bits = new_bits; t->live = 1;
 }
 
 static void ot_count(ovl_tab_t *t, int key)
 {
-    uint32_t n = t->cell ? 1u << t->bits : 0u;
+    uint32_t n = t->live ? 1u << t->bits : 0u;
     if (t->count >= (n >> 1) + (n >> 2)) { ot_grow(t, n + 1); n = 1u << t->bits; }
     const uint32_t mask = n - 1;
     uint32_t i = ot_bucket(key, t->bits), first = i;
@@ -111,7 +127,7 @@ static void ot_count(ovl_tab_t *t, int key)
 static int ot_mode(const ovl_tab_t *t)
 {
     int best = 0, best_n = 0, tied = 0;
-    if (!t->cell) return 0;
+    if (!t->live) return 0;
     for (uint32_t i = 0, n = 1u << t->bits; i < n; ++i) {
         if (!ot_used(t->used, i)) continue;
         if (t->cell[i].val > best_n) { best_n = t->cell[i].val; best = t->cell[i].key; tied = 0; }
@@ -132,9 +148,10 @@ static inline int64_t occ_start(const sr_db_t *db, uint64_t occ)
 }
 
 /* m1 (strand rc1) is followed by m2 (strand rc2): hoco distance between their starts */
-static int neighbour_offset(const sr_db_t *db, const syncmer_t *m1, uint64_t rc1, const syncmer_t *m2, uint64_t rc2, ovl_tab_t *shared)
+/* `t` keeps its capacity from call to call when `carry` is set (one unitig), else it starts as an empty table */
+static int neighbour_offset(const sr_db_t *db, const syncmer_t *m1, uint64_t rc1, const syncmer_t *m2, uint64_t rc2, ovl_tab_t *t, int carry)
 {
-    ovl_tab_t local = {0, 0, 0, 0}, *t = shared ? shared : &local;
+    if (!carry) ot_fresh(t);
     const uint64_t *o1 = m1->m_pos, *o2 = m2->m_pos;
     const uint64_t n1 = m1->cov, n2 = m2->cov;
     assert(n1 > 0 && n2 > 0);
@@ -152,9 +169,7 @@ static int neighbour_offset(const sr_db_t *db, const syncmer_t *m1, uint64_t rc1
             else if (i1 + 1 == i2 && s1 == rc1 && s2 == rc2) ot_count(t, (int) (occ_start(db, o2[b]) - occ_start(db, o1[a])));
         }
     }
-    const int d = ot_mode(t);
-    if (!shared) ot_free(&local);
-    return d;
+    return ot_mode(t);
 }
 
 /* ---------------------------------------------------------------- growing text buffer */
@@ -166,14 +181,22 @@ static inline void txt_put(txt_t *t, int c)
 }
 
 /* ---------------------------------------------------------------- bases of one syncmer */
+static inline void txt_room(txt_t *t, size_t extra)
+{
+    if (t->l + extra + 1 > t->m) { t->m = (t->l + extra + 1) * 2 + 256; t->s = (char *) realloc(t->s, t->m); }
+}
+
+/* out == NULL: only the length is wanted (arc overlaps) */
 static int64_t syncmer_text(const sr_db_t *db, const syncmer_t *m, int rev, int64_t from, txt_t *out, int hoco_only)
 {
     const int w = db->k;
     assert(from < w);
     int64_t written = from < 0 ? -from : 0;
-    for (; from < 0; ++from) txt_put(out, 'N');
+    if (out) for (int64_t i = from; i < 0; ++i) txt_put(out, 'N');
+    if (from < 0) from = 0;
     const uint64_t l = (uint64_t) (w - from);
     written += (int64_t) l;
+    if (hoco_only && !out) return written;              /* one character per hoco base whatever the copies say */
 
     /* the first occurrence that read error correction left alone supplies the bases */
     uint32_t i;
@@ -188,15 +211,14 @@ static int64_t syncmer_text(const sr_db_t *db, const syncmer_t *m, int rev, int6
         break;
     }
     if (i == m->cov) {                                 /* every copy was corrected away: N (reference :925-931) */
-        for (uint64_t j = 0; j < l; ++j) txt_put(out, 'N');
+        if (out) { txt_room(out, l); memset(out->s + out->l, 'N', l); out->l += l; }
         return written;
     }
     if (!r) p += (uint64_t) from;
-    uint8_t *code = (uint8_t *) malloc(l);
-    get_kmer_seq(s->hoco_s, (uint32_t) p, (int) l, (uint32_t) r, code);
     if (hoco_only) {
-        for (uint64_t j = 0; j < l; ++j) txt_put(out, char_nt4_table[code[j]]);
-        free(code);
+        txt_room(out, l);
+        get_kmer_dna_seq(s->hoco_s, (uint32_t) p, (int) l, (uint32_t) r, out->s + out->l);
+        out->l += l;
         return written;
     }
     /* summed run lengths - 1 per hoco base over the uncorrected occurrences, in the syncmer's orientation */
@@ -211,16 +233,24 @@ static int64_t syncmer_text(const sr_db_t *db, const syncmer_t *m, int rev, int6
         if (!rr) q += (uint64_t) from;
         uint32_t side = 0;                             /* entries of the long-run list in front of q */
         if (t->ho_l_rl) for (uint64_t j = 0; j < q; ++j) side += t->ho_rl[j] == 255;
-        for (uint64_t j = 0; j < l; ++j) {
-            uint32_t rl = t->ho_rl[q + j];
-            if (rl == 255) rl = t->ho_l_rl[side++];
-            tot[rr ? l - 1 - j : j] += rl;
-        }
+        const uint8_t *rl8 = t->ho_rl + q;
+        if (rr) for (uint64_t j = 0; j < l; ++j) { uint32_t rl = rl8[j]; if (rl == 255) rl = t->ho_l_rl[side++]; tot[l - 1 - j] += rl; }
+        else for (uint64_t j = 0; j < l; ++j) { uint32_t rl = rl8[j]; if (rl == 255) rl = t->ho_l_rl[side++]; tot[j] += rl; }
         ++copies;
     }
+    if (!out) {
+        for (uint64_t j = 0; j < l; ++j) written += lround((double) tot[j] / copies);
+        free(tot);
+        return written;
+    }
+    uint8_t *code = (uint8_t *) malloc(l);
+    get_kmer_seq(s->hoco_s, (uint32_t) p, (int) l, (uint32_t) r, code);
     for (uint64_t j = 0; j < l; ++j) {
         const long extra = lround((double) tot[j] / copies);
-        for (long e = 0; e <= extra; ++e) txt_put(out, char_nt4_table[code[j]]);
+        const char c = char_nt4_table[code[j]];
+        txt_room(out, (size_t) extra + 1);
+        memset(out->s + out->l, c, (size_t) extra + 1);
+        out->l += (size_t) extra + 1;
         written += extra;
     }
     free(tot);
@@ -229,15 +259,15 @@ static int64_t syncmer_text(const sr_db_t *db, const syncmer_t *m, int rev, int6
 }
 
 /* ---------------------------------------------------------------- bases of a chain of syncmers */
-static int64_t chain_text(const sr_db_t *db, const uint64_t *v, uint64_t n, const syncmer_t *scm, txt_t *out, int hoco_only)
+static int64_t chain_text(const sr_db_t *db, const uint64_t *v, uint64_t n, const syncmer_t *scm, txt_t *out, int hoco_only, ovl_tab_t *tab)
 {
     if (n == 0) return 0;
     const int w = db->k;
-    ovl_tab_t tab = {0, 0, 0, 0};                      /* one table per chain: its capacity carries over (reference :1011-1041) */
+    ot_fresh(tab);                                      /* one table per chain: its capacity carries over inside it (reference :1011-1041) */
     int64_t *pos = (int64_t *) malloc(n * sizeof(int64_t));
     pos[0] = 0;
     for (uint64_t i = 1; i < n; ++i)
-        pos[i] = pos[i - 1] + neighbour_offset(db, &scm[v[i - 1] >> 1], v[i - 1] & 1, &scm[v[i] >> 1], v[i] & 1, &tab);
+        pos[i] = pos[i - 1] + neighbour_offset(db, &scm[v[i - 1] >> 1], v[i - 1] & 1, &scm[v[i] >> 1], v[i] & 1, tab, 1);
     int64_t end = 0, len = 0;
     for (uint64_t i = 0; i < n; ++i) {
         while (i + 1 < n && pos[i + 1] <= end) ++i;     /* the next one still starts inside what is written: skip ahead */
@@ -245,7 +275,6 @@ static int64_t chain_text(const sr_db_t *db, const uint64_t *v, uint64_t n, cons
         end = pos[i] + w;
     }
     free(pos);
-    ot_free(&tab);
     assert(len >= 0 && (uint64_t) len == out->l);
     return len;
 }
@@ -319,7 +348,7 @@ typedef struct {
     int phase;
 } cons_job_t;
 
-static int64_t arc_overlap(cons_job_t *J, const asmg_arc_t *a, txt_t *t)
+static int64_t arc_overlap(cons_job_t *J, const asmg_arc_t *a, txt_t *t, ovl_tab_t *tab)
 {
     const sr_db_t *db = J->db;
     const syncmer_t *scm = J->scg->scm_db->a;
@@ -329,7 +358,7 @@ static int64_t arc_overlap(cons_job_t *J, const asmg_arc_t *a, txt_t *t)
     if (a->ln > 0) {                                    /* the two unitigs share ln syncmers: their length in bases */
         const asmg_vtx_t *u = &G->vtx[a->v >> 1];
         t->l = 0;
-        l = chain_text(db, (a->v & 1) ? u->a : &u->a[u->n - a->ln], a->ln, scm, t, J->hoco);
+        l = chain_text(db, (a->v & 1) ? u->a : &u->a[u->n - a->ln], a->ln, scm, t, J->hoco, tab);
     } else {                                            /* they abut: overlap of the two end syncmers */
         const asmg_vtx_t *u = &G->vtx[a->v >> 1];
         uint64_t z = a->v & 1;
@@ -337,11 +366,9 @@ static int64_t arc_overlap(cons_job_t *J, const asmg_arc_t *a, txt_t *t)
         u = &G->vtx[a->w >> 1];
         z = a->w & 1;
         const uint64_t y = u->a[(u->n - 1) * z] ^ z;
-        l = neighbour_offset(db, &scm[x >> 1], x & 1, &scm[y >> 1], y & 1, 0);
-        if (l < w) {
-            t->l = 0;
-            l = syncmer_text(db, &scm[x >> 1], (int) (x & 1), l, t, J->hoco);
-        } else l = 0;
+        l = neighbour_offset(db, &scm[x >> 1], x & 1, &scm[y >> 1], y & 1, tab, 0);
+        if (l < w) l = syncmer_text(db, &scm[x >> 1], (int) (x & 1), l, 0, J->hoco);    /* length only */
+        else l = 0;
     }
     return l;
 }
@@ -351,6 +378,8 @@ static void *cons_worker(void *arg)
     cons_job_t *J = (cons_job_t *) arg;
     asmg_t *G = J->scg->utg_asmg;
     txt_t t = {0, 0, 0};
+    ovl_tab_t tab;
+    memset(&tab, 0, sizeof(tab));
     for (;;) {
         const uint64_t i = __atomic_fetch_add(&J->next, 1, __ATOMIC_RELAXED);
         if (J->phase == 0) {
@@ -358,7 +387,7 @@ static void *cons_worker(void *arg)
             asmg_vtx_t *u = &G->vtx[i];
             if (u->del) continue;
             t.l = 0;
-            J->len[i] = chain_text(J->db, u->a, u->n, J->scg->scm_db->a, &t, J->hoco);
+            J->len[i] = chain_text(J->db, u->a, u->n, J->scg->scm_db->a, &t, J->hoco, &tab);
             J->cov[i] = u->cov ? u->cov : unitig_coverage(J->scg, u);
             J->text[i] = (char *) malloc((size_t) J->len[i] + 1);
             memcpy(J->text[i], t.s, (size_t) J->len[i]);
@@ -367,10 +396,11 @@ static void *cons_worker(void *arg)
             if (i >= G->n_arc) break;
             const asmg_arc_t *a = &G->arc[i];
             if (a->del || a->comp) continue;
-            J->ovl[i] = arc_overlap(J, a, &t);
+            J->ovl[i] = arc_overlap(J, a, &t, &tab);
         }
     }
     free(t.s);
+    ot_free(&tab);
     return 0;
 }
 

@@ -61,6 +61,12 @@ static inline int32_t wave_slide(const wave_t *w, const wdiag_t *p)
     int32_t k = p->k;
     const int32_t last = (w->ql - p->d < w->tl ? w->ql - p->d : w->tl) - 1;
     const char *t = w->ts + 1, *q = w->qs + p->d + 1;
+    while (k + 8 <= last) {                             /* eight bases per comparison while both strings have them */
+        uint64_t x, y;
+        memcpy(&x, t + k, 8); memcpy(&y, q + k, 8);
+        if (x != y) return k + (__builtin_ctzll(x ^ y) >> 3);
+        k += 8;
+    }
     while (k < last && t[k] == q[k]) ++k;
     return k;
 }
@@ -153,6 +159,7 @@ typedef struct {
     int status, leaves, best, second;                   /* best / second best score so far */
     str_t cand, best_seq;
     v64_t path, best_path;
+    wdiag_t *stash; size_t stash_n, stash_m;            /* wavefronts of the levels above, stacked */
 } search_t;
 
 static void search_from(const asmg_t *G, search_t *S, uint64_t sink, wave_t *w)
@@ -163,8 +170,10 @@ static void search_from(const asmg_t *G, search_t *S, uint64_t sink, wave_t *w)
     const asmg_arc_t *arc = &G->arc[G->idx_p[from]];
     const uint64_t n_arc = G->idx_n[from];
     const int32_t t_end0 = w->t_end, q_end0 = w->q_end, s0 = w->score;
-    wdiag_t *saved = (wdiag_t *) malloc((d0 ? d0 : 1) * sizeof(wdiag_t));
-    memcpy(saved, w->a, d0 * sizeof(wdiag_t));
+    const size_t stash0 = S->stash_n;
+    if (S->stash_n + d0 > S->stash_m) { S->stash_m = (S->stash_n + d0) * 2 + 64; S->stash = (wdiag_t *) realloc(S->stash, S->stash_m * sizeof(wdiag_t)); }
+    memcpy(S->stash + stash0, w->a, d0 * sizeof(wdiag_t));
+    S->stash_n += d0;
 
     for (uint64_t i = 0; i < n_arc; ++i) {
         const asmg_arc_t *e = &arc[i];
@@ -204,9 +213,9 @@ static void search_from(const asmg_t *G, search_t *S, uint64_t sink, wave_t *w)
         /* back to the state in front of this arc */
         S->path.n = n0; S->cand.l = l0;
         w->t_end = t_end0; w->q_end = q_end0; w->score = s0; w->n = d0;
-        memcpy(w->a, saved, d0 * sizeof(wdiag_t));
+        memcpy(w->a, S->stash + stash0, d0 * sizeof(wdiag_t));    /* (the stash may have moved: always through S) */
     }
-    free(saved);
+    S->stash_n = stash0;
 }
 
 /* ---------------------------------------------------------------- one read */
@@ -438,7 +447,7 @@ void read_error_correction(sr_db_t *sr_db, scg_t *g, double max_edist, uint32_t 
     }
     for (int t = 0; t < n_threads; ++t) {
         ec_worker_t *W = &J[t].W;
-        free(W->w.a); free(W->S.cand.s); free(W->S.best_seq.s); free(W->S.path.a); free(W->S.best_path.a);
+        free(W->w.a); free(W->S.cand.s); free(W->S.best_seq.s); free(W->S.path.a); free(W->S.best_path.a); free(W->S.stash);
         free(W->seq.s); free(W->kk.a); free(W->pp.a);
     }
     free(J);
