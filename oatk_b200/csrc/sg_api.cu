@@ -139,6 +139,7 @@ static void reset_state(sg_batch *b)
     b->have_kid_local = false;
     b->pipe_fed = false;
     b->keys_are_ids = false;
+    b->tup_valid = false;
     b->k = b->s = 0;
     b->n_syncmers = 0;
 }
@@ -284,6 +285,9 @@ int sg_extract(sg_batch *b, int k, int s)
     K.scm_off = (const uint64_t *) b->scm_off.p;
     K.sid_base = b->sid_base;
     K.fp = (uint64_t *) b->fp.p;
+    RS(b->tup, (N + 1) * 32);
+    K.tup = (uint64_t *) b->tup.p;
+    b->tup_valid = true;
     K.key = (uint64_t *) b->key.p; K.occ = (uint64_t *) b->occ.p; K.m_pos = (uint32_t *) b->m_pos.p; K.s_mer = (uint64_t *) b->s_mer.p;
     LAUNCHED(SG_T_KMERHASH, launch_kmerhash(K, st));
     ctx->t_end(SG_T_KMERHASH);

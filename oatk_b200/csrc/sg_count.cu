@@ -85,6 +85,17 @@ __global__ void __launch_bounds__(128) sort_repair_kernel(uint64_t *k, uint64_t 
     }
 }
 
+// the same from the 32-byte records written by kmerhash_kernel: one sector per tuple
+__global__ void __launch_bounds__(256) tuple_gather_aos_kernel(const uint64_t *sval, const ulonglong4 *tup, uint64_t *socc, uint64_t *ssmer, uint64_t *sfp, uint64_t n)
+{
+    const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const ulonglong2 *p = reinterpret_cast<const ulonglong2 *>(tup + sval[i]);
+        const ulonglong2 a = __ldg(p), b = __ldg(p + 1);
+        socc[i] = a.x; ssmer[i] = a.y; sfp[i] = b.x;
+    }
+}
+
 __global__ void __launch_bounds__(256) tuple_gather_kernel(const uint64_t *sval, const uint64_t *occ, const uint64_t *smer, const uint64_t *fp,
         uint64_t *socc, uint64_t *ssmer, uint64_t *sfp, uint64_t n)
 {
@@ -406,7 +417,11 @@ static int ensure_sorted(sg_batch *b)
         b->sort_fell_back = true;
         full = true;                                          // too many or too long runs: sort on all 64 bits
     }
-    tuple_gather_kernel<<<nblk(N, 256), 256, 0, st>>>((const uint64_t *) b->sval.p, b->t_occ(),
+    if (b->tup_valid && !b->adopted && !b->keys_are_ids)
+        tuple_gather_aos_kernel<<<nblk(N, 256), 256, 0, st>>>((const uint64_t *) b->sval.p, (const ulonglong4 *) b->tup.p,
+                (uint64_t *) b->socc.p, (uint64_t *) b->ssmer.p, (uint64_t *) b->sfp.p, N);
+    else
+        tuple_gather_kernel<<<nblk(N, 256), 256, 0, st>>>((const uint64_t *) b->sval.p, b->t_occ(),
             b->t_smer(), b->t_fp(), (uint64_t *) b->socc.p, (uint64_t *) b->ssmer.p, (uint64_t *) b->sfp.p, N);
     ctx->count_launch(SG_T_SORT, 1);
     ctx->t_end(SG_T_SORT);

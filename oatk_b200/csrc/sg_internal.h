@@ -57,6 +57,7 @@ struct KmerArgs {
     // ordered outputs (read order)
     uint64_t *key;               // k-mer hash
     uint64_t *fp;                // independent second hash of the same k-mer
+    uint64_t *tup;               // optional: (occ, s_mer, fp, key) per syncmer as one 32-byte record
     uint64_t *occ;               // sid << 32 | idx << 1 | rev
     uint32_t *m_pos;
     uint64_t *s_mer;

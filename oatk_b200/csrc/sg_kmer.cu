@@ -106,6 +106,13 @@ __global__ void __launch_bounds__(256) kmerhash_kernel(KmerArgs A)
     A.occ[o] = (A.sid_base + sid) << 32 | (uint64_t) idx << 1 | (mp & 1u);
     A.m_pos[o] = mp;
     A.s_mer[o] = open ? raw : raw ^ 1ull;
+    // the same three words once more as one 32-byte record: the hash-order gather of sg_count then touches one
+    // sector per tuple instead of three
+    if (A.tup) {
+        ulonglong4 t;
+        t.x = (A.sid_base + sid) << 32 | (uint64_t) idx << 1 | (mp & 1u); t.y = open ? raw : raw ^ 1ull; t.z = fp; t.w = h;
+        reinterpret_cast<ulonglong4 *>(A.tup)[o] = t;
+    }
 }
 
 int launch_kmerhash(const KmerArgs &A, cudaStream_t st)
