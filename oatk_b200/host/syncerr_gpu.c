@@ -129,6 +129,28 @@ static void wave_run(wave_t *w)
     w->score = s; w->n = (size_t) n;
 }
 
+/* test hook: the extension-mode edit distance between two strings in one go, and resumed over a query that grows
+ * piece by piece the way the graph search feeds it (the two must agree). bw < 0: no band. */
+void oatk_wave_align(const char *ts, int32_t tl, const char *qs, int32_t ql, int32_t bw, int32_t grow, int32_t *out /* score, t_end, q_end */)
+{
+    wave_t w;
+    memset(&w, 0, sizeof(w));
+    w.ts = ts; w.tl = tl; w.bw = bw; w.qs = qs;
+    w.m = 4 * (size_t) (tl + ql + 4);
+    w.a = (wdiag_t *) malloc(w.m * sizeof(wdiag_t));
+    w.n = 1; w.a[0].d = 0; w.a[0].k = -1;
+    if (grow <= 0) grow = ql ? ql : 1;
+    for (int32_t have = 0; ; ) {
+        have = have + grow < ql ? have + grow : ql;
+        w.ql = have;
+        wave_run(&w);
+        if (have >= ql || (w.t_end > 0 && w.t_end >= tl) || (bw >= 0 && w.score > bw)) break;
+        /* an end of the QUERY was reached: the graph search appends more query and runs again from this state */
+    }
+    out[0] = w.score; out[1] = w.t_end; out[2] = w.q_end;
+    free(w.a);
+}
+
 /* ---------------------------------------------------------------- small vectors */
 typedef struct { size_t l, m; char *s; } str_t;
 typedef struct { size_t n, m; uint64_t *a; } v64_t;

@@ -236,6 +236,33 @@ void ref_read_ec(sr_db_t *db, scg_t *g, double max_edist, uint32_t err_mer_c, ui
 void ref_scm_flags(syncmer_db_t *s, uint8_t *del) { size_t i; for (i = 0; i < s->n; ++i) del[i] = s->a[i].del; }
 uint64_t ref_scm_total_cov(syncmer_db_t *s) { size_t i; uint64_t t = 0; for (i = 0; i < s->n; ++i) t += s->a[i].cov; return t; }
 
+/* the reference's resumable wavefront edit distance (levdist.c:265 wf_ed_core) in extension mode without traceback,
+ * driven the way syncerr.c:444-485 and dfs_search drive it: one diagonal to start with, the query growing by `grow`
+ * characters per call */
+#include "levdist.h"
+void ref_wave_align(char *ts, int tl, char *qs, int ql, int bw, int grow, int *out)
+{
+    wf_config_t conf;
+    wf_diag_t diag;
+    int have = 0;
+    memset(&conf, 0, sizeof(conf));
+    memset(&diag, 0, sizeof(diag));
+    conf.ts = ts; conf.tl = tl; conf.qs = qs; conf.is_ext = 1; conf.bw = bw;
+    conf.wf_diag = &diag;
+    diag.m = 4 * (size_t) (tl + ql + 4);
+    diag.a = malloc(diag.m * sizeof(wf_diag1_t));
+    diag.n = 1; diag.a[0].d = 0; diag.a[0].k = -1;
+    if (grow <= 0) grow = ql ? ql : 1;
+    for (;;) {
+        have = have + grow < ql ? have + grow : ql;
+        conf.ql = have;
+        wf_ed_core(&conf);
+        if (have >= ql || (conf.t_end > 0 && conf.t_end >= tl) || (bw >= 0 && conf.score > bw)) break;
+    }
+    out[0] = conf.score; out[1] = conf.t_end; out[2] = conf.q_end;
+    free(diag.a);
+}
+
 /* the reference's reader alone (sstream_open / sstream_read, the loop of sr_read with its -D rule): every record's
  * name and sequence, flat. Arrays are malloc()ed; the caller frees them. */
 int ref_parse_files(char **files, int n_files, size_t mD, char **bases_out, uint64_t **off_out, char **names_out, uint64_t **name_off_out, uint64_t *n_out)

@@ -110,3 +110,43 @@ def test_randomised_inputs_with_repeats(host, ref):
             ref.free(g=x[2])
             ref.free(x[0], x[1])
     assert not bad, bad
+
+
+def test_wavefront_edit_distance(host, ref):
+    """the resumable wavefront edit distance under the graph search, alone: the reference's built-in strings
+    (levdist.c:445-446) and random pairs, in one go and with the query growing piece by piece, with and without band"""
+    host.oatk_wave_align.argtypes = [C.c_char_p, C.c_int32, C.c_char_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
+    ref.L.ref_wave_align.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+
+    def both(t, q, bw, grow):
+        a, b = np.zeros(3, np.int32), np.zeros(3, np.int32)
+        host.oatk_wave_align(t, len(t), q, len(q), bw, grow, a.ctypes.data)
+        ref.L.ref_wave_align(t, len(t), q, len(q), bw, grow, b.ctypes.data)
+        return tuple(a), tuple(b)
+
+    t = b"AATGCTCTCATGACATATGAGATAGATACATAGAGACAGATATAGATACACACAGAGATATATGACGTCTGTATGCTCTCTCTCATAGATATACTCTGTAGACTGTCATATACATGCAGAAAAA"
+    q = b"CGCTCTCATGACANATGAGATAGATACATAGAGNCAGATATAGATACACACAGTTT"
+    got, want = both(t, q, -1, 0)
+    assert got == want and got[0] == 8                     # the known answer of the reference's own test main: ED = 8
+    rng = np.random.default_rng(4)
+    for it in range(400):
+        L = int(rng.integers(10, 400))
+        base = rng.integers(0, 4, L)
+        tt = bytes(b"ACGT"[i] for i in base)
+        qq = bytearray(tt)
+        for _ in range(int(rng.integers(0, 12))):             # a few edits
+            p = int(rng.integers(0, max(len(qq), 1)))
+            kind = int(rng.integers(0, 3))
+            if kind == 0 and qq:
+                qq[p] = b"ACGT"[int(rng.integers(0, 4))]
+            elif kind == 1 and qq:
+                del qq[p]
+            else:
+                qq.insert(p, b"ACGT"[int(rng.integers(0, 4))])
+        qq = bytes(qq) + bytes(b"ACGT"[i] for i in rng.integers(0, 4, int(rng.integers(0, 60))))
+        if not qq:
+            continue
+        for bw in (-1, 6, int(np.ceil(0.02 * L)) + 1):
+            for grow in (0, 37, 1001):
+                got, want = both(tt, qq, bw, grow)
+                assert got == want, (it, L, len(qq), bw, grow, got, want)
