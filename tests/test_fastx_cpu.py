@@ -192,3 +192,25 @@ def _parallel_case(host, ref, poison):
         p2 = _write(d, "big2.fa.gz", data[:len(data) // 2], gz=True)
         got, _ = ours(host, [p, p2])
         assert got == theirs(ref, [p, p2])
+
+
+def test_fuzz_against_kseq(host, ref):
+    """byte soups made of the characters the grammar cares about: whatever kseq makes of them, so must we"""
+    from hypothesis import given, settings, strategies as st, HealthCheck
+    alphabet = [b">", b"@", b"+", b"A", b"C", b"g", b"N", b"\r", b" ", b"\t", b"I", b"#"]
+    line = st.lists(st.sampled_from(alphabet), min_size=0, max_size=12).map(b"".join)
+    doc = st.tuples(st.lists(line, min_size=0, max_size=14), st.booleans()).map(lambda t: b"\n".join(t[0]) + (b"\n" if t[1] else b""))
+    d = tempfile.mkdtemp()
+    p = os.path.join(d, "fuzz.fx")
+
+    @settings(max_examples=600, deadline=None, suppress_health_check=list(HealthCheck))
+    @given(doc)
+    def run(data):
+        with open(p, "wb") as f:
+            f.write(data)
+        got, _ = ours(host, [p])
+        assert got == theirs(ref, [p]), data
+
+    run()
+    os.unlink(p)
+    os.rmdir(d)
