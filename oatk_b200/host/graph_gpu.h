@@ -52,6 +52,22 @@ typedef struct {
     uint128_t *scm_u;          /* scm_id[49] | scm_rev[1] | utg_id[42] | utg_pos[36], sorted */
     uint128_t **idx_u;         /* n_scm + 1 pointers into scm_u */
 } scg_t;
+
+/* one read against the unitig graph (syncasm.h:62-77): a chain of fragments, each a stretch of one oriented unitig */
+typedef struct {
+    uint64_t uid;              /* unitig << 1 | strand */
+    uint64_t u_beg, u_end;     /* first / last syncmer on the oriented unitig (inclusive) */
+    uint32_t s_beg, s_end;     /* first / last syncmer on the read (inclusive) */
+} ra_frg_t;
+
+typedef struct {
+    uint64_t sid;
+    uint32_t n;
+    ra_frg_t *a;               /* its own malloc block */
+    double s;                  /* best chain score + 1 / (number of equally good alignments of this read) */
+} scg_ra_t;
+
+typedef struct { size_t n, m; scg_ra_t *a; } scg_ra_v;
 #endif
 
 void asmg_destroy(asmg_t *g);
@@ -75,6 +91,19 @@ void scg_consensus(sr_db_t *sr_db, scg_t *scg, int hoco_seq, int save_seq, FILE 
 int64_t find_error_syncmers(scg_t *g, uint32_t err_mer_c, uint32_t max_err_c, uint32_t err_arc_c, double max_arc_f, int del_err);
 void read_error_correction(sr_db_t *sr_db, scg_t *g, double max_edist, uint32_t err_mer_c, uint32_t max_err_c,
         uint32_t err_arc_c, double max_arc_f, int n_threads, FILE *fo, int verbose);
+
+/* row f3 (alignment_gpu.c, coverage_gpu.c): reads against the unitig graph and the coverage estimates drawn from
+ * the alignments (reference alignment.c:596-684, syncasm.c:1882-2261, graph.c:117-127, 237-248).
+ * ra_v is replaced by the new records, ordered by read and, within a read, in the reference's enumeration order;
+ * for_unzip re-aligns only reads that spanned more than two unitigs before and keeps a result only if it scores
+ * at least what the old one did */
+void scg_read_alignment(sr_db_t *sr_db, scg_ra_v *ra_v, scg_t *g, int n_threads, int for_unzip);
+void scg_ra_v_destroy(scg_ra_v *ra_v);
+void scg_ra_utg_coverage(scg_t *g, sr_db_t *sr_db, scg_ra_v *ra_v, int verbose);
+void scg_ra_arc_coverage(scg_t *g, sr_db_t *sr_db, scg_ra_v *ra_v, int refine, int verbose);
+void scg_refine_arc_coverage(scg_t *g, int verbose);
+uint64_t asmg_max_link_id(asmg_t *g);
+void asmg_arc_fix_cov(asmg_t *g);
 
 #ifdef __cplusplus
 }

@@ -236,6 +236,46 @@ void ref_read_ec(sr_db_t *db, scg_t *g, double max_edist, uint32_t err_mer_c, ui
 void ref_scm_flags(syncmer_db_t *s, uint8_t *del) { size_t i; for (i = 0; i < s->n; ++i) del[i] = s->a[i].del; }
 uint64_t ref_scm_total_cov(syncmer_db_t *s) { size_t i; uint64_t t = 0; for (i = 0; i < s->n; ++i) t += s->a[i].cov; return t; }
 
+/* row f3: read -> unitig-graph alignment (alignment.c:596) and the coverage estimators (syncasm.c:1882-2261),
+ * run by the reference on its own structures; alignment records flattened for comparison */
+scg_ra_v *ref_ra_new(void) { return (scg_ra_v *) calloc(1, sizeof(scg_ra_v)); }
+void ref_ra_free(scg_ra_v *ra) { scg_ra_v_destroy(ra); }
+void ref_read_alignment(sr_db_t *db, scg_ra_v *ra, scg_t *g, int n_threads, int for_unzip) { scg_read_alignment(db, ra, g, n_threads, for_unzip); }
+uint64_t ref_ra_n(scg_ra_v *ra) { return ra->n; }
+uint64_t ref_ra_total(scg_ra_v *ra) { size_t i; uint64_t t = 0; for (i = 0; i < ra->n; ++i) t += ra->a[i].n; return t; }
+/* per record: sid, n, s; per fragment 5 uint64: uid, u_beg, u_end, s_beg, s_end */
+void ref_ra_flatten(scg_ra_v *ra, uint64_t *sid, uint32_t *n, double *s, uint64_t *frg)
+{
+    size_t i, p = 0;
+    uint32_t j;
+    for (i = 0; i < ra->n; ++i) {
+        sid[i] = ra->a[i].sid; n[i] = ra->a[i].n; s[i] = ra->a[i].s;
+        for (j = 0; j < ra->a[i].n; ++j, ++p) {
+            ra_frg_t *f = &ra->a[i].a[j];
+            frg[5 * p] = f->uid; frg[5 * p + 1] = f->u_beg; frg[5 * p + 2] = f->u_end; frg[5 * p + 3] = f->s_beg; frg[5 * p + 4] = f->s_end;
+        }
+    }
+}
+/* the reference's repeat unzipping (run_syncasm.c:207-233) on its own graph: leaves unitigs duplicated along the
+ * read paths, i.e. syncmers with several unitig occurrences -- the input that makes alignments ambiguous */
+int ref_multiplex_rounds(sr_db_t *db, scg_t *g, int rounds, int n_threads)
+{
+    scg_ra_v *ra = (scg_ra_v *) calloc(1, sizeof(scg_ra_v));
+    int r = 0, updated = 1, total = 0;
+    uint32_t max_n_scm = ceil(30000.0 / db->k);
+    while (updated != 0 && r < rounds) {
+        ++r;
+        scg_read_alignment(db, ra, g, n_threads, 1);
+        scg_update_utg_cov(g);
+        updated = scg_multiplex(g, ra, max_n_scm, 10, .3);
+        total += updated;
+    }
+    scg_ra_v_destroy(ra);
+    return total;
+}
+void ref_ra_utg_coverage(scg_t *g, sr_db_t *db, scg_ra_v *ra) { scg_ra_utg_coverage(g, db, ra, 0); }
+void ref_ra_arc_coverage(scg_t *g, sr_db_t *db, scg_ra_v *ra, int refine) { scg_ra_arc_coverage(g, db, ra, refine, 0); }
+
 /* the reference's resumable wavefront edit distance (levdist.c:265 wf_ed_core) in extension mode without traceback,
  * driven the way syncerr.c:444-485 and dfs_search drive it: one diagonal to start with, the query growing by `grow`
  * characters per call */
