@@ -104,6 +104,11 @@ void scg_ra_arc_coverage(scg_t *g, sr_db_t *sr_db, scg_ra_v *ra_v, int refine, i
 void scg_refine_arc_coverage(scg_t *g, int verbose);
 uint64_t asmg_max_link_id(asmg_t *g);
 void asmg_arc_fix_cov(asmg_t *g);
+/* clean-up of the unitig graph between .utg.gfa and .utg.final.gfa (cleaning_gpu.c; reference graph.c:607, 698, 855):
+ * return the number of tips / links / bubbles (| short tips << 32) removed; do_cleanup re-finalizes the graph */
+uint64_t asmg_drop_tip(asmg_t *g, int32_t tip_cnt, uint64_t tip_len, int protect_super_tip, int do_cleanup, int VERBOSE);
+uint64_t asmg_remove_weak_crosslink(asmg_t *g, double c_thresh, double m_cov, int do_cleanup, int VERBOSE);
+uint64_t asmg_pop_bubble(asmg_t *g, uint64_t radius, uint64_t max_del, int protect_tip, int protect_super_bubble, int do_cleanup, int VERBOSE);
 
 #ifdef __cplusplus
 }

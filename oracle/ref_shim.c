@@ -273,6 +273,13 @@ int ref_multiplex_rounds(sr_db_t *db, scg_t *g, int rounds, int n_threads)
     scg_ra_v_destroy(ra);
     return total;
 }
+/* the clean-up passes between .utg.gfa and .utg.final.gfa (graph.c:607, 698, 855; syncasm.c:682, 1090, 1486) */
+uint64_t ref_drop_tip(scg_t *g, int32_t tip_cnt, uint64_t tip_len, int protect, int cleanup) { return asmg_drop_tip(g->utg_asmg, tip_cnt, tip_len, protect, cleanup, 0); }
+uint64_t ref_weak_crosslink(scg_t *g, double c_thresh, double m_cov, int cleanup) { return asmg_remove_weak_crosslink(g->utg_asmg, c_thresh, m_cov, cleanup, 0); }
+uint64_t ref_pop_bubble(scg_t *g, uint64_t radius, uint64_t max_del, int protect_tip, int protect_super, int cleanup) { return asmg_pop_bubble(g->utg_asmg, radius, max_del, protect_tip, protect_super, cleanup, 0); }
+void ref_update_utg_cov(scg_t *g) { scg_update_utg_cov(g); }
+int ref_multiplex(scg_t *g, scg_ra_v *ra, uint32_t max_n_scm, double min_n_r, double min_d_f) { return scg_multiplex(g, ra, max_n_scm, min_n_r, min_d_f); }
+void ref_demultiplex(scg_t *g) { scg_demultiplex(g); }
 void ref_ra_utg_coverage(scg_t *g, sr_db_t *db, scg_ra_v *ra) { scg_ra_utg_coverage(g, db, ra, 0); }
 void ref_ra_arc_coverage(scg_t *g, sr_db_t *db, scg_ra_v *ra, int refine) { scg_ra_arc_coverage(g, db, ra, refine, 0); }
 
