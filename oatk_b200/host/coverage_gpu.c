@@ -90,6 +90,36 @@ void asmg_arc_fix_cov(asmg_t *g)
     }
 }
 
+/* every unitig's coverage from its syncmers' k-mer coverages: the trimmed mean over the syncmers that occur once in
+ * the graph, over all of them if there is none (syncasm.c:630-703) */
+void scg_update_utg_cov(scg_t *scg)
+{
+    asmg_t *ug = scg->utg_asmg;
+    const syncmer_t *scm = scg->scm_db->a;
+    uint64_t i, j;
+    for (i = 0; i < ug->n_vtx; ++i) {
+        asmg_vtx_t *x = &ug->vtx[i];
+        double *c, mean;
+        uint64_t zero = 0;
+        if (x->del) { x->cov = 0; continue; }
+        c = (double *) calloc(x->n ? x->n : 1, sizeof(double));
+        for (j = 0; j < x->n; ++j) {
+            const uint64_t u = x->a[j] >> 1;
+            if (scg->idx_u[u + 1] - scg->idx_u[u] == 1) c[j] = scm[u].cov;
+        }
+        qsort(c, x->n, sizeof(double), dbl_cmp);
+        while (zero < x->n && c[zero] < DBL_EPSILON) ++zero;
+        if (zero == x->n) {
+            for (j = 0; j < x->n; ++j) c[j] = scm[x->a[j] >> 1].cov;
+            qsort(c, x->n, sizeof(double), dbl_cmp);
+            zero = 0;
+        }
+        mean = trimmed_mean(c + zero, (int) (x->n - zero), 1);
+        x->cov = mean;
+        free(c);
+    }
+}
+
 /* ---------- matching blocks of one fragment: LCS of read and unitig syncmer ids (syncasm.c:1654-1751) ---------- */
 static void match_blocks(const uint64_t *rd, int n_rd, const uint64_t *ut, int n_ut, int rev_ut, uint32_t offset, blk_v *out)
 {

@@ -104,6 +104,11 @@ void scg_ra_arc_coverage(scg_t *g, sr_db_t *sr_db, scg_ra_v *ra_v, int refine, i
 void scg_refine_arc_coverage(scg_t *g, int verbose);
 uint64_t asmg_max_link_id(asmg_t *g);
 void asmg_arc_fix_cov(asmg_t *g);
+/* repeat unzipping (unzip_gpu.c; reference syncasm.c:682, 1090, 1486): scg_multiplex returns the number of
+ * (arc in, arc out) pairings it dropped, 0 = graph untouched */
+void scg_update_utg_cov(scg_t *scg);
+int scg_multiplex(scg_t *g, scg_ra_v *ra_v, uint32_t max_n_scm, double min_n_r, double min_d_f);
+void scg_demultiplex(scg_t *g);
 /* clean-up of the unitig graph between .utg.gfa and .utg.final.gfa (cleaning_gpu.c; reference graph.c:607, 698, 855):
  * return the number of tips / links / bubbles (| short tips << 32) removed; do_cleanup re-finalizes the graph */
 uint64_t asmg_drop_tip(asmg_t *g, int32_t tip_cnt, uint64_t tip_len, int protect_super_tip, int do_cleanup, int VERBOSE);
