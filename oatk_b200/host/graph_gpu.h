@@ -68,6 +68,15 @@ typedef struct {
 } scg_ra_t;
 
 typedef struct { size_t n, m; scg_ra_t *a; } scg_ra_v;
+
+/* what syncasm() hands to a caller that wants to go on with the graph (syncasm.h:79-85) */
+typedef struct {
+    int k, s;
+    scg_t *scg;
+    syncmer_db_t *scm_db;
+    sr_db_t *sr_db;
+    scg_ra_v *ra_db;
+} scg_meta_t;
 #endif
 
 void asmg_destroy(asmg_t *g);
@@ -104,6 +113,17 @@ void scg_ra_arc_coverage(scg_t *g, sr_db_t *sr_db, scg_ra_v *ra_v, int refine, i
 void scg_refine_arc_coverage(scg_t *g, int verbose);
 uint64_t asmg_max_link_id(asmg_t *g);
 void asmg_arc_fix_cov(asmg_t *g);
+/* the whole command (run_syncasm_gpu.c; reference run_syncasm.c:52-326): files -> <out>.utg.gfa, <out>.utg.final.gfa.
+ * min_k_cov 0 = ten times the k-mer coverage peak; do_unzip = rounds of repeat unzipping (0: none, bubbles are popped
+ * straight away); meta, if given, receives the structures instead of their being freed. Returns 0, or 1 after an
+ * [E::syncasm] line */
+int syncasm(char **file_in, int n_file, size_t m_data, int k, int s, int bubble_size, int tip_size, int min_k_cov, double min_a_cov_f,
+        double weak_cross, int do_ec, int do_unzip, int n_threads, char *out, scg_meta_t *meta, int VERBOSE);
+int oatk_syncasm_graph_stage(sr_db_t *sr_db, scg_t *scg, scg_ra_v *ra_db, int bubble_size, int tip_size, double weak_cross,
+        int do_unzip, int n_threads, char *out, int VERBOSE);
+int scg_is_empty(scg_t *scg);
+void scg_meta_clean(scg_meta_t *meta);
+void scg_meta_destroy(scg_meta_t *meta);
 /* repeat unzipping (unzip_gpu.c; reference syncasm.c:682, 1090, 1486): scg_multiplex returns the number of
  * (arc in, arc out) pairings it dropped, 0 = graph untouched */
 void scg_update_utg_cov(scg_t *scg);
