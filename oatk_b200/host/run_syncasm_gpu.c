@@ -144,6 +144,11 @@ int syncasm(char **file_in, int n_file, size_t m_data, int k, int s, int bubble_
     if (sr_db_validate(sr_db)) { ret = 1; goto done; }
     sr_db_stat(sr_db, stderr, VERBOSE);
     if (min_k_cov == 0) {
+        if (!sr_db->stats) {                          /* no syncmers, no spectrum to read the threshold from */
+            fprintf(stderr, "[E::%s] empty syncmer graph\n", __func__);
+            ret = 1;
+            goto done;
+        }
         min_k_cov = sr_db->stats->kmer_peak_het > 0 ? sr_db->stats->kmer_peak_het * 10 : sr_db->stats->kmer_peak_hom * 10;
         fprintf(stderr, "[M::%s] set minimum kmer coverage as %d\n", __func__, min_k_cov);
     }
