@@ -66,7 +66,15 @@ static int arc_vw_cmp(const void *x, const void *y)
     return (a->w > b->w) - (a->w < b->w);
 }
 
-void asmg_arc_sort(asmg_t *g) { qsort(g->arc, g->n_arc, sizeof(asmg_arc_t), arc_vw_cmp); }
+/* Arcs that are already in strictly ascending (v, w) order stay as they are: with no two equal keys every sort gives
+ * this one order (the device hands the arc tally over sorted, which saves sorting 10^7 48-byte arcs on the host). Equal
+ * keys (graph.c:252 "multi-arc") leave the order to libc's qsort, as in the reference. */
+void asmg_arc_sort(asmg_t *g)
+{
+    uint64_t i;
+    for (i = 1; i < g->n_arc; ++i) if (arc_vw_cmp(&g->arc[i - 1], &g->arc[i]) >= 0) break;
+    if (i < g->n_arc) qsort(g->arc, g->n_arc, sizeof(asmg_arc_t), arc_vw_cmp);
+}
 
 void asmg_arc_index(asmg_t *g)
 {
@@ -329,7 +337,8 @@ static void index_syncmers(scg_t *g)
         if (a->vtx[i].del) continue;
         for (j = 0; j < a->vtx[i].n; ++j) u[tot++] = (uint128_t) a->vtx[i].a[j] << 78 | (uint128_t) i << 36 | j;
     }
-    qsort(u, tot, sizeof(uint128_t), u128_cmp);
+    for (i = 1; i < tot; ++i) if (u[i - 1] >= u[i]) break;        /* singleton graphs come out in order (keys are distinct) */
+    if (i < tot) qsort(u, tot, sizeof(uint128_t), u128_cmp);
     g->idx_u = (uint128_t **) malloc(sizeof(uint128_t *) * (n_scm + 1));
     p = u; end = u + tot;
     for (s = 0; s <= n_scm; ++s) {                /* idx_u[s] = first entry whose syncmer id is >= s */
@@ -346,6 +355,7 @@ scg_t *make_syncmer_graph(sr_db_t *sr_db, syncmer_db_t *scm_db, uint32_t min_k_c
     uint64_t i, n, *arcs4 = 0, n_arcs = 0;
     if (scm_db->n == 0) return 0;
     n = scm_db->n;
+    oatk_tick(0);
     /* one singleton unitig per syncmer; the coverage filter marks both the syncmer and its vertex (syncasm.c:223-232) */
     g = (asmg_t *) calloc(1, sizeof(asmg_t));
     g->vtx = (asmg_vtx_t *) calloc(n, sizeof(asmg_vtx_t));
@@ -359,6 +369,7 @@ scg_t *make_syncmer_graph(sr_db_t *sr_db, syncmer_db_t *scm_db, uint32_t min_k_c
         g->vtx[i].cov = m->cov;
         g->vtx[i].del = m->del;
     }
+    oatk_tick("graph: vertices");
     /* arcs: counted, filtered and paired with their complements on the device */
     if (syncmer_graph_arcs(sr_db, scm_db, min_k_cov, min_a_cov_f, &arcs4, &n_arcs) != 0) {
         fprintf(stderr, "[E::%s] arc tally failed\n", __func__);
@@ -366,6 +377,7 @@ scg_t *make_syncmer_graph(sr_db_t *sr_db, syncmer_db_t *scm_db, uint32_t min_k_c
         free(arcs4);
         return 0;
     }
+    oatk_tick("graph: arc tally (device) + download");
     g->arc = (asmg_arc_t *) malloc(sizeof(asmg_arc_t) * (n_arcs ? n_arcs : 1));
     g->n_arc = g->m_arc = n_arcs;
     for (i = 0; i < n_arcs; ++i) {
@@ -379,11 +391,14 @@ scg_t *make_syncmer_graph(sr_db_t *sr_db, syncmer_db_t *scm_db, uint32_t min_k_c
         if (g->vtx[a->v >> 1].del || g->vtx[a->w >> 1].del) a->del = 1;
     }
     free(arcs4);
+    oatk_tick("graph: arc records");
     asmg_finalize(g, 1);
+    oatk_tick("graph: finalize");
     scg = (scg_t *) calloc(1, sizeof(scg_t));
     scg->scm_db = scm_db;
     scg->utg_asmg = g;
     index_syncmers(scg);
+    oatk_tick("graph: syncmer index");
     return scg;
 }
 

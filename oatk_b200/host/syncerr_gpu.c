@@ -432,7 +432,9 @@ void read_error_correction(sr_db_t *sr_db, scg_t *g, double max_edist, uint32_t 
     (void) fo;                                          /* the corrected-read FASTA is a debugging aid of the reference */
     if (n_threads <= 0) n_threads = 1;
     if (n_threads > 64) n_threads = 64;
+    oatk_tick(0);
     find_error_syncmers(g, err_mer_c, max_err_c, err_arc_c, max_arc_f, 1);
+    oatk_tick("ec: find error syncmers");
 
     ec_job_t *J = (ec_job_t *) calloc((size_t) n_threads, sizeof(ec_job_t));
     uint64_t next = 0;
@@ -445,8 +447,11 @@ void read_error_correction(sr_db_t *sr_db, scg_t *g, double max_edist, uint32_t 
     long stats[11] = {0};
     for (int t = 0; t < n_threads; ++t) for (int j = 0; j < 11; ++j) stats[j] += J[t].W.stats[j];
 
+    oatk_tick("ec: correct reads");
     rebuild_syncmer_db(sr_db, g->scm_db);
+    oatk_tick("ec: rebuild database");
     oatk_gpu_update_lists(sr_db, g->scm_db);            /* the device-resident lists follow the host's */
+    oatk_tick("ec: refresh device lists");
 
     fprintf(stderr, "[M::%s] Error Correction Summary Results\n", __func__);
     fprintf(stderr, "[M::%s] total number of error blocks : %ld\n", __func__, stats[0] + stats[5] + stats[10]);

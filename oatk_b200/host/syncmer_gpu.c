@@ -5,6 +5,7 @@
  * reference prints. No sequence arithmetic happens here.
  */
 #include <stdlib.h>
+#include <time.h>
 #include <string.h>
 #include <math.h>
 #include <pthread.h>
@@ -315,6 +316,19 @@ int syncmer_graph_arcs(sr_db_t *sr_db, syncmer_db_t *scm_db, uint32_t min_k_cov,
  * the device-resident batch behind this sr_db_t up to date, so that the second sr_db_stat and the arc tally of the
  * final graph (both on the device) see the corrected lists. A database that was not produced by sr_read_mem has no
  * batch and nothing to refresh. */
+/* stage timer for tuning: with OATK_TIMING set, prints the time since the previous call to stderr */
+void oatk_tick(const char *what)
+{
+    static int on = -1;
+    static struct timespec last;
+    struct timespec now;
+    if (on < 0) { on = getenv("OATK_TIMING") != 0; clock_gettime(CLOCK_MONOTONIC, &last); }
+    if (!on) return;
+    clock_gettime(CLOCK_MONOTONIC, &now);
+    if (what) fprintf(stderr, "[T::%s] %.3f s\n", what, (double) (now.tv_sec - last.tv_sec) + 1e-9 * (double) (now.tv_nsec - last.tv_nsec));
+    last = now;
+}
+
 int oatk_gpu_update_lists(sr_db_t *sr_db, syncmer_db_t *scm_db)
 {
     sg_batch *b = batch_of(sr_db, 0);
