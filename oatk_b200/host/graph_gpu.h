@@ -95,7 +95,8 @@ void scg_stat(scg_t *scg, FILE *fo, uint64_t *stats);
  * fo may be NULL (lengths, coverages and overlaps are still filled in) */
 void scg_consensus(sr_db_t *sr_db, scg_t *scg, int hoco_seq, int save_seq, FILE *fo);
 /* row f2 (syncerr_gpu.c): read error correction on the all-syncmer graph (reference syncerr.c:679-757, 819-943).
- * g must be the graph of ALL syncmers (make_syncmer_graph(sr_db, scm_db, 0, 0.)) after scg_consensus(sr_db, g, 1, 1, 0);
+ * g must be the graph of ALL syncmers (make_syncmer_graph(sr_db, scm_db, 0, 0.)), either after scg_consensus(sr_db, g, 1, 1, 0)
+ * as in the reference, or without it: then the consensus is computed inside, only for what the error filter leaves;
  * rewrites the reads' syncmer lists and rebuilds the coverages / occurrence lists of g->scm_db */
 int64_t find_error_syncmers(scg_t *g, uint32_t err_mer_c, uint32_t max_err_c, uint32_t err_arc_c, double max_arc_f, int del_err);
 void read_error_correction(sr_db_t *sr_db, scg_t *g, double max_edist, uint32_t err_mer_c, uint32_t max_err_c,

@@ -432,9 +432,16 @@ void read_error_correction(sr_db_t *sr_db, scg_t *g, double max_edist, uint32_t 
     (void) fo;                                          /* the corrected-read FASTA is a debugging aid of the reference */
     if (n_threads <= 0) n_threads = 1;
     if (n_threads > 64) n_threads = 64;
+    /* The walk needs the hoco text of the vertices and the overlaps of the arcs it can reach. The reference computes
+     * them for ALL syncmers before the error filter (run_syncasm.c:118, its largest single cost); a caller that has not
+     * done so gets them here for what the filter leaves -- texts and overlaps are per vertex and per arc, so the
+     * survivors' are the same (tests/test_syncerr_cpu.py::test_deferred_consensus). */
+    int have_text = 0;
+    for (uint64_t i = 0; i < g->utg_asmg->n_vtx && !have_text; ++i) if (!g->utg_asmg->vtx[i].del) { have_text = g->utg_asmg->vtx[i].seq != 0; break; }
     oatk_tick(0);
     find_error_syncmers(g, err_mer_c, max_err_c, err_arc_c, max_arc_f, 1);
     oatk_tick("ec: find error syncmers");
+    if (!have_text) { scg_consensus(sr_db, g, 1, 1, 0); oatk_tick("ec: hoco consensus of the surviving graph"); }
 
     ec_job_t *J = (ec_job_t *) calloc((size_t) n_threads, sizeof(ec_job_t));
     uint64_t next = 0;

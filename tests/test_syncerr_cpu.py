@@ -21,12 +21,13 @@ def host():
     return L
 
 
-def _pipeline(ref, bases, off, k, s):
+def _pipeline(ref, bases, off, k, s, consensus=True):
     rdb, _ = ref.extract(bases, off, k, s)
     rscm = ref.collect(rdb)
     g = ref.graph(rdb, rscm, 0, 0.0)                      # all syncmers: vertex id == syncmer id
     ref.L.ref_write_gfa2.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_char_p]
-    assert ref.L.ref_write_gfa2(rdb, g, 1, 1, b"/dev/null") == 0      # hoco consensus saved in the graph (run_syncasm.c:118)
+    if consensus:
+        assert ref.L.ref_write_gfa2(rdb, g, 1, 1, b"/dev/null") == 0      # hoco consensus saved in the graph (run_syncasm.c:118)
     return rdb, rscm, g
 
 
@@ -77,6 +78,32 @@ def test_read_error_correction_matches_reference(host, ref, k, s, G, n, L, err, 
     d1, d2 = ref.graph_dump(a[2]), ref.graph_dump(b[2])
     for f in d1:
         assert np.array_equal(d1[f], d2[f]), f
+    for x in (a, b):
+        ref.free(g=x[2])
+        ref.free(x[0], x[1])
+
+
+@pytest.mark.parametrize("k,s,G,n,L,err,seed,mkc,threads", CASES)
+def test_deferred_consensus(host, ref, k, s, G, n, L, err, seed, mkc, threads):
+    """read_error_correction on a graph WITHOUT the up-front all-syncmer consensus: it computes the texts and overlaps of
+    what its error filter leaves, and the corrected reads, the database and the pruning are the reference's all the same"""
+    reads = synth.hifi_reads(seed, G, n, L, err) + synth.adversarial_reads(3, k, s)
+    bases, off = pack_reads(reads)
+    n_n = count_ambiguous(bases, off)
+    a = _pipeline(ref, bases, off, k, s)
+    b = _pipeline(ref, bases, off, k, s, consensus=False)
+    ref.L.ref_read_ec.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_uint32, C.c_uint32, C.c_uint32, C.c_double, C.c_int]
+    ref.L.ref_read_ec(a[0], a[2], 0.02, mkc, mkc * 10, mkc, 0.35, threads)
+    host.read_error_correction(b[0], b[2], 0.02, mkc, mkc * 10, mkc, 0.35, threads, None, 0)
+    want = _state(ref, a[0], a[1], len(reads), n_n)
+    got = _state(ref, b[0], b[1], len(reads), n_n)
+    for key in want:
+        assert np.array_equal(got[key], want[key]), key
+    d1, d2 = ref.graph_dump(a[2]), ref.graph_dump(b[2])
+    assert np.array_equal(d1["vtx_flags"] >> 30, d2["vtx_flags"] >> 30)                  # same vertices pruned
+    assert np.array_equal(d1["arcs"][:, 4] >> 30, d2["arcs"][:, 4] >> 30)                # same arcs pruned
+    live = (d1["arcs"][:, 4] >> 30 & 1) == 0
+    assert np.array_equal(d1["arcs"][live], d2["arcs"][live])                            # and the same overlaps on the live ones
     for x in (a, b):
         ref.free(g=x[2])
         ref.free(x[0], x[1])
