@@ -337,29 +337,22 @@ static void correct_read(sr_db_t *db, const scg_t *g, double max_edist, uint64_t
 }
 
 /* ---------------------------------------------------------------- suspects */
-static void drop_arc(asmg_t *G, uint64_t v, uint64_t w)
-{
-    asmg_arc_t *a = &G->arc[G->idx_p[v]];
-    for (uint64_t i = 0, n = G->idx_n[v]; i < n; ++i) if (a[i].w == w) a[i].del = 1;
-}
-static void drop_vertex(asmg_t *G, uint64_t id)
-{
-    G->vtx[id].del = 1;
-    for (int side = 0; side < 2; ++side) {
-        const uint64_t v = id << 1 | (uint64_t) side;
-        asmg_arc_t *a = &G->arc[G->idx_p[v]];
-        for (uint64_t i = 0, n = G->idx_n[v]; i < n; ++i) { a[i].del = 1; drop_arc(G, a[i].w ^ 1, v ^ 1); }
-    }
-}
+/* Which syncmers look like sequencing errors (syncerr.c:679-757): fewer than err_mer_c occurrences, or -- below
+ * max_err_c -- a side that has arcs but none of them reliable (>= err_arc_c reads and >= max_arc_f of the thinner
+ * end). The test of one syncmer reads only coverages and the arcs' flags as they were on entry, so the candidates are
+ * found in parallel into a byte map and the flags set afterwards; a deleted vertex takes every arc that touches it
+ * with it (the graph is symmetric after asmg_finalize, so "its out-arcs and their complements" is "both ends"),
+ * which one pass over the arc array does without chasing pointers. */
+typedef struct { const scg_t *g; uint8_t *err; uint32_t err_mer_c, max_err_c, err_arc_c; double max_arc_f; } fes_t;
 
-int64_t find_error_syncmers(scg_t *g, uint32_t err_mer_c, uint32_t max_err_c, uint32_t err_arc_c, double max_arc_f, int del_err)
+static void fes_mark(uint64_t lo, uint64_t hi, void *arg)
 {
-    asmg_t *G = g->utg_asmg;
-    syncmer_t *scm = g->scm_db->a;
-    const size_t n_scm = g->scm_db->n;
-    for (size_t i = 0; i < n_scm; ++i) {
-        if (scm[i].del || scm[i].cov >= max_err_c) continue;
-        if (scm[i].cov < err_mer_c) { scm[i].del = 1; continue; }
+    const fes_t *F = (const fes_t *) arg;
+    const asmg_t *G = F->g->utg_asmg;
+    const syncmer_t *scm = F->g->scm_db->a;
+    for (uint64_t i = lo; i < hi; ++i) {
+        if (scm[i].del || scm[i].cov >= F->max_err_c) continue;
+        if (scm[i].cov < F->err_mer_c) { F->err[i] = 1; continue; }
         int side_ok[2] = {-1, -1};                      /* -1: no live arc on that side */
         for (int side = 0; side < 2; ++side) {
             const uint64_t v = (uint64_t) i << 1 | (uint64_t) side;
@@ -372,15 +365,39 @@ int64_t find_error_syncmers(scg_t *g, uint32_t err_mer_c, uint32_t max_err_c, ui
             for (uint64_t j = 0; j < na; ++j) {
                 if (a[j].del) continue;
                 const uint32_t cw = scm[a[j].w >> 1].cov, cv = scm[i].cov;
-                if (a[j].cov >= err_arc_c && a[j].cov >= (cv < cw ? cv : cw) * max_arc_f) { side_ok[side] = 1; break; }
+                if (a[j].cov >= F->err_arc_c && a[j].cov >= (cv < cw ? cv : cw) * F->max_arc_f) { side_ok[side] = 1; break; }
             }
         }
-        if (!side_ok[0] || !side_ok[1]) scm[i].del = 1;
+        if (!side_ok[0] || !side_ok[1]) F->err[i] = 1;
     }
+}
+
+static void fes_drop_arcs(uint64_t lo, uint64_t hi, void *arg)
+{
+    const fes_t *F = (const fes_t *) arg;
+    asmg_arc_t *a = F->g->utg_asmg->arc;
+    for (uint64_t i = lo; i < hi; ++i) if (F->err[a[i].v >> 1] || F->err[a[i].w >> 1]) a[i].del = 1;
+}
+
+int64_t find_error_syncmers(scg_t *g, uint32_t err_mer_c, uint32_t max_err_c, uint32_t err_arc_c, double max_arc_f, int del_err)
+{
+    asmg_t *G = g->utg_asmg;
+    syncmer_t *scm = g->scm_db->a;
+    const size_t n_scm = g->scm_db->n;
+    fes_t F = {g, (uint8_t *) calloc(n_scm ? n_scm : 1, 1), err_mer_c, max_err_c, err_arc_c, max_arc_f};
+    oatk_parallel_for(n_scm, fes_mark, &F);
     int64_t n_err = 0;
     uint32_t max_c = 0;
-    for (size_t i = 0; i < n_scm; ++i) if (scm[i].del) { if (scm[i].cov > max_c) max_c = scm[i].cov; ++n_err; }
-    if (del_err) for (size_t i = 0; i < n_scm; ++i) if (scm[i].del) drop_vertex(G, i);
+    for (size_t i = 0; i < n_scm; ++i) {
+        if (F.err[i]) scm[i].del = 1;
+        else F.err[i] = scm[i].del;                     /* deleted before this call: dropped from the graph as well */
+        if (scm[i].del) { if (scm[i].cov > max_c) max_c = scm[i].cov; ++n_err; }
+    }
+    if (del_err) {
+        for (size_t i = 0; i < n_scm; ++i) if (F.err[i]) G->vtx[i].del = 1;
+        oatk_parallel_for(G->n_arc, fes_drop_arcs, &F);
+    }
+    free(F.err);
     fprintf(stderr, "[M::%s] error syncmer candidates: num = %ld, max_c = %u\n", __func__, (long) n_err, max_c);
     return n_err;
 }

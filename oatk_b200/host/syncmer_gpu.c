@@ -5,6 +5,7 @@
  * reference prints. No sequence arithmetic happens here.
  */
 #include <stdlib.h>
+#include <unistd.h>
 #include <time.h>
 #include <string.h>
 #include <math.h>
@@ -316,6 +317,25 @@ int syncmer_graph_arcs(sr_db_t *sr_db, syncmer_db_t *scm_db, uint32_t min_k_cov,
  * the device-resident batch behind this sr_db_t up to date, so that the second sr_db_stat and the arc tally of the
  * final graph (both on the device) see the corrected lists. A database that was not produced by sr_read_mem has no
  * batch and nothing to refresh. */
+/* fn(lo, hi, arg) over [0, n) cut into contiguous ranges, on up to 16 threads (the caller's included) */
+typedef struct { void (*fn)(uint64_t, uint64_t, void *); void *arg; uint64_t lo, hi; } pf_job_t;
+static void *pf_run(void *p) { pf_job_t *j = (pf_job_t *) p; j->fn(j->lo, j->hi, j->arg); return 0; }
+void oatk_parallel_for(uint64_t n, void (*fn)(uint64_t lo, uint64_t hi, void *arg), void *arg)
+{
+    long nt = sysconf(_SC_NPROCESSORS_ONLN), t;
+    pf_job_t job[16];
+    pthread_t th[16];
+    static long min_n = -1;                            /* OATK_PF_MIN: smallest n worth threads (tests lower it) */
+    if (min_n < 0) { const char *e = getenv("OATK_PF_MIN"); min_n = e ? atol(e) : 65536; }
+    if (nt > 16) nt = 16;
+    if (nt < 1 || n < (uint64_t) min_n) nt = 1;
+    if (nt == 1 && min_n <= 1 && n > 1) nt = 4;        /* ... and force threads even on a one-core box */
+    for (t = 0; t < nt; ++t) { job[t].fn = fn; job[t].arg = arg; job[t].lo = n * (uint64_t) t / (uint64_t) nt; job[t].hi = n * (uint64_t) (t + 1) / (uint64_t) nt; }
+    for (t = 1; t < nt; ++t) pthread_create(&th[t], 0, pf_run, &job[t]);
+    pf_run(&job[0]);
+    for (t = 1; t < nt; ++t) pthread_join(th[t], 0);
+}
+
 /* stage timer for tuning: with OATK_TIMING set, prints the time since the previous call to stderr */
 void oatk_tick(const char *what)
 {

@@ -101,6 +101,7 @@ int syncmer_graph_arcs(sr_db_t *sr_db, syncmer_db_t *scm_db, uint32_t min_k_cov,
 /* which GPU the layer uses (default 0), and its release */
 /* after read_error_correction (called by it): refresh the device-resident batch from the corrected host lists */
 int oatk_gpu_update_lists(sr_db_t *sr_db, syncmer_db_t *scm_db);
+void oatk_parallel_for(uint64_t n, void (*fn)(uint64_t lo, uint64_t hi, void *arg), void *arg);
 void oatk_tick(const char *what);      /* OATK_TIMING=1: stage times on stderr */
 int oatk_gpu_set_device(int device);
 void oatk_gpu_shutdown(void);

@@ -2,6 +2,8 @@ import os
 import sys
 import pytest
 
+os.environ.setdefault("OATK_PF_MIN", "1")     # the host layer's parallel loops use threads even on the small test inputs
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
     if p not in sys.path:
