@@ -157,11 +157,66 @@ void asmg_shrink_link_id(asmg_t *g)
     }
 }
 
+/* Large graphs (the all-syncmer graph of the error-correction step: ~10^7 arcs) spend their time in the two passes
+ * that look every arc's complement up. The look-up is independent per arc, so it is done once, in parallel, into an
+ * index; an arc array that is already symmetric and consistent (what the device tally delivers) then needs no repair
+ * pass at all, and the link ids are handed out from the index in one sequential sweep. Anything else -- a missing
+ * complement, flags or overlaps that disagree, deleted arcs still in the array -- takes the plain path above. */
+typedef struct { const asmg_t *g; uint64_t *comp; int bad; } sym_t;
+
+static void sym_scan(uint64_t lo, uint64_t hi, void *arg)
+{
+    sym_t *S = (sym_t *) arg;
+    const asmg_t *g = S->g;
+    uint64_t i;
+    int bad = 0;
+    for (i = lo; i < hi; ++i) {
+        const asmg_arc_t *a = &g->arc[i], *c = find_arc(g, a->w ^ 1, a->v ^ 1, 1);
+        if (a->del || !c || c->comp != (a->comp ^ 1u) || c->ln != a->ln || c->ls != a->ls) { bad = 1; break; }
+        S->comp[i] = (uint64_t) (c - g->arc);
+    }
+    if (bad) __atomic_store_n(&S->bad, 1, __ATOMIC_RELAXED);
+}
+
+static int finalize_symmetric(asmg_t *g)
+{
+    sym_t S = {g, 0, 0};
+    const uint64_t PENDING = 0x8000000000000000ULL;
+    uint64_t i, next = 0;
+    static long min_arcs = -1;                           /* small graphs have nothing to gain; OATK_PF_MIN (tests) overrides */
+    if (min_arcs < 0) { const char *e = getenv("OATK_PF_MIN"); min_arcs = e ? atol(e) : 1000000; }
+    if (g->n_arc < (uint64_t) min_arcs || g->n_arc == 0) return 0;
+    S.comp = (uint64_t *) malloc(sizeof(uint64_t) * g->n_arc);
+    oatk_parallel_for(g->n_arc, sym_scan, &S);
+    if (S.bad) { free(S.comp); return 0; }
+    /* asmg_shrink_link_id, with the complement taken from the index (no arc is deleted, so "first arc" and "first live
+     * arc" are the same) */
+    for (i = 0; i < g->n_arc; ++i) g->arc[i].link_id |= PENDING;
+    for (i = 0; i < g->n_arc; ++i) {
+        asmg_arc_t *a = &g->arc[i];
+        if (!(a->link_id & PENDING)) continue;
+        a->link_id = next;
+        g->arc[S.comp[i]].link_id = next;
+        ++next;
+    }
+    free(S.comp);
+    return 1;
+}
+
+static int nothing_deleted(const asmg_t *g)
+{
+    uint64_t i;
+    for (i = 0; i < g->n_vtx; ++i) if (g->vtx[i].del) return 0;
+    for (i = 0; i < g->n_arc; ++i) if (g->arc[i].del) return 0;
+    return 1;
+}
+
 void asmg_finalize(asmg_t *g, int do_cleanup)
 {
-    if (do_cleanup) compact(g);
+    if (do_cleanup && !nothing_deleted(g)) compact(g);
     asmg_arc_sort(g);
     asmg_arc_index(g);
+    if (finalize_symmetric(g)) return;
     if (repair_symmetry(g) > 0) { asmg_arc_sort(g); asmg_arc_index(g); }
     asmg_shrink_link_id(g);
 }
@@ -348,6 +403,26 @@ static void index_syncmers(scg_t *g)
     g->scm_u = u;
 }
 
+typedef struct { asmg_t *g; const uint64_t *arcs4; } arc_fill_t;
+
+/* arc records from the device's (v, w, cov, comp) quadruples */
+static void arc_fill(uint64_t lo, uint64_t hi, void *arg)
+{
+    const arc_fill_t *F = (const arc_fill_t *) arg;
+    asmg_t *g = F->g;
+    uint64_t i;
+    for (i = lo; i < hi; ++i) {
+        asmg_arc_t *a = &g->arc[i];
+        memset(a, 0, sizeof(*a));
+        a->v = F->arcs4[4 * i]; a->w = F->arcs4[4 * i + 1];
+        a->cov = (uint32_t) F->arcs4[4 * i + 2]; a->comp = (uint32_t) F->arcs4[4 * i + 3];
+        a->link_id = UINT64_MAX;
+        /* the device filter looked at coverages only; a syncmer deleted by other means (error
+         * correction sets del, syncerr.c:811-812) also removes its arcs (syncasm.c:271) */
+        if (g->vtx[a->v >> 1].del || g->vtx[a->w >> 1].del) a->del = 1;
+    }
+}
+
 scg_t *make_syncmer_graph(sr_db_t *sr_db, syncmer_db_t *scm_db, uint32_t min_k_cov, double min_a_cov_f)
 {
     scg_t *scg;
@@ -380,16 +455,7 @@ scg_t *make_syncmer_graph(sr_db_t *sr_db, syncmer_db_t *scm_db, uint32_t min_k_c
     oatk_tick("graph: arc tally (device) + download");
     g->arc = (asmg_arc_t *) malloc(sizeof(asmg_arc_t) * (n_arcs ? n_arcs : 1));
     g->n_arc = g->m_arc = n_arcs;
-    for (i = 0; i < n_arcs; ++i) {
-        asmg_arc_t *a = &g->arc[i];
-        memset(a, 0, sizeof(*a));
-        a->v = arcs4[4 * i]; a->w = arcs4[4 * i + 1];
-        a->cov = (uint32_t) arcs4[4 * i + 2]; a->comp = (uint32_t) arcs4[4 * i + 3];
-        a->link_id = UINT64_MAX;
-        /* the device filter looked at coverages only; a syncmer deleted by other means (error
-         * correction sets del, syncerr.c:811-812) also removes its arcs (syncasm.c:271) */
-        if (g->vtx[a->v >> 1].del || g->vtx[a->w >> 1].del) a->del = 1;
-    }
+    { arc_fill_t F = {g, arcs4}; oatk_parallel_for(n_arcs, arc_fill, &F); }
     free(arcs4);
     oatk_tick("graph: arc records");
     asmg_finalize(g, 1);
