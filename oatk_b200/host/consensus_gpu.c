@@ -373,6 +373,8 @@ static int64_t arc_overlap(cons_job_t *J, const asmg_arc_t *a, txt_t *t, ovl_tab
     return l;
 }
 
+#define CONS_BLOCK 64
+
 static void *cons_worker(void *arg)
 {
     cons_job_t *J = (cons_job_t *) arg;
@@ -380,23 +382,26 @@ static void *cons_worker(void *arg)
     txt_t t = {0, 0, 0};
     ovl_tab_t tab;
     memset(&tab, 0, sizeof(tab));
-    for (;;) {
-        const uint64_t i = __atomic_fetch_add(&J->next, 1, __ATOMIC_RELAXED);
-        if (J->phase == 0) {
-            if (i >= G->n_vtx) break;
-            asmg_vtx_t *u = &G->vtx[i];
-            if (u->del) continue;
-            t.l = 0;
-            J->len[i] = chain_text(J->db, u->a, u->n, J->scg->scm_db->a, &t, J->hoco, &tab);
-            J->cov[i] = u->cov ? u->cov : unitig_coverage(J->scg, u);
-            J->text[i] = (char *) malloc((size_t) J->len[i] + 1);
-            memcpy(J->text[i], t.s, (size_t) J->len[i]);
-            J->text[i][J->len[i]] = 0;
-        } else {
-            if (i >= G->n_arc) break;
-            const asmg_arc_t *a = &G->arc[i];
-            if (a->del || a->comp) continue;
-            J->ovl[i] = arc_overlap(J, a, &t, &tab);
+    const uint64_t n_items = J->phase == 0 ? G->n_vtx : G->n_arc;
+    for (;;) {                                           /* blocks of indices: most of an error-filtered graph is skipped */
+        const uint64_t lo = __atomic_fetch_add(&J->next, CONS_BLOCK, __ATOMIC_RELAXED);
+        const uint64_t hi = lo + CONS_BLOCK < n_items ? lo + CONS_BLOCK : n_items;
+        if (lo >= n_items) break;
+        for (uint64_t i = lo; i < hi; ++i) {
+            if (J->phase == 0) {
+                asmg_vtx_t *u = &G->vtx[i];
+                if (u->del) continue;
+                t.l = 0;
+                J->len[i] = chain_text(J->db, u->a, u->n, J->scg->scm_db->a, &t, J->hoco, &tab);
+                J->cov[i] = u->cov ? u->cov : unitig_coverage(J->scg, u);
+                J->text[i] = (char *) malloc((size_t) J->len[i] + 1);
+                memcpy(J->text[i], t.s, (size_t) J->len[i]);
+                J->text[i][J->len[i]] = 0;
+            } else {
+                const asmg_arc_t *a = &G->arc[i];
+                if (a->del || a->comp) continue;
+                J->ovl[i] = arc_overlap(J, a, &t, &tab);
+            }
         }
     }
     free(t.s);

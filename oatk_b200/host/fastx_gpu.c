@@ -330,10 +330,14 @@ void fastx_free(fastx_t *x)
 int sr_read_files(sr_db_t *sr_db, const char *const *files, int n_files, size_t max_bases)
 {
     fastx_t x;
+    oatk_tick(0);
     if (fastx_load(files, n_files, max_bases, &x) != 0) return -1;
+    oatk_tick("reads: parse files");
     if (x.limit_reached)
         fprintf(stderr, "[M::%s] data limit (%lu) reached. Discard the remaining sequences...\n", "sr_read", (unsigned long) max_bases);
     const int rc = sr_read_mem(sr_db, x.bases, x.off, x.names, x.n);
+    oatk_tick("reads: device pipeline + per-read blocks");
     fastx_free(&x);
+    oatk_tick("reads: free the parse buffers");
     return rc;
 }
