@@ -6,6 +6,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 def build(force=False):
+    if os.environ.get("OATK_HOST_LIB"):          # a prebuilt variant (e.g. an AddressSanitizer build for the test-suite)
+        return os.environ["OATK_HOST_LIB"]
     srcs = [os.path.join(HERE, f) for f in sorted(os.listdir(HERE)) if f.endswith(".c")]
     if not srcs:
         return None
