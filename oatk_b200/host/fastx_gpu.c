@@ -65,7 +65,8 @@ static int blob_open(const char *path, blob_t *b)
         return 0;
     }
     if (st.st_size == 0) { close(fd); b->p = ""; b->n = 0; return 0; }
-    void *m = mmap(0, (size_t) st.st_size, PROT_READ, MAP_PRIVATE | MAP_POPULATE, fd, 0);
+    /* not MAP_POPULATE: the parser's threads fault their own pieces in, in parallel */
+    void *m = mmap(0, (size_t) st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
     close(fd);
     if (m == MAP_FAILED) return -1;
     madvise(m, (size_t) st.st_size, MADV_SEQUENTIAL);
@@ -239,7 +240,15 @@ static int parse_fasta_parallel(const char *buf, size_t n, int eof_known_at_end,
             uint64_t nr = 0, nb = 0;
             for (i = 0; i < np; ++i) { if (pc[i].odd || pc[i].rc) return -1; nr += pc[i].sink.n; nb += pc[i].sink.n_bases; }
             /* room for everything, then every piece gets its window into the final arrays */
-            if (x->n_bases + nb + 1 > x->m_bases) { x->m_bases = x->n_bases + nb + 1; x->bases = (char *) realloc(x->bases, x->m_bases); }
+            if (x->n_bases + nb + 1 > x->m_bases) {
+                x->m_bases = x->n_bases + nb + 1; x->bases = (char *) realloc(x->bases, x->m_bases);
+#ifdef MADV_HUGEPAGE
+                if (x->m_bases >= (64u << 20)) {           /* gigabytes of fresh memory: 2 MB pages cut the page faults 512-fold */
+                    const uintptr_t a0 = ((uintptr_t) x->bases + 0x1fffff) & ~(uintptr_t) 0x1fffff, a1 = ((uintptr_t) x->bases + x->m_bases) & ~(uintptr_t) 0x1fffff;
+                    if (a1 > a0) madvise((void *) a0, a1 - a0, MADV_HUGEPAGE);
+                }
+#endif
+            }
             if (x->n + nr + 2 > x->m) {
                 x->m = x->n + nr + 2;
                 x->off = (uint64_t *) realloc(x->off, (x->m + 1) * sizeof(uint64_t));
