@@ -152,7 +152,10 @@ int sr_read_mem(sr_db_t *sr_db, const char *bases, const uint64_t *off, char **n
     pthread_mutex_lock(&g_lock);
     pipe = g_spare; g_spare = 0;
     pthread_mutex_unlock(&g_lock);
-    if (!pipe && sg_pipe_create(g_device, SR_READ_SLOTS, &pipe) != SG_OK) {
+    int slots = getenv("OATK_SR_SLOTS") ? atoi(getenv("OATK_SR_SLOTS")) : SR_READ_SLOTS;      /* tuning knob; the pipeline takes 1..8 */
+    if (slots < 1) slots = 1;
+    if (slots > 8) slots = 8;
+    if (!pipe && sg_pipe_create(g_device, slots, &pipe) != SG_OK) {
         fprintf(stderr, "[E::%s] no usable CUDA device %d (libsyncgpu has no CPU path)\n", __func__, g_device);
         return SG_E_CUDA;
     }
