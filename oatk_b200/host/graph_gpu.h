@@ -123,6 +123,14 @@ int syncasm(char **file_in, int n_file, size_t m_data, int k, int s, int bubble_
 int oatk_syncasm_graph_stage(sr_db_t *sr_db, scg_t *scg, scg_ra_v *ra_db, int bubble_size, int tip_size, double weak_cross,
         int do_unzip, int n_threads, char *out, int VERBOSE);
 int scg_is_empty(scg_t *scg);
+/* report_gpu.c: GFA of the graph as it stands (no consensus run), unitig syncmer lists, per-component statistics, alignment
+ * records, and the arc coverage recount from the reads (syncasm.c:825, 857, 423, 309; alignment.c:686-708) */
+void scg_print(scg_t *g, FILE *fo, int no_seq);
+void scg_print_unitig_syncmer_list(scg_t *g, FILE *fo);
+void scg_subgraph_stat(scg_t *scg, FILE *fo);
+void scg_arc_coverage(scg_t *scg, sr_db_t *sr_db);
+void scg_ra_print(scg_ra_t *ra, FILE *fo);
+void scg_rv_print(scg_ra_v *rv, FILE *fo);
 void scg_meta_clean(scg_meta_t *meta);
 void scg_meta_destroy(scg_meta_t *meta);
 /* repeat unzipping (unzip_gpu.c; reference syncasm.c:682, 1090, 1486): scg_multiplex returns the number of

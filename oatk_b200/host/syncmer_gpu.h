@@ -74,6 +74,10 @@ typedef struct {
 } syncmer_db_t;
 #endif
 
+#ifndef KSTRING_H              /* klib's kstring.h provides this inside the reference tree */
+typedef struct { size_t l, m; char *s; } kstring_t;
+#endif
+
 extern const unsigned char seq_nt4_table[256];
 extern const char char_nt4_table[4];
 
@@ -93,6 +97,11 @@ void syncmer_db_destroy(syncmer_db_t *scm_db);
 void get_kmer_seq(uint8_t *hoco_s, uint32_t pos, int l, uint32_t rev, uint8_t *kmer_s);
 void get_kmer_dna_seq(uint8_t *hoco_s, uint32_t pos, int l, uint32_t rev, char *dna_seq);
 void print_hoco_seq(sr_t *sr, FILE *fo);
+/* report_gpu.c: the debugging printers (syncmer.c:1164-1216). k = s-mer length, w = k-mer length, as the reference names them */
+void get_hoco_seq(sr_t *sr, kstring_t *s);
+void print_syncmer_on_seq(sr_t *sr, uint32_t n, int k, int w, FILE *fo);
+void print_all_syncmers_on_seq(sr_t *sr, int k, int w, FILE *fo);
+void print_aligned_syncmers_on_seq(sr_t *sr, int w, uint32_t beg, uint32_t end, FILE *fo);
 
 /* arcs of make_syncmer_graph (syncasm.c:236-282) for the database just collected:
  * 4 uint64 per arc (v, w, cov, comp), sorted by (v, w, comp); caller frees. */
