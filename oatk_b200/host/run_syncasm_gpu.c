@@ -79,6 +79,7 @@ int oatk_syncasm_graph_stage(sr_db_t *sr_db, scg_t *scg, scg_ra_v *ra_db, int bu
     if (!(fo = open_out(out, ".utg.gfa"))) return 1;
     scg_consensus(sr_db, scg, 0, 0, fo);
     fclose(fo);
+    if (VERBOSE > 1) scg_subgraph_stat(scg, stderr);
 
     /* bubbles are haplotypes until the repeats are unzipped: only tips go before that */
     fprintf(stderr, "[M::syncasm] syncmer graph cleanup\n");
@@ -180,6 +181,7 @@ int syncasm(char **file_in, int n_file, size_t m_data, int k, int s, int bubble_
     }
     fprintf(stderr, "[M::%s] syncmer graph stats\n", __func__);
     scg_stat(scg, stderr, 0);
+    if (VERBOSE > 1) scg_subgraph_stat(scg, stderr);
 
     fprintf(stderr, "[M::%s] syncmer graph unitigging\n", __func__);
     process_mergeable_unitigs(scg);
