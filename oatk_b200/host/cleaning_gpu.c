@@ -106,6 +106,47 @@ static uint64_t weighted_len(const asmg_t *g, const uint64_t *v, size_t n)
     return wt;
 }
 
+/* arcs grouped by the unbranched chain they lie on (graph.c:382-437): per link id a group number, chains first in
+ * vertex order, then every remaining live arc a group of its own; caller frees */
+uint32_t *asmg_uext_arc_group(asmg_t *g, uint32_t *n_group)
+{
+    const uint64_t n_link = asmg_max_link_id(g) + 1;
+    uint32_t *group_of = (uint32_t *) malloc(sizeof(uint32_t) * n_link), group = 0;
+    uint8_t *visited = (uint8_t *) calloc(g->n_vtx ? g->n_vtx : 1, 1);
+    vec_t path = {0, 0, 0};
+    uint64_t i, j, len;
+    int o;
+    memset(group_of, 0xff, sizeof(uint32_t) * n_link);
+    for (i = 0; i < g->n_vtx; ++i) {
+        uint32_t na = 0;
+        if (visited[i] || g->vtx[i].del) continue;
+        for (o = 0; o < 2; ++o) {
+            const int kind = chain_from(g, i << 1 | (uint64_t) o, (int32_t) (g->n_vtx * 2 + 1), &len, &path, 0);
+            for (j = 1; j < path.n; ++j) {
+                const asmg_arc_t *a = arcs_of(g, path.a[j - 1]);
+                uint64_t k = 0;
+                while (a[k].w != path.a[j] || a[k].del) ++k;
+                group_of[a[k].link_id] = group;
+                visited[path.a[j] >> 1] = 1;
+                ++na;
+            }
+            if (kind == END_SHARED) {
+                const asmg_arc_t *a = arcs_of(g, path.a[path.n - 1]);
+                uint64_t k = 0;
+                while (a[k].del) ++k;
+                group_of[a[k].link_id] = group;
+                ++na;
+            }
+        }
+        if (na > 0) ++group;
+        visited[i] = 1;
+    }
+    for (i = 0; i < g->n_arc; ++i) if (!g->arc[i].del && group_of[g->arc[i].link_id] == UINT32_MAX) group_of[g->arc[i].link_id] = group++;
+    if (n_group) *n_group = group;
+    free(path.a); free(visited);
+    return group_of;
+}
+
 uint64_t asmg_drop_tip(asmg_t *g, int32_t tip_cnt, uint64_t tip_len, int protect_super_tip, int do_cleanup, int VERBOSE)
 {
     const uint64_t n_or = g->n_vtx << 1;

@@ -80,6 +80,14 @@ typedef struct {
 #endif
 
 void asmg_destroy(asmg_t *g);
+/* graphutil_gpu.c / cleaning_gpu.c: the queries of graph.h:72-96 that callers beyond syncasm() use */
+int asmg_arc_is_sorted(asmg_t *g);
+uint64_t *asmg_vtx_list(asmg_t *g, uint64_t *_n);
+void asmg_print(asmg_t *g, FILE *fo, int no_seq);
+uint32_t *asmg_uext_arc_group(asmg_t *g, uint32_t *n);
+uint32_t *asmg_subgraph(asmg_t *g, uint32_t *seeds, uint32_t n, uint32_t step, uint64_t dist, uint32_t *_nv, int modify_graph);
+int asmg_tarjans_scc(asmg_t *g, int *scc);
+int asmg_path_exists(asmg_t *g, uint32_t source, uint32_t sink, uint32_t step, uint64_t dist, uint32_t *_step, uint64_t *_dist);
 void asmg_arc_sort(asmg_t *g);
 void asmg_arc_index(asmg_t *g);
 void asmg_shrink_link_id(asmg_t *g);
