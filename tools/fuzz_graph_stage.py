@@ -49,6 +49,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--seeds", default="0:20")
     ap.add_argument("--threads", type=int, default=3)
+    ap.add_argument("--hifi", action="store_true", help="k = 1001, s = 31 and 15 kb reads (the reference's defaults) on larger genomes")
     args = ap.parse_args()
     lo, hi = (int(x) for x in args.seeds.split(":"))
     R = Ref().L
@@ -71,9 +72,13 @@ def main():
     for seed in range(lo, hi):
         rng = np.random.default_rng(1000 + seed)
         k, s = [(101, 11), (201, 15), (301, 21), (501, 31), (151, 13)][int(rng.integers(0, 5))]
+        if args.hifi:
+            k, s = 1001, 31
         genomes = random_genomes(rng, k)
         n = int(rng.integers(400, 1600))
         L1, L2 = int(rng.integers(6000, 14000)), int(rng.integers(1500, 6000))
+        if args.hifi:
+            n, L1, L2 = int(rng.integers(500, 1200)), int(rng.integers(12000, 20000)), int(rng.integers(6000, 12000))
         err = float(rng.choice([0.0001, 0.0003, 0.001]))
         reads = _sample(rng, genomes, n // 2, L1, err) + _sample(rng, genomes, n - n // 2, L2, err)
         mkc, af = int(rng.integers(2, 6)), float(rng.choice([0.0, 0.05, 0.2, 0.35]))
