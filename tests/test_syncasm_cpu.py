@@ -13,6 +13,8 @@ from test_cleaning_cpu import _genome as _genome2
 
 
 def genomes_for(kind, rng):
+    if kind == "linear":                                 # one linear molecule: a single unitig and no arc at all
+        return [bytes(b"ACGT"[i] for i in rng.integers(0, 4, 30000))]
     return _genome2(kind, rng) if kind in ("minor", "branches", "chimera") else _genome(kind, rng)
 
 
@@ -38,6 +40,8 @@ CASES = [
     ("minor", 201, 15, 2, 0.05, 500, (6000, 6000), 0.0003, 11, 0, 0, 100000, 10000, 0.3),
     ("chimera", 201, 15, 2, 0.05, 2500, (5000, 5000), 0.0002, 17, 0, 1, 1000, 3000, 0.3),
     ("branches", 201, 15, 2, 0.05, 700, (6000, 6000), 0.0003, 13, 1, 2, 100000, 10000, 0.3),
+    ("linear", 201, 15, 3, 0.35, 200, (6000, 6000), 0.0, 21, 1, 3, 100000, 10000, 0.3),
+    ("linear", 201, 15, 3, 0.35, 200, (6000, 6000), 0.0, 21, 0, 0, 100000, 10000, 0.3),
 ]
 
 
@@ -62,7 +66,11 @@ def test_graph_stage_matches_reference_command(host, ref, kind, k, s, mkc, af, n
     R.ref_make_graph.restype = C.c_void_p
     rng = np.random.default_rng(seed)
     genomes = genomes_for(kind, rng)
-    reads = _sample(rng, genomes, n // 2, L[0], err) + _sample(rng, genomes, n - n // 2, L[1], err)
+    if kind == "linear":
+        g0 = genomes[0]
+        reads = [g0[p:p + L[0]] for p in (int(x) for x in rng.integers(0, len(g0) - L[0], n))]
+    else:
+        reads = _sample(rng, genomes, n // 2, L[0], err) + _sample(rng, genomes, n - n // 2, L[1], err)
     tmp = tempfile.mkdtemp()
     fa = os.path.join(tmp, "reads.fa")
     with open(fa, "wb") as f:
@@ -85,7 +93,7 @@ def test_graph_stage_matches_reference_command(host, ref, kind, k, s, mkc, af, n
     assert host.oatk_syncasm_graph_stage(rdb, g, ra, bubble, tip, weak, unzip, 3, p_ours.encode(), 0) == 0
     for suffix in (".utg.gfa", ".utg.final.gfa"):
         a, b = open(p_ours + suffix, "rb").read(), open(p_ref + suffix, "rb").read()
-        assert b.count(b"\nS\t") > 0
+        assert b.count(b"\nS\t") > 0 or kind == "linear"      # (everything of a short linear molecule ends up trimmed as tips)
         assert a == b, (suffix, _first_diff(a, b))
         os.unlink(p_ours + suffix)
         os.unlink(p_ref + suffix)
