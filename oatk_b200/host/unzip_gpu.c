@@ -323,17 +323,23 @@ void scg_demultiplex(scg_t *g)
                 }
             }
         }
-        /* arcs between unitigs that do not overlap: last syncmer of one -> first of the other */
+        /* arcs between unitigs that do not overlap: last syncmer of one -> first of the other. A component is closed
+         * under live arcs, so walking the arcs of its members finds the same pairs as trying every member against
+         * every other (syncasm.c:1596-1621); of several arcs v -> w only the first live one counts there, and here */
         for (j = 0; j < members.n * 2; ++j) {
-            const asmg_vtx_t *x = &ug->vtx[members.a[j >> 1]];
-            uint64_t from = (j & 1) ? x->a[0] ^ 1 : x->a[x->n - 1];
+            const uint64_t v = members.a[j >> 1] << 1 | (j & 1);
+            const asmg_vtx_t *x = &ug->vtx[v >> 1];
+            const asmg_arc_t *a = arcs_of(ug, v);
+            uint64_t from = (v & 1) ? x->a[0] ^ 1 : x->a[x->n - 1], last_w = NONE;
             from = map_get(&vertex_of, from >> 1)->u << 1 | (from & 1);
-            for (k = 0; k < members.n * 2; ++k) {
-                const asmg_vtx_t *y = &ug->vtx[members.a[k >> 1]];
-                const asmg_arc_t *a = find(ug, members.a[j >> 1] << 1 | (j & 1), members.a[k >> 1] << 1 | (k & 1), 1);
+            for (k = 0; k < ug->idx_n[v]; ++k) {
+                const asmg_vtx_t *y;
                 uint64_t to;
-                if (!a || a->ln > 0) continue;
-                to = (k & 1) ? y->a[y->n - 1] ^ 1 : y->a[0];
+                if (a[k].del || a[k].w == last_w) continue;
+                last_w = a[k].w;
+                if (a[k].ln > 0) continue;
+                y = &ug->vtx[a[k].w >> 1];
+                to = (a[k].w & 1) ? y->a[y->n - 1] ^ 1 : y->a[0];
                 to = map_get(&vertex_of, to >> 1)->u << 1 | (to & 1);
                 if (map_get(&made, PAIR(from, to))) continue;
                 new_arc(dg, from, to, 0, 0, 0, 0, 0);
