@@ -406,17 +406,20 @@ int64_t find_error_syncmers(scg_t *g, uint32_t err_mer_c, uint32_t max_err_c, ui
 static void rebuild_syncmer_db(sr_db_t *db, syncmer_db_t *S)
 {
     syncmer_t *scm = S->a;
+    uint32_t *cnt = (uint32_t *) calloc(S->n ? S->n : 1, sizeof(uint32_t)), *fwd = (uint32_t *) calloc(S->n ? S->n : 1, sizeof(uint32_t));
     free(S->c); S->c = 0;
     free(S->h); S->h = 0;
-    for (size_t i = 0; i < S->n; ++i) scm[i].cov = 0;
     for (size_t r = 0; r < db->n; ++r)
-        for (uint32_t j = 0; j < db->a[r].n; ++j) ++scm[db->a[r].k_mer[j] >> 1].cov;
+        for (uint32_t j = 0; j < db->a[r].n; ++j) ++cnt[db->a[r].k_mer[j] >> 1];
+    /* the occurrence lists are one malloc block per syncmer (syncmer.c:1359); a block that is large enough is kept --
+     * nearly all syncmers are sequencing errors whose list only shrinks */
     for (size_t i = 0; i < S->n; ++i) {
-        free(scm[i].m_pos);
-        scm[i].m_pos = (uint64_t *) malloc((scm[i].cov ? scm[i].cov : 1) * sizeof(uint64_t));
+        if (cnt[i] > scm[i].cov || !scm[i].m_pos) {
+            free(scm[i].m_pos);
+            scm[i].m_pos = (uint64_t *) malloc((cnt[i] ? cnt[i] : 1) * sizeof(uint64_t));
+        }
         scm[i].cov = 0;
     }
-    uint32_t *fwd = (uint32_t *) calloc(S->n ? S->n : 1, sizeof(uint32_t));
     for (size_t r = 0; r < db->n; ++r) {
         const sr_t *sr = &db->a[r];
         for (uint32_t j = 0; j < sr->n; ++j) {
@@ -426,7 +429,7 @@ static void rebuild_syncmer_db(sr_db_t *db, syncmer_db_t *S)
         }
     }
     for (size_t i = 0; i < S->n; ++i) scm[i].del = !fwd[i];   /* syncerr.c:805-812 */
-    free(fwd);
+    free(fwd); free(cnt);
 }
 
 /* ---------------------------------------------------------------- driver */
