@@ -161,15 +161,25 @@ static inline void str_room(str_t *s, size_t extra)
     if (s->l + extra + 1 >= s->m) { s->m = (s->l + extra + 2) * 2; s->s = (char *) realloc(s->s, s->m); }
 }
 static inline void str_add(str_t *s, const char *p, size_t l) { str_room(s, l); memcpy(s->s + s->l, p, l); s->l += l; s->s[s->l] = 0; }
-static inline char comp_base(char c)
+/* complement by table; the graph's strings hold ACGT (and N for syncmers without a copy), anything else stays as it is */
+static const char *comp_table(void)
 {
-    switch (c) { case 'A': return 'T'; case 'C': return 'G'; case 'G': return 'C'; case 'T': return 'A'; }
-    return c;                                           /* the graph's strings hold ACGT (and N for syncmers without a copy) */
+    static char t[256];
+    static volatile int ready;
+    if (!ready) {
+        for (int c = 0; c < 256; ++c) t[c] = (char) c;
+        t['A'] = 'T'; t['C'] = 'G'; t['G'] = 'C'; t['T'] = 'A';
+        __sync_synchronize();
+        ready = 1;
+    }
+    return t;
 }
 static inline void str_add_rc(str_t *s, const char *p, size_t l)
 {
+    const char *t = comp_table();
     str_room(s, l);
-    for (size_t i = 0; i < l; ++i) s->s[s->l + i] = comp_base(p[l - 1 - i]);
+    char *o = s->s + s->l;
+    for (size_t i = 0; i < l; ++i) o[i] = t[(unsigned char) p[l - 1 - i]];
     s->l += l; s->s[s->l] = 0;
 }
 static inline void v64_push(v64_t *v, uint64_t x) { if (v->n == v->m) { v->m = v->m ? v->m * 2 : 16; v->a = (uint64_t *) realloc(v->a, v->m * 8); } v->a[v->n++] = x; }

@@ -432,10 +432,34 @@ void get_kmer_seq(uint8_t *hoco_s, uint32_t pos, int l, uint32_t rev, uint8_t *k
     for (i = 0; i < l; ++i) kmer_s[i] = (uint8_t) (rev ? 3 - hoco_base(hoco_s, pos + l - 1 - i) : hoco_base(hoco_s, pos + i));
 }
 
+/* l bases from hoco position pos as text, reverse-complemented when rev. Whole packed bytes go through a table of
+ * four characters per byte (the error correction unpacks every block of every read with this). */
 void get_kmer_dna_seq(uint8_t *hoco_s, uint32_t pos, int l, uint32_t rev, char *dna_seq)
 {
-    int i;
-    for (i = 0; i < l; ++i) dna_seq[i] = char_nt4_table[rev ? 3 - hoco_base(hoco_s, pos + l - 1 - i) : hoco_base(hoco_s, pos + i)];
+    static uint32_t fwd4[256], rc4[256];
+    static volatile int ready;
+    int i = 0;
+    if (!ready) {
+        int b, j;
+        for (b = 0; b < 256; ++b) {
+            char f[4], r[4];
+            for (j = 0; j < 4; ++j) { const int c = (b >> ((3 - j) * 2)) & 3; f[j] = char_nt4_table[c]; r[3 - j] = char_nt4_table[3 - c]; }
+            memcpy(&fwd4[b], f, 4); memcpy(&rc4[b], r, 4);
+        }
+        __sync_synchronize();
+        ready = 1;
+    }
+    if (!rev) {
+        uint32_t p = pos;
+        for (; i < l && (p & 3); ++i, ++p) dna_seq[i] = char_nt4_table[hoco_base(hoco_s, p)];
+        for (; i + 4 <= l; i += 4, p += 4) memcpy(dna_seq + i, &fwd4[hoco_s[p >> 2]], 4);
+        for (; i < l; ++i, ++p) dna_seq[i] = char_nt4_table[hoco_base(hoco_s, p)];
+    } else {
+        uint32_t p = pos + (uint32_t) l;                   /* one past the base that comes out first */
+        for (; i < l && (p & 3); ++i) dna_seq[i] = char_nt4_table[3 - hoco_base(hoco_s, --p)];
+        for (; i + 4 <= l; i += 4) { p -= 4; memcpy(dna_seq + i, &rc4[hoco_s[p >> 2]], 4); }
+        for (; i < l; ++i) dna_seq[i] = char_nt4_table[3 - hoco_base(hoco_s, --p)];
+    }
 }
 
 void print_hoco_seq(sr_t *sr, FILE *fo)

@@ -98,3 +98,19 @@ def test_reports_match_reference(host, ref, kind, k, s, mkc, seed):
     ref.free(g=g1)
     ref.free(g=g2)
     ref.free(rdb, rscm)
+
+
+def test_get_kmer_dna_seq_matches_reference(host, ref):
+    """every alignment of start and length against the packed bytes, both strands"""
+    rng = np.random.default_rng(9)
+    packed = rng.integers(0, 256, 400, dtype=np.uint8)
+    for L in (host, ref.L):
+        L.get_kmer_dna_seq.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_uint32, C.c_char_p]
+        L.get_kmer_dna_seq.restype = None
+    for pos in list(range(0, 9)) + [int(x) for x in rng.integers(0, 1000, 40)]:
+        for ln in list(range(0, 14)) + [int(x) for x in rng.integers(14, 500, 25)]:
+            for rev in (0, 1):
+                a, b = C.create_string_buffer(ln + 8), C.create_string_buffer(ln + 8)
+                host.get_kmer_dna_seq(packed.ctypes.data, pos, ln, rev, a)
+                ref.L.get_kmer_dna_seq(packed.ctypes.data, pos, ln, rev, b)
+                assert a.raw[:ln] == b.raw[:ln] and a.raw[ln:] == b"\0" * 8, (pos, ln, rev)
