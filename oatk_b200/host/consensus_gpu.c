@@ -186,6 +186,16 @@ static inline void txt_room(txt_t *t, size_t extra)
     if (t->l + extra + 1 > t->m) { t->m = (t->l + extra + 1) * 2 + 256; t->s = (char *) realloc(t->s, t->m); }
 }
 
+__attribute__((optimize("O3"))) static void lane_add(uint16_t *restrict lane, const uint8_t *restrict rl, uint64_t l)
+{
+    for (uint64_t j = 0; j < l; ++j) lane[j] = (uint16_t) (lane[j] + rl[j]);
+}
+
+__attribute__((optimize("O3"))) static void lane_add_rev(uint16_t *restrict lane, const uint8_t *restrict rl, uint64_t l)
+{
+    for (uint64_t j = 0; j < l; ++j) lane[j] = (uint16_t) (lane[j] + rl[l - 1 - j]);
+}
+
 /* out == NULL: only the length is wanted (arc overlaps) */
 static int64_t syncmer_text(const sr_db_t *db, const syncmer_t *m, int rev, int64_t from, txt_t *out, int hoco_only)
 {
@@ -221,9 +231,13 @@ static int64_t syncmer_text(const sr_db_t *db, const syncmer_t *m, int rev, int6
         out->l += l;
         return written;
     }
-    /* summed run lengths - 1 per hoco base over the uncorrected occurrences, in the syncmer's orientation */
+    /* summed run lengths - 1 per hoco base over the uncorrected occurrences, in the syncmer's orientation. This is
+     * the bulk of the consensus (bases x coverage additions): the one-byte run lengths are added into 16-bit lanes
+     * with plain loops the compiler vectorises, folded into the 64-bit sums every 256 copies (255 * 256 < 2^16); the
+     * rare runs of 255 or more, kept in a side list per read, are patched in on top */
     uint64_t *tot = (uint64_t *) calloc(l, sizeof(uint64_t));
-    uint32_t copies = 0;
+    uint16_t *lane = (uint16_t *) calloc(l, sizeof(uint16_t));
+    uint32_t copies = 0, pending = 0;
     for (i = 0; i < m->cov; ++i) {
         if (occ_is_corrected(db, m->m_pos[i])) continue;
         const sr_t *t = &db->a[m->m_pos[i] >> 32];
@@ -231,13 +245,22 @@ static int64_t syncmer_text(const sr_db_t *db, const syncmer_t *m, int rev, int6
         const uint64_t rr = (q & 1) ^ (uint64_t) rev;
         q >>= 1;
         if (!rr) q += (uint64_t) from;
-        uint32_t side = 0;                             /* entries of the long-run list in front of q */
-        if (t->ho_l_rl) for (uint64_t j = 0; j < q; ++j) side += t->ho_rl[j] == 255;
         const uint8_t *rl8 = t->ho_rl + q;
-        if (rr) for (uint64_t j = 0; j < l; ++j) { uint32_t rl = rl8[j]; if (rl == 255) rl = t->ho_l_rl[side++]; tot[l - 1 - j] += rl; }
-        else for (uint64_t j = 0; j < l; ++j) { uint32_t rl = rl8[j]; if (rl == 255) rl = t->ho_l_rl[side++]; tot[j] += rl; }
+        if (rr) lane_add_rev(lane, rl8, l);
+        else lane_add(lane, rl8, l);
+        if (t->ho_l_rl) {                              /* this read has long runs: swap the 255 marks for the real lengths */
+            uint32_t side = 0;                         /* entries of the long-run list in front of q */
+            for (uint64_t j = 0; j < q; ++j) side += t->ho_rl[j] == 255;
+            for (const uint8_t *z = (const uint8_t *) memchr(rl8, 255, l); z; z = (const uint8_t *) memchr(z + 1, 255, l - (size_t) (z + 1 - rl8))) {
+                const uint64_t j = (uint64_t) (z - rl8);
+                tot[rr ? l - 1 - j : j] += (uint64_t) t->ho_l_rl[side++] - 255;
+            }
+        }
         ++copies;
+        if (++pending == 256) { for (uint64_t j = 0; j < l; ++j) { tot[j] += lane[j]; lane[j] = 0; } pending = 0; }
     }
+    for (uint64_t j = 0; j < l; ++j) tot[j] += lane[j];
+    free(lane);
     if (!out) {
         for (uint64_t j = 0; j < l; ++j) written += lround((double) tot[j] / copies);
         free(tot);

@@ -76,14 +76,17 @@ int oatk_syncasm_graph_stage(sr_db_t *sr_db, scg_t *scg, scg_ra_v *ra_db, int bu
 {
     const int k = sr_db->k;
     FILE *fo;
+    oatk_tick(0);
     if (!(fo = open_out(out, ".utg.gfa"))) return 1;
     scg_consensus(sr_db, scg, 0, 0, fo);
     fclose(fo);
+    oatk_tick("stage: consensus + .utg.gfa");
     if (VERBOSE > 1) scg_subgraph_stat(scg, stderr);
 
     /* bubbles are haplotypes until the repeats are unzipped: only tips go before that */
     fprintf(stderr, "[M::syncasm] syncmer graph cleanup\n");
     clean_graph(scg, do_unzip <= 0, bubble_size, tip_size, weak_cross, VERBOSE);
+    oatk_tick("stage: clean-up");
 
     if (do_unzip > 0) {
         const uint32_t max_n_scm = (uint32_t) ceil(30000.0 / k);      /* repeats up to ~15 kb: what a HiFi read can span */
@@ -103,24 +106,29 @@ int oatk_syncasm_graph_stage(sr_db_t *sr_db, scg_t *scg, scg_ra_v *ra_db, int bu
         scg_read_alignment(sr_db, ra_db, scg, n_threads, 1);
         scg_ra_arc_coverage(scg, sr_db, ra_db, 0, VERBOSE);
         asmg_remove_weak_crosslink(scg->utg_asmg, weak_cross, 10, 0, VERBOSE);
+        oatk_tick("stage: unzip rounds (alignment, multiplex)");
 
         scg_demultiplex(scg);
         scg_read_alignment(sr_db, ra_db, scg, n_threads, 0);
         scg_ra_utg_coverage(scg, sr_db, ra_db, VERBOSE);
         scg_ra_arc_coverage(scg, sr_db, ra_db, 1, VERBOSE);
+        oatk_tick("stage: demultiplex, alignment, coverages");
         scg_consensus(sr_db, scg, 0, 0, 0);                            /* lengths and overlaps for the clean-up */
         clean_graph(scg, 1, bubble_size, tip_size, weak_cross, VERBOSE);
+        oatk_tick("stage: consensus + clean-up");
     }
 
     scg_read_alignment(sr_db, ra_db, scg, n_threads, 0);
     scg_ra_utg_coverage(scg, sr_db, ra_db, VERBOSE);
     scg_ra_arc_coverage(scg, sr_db, ra_db, 1, VERBOSE);
+    oatk_tick("stage: final alignment + coverages");
 
     fprintf(stderr, "[M::syncasm] syncmer graph stats after final processing\n");
     scg_stat(scg, stderr, 0);
     if (!(fo = open_out(out, ".utg.final.gfa"))) return 1;
     scg_consensus(sr_db, scg, 0, 0, fo);
     fclose(fo);
+    oatk_tick("stage: consensus + .utg.final.gfa");
 
     return 0;
 }

@@ -134,3 +134,40 @@ def test_gfa_matches_reference(host, ref, k, s, mkc, a, G, n, L, err, seed, unit
     ref.free(g=g1)
     ref.free(g=g2)
     ref.free(rdb, rscm)
+
+
+def test_long_homopolymer_runs(host, ref):
+    """runs of 255 bases and more live in a side list per read (ho_l_rl); their lengths vary from read to read, so the
+    consensus has to average the real lengths, not the 255 marks"""
+    rng = np.random.default_rng(11)
+    rnd = lambda n: bytes(b"ACGT"[i] for i in rng.integers(0, 4, n))
+    parts = [rnd(3000), rnd(2500), rnd(3500), rnd(2000), rnd(3000)]
+    runs = [(b"A", 300), (b"C", 255), (b"T", 700), (b"G", 254)]
+    reads = []
+    for _ in range(60):
+        seq = parts[0]
+        for (base, n), nxt in zip(runs, parts[1:]):
+            seq += base * (n + int(rng.integers(-3, 4))) + nxt
+        a = int(rng.integers(0, 2000))
+        b = len(seq) - int(rng.integers(0, 2000))
+        r = seq[a:b]
+        reads.append(r if rng.integers(0, 2) else _rc(r))
+    bases, off = pack_reads(reads)
+    for k, s in ((301, 15), (101, 11)):
+        rdb, _ = ref.extract(bases, off, k, s)
+        rscm = ref.collect(rdb)
+        g1, g2 = ref.graph(rdb, rscm, 3, 0.2), ref.graph(rdb, rscm, 3, 0.2)
+        assert g1 and g2
+        ref.unitig(g1)
+        ref.unitig(g2)
+        ref.L.ref_write_gfa.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p]
+        path = tempfile.mktemp()
+        assert ref.L.ref_write_gfa(rdb, g2, path.encode()) == 0
+        want = open(path, "rb").read()
+        os.unlink(path)
+        got = _gfa(lambda fo: host.scg_consensus(rdb, g1, 0, 0, fo))
+        assert got == want, _first_diff(got, want)
+        assert b"A" * 290 in want or b"T" * 290 in want, "no long run made it into a unitig"
+        ref.free(g=g1)
+        ref.free(g=g2)
+        ref.free(rdb, rscm)
