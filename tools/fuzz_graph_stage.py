@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Randomised hunt for divergences in the graph stage of syncasm() (host code, no GPU): random mixtures of repeats,
 haplotypes, rare molecules and recombinants, random k / coverage thresholds / clean-up limits; the reference's whole
-command against oatk_syncasm_graph_stage fed with the reference's own front half, both GFA files compared.
+command against this layer's read error correction and graph stage, fed with the reference's extraction, database and
+graph construction (the device rows, which have their own GPU tests); both GFA files compared.
 
   python tools/fuzz_graph_stage.py [--seeds 0:40] [--threads 3]
 
@@ -49,6 +50,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--seeds", default="0:20")
     ap.add_argument("--threads", type=int, default=3)
+    ap.add_argument("--ref-ec", action="store_true", help="read error correction of our arm by the reference (default: by this layer, without the up-front consensus)")
     ap.add_argument("--hifi", action="store_true", help="k = 1001, s = 31 and 15 kb reads (the reference's defaults) on larger genomes")
     args = ap.parse_args()
     lo, hi = (int(x) for x in args.seeds.split(":"))
@@ -67,6 +69,8 @@ def main():
     H.oatk_syncasm_graph_stage.restype = C.c_int
     H.oatk_syncasm_graph_stage.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_char_p, C.c_int]
     H.scg_ra_v_destroy.argtypes = [C.c_void_p]
+    H.read_error_correction.restype = None
+    H.read_error_correction.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_uint32, C.c_uint32, C.c_uint32, C.c_double, C.c_int, C.c_void_p, C.c_int]
     bad = []
     tmp = tempfile.mkdtemp()
     for seed in range(lo, hi):
@@ -103,8 +107,11 @@ def main():
         scm = R.ref_collect(rdb)
         if ec:
             g = R.ref_make_graph(rdb, scm, 0, 0.0)
-            R.ref_write_gfa2(rdb, g, 1, 1, b"/dev/null")
-            R.ref_read_ec(rdb, g, 0.02, mkc, mkc * 10, mkc, af, 2)
+            if args.ref_ec:
+                R.ref_write_gfa2(rdb, g, 1, 1, b"/dev/null")
+                R.ref_read_ec(rdb, g, 0.02, mkc, mkc * 10, mkc, af, 2)
+            else:
+                H.read_error_correction(rdb, g, 0.02, mkc, mkc * 10, mkc, af, args.threads, None, 0)
             R.ref_scg_free(g)
         g = R.ref_make_graph(rdb, scm, mkc, af)
         R.ref_unitig(g)
