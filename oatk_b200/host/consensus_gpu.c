@@ -238,26 +238,39 @@ static int64_t syncmer_text(const sr_db_t *db, const syncmer_t *m, int rev, int6
     uint64_t *tot = (uint64_t *) calloc(l, sizeof(uint64_t));
     uint16_t *lane = (uint16_t *) calloc(l, sizeof(uint16_t));
     uint32_t copies = 0, pending = 0;
-    for (i = 0; i < m->cov; ++i) {
-        if (occ_is_corrected(db, m->m_pos[i])) continue;
-        const sr_t *t = &db->a[m->m_pos[i] >> 32];
-        uint64_t q = t->m_pos[m->m_pos[i] >> 1 & MAX_RD_SCM];
-        const uint64_t rr = (q & 1) ^ (uint64_t) rev;
-        q >>= 1;
-        if (!rr) q += (uint64_t) from;
-        const uint8_t *rl8 = t->ho_rl + q;
-        if (rr) lane_add_rev(lane, rl8, l);
-        else lane_add(lane, rl8, l);
-        if (t->ho_l_rl) {                              /* this read has long runs: swap the 255 marks for the real lengths */
-            uint32_t side = 0;                         /* entries of the long-run list in front of q */
-            for (uint64_t j = 0; j < q; ++j) side += t->ho_rl[j] == 255;
-            for (const uint8_t *z = (const uint8_t *) memchr(rl8, 255, l); z; z = (const uint8_t *) memchr(z + 1, 255, l - (size_t) (z + 1 - rl8))) {
-                const uint64_t j = (uint64_t) (z - rl8);
-                tot[rr ? l - 1 - j : j] += (uint64_t) t->ho_l_rl[side++] - 255;
-            }
+    /* the copies sit in as many different reads: their run lengths are fetched a batch ahead of the additions */
+    enum { AHEAD = 16 };
+    struct { const sr_t *t; const uint8_t *rl8; uint64_t q; int rr; } nxt[AHEAD];
+    for (uint32_t i0 = 0; i0 < m->cov; i0 += AHEAD) {
+        uint32_t nb = 0;
+        for (i = i0; i < m->cov && i < i0 + AHEAD; ++i) {
+            if (occ_is_corrected(db, m->m_pos[i])) continue;
+            const sr_t *t = &db->a[m->m_pos[i] >> 32];
+            uint64_t q = t->m_pos[m->m_pos[i] >> 1 & MAX_RD_SCM];
+            const int rr = (int) ((q & 1) ^ (uint64_t) rev);
+            q >>= 1;
+            if (!rr) q += (uint64_t) from;
+            nxt[nb].t = t; nxt[nb].q = q; nxt[nb].rr = rr; nxt[nb].rl8 = t->ho_rl + q;
+            for (uint64_t o = 0; o < l; o += 64) __builtin_prefetch(nxt[nb].rl8 + o, 0, 1);
+            ++nb;
         }
-        ++copies;
-        if (++pending == 256) { for (uint64_t j = 0; j < l; ++j) { tot[j] += lane[j]; lane[j] = 0; } pending = 0; }
+        for (uint32_t b = 0; b < nb; ++b) {
+            const sr_t *t = nxt[b].t;
+            const uint8_t *rl8 = nxt[b].rl8;
+            const uint64_t q = nxt[b].q, rr = (uint64_t) nxt[b].rr;
+            if (rr) lane_add_rev(lane, rl8, l);
+            else lane_add(lane, rl8, l);
+            if (t->ho_l_rl) {                          /* this read has long runs: swap the 255 marks for the real lengths */
+                uint32_t side = 0;                     /* entries of the long-run list in front of q */
+                for (uint64_t j = 0; j < q; ++j) side += t->ho_rl[j] == 255;
+                for (const uint8_t *z = (const uint8_t *) memchr(rl8, 255, l); z; z = (const uint8_t *) memchr(z + 1, 255, l - (size_t) (z + 1 - rl8))) {
+                    const uint64_t j = (uint64_t) (z - rl8);
+                    tot[rr ? l - 1 - j : j] += (uint64_t) t->ho_l_rl[side++] - 255;
+                }
+            }
+            ++copies;
+            if (++pending == 256) { for (uint64_t j = 0; j < l; ++j) { tot[j] += lane[j]; lane[j] = 0; } pending = 0; }
+        }
     }
     for (uint64_t j = 0; j < l; ++j) tot[j] += lane[j];
     free(lane);
