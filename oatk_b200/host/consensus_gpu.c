@@ -156,6 +156,12 @@ static int neighbour_offset(const sr_db_t *db, const syncmer_t *m1, uint64_t rc1
     const uint64_t n1 = m1->cov, n2 = m2->cov;
     assert(n1 > 0 && n2 > 0);
     ot_clear(t);
+    /* every occurrence is looked up in its read (was it corrected, where does it start): bring the reads' headers in
+     * first, then the list entries they point at, before the merge below asks for them one by one */
+    for (uint64_t a = 0; a < n1; ++a) __builtin_prefetch(&db->a[o1[a] >> 32], 0, 1);
+    for (uint64_t b = 0; b < n2; ++b) __builtin_prefetch(&db->a[o2[b] >> 32], 0, 1);
+    for (uint64_t a = 0; a < n1; ++a) __builtin_prefetch(&db->a[o1[a] >> 32].m_pos[o1[a] >> 1 & MAX_RD_SCM], 0, 1);
+    for (uint64_t b = 0; b < n2; ++b) __builtin_prefetch(&db->a[o2[b] >> 32].m_pos[o2[b] >> 1 & MAX_RD_SCM], 0, 1);
     uint64_t j0 = 0;                                  /* first occurrence of m2 on a read >= the current one */
     for (uint64_t a = 0; a < n1; ++a) {
         const uint64_t read = o1[a] >> 32, i1 = o1[a] >> 1 & MAX_RD_SCM, s1 = o1[a] & 1;
