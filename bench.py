@@ -175,9 +175,11 @@ def run_reference(args):
     return 0
 
 
-def workload_config(n_gpus, n_reads=None):
-    return {"workload": "syncmer extract+count, %s x %d b synthetic HiFi reads per GPU, k=%d s=%d (BASELINE.json configs[1])" % (
-                "1M" if n_reads in (None, 1000000) else str(n_reads), READ_LEN, K, S),
+def workload_config(n_gpus, n_reads=None, workload="uniform", n_planted=0):
+    extra = "" if workload == "uniform" else "; %d reads per GPU carry a 2-15 kb tandem array (period 2/3/6=TTAGGG/37/171)" % n_planted
+    return {"workload": "syncmer extract+count, %s x %d b synthetic HiFi reads per GPU, k=%d s=%d (BASELINE.json configs[1])%s" % (
+                "1M" if n_reads in (None, 1000000) else str(n_reads), READ_LEN, K, S, extra),
+            "input_class": workload,
             "k": K, "s": S, "read_len": READ_LEN, "error_rate": ERR, "genome_len": 50_000_000,
             "reads_per_gpu": n_reads or 1000000, "parallelism": "reads sharded by record, %d GPU(s)" % n_gpus,
             "l2": "inputs (15 GB per step) larger than L2; no flush needed"}
@@ -195,6 +197,9 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--k", type=int, default=K, help="k-mer size (configs[4] sweep: 501, 1001, 2001)")
     ap.add_argument("--err", type=float, default=ERR, help="per-base error rate of the synthetic reads")
+    ap.add_argument("--workload", default="uniform", choices=("uniform", "repeats"),
+                    help="uniform: configs[1] as is; repeats: the same with every 100th read carrying a 2-15 kb tandem array "
+                         "(period 2, 3, TTAGGG, 37, 171)")
     args = ap.parse_args()
     globals()["K"], globals()["ERR"] = args.k, args.err
     if args.impl == "reference":
@@ -219,6 +224,9 @@ def main():
 
     bases, off = synth_gpu.hifi_reads_gpu(1000 + rank, 50_000_000, n_reads, READ_LEN, ERR, dev, genome_seed=1)
     total = n_reads * READ_LEN
+    n_planted = 0
+    if args.workload == "repeats":
+        n_planted = synth_gpu.plant_repeats_gpu(bases, n_reads, READ_LEN, 100, 77 + rank, dev)
     torch.cuda.synchronize()
 
     ctx = lib.Context(local)          # launches on the legacy default stream = torch's current stream
@@ -313,9 +321,10 @@ def main():
 
     line = {"metric": "HiFi bases/sec syncmer-extract+count", "value": value, "unit": "bases/s", "n_gpus": world,
             "steps": args.steps, "warmup": W, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": workload_config(world, n_reads),
+            "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": workload_config(world, n_reads, args.workload, n_planted),
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
-            "results": {"syncmers": int(sizes.n_syncmers), "distinct_kmers": int(csz.n_unique), "hoco_bases": int(sizes.hoco_bases)}}
+            "results": {"syncmers": int(sizes.n_syncmers), "distinct_kmers": int(csz.n_unique), "hoco_bases": int(sizes.hoco_bases),
+                        "reads_on_exact_scan_path": int(batch.debug_scan_info())}}
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

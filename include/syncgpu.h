@@ -217,6 +217,9 @@ int sg_debug_set_hash_bits(sg_batch *b, int bits);
  * out-of-order pairs the last sort repaired and whether it fell back to the full sort. */
 int sg_debug_set_sort_low_bits(sg_batch *b, int low_bits);
 int sg_debug_sort_info(sg_batch *b, uint64_t *repairs, int *fell_back);
+/* tests only: how many reads of the last sg_extract were finished by scan_exact_kernel (full-hash window
+ * minimum; taken by reads on which identical s-mers keep tying for the minimum: tandem repeats) */
+int sg_debug_scan_info(sg_batch *b, uint64_t *deferred_reads);
 
 /* After read error correction has rewritten the reads' syncmer lists on the host (reference syncerr.c:592-606, 769-817):
  * replace the batch's per-syncmer arrays (read order: k_mer = id << 1 | corrected, m_pos, s_mer; scm_off = n_reads + 1

@@ -236,6 +236,10 @@ static int run_extract(sg_batch *b, uint64_t rec_cap_hint)
     S.n_scm = (uint32_t *) b->n_scm.p;
     S.rec_count = cnt + 2; S.rec_cap = rec_cap;
     S.rec_sid = (uint32_t *) b->rec_sid.p; S.rec_idx = (uint32_t *) b->rec_idx.p; S.rec_mpos = (uint32_t *) b->rec_mpos.p;
+    RS(b->scan_defer, (n + 1) * 4 * sizeof(uint32_t));
+    RS(b->scan_xring, scan_exact_scratch_bytes(b->k, b->s, nullptr));
+    S.defer_count = reinterpret_cast<unsigned int *>(cnt + 5); S.work2 = reinterpret_cast<unsigned int *>(cnt + 6);
+    S.defer = (uint32_t *) b->scan_defer.p; S.xring = (uint64_t *) b->scan_xring.p;
     LAUNCHED(SG_T_SCAN, launch_scan(S, st));
     ctx->t_end(SG_T_SCAN);
 
@@ -263,7 +267,7 @@ int sg_extract(sg_batch *b, int k, int s)
         int rc = run_extract(b, hint);
         if (rc) return rc;
         // the record count decides the size of everything downstream: read it back
-        unsigned long long hc[3];
+        unsigned long long hc[6];
         CK(cudaMemcpyAsync(hc, b->counters.p, sizeof(hc), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         CK(cudaGetLastError());
@@ -272,6 +276,7 @@ int sg_extract(sg_batch *b, int k, int s)
         if (hc[1] > b->lrl_cap) { b->lrl_cap = hc[1] + 16; again = true; }
         if (hc[2] > b->rec_cap) { hint = hc[2] + 16; again = true; }
         b->n_amb_total = hc[0]; b->n_lrl_total = hc[1]; b->n_syncmers = hc[2];
+        b->n_scan_deferred = (uint32_t) hc[5];
         if (!again) break;
         if (attempt == 3) { ctx->err = "side-list capacity did not converge"; return SG_E_NOMEM; }
     }
@@ -320,6 +325,14 @@ static int ensure_sizes(sg_batch *b)
     }
     b->hoco_bases = hb;
     b->sizes_known = true;
+    return SG_OK;
+}
+
+int sg_debug_scan_info(sg_batch *b, uint64_t *deferred_reads)
+{
+    if (!b) return SG_E_ARG;
+    if (!b->extracted) return SG_E_STATE;
+    if (deferred_reads) *deferred_reads = b->n_scan_deferred;
     return SG_OK;
 }
 

@@ -43,12 +43,14 @@ struct sg_batch {
     bool extracted = false, counted = false, sizes_known = false;
     int k = 0, s = 0;
     uint64_t n_syncmers = 0, n_amb_total = 0, n_lrl_total = 0, hoco_bases = 0;
+    uint64_t n_scan_deferred = 0;                // reads of the last sg_extract that went through scan_exact_kernel
     uint64_t h2d_bytes = 0, d2h_bytes = 0;
     // a2-a4 device results (capacity-indexed layout, see sg_common.cuh)
     sg::DevBuf hoff, scan_tmp, hoco_s, ho_rl, nbits, hoco_l, n_amb, n_scm, scm_off, counters;
     uint64_t amb_cap = 0, lrl_cap = 0, rec_cap = 0;
     sg::DevBuf amb_sid, amb_pos, lrl_sid, lrl_idx, lrl_val;
     sg::DevBuf rec_sid, rec_idx, rec_mpos, rec_smer;
+    sg::DevBuf scan_defer, scan_xring;           // reads deferred to scan_exact_kernel and its hash rings
     sg::DevBuf key, occ, m_pos, s_mer, fp;      // read order, one entry per syncmer (fp: second hash)
     sg::DevBuf tup;                              // read order: (occ, s_mer, fp, key) as 32-byte records (sg_extract only)
     bool tup_valid = false;

@@ -33,7 +33,12 @@ struct ScanArgs {
     unsigned long long *rec_count;
     uint64_t rec_cap;
     uint32_t *rec_sid, *rec_idx, *rec_mpos;   // unordered records (one per syncmer): read, rank on the read, start << 1 | open
+    // reads handed over to scan_exact_kernel (see sg_scan.cu): (read, first tile, records so far, CLOSE carry) each
+    unsigned int *defer_count, *work2;        // zeroed before the launch
+    uint32_t *defer;                          // 4 * n_reads
+    uint64_t *xring;                          // scan_exact_scratch_bytes(k, s)
 };
+size_t scan_exact_scratch_bytes(int k, int s, int *grid_out);
 constexpr int SYNC_SCAN_WARPS = 4;  // warps per CTA of the syncmer scan kernel (one read per warp, 16 positions per lane and tile)
 struct ScanGeom {
     int rch;        // ring size in chunks of 16 positions (power of two, >= window + one tile)

@@ -174,3 +174,25 @@ def adversarial_reads(seed, k, s, scale=1):
         out.append(t)
         out.append(revcomp(t))
     return out
+
+
+REPEAT_PERIODS = (2, 3, 6, 37, 171)
+
+
+def repeat_reads(seed, n_reads, read_len, min_arr=2000):
+    """Reads that carry one tandem array each (period 2, 3, 37, 171 or the telomere unit TTAGGG,
+    2 kb up to the whole read) inside random sequence: the input class on which every window
+    position ties for the minimum (the scan kernel's cliff)."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for i in range(n_reads):
+        p = REPEAT_PERIODS[i % len(REPEAT_PERIODS)]
+        unit = b"TTAGGG" if p == 6 else _nohp(rng, p)
+        la = int(rng.integers(min(min_arr, read_len), read_len + 1))
+        st = int(rng.integers(0, read_len - la + 1))
+        arr = (unit * (la // p + 2))[:la]
+        r = _rand(rng, st) + arr + _rand(rng, read_len - st - la)
+        if rng.integers(0, 2):
+            r = revcomp(r)
+        out.append(r)
+    return out

@@ -37,6 +37,35 @@ def test_adversarial(gpu_ctx, oracle, k, s):
     check(gpu_ctx, oracle, synth.adversarial_reads(3, k, s), k, s)
 
 
+@pytest.mark.parametrize("k,s", [(1001, 31), (501, 31), (2001, 31), (301, 15), (40, 1), (12, 11), (20001, 31)])
+def test_tandem_repeats(gpu_ctx, oracle, k, s):
+    """reads carrying tandem arrays (period 2, 3, TTAGGG, 37, 171; 2 kb up to the whole read): every window position
+    ties for the minimum. scan_kernel hands such reads to scan_exact_kernel; both must agree with the reference rules"""
+    from oatk_b200 import lib
+    L = 15000 if k < 20000 else 60000
+    reads = synth.repeat_reads(5, 60, L) + synth.hifi_reads(6, 200000, 20, L, 0.001)
+    r = bytearray(synth.repeat_reads(7, 5, L)[4])
+    for p in (100, L // 2, L // 2 + 1, L - 50):
+        r[p] = ord("N")
+    reads.append(bytes(r))                                    # ambiguous bases inside and around an array
+    bases, off = pack_reads(reads)
+    db, exp = oracle.extract(bases, off, k, s)
+    oracle.free(db)
+    b = lib.Batch(gpu_ctx)
+    b.set_reads_host(bases, off)
+    b.extract(k, s)
+    got = b.extract_download()
+    n_def = b.debug_scan_info()
+    b.close()
+    d = parity.diff(got, exp, parity.EXTRACT_FIELDS)
+    if d:
+        d += parity.per_read_report(got, exp)
+    assert not d, "\n".join(d)
+    if k - s + 1 > 64:
+        assert n_def >= 30, "the repeat reads were expected on the exact path, only %d went" % n_def
+    assert n_def <= len(reads)
+
+
 @pytest.mark.parametrize("k,s", [(63, 31), (95, 21), (127, 31), (96, 31), (1023, 31)])
 def test_kmer_block_shapes(gpu_ctx, oracle, k, s):
     """k-mer lengths around multiples of 32 bases: a last 8-byte Murmur block that is not full of bases, no tail,
