@@ -38,32 +38,55 @@
 
 typedef struct { const char *p; size_t n; int mapped; char *owned; } blob_t;
 
+/* whole gzip stream (possibly several members; plain data passes through unchanged) into one buffer */
+static int blob_inflate(int fd, size_t size_hint, const char *path, blob_t *b)
+{
+    gzFile g = gzdopen(fd, "r");
+    size_t cap = size_hint * 4 + (1 << 20), n = 0;
+    char *buf;
+    int r = 0, zerr = 0;
+    if (!g) { close(fd); return -1; }
+    gzbuffer(g, 1 << 20);
+    buf = (char *) malloc(cap);
+    while (buf) {
+        if (cap - n < (1 << 20)) {
+            char *grown = (char *) realloc(buf, cap + cap / 2);
+            if (!grown) { free(buf); buf = 0; break; }
+            buf = grown; cap += cap / 2;
+        }
+        r = gzread(g, buf + n, (unsigned) ((cap - n) > (1u << 30) ? (1u << 30) : (cap - n)));
+        if (r <= 0) break;
+        n += (size_t) r;
+    }
+    if (!buf) {
+        fprintf(stderr, "[E::%s] out of memory while reading \"%s\"\n", __func__, path);
+        gzclose(g);
+        return -1;
+    }
+    if (r < 0) {
+        /* kseq treats a read error as the end of the stream (kseq.h:96-101) and so does this reader: the records
+         * before the damage are kept. Said aloud here, silently there. */
+        const char *msg = gzerror(g, &zerr);
+        fprintf(stderr, "[W::%s] \"%s\": %s; keeping what was read before the error\n", __func__, path, msg ? msg : "read error");
+    }
+    gzclose(g);
+    b->p = b->owned = buf; b->n = n;
+    return 0;
+}
+
 static int blob_open(const char *path, blob_t *b)
 {
     memset(b, 0, sizeof(*b));
+    if (strcmp(path, "-") == 0) return blob_inflate(dup(STDIN_FILENO), 1 << 24, path, b);   /* kopen.c reads "-" from stdin */
     int fd = open(path, O_RDONLY);
     if (fd < 0) return -1;
     unsigned char magic[2] = {0, 0};
     struct stat st;
     if (fstat(fd, &st) != 0) { close(fd); return -1; }
+    if (!S_ISREG(st.st_mode)) return blob_inflate(fd, 1 << 24, path, b);                      /* pipes, process substitution */
     ssize_t got = pread(fd, magic, 2, 0);
-    if (got == 2 && magic[0] == 0x1f && magic[1] == 0x8b) {
-        /* gzip (possibly several members): inflate the whole stream; zlib is the reference's reader too */
-        gzFile g = gzdopen(fd, "r");
-        if (!g) { close(fd); return -1; }
-        gzbuffer(g, 1 << 20);
-        size_t cap = (size_t) st.st_size * 4 + (1 << 20), n = 0;
-        char *buf = (char *) malloc(cap);
-        for (;;) {
-            if (cap - n < (1 << 20)) { cap += cap / 2; buf = (char *) realloc(buf, cap); }
-            int r = gzread(g, buf + n, (unsigned) ((cap - n) > (1u << 30) ? (1u << 30) : (cap - n)));
-            if (r <= 0) break;
-            n += (size_t) r;
-        }
-        gzclose(g);
-        b->p = b->owned = buf; b->n = n;
-        return 0;
-    }
+    if (got == 2 && magic[0] == 0x1f && magic[1] == 0x8b)
+        return blob_inflate(fd, (size_t) st.st_size, path, b);          /* zlib is the reference's reader too */
     if (st.st_size == 0) { close(fd); b->p = ""; b->n = 0; return 0; }
     /* not MAP_POPULATE: the parser's threads fault their own pieces in, in parallel */
     void *m = mmap(0, (size_t) st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
@@ -71,6 +94,15 @@ static int blob_open(const char *path, blob_t *b)
     if (m == MAP_FAILED) return -1;
     madvise(m, (size_t) st.st_size, MADV_SEQUENTIAL);
     b->p = (const char *) m; b->n = (size_t) st.st_size; b->mapped = 1;
+    return 0;
+}
+
+int fastx_can_open(const char *path)
+{
+    if (strcmp(path, "-") == 0) return 0;
+    int fd = open(path, O_RDONLY);
+    if (fd < 0) return -1;
+    close(fd);
     return 0;
 }
 

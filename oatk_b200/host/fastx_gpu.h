@@ -24,6 +24,8 @@ typedef struct {
 /* reads the files in order; max_bases = 0: no limit. Returns 0, or -1 when a file cannot be opened. */
 int fastx_load(const char *const *files, int n_files, uint64_t max_bases, fastx_t *out);
 void fastx_free(fastx_t *x);
+/* 0 when the file can be opened for reading the way fastx_load would */
+int fastx_can_open(const char *path);
 /* sr_read for files: fastx_load + sr_read_mem, printing the reference's data-limit message */
 int sr_read_files(sr_db_t *sr_db, const char *const *files, int n_files, size_t max_bases);
 

@@ -188,44 +188,232 @@ int sr_db_validate(sr_db_t *sr_db)
     return 0;
 }
 
-/* peak finder the reference borrows from hifiasm (syncmer.c:775-865): lowest point from the left,
- * highest peak after it, then a smaller peak on either side that is separated by a real valley */
-static int find_peaks(int n, int start_cnt, const int64_t *cnt, int *peak_het)
+/*
+ * Peaks of a multiplicity spectrum cnt[0..n) -- what the reference's ha_analyze_count computes (syncmer.c:775-865;
+ * a heuristic it took from hifiasm) and, at verbose levels above 1, prints. The numbers and the printed lines are
+ * part of the contract (-c 0 derives the coverage threshold from the k-mer peak, run_syncasm.c:90-93), so the rule
+ * is restated here piece by piece:
+ *   floor   the spectrum falls from its first used bin (1, or 2 when bin 1 is empty, and not below `first_bin`)
+ *           until it first rises; the bin before the rise is the floor. A spectrum that never rises has no peak (-1).
+ *   summit  the first highest bin after the floor.
+ *   a side peak is the highest local maximum (>= both neighbours, first one wins ties) strictly between floor and
+ *   summit (left) or after the summit, last bin excluded (right). It only counts when it reaches 5 % of the summit and
+ *   the valley between the two dips below 95 % of it; a right peak must also lie within 2.5 x the summit's bin.
+ * With a right peak the summit is the heterozygous peak and the right peak the homozygous one; otherwise the summit
+ * is homozygous and a left peak, if any, heterozygous.
+ */
+typedef struct { int bin; int64_t height; } peak_t;
+
+static int64_t lowest_between(const int64_t *cnt, int from, int to, int64_t start)
 {
-    int i, low, top, left = -1, right = -1;
-    int64_t vtop, vleft = -1, vright = -1, mn;
-    *peak_het = -1;
-    low = cnt[1] > 0 ? 1 : 2;
-    if (low < start_cnt) low = start_cnt;
-    for (i = low + 1; i < n && cnt[i] <= cnt[i - 1]; ++i) {}
-    low = i - 1;
-    if (low == n - 1) return -1;
-    top = low + 1; vtop = cnt[top];
-    for (i = low + 1; i < n; ++i) if (cnt[i] > vtop) vtop = cnt[i], top = i;
-    for (i = top - 1; i > low; --i)
-        if (cnt[i] >= cnt[i - 1] && cnt[i] >= cnt[i + 1] && cnt[i] > vleft) vleft = cnt[i], left = i;
-    if (left > low && left < top) {
-        for (i = left + 1, mn = vtop; i < top; ++i) if (cnt[i] < mn) mn = cnt[i];
-        if (vleft < vtop * 0.05 || mn > vleft * 0.95) vleft = -1, left = -1;
-    }
-    for (i = top + 1; i < n - 1; ++i)
-        if (cnt[i] >= cnt[i - 1] && cnt[i] >= cnt[i + 1] && cnt[i] > vright) vright = cnt[i], right = i;
-    if (right > top) {
-        for (i = top + 1, mn = vtop; i < right; ++i) if (cnt[i] < mn) mn = cnt[i];
-        if (vright < vtop * 0.05 || mn > vright * 0.95 || right > top * 2.5) vright = -1, right = -1;
-    }
-    if (right > 0) { *peak_het = top; return right; }
-    if (left > 0) *peak_het = left;
-    return top;
+    int i;
+    for (i = from; i < to; ++i) if (cnt[i] < start) start = cnt[i];
+    return start;
 }
 
-void sr_db_stat(sr_db_t *sr_db, FILE *fo, int more)
+/* highest local maximum among bins [from, to), scanned in the given direction; bin -1 if there is none */
+static peak_t best_local_maximum(const int64_t *cnt, int from, int to, int step)
+{
+    peak_t best = { -1, -1 };
+    int i;
+    for (i = step > 0 ? from : to - 1; i >= from && i < to; i += step)
+        if (cnt[i] >= cnt[i - 1] && cnt[i] >= cnt[i + 1] && cnt[i] > best.height) best.bin = i, best.height = cnt[i];
+    return best;
+}
+
+static void spectrum_line(int bin, int64_t value, int64_t summit)
+{
+    const int width = 100;
+    int stars = (int) ((double) width * value / summit + .499), over = stars > width, j;
+    if (over) stars = width;
+    if (bin >= 0) fprintf(stderr, "[M::ha_hist_line] %5d: ", bin);
+    else fprintf(stderr, "[M::ha_hist_line] %5s: ", "rest");
+    for (j = 0; j < stars; ++j) fputc('*', stderr);
+    if (over) fputc('>', stderr);
+    fprintf(stderr, " %lld\n", (long long) value);
+}
+
+static int find_peaks(int n, int first_bin, const int64_t *cnt, int *peak_het, int verbose)
+{
+    const int first_used = cnt[1] > 0 ? 1 : 2;
+    int floor_bin = first_used > first_bin ? first_used : first_bin, i;
+    peak_t summit, left, right;
+    *peak_het = -1;
+    while (floor_bin + 1 < n && cnt[floor_bin + 1] <= cnt[floor_bin]) ++floor_bin;
+    if (verbose > 0) fprintf(stderr, "[M::ha_analyze_count] lowest: count[%d] = %ld\n", floor_bin, (long) cnt[floor_bin]);
+    if (floor_bin == n - 1) return -1;
+
+    summit.bin = floor_bin + 1; summit.height = cnt[summit.bin];
+    for (i = floor_bin + 2; i < n; ++i) if (cnt[i] > summit.height) summit.bin = i, summit.height = cnt[i];
+    if (verbose > 0) {
+        int64_t rest = 0;
+        fprintf(stderr, "[M::ha_analyze_count] highest: count[%d] = %ld\n", summit.bin, (long) cnt[summit.bin]);
+        /* bins up to the first empty-looking one after the summit, the remainder as one line */
+        for (i = first_used; i < n; ++i) {
+            if (i > summit.bin && (int) ((double) 100 * cnt[i] / summit.height + .499) == 0) break;
+            spectrum_line(i, cnt[i], summit.height);
+        }
+        for (; i < n; ++i) rest += cnt[i];
+        spectrum_line(-1, rest, summit.height);
+    }
+
+    left = best_local_maximum(cnt, floor_bin + 1, summit.bin, -1);
+    if (left.bin > floor_bin && left.bin < summit.bin) {
+        const int64_t valley = lowest_between(cnt, left.bin + 1, summit.bin, summit.height);
+        if (left.height < summit.height * 0.05 || valley > left.height * 0.95) left.bin = -1, left.height = -1;
+    }
+    if (verbose > 0) {
+        if (left.height > 0) fprintf(stderr, "[M::ha_analyze_count] left: count[%d] = %ld\n", left.bin, (long) cnt[left.bin]);
+        else fprintf(stderr, "[M::ha_analyze_count] left: none\n");
+    }
+    right = best_local_maximum(cnt, summit.bin + 1, n - 1, 1);
+    if (right.bin > summit.bin) {
+        const int64_t valley = lowest_between(cnt, summit.bin + 1, right.bin, summit.height);
+        if (right.height < summit.height * 0.05 || valley > right.height * 0.95 || right.bin > summit.bin * 2.5)
+            right.bin = -1, right.height = -1;
+    }
+    if (verbose > 0) {
+        if (right.height > 0) fprintf(stderr, "[M::ha_analyze_count] right: count[%d] = %ld\n", right.bin, (long) cnt[right.bin]);
+        else fprintf(stderr, "[M::ha_analyze_count] right: none\n");
+    }
+    if (right.bin > 0) { *peak_het = summit.bin; return right.bin; }
+    if (left.bin > 0) *peak_het = left.bin;
+    return summit.bin;
+}
+
+/*
+ * The three tables sr_db_stat prints at verbose levels above 1 (syncmer.c:1018-1022 -> kh_ctab_print :736-757 ->
+ * hist_plot :669-734): gap between neighbouring syncmers of a read, s-mer multiplicities, k-mer multiplicities, each
+ * as (value, how often) pairs in ascending order of value. The device keeps only what the statistics need (bins up
+ * to 1000, the gap sum), so for this diagnostic output the full tables are rebuilt from the per-read lists on the host.
+ */
+typedef struct { int64_t value; int64_t times; } tally_t;
+
+static int cmp_i64(const void *a, const void *b) { int64_t x = *(const int64_t *) a, y = *(const int64_t *) b; return (x > y) - (x < y); }
+static int cmp_u64(const void *a, const void *b) { uint64_t x = *(const uint64_t *) a, y = *(const uint64_t *) b; return (x > y) - (x < y); }
+
+/* sorted values -> (value, times) pairs; returns how many */
+static size_t tally_sorted_i64(const int64_t *v, size_t n, tally_t *out)
+{
+    size_t i, m = 0;
+    for (i = 0; i < n; ++i) {
+        if (m && out[m - 1].value == v[i]) ++out[m - 1].times;
+        else { out[m].value = v[i]; out[m].times = 1; ++m; }
+    }
+    return m;
+}
+
+/* keys -> multiplicity of every distinct key -> (multiplicity, times) pairs */
+static size_t multiplicity_table(uint64_t *keys, size_t n, tally_t **out)
+{
+    int64_t *mult = (int64_t *) malloc(sizeof(int64_t) * (n ? n : 1));
+    size_t i, m = 0, run = 0;
+    qsort(keys, n, sizeof(uint64_t), cmp_u64);
+    for (i = 0; i < n; ++i) {
+        ++run;
+        if (i + 1 == n || keys[i + 1] != keys[i]) { mult[m++] = (int64_t) run; run = 0; }
+    }
+    qsort(mult, m, sizeof(int64_t), cmp_i64);
+    *out = (tally_t *) malloc(sizeof(tally_t) * (m ? m : 1));
+    m = tally_sorted_i64(mult, m, *out);
+    free(mult);
+    return m;
+}
+
+static int printed_width(int32_t v)
+{
+    int w = v > 0 ? 0 : 1;              /* the reference counts a sign position for zero as well */
+    do { v /= 10; ++w; } while (v != 0);
+    return w;
+}
+
+static void bar(FILE *fo, double count, double per_dot)
+{
+    const double dots = count / per_dot;
+    uint32_t j, n = (uint32_t) dots;
+    for (j = 0; j < (n < 100 ? n : 100); ++j) fputc('*', fo);
+    n = dots > 100 ? (uint32_t) log10(dots / 100) : 0;
+    for (j = 0; j < n; ++j) fputc('+', fo);
+    fprintf(fo, " %d\n", (int) count);
+}
+
+static void print_table(const tally_t *t, size_t n, const char *title, FILE *fo, int list_all)
+{
+    size_t i, shown = 0;
+    if (n >= 5) {
+        /* rows until 99 % of the mass outside the three smallest values is covered; the rest as one line */
+        double mass = 0, acc = 0, rest = 0;
+        uint32_t tallest = 0;
+        int width = 0;
+        for (i = 3; i < n; ++i) mass += (uint32_t) t[i].times;
+        mass *= .99;
+        for (i = 0; i < n; ++i) {
+            if (i >= 3) acc += (uint32_t) t[i].times;
+            if (acc >= mass) { shown = i + 1; break; }
+        }
+        for (i = 0; i < shown; ++i) {
+            const int w = printed_width((int32_t) t[i].value);
+            if (i >= 3 && (uint32_t) t[i].times > tallest) tallest = (uint32_t) t[i].times;
+            if (w > width) width = w;
+        }
+        if (shown < n) ++width;
+        {
+            const double per_dot = tallest / 100 > 1 ? tallest / 100 : 1;
+            for (i = 0; i < shown; ++i) {
+                fprintf(fo, "[M::hist_plot] [%s] %*d: ", title, width, (int32_t) t[i].value);
+                bar(fo, (uint32_t) t[i].times, per_dot);
+            }
+            if (shown < n) {
+                for (i = shown; i < n; ++i) rest += (uint32_t) t[i].times;
+                fprintf(fo, "[M::hist_plot] [%s] >%*d: ", title, width - 1, (int32_t) t[shown - 1].value);
+                bar(fo, rest, per_dot);
+            }
+        }
+    }
+    if (list_all)
+        for (i = 0; i < n; ++i) fprintf(fo, "[M::kh_ctab_print] [%s CNTS] %ld %d\n", title, (long) t[i].value, (int) t[i].times);
+}
+
+static void print_verbose_tables(sr_db_t *db, FILE *fo, int list_all)
+{
+    uint64_t total = 0, i, j, n_gap = 0, p;
+    int64_t *gap;
+    uint64_t *key;
+    tally_t *t;
+    size_t m;
+    for (i = 0; i < db->n; ++i) total += db->a[i].n;
+    gap = (int64_t *) malloc(sizeof(int64_t) * (total ? total : 1));
+    key = (uint64_t *) malloc(sizeof(uint64_t) * (total ? total : 1));
+    for (i = 0; i < db->n; ++i) {
+        const sr_t *r = &db->a[i];
+        int prev = (int) MAX_RD_LEN;
+        for (j = 0; j < r->n; ++j) {                           /* corrected entries carry MAX_RD_LEN and break the chain (syncmer.c:896-902) */
+            const int here = (int) (r->m_pos[j] >> 1);
+            if (prev != (int) MAX_RD_LEN && here != (int) MAX_RD_LEN) gap[n_gap++] = (int64_t) here - prev - db->k;
+            prev = here;
+        }
+    }
+    qsort(gap, n_gap, sizeof(int64_t), cmp_i64);
+    t = (tally_t *) malloc(sizeof(tally_t) * (n_gap ? n_gap : 1));
+    m = tally_sorted_i64(gap, n_gap, t);
+    print_table(t, m, "DIST", fo, list_all);
+    free(t); free(gap);
+    for (i = 0, p = 0; i < db->n; ++i) for (j = 0; j < db->a[i].n; ++j) key[p++] = db->a[i].s_mer[j];
+    m = multiplicity_table(key, total, &t);
+    print_table(t, m, "SMER", fo, list_all);
+    free(t);
+    for (i = 0, p = 0; i < db->n; ++i) for (j = 0; j < db->a[i].n; ++j) key[p++] = db->a[i].k_mer[j] >> 1;
+    m = multiplicity_table(key, total, &t);
+    print_table(t, m, "KMER", fo, list_all);
+    free(t); free(key);
+}
+
+void sr_db_stat(sr_db_t *sr_db, FILE *fo, int verbose)
 {
     sg_batch *b = batch_of(sr_db, 0);
     sg_stat_t st;
     sr_stat_t *s;
     int rc;
-    (void) more;
     if (!sr_db->stats) sr_db->stats = (sr_stat_t *) calloc(1, sizeof(sr_stat_t));
     s = sr_db->stats;
     if (!b) { fprintf(stderr, "[E::%s] the read database was not produced by sr_read_mem\n", __func__); return; }
@@ -239,8 +427,8 @@ void sr_db_stat(sr_db_t *sr_db, FILE *fo, int more)
     s->smer_avg_cnt = (double) st.n_syncmers / (double) st.smer_unique;
     s->kmer_unique = (int) st.kmer_unique; s->kmer_singleton = (int) st.kmer_singleton;
     s->kmer_avg_cnt = (double) st.n_syncmers / (double) st.kmer_unique;
-    s->smer_peak_hom = find_peaks(1001, 5, st.smer_cnts, &s->smer_peak_het);
-    s->kmer_peak_hom = find_peaks(1001, 5, st.kmer_cnts, &s->kmer_peak_het);
+    s->smer_peak_hom = find_peaks(1001, 5, st.smer_cnts, &s->smer_peak_het, verbose - 1);
+    s->kmer_peak_hom = find_peaks(1001, 5, st.kmer_cnts, &s->kmer_peak_het, verbose - 1);
     fprintf(fo, "[M::%s] number syncmers collected: %lu\n", __func__, (unsigned long) s->syncmer_n);
     fprintf(fo, "[M::%s] number syncmers per read: %.3f\n", __func__, s->syncmer_per_read);
     fprintf(fo, "[M::%s] average kmer space: %.3f\n", __func__, s->syncmer_avg_dist);
@@ -252,6 +440,7 @@ void sr_db_stat(sr_db_t *sr_db, FILE *fo, int more)
             (double) s->kmer_singleton * 100 / s->kmer_unique);
     fprintf(fo, "[M::%s] average kmer count: %.3f\n", __func__, s->kmer_avg_cnt);
     fprintf(fo, "[M::%s] kmer peak_hom: %d; peak_het: %d\n", __func__, s->kmer_peak_hom, s->kmer_peak_het);
+    if (verbose > 1) print_verbose_tables(sr_db, fo, verbose - 1 > 0);
 }
 
 syncmer_db_t *collect_syncmer_from_reads(sr_db_t *sr_db)

@@ -11,10 +11,9 @@
  *     correction reallocs k_mer/m_pos/s_mer in place, syncerr.c:604-608)
  *   - syncmer_t.m_pos is one malloc block per syncmer (syncmer.c:1359)
  *   - sr_db_stat prints the reference's nine [M::sr_db_stat] lines
- * The only function with a different signature is the reader: sr_read() in the
- * reference pulls records from its sstream_t; here sr_read_mem() takes the
- * records already in memory (INTEGRATION.md shows the 20-line sr_read() a
- * maintainer writes on top of it inside the reference tree).
+ * The reader comes in three forms: sr_read() over an sstream_t as in the reference
+ * (sstream_gpu.c), sr_read_files() for file names (fastx_gpu.h) and sr_read_mem()
+ * for records already in memory.
  */
 #ifndef SYNCMER_GPU_H
 #define SYNCMER_GPU_H
@@ -77,6 +76,20 @@ typedef struct {
 #ifndef KSTRING_H              /* klib's kstring.h provides this inside the reference tree */
 typedef struct { size_t l, m; char *s; } kstring_t;
 #endif
+
+#ifndef __SSTREAM_H__           /* sstream.h:46-51: same members, same order; `s` is this layer's own state (sstream_gpu.c) */
+typedef struct {
+    uint64_t n_seq;             /* records delivered so far */
+    char **files;
+    int n_files, n;             /* n: index of the file being read */
+    void *s;
+} sstream_t;
+sstream_t *sstream_open(char **files, int n_files);
+void sstream_close(sstream_t *stream);
+#endif
+/* syncmer.h:120, syncmer.c:487-556: every record of the stream through the device pipeline into sr_db (read order
+ * kept, sid == index); m_data = 0: no limit, else stop after the record that reaches it, with the reference's message */
+void sr_read(sstream_t *s_stream, sr_db_t *sr_db, size_t m_data, int n_threads);
 
 extern const unsigned char seq_nt4_table[256];
 extern const char char_nt4_table[4];

@@ -32,6 +32,7 @@ def build(force=False):
         subprocess.check_call(["make", "-C", HERE, "liboracle.so"], stdout=subprocess.DEVNULL)
     ref_so = os.path.join(HERE, "_ref", "libref.so")
     if os.path.isdir("/root/reference") and (force or not os.path.exists(ref_so)
+            or not os.path.exists(os.path.join(HERE, "_ref", "syncasm"))
             or os.path.getmtime(ref_so) < os.path.getmtime(os.path.join(HERE, "ref_shim.c"))):
         subprocess.check_call(["make", "-C", HERE, "ref"], stdout=subprocess.DEVNULL)
 

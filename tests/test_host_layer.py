@@ -252,6 +252,23 @@ def test_sr_read_files_matches_reference(host, ref):
         cum = np.cumsum(np.diff(off))
         assert db2.n == int(np.searchsorted(cum, total // 3, side="left")) + 1
         host.sr_db_clean(C.byref(db2))
+        # the reference's own calling sequence (run_syncasm.c:79-86): sstream_open -> sr_read -> sstream_close
+        class SStream(C.Structure):
+            _fields_ = [("n_seq", C.c_uint64), ("files", C.POINTER(C.c_char_p)), ("n_files", C.c_int), ("n", C.c_int), ("s", C.c_void_p)]
+        host.sstream_open.restype = C.POINTER(SStream)
+        host.sstream_open.argtypes = [C.POINTER(C.c_char_p), C.c_int]
+        host.sr_read.argtypes = [C.POINTER(SStream), C.c_void_p, C.c_size_t, C.c_int]
+        host.sr_read.restype = None
+        host.sstream_close.argtypes = [C.POINTER(SStream)]
+        ss = host.sstream_open(files, 2)
+        db3 = SrDb()
+        host.sr_db_init(C.byref(db3), k, s)
+        host.sr_read(ss, C.byref(db3), 0, 8)
+        assert ss.contents.n_seq == len(reads) and ss.contents.n == 1
+        host.sstream_close(ss)
+        again = ref._flat(C.addressof(db3), len(reads), count_ambiguous(bases, off))
+        assert parity.diff(again, theirs, parity.EXTRACT_FIELDS) == []
+        host.sr_db_clean(C.byref(db3))
         host.sr_db_clean(C.byref(db))
         ref.free(rdb)
 
