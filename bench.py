@@ -232,20 +232,28 @@ def main():
     ctx = lib.Context(local)          # launches on the legacy default stream = torch's current stream
     batch = lib.Batch(ctx)
     batch.set_sid_base(rank * n_reads)
-    exchange = None
+    comm = None
+    mgpu = None
     if world > 1:
-        from oatk_b200 import dist as sgdist
-        exchange = sgdist.TupleExchange(ctx, dist, rank, world)
+        # parity first: a seeded read set (HiFi-like + adversarial + tandem arrays) through the same C-side exchange,
+        # checked on rank 0 against the CPU oracle run on the WHOLE set; the result rides on the JSON line
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import mgpu_parity
+        try:
+            mgpu = mgpu_parity.run(dist, rank, world, local)
+        except Exception as e:                       # a failed check must not take the timing run with it: it is reported
+            mgpu = {"ok": False, "world": world, "error": repr(e)[:300]}
+        comm = lib.Comm(ctx, world, rank, share_unique_id(torch, dist, lib, rank, dev))
 
     def step():
         batch.set_reads_device(bases.data_ptr(), off.data_ptr(), n_reads, total)
         batch.extract(K, S)
-        if exchange is not None:
-            exchange.run(batch)
+        if comm is not None:
+            comm.exchange_tuples(batch)      # sg_tuples_partition -> NCCL all-to-all-v -> sg_tuples_adopt, in C
         st = batch.stat()
         batch.count()
-        if exchange is not None:
-            exchange.return_ids(batch, batch.count_sizes().n_unique)
+        if comm is not None:
+            comm.return_ids(batch)           # global ids back to the GPU that holds the read
         return st
 
     for _ in range(W):
@@ -288,7 +296,10 @@ def main():
     # ---- end to end through the C ABI with host buffers ----
     e2e = None
     if not args.no_e2e:
-        e2e = run_e2e(torch, lib, ctx, batch, bases, off, n_reads, total, sizes, csz, max(1, min(args.steps, 3)), dist, dev, world)
+        e2e = run_e2e(torch, lib, ctx, batch, bases, off, n_reads, total, sizes, csz, max(1, min(args.steps, 3)), dist, dev, world, rank)
+    ids_check = None
+    if world > 1:
+        ids_check = check_global_ids(torch, dist, batch, comm, rank, world, dev, n_reads)
 
     if rank != 0:
         if dist is not None:
@@ -323,12 +334,67 @@ def main():
             "steps": args.steps, "warmup": W, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": workload_config(world, n_reads, args.workload, n_planted),
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+            "multi_gpu_parity": mgpu, "global_ids_sample_check": ids_check,
+            "exchange": None if comm is None else {"transport": "sg_comm_* in C: grouped ncclSend/ncclRecv, counts on the device",
+                                                   "bytes_sent_per_step_rank0": comm.bytes_sent() // max(1, W + args.steps + 0)},
             "results": {"syncmers": int(sizes.n_syncmers), "distinct_kmers": int(csz.n_unique), "hoco_bases": int(sizes.hoco_bases),
                         "reads_on_exact_scan_path": int(batch.debug_scan_info())}}
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
     return 0
+
+
+def share_unique_id(torch, dist, lib, rank, dev):
+    """rank 0's NCCL unique id (sg_comm_unique_id) to every rank over the launcher's process group"""
+    raw = lib.comm_unique_id() if rank == 0 else bytes(128)
+    t = torch.tensor(list(raw), dtype=torch.uint8, device=dev)
+    dist.broadcast(t, 0)
+    return bytes(t.cpu().tolist())
+
+
+def check_global_ids(torch, dist, batch, comm, rank, world, dev, n_reads, sample=4096):
+    """configs[3]: global ids at full size. For the syncmers of every rank's first reads: (i) over all ranks, sorting the
+    sampled (hash, id) pairs by hash gives non-decreasing ids, equal exactly when the hashes are equal (ids are ranks in
+    hash order, syncmer.c:1419-1446); (ii) every sampled id equals id_base(owner) + the position of the hash in the
+    owner's sorted table of distinct hashes -- looked up in the owner's table directly, not through the return path."""
+    from oatk_b200 import dist as sgdist
+    import numpy as np
+    kp, kn = batch.buffer("key")
+    m = int(min(sample, kn))
+    keys = sgdist.tensor_from_ptr(kp, kn, dev)[:m].clone()
+    f = batch.extract_download(want_seq=False)
+    ids = torch.from_numpy((f["k_mer"][:m] >> np.uint64(1)).astype(np.int64)).to(dev)
+    allk = [torch.empty(m, dtype=torch.int64, device=dev) for _ in range(world)]
+    alli = [torch.empty(m, dtype=torch.int64, device=dev) for _ in range(world)]
+    ms = [torch.empty(1, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(ms, torch.tensor([m], dtype=torch.int64, device=dev))
+    if len({int(x.item()) for x in ms}) != 1:
+        return {"ok": False, "why": "ranks hold different sample sizes"}
+    dist.all_gather(allk, keys)
+    dist.all_gather(alli, ids)
+    k_all = torch.cat(allk).cpu().numpy().view(np.uint64)
+    i_all = torch.cat(alli).cpu().numpy()
+    order = np.argsort(k_all, kind="stable")
+    ks, is_ = k_all[order], i_all[order]
+    mono = bool(np.all(np.diff(is_) >= 0) and np.array_equal(np.diff(is_) == 0, np.diff(ks) == 0))
+    # owner look-up: this rank answers for the sampled hashes that fall into its range
+    hp, hn = batch.buffer("scm_h")
+    table = sgdist.tensor_from_ptr(hp, hn, dev).cpu().numpy().view(np.uint64)
+    uniq = [torch.empty(1, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(uniq, torch.tensor([hn], dtype=torch.int64, device=dev))
+    base = sum(int(u.item()) for u in uniq[:rank])
+    pos = np.searchsorted(table, k_all)
+    mine = (pos < len(table)) & (table[np.minimum(pos, max(len(table) - 1, 0))] == k_all) if len(table) else np.zeros(len(k_all), bool)
+    want = np.where(mine, base + pos, 0).astype(np.int64)
+    t = torch.from_numpy(np.stack([want, mine.astype(np.int64)])).to(dev)
+    dist.all_reduce(t)
+    want_all, owners = t[0].cpu().numpy(), t[1].cpu().numpy()
+    owned_once = bool(np.all(owners == 1))
+    exact = bool(np.array_equal(want_all, i_all))
+    return {"ok": mono and owned_once and exact, "sampled_syncmers": int(len(k_all)), "ids_follow_hash_order": mono,
+            "every_hash_has_one_owner": owned_once, "ids_equal_base_plus_rank_in_owner_table": exact,
+            "distinct_kmers_total": int(sum(int(u.item()) for u in uniq))}
 
 
 def ncu_traffic():
@@ -342,7 +408,7 @@ def ncu_traffic():
     return None
 
 
-def run_e2e(torch, lib, ctx, batch, bases, off, n_reads, total, sizes, csz, steps, dist, dev, world):
+def run_e2e(torch, lib, ctx, batch, bases, off, n_reads, total, sizes, csz, steps, dist, dev, world, rank=0):
     """host buffers in, host buffers out through the C ABI: sg_pipe_run_host (chunked over 3 streams:
     upload, kernels and download overlap) -> sg_stat -> sg_count -> sg_count_download on the master batch.
     Every input byte crosses PCIe inside the timed region and every result array lands in pinned host memory."""
@@ -367,7 +433,7 @@ def run_e2e(torch, lib, ctx, batch, bases, off, n_reads, total, sizes, csz, step
     h_off = pin(n_reads + 1, torch.int64)
     h_off.copy_(off[:n_reads + 1])
     N, U = int(sizes.n_syncmers), int(csz.n_unique)
-    slack = 1.02
+    slack = 1.02 if world == 1 else 1.15          # a hash range holds about, not exactly, 1/world of the tuples
     o = lib.ExtractOut()
     bufs = {
         "hoco_l": pin(n_reads, torch.int32), "n_scm": pin(n_reads, torch.int32),
@@ -390,12 +456,24 @@ def run_e2e(torch, lib, ctx, batch, bases, off, n_reads, total, sizes, csz, step
     n_slots = env_int("SG_PIPE_SLOTS", 6)
     pipe = lib.Pipe(ctx.device, n_slots)
     chunk = env_int("SG_PIPE_CHUNK", 4096)
+    comm2 = None
+    ko = None
+    if world > 1:
+        pipe.set_sid_base(rank * full_reads)
+        comm2 = lib.Comm(pipe.ctx, world, rank, share_unique_id(torch, dist, lib, rank, dev))
+        ko = lib.ExtractOut()                      # the reads' k_mer[] as global ids: one more download of 8 B per syncmer
+        ko.k_mer = bufs["k_mer"].data_ptr()
     torch.cuda.synchronize()
 
     def one():
         z = pipe.run_host(h_bases.data_ptr(), h_off.data_ptr(), n_reads, K, S, chunk, o, caps)
+        if comm2 is not None:
+            comm2.exchange_tuples(pipe.master)
         pipe.master.stat()
         pipe.master.count()
+        if comm2 is not None:
+            comm2.return_ids(pipe.master)
+            lib._ck(pipe.ctx.h, L.sg_extract_download(pipe.master.h, C.byref(ko)), "sg_extract_download")
         lib._ck(pipe.ctx.h, L.sg_count_download(pipe.master.h, C.byref(co)), "sg_count_download")
         return z
 
@@ -418,11 +496,15 @@ def run_e2e(torch, lib, ctx, batch, bases, off, n_reads, total, sizes, csz, step
     N = int(z.n_syncmers)
     U = int(pipe.master.count_sizes().n_unique)
     h2d = total + 8 * (n_reads + n_reads // chunk + 1)
-    d2h = int(z.hoco_s_bytes + z.ho_rl_bytes + 12 * N + 8 * n_reads + 28 * U + 16 * N)
+    NA = int(pipe.master.count_sizes().n_syncmers)          # tuples of this rank's hash range (== N on one GPU)
+    d2h = int(z.hoco_s_bytes + z.ho_rl_bytes + 12 * N + 8 * n_reads + 28 * U + 16 * NA + (8 * N if world > 1 else 0))
     res = {"value": world * total / sec, "unit": "bases/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": d2h,
            "ms_per_step": sec * 1e3, "steps": steps, "reads_per_gpu": n_reads, "gpu_launches_per_step": int(launches), "chunk_reads": chunk, "streams": n_slots,
            "path": "sg_pipe_run_host (chunks of %d reads over several streams) -> sg_stat -> sg_count -> sg_count_download; pinned host buffers; "
-                   "multi-GPU runs time each rank's own shard without the tuple exchange" % chunk}
+                   "%s" % (chunk, "one GPU" if world == 1 else "with the tuple exchange and the id return over NCCL (sg_comm_*) between extract and count; "
+                                  "each rank downloads its hash range of the database and the global ids of its reads")}
+    if comm2 is not None:
+        comm2.close()
     pipe.close()
     res["pcie"] = pcie_probe(torch, dev, h_bases)
     return res

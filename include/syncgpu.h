@@ -43,6 +43,7 @@ extern "C" {
 #define SG_E_EMPTY        -7   /* no syncmers in the batch (reference returns NULL, syncmer.c:1414-1417) */
 #define SG_E_STATE        -8   /* call order violated (e.g. sg_count before sg_extract) */
 #define SG_E_COLLISION    -9   /* multi-GPU only: two different k-mers of different GPUs share a 64-bit hash */
+#define SG_E_COMM        -10   /* NCCL missing or a collective failed (sg_comm_*) */
 
 typedef struct sg_ctx sg_ctx;
 typedef struct sg_batch sg_batch;
@@ -127,6 +128,11 @@ typedef struct {
     int64_t kmer_cnts[1001];
 } sg_stat_t;
 int sg_stat(sg_batch *b, sg_stat_t *out);                     /* synchronises */
+/* after sg_stat: the multiplicity of every distinct key in ascending key order (which = 0: k_mer >> 1, 1: s-mer codes),
+ * i.e. in the order the reference's sr_db_stat feeds its multiplicity tables (syncmer.c:916-926, 967-977). Only that
+ * order is not in sg_stat_t; the host layer needs it to print the reference's singleton figure when no key occurs
+ * once (see oatk_b200/host/syncmer_gpu.c). *host_out is malloc'ed (NULL when empty), the caller frees it. */
+int sg_stat_multiplicities(sg_batch *b, int which, uint32_t **host_out, uint64_t *n);
 
 /* a6: syncmer database. Sorts the (hash, sid, idx, rev) tuples, groups them by
  * hash, verifies with an exact sequence comparison that a group holds one
@@ -195,6 +201,8 @@ sg_batch *sg_pipe_master(sg_pipe *p);
 sg_ctx *sg_pipe_ctx(sg_pipe *p);
 const char *sg_pipe_last_error(sg_pipe *p);
 uint64_t sg_pipe_launches(sg_pipe *p);
+/* multi-GPU: global index of this pipe's first read (sid of read i = sid_base + i); default 0 */
+int sg_pipe_set_sid_base(sg_pipe *p, uint64_t sid_base);
 
 /* device pointers of the batch's result arrays (for device-side consumers such as the multi-GPU
  * exchange); valid until the next call that recomputes them. n = number of elements. */
@@ -250,6 +258,33 @@ int sg_tuples_adopt(sg_batch *b, const void *d_tuples, uint64_t n);
 int sg_ids_pack(sg_batch *b, uint64_t id_base, void **d_pairs, uint64_t *n);
 /* the pairs received back for this rank's own reads: fills k_mer[] (read order) with id << 1 */
 int sg_ids_scatter(sg_batch *b, const void *d_pairs, uint64_t n);
+
+/* ---- the same exchange in C over NCCL (csrc/sg_comm.cu; NCCL is dlopen'ed at the first call) ----
+ * One sg_comm per GPU. Either one process per GPU (sg_comm_unique_id on rank 0, the 128 bytes handed to the
+ * other ranks by the launcher, sg_comm_init_rank everywhere) or one process with one thread per GPU
+ * (sg_comm_init_all, then each thread drives its own context). All data calls are collective: every rank makes
+ * the same calls in the same order; they run on the context's stream. */
+typedef struct sg_comm sg_comm;
+int sg_comm_unique_id(void *id128 /* 128 bytes out */);
+int sg_comm_init_rank(sg_ctx *ctx, int world, int rank, const void *id128, sg_comm **out);
+int sg_comm_init_all(sg_ctx **ctxs, int n, sg_comm **out /* n */);
+void sg_comm_destroy(sg_comm *c);
+int sg_comm_rank(sg_comm *c);
+int sg_comm_world(sg_comm *c);
+uint64_t sg_comm_bytes_sent(sg_comm *c);                    /* payload this rank put on the wire so far */
+/* between sg_extract and sg_stat / sg_count: sg_tuples_partition -> all-to-all-v -> sg_tuples_adopt. Counts are
+ * exchanged on the device; the host reads the world x world count matrix once. */
+int sg_comm_exchange_tuples(sg_comm *c, sg_batch *b);
+/* after sg_stat on every rank: *st (this rank's result) becomes the table over ALL reads (reference sr_db_stat on
+ * the whole input): k-mer tables, gap sums and totals are summed, s-mer codes merged as (code, count) pairs */
+int sg_comm_global_stat(sg_comm *c, sg_batch *b, sg_stat_t *st);
+/* after sg_count on every rank: global ids (local rank in the hash range + distinct k-mers of the lower ranges,
+ * summed on the device) go back to the ranks that hold the reads; k_mer[] of sg_extract_download then holds them */
+int sg_comm_return_ids(sg_comm *c, sg_batch *b, uint64_t *id_base, uint64_t *n_unique_total);
+/* a7 over all ranks (reference syncasm.c:236-282), after sg_comm_return_ids: local pair tally -> all-to-all-v keyed by
+ * the canonical pair -> filter with the coverages of all ranges -> the whole arc list, (v, w, comp) order, on `root`
+ * (sg_arcs_download there; *n_arcs is 0 on the other ranks) */
+int sg_comm_arcs(sg_comm *c, sg_batch *b, uint32_t min_k_cov, double min_a_cov_f, int root, uint64_t *n_arcs);
 
 #ifdef __cplusplus
 }

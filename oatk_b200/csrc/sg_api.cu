@@ -69,6 +69,7 @@ const char *sg_strerror(int code)
         case SG_E_EMPTY: return "empty syncmer collection";
         case SG_E_STATE: return "call order violated";
         case SG_E_COLLISION: return "64-bit k-mer hash collision across GPUs";
+        case SG_E_COMM: return "NCCL unavailable or a collective failed";
     }
     return "unknown error";
 }

@@ -23,6 +23,12 @@
 #include "sg_host.h"
 #include "sg_table.cuh"
 
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+    ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_); return SG_E_CUDA; } } while (0)
+#define RS(buf, bytes) do { if ((buf).reserve(bytes)) { ctx->err = "device allocation of " + std::to_string((size_t)(bytes)) + " bytes failed"; return SG_E_NOMEM; } } while (0)
+#define LAUNCHED(stage, expr) do { int n_ = (expr); if (n_ < 0) return n_; ctx->count_launch(stage, n_); } while (0)
+static inline unsigned nblk(uint64_t n, unsigned t) { return (unsigned) ((n + t - 1) / t); }
+
 namespace sg {
 
 struct ArcTallyArgs {
@@ -135,35 +141,74 @@ __global__ void __launch_bounds__(256) pair_pack_kernel(const uint64_t *occ, con
 
 using namespace sg;
 
-#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
-    ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_); return SG_E_CUDA; } } while (0)
-#define RS(buf, bytes) do { if ((buf).reserve(bytes)) { ctx->err = "device allocation of " + std::to_string((size_t)(bytes)) + " bytes failed"; return SG_E_NOMEM; } } while (0)
-#define LAUNCHED(stage, expr) do { int n_ = (expr); if (n_ < 0) return n_; ctx->count_launch(stage, n_); } while (0)
-static inline unsigned nblk(uint64_t n, unsigned t) { return (unsigned) ((n + t - 1) / t); }
 
-extern "C" {
+namespace sg {
 
-int sg_arcs(sg_batch *b, uint32_t min_k_cov, double min_a_cov_f, uint64_t *n_arcs)
+// (key, count) pairs added into a tally table (the owner's side of the multi-GPU arc exchange)
+__global__ void __launch_bounds__(256) arc_pair_tally_kernel(const uint64_t *pairs, uint64_t n, uint64_t *tk, uint32_t *tv, uint64_t nslot_mask)
 {
-    if (!b || !n_arcs) return SG_E_ARG;
-    if (!b->counted) return SG_E_STATE;
-    if (b->adopted) return SG_E_STATE;            // needs the per-read id sequences of the local reads
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp0 = ((uint64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nwarp = ((uint64_t) gridDim.x * blockDim.x) >> 5;
+    for (uint64_t base = warp0 * 32; base < n; base += nwarp * 32) {
+        const bool ok = base + lane < n;
+        const uint64_t key = ok ? pairs[2 * (base + lane)] : EMPTY_KEY;
+        const uint32_t cnt = ok ? (uint32_t) pairs[2 * (base + lane) + 1] : 0u;
+        uint32_t work = __ballot_sync(SG_FULL, ok);
+        while (work) {
+            const int src = __ffs(work) - 1;
+            work &= work - 1;
+            table_add(tk, tv, nslot_mask, __shfl_sync(SG_FULL, key, src), __shfl_sync(SG_FULL, cnt, src), lane);
+        }
+    }
+}
+
+static int arcs_table(sg_batch *b, uint64_t items, uint64_t *nslots_out)
+{
     sg_ctx *ctx = b->ctx;
     cudaStream_t st = ctx->stream;
-    CK(cudaSetDevice(ctx->device));
-    const uint64_t N = b->n_syncmers;
     uint64_t nslots = 1024;
-    while (nslots < 2 * N) nslots <<= 1;          // load factor <= 0.5 even if every pair is distinct
+    while (nslots < 2 * items) nslots <<= 1;      // load factor <= 0.5 even if every item is a distinct key
     RS(b->arc_keys, nslots * 8); RS(b->arc_vals, nslots * 4);
     RS(b->status, 4 * 8);
-    ctx->t_begin(SG_T_ARCS);
     CK(cudaMemsetAsync(b->arc_keys.p, 0xff, nslots * 8, st));
     CK(cudaMemsetAsync(b->arc_vals.p, 0, nslots * 4, st));
+    b->smer_slots = 0;                            // sg_stat's s-mer table lived in the same buffers
+    *nslots_out = nslots;
+    return SG_OK;
+}
+
+// neighbouring pairs of this batch's reads -> table; kid = id << 1 per syncmer in read order (ids < 2^31)
+int arcs_tally_local(sg_batch *b, const uint64_t *kid, uint64_t *nslots_out)
+{
+    sg_ctx *ctx = b->ctx;
+    const uint64_t N = b->n_syncmers;
+    int rc = arcs_table(b, N, nslots_out);
+    if (rc) return rc;
     ArcTallyArgs T;
-    T.occ = (const uint64_t *) b->occ.p; T.kid = (const uint64_t *) b->kid.p; T.m_pos = (const uint32_t *) b->m_pos.p; T.n = N;
-    T.tk = (uint64_t *) b->arc_keys.p; T.tv = (uint32_t *) b->arc_vals.p; T.nslot_mask = nslots - 1;
-    arc_tally_kernel<<<std::min<unsigned>(nblk(N, 256), 148u * 16u), 256, 0, st>>>(T);
+    T.occ = (const uint64_t *) b->occ.p; T.kid = kid; T.m_pos = (const uint32_t *) b->m_pos.p; T.n = N;
+    T.tk = (uint64_t *) b->arc_keys.p; T.tv = (uint32_t *) b->arc_vals.p; T.nslot_mask = *nslots_out - 1;
+    if (N) arc_tally_kernel<<<std::min<unsigned>(nblk(N, 256), 148u * 16u), 256, 0, ctx->stream>>>(T);
     ctx->count_launch(SG_T_ARCS, 1);
+    return SG_OK;
+}
+
+int arcs_merge_pairs(sg_batch *b, const uint64_t *pairs, uint64_t n, uint64_t *nslots_out)
+{
+    sg_ctx *ctx = b->ctx;
+    int rc = arcs_table(b, n, nslots_out);
+    if (rc) return rc;
+    if (n) arc_pair_tally_kernel<<<std::min<unsigned>(nblk(n, 256), 148u * 16u), 256, 0, ctx->stream>>>(pairs, n, (uint64_t *) b->arc_keys.p,
+            (uint32_t *) b->arc_vals.p, *nslots_out - 1);
+    ctx->count_launch(SG_T_ARCS, 1);
+    return SG_OK;
+}
+
+// table -> arcs that pass the filter, with their complements, in table order (arc_okey / arc_oval). Synchronises.
+int arcs_emit(sg_batch *b, uint64_t nslots, const uint32_t *cov, uint32_t min_k_cov, double min_a_cov_f, uint64_t *n_arcs)
+{
+    sg_ctx *ctx = b->ctx;
+    cudaStream_t st = ctx->stream;
     unsigned long long *d_n = (unsigned long long *) b->status.p + 3;
     uint64_t cap = std::max<uint64_t>(b->arc_cap, 1 << 16);
     uint64_t na = 0;
@@ -172,7 +217,7 @@ int sg_arcs(sg_batch *b, uint32_t min_k_cov, double min_a_cov_f, uint64_t *n_arc
         RS(b->arc_okey_alt, (cap + 2) * 8); RS(b->arc_oval_alt, (cap + 2) * 8);
         CK(cudaMemsetAsync(d_n, 0, 8, st));
         ArcEmitArgs E;
-        E.tk = T.tk; E.tv = T.tv; E.nslots = nslots; E.cov = (const uint32_t *) b->scm_cov.p;
+        E.tk = (const uint64_t *) b->arc_keys.p; E.tv = (const uint32_t *) b->arc_vals.p; E.nslots = nslots; E.cov = cov;
         E.min_k_cov = min_k_cov; E.min_a_cov_f = min_a_cov_f; E.n_out = d_n; E.cap = cap;
         E.okey = (uint64_t *) b->arc_okey.p; E.oval = (uint64_t *) b->arc_oval.p;
         arc_emit_kernel<<<std::min<unsigned>(nblk(nslots, 256), 148u * 16u), 256, 0, st>>>(E);
@@ -183,18 +228,78 @@ int sg_arcs(sg_batch *b, uint32_t min_k_cov, double min_a_cov_f, uint64_t *n_arc
         cap = na + 16;
     }
     b->arc_cap = cap;
-    b->n_arcs = na;
-    if (na) {
-        // order by (v, w, comp): stable LSD, minor key first
-        RS(b->sort_tmp, sort_tmp_words(na) * 4);
-        uint64_t *k0 = (uint64_t *) b->arc_okey.p, *v0 = (uint64_t *) b->arc_oval.p;
-        uint64_t *k1 = (uint64_t *) b->arc_okey_alt.p, *v1 = (uint64_t *) b->arc_oval_alt.p;
-        LAUNCHED(SG_T_ARCS, launch_sort_pairs(v0, k0, v1, k1, na, 0, 40, (uint32_t *) b->sort_tmp.p, st));   // by cov<<1|comp
-        LAUNCHED(SG_T_ARCS, launch_sort_pairs(k0, v0, k1, v1, na, 0, 64, (uint32_t *) b->sort_tmp.p, st));   // by v<<32|w
-        RS(b->arc_out, na * 32);
-        arc_unpack_kernel<<<nblk(na, 256), 256, 0, st>>>(k0, v0, na, (uint64_t *) b->arc_out.p);
-        ctx->count_launch(SG_T_ARCS, 1);
+    *n_arcs = na;
+    return SG_OK;
+}
+
+// arc_okey / arc_oval (na entries) -> (v, w, comp) order -> arc_out as 4 words per arc
+int arcs_sort_unpack(sg_batch *b, uint64_t na)
+{
+    sg_ctx *ctx = b->ctx;
+    cudaStream_t st = ctx->stream;
+    if (!na) return SG_OK;
+    // order by (v, w, comp): stable LSD, minor key first
+    RS(b->sort_tmp, sort_tmp_words(na) * 4);
+    uint64_t *k0 = (uint64_t *) b->arc_okey.p, *v0 = (uint64_t *) b->arc_oval.p;
+    uint64_t *k1 = (uint64_t *) b->arc_okey_alt.p, *v1 = (uint64_t *) b->arc_oval_alt.p;
+    LAUNCHED(SG_T_ARCS, launch_sort_pairs(v0, k0, v1, k1, na, 0, 40, (uint32_t *) b->sort_tmp.p, st));   // by cov<<1|comp
+    LAUNCHED(SG_T_ARCS, launch_sort_pairs(k0, v0, k1, v1, na, 0, 64, (uint32_t *) b->sort_tmp.p, st));   // by v<<32|w
+    RS(b->arc_out, na * 32);
+    arc_unpack_kernel<<<nblk(na, 256), 256, 0, st>>>(k0, v0, na, (uint64_t *) b->arc_out.p);
+    ctx->count_launch(SG_T_ARCS, 1);
+    return SG_OK;
+}
+
+// this batch's tuples grouped by hash range (b->tuples, 4 words each, (sid, idx) order kept inside a part);
+// b->part_counts[p] = end offset of part p, 0 for an empty part. No host synchronisation.
+int tuples_partition_device(sg_batch *b, int n_parts)
+{
+    sg_ctx *ctx = b->ctx;
+    cudaStream_t st = ctx->stream;
+    const uint64_t N = b->n_syncmers;
+    RS(b->skey, (N + 1) * 8); RS(b->sval, (N + 1) * 8); RS(b->skey_alt, (N + 1) * 8); RS(b->sval_alt, (N + 1) * 8);
+    RS(b->sort_tmp, sort_tmp_words(std::max<uint64_t>(N, 1)) * 4);
+    RS(b->tuples, (N + 1) * 32);
+    RS(b->status, 4 * 8);
+    RS(b->part_counts, 257 * 8);
+    CK(cudaMemsetAsync(b->part_counts.p, 0, 257 * 8, st));
+    if (N) {
+        part_key_kernel<<<nblk(N, 256), 256, 0, st>>>((const uint64_t *) b->key.p, N, (uint32_t) n_parts, (uint64_t *) b->skey.p, (uint64_t *) b->sval.p);
+        ctx->count_launch(SG_T_SORT, 1);
+        // one stable counting pass on the part index keeps the (sid, idx) order inside every part
+        LAUNCHED(SG_T_SORT, launch_sort_pairs((uint64_t *) b->skey.p, (uint64_t *) b->sval.p, (uint64_t *) b->skey_alt.p,
+                (uint64_t *) b->sval_alt.p, N, 0, 8, (uint32_t *) b->sort_tmp.p, st));
+        part_gather_kernel<<<nblk(N, 256), 256, 0, st>>>((const uint64_t *) b->skey.p, (const uint64_t *) b->sval.p,
+                (const uint64_t *) b->key.p, (const uint64_t *) b->occ.p, (const uint64_t *) b->s_mer.p, (const uint64_t *) b->fp.p, N,
+                (uint64_t *) b->tuples.p, (unsigned long long *) b->part_counts.p);
+        ctx->count_launch(SG_T_SORT, 1);
     }
+    b->sorted = false;                                     // skey/sval were used as scratch
+    return SG_OK;
+}
+
+} // namespace sg
+
+extern "C" {
+
+int sg_arcs(sg_batch *b, uint32_t min_k_cov, double min_a_cov_f, uint64_t *n_arcs)
+{
+    if (!b || !n_arcs) return SG_E_ARG;
+    if (!b->counted) return SG_E_STATE;
+    if (b->adopted) return SG_E_STATE;            // needs the per-read id sequences of the local reads: sg_comm_arcs
+    sg_ctx *ctx = b->ctx;
+    cudaStream_t st = ctx->stream;
+    CK(cudaSetDevice(ctx->device));
+    if (b->n_unique >= (1ull << 31)) { ctx->err = "2^31 or more distinct k-mers: vertex ids no longer fit the 64-bit arc keys"; return SG_E_LIMIT; }
+    ctx->t_begin(SG_T_ARCS);
+    uint64_t nslots = 0, na = 0;
+    int rc = arcs_tally_local(b, (const uint64_t *) b->kid.p, &nslots);
+    if (rc) return rc;
+    rc = arcs_emit(b, nslots, (const uint32_t *) b->scm_cov.p, min_k_cov, min_a_cov_f, &na);
+    if (rc) return rc;
+    b->n_arcs = na;
+    rc = arcs_sort_unpack(b, na);
+    if (rc) return rc;
     ctx->t_end(SG_T_ARCS);
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
@@ -221,24 +326,8 @@ int sg_tuples_partition(sg_batch *b, int n_parts, uint64_t *counts, void **d_tup
     sg_ctx *ctx = b->ctx;
     cudaStream_t st = ctx->stream;
     CK(cudaSetDevice(ctx->device));
-    const uint64_t N = b->n_syncmers;
-    RS(b->skey, (N + 1) * 8); RS(b->sval, (N + 1) * 8); RS(b->skey_alt, (N + 1) * 8); RS(b->sval_alt, (N + 1) * 8);
-    RS(b->sort_tmp, sort_tmp_words(std::max<uint64_t>(N, 1)) * 4);
-    RS(b->tuples, (N + 1) * 32);
-    RS(b->status, 4 * 8);
-    RS(b->part_counts, 257 * 8);
-    CK(cudaMemsetAsync(b->part_counts.p, 0, 257 * 8, st));
-    if (N) {
-        part_key_kernel<<<nblk(N, 256), 256, 0, st>>>((const uint64_t *) b->key.p, N, (uint32_t) n_parts, (uint64_t *) b->skey.p, (uint64_t *) b->sval.p);
-        ctx->count_launch(SG_T_SORT, 1);
-        // one stable counting pass on the part index keeps the (sid, idx) order inside every part
-        LAUNCHED(SG_T_SORT, launch_sort_pairs((uint64_t *) b->skey.p, (uint64_t *) b->sval.p, (uint64_t *) b->skey_alt.p,
-                (uint64_t *) b->sval_alt.p, N, 0, 8, (uint32_t *) b->sort_tmp.p, st));
-        part_gather_kernel<<<nblk(N, 256), 256, 0, st>>>((const uint64_t *) b->skey.p, (const uint64_t *) b->sval.p,
-                (const uint64_t *) b->key.p, (const uint64_t *) b->occ.p, (const uint64_t *) b->s_mer.p, (const uint64_t *) b->fp.p, N,
-                (uint64_t *) b->tuples.p, (unsigned long long *) b->part_counts.p);
-        ctx->count_launch(SG_T_SORT, 1);
-    }
+    int rc = tuples_partition_device(b, n_parts);
+    if (rc) return rc;
     std::vector<unsigned long long> ends(256, 0);
     CK(cudaMemcpyAsync(ends.data(), b->part_counts.p, 256 * 8, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
@@ -249,7 +338,6 @@ int sg_tuples_partition(sg_batch *b, int n_parts, uint64_t *counts, void **d_tup
         counts[p] = e - prev;
         prev = e;
     }
-    b->sorted = false;                                     // skey/sval were used as scratch
     *d_tuples = b->tuples.p;
     return SG_OK;
 }

@@ -544,6 +544,75 @@ int sg_stat(sg_batch *b, sg_stat_t *out)
     return SG_OK;
 }
 
+// run lengths of a starts[] array, or the second word of sorted (key, count) pairs, as uint32 in key order
+__global__ void __launch_bounds__(256) run_len_kernel(const uint64_t *starts, uint64_t g, uint32_t *out)
+{
+    const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < g) out[i] = (uint32_t) (starts[i + 1] - starts[i]);
+}
+__global__ void __launch_bounds__(256) pair_split_kernel(const uint64_t *pairs, uint64_t n, uint64_t *key, uint64_t *val)
+{
+    const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { key[i] = pairs[2 * i]; val[i] = pairs[2 * i + 1]; }
+}
+__global__ void __launch_bounds__(256) narrow_kernel(const uint64_t *val, uint64_t n, uint32_t *out)
+{
+    const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (uint32_t) val[i];
+}
+
+int sg_stat_multiplicities(sg_batch *b, int which, uint32_t **host_out, uint64_t *n_out)
+{
+    if (!b || !host_out || !n_out || (which != 0 && which != 1)) return SG_E_ARG;
+    if (!b->extracted) return SG_E_STATE;
+    sg_ctx *ctx = b->ctx;
+    cudaStream_t st = ctx->stream;
+    CK(cudaSetDevice(ctx->device));
+    *host_out = nullptr; *n_out = 0;
+    uint64_t G = 0;
+    if (which == 0) {
+        const uint64_t N = b->t_n();
+        int rc = ensure_sorted(b);
+        if (rc) return rc;
+        RS(b->stat_dev2, 1002 * 8);
+        CK(cudaMemsetAsync(b->stat_dev2.p, 0, 1002 * 8, st));
+        rc = mult_table(b, (const uint64_t *) b->skey.p, N, 1, (unsigned long long *) b->stat_dev2.p, &G);   // leaves starts[0..G]
+        if (rc) return rc;
+        b->smer_slots = 0;
+        if (G) {
+            RS(b->flags, (G + 1) * 4);
+            run_len_kernel<<<nblk(G, 256), 256, 0, st>>>((const uint64_t *) b->starts.p, G, (uint32_t *) b->flags.p);
+            ctx->count_launch(SG_T_STAT, 1);
+        }
+    } else {
+        void *pairs = nullptr;
+        int rc = sg_smer_counts_pack(b, &pairs, &G);
+        if (rc) return rc;
+        if (G) {
+            RS(b->skey2, (G + 1) * 8); RS(b->sval2, (G + 1) * 8);
+            RS(b->ids, (G + 2) * 8); RS(b->starts, (G + 2) * 8);
+            RS(b->sort_tmp, sort_tmp_words(G) * 4);
+            pair_split_kernel<<<nblk(G, 256), 256, 0, st>>>((const uint64_t *) pairs, G, (uint64_t *) b->skey2.p, (uint64_t *) b->sval2.p);
+            LAUNCHED(SG_T_STAT, launch_sort_pairs((uint64_t *) b->skey2.p, (uint64_t *) b->sval2.p, (uint64_t *) b->ids.p, (uint64_t *) b->starts.p,
+                    G, 0, 64, (uint32_t *) b->sort_tmp.p, st));
+            RS(b->flags, (G + 1) * 4);
+            narrow_kernel<<<nblk(G, 256), 256, 0, st>>>((const uint64_t *) b->sval2.p, G, (uint32_t *) b->flags.p);
+            ctx->count_launch(SG_T_STAT, 2);
+        }
+    }
+    if (G) {
+        uint32_t *h = (uint32_t *) malloc(G * sizeof(uint32_t));
+        if (!h) return SG_E_NOMEM;
+        CK(cudaMemcpyAsync(h, b->flags.p, G * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        CK(cudaGetLastError());
+        b->d2h_bytes += G * 4;
+        *host_out = h;
+    }
+    *n_out = G;
+    return SG_OK;
+}
+
 int sg_smer_counts_pack(sg_batch *b, void **d_pairs, uint64_t *n)
 {
     if (!b || !d_pairs || !n) return SG_E_ARG;

@@ -66,6 +66,7 @@ struct sg_pipe {
     sg_ctx *mctx = nullptr;
     sg_batch *master = nullptr;
     std::string err;
+    uint64_t sid_base = 0;       // global index of the first read (multi-GPU: this GPU's block of the read set)
 };
 
 static inline unsigned nblk(uint64_t n, unsigned t) { return (unsigned) ((n + t - 1) / t); }
@@ -129,6 +130,8 @@ void sg_pipe_destroy(sg_pipe *p)
 sg_batch *sg_pipe_master(sg_pipe *p) { return p ? p->master : nullptr; }
 sg_ctx *sg_pipe_ctx(sg_pipe *p) { return p ? p->mctx : nullptr; }
 const char *sg_pipe_last_error(sg_pipe *p) { return p ? p->err.c_str() : "no pipe"; }
+
+int sg_pipe_set_sid_base(sg_pipe *p, uint64_t sid_base) { if (!p) return SG_E_ARG; p->sid_base = sid_base; return SG_OK; }
 
 uint64_t sg_pipe_launches(sg_pipe *p)
 {
@@ -233,7 +236,7 @@ static int pipe_run(sg_pipe *p, const char *bases, const uint64_t *off, uint64_t
             double t0 = now();
             std::vector<uint64_t> l_hs(nr + 1), l_rl(nr + 1), l_scm(nr + 1);
             const uint64_t *loff = in->h_off[cur];
-            sg_batch_set_sid_base(b, r0);
+            sg_batch_set_sid_base(b, p->sid_base + r0);
             sg_extract_sizes_t z;
             memset(&z, 0, sizeof(z));
             {
@@ -364,7 +367,7 @@ static int pipe_run(sg_pipe *p, const char *bases, const uint64_t *off, uint64_t
 
     // the master batch now looks like the result of one big sg_extract
     M->d_bases = nullptr; M->d_off = nullptr;
-    M->n_reads = n_reads; M->total_bases = total; M->sid_base = 0;
+    M->n_reads = n_reads; M->total_bases = total; M->sid_base = p->sid_base;
     M->k = k; M->s = s;
     M->n_syncmers = tot.scm; M->n_amb_total = tot.amb; M->n_lrl_total = tot.lrl; M->hoco_bases = tot.hoco;
     M->extracted = true; M->counted = M->sorted = M->adopted = M->sizes_known = M->have_kid_local = false;

@@ -408,6 +408,77 @@ static void print_verbose_tables(sr_db_t *db, FILE *fo, int list_all)
     free(t); free(key);
 }
 
+/*
+ * The singleton count of sr_db_stat when NO key occurs exactly once. The reference tabulates "how many keys have
+ * multiplicity m" in a khashl map and reads the singletons as the value under key 1; when that key is absent it
+ * reports whatever value its scan over the table met last (kh_ctab_stat, syncmer.c:618-646: `c` keeps the value of the
+ * last occupied slot). After read error correction there are normally no singletons left, so that number is on
+ * stderr in every default run and is reproduced here: the multiplicities are replayed in the order the reference
+ * inserts them (ascending key order, from the device) into a table with khashl 0.1's geometry -- capacity a power
+ * of two from 4 up, bucket = Wang hash x 2654435769 >> (32 - bits), linear probing, doubling at 75 % load where the old
+ * slots are re-seated in slot order and an element that lands on a not yet re-seated one takes its place and
+ * sends it on (khashl.h:130-211).
+ */
+typedef struct { uint32_t key; int val; uint8_t full; } mslot_t;
+
+static uint32_t mslot_home(uint32_t key, int bits)
+{
+    key += ~(key << 15); key ^= key >> 10; key += key << 3; key ^= key >> 6; key += ~(key << 11); key ^= key >> 16;
+    return (key * 2654435769u) >> (32 - bits);
+}
+
+static int value_of_last_slot(const uint32_t *mult, uint64_t n)
+{
+    mslot_t *tab = 0;
+    uint32_t cap = 0, live = 0, j;
+    int bits = 0, last = 0;
+    uint64_t x;
+    for (x = 0; x < n; ++x) {
+        uint32_t i, start;
+        if (live >= (cap >> 1) + (cap >> 2)) {              /* also true for the empty table: 0 >= 0 */
+            int nbits = 2;
+            uint32_t ncap;
+            mslot_t *next;
+            while ((1u << nbits) < cap + 1) ++nbits;
+            ncap = 1u << nbits;
+            next = (mslot_t *) calloc(ncap, sizeof(mslot_t));
+            for (j = 0; j < cap; ++j) {
+                mslot_t moving;
+                if (!tab[j].full) continue;
+                moving = tab[j]; tab[j].full = 0;
+                for (;;) {
+                    i = mslot_home(moving.key, nbits);
+                    while (next[i].full) i = (i + 1) & (ncap - 1);
+                    next[i] = moving;
+                    if (i < cap && tab[i].full) { moving = tab[i]; tab[i].full = 0; }   /* the old tenant of that slot goes next */
+                    else break;
+                }
+            }
+            free(tab);
+            tab = next; cap = ncap; bits = nbits;
+        }
+        i = start = mslot_home(mult[x], bits);
+        while (tab[i].full && tab[i].key != mult[x]) { i = (i + 1) & (cap - 1); if (i == start) break; }
+        if (!tab[i].full) { tab[i].key = mult[x]; tab[i].val = 1; tab[i].full = 1; ++live; }
+        else ++tab[i].val;
+    }
+    for (j = 0; j < cap; ++j) if (tab[j].full) last = tab[j].val;
+    free(tab);
+    return last;
+}
+
+static int singletons_as_reported(sg_batch *b, int which, int64_t true_count)
+{
+    uint32_t *mult = 0;
+    uint64_t n = 0;
+    int v;
+    if (true_count > 0) return (int) true_count;
+    if (sg_stat_multiplicities(b, which, &mult, &n) != SG_OK || n == 0) { free(mult); return 0; }
+    v = value_of_last_slot(mult, n);
+    free(mult);
+    return v;
+}
+
 void sr_db_stat(sr_db_t *sr_db, FILE *fo, int verbose)
 {
     sg_batch *b = batch_of(sr_db, 0);
@@ -423,9 +494,9 @@ void sr_db_stat(sr_db_t *sr_db, FILE *fo, int verbose)
     s->syncmer_n = st.n_syncmers;
     s->syncmer_per_read = (double) st.n_syncmers / (double) sr_db->n;
     s->syncmer_avg_dist = (double) st.gap_sum / (double) st.n_gaps;
-    s->smer_unique = (int) st.smer_unique; s->smer_singleton = (int) st.smer_singleton;
+    s->smer_unique = (int) st.smer_unique; s->smer_singleton = singletons_as_reported(b, 1, st.smer_cnts[1]);
     s->smer_avg_cnt = (double) st.n_syncmers / (double) st.smer_unique;
-    s->kmer_unique = (int) st.kmer_unique; s->kmer_singleton = (int) st.kmer_singleton;
+    s->kmer_unique = (int) st.kmer_unique; s->kmer_singleton = singletons_as_reported(b, 0, st.kmer_cnts[1]);
     s->kmer_avg_cnt = (double) st.n_syncmers / (double) st.kmer_unique;
     s->smer_peak_hom = find_peaks(1001, 5, st.smer_cnts, &s->smer_peak_het, verbose - 1);
     s->kmer_peak_hom = find_peaks(1001, 5, st.kmer_cnts, &s->kmer_peak_het, verbose - 1);

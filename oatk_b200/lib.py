@@ -59,10 +59,12 @@ SYMBOLS = [
     "sg_ctx_launches", "sg_ctx_enable_timing", "sg_ctx_timings",
     "sg_batch_create", "sg_batch_destroy", "sg_batch_set_reads_host", "sg_batch_set_reads_device",
     "sg_batch_set_sid_base", "sg_extract", "sg_extract_sizes", "sg_extract_download",
-    "sg_stat", "sg_count", "sg_count_sizes", "sg_count_download", "sg_arcs", "sg_arcs_download",
+    "sg_stat", "sg_stat_multiplicities", "sg_count", "sg_count_sizes", "sg_count_download", "sg_arcs", "sg_arcs_download",
     "sg_tuples_partition", "sg_tuples_adopt", "sg_debug_set_hash_bits", "sg_debug_set_sort_low_bits", "sg_debug_sort_info", "sg_debug_scan_info", "sg_batch_buffer",
     "sg_ids_pack", "sg_ids_scatter", "sg_batch_set_exact_verify", "sg_smer_counts_pack", "sg_smer_counts_merge", "sg_batch_set_lists_host",
-    "sg_pipe_create", "sg_pipe_destroy", "sg_pipe_run_host", "sg_pipe_run_host_cb", "sg_pipe_master", "sg_pipe_ctx", "sg_pipe_last_error", "sg_pipe_launches",
+    "sg_comm_unique_id", "sg_comm_init_rank", "sg_comm_init_all", "sg_comm_destroy", "sg_comm_rank", "sg_comm_world", "sg_comm_bytes_sent",
+    "sg_comm_exchange_tuples", "sg_comm_global_stat", "sg_comm_return_ids", "sg_comm_arcs",
+    "sg_pipe_create", "sg_pipe_destroy", "sg_pipe_run_host", "sg_pipe_run_host_cb", "sg_pipe_master", "sg_pipe_ctx", "sg_pipe_last_error", "sg_pipe_launches", "sg_pipe_set_sid_base",
 ]
 
 
@@ -107,6 +109,17 @@ def _lib():
                        ("sg_smer_counts_merge", [vp, vp, u64, vp]), ("sg_ids_scatter", [vp, vp, u64]), ("sg_batch_set_exact_verify", [vp, i32])):
         if hasattr(L, name):
             getattr(L, name).argtypes = args
+    L.sg_comm_unique_id.argtypes = [vp]
+    L.sg_comm_init_rank.argtypes = [vp, i32, i32, vp, C.POINTER(vp)]
+    L.sg_comm_init_all.argtypes = [C.POINTER(vp), i32, C.POINTER(vp)]
+    L.sg_comm_destroy.argtypes = [vp]
+    L.sg_comm_destroy.restype = None
+    L.sg_comm_bytes_sent.argtypes = [vp]
+    L.sg_comm_bytes_sent.restype = u64
+    L.sg_comm_exchange_tuples.argtypes = [vp, vp]
+    L.sg_comm_global_stat.argtypes = [vp, vp, vp]
+    L.sg_comm_return_ids.argtypes = [vp, vp, C.POINTER(u64), C.POINTER(u64)]
+    L.sg_comm_arcs.argtypes = [vp, vp, C.c_uint32, C.c_double, i32, C.POINTER(u64)]
     L.sg_pipe_create.argtypes = [i32, i32, C.POINTER(vp)]
     L.sg_pipe_destroy.argtypes = [vp]
     L.sg_pipe_destroy.restype = None
@@ -336,6 +349,53 @@ class Batch:
             pass
 
 
+def comm_unique_id():
+    """128 bytes that rank 0 hands to the other ranks (ncclGetUniqueId)"""
+    buf = C.create_string_buffer(128)
+    rc = _lib().sg_comm_unique_id(buf)
+    if rc:
+        raise SgError("sg_comm_unique_id: %s" % _lib().sg_strerror(rc).decode())
+    return buf.raw
+
+
+class Comm:
+    """the multi-GPU exchange in C over NCCL (csrc/sg_comm.cu); one per rank, every call is collective"""
+
+    def __init__(self, ctx, world, rank, unique_id):
+        self.ctx, self.world, self.rank = ctx, world, rank
+        h = C.c_void_p()
+        _ck(ctx.h, _lib().sg_comm_init_rank(ctx.h, world, rank, unique_id, C.byref(h)), "sg_comm_init_rank")
+        self.h = h
+
+    def exchange_tuples(self, batch):
+        _ck(self.ctx.h, _lib().sg_comm_exchange_tuples(self.h, batch.h), "sg_comm_exchange_tuples")
+
+    def global_stat(self, batch, st):
+        _ck(self.ctx.h, _lib().sg_comm_global_stat(self.h, batch.h, C.byref(st)), "sg_comm_global_stat")
+        return st
+
+    def return_ids(self, batch):
+        base, tot = C.c_uint64(0), C.c_uint64(0)
+        _ck(self.ctx.h, _lib().sg_comm_return_ids(self.h, batch.h, C.byref(base), C.byref(tot)), "sg_comm_return_ids")
+        return int(base.value), int(tot.value)
+
+    def arcs(self, batch, min_k_cov, min_a_cov_f, root=0):
+        n = C.c_uint64(0)
+        _ck(self.ctx.h, _lib().sg_comm_arcs(self.h, batch.h, min_k_cov, min_a_cov_f, root, C.byref(n)), "sg_comm_arcs")
+        out = np.zeros((n.value, 4), np.uint64)
+        if n.value:
+            _ck(self.ctx.h, _lib().sg_arcs_download(batch.h, out.ctypes.data), "sg_arcs_download")
+        return out
+
+    def bytes_sent(self):
+        return int(_lib().sg_comm_bytes_sent(self.h))
+
+    def close(self):
+        if self.h:
+            _lib().sg_comm_destroy(self.h)
+            self.h = None
+
+
 def _unpad(buf, off, lens):
     """concatenate buf[off[r] : off[r] + lens[r]] over reads"""
     n = len(lens)
@@ -379,6 +439,12 @@ class Pipe:
         m._keep = None
         m.close = lambda: None
         self.master = m
+
+    def set_sid_base(self, base):
+        _lib().sg_pipe_set_sid_base.argtypes = [C.c_void_p, C.c_uint64]
+        rc = _lib().sg_pipe_set_sid_base(self.h, base)
+        if rc != 0:
+            raise SgError(rc, "sg_pipe_set_sid_base")
 
     def run_host(self, bases_ptr, off_ptr, n_reads, k, s, chunk_reads, out, caps):
         z = ExtractSizes()
