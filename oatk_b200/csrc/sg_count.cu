@@ -44,15 +44,31 @@ __global__ void __launch_bounds__(256) tuple_init_kernel(const uint64_t *key, ui
 constexpr uint32_t SORT_FIX_CAP = 8192;       // listed pairs
 constexpr uint64_t SORT_FIX_MAXRUN = 4096;    // longest run a single thread is allowed to repair
 
+// Lists, for every run (maximal stretch of equal top bits) that is out of order, the position of its FIRST inversion.
+// Ownership is decided here, on data nobody is writing: a thread that sees an inversion walks back through its run and
+// stays silent if an earlier inversion exists. Runs are disjoint, so the repair threads never touch the same element.
 __global__ void __launch_bounds__(256) sort_detect_kernel(const uint64_t *k, uint64_t n, int SORT_LOW_BITS, uint32_t *fix /* [0] count, [1] overflow, [2..] positions */)
 {
     const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (i + 1 >= n) return;
     const uint64_t a = k[i], b = k[i + 1];
-    if ((a >> SORT_LOW_BITS) == (b >> SORT_LOW_BITS) && a > b) {
-        const uint32_t o = atomicAdd(&fix[0], 1u);
-        if (o < SORT_FIX_CAP) fix[2 + o] = (uint32_t) i; else fix[1] = 1u;
+    if ((a >> SORT_LOW_BITS) != (b >> SORT_LOW_BITS) || a <= b) return;
+    const uint64_t top = a >> SORT_LOW_BITS;
+    for (uint64_t j = i; j > 0 && (k[j - 1] >> SORT_LOW_BITS) == top; --j) {
+        if (k[j - 1] > k[j]) return;                       // an earlier inversion owns the run
+        if (i - j > SORT_FIX_MAXRUN) { fix[1] = 1u; return; }
     }
+    const uint32_t o = atomicAdd(&fix[0], 1u);
+    if (o < SORT_FIX_CAP) fix[2 + o] = (uint32_t) i; else fix[1] = 1u;
+}
+
+// any inversion left inside a run? (run after the repair: its answer decides whether the partial sort stands)
+__global__ void __launch_bounds__(256) sort_check_kernel(const uint64_t *k, uint64_t n, int SORT_LOW_BITS, uint32_t *fix)
+{
+    const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i + 1 >= n) return;
+    const uint64_t a = k[i], b = k[i + 1];
+    if ((a >> SORT_LOW_BITS) == (b >> SORT_LOW_BITS) && a > b) fix[1] = 1u;
 }
 
 __global__ void __launch_bounds__(128) sort_repair_kernel(uint64_t *k, uint64_t *v, uint64_t n, int SORT_LOW_BITS, uint32_t *fix)
@@ -61,22 +77,11 @@ __global__ void __launch_bounds__(128) sort_repair_kernel(uint64_t *k, uint64_t 
     for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < cnt; e += gridDim.x * blockDim.x) {
         const uint64_t i = fix[2 + e];
         const uint64_t top = k[i] >> SORT_LOW_BITS;
-        // walk to the start of the run; the run belongs to its FIRST out-of-order pair
-        uint64_t s0 = i;
-        bool owner = true;
-        while (s0 > 0 && (k[s0 - 1] >> SORT_LOW_BITS) == top) {
-            if (k[s0 - 1] > k[s0]) { owner = false; break; }
-            --s0;
-            if (i - s0 > SORT_FIX_MAXRUN) { fix[1] = 1u; owner = false; break; }
-        }
-        if (!owner) continue;
-        uint64_t s1 = i + 1;
-        while (s1 + 1 < n && (k[s1 + 1] >> SORT_LOW_BITS) == top) {
-            ++s1;
-            if (s1 - s0 > SORT_FIX_MAXRUN) { fix[1] = 1u; owner = false; break; }
-        }
-        if (!owner) continue;
-        for (uint64_t a = s0 + 1; a <= s1; ++a) {          // stable insertion sort of [s0, s1]
+        uint64_t s0 = i, s1 = i + 1;                       // the run: everything before i is in order already
+        while (s0 > 0 && (k[s0 - 1] >> SORT_LOW_BITS) == top) --s0;
+        while (s1 + 1 < n && (k[s1 + 1] >> SORT_LOW_BITS) == top) ++s1;
+        if (s1 - s0 > SORT_FIX_MAXRUN) { fix[1] = 1u; continue; }
+        for (uint64_t a = i + 1; a <= s1; ++a) {           // stable insertion sort of [s0, s1]
             const uint64_t kk = k[a], vv = v[a];
             uint64_t b = a;
             while (b > s0 && k[b - 1] > kk) { k[b] = k[b - 1]; v[b] = v[b - 1]; --b; }
@@ -407,7 +412,8 @@ static int ensure_sorted(sg_batch *b)
         CK(cudaMemsetAsync(b->sort_fix.p, 0, 8, st));
         sort_detect_kernel<<<nblk(N, 256), 256, 0, st>>>((const uint64_t *) b->skey.p, N, SORT_LOW_BITS, (uint32_t *) b->sort_fix.p);
         sort_repair_kernel<<<8, 128, 0, st>>>((uint64_t *) b->skey.p, (uint64_t *) b->sval.p, N, SORT_LOW_BITS, (uint32_t *) b->sort_fix.p);
-        ctx->count_launch(SG_T_SORT, 2);
+        sort_check_kernel<<<nblk(N, 256), 256, 0, st>>>((const uint64_t *) b->skey.p, N, SORT_LOW_BITS, (uint32_t *) b->sort_fix.p);
+        ctx->count_launch(SG_T_SORT, 3);
         uint32_t hf[2];
         CK(cudaMemcpyAsync(hf, b->sort_fix.p, sizeof(hf), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));

@@ -29,6 +29,8 @@
  * reads the graph. Host code: it walks pointer-rich structures (per-read arrays, per-vertex strings).
  */
 #include <stdlib.h>
+#include <sys/time.h>
+#include <sys/resource.h>
 #include <string.h>
 #include <math.h>
 #include <assert.h>
@@ -460,6 +462,15 @@ void read_error_correction(sr_db_t *sr_db, scg_t *g, double max_edist, uint32_t 
         uint32_t err_arc_c, double max_arc_f, int n_threads, FILE *fo, int verbose)
 {
     (void) fo;                                          /* the corrected-read FASTA is a debugging aid of the reference */
+    double cpu_at_entry, wall_at_entry;
+    {
+        struct rusage ru;
+        struct timeval tv;
+        getrusage(RUSAGE_SELF, &ru);
+        gettimeofday(&tv, 0);
+        cpu_at_entry = ru.ru_utime.tv_sec + ru.ru_stime.tv_sec + 1e-6 * (ru.ru_utime.tv_usec + ru.ru_stime.tv_usec);
+        wall_at_entry = tv.tv_sec + 1e-6 * tv.tv_usec;
+    }
     if (n_threads <= 0) n_threads = 1;
     if (n_threads > 64) n_threads = 64;
     /* The walk needs the hoco text of the vertices and the overlaps of the arcs it can reach. The reference computes
@@ -508,6 +519,15 @@ void read_error_correction(sr_db_t *sr_db, scg_t *g, double max_edist, uint32_t 
         fprintf(stderr, "[M::%s]             - ambiguous seqs : %ld\n", __func__, stats[8]);
         fprintf(stderr, "[M::%s]             - ambiguous path : %ld\n", __func__, stats[9]);
         fprintf(stderr, "[M::%s]      error blocks overlapped : %ld\n", __func__, stats[10]);
+        {   /* syncerr.c:921-922: the step's own clocks */
+            struct rusage ru;
+            struct timeval tv;
+            getrusage(RUSAGE_SELF, &ru);
+            gettimeofday(&tv, 0);
+            fprintf(stderr, "[M::%s]   error correction  CPU time : %.3f sec\n", __func__,
+                    ru.ru_utime.tv_sec + ru.ru_stime.tv_sec + 1e-6 * (ru.ru_utime.tv_usec + ru.ru_stime.tv_usec) - cpu_at_entry);
+            fprintf(stderr, "[M::%s]   error correction real time : %.3f sec\n", __func__, tv.tv_sec + 1e-6 * tv.tv_usec - wall_at_entry);
+        }
     }
     for (int t = 0; t < n_threads; ++t) {
         ec_worker_t *W = &J[t].W;

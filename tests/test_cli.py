@@ -63,7 +63,7 @@ def norm_stderr(txt, exe):
         if not re.match(r"\[[MWE]::", line):
             continue
         line = re.sub(r"Real time: [0-9.]+ sec; CPU: [0-9.]+ sec; Peak RSS: [0-9.]+ GB", "Real time: T", line)
-        line = re.sub(r"(CPU|real) time: [0-9.]+", r"\1 time: T", line)
+        line = re.sub(r"(CPU|real) time *: [0-9.]+", r"\1 time: T", line)
         line = line.replace(exe, "syncasm")
         out.append(line)
     return out
