@@ -114,6 +114,14 @@ typedef struct {
 } sg_extract_out_t;
 int sg_extract_download(sg_batch *b, const sg_extract_out_t *out);
 
+/* f1, the bulk of scg_syncmer_consensus (reference syncasm.c:946-998) on the device. For each of n_req syncmers the caller lists the
+ * occurrences that count (occ[occ_off[i] .. occ_off[i+1]), each read << 32 | hoco start << 1 | strand -- i.e. sr_t.sid and
+ * sr_t.m_pos[] of the copies read error correction left alone); sums[i * k + j] = sum over strand-0 copies of (run length - 1) at
+ * start + j plus sum over strand-1 copies at start + k - 1 - j, long runs resolved through the side list. Needs the run lengths
+ * on the device: a batch after sg_extract, or a pipe's master batch with sg_pipe_keep_run_lengths. Synchronises. */
+int sg_runlen_sums(sg_batch *b, uint64_t n_req, const uint64_t *occ_off, const uint64_t *occ, uint64_t *sums /* host, n_req * k */);
+int sg_runlen_resident(sg_batch *b);                          /* 1 when sg_runlen_sums can be served */
+
 /* a5: the counting part of sr_db_stat. Dense multiplicity-of-multiplicity tables
  * for distinct s-mer codes and distinct (k_mer >> 1) keys, multiplicities >= 1000
  * summed in [1000] (reference kh_ctab_cnt with MAX_DEPTH 1000, syncmer.c:639-659),
@@ -201,6 +209,10 @@ sg_batch *sg_pipe_master(sg_pipe *p);
 sg_ctx *sg_pipe_ctx(sg_pipe *p);
 const char *sg_pipe_last_error(sg_pipe *p);
 uint64_t sg_pipe_launches(sg_pipe *p);
+/* 1: the run lengths (ho_rl, 1 byte per hoco base -- as large as the input) stay on the device in the master batch instead of
+ * being downloaded; sg_runlen_sums then serves the one consumer they have, the run-length consensus. sg_pipe_run_host does the
+ * same on its own when the caller passes no ho_rl buffer. */
+int sg_pipe_keep_run_lengths(sg_pipe *p, int on);
 /* multi-GPU: global index of this pipe's first read (sid of read i = sid_base + i); default 0 */
 int sg_pipe_set_sid_base(sg_pipe *p, uint64_t sid_base);
 

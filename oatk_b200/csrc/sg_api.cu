@@ -139,6 +139,8 @@ static void reset_state(sg_batch *b)
     b->n_adopted = 0;
     b->have_kid_local = false;
     b->pipe_fed = false;
+    b->rl_resident = false;
+    b->lrl_sorted = false;
     b->keys_are_ids = false;
     b->tup_valid = false;
     b->k = b->s = 0;
@@ -299,6 +301,8 @@ int sg_extract(sg_batch *b, int k, int s)
     ctx->t_end(SG_T_KMERHASH);
     CK(cudaGetLastError());
     b->extracted = true;
+    b->rl_resident = true;                     // ho_rl and the side list of this batch stay on the device until the next extract
+    b->lrl_sorted = false;
     return SG_OK;
 }
 
@@ -373,12 +377,13 @@ int sg_extract_download(sg_batch *b, const sg_extract_out_t *o)
     if ((o->hoco_s_buf || o->ho_rl_buf) && n) {
         // pack the capacity-indexed device layout into the 16-byte aligned compact one, then one copy each
         const uint64_t hsb = b->h_hs_off[n], rlb = b->h_rl_off[n];
-        RS(b->pk_hs, hsb + 16); RS(b->pk_rl, rlb + 16);
+        if (o->hoco_s_buf) RS(b->pk_hs, hsb + 16);
+        if (o->ho_rl_buf) RS(b->pk_rl, rlb + 16);
         RS(b->pk_hs_off, (n + 1) * 8); RS(b->pk_rl_off, (n + 1) * 8);
         CK(cudaMemcpyAsync(b->pk_hs_off.p, b->h_hs_off.data(), (n + 1) * 8, cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync(b->pk_rl_off.p, b->h_rl_off.data(), (n + 1) * 8, cudaMemcpyHostToDevice, st));
         ctx->t_begin(SG_T_PACK);
-        LAUNCHED(SG_T_PACK, launch_pack(b, st));
+        LAUNCHED(SG_T_PACK, launch_pack(b, st, o->hoco_s_buf != nullptr, o->ho_rl_buf != nullptr));
         ctx->t_end(SG_T_PACK);
         if (o->hoco_s_buf && hsb) CK(cudaMemcpyAsync(o->hoco_s_buf, b->pk_hs.p, hsb, cudaMemcpyDeviceToHost, st));
         if (o->ho_rl_buf && rlb) CK(cudaMemcpyAsync(o->ho_rl_buf, b->pk_rl.p, rlb, cudaMemcpyDeviceToHost, st));

@@ -80,7 +80,10 @@ struct sg_batch {
     sg::DevBuf tuples, part_counts, akey, aocc, asmer, afp, kid_local, sfp;
     bool have_kid_local = false;
     bool adopted = false;
-    bool pipe_fed = false;                       // filled by sg_pipe_run_host: no ho_rl / raw reads on the device
+    bool pipe_fed = false;                       // filled by sg_pipe_run_host: no raw reads on the device, ho_rl only if rl_resident
+    bool rl_resident = false;                    // ho_rl (capacity layout) and the long-run side list are on the device: sg_runlen_sums works
+    bool lrl_sorted = false;                     // lrl_key / lrl_sval hold the side list ordered by (read, hoco index)
+    sg::DevBuf lrl_key, lrl_sval, lrl_key_alt, lrl_val_alt, rq_off, rq_occ, rq_out;
     uint64_t n_adopted = 0;
     // the tuple set a5/a6 work on
     const uint64_t *t_key() const { return (const uint64_t *) (adopted ? akey.p : key.p); }
@@ -91,5 +94,5 @@ struct sg_batch {
 };
 
 namespace sg {
-int launch_pack(sg_batch *b, cudaStream_t st);
+int launch_pack(sg_batch *b, cudaStream_t st, bool want_hs, bool want_rl);
 }

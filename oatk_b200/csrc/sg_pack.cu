@@ -31,17 +31,17 @@ __global__ void __launch_bounds__(128) pack_kernel(const uint64_t *hoff, const u
     uint4 *dst_s = reinterpret_cast<uint4 *>(pk_hs + hs_off[r]);
     uint4 *dst_r = reinterpret_cast<uint4 *>(pk_rl + rl_off[r]);
     const int64_t ns = (hsb + 15) >> 4, nr = (L + 15) >> 4;
-    for (int64_t i = threadIdx.x; i < ns; i += blockDim.x) dst_s[i] = mask_tail(src_s[i], hsb - 16 * i);
-    for (int64_t i = threadIdx.x; i < nr; i += blockDim.x) dst_r[i] = mask_tail(src_r[i], L - 16 * i);
+    if (pk_hs) for (int64_t i = threadIdx.x; i < ns; i += blockDim.x) dst_s[i] = mask_tail(src_s[i], hsb - 16 * i);
+    if (pk_rl) for (int64_t i = threadIdx.x; i < nr; i += blockDim.x) dst_r[i] = mask_tail(src_r[i], L - 16 * i);
 }
 
-int launch_pack(sg_batch *b, cudaStream_t st)
+int launch_pack(sg_batch *b, cudaStream_t st, bool want_hs, bool want_rl)
 {
     if (b->n_reads == 0) return 0;
     pack_kernel<<<(unsigned) b->n_reads, 128, 0, st>>>((const uint64_t *) b->hoff.p, (const uint32_t *) b->hoco_l.p,
             (const uint8_t *) b->hoco_s.p, (const uint8_t *) b->ho_rl.p,
             (const uint64_t *) b->pk_hs_off.p, (const uint64_t *) b->pk_rl_off.p,
-            (uint8_t *) b->pk_hs.p, (uint8_t *) b->pk_rl.p);
+            want_hs ? (uint8_t *) b->pk_hs.p : nullptr, want_rl ? (uint8_t *) b->pk_rl.p : nullptr);
     return 1;
 }
 

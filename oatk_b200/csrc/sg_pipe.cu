@@ -27,6 +27,11 @@ __global__ void __launch_bounds__(256) add_offset_kernel(const uint64_t *src, ui
     const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i] = src[i] + add;
 }
+__global__ void __launch_bounds__(256) add_offset32_kernel(const uint32_t *src, uint32_t *dst, uint64_t n, uint32_t add)
+{
+    const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[i] + add;
+}
 
 } // namespace sg
 
@@ -67,6 +72,7 @@ struct sg_pipe {
     sg_batch *master = nullptr;
     std::string err;
     uint64_t sid_base = 0;       // global index of the first read (multi-GPU: this GPU's block of the read set)
+    bool keep_rl = false;        // ho_rl stays on the device (master batch) instead of travelling to the host: sg_runlen_sums serves the consensus
 };
 
 static inline unsigned nblk(uint64_t n, unsigned t) { return (unsigned) ((n + t - 1) / t); }
@@ -131,6 +137,8 @@ sg_batch *sg_pipe_master(sg_pipe *p) { return p ? p->master : nullptr; }
 sg_ctx *sg_pipe_ctx(sg_pipe *p) { return p ? p->mctx : nullptr; }
 const char *sg_pipe_last_error(sg_pipe *p) { return p ? p->err.c_str() : "no pipe"; }
 
+int sg_pipe_keep_run_lengths(sg_pipe *p, int on) { if (!p) return SG_E_ARG; p->keep_rl = on != 0; return SG_OK; }
+
 int sg_pipe_set_sid_base(sg_pipe *p, uint64_t sid_base) { if (!p) return SG_E_ARG; p->sid_base = sid_base; return SG_OK; }
 
 uint64_t sg_pipe_launches(sg_pipe *p)
@@ -167,6 +175,11 @@ static int pipe_run(sg_pipe *p, const char *bases, const uint64_t *off, uint64_t
     const uint64_t qwin = (uint64_t) (k - s + 1);
     const uint64_t cap_pos = total + 64 * n_reads + 64;
     const uint64_t capN = cb ? std::min<uint64_t>(total + n_reads, 16 * (total / qwin + n_reads)) + 1024 : caps->max_syncmers;
+    // run lengths stay on the device when asked to (sg_pipe_keep_run_lengths) or when the caller gave no buffer for them
+    const bool keep_rl = p->keep_rl || (!cb && out && !out->ho_rl_buf);
+    const uint64_t cap_lrl = total / 256 + 1024;             // a listed run is at least 256 bases long
+    if (keep_rl && (M->ho_rl.reserve(cap_pos + 64) || M->lrl_sid.reserve(cap_lrl * 4) || M->lrl_idx.reserve(cap_lrl * 4) || M->lrl_val.reserve(cap_lrl * 4)))
+        return fail(SG_E_NOMEM, "master allocation failed");
     if (M->hoff.reserve((n_reads + 1) * 8) || M->hoco_s.reserve(cap_pos / 4 + 64) || M->hoco_l.reserve((n_reads + 1) * 4) ||
             M->n_scm.reserve((n_reads + 1) * 4) || M->scm_off.reserve((n_reads + 1) * 8) || M->n_amb.reserve((n_reads + 1) * 4) ||
             M->key.reserve((capN + 1) * 8) || M->occ.reserve((capN + 1) * 8) || M->m_pos.reserve((capN + 1) * 4) || M->s_mer.reserve((capN + 1) * 8) || M->fp.reserve((capN + 1) * 8))
@@ -260,7 +273,7 @@ static int pipe_run(sg_pipe *p, const char *bases, const uint64_t *off, uint64_t
                 base = tot;
                 if (!rc && !first_err) {
                     if (tot.scm + z.n_syncmers > capN || (!cb && (tot.hs + z.hoco_s_bytes > caps->hoco_s_bytes ||
-                            tot.rl + z.ho_rl_bytes > caps->ho_rl_bytes || tot.amb + z.n_ambiguous > caps->max_ambiguous ||
+                            (out->ho_rl_buf && tot.rl + z.ho_rl_bytes > caps->ho_rl_bytes) || tot.amb + z.n_ambiguous > caps->max_ambiguous ||
                             tot.lrl + z.n_long_runs > caps->max_long_runs))) {
                         rc = SG_E_NOMEM; msg = "caller capacities too small";
                     }
@@ -278,6 +291,15 @@ static int pipe_run(sg_pipe *p, const char *bases, const uint64_t *off, uint64_t
             // ---- append to the master batch (device to device, this slot's stream) ----
             const uint64_t N = z.n_syncmers;
             if (hcap) cudaMemcpyAsync((uint8_t *) M->hoco_s.p + base.hoff / 4, b->hoco_s.p, hcap / 4, cudaMemcpyDeviceToDevice, st);
+            if (keep_rl) {
+                if (hcap) cudaMemcpyAsync((uint8_t *) M->ho_rl.p + base.hoff, b->ho_rl.p, hcap, cudaMemcpyDeviceToDevice, st);
+                if (z.n_long_runs) {
+                    add_offset32_kernel<<<nblk(z.n_long_runs, 256), 256, 0, st>>>((const uint32_t *) b->lrl_sid.p, (uint32_t *) M->lrl_sid.p + base.lrl, z.n_long_runs, (uint32_t) r0);
+                    cudaMemcpyAsync((uint32_t *) M->lrl_idx.p + base.lrl, b->lrl_idx.p, z.n_long_runs * 4, cudaMemcpyDeviceToDevice, st);
+                    cudaMemcpyAsync((uint32_t *) M->lrl_val.p + base.lrl, b->lrl_val.p, z.n_long_runs * 4, cudaMemcpyDeviceToDevice, st);
+                    ctx->count_launch(SG_T_PLACE, 1);
+                }
+            }
             cudaMemcpyAsync((uint32_t *) M->hoco_l.p + r0, b->hoco_l.p, nr * 4, cudaMemcpyDeviceToDevice, st);
             cudaMemcpyAsync((uint32_t *) M->n_scm.p + r0, b->n_scm.p, nr * 4, cudaMemcpyDeviceToDevice, st);
             cudaMemcpyAsync((uint32_t *) M->n_amb.p + r0, b->n_amb.p, nr * 4, cudaMemcpyDeviceToDevice, st);
@@ -298,7 +320,7 @@ static int pipe_run(sg_pipe *p, const char *bases, const uint64_t *off, uint64_t
                 o.hoco_l = (uint32_t *) in->staged(0, (nr + 1) * 4); o.n_scm = (uint32_t *) in->staged(1, (nr + 1) * 4);
                 o.hoco_s_off = (uint64_t *) in->staged(2, (nr + 2) * 8); o.ho_rl_off = (uint64_t *) in->staged(3, (nr + 2) * 8);
                 o.scm_off = (uint64_t *) in->staged(4, (nr + 2) * 8);
-                o.hoco_s_buf = (uint8_t *) in->staged(5, z.hoco_s_bytes + 64); o.ho_rl_buf = (uint8_t *) in->staged(6, z.ho_rl_bytes + 64);
+                o.hoco_s_buf = (uint8_t *) in->staged(5, z.hoco_s_bytes + 64); o.ho_rl_buf = (uint8_t *) in->staged(6, keep_rl ? 64 : z.ho_rl_bytes + 64);
                 o.m_pos = (uint32_t *) in->staged(7, (N + 1) * 4); o.s_mer = (uint64_t *) in->staged(8, (N + 1) * 8); o.k_mer = (uint64_t *) in->staged(9, (N + 1) * 8);
                 o.amb_sid = (uint32_t *) in->staged(10, (z.n_ambiguous + 1) * 4); o.amb_pos = (uint32_t *) in->staged(11, (z.n_ambiguous + 1) * 4);
                 o.lrl_sid = (uint32_t *) in->staged(12, (z.n_long_runs + 1) * 4); o.lrl_idx = (uint32_t *) in->staged(13, (z.n_long_runs + 1) * 4);
@@ -306,6 +328,7 @@ static int pipe_run(sg_pipe *p, const char *bases, const uint64_t *off, uint64_t
                 bool ok = true;
                 for (int j = 0; j < 15; ++j) ok = ok && in->stage[j];
                 double t3 = now(); tp[2] += t3 - t2;
+                if (keep_rl) o.ho_rl_buf = nullptr;        // stays on the device
                 rc = ok ? sg_extract_download(b, &o) : SG_E_NOMEM;
                 double t4 = now(); tp[3] += t4 - t3;
                 if (!rc) rc = cb(cb_user, r0, nr, &o, &z);
@@ -372,6 +395,8 @@ static int pipe_run(sg_pipe *p, const char *bases, const uint64_t *off, uint64_t
     M->n_syncmers = tot.scm; M->n_amb_total = tot.amb; M->n_lrl_total = tot.lrl; M->hoco_bases = tot.hoco;
     M->extracted = true; M->counted = M->sorted = M->adopted = M->sizes_known = M->have_kid_local = false;
     M->pipe_fed = true;
+    M->rl_resident = keep_rl;
+    M->lrl_sorted = false;
     M->keys_are_ids = false;
     sizes->n_reads = n_reads; sizes->n_syncmers = tot.scm; sizes->hoco_bases = tot.hoco;
     sizes->hoco_s_bytes = tot.hs; sizes->ho_rl_bytes = tot.rl; sizes->n_ambiguous = tot.amb; sizes->n_long_runs = tot.lrl;

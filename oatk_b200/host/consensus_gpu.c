@@ -202,8 +202,16 @@ __attribute__((optimize("O3"))) static void lane_add_rev(uint16_t *restrict lane
     for (uint64_t j = 0; j < l; ++j) lane[j] = (uint16_t) (lane[j] + rl[l - 1 - j]);
 }
 
+/* Run-length sums fetched from the device for a set of syncmers (read databases whose ho_rl stayed there): row i holds, for
+ * syncmer ids[i] in its own orientation, sum over the uncorrected copies of (run length - 1) per hoco position. */
+typedef struct {
+    const int64_t *row_of;        /* per syncmer id: row, or -1 */
+    const uint64_t *sums;         /* rows x w */
+    const uint32_t *copies;       /* per row: uncorrected copies */
+} rl_table_t;
+
 /* out == NULL: only the length is wanted (arc overlaps) */
-static int64_t syncmer_text(const sr_db_t *db, const syncmer_t *m, int rev, int64_t from, txt_t *out, int hoco_only)
+static int64_t syncmer_text(const sr_db_t *db, const syncmer_t *m, int rev, int64_t from, txt_t *out, int hoco_only, const rl_table_t *rlt, uint64_t id)
 {
     const int w = db->k;
     assert(from < w);
@@ -242,8 +250,17 @@ static int64_t syncmer_text(const sr_db_t *db, const syncmer_t *m, int rev, int6
      * with plain loops the compiler vectorises, folded into the 64-bit sums every 256 copies (255 * 256 < 2^16); the
      * rare runs of 255 or more, kept in a side list per read, are patched in on top */
     uint64_t *tot = (uint64_t *) calloc(l, sizeof(uint64_t));
-    uint16_t *lane = (uint16_t *) calloc(l, sizeof(uint16_t));
     uint32_t copies = 0, pending = 0;
+    if (rlt) {
+        /* the device summed the copies in the syncmer's forward frame F[0..w): position j of this view is F[from + j]
+         * on the forward strand and F[w - 1 - from - j] on the reverse one */
+        const int64_t row = rlt->row_of[id];
+        assert(row >= 0);
+        const uint64_t *F = rlt->sums + (uint64_t) row * (uint64_t) w;
+        copies = rlt->copies[row];
+        for (uint64_t j = 0; j < l; ++j) tot[j] = rev ? F[(uint64_t) w - 1 - (uint64_t) from - j] : F[(uint64_t) from + j];
+    } else {
+    uint16_t *lane = (uint16_t *) calloc(l, sizeof(uint16_t));
     /* the copies sit in as many different reads: their run lengths are fetched a batch ahead of the additions */
     enum { AHEAD = 16 };
     struct { const sr_t *t; const uint8_t *rl8; uint64_t q; int rr; } nxt[AHEAD];
@@ -280,6 +297,7 @@ static int64_t syncmer_text(const sr_db_t *db, const syncmer_t *m, int rev, int6
     }
     for (uint64_t j = 0; j < l; ++j) tot[j] += lane[j];
     free(lane);
+    }
     if (!out) {
         for (uint64_t j = 0; j < l; ++j) written += lround((double) tot[j] / copies);
         free(tot);
@@ -301,7 +319,7 @@ static int64_t syncmer_text(const sr_db_t *db, const syncmer_t *m, int rev, int6
 }
 
 /* ---------------------------------------------------------------- bases of a chain of syncmers */
-static int64_t chain_text(const sr_db_t *db, const uint64_t *v, uint64_t n, const syncmer_t *scm, txt_t *out, int hoco_only, ovl_tab_t *tab)
+static int64_t chain_text(const sr_db_t *db, const uint64_t *v, uint64_t n, const syncmer_t *scm, txt_t *out, int hoco_only, ovl_tab_t *tab, const rl_table_t *rlt)
 {
     if (n == 0) return 0;
     const int w = db->k;
@@ -313,7 +331,7 @@ static int64_t chain_text(const sr_db_t *db, const uint64_t *v, uint64_t n, cons
     int64_t end = 0, len = 0;
     for (uint64_t i = 0; i < n; ++i) {
         while (i + 1 < n && pos[i + 1] <= end) ++i;     /* the next one still starts inside what is written: skip ahead */
-        len += syncmer_text(db, &scm[v[i] >> 1], (int) (v[i] & 1), end - pos[i], out, hoco_only);
+        len += syncmer_text(db, &scm[v[i] >> 1], (int) (v[i] & 1), end - pos[i], out, hoco_only, rlt, v[i] >> 1);
         end = pos[i] + w;
     }
     free(pos);
@@ -388,6 +406,7 @@ typedef struct {
     int64_t *ovl;                                       /* per arc */
     uint64_t next;                                      /* shared work counter */
     int phase;
+    const rl_table_t *rlt;                              /* run-length sums from the device, or NULL: the reads carry ho_rl */
 } cons_job_t;
 
 static int64_t arc_overlap(cons_job_t *J, const asmg_arc_t *a, txt_t *t, ovl_tab_t *tab)
@@ -400,7 +419,7 @@ static int64_t arc_overlap(cons_job_t *J, const asmg_arc_t *a, txt_t *t, ovl_tab
     if (a->ln > 0) {                                    /* the two unitigs share ln syncmers: their length in bases */
         const asmg_vtx_t *u = &G->vtx[a->v >> 1];
         t->l = 0;
-        l = chain_text(db, (a->v & 1) ? u->a : &u->a[u->n - a->ln], a->ln, scm, t, J->hoco, tab);
+        l = chain_text(db, (a->v & 1) ? u->a : &u->a[u->n - a->ln], a->ln, scm, t, J->hoco, tab, J->rlt);
     } else {                                            /* they abut: overlap of the two end syncmers */
         const asmg_vtx_t *u = &G->vtx[a->v >> 1];
         uint64_t z = a->v & 1;
@@ -409,7 +428,7 @@ static int64_t arc_overlap(cons_job_t *J, const asmg_arc_t *a, txt_t *t, ovl_tab
         z = a->w & 1;
         const uint64_t y = u->a[(u->n - 1) * z] ^ z;
         l = neighbour_offset(db, &scm[x >> 1], x & 1, &scm[y >> 1], y & 1, tab, 0);
-        if (l < w) l = syncmer_text(db, &scm[x >> 1], (int) (x & 1), l, 0, J->hoco);    /* length only */
+        if (l < w) l = syncmer_text(db, &scm[x >> 1], (int) (x & 1), l, 0, J->hoco, J->rlt, x >> 1);    /* length only */
         else l = 0;
     }
     return l;
@@ -434,7 +453,7 @@ static void *cons_worker(void *arg)
                 asmg_vtx_t *u = &G->vtx[i];
                 if (u->del) continue;
                 t.l = 0;
-                J->len[i] = chain_text(J->db, u->a, u->n, J->scg->scm_db->a, &t, J->hoco, &tab);
+                J->len[i] = chain_text(J->db, u->a, u->n, J->scg->scm_db->a, &t, J->hoco, &tab, J->rlt);
                 J->cov[i] = u->cov ? u->cov : unitig_coverage(J->scg, u);
                 J->text[i] = (char *) malloc((size_t) J->len[i] + 1);
                 memcpy(J->text[i], t.s, (size_t) J->len[i]);
@@ -479,6 +498,47 @@ void scg_consensus(sr_db_t *sr_db, scg_t *scg, int hoco_seq, int save_seq, FILE 
     J.cov = (double *) calloc(G->n_vtx ? G->n_vtx : 1, sizeof(double));
     J.ovl = (int64_t *) calloc(G->n_arc ? G->n_arc : 1, sizeof(int64_t));
 
+    /* run lengths that stayed on the device: one request for every syncmer on a live unitig, answered by sg_runlen_sums */
+    rl_table_t rlt;
+    int64_t *row_of = 0;
+    uint64_t *sums = 0;
+    uint32_t *copies = 0;
+    if (!hoco_seq && oatk_gpu_run_lengths_on_device(sr_db)) {
+        const syncmer_t *scm = scg->scm_db->a;
+        uint64_t n_req = 0, n_occ = 0, j, *ids, *occ_off, *occ;
+        row_of = (int64_t *) malloc(sizeof(int64_t) * (scg->scm_db->n ? scg->scm_db->n : 1));
+        for (j = 0; j < scg->scm_db->n; ++j) row_of[j] = -1;
+        for (i = 0; i < G->n_vtx; ++i) {
+            const asmg_vtx_t *u = &G->vtx[i];
+            if (u->del) continue;
+            for (j = 0; j < u->n; ++j) if (row_of[u->a[j] >> 1] < 0) { row_of[u->a[j] >> 1] = (int64_t) n_req++; n_occ += scm[u->a[j] >> 1].cov; }
+        }
+        ids = (uint64_t *) malloc(sizeof(uint64_t) * (n_req ? n_req : 1));
+        for (j = 0; j < scg->scm_db->n; ++j) if (row_of[j] >= 0) ids[row_of[j]] = j;
+        occ_off = (uint64_t *) malloc(sizeof(uint64_t) * (n_req + 1));
+        occ = (uint64_t *) malloc(sizeof(uint64_t) * (n_occ ? n_occ : 1));
+        copies = (uint32_t *) malloc(sizeof(uint32_t) * (n_req ? n_req : 1));
+        n_occ = 0;
+        for (j = 0; j < n_req; ++j) {
+            const syncmer_t *m = &scm[ids[j]];
+            occ_off[j] = n_occ;
+            for (uint32_t c = 0; c < m->cov; ++c) {
+                if (occ_is_corrected(sr_db, m->m_pos[c])) continue;
+                occ[n_occ++] = (m->m_pos[c] >> 32) << 32 | sr_db->a[m->m_pos[c] >> 32].m_pos[m->m_pos[c] >> 1 & MAX_RD_SCM];
+            }
+            copies[j] = (uint32_t) (n_occ - occ_off[j]);
+        }
+        occ_off[n_req] = n_occ;
+        sums = (uint64_t *) malloc(sizeof(uint64_t) * (n_req ? n_req : 1) * (size_t) sr_db->k);
+        if (oatk_gpu_runlen_sums(sr_db, n_req, occ_off, occ, sums) != 0) {
+            fprintf(stderr, "[E::%s] the run lengths could not be read from the device\n", __func__);
+            exit(EXIT_FAILURE);
+        }
+        free(ids); free(occ_off); free(occ);
+        rlt.row_of = row_of; rlt.sums = sums; rlt.copies = copies;
+        J.rlt = &rlt;
+    }
+
     cons_run(&J, 0, G->n_vtx);
     if (fo) fprintf(fo, "H\tVN:Z:1.0\n");
     for (i = 0; i < G->n_vtx; ++i) {
@@ -507,4 +567,5 @@ void scg_consensus(sr_db_t *sr_db, scg_t *scg, int hoco_seq, int save_seq, FILE 
         }
     }
     free(J.text); free(J.len); free(J.cov); free(J.ovl);
+    free(row_of); free(sums); free(copies);
 }

@@ -144,7 +144,16 @@ int syncasm(char **file_in, int n_file, size_t m_data, int k, int s, int bubble_
 
     sr_db = (sr_db_t *) malloc(sizeof(sr_db_t));
     sr_db_init(sr_db, k, s);
-    if ((rc = sr_read_files(sr_db, (const char *const *) file_in, n_file, m_data)) != 0) {
+    {
+        /* A caller that takes no structures back (meta == NULL: the syncasm command) never looks at sr_t.ho_rl, whose one
+         * consumer, the run-length consensus, is served on the device: the array -- as large as the input -- is not
+         * downloaded. OATK_FULL_READS=1 keeps the full records; a caller with meta always gets them. */
+        const char *full = getenv("OATK_FULL_READS");
+        const int was = oatk_gpu_keep_run_lengths(!meta && !(full && atoi(full) > 0));
+        rc = sr_read_files(sr_db, (const char *const *) file_in, n_file, m_data);
+        oatk_gpu_keep_run_lengths(was);
+    }
+    if (rc != 0) {
         fprintf(stderr, "[E::%s] failed to read the input files (%d)\n", __func__, rc);
         ret = 1;
         goto done;

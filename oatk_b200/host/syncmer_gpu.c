@@ -33,6 +33,12 @@ static pthread_mutex_t g_lock = PTHREAD_MUTEX_INITIALIZER;
 
 int oatk_gpu_set_device(int device) { g_device = device; return 0; }
 
+/* 1: sr_read_mem / sr_read_files / sr_read leave the run lengths (sr_t.ho_rl, one byte per hoco base: as large as the input)
+ * on the device; sr_t.ho_rl is NULL and scg_consensus gets its run-length sums from there (oatk_gpu_runlen_sums). syncasm()
+ * switches it on; callers of the API get the full read records unless they ask. */
+static int g_keep_rl;
+int oatk_gpu_keep_run_lengths(int on) { const int was = g_keep_rl; g_keep_rl = on != 0; return was; }
+
 static sg_batch *batch_of(sr_db_t *db, int create)
 {
     reg_t *r;
@@ -123,7 +129,7 @@ static int fill_chunk(void *user, uint64_t r0, uint64_t nr, const sg_extract_out
         else { snprintf(nm, sizeof(nm), "r%lu", (unsigned long) (r0 + i)); r->sname = strdup(nm); }
         r->hoco_l = c->hoco_l[i];
         r->hoco_s = (uint8_t *) dup_block(c->hoco_s_buf + c->hoco_s_off[i], (c->hoco_l[i] + 3) / 4);
-        r->ho_rl = (uint8_t *) dup_block(c->ho_rl_buf + c->ho_rl_off[i], c->hoco_l[i]);
+        r->ho_rl = c->ho_rl_buf ? (uint8_t *) dup_block(c->ho_rl_buf + c->ho_rl_off[i], c->hoco_l[i]) : 0;   /* NULL: resident on the device */
         while (ia < z->n_ambiguous && c->amb_sid[ia] == i) ++ia;
         r->n_nucl = (uint32_t *) dup_block(c->amb_pos + a0, 4 * (ia - a0));
         while (il < z->n_long_runs && c->lrl_sid[il] == i) ++il;
@@ -167,6 +173,7 @@ int sr_read_mem(sr_db_t *sr_db, const char *bases, const uint64_t *off, char **n
     sr_db->a = (sr_t *) calloc(n_reads ? n_reads : 1, sizeof(sr_t));
     sr_db->n = sr_db->m = n_reads;
     f.db = sr_db; f.names = names;
+    sg_pipe_keep_run_lengths(pipe, g_keep_rl);
     rc = sg_pipe_run_host_cb(pipe, bases, off, n_reads, k, s, SR_READ_CHUNK, fill_chunk, &f, &z);
     if (rc != SG_OK) fprintf(stderr, "[E::%s] %s: %s\n", __func__, sg_strerror(rc), sg_pipe_last_error(pipe));
     return rc;
@@ -562,6 +569,27 @@ syncmer_db_t *collect_syncmer_from_reads(sr_db_t *sr_db)
     }
     free(h); free(s); free(cov); free(off); free(occ); free(kid);
     return db;
+}
+
+/* 1 when the run lengths of this read database live on the device only (see oatk_gpu_keep_run_lengths) */
+int oatk_gpu_run_lengths_on_device(sr_db_t *sr_db)
+{
+    sg_batch *b = batch_of(sr_db, 0);
+    uint64_t i;
+    if (!b || !sg_runlen_resident(b)) return 0;
+    for (i = 0; i < sr_db->n; ++i) if (sr_db->a[i].hoco_l) return sr_db->a[i].ho_rl == 0;
+    return 0;
+}
+
+/* sums of (run length - 1) per hoco position for n_req syncmers over the listed occurrences (sg_runlen_sums) */
+int oatk_gpu_runlen_sums(sr_db_t *sr_db, uint64_t n_req, const uint64_t *occ_off, const uint64_t *occ, uint64_t *sums)
+{
+    sg_batch *b = batch_of(sr_db, 0);
+    int rc;
+    if (!b) return SG_E_STATE;
+    rc = sg_runlen_sums(b, n_req, occ_off, occ, sums);
+    if (rc != SG_OK) fprintf(stderr, "[E::%s] %s: %s\n", __func__, sg_strerror(rc), sg_last_error(ctx_of(sr_db)));
+    return rc;
 }
 
 int syncmer_graph_arcs(sr_db_t *sr_db, syncmer_db_t *scm_db, uint32_t min_k_cov, double min_a_cov_f, uint64_t **arcs4, uint64_t *n_arcs)

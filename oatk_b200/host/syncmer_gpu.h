@@ -126,6 +126,10 @@ int oatk_gpu_update_lists(sr_db_t *sr_db, syncmer_db_t *scm_db);
 void oatk_parallel_for(uint64_t n, void (*fn)(uint64_t lo, uint64_t hi, void *arg), void *arg);
 void oatk_tick(const char *what);      /* OATK_TIMING=1: stage times on stderr */
 int oatk_gpu_set_device(int device);
+/* run lengths stay on the device (sr_t.ho_rl == NULL) for the read databases made from now on; returns the previous setting */
+int oatk_gpu_keep_run_lengths(int on);
+int oatk_gpu_run_lengths_on_device(sr_db_t *sr_db);
+int oatk_gpu_runlen_sums(sr_db_t *sr_db, uint64_t n_req, const uint64_t *occ_off, const uint64_t *occ, uint64_t *sums);
 void oatk_gpu_shutdown(void);
 
 #ifdef __cplusplus

@@ -64,7 +64,7 @@ SYMBOLS = [
     "sg_ids_pack", "sg_ids_scatter", "sg_batch_set_exact_verify", "sg_smer_counts_pack", "sg_smer_counts_merge", "sg_batch_set_lists_host",
     "sg_comm_unique_id", "sg_comm_init_rank", "sg_comm_init_all", "sg_comm_destroy", "sg_comm_rank", "sg_comm_world", "sg_comm_bytes_sent",
     "sg_comm_exchange_tuples", "sg_comm_global_stat", "sg_comm_return_ids", "sg_comm_arcs",
-    "sg_pipe_create", "sg_pipe_destroy", "sg_pipe_run_host", "sg_pipe_run_host_cb", "sg_pipe_master", "sg_pipe_ctx", "sg_pipe_last_error", "sg_pipe_launches", "sg_pipe_set_sid_base",
+    "sg_pipe_create", "sg_pipe_destroy", "sg_pipe_run_host", "sg_pipe_run_host_cb", "sg_pipe_master", "sg_pipe_ctx", "sg_pipe_last_error", "sg_pipe_launches", "sg_pipe_set_sid_base", "sg_pipe_keep_run_lengths", "sg_runlen_sums", "sg_runlen_resident",
 ]
 
 
@@ -331,6 +331,17 @@ class Batch:
         r, f = C.c_uint64(0), C.c_int(0)
         _ck(self.ctx.h, _lib().sg_debug_sort_info(self.h, C.byref(r), C.byref(f)), "sg_debug_sort_info")
         return int(r.value), bool(f.value)
+
+    def runlen_sums(self, occ_off, occ, k):
+        """occ_off: n+1 offsets, occ: read << 32 | start << 1 | strand; returns (n, k) uint64 sums of run length - 1"""
+        occ_off = np.ascontiguousarray(occ_off, dtype=np.uint64)
+        occ = np.ascontiguousarray(occ, dtype=np.uint64)
+        n = len(occ_off) - 1
+        out = np.zeros((n, k), np.uint64)
+        L = _lib()
+        L.sg_runlen_sums.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
+        _ck(self.ctx.h, L.sg_runlen_sums(self.h, n, occ_off.ctypes.data, occ.ctypes.data if len(occ) else None, out.ctypes.data), "sg_runlen_sums")
+        return out
 
     def debug_scan_info(self):
         r = C.c_uint64(0)
