@@ -218,148 +218,171 @@ uint64_t asmg_remove_weak_crosslink(asmg_t *g, double c_thresh, double m_cov, in
     return cnt;
 }
 
-/* ---------- bubbles ---------- */
+/* ---------- bubbles ----------
+ * What asmg_pop_bubble does (reference graph.c:494-575, 782-882), stated as rules and written from them:
+ *
+ * EXPLORE. From an oriented unitig `src` with two or more ways out, unitigs are taken in dependency order: one becomes
+ * "free" when every live arc into it has been followed, and the most recently freed one is taken next. Following an arc
+ * x -> y offers y a route: its length (bases from the end of src, overlaps removed) and its mass (bases x coverage).
+ * y remembers the SHORTEST length, the LARGEST mass, and as predecessor the x of the most massive offer, the longer
+ * route winning a tie on mass. The exploration ends
+ *   - at a JOIN: the unitig just taken is the only free one and nothing is still held back -- every route from src has
+ *     funnelled into it. src itself qualifies trivially and does not count;
+ *   - at an arc back into src (either strand): a cycle through the source, nothing is resolved;
+ *   - at a dead end. A dead end closer than the radius is a short tip; it is counted unless it is where everything
+ *     ended anyway, and the exploration carries on past it only when tips are not protected;
+ *   - when some remembered length exceeds the radius.
+ * RESOLVE. If a join was found, the predecessor chain join -> src is the path that stays; every other unitig and arc
+ * the exploration touched goes -- unless more than max_del unitigs would go, or (super-bubble protection) what would go
+ * is covered at least half as deeply per base as the flanking unbranched stretches, or as the path that stays.
+ */
 typedef struct {
-    uint64_t from;       /* predecessor on the heaviest path */
-    uint64_t dist;       /* fewest bases from the source's end */
-    uint64_t weight;     /* most bases x coverage from the source */
-    uint64_t waiting;    /* incoming arcs not yet walked */
-    int seen;
-} visit_t;
+    uint64_t pred;       /* where the most massive route comes from */
+    uint64_t shortest;   /* bases, shortest route */
+    uint64_t mass;       /* bases x coverage, most massive route */
+    uint64_t held;       /* live arcs into it not followed yet */
+    int known;
+} route_t;
 
 typedef struct {
-    visit_t *at;
-    vec_t ready, seen, arcs;
-    uint64_t n_short_tip, n_sink, dist, sink;
-    int self_cycle;
-} walk_t;
+    route_t *of;                   /* per oriented unitig */
+    vec_t free_list, touched, arcs_used;
+    uint64_t n_short_tip, n_join, join, join_dist;
+    int cycle_through_source;
+} region_t;
 
-#define THRU_SHORT_TIP 1
-#define THRU_BUBBLE 2
+static void route_clear(route_t *r) { r->pred = UINT64_MAX; r->shortest = r->mass = r->held = 0; r->known = 0; }
 
-/* topological walk from v0 while everything seen stays within max_dist; a vertex is expanded once all its incoming arcs
- * have been walked; when exactly one vertex is ready and none is waiting, everything has funnelled into it: a sink */
-static uint64_t funnel_walk(const asmg_t *g, uint64_t v0, uint64_t max_dist, int thru, walk_t *b)
+/* y is reached from x over a route of `len` bases and `mass`; returns 1 when that was the last arc y was waiting for */
+static int offer_route(const asmg_t *g, region_t *R, uint64_t x, uint64_t y, uint64_t len, uint64_t mass, uint64_t *n_held)
 {
-    uint64_t pending = 0, far = 0;
-    visit_t *t;
-    if (g->vtx[v0 >> 1].del) return 0;
-    b->ready.n = b->seen.n = b->arcs.n = 0;
-    b->n_short_tip = b->n_sink = b->dist = 0;
-    b->self_cycle = 0;
-    b->sink = UINT64_MAX;
-    t = &b->at[v0];
-    t->dist = t->weight = t->waiting = 0; t->seen = 0; t->from = UINT64_MAX;
-    vpush(&b->ready, v0);
-    while (b->ready.n > 0 && far <= max_dist) {
-        const uint64_t v = b->ready.a[--b->ready.n], n = g->idx_n[v], d = b->at[v].dist, c = b->at[v].weight;
-        const asmg_arc_t *a = arcs_of(g, v);
-        uint64_t i;
-        if (b->ready.n == 0 && pending == 0) {
-            b->dist = d; b->sink = v;
-            if (v != v0) { ++b->n_sink; if (!(thru & THRU_BUBBLE)) break; }
-        }
-        if (live_out(g, v) == 0) {
-            if (d + g->vtx[v >> 1].len < max_dist) {
-                if (b->ready.n || pending) ++b->n_short_tip;              /* not counted when it ends a bubble chain */
-                if (thru & THRU_SHORT_TIP) continue;
-            }
-            break;
-        }
-        for (i = 0; i < n; ++i) {
-            uint64_t w, step, gain;
-            if (a[i].del) continue;
-            w = a[i].w;
-            step = g->vtx[v >> 1].len - a[i].ls;
-            gain = g->vtx[v >> 1].cov * step;
-            t = &b->at[w];
-            if (w >> 1 == v0 >> 1) { b->self_cycle |= w == v0 ? 1 : 2; break; }
-            vpush(&b->arcs, g->idx_p[v] + i);
-            if (!t->seen) {
-                vpush(&b->seen, w);
-                t->from = v; t->seen = 1; t->dist = d + step; t->weight = c + gain;
-                t->waiting = live_out(g, w ^ 1);
-                ++pending;
-            } else {
-                if (c + gain > t->weight || (c + gain == t->weight && d + step > t->dist)) t->from = v;
-                if (c + gain > t->weight) t->weight = c + gain;
-                if (d + step < t->dist) t->dist = d + step;
-            }
-            if (t->dist > far) far = t->dist;
-            assert(t->waiting > 0 && pending > 0);
-            if (--t->waiting == 0) { vpush(&b->ready, w); --pending; }
-        }
-        if (i < n) break;
+    route_t *r = &R->of[y];
+    if (!r->known) {
+        vpush(&R->touched, y);
+        r->known = 1; r->pred = x; r->shortest = len; r->mass = mass;
+        r->held = live_out(g, y ^ 1);
+        ++*n_held;
+    } else {
+        const int heavier = mass > r->mass, as_heavy_but_longer = mass == r->mass && len > r->shortest;
+        if (heavier || as_heavy_but_longer) r->pred = x;
+        if (heavier) r->mass = mass;
+        if (len < r->shortest) r->shortest = len;
     }
-    return b->n_sink;
+    assert(r->held > 0 && *n_held > 0);
+    if (--r->held) return 0;
+    --*n_held;
+    return 1;
 }
 
-/* keep the heaviest source->sink path of the walked region, delete the rest (unless it looks like real sequence) */
-static int resolve(asmg_t *g, uint64_t v0, uint64_t max_del, int protect_super_bubble, walk_t *b)
+static uint64_t explore_region(const asmg_t *g, uint64_t src, uint64_t radius, int pass_short_tips, region_t *R)
 {
-    uint64_t i, v, w;
-    assert(b->ready.n == 0);
-    if (max_del > 0) {
-        uint64_t kept = 0;
-        v = b->sink;
-        do { ++kept; v = b->at[v].from; } while (v != v0);
-        if (b->seen.n > kept + max_del) return 0;
-    }
-    if (protect_super_bubble) {
-        uint64_t b_kept = 0, c_kept = 0, b_tot = 0, c_tot = 0, left, right, left_wt, right_wt;
-        vec_t p = {0, 0, 0};
-        v = b->sink;
-        do { b_kept += g->vtx[v >> 1].len; c_kept += g->vtx[v >> 1].len * g->vtx[v >> 1].cov; v = b->at[v].from; } while (v != v0);
-        for (i = 0; i < b->seen.n; ++i) {
-            const asmg_vtx_t *x = &g->vtx[b->seen.a[i] >> 1];
-            b_tot += x->len; c_tot += x->len * x->cov;
+    uint64_t n_held = 0, reach = 0;
+    int stop = 0;
+    R->free_list.n = R->touched.n = R->arcs_used.n = 0;
+    R->n_short_tip = R->n_join = R->join_dist = 0;
+    R->cycle_through_source = 0;
+    R->join = UINT64_MAX;
+    if (g->vtx[src >> 1].del) return 0;
+    route_clear(&R->of[src]);
+    vpush(&R->free_list, src);
+    while (!stop && R->free_list.n > 0 && reach <= radius) {
+        const uint64_t x = R->free_list.a[--R->free_list.n];
+        const route_t here = R->of[x];
+        const int funnelled = R->free_list.n == 0 && n_held == 0;
+        if (funnelled) {
+            R->join = x; R->join_dist = here.shortest;
+            if (x != src) { ++R->n_join; break; }         /* the first join ends the exploration (bubble chains are not followed) */
         }
-        chain_from(g, v0 ^ 1, (int32_t) (g->n_vtx * 2 + 1), &left, &p, 0);
-        left_wt = weighted_len(g, p.a, p.n);
-        chain_from(g, b->sink, (int32_t) (g->n_vtx * 2 + 1), &right, &p, 0);
-        right_wt = weighted_len(g, p.a, p.n);
-        free(p.a);
-        /* what would go is covered more than half as deeply as the flanks, or as the path that stays: leave it */
-        if ((c_tot - c_kept) * (left + right) * 2 > (left_wt + right_wt) * (b_tot - b_kept)) return 0;
-        if ((c_tot - c_kept) * b_kept * 2 > c_kept * (b_tot - b_kept)) return 0;
+        if (live_out(g, x) == 0) {                         /* dead end */
+            const int is_short = here.shortest + g->vtx[x >> 1].len < radius;
+            if (is_short && !funnelled) ++R->n_short_tip;
+            if (is_short && pass_short_tips) continue;
+            break;
+        }
+        const asmg_arc_t *out = arcs_of(g, x);
+        const uint64_t n_out = g->idx_n[x];
+        for (uint64_t i = 0; i < n_out; ++i) {
+            if (out[i].del) continue;
+            const uint64_t y = out[i].w;
+            if (y >> 1 == src >> 1) { R->cycle_through_source |= y == src ? 1 : 2; stop = 1; break; }
+            const uint64_t step = g->vtx[x >> 1].len - out[i].ls;
+            vpush(&R->arcs_used, g->idx_p[x] + i);
+            if (offer_route(g, R, x, y, here.shortest + step, here.mass + g->vtx[x >> 1].cov * step, &n_held)) vpush(&R->free_list, y);
+            if (R->of[y].shortest > reach) reach = R->of[y].shortest;
+        }
     }
-    for (i = 0; i < b->seen.n; ++i) g->vtx[b->seen.a[i] >> 1].del = 1;
-    for (i = 0; i < b->arcs.n; ++i) {
-        asmg_arc_t *a = &g->arc[b->arcs.a[i]];
-        a->del = 1;
-        flag_arcs(g, a->w ^ 1, a->v ^ 1, 1);
+    return R->n_join;
+}
+
+/* bases and bases x coverage of a set of oriented unitigs */
+static void bases_and_mass(const asmg_t *g, const uint64_t *v, uint64_t n, uint64_t *bases, uint64_t *mass)
+{
+    *bases = *mass = 0;
+    for (uint64_t i = 0; i < n; ++i) { const asmg_vtx_t *x = &g->vtx[v[i] >> 1]; *bases += x->len; *mass += x->len * x->cov; }
+}
+
+/* does the part of the region that would be deleted look like real sequence? (graph.c:800-815) */
+static int region_is_well_covered(const asmg_t *g, uint64_t src, const region_t *R, const vec_t *kept)
+{
+    uint64_t b_kept, m_kept, b_all, m_all, left_b, right_b;
+    vec_t flank = {0, 0, 0};
+    bases_and_mass(g, kept->a, kept->n, &b_kept, &m_kept);
+    bases_and_mass(g, R->touched.a, R->touched.n, &b_all, &m_all);
+    chain_from(g, src ^ 1, (int32_t) (g->n_vtx * 2 + 1), &left_b, &flank, 0);
+    const uint64_t left_m = weighted_len(g, flank.a, flank.n);
+    chain_from(g, R->join, (int32_t) (g->n_vtx * 2 + 1), &right_b, &flank, 0);
+    const uint64_t right_m = weighted_len(g, flank.a, flank.n);
+    free(flank.a);
+    const uint64_t b_gone = b_all - b_kept, m_gone = m_all - m_kept;
+    /* coverage per base of what goes, against half that of the flanks and half that of what stays */
+    if (m_gone * (left_b + right_b) * 2 > (left_m + right_m) * b_gone) return 1;
+    if (m_gone * b_kept * 2 > m_kept * b_gone) return 1;
+    return 0;
+}
+
+static int keep_heaviest_path(asmg_t *g, uint64_t src, uint64_t max_del, int protect_super_bubble, region_t *R)
+{
+    vec_t kept = {0, 0, 0};                                /* join, ..., first unitig after src */
+    uint64_t i, x;
+    int done = 0;
+    assert(R->free_list.n == 0);
+    for (x = R->join; x != src; x = R->of[x].pred) vpush(&kept, x);
+    if (!(max_del > 0 && R->touched.n > kept.n + max_del) && !(protect_super_bubble && region_is_well_covered(g, src, R, &kept))) {
+        for (i = 0; i < R->touched.n; ++i) g->vtx[R->touched.a[i] >> 1].del = 1;
+        for (i = 0; i < R->arcs_used.n; ++i) {
+            asmg_arc_t *e = &g->arc[R->arcs_used.a[i]];
+            e->del = 1;
+            flag_arcs(g, e->w ^ 1, e->v ^ 1, 1);
+        }
+        for (i = 0; i < kept.n; ++i) {                     /* bring the path back, arc by arc and on both strands */
+            const uint64_t y = kept.a[i], px = R->of[y].pred;
+            g->vtx[y >> 1].del = 0;
+            flag_arcs(g, px, y, 0);
+            flag_arcs(g, y ^ 1, px ^ 1, 0);
+        }
+        done = 1;
     }
-    v = b->sink;
-    do {
-        w = b->at[v].from;
-        g->vtx[v >> 1].del = 0;
-        flag_arcs(g, w, v, 0);
-        flag_arcs(g, v ^ 1, w ^ 1, 0);
-        v = w;
-    } while (v != v0);
-    return 1;
+    free(kept.a);
+    return done;
 }
 
 uint64_t asmg_pop_bubble(asmg_t *g, uint64_t radius, uint64_t max_del, int protect_tip, int protect_super_bubble, int do_cleanup, int VERBOSE)
 {
     const uint64_t n_or = g->n_vtx << 1;
-    walk_t b;
+    region_t R;
     uint64_t v, i, n_pop = 0;
-    memset(&b, 0, sizeof(b));
-    b.at = (visit_t *) calloc(n_or ? n_or : 1, sizeof(visit_t));
-    for (v = 0; v < n_or; ++v) b.at[v].from = UINT64_MAX;
+    memset(&R, 0, sizeof(R));
+    R.of = (route_t *) calloc(n_or ? n_or : 1, sizeof(route_t));
+    for (v = 0; v < n_or; ++v) R.of[v].pred = UINT64_MAX;
     for (v = 0; v < n_or; ++v) {
         uint64_t ret = 0;
         if (g->vtx[v >> 1].del || live_out(g, v) < 2) continue;
-        funnel_walk(g, v, g->vtx[v >> 1].len + radius, protect_tip ? 0 : THRU_SHORT_TIP, &b);
-        if (b.n_sink && (ret = (uint64_t) resolve(g, v, max_del, protect_super_bubble, &b))) ret |= b.n_short_tip << 32;
-        for (i = 0; i < b.seen.n; ++i) {
-            visit_t *t = &b.at[b.seen.a[i]];
-            t->dist = t->weight = t->waiting = 0; t->seen = 0; t->from = UINT64_MAX;
-        }
+        explore_region(g, v, g->vtx[v >> 1].len + radius, !protect_tip, &R);
+        if (R.n_join && keep_heaviest_path(g, v, max_del, protect_super_bubble, &R)) ret = 1 | R.n_short_tip << 32;
+        for (i = 0; i < R.touched.n; ++i) route_clear(&R.of[R.touched.a[i]]);
         n_pop += ret;
     }
-    free(b.at); free(b.ready.a); free(b.seen.a); free(b.arcs.a);
+    free(R.of); free(R.free_list.a); free(R.touched.a); free(R.arcs_used.a);
     if (do_cleanup && n_pop > 0) asmg_finalize(g, 1);
     if (VERBOSE)
         fprintf(stderr, "[M::%s] popped %u bubbles and trimmed %u short tips\n", __func__, (uint32_t) n_pop, (uint32_t) (n_pop >> 32));

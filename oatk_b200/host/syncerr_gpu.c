@@ -48,87 +48,117 @@
 #define NO_SINK UINT64_MAX
 #define ID_MASK 0xFFFFFFFFFFFFFFFEULL
 
-/* ---------------------------------------------------------------- wavefront edit distance, resumable */
-typedef struct { int32_t d, k; } wdiag_t;   /* diagonal = query pos - target pos; k = last target index reached on it */
+/* ---------------------------------------------------------------- wavefront edit distance, resumable
+ * Landau-Vishkin / WFA in extension mode, as the graph search uses it (what the reference obtains from levdist.c's
+ * wf_ed_core with is_ext = 1 and no traceback; its known answer, ED = 8 on the strings of levdist.c:445-446, and 3 600
+ * random resumed comparisons against it are in tests/test_syncerr_cpu.py). Written from the recurrence:
+ *
+ *   far_e[d] = the last target index matched on diagonal d (query index - target index) with e edits
+ *   far_{e+1}[d] = max(far_e[d-1], far_e[d] + 1, far_e[d+1] + 1), then slid along the matches of diagonal d
+ *
+ * The live diagonals of a wave are always contiguous, so the state is (lowest diagonal, count, far[]) plus the score;
+ * it survives between calls, and a call with a longer query simply carries on -- which is how the search extends a
+ * candidate by one vertex without re-aligning its prefix. A run ends when a diagonal reaches the last base of the
+ * target or of the query (t_end / q_end = lengths aligned), or, with a band, when the score exceeds it.
+ * The band rule is the reference's (levdist.c:99-113): once 2 bw + 1 diagonals are live, those outside
+ * [max(-bw, -tl), max(bw, ql)] are dropped -- the upper bound WIDENS to the query length rather than clipping to bw;
+ * before that only diagonals that left the matrix go. Observable through the scores, hence kept.
+ */
 typedef struct {
     const char *ts, *qs;
     int32_t tl, ql, bw;
     int32_t score, t_end, q_end;            /* t_end/q_end: aligned lengths when an end was reached, else 0 */
-    wdiag_t *a;
-    size_t n, m;
+    int32_t d_lo;                           /* lowest live diagonal */
+    int32_t *far, *nxt;                     /* far[j]: diagonal d_lo + j; nxt: scratch for the next wave */
+    size_t n, m;                            /* live diagonals, capacity of far / nxt */
 } wave_t;
 
-static inline int32_t wave_slide(const wave_t *w, const wdiag_t *p)
+#define WAVE_NONE (INT32_MIN / 2)
+
+static void wave_reserve(wave_t *w, size_t need)
 {
-    int32_t k = p->k;
-    const int32_t last = (w->ql - p->d < w->tl ? w->ql - p->d : w->tl) - 1;
-    const char *t = w->ts + 1, *q = w->qs + p->d + 1;
-    while (k + 8 <= last) {                             /* eight bases per comparison while both strings have them */
-        uint64_t x, y;
-        memcpy(&x, t + k, 8); memcpy(&y, q + k, 8);
-        if (x != y) return k + (__builtin_ctzll(x ^ y) >> 3);
-        k += 8;
-    }
-    while (k < last && t[k] == q[k]) ++k;
-    return k;
+    if (w->m >= need) return;
+    w->m = need + need / 2 + 16;
+    w->far = (int32_t *) realloc(w->far, w->m * sizeof(int32_t));
+    w->nxt = (int32_t *) realloc(w->nxt, w->m * sizeof(int32_t));
 }
 
-/* one more edit: slide every diagonal, stop if one reaches the end of target or query, else open the next wave.
- * Returns the new number of diagonals, or -1 when an end was reached (t_end/q_end then hold the last indices). */
-static int wave_step(wave_t *w, int32_t n, int32_t *t_end, int32_t *q_end)
+static void wave_begin(wave_t *w)           /* zero edits, nothing matched yet */
 {
-    wdiag_t *a = w->a, *b = w->a + n + 2;
-    const int32_t tl = w->tl, ql = w->ql, bw = w->bw;
-    int32_t j, st = 0, en = n + 2;
-    *t_end = *q_end = -1;
-    for (j = 0; j < n; ++j) {
-        wdiag_t *p = &a[j];
-        int32_t k = p->k;
-        if (k >= tl || k + p->d >= ql) continue;
-        k = wave_slide(w, p);
-        if (k + p->d == ql - 1 || k == tl - 1) { *t_end = k; *q_end = k + p->d; return -1; }
-        p->k = k;
+    wave_reserve(w, 8);
+    w->score = 0; w->t_end = w->q_end = 0;
+    w->d_lo = 0; w->n = 1; w->far[0] = -1;
+}
+
+static void wave_free(wave_t *w) { free(w->far); free(w->nxt); w->far = w->nxt = 0; w->m = 0; }
+
+/* number of leading bytes two buffers share, at most `max` */
+static inline int32_t shared_prefix(const char *x, const char *y, int32_t max)
+{
+    int32_t i = 0;
+    for (; i + 8 <= max; i += 8) {
+        uint64_t a, b;
+        memcpy(&a, x + i, 8); memcpy(&b, y + i, 8);
+        if (a != b) return i + (__builtin_ctzll(a ^ b) >> 3);
     }
-    b[0].d = a[0].d - 1; b[0].k = a[0].k + 1;
-    b[1].d = a[0].d; b[1].k = ((n == 1 || a[0].k > a[1].k) ? a[0].k : a[1].k) + 1;
-    for (j = 1; j < n - 1; ++j) {
-        int32_t k = a[j - 1].k;
-        if (a[j].k + 1 > k) k = a[j].k + 1;
-        if (a[j + 1].k + 1 > k) k = a[j + 1].k + 1;
-        b[j + 1].d = a[j].d; b[j + 1].k = k;
+    while (i < max && x[i] == y[i]) ++i;
+    return i;
+}
+
+/* slides every live diagonal; 1 when one of them reached the end of the target or of the query */
+static int wave_slide_all(wave_t *w, int32_t *t_end, int32_t *q_end)
+{
+    for (size_t j = 0; j < w->n; ++j) {
+        const int32_t d = w->d_lo + (int32_t) j;
+        int32_t k = w->far[j];
+        if (k >= w->tl || k + d >= w->ql) continue;                     /* already outside */
+        const int32_t room = (w->ql - d < w->tl ? w->ql - d : w->tl) - 1 - k;
+        if (room > 0) k += shared_prefix(w->ts + k + 1, w->qs + k + d + 1, room);
+        if (k == w->tl - 1 || k + d == w->ql - 1) { *t_end = k; *q_end = k + d; return 1; }
+        w->far[j] = k;
     }
-    if (n >= 2) { b[n].d = a[n - 1].d; b[n].k = a[n - 2].k > a[n - 1].k + 1 ? a[n - 2].k : a[n - 1].k + 1; }
-    b[n + 1].d = a[n - 1].d + 1; b[n + 1].k = a[n - 1].k;
-    if (bw < 0 || n < bw + bw + 1) {
-        if (b[0].d < -tl) ++st;
-        if (b[n + 1].d > ql) --en;
-    } else {                                            /* fixed band in extension mode (levdist.c:99-113) */
-        int32_t lo = -bw, hi = bw;
-        if (lo < -tl) lo = -tl;
-        if (hi < ql) hi = ql;                           /* sic: the reference widens, it does not clip */
-        while (b[st].d < lo) ++st;
-        while (b[en - 1].d > hi) --en;
+    return 0;
+}
+
+/* one more edit: the wave widens by a diagonal on either side, then the band rule trims it */
+static void wave_widen(wave_t *w)
+{
+    const int32_t n = (int32_t) w->n, bw = w->bw;
+    wave_reserve(w, (size_t) n + 4);
+    const int32_t *f = w->far;
+    int32_t *g = w->nxt, lo = 0, hi = n + 2, j;
+    for (j = 0; j < n + 2; ++j) {                                       /* g[j]: diagonal d_lo - 1 + j */
+        const int32_t ins = j >= 2 ? f[j - 2] : WAVE_NONE;              /* from the diagonal below */
+        const int32_t sub = j >= 1 && j <= n ? f[j - 1] + 1 : WAVE_NONE;
+        const int32_t del = j < n ? f[j] + 1 : WAVE_NONE;               /* from the diagonal above */
+        int32_t best = ins > sub ? ins : sub;
+        g[j] = best > del ? best : del;
     }
-    memmove(a, &b[st], (size_t) (en - st) * sizeof(*a));
-    return en - st;
+    const int32_t d0 = w->d_lo - 1;
+    if (bw < 0 || n < 2 * bw + 1) {
+        if (d0 < -w->tl) ++lo;
+        if (d0 + n + 1 > w->ql) --hi;
+    } else {
+        const int32_t min_d = -bw > -w->tl ? -bw : -w->tl, max_d = bw > w->ql ? bw : w->ql;
+        while (d0 + lo < min_d) ++lo;
+        while (d0 + hi - 1 > max_d) --hi;
+    }
+    w->d_lo = d0 + lo;
+    w->n = (size_t) (hi - lo);
+    memcpy(w->far, g + lo, w->n * sizeof(int32_t));
 }
 
 static void wave_run(wave_t *w)
 {
-    int32_t s = w->score, n = (int32_t) w->n, t_end = w->t_end, q_end = w->q_end, na;
-    if (w->m < 2 * (size_t) (w->tl + w->ql + 2)) {
-        w->m = 2 * (size_t) (w->tl + w->ql + 2);
-        w->a = (wdiag_t *) realloc(w->a, w->m * sizeof(wdiag_t));
-    }
+    int32_t t_end = w->t_end, q_end = w->q_end;
     for (;;) {
-        na = wave_step(w, n, &t_end, &q_end);
-        if (na < 0) break;
-        ++s;
-        n = na;
-        if (w->bw >= 0 && s > w->bw) break;
+        t_end = q_end = -1;
+        if (wave_slide_all(w, &t_end, &q_end)) break;
+        wave_widen(w);
+        ++w->score;
+        if (w->bw >= 0 && w->score > w->bw) break;
     }
     w->t_end = t_end + 1; w->q_end = q_end + 1;
-    w->score = s; w->n = (size_t) n;
 }
 
 /* test hook: the extension-mode edit distance between two strings in one go, and resumed over a query that grows
@@ -138,9 +168,7 @@ void oatk_wave_align(const char *ts, int32_t tl, const char *qs, int32_t ql, int
     wave_t w;
     memset(&w, 0, sizeof(w));
     w.ts = ts; w.tl = tl; w.bw = bw; w.qs = qs;
-    w.m = 4 * (size_t) (tl + ql + 4);
-    w.a = (wdiag_t *) malloc(w.m * sizeof(wdiag_t));
-    w.n = 1; w.a[0].d = 0; w.a[0].k = -1;
+    wave_begin(&w);
     if (grow <= 0) grow = ql ? ql : 1;
     for (int32_t have = 0; ; ) {
         have = have + grow < ql ? have + grow : ql;
@@ -150,7 +178,7 @@ void oatk_wave_align(const char *ts, int32_t tl, const char *qs, int32_t ql, int
         /* an end of the QUERY was reached: the graph search appends more query and runs again from this state */
     }
     out[0] = w.score; out[1] = w.t_end; out[2] = w.q_end;
-    free(w.a);
+    wave_free(&w);
 }
 
 /* ---------------------------------------------------------------- small vectors */
@@ -193,7 +221,7 @@ typedef struct {
     int status, leaves, best, second;                   /* best / second best score so far */
     str_t cand, best_seq;
     v64_t path, best_path;
-    wdiag_t *stash; size_t stash_n, stash_m;            /* wavefronts of the levels above, stacked */
+    int32_t *stash; size_t stash_n, stash_m;            /* wavefronts of the levels above, stacked */
 } search_t;
 
 static void search_from(const asmg_t *G, search_t *S, uint64_t sink, wave_t *w)
@@ -203,10 +231,10 @@ static void search_from(const asmg_t *G, search_t *S, uint64_t sink, wave_t *w)
     const uint64_t from = S->path.a[n0 - 1];
     const asmg_arc_t *arc = &G->arc[G->idx_p[from]];
     const uint64_t n_arc = G->idx_n[from];
-    const int32_t t_end0 = w->t_end, q_end0 = w->q_end, s0 = w->score;
+    const int32_t t_end0 = w->t_end, q_end0 = w->q_end, s0 = w->score, lo0 = w->d_lo;
     const size_t stash0 = S->stash_n;
-    if (S->stash_n + d0 > S->stash_m) { S->stash_m = (S->stash_n + d0) * 2 + 64; S->stash = (wdiag_t *) realloc(S->stash, S->stash_m * sizeof(wdiag_t)); }
-    memcpy(S->stash + stash0, w->a, d0 * sizeof(wdiag_t));
+    if (S->stash_n + d0 > S->stash_m) { S->stash_m = (S->stash_n + d0) * 2 + 64; S->stash = (int32_t *) realloc(S->stash, S->stash_m * sizeof(int32_t)); }
+    memcpy(S->stash + stash0, w->far, d0 * sizeof(int32_t));
     S->stash_n += d0;
 
     for (uint64_t i = 0; i < n_arc; ++i) {
@@ -246,8 +274,8 @@ static void search_from(const asmg_t *G, search_t *S, uint64_t sink, wave_t *w)
         else ++S->leaves;
         /* back to the state in front of this arc */
         S->path.n = n0; S->cand.l = l0;
-        w->t_end = t_end0; w->q_end = q_end0; w->score = s0; w->n = d0;
-        memcpy(w->a, S->stash + stash0, d0 * sizeof(wdiag_t));    /* (the stash may have moved: always through S) */
+        w->t_end = t_end0; w->q_end = q_end0; w->score = s0; w->n = d0; w->d_lo = lo0;
+        memcpy(w->far, S->stash + stash0, d0 * sizeof(int32_t));    /* (the stash may have moved: always through S) */
     }
     S->stash_n = stash0;
 }
@@ -297,11 +325,10 @@ static void correct_read(sr_db_t *db, const scg_t *g, double max_edist, uint64_t
             W->seq.l = (size_t) l;
             if (l >= EC_MIN_BLOCK) {
                 wave_t *w = &W->w;
-                w->ts = W->seq.s; w->tl = l; w->score = 0; w->qs = 0; w->ql = 0;
+                w->ts = W->seq.s; w->tl = l; w->qs = 0; w->ql = 0;
+                wave_begin(w);
                 w->bw = (int32_t) ceil(l * max_edist);
                 if (w->bw < EC_MIN_BAND) w->bw = EC_MIN_BAND;
-                if (w->m < (size_t) l * 4) { w->m = (size_t) l * 4; w->a = (wdiag_t *) realloc(w->a, w->m * sizeof(wdiag_t)); }
-                w->n = 1; w->a[0].d = 0; w->a[0].k = -1;
                 search_t *S = &W->S;
                 S->status = EC_FAILURE; S->leaves = 0; S->best = S->second = INT32_MAX;
                 S->cand.l = 0; S->best_seq.l = 0; S->path.n = 0; S->best_path.n = 0;
@@ -531,7 +558,7 @@ void read_error_correction(sr_db_t *sr_db, scg_t *g, double max_edist, uint32_t 
     }
     for (int t = 0; t < n_threads; ++t) {
         ec_worker_t *W = &J[t].W;
-        free(W->w.a); free(W->S.cand.s); free(W->S.best_seq.s); free(W->S.path.a); free(W->S.best_path.a); free(W->S.stash);
+        wave_free(&W->w); free(W->S.cand.s); free(W->S.best_seq.s); free(W->S.path.a); free(W->S.best_path.a); free(W->S.stash);
         free(W->seq.s); free(W->kk.a); free(W->pp.a);
     }
     free(J);

@@ -113,7 +113,10 @@ def test_partial_sort_and_repair(gpu_ctx, oracle, low_bits, expect):
     """sg_count sorts on the top 64 - low_bits hash bits and repairs the runs that differ below; moving the split
     makes the repair pass (and, past its buffers, the fall-back to the full sort) do real work"""
     from oatk_b200 import lib
-    reads = synth.hifi_reads(11, 100000, 300, 15000, 0.001) + synth.adversarial_reads(5, 101, 11)
+    # one owner per run now repairs it whole, however many inversions it holds: only runs past 4096 tuples (here: 256
+    # buckets of ~4600) send the sort back to all 64 bits
+    n_reads, read_len = (6000, 12000) if expect == "fallback" else (300, 15000)
+    reads = synth.hifi_reads(11, 100000, n_reads, read_len, 0.001) + synth.adversarial_reads(5, 101, 11)
     bases, off = pack_reads(reads)
     db, _ = oracle.extract(bases, off, 101, 11)
     exp = oracle.collect(db, len(reads), 64)
