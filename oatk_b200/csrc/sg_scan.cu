@@ -572,7 +572,10 @@ __global__ void __launch_bounds__(32 * SYNC_SCAN_WARPS) scan_exact_kernel(ScanAr
                     // nothing can close unless it is at most every whole chunk in its window, nothing can open
                     // unless the element leaving is: whole-chunk minima decide for most chunks
                     const uint64_t own = ringS[P & RMASK];
-                    const uint64_t lv = cA >= 0 ? min(cm[cA & CM], c1) : c1;
+                    // the leaving elements e(p) = m[a0 - 1 + i] sit in the two chunks from (a0 - 1) >> 4 on (that is
+                    // cA - 1 and cA when q - 1 is a multiple of 16)
+                    const int cE = (a0 - 1) >> 4;
+                    const uint64_t lv = min(cE >= 0 ? cm[cE & CM] : SG_NONE64, cE + 1 >= 0 ? cm[(cE + 1) & CM] : SG_NONE64);
                     if (own > R2) mC = 0;
                     if (lv > R2) mO = 0;
                 }

@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libsyncgpu.so")
+LIB_PATH = os.environ.get("OATK_SYNCGPU_LIB") or os.path.join(HERE, "libsyncgpu.so")   # the override is for kernel experiments (tools/)
 
 SG_T_NAMES = ["encode", "scan", "kmerhash", "place", "sort", "group", "stat", "arcs", "pack"]
 

@@ -37,7 +37,8 @@ def test_adversarial(gpu_ctx, oracle, k, s):
     check(gpu_ctx, oracle, synth.adversarial_reads(3, k, s), k, s)
 
 
-@pytest.mark.parametrize("k,s", [(1001, 31), (501, 31), (2001, 31), (301, 15), (40, 1), (12, 11), (20001, 31)])
+@pytest.mark.parametrize("k,s", [(1001, 31), (501, 31), (2001, 31), (301, 15), (40, 1), (12, 11), (20001, 31),
+                                 (127, 31), (1007, 31), (47, 31), (142, 31), (1006, 31)])   # q - 1 a multiple of 16, and one off on either side
 def test_tandem_repeats(gpu_ctx, oracle, k, s):
     """reads carrying tandem arrays (period 2, 3, TTAGGG, 37, 171; 2 kb up to the whole read): every window position
     ties for the minimum. scan_kernel hands such reads to scan_exact_kernel; both must agree with the reference rules"""
