@@ -70,7 +70,9 @@ void sg_batch_destroy(sg_batch *b);
  * off: n_reads+1 byte offsets into bases. Host version copies (bases need not be
  * pinned; pinned makes the copy asynchronous). Device version borrows the
  * pointers, which must stay valid until the batch is destroyed or reset; the
- * bases pointer must be 16-byte aligned. */
+ * bases pointer must be 16-byte aligned and the buffer readable up to the next
+ * multiple of 16 bytes after total_bases (the encode kernel moves whole 16-byte
+ * units, by 128-bit loads before and by the TMA unit's bulk copies now). */
 int sg_batch_set_reads_host(sg_batch *b, const char *bases, const uint64_t *off, uint64_t n_reads);
 int sg_batch_set_reads_device(sg_batch *b, const void *d_bases, const uint64_t *d_off, uint64_t n_reads, uint64_t total_bases);
 /* read ids of this batch start here (sid = sid_base + index); default 0 */

@@ -9,8 +9,10 @@
 //
 // One WARP per read (reads are handed out through an atomic counter, the grid is
 // persistent), no block-wide barriers. The warp walks the read in tiles of 1024
-// raw bytes; lane l owns 32 consecutive bytes (two aligned 128-bit loads, issued
-// one tile ahead). Per tile:
+// raw bytes. A tile travels global -> shared memory as ONE bulk copy of the TMA
+// unit (cp.async.bulk, issued by lane 0 two tiles ahead, completion counted in
+// bytes on an mbarrier of the stage); lane l then owns 32 consecutive bytes of the
+// tile (two 128-bit shared-memory loads). Per tile:
 //   classify   four bytes at a time in registers: codes from bits 1-2 of the ASCII
 //              byte, validity by re-deriving the three bits that separate ACGT/acgt
 //              from everything else; anything else (N, IUPAC, U, bytes 0..3) sends
@@ -32,6 +34,29 @@ namespace sg {
 constexpr int ENC_WARPS = 8;
 constexpr int ENC_TILE = 1024;                 // raw bytes per warp and tile
 constexpr int ENC_SLOTS = ENC_TILE + 64;       // staged 16-bit entries per warp (tile + carry + slack)
+constexpr int ENC_STAGES = 2;                  // raw tiles in flight per warp
+
+// ---- TMA bulk copy + mbarrier (PTX; SASS: UBLKCP / SYNCS) ----
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t arrivals)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(arrivals) : "memory");
+}
+// one arrival that also announces `bytes` of asynchronous traffic: the phase completes when they have landed
+__device__ __forceinline__ void mbar_arrive_expect(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+            :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile("{\n.reg .pred p;\nSG_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra SG_DONE;\nbra SG_WAIT;\nSG_DONE:\n}"
+            :: "r"(bar), "r"(parity) : "memory");
+}
 
 __device__ __forceinline__ int base_code_slow(uint32_t ch)
 {
@@ -69,10 +94,20 @@ __device__ __forceinline__ uint32_t pack4(uint32_t cc) { return ((cc & 0x0303030
 __global__ void __launch_bounds__(32 * ENC_WARPS) encode_kernel(EncodeArgs A)
 {
     __shared__ __align__(16) uint16_t s_ent_all[ENC_WARPS][ENC_SLOTS];
+    __shared__ __align__(128) uint8_t s_raw_all[ENC_WARPS][ENC_STAGES][ENC_TILE];   // raw tiles, filled by the TMA unit
+    __shared__ __align__(8) uint64_t s_bar_all[ENC_WARPS][ENC_STAGES];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     uint16_t *ent = s_ent_all[wid];
     uint32_t *ent32 = reinterpret_cast<uint32_t *>(ent);
     const uint32_t lt_mask = (1u << lane) - 1u;
+    const uint32_t raw_s = smem_addr(s_raw_all[wid][0]), bar_s = smem_addr(&s_bar_all[wid][0]);
+    if (lane == 0) {
+        for (int i = 0; i < ENC_STAGES; ++i) mbar_init(bar_s + 8 * i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncwarp();
+    uint32_t n_used = 0;             // tiles this warp has consumed so far: stage = n_used % STAGES, parity = (n_used / STAGES) & 1
 
     for (;;) {
         unsigned int r32 = 0;
@@ -97,13 +132,17 @@ __global__ void __launch_bounds__(32 * ENC_WARPS) encode_kernel(EncodeArgs A)
         uint32_t n_amb = 0;          // ambiguous characters seen by this lane
         bool any_n = false;          // the staged entries may carry N flags (uniform)
 
-        auto load_chunk = [&](int t, uint4 &q0, uint4 &q1) {
-            const uint64_t g = a0 + (uint64_t) t * ENC_TILE + (uint64_t) lane * 32;
-            q0 = make_uint4(0, 0, 0, 0); q1 = q0;
-            if (t < ntiles && g < raw1 && g + 32 > raw0) {
-                q0 = __ldg(reinterpret_cast<const uint4 *>(A.bases + g));
-                if (g + 16 < raw1) q1 = __ldg(reinterpret_cast<const uint4 *>(A.bases + g + 16));
-            }
+        // tile t of this read into the stage it will be consumed from (lane 0 only). The copy ends at the 16-byte
+        // boundary after the read's last base (the input buffer is readable up to there, include/syncgpu.h).
+        const uint64_t raw_end = (raw1 + 15ull) & ~15ull;
+        auto issue_tile = [&](int t, uint32_t use) {
+            const uint64_t g = a0 + (uint64_t) t * ENC_TILE;
+            const uint32_t bytes = (uint32_t) min((uint64_t) ENC_TILE, raw_end - g);
+            const uint32_t st = use % ENC_STAGES;
+            // the slow path may have written codes over the stage with ordinary stores: order them before the unit's writes
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive_expect(bar_s + 8 * st, bytes);
+            bulk_load(raw_s + st * ENC_TILE, A.bases + g, bytes, bar_s + 8 * st);
         };
         // a run of 256 or more saturates ho_rl and goes to the side list (syncmer.c:301-304)
         auto side_list = [&](uint32_t idx, uint32_t rl1) {
@@ -111,11 +150,17 @@ __global__ void __launch_bounds__(32 * ENC_WARPS) encode_kernel(EncodeArgs A)
             if (o < A.lrl_cap) { A.lrl_sid[o] = sid; A.lrl_idx[o] = idx; A.lrl_val[o] = rl1; }
         };
 
-        uint4 nq0, nq1;
-        load_chunk(0, nq0, nq1);
-        for (int t = 0; t < ntiles; ++t) {
-            const uint4 q0 = nq0, q1 = nq1;
-            load_chunk(t + 1, nq0, nq1);                   // in flight while this tile is processed
+        if (lane == 0)
+            for (int t = 0; t < ENC_STAGES && t < ntiles; ++t) issue_tile(t, n_used + t);
+        for (int t = 0; t < ntiles; ++t, ++n_used) {
+            const uint32_t st = n_used % ENC_STAGES;
+            mbar_wait(bar_s + 8 * st, (n_used / ENC_STAGES) & 1u);
+            // bytes the copy did not bring (beyond the read's end) read as zero, as do chunks outside the read
+            const uint64_t g = a0 + (uint64_t) t * ENC_TILE + (uint64_t) lane * 32;
+            const bool in0 = g < raw1 && g + 32 > raw0, in1 = in0 && g + 16 < raw1;
+            const uint4 *tp = reinterpret_cast<const uint4 *>(s_raw_all[wid][st]) + 2 * lane;
+            const uint4 zero4 = make_uint4(0, 0, 0, 0);
+            const uint4 q0 = in0 ? tp[0] : zero4, q1 = in1 ? tp[1] : zero4;
             const int rel = (int) (int64_t) (a0 + (uint64_t) t * ENC_TILE + (uint64_t) lane * 32 - raw0);   // read position of my first byte
             const uint32_t w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
             uint32_t cc[8];
@@ -137,14 +182,15 @@ __global__ void __launch_bounds__(32 * ENC_WARPS) encode_kernel(EncodeArgs A)
                 }
             }
             if (bad) {
-                // exact per-byte codes (also fixes U, raw 0..3) for the valid bytes; everything else becomes 0
+                // exact per-byte codes (also fixes U, raw 0..3) for the valid bytes; everything else becomes 0. The words
+                // are taken from the staged tile and the codes written back over them, so that no register array is
+                // indexed at run time (it would move to local memory); my 32 bytes of the stage are mine alone.
                 bad = 0;
+                uint32_t *mine = reinterpret_cast<uint32_t *>(s_raw_all[wid][st]) + 8 * lane;
 #pragma unroll 1
                 for (int j = 0; j < 8; ++j) {
-                    uint32_t cw = 0, wj = 0;
-                    // runtime-indexed register arrays go through select chains (no local memory)
-#pragma unroll
-                    for (int jj = 0; jj < 8; ++jj) if (jj == j) wj = w[jj];
+                    uint32_t cw = 0;
+                    const uint32_t wj = mine[j];
                     for (int b = 0; b < 4; ++b) {
                         const int i = 4 * j + b;
                         if (i < vlo || i >= vhi) continue;
@@ -157,11 +203,14 @@ __global__ void __launch_bounds__(32 * ENC_WARPS) encode_kernel(EncodeArgs A)
                             ++n_amb;
                         } else cw |= (uint32_t) c << (8 * b);
                     }
-#pragma unroll
-                    for (int jj = 0; jj < 8; ++jj) if (jj == j) cc[jj] = cw;
+                    mine[j] = cw;
                 }
+                const uint4 c0 = reinterpret_cast<const uint4 *>(mine)[0], c1 = reinterpret_cast<const uint4 *>(mine)[1];
+                cc[0] = c0.x; cc[1] = c0.y; cc[2] = c0.z; cc[3] = c0.w; cc[4] = c1.x; cc[5] = c1.y; cc[6] = c1.z; cc[7] = c1.w;
             }
             if (__any_sync(SG_FULL, (NM0 | NM1) != 0)) any_n = true;
+            // every lane is done with the staged bytes (the vote above is the warp's rendezvous): refill the stage
+            if (lane == 0 && t + ENC_STAGES < ntiles) issue_tile(t + ENC_STAGES, n_used + ENC_STAGES);
 
             // packed codes: positions 0..15 in P0, 16..31 in P1, first position in bits 31:30
             const uint32_t P0 = pack4(cc[0]) << 24 | pack4(cc[1]) << 16 | pack4(cc[2]) << 8 | pack4(cc[3]);
@@ -235,10 +284,10 @@ __global__ void __launch_bounds__(32 * ENC_WARPS) encode_kernel(EncodeArgs A)
                         if (!((MW >> (2 * (15 - (i & 15)))) & 1u)) continue;
                         uint32_t rl1 = (uint32_t) (rel + i - pv - 1);
                         if (rl1 >= 255u) { if (g_done + e > 0) side_list(g_done + e - 1, rl1); rl1 = 255u; }
-                        uint32_t cw = 0;
-#pragma unroll
-                        for (int jj = 0; jj < 8; ++jj) if (jj == (i >> 2)) cw = cc[jj];
-                        ent[e] = (uint16_t) (rl1 | ((cw >> (8 * (i & 3))) & 0xffu) << 8);
+                        // code byte of position i from the packed words (no run-time index into cc[]): code | N flag << 2
+                        const int sh = 2 * (15 - (i & 15));
+                        const uint32_t cb = (((i < 16 ? P0 : P1) >> sh) & 3u) | ((((i < 16 ? NM0 : NM1) >> sh) & 1u) << 2);
+                        ent[e] = (uint16_t) (rl1 | cb << 8);
                         pv = rel + i;
                         ++e;
                     }
