@@ -201,6 +201,10 @@ def main():
     ap.add_argument("--workload", default="uniform", choices=("uniform", "repeats"),
                     help="uniform: configs[1] as is; repeats: the same with every 100th read carrying a 2-15 kb tandem array "
                          "(period 2, 3, TTAGGG, 37, 171)")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the configs[4] lines (k = 501 and 2001 on the same reads)")
+    ap.add_argument("--no-config3", action="store_true", help="skip the configs[3] line (10 M reads over 8 GPUs; runs only at 8 GPUs)")
+    ap.add_argument("--no-whole", action="store_true", help="skip the configs[2] line (whole syncasm command on 200 k reads; one GPU only)")
+    ap.add_argument("--whole-reads", type=int, default=200000)
     args = ap.parse_args()
     globals()["K"], globals()["ERR"] = args.k, args.err
     if args.impl == "reference":
@@ -246,9 +250,10 @@ def main():
             mgpu = {"ok": False, "world": world, "error": repr(e)[:300]}
         comm = lib.Comm(ctx, world, rank, share_unique_id(torch, dist, lib, rank, dev))
 
-    def step():
-        batch.set_reads_device(bases.data_ptr(), off.data_ptr(), n_reads, total)
-        batch.extract(K, S)
+    def step(k=None, rd=None):
+        b_, o_, n_, t_ = rd if rd is not None else (bases, off, n_reads, total)
+        batch.set_reads_device(b_.data_ptr(), o_.data_ptr(), n_, t_)
+        batch.extract(K if k is None else k, S)
         if comm is not None:
             comm.exchange_tuples(batch)      # sg_tuples_partition -> NCCL all-to-all-v -> sg_tuples_adopt, in C
         st = batch.stat()
@@ -285,6 +290,7 @@ def main():
     if dist is not None:
         dist.barrier()
     launches = ctx.launches() - l0
+    ex_bytes = None if comm is None else comm.bytes_sent() // max(1, W + args.steps)
     clocks = sampler.stop() if sampler else None
     ms_step = e0.elapsed_time(e1) / args.steps
     if dist is not None:
@@ -305,12 +311,66 @@ def main():
     if world > 1:
         ids_check = check_global_ids(torch, dist, batch, comm, rank, world, dev, n_reads)
 
+    def timed(k, rd, steps):
+        """device-resident throughput of one more configuration, same protocol as the headline (barrier, CUDA events, max over ranks)"""
+        n_, t_ = (rd[2], rd[3]) if rd is not None else (n_reads, total)
+        for _ in range(3):
+            step(k, rd)
+        ctx.enable_timing(True)
+        ctx.timings()
+        sm = {}
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            step(k, rd)
+            for name, (ms, _ln) in ctx.timings().items():
+                sm[name] = sm.get(name, 0.0) + ms / steps
+        b.record()
+        torch.cuda.synchronize()
+        ctx.enable_timing(False)
+        ms_ = a.elapsed_time(b) / steps
+        if dist is not None:
+            t = torch.tensor([ms_], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_ = float(t.item())
+        z, c = batch.extract_sizes(), batch.count_sizes()
+        ext_b = t_ + 1.25 * z.hoco_bases + 20.0 * z.n_syncmers
+        ext_ms = sm["encode"] + sm["scan"] + sm["kmerhash"]
+        return {"k": int(K if k is None else k), "s": S, "reads_per_gpu": int(n_), "value": world * t_ / (ms_ * 1e-3), "unit": "bases/s",
+                "ms_per_step": ms_, "steps": steps, "warmup": 3, "extract_ms": ext_ms, "extract_gbs": ext_b / (ext_ms * 1e-3) / 1e9,
+                "stage_ms": sm, "syncmers_rank0": int(z.n_syncmers), "distinct_kmers_rank0": int(c.n_unique)}
+
+    # configs[4]: the same reads at k = 501 and k = 2001 (every N the driver launches carries the sweep)
+    sweep = None
+    if not args.no_sweep and args.k == 1001 and args.workload == "uniform":
+        sweep = [timed(kk, None, max(2, min(args.steps, 3))) for kk in (501, 2001)]
+
+    # configs[3]: ONE read set of 10 M x 15 kb reads in contiguous blocks over 8 GPUs, global ids checked on a sample
+    config3 = None
+    if not args.no_config3 and world == 8 and args.workload == "uniform":
+        n3 = 10_000_000 // world
+        b3, o3 = synth_gpu.hifi_reads_gpu(3000 + rank, 500_000_000, n3, READ_LEN, ERR, dev, genome_seed=3)
+        batch.set_sid_base(rank * n3)
+        config3 = timed(None, (b3, o3, n3, n3 * READ_LEN), 2)
+        config3["workload"] = "BASELINE.json configs[3]: 10 M x %d b reads of a 500 Mb genome, %d per GPU in contiguous blocks, tuple exchange + id return over NCCL" % (READ_LEN, n3)
+        config3["global_ids_sample_check"] = check_global_ids(torch, dist, batch, comm, rank, world, dev, n3)
+        batch.set_sid_base(rank * n_reads)
+        del b3, o3
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return 0
 
     peak, peak_src = measured_peak()
+    if sweep:
+        for e_ in sweep:
+            e_["roofline_frac"] = e_["extract_gbs"] / peak
+    if config3:
+        config3["roofline_frac"] = config3["extract_gbs"] / peak
     # algorithmic bytes of the extract kernels (SURVEY.md 8(d)): raw read + hoco_s + ho_rl written + 20 B per syncmer
     ext_bytes = total + 1.25 * sizes.hoco_bases + 20.0 * sizes.n_syncmers
     ext_ms = (stage_ms["encode"] + stage_ms["scan"] + stage_ms["kmerhash"]) / args.steps
@@ -334,19 +394,104 @@ def main():
                    "sample": "first %d reads of the step's batch (%.2f Gbases), reference sr_read -t %d + sr_db_stat + collect, FASTA in /dev/shm" % (
                        ns, ns * READ_LEN / 1e9, threads), "stages_s": r["stages"]}
 
+    scan_info = int(batch.debug_scan_info())
+    whole = None
+    if world == 1 and not args.no_whole:
+        del bases, off
+        batch.close()
+        torch.cuda.empty_cache()
+        try:
+            whole = whole_command(torch, synth_gpu, dev, args.whole_reads, os.cpu_count() or 1)
+        except Exception as e:                         # reported, never fatal for the headline
+            whole = {"error": repr(e)[:300]}
+
     line = {"metric": "HiFi bases/sec syncmer-extract+count", "value": value, "unit": "bases/s", "n_gpus": world,
             "steps": args.steps, "warmup": W, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": workload_config(world, n_reads, args.workload, n_planted),
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+            "k_sweep": sweep, "config3": config3, "whole_command": whole,
             "multi_gpu_parity": mgpu, "global_ids_sample_check": ids_check,
             "exchange": None if comm is None else {"transport": "sg_comm_* in C: grouped ncclSend/ncclRecv, counts on the device",
-                                                   "bytes_sent_per_step_rank0": comm.bytes_sent() // max(1, W + args.steps + 0)},
+                                                   "bytes_sent_per_step_rank0": ex_bytes},
             "results": {"syncmers": int(sizes.n_syncmers), "distinct_kmers": int(csz.n_unique), "hoco_bases": int(sizes.hoco_bases),
-                        "reads_on_exact_scan_path": int(batch.debug_scan_info())}}
+                        "reads_on_exact_scan_path": scan_info}}
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
     return 0
+
+
+def whole_command(torch, synth_gpu, dev, n_reads, threads):
+    """BASELINE.json configs[2]: the WHOLE command, FASTA -> <out>.utg.gfa + <out>.utg.final.gfa, with the reference's defaults
+    (-k 1001 -s 31 -c 30 -a 0.35, read error correction, 3 unzip rounds): once through this repository's syncasm()
+    (oatk_b200/host/liboatk_gpu.so over libsyncgpu.so, second call in the process timed) and its `syncasm` command (one
+    shot, process start and CUDA context included), once through the unmodified reference's syncasm() on the host cores
+    (oracle/_ref/libref.so -- the checker and the CPU baseline). Both output files must be byte-identical."""
+    import hashlib
+    import numpy as np
+    G = 10_000_000
+    bases, _ = synth_gpu.hifi_reads_gpu(2, G, n_reads, READ_LEN, ERR, dev, genome_seed=2)
+    h = bases.cpu().numpy()
+    del bases
+    torch.cuda.empty_cache()
+    d = tempfile.mkdtemp(dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    fa = os.path.join(d, "reads.fa")
+    write_fasta(fa, h, n_reads, READ_LEN)
+    del h
+    out = {"workload": "BASELINE.json configs[2]: syncasm -k 1001 -s 31 -c 30 -a 0.35 -t %d on %d x %d b reads of a %d b genome (%.2f Gbases), FASTA in /dev/shm" % (
+        threads, n_reads, READ_LEN, G, n_reads * READ_LEN / 1e9), "raw_bases": n_reads * READ_LEN}
+    try:
+        from oatk_b200.host import build_host
+        H = C.CDLL(build_host.build())
+        proto = [C.POINTER(C.c_char_p), C.c_int, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double,
+                 C.c_double, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_void_p, C.c_int]
+
+        def call(L, prefix):
+            L.syncasm.restype = C.c_int
+            L.syncasm.argtypes = proto
+            files = (C.c_char_p * 1)(fa.encode())
+            t0 = time.perf_counter()
+            rc = L.syncasm(files, 1, 0, 1001, 31, 100000, 10000, 30, 0.35, 0.3, 1, 3, threads, prefix.encode(), None, 0)
+            return rc, time.perf_counter() - t0
+
+        def digest(prefix):
+            r = {}
+            for sfx in (".utg.gfa", ".utg.final.gfa"):
+                x = open(prefix + sfx, "rb").read()
+                r[sfx] = {"md5": hashlib.md5(x).hexdigest(), "bytes": len(x), "S": x.count(b"\nS\t"), "L": x.count(b"\nL\t")}
+            return r
+
+        po, pc, pr = os.path.join(d, "ours"), os.path.join(d, "ours_cli"), os.path.join(d, "ref")
+        sys.stderr.flush()
+        rc, t_first = call(H, po)
+        assert rc == 0, "syncasm() returned %d" % rc
+        rc, t_ours = call(H, po)
+        assert rc == 0
+        out["ours_s"], out["ours_first_call_s"] = t_ours, t_first
+        out["ours"] = digest(po)
+        exe = os.path.join(ROOT, "oatk_b200", "host", "syncasm")
+        if os.path.exists(exe):
+            t0 = time.perf_counter()
+            rc = subprocess.call([exe, "-k", "1001", "-s", "31", "-c", "30", "-t", str(threads), "-o", pc, fa],
+                                 stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            out["ours_cli_one_shot_s"] = time.perf_counter() - t0
+            out["ours_cli_identical"] = rc == 0 and digest(pc) == out["ours"]
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import pyoracle
+        if pyoracle.have_ref():
+            R = pyoracle.Ref().L
+            rc, t_ref = call(R, pr)
+            out["reference_s"], out["reference_threads"] = t_ref, threads
+            out["reference"] = digest(pr) if rc == 0 else None
+            out["identical"] = rc == 0 and out["reference"] == out["ours"]
+            out["speedup"] = t_ref / t_ours
+        else:
+            out["reference"] = "oracle/_ref/libref.so not built"
+        out["gbases_per_s"] = n_reads * READ_LEN / t_ours / 1e9
+    finally:
+        import shutil
+        shutil.rmtree(d, ignore_errors=True)
+    return out
 
 
 def share_unique_id(torch, dist, lib, rank, dev):
