@@ -59,7 +59,7 @@ const char *sg_last_error(sg_ctx *ctx);
 /* number of kernels launched by this context since creation (bench.py's gpu_launches) */
 uint64_t sg_ctx_launches(sg_ctx *ctx);
 /* per-stage device time of the most recent call, CUDA events on the context's stream */
-enum { SG_T_ENCODE = 0, SG_T_SCAN, SG_T_KMERHASH, SG_T_PLACE, SG_T_SORT, SG_T_GROUP, SG_T_STAT, SG_T_ARCS, SG_T_PACK, SG_T_N };
+enum { SG_T_ENCODE = 0, SG_T_SCAN, SG_T_KMERHASH, SG_T_PLACE, SG_T_SORT, SG_T_GROUP, SG_T_STAT, SG_T_ARCS, SG_T_PACK, SG_T_EC, SG_T_N };
 int sg_ctx_enable_timing(sg_ctx *ctx, int on);
 int sg_ctx_timings(sg_ctx *ctx, float *ms /* SG_T_N */, uint32_t *launches /* SG_T_N */);
 
@@ -123,6 +123,35 @@ int sg_extract_download(sg_batch *b, const sg_extract_out_t *out);
  * on the device: a batch after sg_extract, or a pipe's master batch with sg_pipe_keep_run_lengths. Synchronises. */
 int sg_runlen_sums(sg_batch *b, uint64_t n_req, const uint64_t *occ_off, const uint64_t *occ, uint64_t *sums /* host, n_req * k */);
 int sg_runlen_resident(sg_batch *b);                          /* 1 when sg_runlen_sums can be served */
+
+/* ---- f2: the per-read pass of read error correction on the device ----
+ * Replaces the kt_for over reads inside read_error_correction (reference syncerr.c:342-612 per read, :144-288 dfs_search,
+ * levdist.c:156-225, 265-310 wf_ed_core in extension mode). The caller has run the error filter (syncerr.c:679-757) and
+ * passes what is left of the all-syncmer graph; the reads, their syncmer lists (k_mer = id << 1 | corrected, m_pos) and
+ * hoco_s are those resident in the batch (after sg_count, or after sg_batch_set_lists_host). Results come back as the
+ * rewritten list of every read that has at least one anchor (out_n[r] = 0xffffffff: read r keeps its list). */
+typedef struct {
+    uint64_t n_syncmers;            /* entries of del */
+    const uint8_t *del;             /* per syncmer id: flagged deleted (syncmer_t.del after the filter) */
+    uint64_t n_arcs;                /* live arcs of the filtered graph, in the graph's own order (sorted by v, then as asmg_finalize left them) */
+    const uint64_t *arc_v, *arc_w;  /* oriented vertices, id << 1 | strand */
+    const uint32_t *arc_ls;         /* overlap of v and w in hoco bases (asmg_arc_t.ls) */
+    const uint64_t *arc_txt;        /* where the k hoco bases of w's syncmer are read from: batch-local read << 32 | hoco start << 1 |
+                                       strand of that occurrence (the first one no correction touched, syncasm.c:911-921); ~0: none left, the text is all N */
+} sg_ec_graph_t;
+typedef struct {
+    int64_t stats[11];              /* tail blocks, their 4 outcomes, middle blocks, their 4 outcomes, blocks shorter than 10 bases */
+    uint64_t n_out;                 /* entries of out_k / out_p */
+    uint64_t *out_off;              /* per read: first entry of its rewritten list */
+    uint32_t *out_n;                /* per read: entries, or 0xffffffff when the read keeps its list */
+    uint64_t *out_k;                /* k_mer of the rewritten lists */
+    uint32_t *out_p;                /* m_pos of the rewritten lists */
+    uint64_t n_overflow_reads;      /* reads whose search outgrew the ordinary arena and ran again in the worst-case one */
+} sg_ec_result_t;
+int sg_ec_correct(sg_batch *b, const sg_ec_graph_t *g, double max_edist, sg_ec_result_t *res);
+void sg_ec_result_free(sg_ec_result_t *res);
+/* test hook: vertices per path and stacked wavefront entries of the first-pass search arena (default 256 / 16384) */
+int sg_debug_set_ec_arena(uint32_t path, uint32_t stash);
 
 /* a5: the counting part of sr_db_stat. Dense multiplicity-of-multiplicity tables
  * for distinct s-mer codes and distinct (k_mer >> 1) keys, multiplicities >= 1000

@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsyncgpu.so")
-SOURCES = ["sg_api.cu", "sg_encode.cu", "sg_scan.cu", "sg_kmer.cu", "sg_prims.cu", "sg_pack.cu", "sg_count.cu", "sg_arcs.cu", "sg_pipe.cu", "sg_comm.cu", "sg_runlen.cu"]
+SOURCES = ["sg_api.cu", "sg_encode.cu", "sg_scan.cu", "sg_kmer.cu", "sg_prims.cu", "sg_pack.cu", "sg_count.cu", "sg_arcs.cu", "sg_pipe.cu", "sg_comm.cu", "sg_runlen.cu", "sg_ec.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "--std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "--expt-relaxed-constexpr"]
 

@@ -79,6 +79,7 @@ typedef struct {
 } scg_meta_t;
 #endif
 
+int oatk_ec_last_run(uint64_t *overflow_reads);   /* 1: the last read_error_correction searched on the device */
 void asmg_destroy(asmg_t *g);
 /* graphutil_gpu.c / cleaning_gpu.c: the queries of graph.h:72-96 that callers beyond syncasm() use */
 int asmg_arc_is_sorted(asmg_t *g);

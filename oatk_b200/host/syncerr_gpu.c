@@ -37,6 +37,7 @@
 #include <pthread.h>
 #include <unistd.h>
 #include "graph_gpu.h"
+#include "syncgpu.h"
 
 #define EC_FAILURE 0
 #define EC_SUCCESS 1
@@ -441,6 +442,137 @@ int64_t find_error_syncmers(scg_t *g, uint32_t err_mer_c, uint32_t max_err_c, ui
     return n_err;
 }
 
+/* ---------------------------------------------------------------- the per-read pass on the device
+ * sg_ec_correct (csrc/sg_ec.cu) runs the same blocks / search / rewrite, one warp per read, on the lists and hoco_s that are
+ * resident in the batch behind sr_db. It gets what the error filter left of the graph: the live arcs in the graph's own
+ * order (the search visits them in that order) with their overlaps, and for every arc target the occurrence its k hoco
+ * bases are read from -- the first one no correction touched, which is what scg_consensus writes as the vertex text in
+ * hoco mode (syncasm.c:911-931). Returns 0 when the lists were rewritten; anything else leaves the reads untouched and the
+ * caller runs the host form. Conditions: every vertex is one syncmer with a text of k hoco bases (true for the graph
+ * read_error_correction is given) and the arc array is sorted by its source vertex. */
+static int g_last_on_device;
+static uint64_t g_last_overflow;
+/* where the per-read pass of the last read_error_correction ran (1: device) and how many reads needed the worst-case arena */
+int oatk_ec_last_run(uint64_t *overflow_reads) { if (overflow_reads) *overflow_reads = g_last_overflow; return g_last_on_device; }
+
+/* the live arcs of the filtered graph, in the graph's order, gathered by worker threads: every range counts its live arcs
+ * first, the ranges are then placed one after another, and the same ranges fill their part */
+typedef struct { uint64_t lo, n, at; } ec_part_t;
+typedef struct {
+    sr_db_t *db; const asmg_t *G; const syncmer_t *scm;
+    uint64_t *av, *aw, *at; uint32_t *al;
+    ec_part_t part[64]; int n_part; int fill; int bad;
+    pthread_mutex_t lock;
+} ec_pack_t;
+
+static void ec_pack_range(uint64_t lo, uint64_t hi, void *arg)
+{
+    ec_pack_t *P = (ec_pack_t *) arg;
+    const asmg_t *G = P->G;
+    const int ksz = P->db->k;
+    uint64_t i, j = 0;
+    if (!P->fill) {
+        uint64_t c = 0, prev = lo ? G->arc[lo - 1].v : 0;
+        int bad = 0;
+        for (i = lo; i < hi; ++i) {
+            const asmg_arc_t *a = &G->arc[i];
+            if (a->v < prev) bad = 1;                               /* the search relies on arcs sorted by their source */
+            prev = a->v;
+            if (a->del) continue;
+            const asmg_vtx_t *vx = &G->vtx[a->w >> 1];
+            if (vx->len != (uint64_t) ksz || vx->n != 1 || a->ls >= (uint64_t) ksz) bad = 1;
+            ++c;
+        }
+        pthread_mutex_lock(&P->lock);
+        if (P->n_part < 64) { P->part[P->n_part].lo = lo; P->part[P->n_part].n = c; ++P->n_part; } else bad = 1;
+        P->bad |= bad;
+        pthread_mutex_unlock(&P->lock);
+        return;
+    }
+    for (int q = 0; q < P->n_part; ++q) if (P->part[q].lo == lo) j = P->part[q].at;
+    for (i = lo; i < hi; ++i) {
+        const asmg_arc_t *a = &G->arc[i];
+        if (a->del) continue;
+        P->av[j] = a->v; P->aw[j] = a->w; P->al[j] = (uint32_t) a->ls;
+        /* the occurrence that supplies the bases of w's syncmer, in the syncmer's own orientation */
+        const syncmer_t *m = &P->scm[a->w >> 1];
+        uint64_t ref = UINT64_MAX;
+        for (uint32_t c = 0; c < m->cov; ++c) {
+            const uint64_t occ = m->m_pos[c];
+            const sr_t *r = &P->db->a[occ >> 32];
+            const uint64_t idx = occ >> 1 & MAX_RD_SCM;
+            if (r->k_mer[idx] & 1) continue;
+            ref = (occ >> 32) << 32 | (uint64_t) (r->m_pos[idx] >> 1) << 1 | (r->m_pos[idx] & 1);
+            break;
+        }
+        P->at[j] = ref;
+        ++j;
+    }
+}
+
+typedef struct { sr_db_t *db; const syncmer_t *scm; const sg_ec_result_t *R; } ec_apply_t;
+static void ec_apply_range(uint64_t lo, uint64_t hi, void *arg)
+{
+    const ec_apply_t *A = (const ec_apply_t *) arg;
+    const sg_ec_result_t *R = A->R;
+    for (uint64_t r = lo; r < hi; ++r) {
+        if (R->out_n[r] == 0xffffffffu) continue;
+        sr_t *sr = &A->db->a[r];
+        const size_t nc = R->out_n[r];
+        sr->k_mer = (uint64_t *) realloc(sr->k_mer, nc * sizeof(uint64_t));
+        sr->m_pos = (uint32_t *) realloc(sr->m_pos, nc * sizeof(uint32_t));
+        sr->s_mer = (uint64_t *) realloc(sr->s_mer, nc * sizeof(uint64_t));
+        if (nc) { memcpy(sr->k_mer, R->out_k + R->out_off[r], nc * sizeof(uint64_t)); memcpy(sr->m_pos, R->out_p + R->out_off[r], nc * sizeof(uint32_t)); }
+        for (size_t q = 0; q < nc; ++q) sr->s_mer[q] = A->scm[sr->k_mer[q] >> 1].s;
+        sr->n = (uint32_t) nc;
+    }
+}
+
+static int cmp_part(const void *a, const void *b) { const ec_part_t *x = (const ec_part_t *) a, *y = (const ec_part_t *) b; return x->lo < y->lo ? -1 : x->lo > y->lo; }
+
+static int correct_reads_on_device(sr_db_t *db, scg_t *g, double max_edist, long stats[11])
+{
+    const asmg_t *G = g->utg_asmg;
+    const syncmer_db_t *S = g->scm_db;
+    const syncmer_t *scm = S->a;
+    if (!oatk_gpu_ec_available(db) || G->n_vtx != S->n) return -1;
+    ec_pack_t P;
+    memset(&P, 0, sizeof(P));
+    P.db = db; P.G = G; P.scm = scm;
+    pthread_mutex_init(&P.lock, 0);
+    oatk_parallel_for(G->n_arc, ec_pack_range, &P);
+    qsort(P.part, (size_t) P.n_part, sizeof(ec_part_t), cmp_part);
+    uint64_t n_live = 0;
+    for (int q = 0; q < P.n_part; ++q) { P.part[q].at = n_live; n_live += P.part[q].n; }
+    int rc = -1;
+    if (!P.bad) {
+        uint8_t *del = (uint8_t *) malloc(S->n ? S->n : 1);
+        P.av = (uint64_t *) malloc(8 * (n_live + 1)); P.aw = (uint64_t *) malloc(8 * (n_live + 1)); P.at = (uint64_t *) malloc(8 * (n_live + 1));
+        P.al = (uint32_t *) malloc(4 * (n_live + 1));
+        P.fill = 1;
+        oatk_parallel_for(G->n_arc, ec_pack_range, &P);             /* same n, same ranges */
+        for (uint64_t i = 0; i < S->n; ++i) del[i] = (uint8_t) scm[i].del;
+        oatk_tick("ec/device: arrays of the filtered graph");
+        sg_ec_graph_t E;
+        memset(&E, 0, sizeof(E));
+        E.n_syncmers = S->n; E.del = del; E.n_arcs = n_live; E.arc_v = P.av; E.arc_w = P.aw; E.arc_ls = P.al; E.arc_txt = P.at;
+        sg_ec_result_t R;
+        rc = oatk_gpu_ec_correct(db, &E, max_edist, &R);
+        oatk_tick("ec/device: upload, search kernel, download");
+        if (rc == 0) {
+            ec_apply_t A = {db, scm, &R};
+            oatk_parallel_for(db->n, ec_apply_range, &A);
+            for (int q = 0; q < 11; ++q) stats[q] = (long) R.stats[q];
+            g_last_overflow = R.n_overflow_reads;
+            sg_ec_result_free(&R);
+            oatk_tick("ec/device: lists back into the reads");
+        }
+        free(del); free(P.av); free(P.aw); free(P.at); free(P.al);
+    }
+    pthread_mutex_destroy(&P.lock);
+    return rc;
+}
+
 /* ---------------------------------------------------------------- database after the rewrite */
 static void rebuild_syncmer_db(sr_db_t *db, syncmer_db_t *S)
 {
@@ -511,18 +643,26 @@ void read_error_correction(sr_db_t *sr_db, scg_t *g, double max_edist, uint32_t 
     oatk_tick("ec: find error syncmers");
     if (!have_text) { scg_consensus(sr_db, g, 1, 1, 0); oatk_tick("ec: hoco consensus of the surviving graph"); }
 
-    ec_job_t *J = (ec_job_t *) calloc((size_t) n_threads, sizeof(ec_job_t));
-    uint64_t next = 0;
-    for (int t = 0; t < n_threads; ++t) { J[t].db = sr_db; J[t].g = g; J[t].max_edist = max_edist; J[t].next = &next; }
-    if (n_threads == 1) ec_job(&J[0]);
-    else {
-        for (int t = 0; t < n_threads; ++t) pthread_create(&J[t].th, 0, ec_job, &J[t]);
-        for (int t = 0; t < n_threads; ++t) pthread_join(J[t].th, 0);
-    }
+    /* the per-read pass: on the device when the reads live there (the reference's kt_for over reads, syncerr.c:896),
+     * on worker threads for read databases that were built on the host (OATK_EC_HOST=1 forces that form: parity tests) */
     long stats[11] = {0};
-    for (int t = 0; t < n_threads; ++t) for (int j = 0; j < 11; ++j) stats[j] += J[t].W.stats[j];
+    ec_job_t *J = (ec_job_t *) calloc((size_t) n_threads, sizeof(ec_job_t));
+    const char *force_host = getenv("OATK_EC_HOST");
+    int on_device = 0;
+    if (!(force_host && atoi(force_host) > 0)) on_device = correct_reads_on_device(sr_db, g, max_edist, stats) == 0;
+    g_last_on_device = on_device;
+    if (!on_device) {
+        uint64_t next = 0;
+        for (int t = 0; t < n_threads; ++t) { J[t].db = sr_db; J[t].g = g; J[t].max_edist = max_edist; J[t].next = &next; }
+        if (n_threads == 1) ec_job(&J[0]);
+        else {
+            for (int t = 0; t < n_threads; ++t) pthread_create(&J[t].th, 0, ec_job, &J[t]);
+            for (int t = 0; t < n_threads; ++t) pthread_join(J[t].th, 0);
+        }
+        for (int t = 0; t < n_threads; ++t) for (int j = 0; j < 11; ++j) stats[j] += J[t].W.stats[j];
+    }
 
-    oatk_tick("ec: correct reads");
+    oatk_tick(on_device ? "ec: correct reads (device)" : "ec: correct reads (host threads)");
     rebuild_syncmer_db(sr_db, g->scm_db);
     oatk_tick("ec: rebuild database");
     oatk_gpu_update_lists(sr_db, g->scm_db);            /* the device-resident lists follow the host's */

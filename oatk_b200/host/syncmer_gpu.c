@@ -592,6 +592,24 @@ int oatk_gpu_runlen_sums(sr_db_t *sr_db, uint64_t n_req, const uint64_t *occ_off
     return rc;
 }
 
+/* f2 on the device (sg_ec_correct): 1 when this read database has a device-resident batch whose lists can be searched */
+int oatk_gpu_ec_available(sr_db_t *sr_db)
+{
+    return batch_of(sr_db, 0) != 0;
+}
+
+/* graph / result are sg_ec_graph_t / sg_ec_result_t of include/syncgpu.h (kept opaque here so that the headers of the host
+ * layer do not pull the device ABI in) */
+int oatk_gpu_ec_correct(sr_db_t *sr_db, const void *graph, double max_edist, void *result)
+{
+    sg_batch *b = batch_of(sr_db, 0);
+    int rc;
+    if (!b) return SG_E_STATE;
+    rc = sg_ec_correct(b, (const sg_ec_graph_t *) graph, max_edist, (sg_ec_result_t *) result);
+    if (rc != SG_OK) fprintf(stderr, "[E::%s] %s: %s\n", __func__, sg_strerror(rc), sg_last_error(ctx_of(sr_db)));
+    return rc;
+}
+
 int syncmer_graph_arcs(sr_db_t *sr_db, syncmer_db_t *scm_db, uint32_t min_k_cov, double min_a_cov_f, uint64_t **arcs4, uint64_t *n_arcs)
 {
     sg_batch *b = batch_of(sr_db, 0);

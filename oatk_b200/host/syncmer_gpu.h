@@ -130,6 +130,9 @@ int oatk_gpu_set_device(int device);
 int oatk_gpu_keep_run_lengths(int on);
 int oatk_gpu_run_lengths_on_device(sr_db_t *sr_db);
 int oatk_gpu_runlen_sums(sr_db_t *sr_db, uint64_t n_req, const uint64_t *occ_off, const uint64_t *occ, uint64_t *sums);
+/* the per-read pass of read error correction on the device (syncerr_gpu.c builds the arguments) */
+int oatk_gpu_ec_available(sr_db_t *sr_db);
+int oatk_gpu_ec_correct(sr_db_t *sr_db, const void *graph, double max_edist, void *result);
 void oatk_gpu_shutdown(void);
 
 #ifdef __cplusplus

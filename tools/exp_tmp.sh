@@ -1,8 +1,4 @@
-python bench.py --steps 3 --warmup 3 --no-full-e2e > gpurun_out/exp_bench.json 2>gpurun_out/exp_bench.err; echo rc=$?; tail -5 gpurun_out/exp_bench.err
-python - <<PY
-import json
-d=json.load(open("gpurun_out/exp_bench.json"))
-print("value", d["value"]/1e9, "ms", d["ms_per_step"], "e2e", d["e2e"] and d["e2e"]["value"]/1e9)
-print(json.dumps(d["k_sweep"])[:1500])
-print(json.dumps(d["whole_command"])[:3000])
-PY
+python -m pytest tests/test_gpu_ec.py tests/test_gpu_syncasm.py -x -q 2>&1 | tail -5
+OATK_PF_MIN=1 python -m pytest tests/test_gpu_ec.py -x -q 2>&1 | tail -3
+OATK_TIMING=1 python tools/syncasm_run.py --reads 200000 --genome 10000000 --c 30 2> gpurun_out/whole_stages.err | tail -1 | cut -c1-200
+grep -n "T::ec" gpurun_out/whole_stages.err | tail -8
