@@ -267,6 +267,8 @@ int sg_debug_set_hash_bits(sg_batch *b, int bits);
  * rare runs that differ below (default 24; 0 = sort on all 64 bits). sg_debug_sort_info reports how many
  * out-of-order pairs the last sort repaired and whether it fell back to the full sort. */
 int sg_debug_set_sort_low_bits(sg_batch *b, int low_bits);
+/* test hook: hash bits ordered by the packed sort (8, 16, 24 or 32; default 32) -- fewer bits leave longer runs to the repair pass */
+int sg_debug_set_pack_bits(sg_batch *b, int bits);
 int sg_debug_sort_info(sg_batch *b, uint64_t *repairs, int *fell_back);
 /* tests only: how many reads of the last sg_extract were finished by scan_exact_kernel (full-hash window
  * minimum; taken by reads on which identical s-mers keep tying for the minimum: tandem repeats) */

@@ -90,6 +90,78 @@ __global__ void __launch_bounds__(128) sort_repair_kernel(uint64_t *k, uint64_t 
     }
 }
 
+// ---- packed sort: the top 32 hash bits and the tuple index share one 64-bit word -----------------------------
+// Tuples exist in (sid, idx) order and a stable sort keeps that order among equal keys, so sorting the words
+// (hash >> 32) << 32 | index on their top half alone -- four passes over 8-byte words instead of five over
+// 16-byte pairs -- leaves every tuple in its final place except inside the runs that agree on 32 hash bits
+// (N^2 / 2^33 pairs: a few 10^4 at 21 M tuples). The gather then brings the whole 32-byte record (hash, occurrence,
+// s-mer code, fingerprint) of every word in, and the detect / repair pair below puts the few runs right.
+__global__ void __launch_bounds__(256) pack_init_kernel(const ulonglong4 *tup, uint64_t *pk, uint64_t n, int low_bits)
+{
+    const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) pk[i] = (tup[i].w >> low_bits) << 32 | i;       // low_bits = 32: the top half of the hash stays where it is
+}
+
+__global__ void __launch_bounds__(256) pack_gather_kernel(const uint64_t *pk, const ulonglong4 *tup, uint64_t *skey, uint64_t *sval, uint64_t *socc,
+        uint64_t *ssmer, uint64_t *sfp, uint64_t n)
+{
+    const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const uint64_t idx = pk[i] & 0xffffffffull;
+        const ulonglong2 *p = reinterpret_cast<const ulonglong2 *>(tup + idx);
+        const ulonglong2 a = __ldg(p), b = __ldg(p + 1);
+        skey[i] = b.y; sval[i] = idx; socc[i] = a.x; ssmer[i] = a.y; sfp[i] = b.x;
+    }
+}
+
+// The listed runs, put right over all five gathered arrays: one WARP per run. A run holds the occurrences of the few
+// distinct k-mers that share their top hash bits, each k-mer's occurrences already in tuple order but interleaved with
+// the others' (a genomic k-mer brings its whole coverage along), so an insertion sort would shift hundreds of elements
+// again and again. Every element instead computes its final place -- the number of elements with a smaller hash, or
+// the same hash and an earlier position (stable) -- with the run's hashes read by all lanes together, is parked there
+// in scratch arrays, and the run is copied back. Runs were listed by sort_detect_cap_kernel.
+struct Repair5 { uint64_t *k, *v, *o, *sm, *fp, *tk, *tv, *to, *tsm, *tfp; };
+__global__ void __launch_bounds__(128) sort_repair5_kernel(Repair5 R, uint64_t n, int low_bits, uint32_t cap, uint32_t *fix)
+{
+    const uint32_t cnt = min(fix[0], cap);
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t e = warp; e < cnt; e += nwarp) {
+        const uint64_t i = fix[2 + e];
+        const uint64_t top = R.k[i] >> low_bits;
+        uint64_t s0 = i, s1 = i + 1;
+        while (s0 > 0 && (R.k[s0 - 1] >> low_bits) == top) --s0;
+        while (s1 + 1 < n && (R.k[s1 + 1] >> low_bits) == top) ++s1;
+        if (s1 - s0 > SORT_FIX_MAXRUN) { if (lane == 0) fix[1] = 1u; continue; }
+        for (uint64_t a = s0 + lane; a <= s1; a += 32) {
+            const uint64_t ka = R.k[a];
+            uint64_t r = 0;
+            for (uint64_t b = s0; b <= s1; ++b) { const uint64_t kb = R.k[b]; r += (kb < ka || (kb == ka && b < a)) ? 1u : 0u; }
+            const uint64_t d = s0 + r;
+            R.tk[d] = ka; R.tv[d] = R.v[a]; R.to[d] = R.o[a]; R.tsm[d] = R.sm[a]; R.tfp[d] = R.fp[a];
+        }
+        __syncwarp();
+        for (uint64_t a = s0 + lane; a <= s1; a += 32) { R.k[a] = R.tk[a]; R.v[a] = R.tv[a]; R.o[a] = R.to[a]; R.sm[a] = R.tsm[a]; R.fp[a] = R.tfp[a]; }
+        __syncwarp();
+    }
+}
+
+// sort_detect_kernel with a caller-sized list
+__global__ void __launch_bounds__(256) sort_detect_cap_kernel(const uint64_t *k, uint64_t n, int low_bits, uint32_t cap, uint32_t *fix)
+{
+    const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i + 1 >= n) return;
+    const uint64_t a = k[i], b = k[i + 1];
+    if ((a >> low_bits) != (b >> low_bits) || a <= b) return;
+    const uint64_t top = a >> low_bits;
+    for (uint64_t j = i; j > 0 && (k[j - 1] >> low_bits) == top; --j) {
+        if (k[j - 1] > k[j]) return;                       // an earlier inversion owns the run
+        if (i - j > SORT_FIX_MAXRUN) { fix[1] = 1u; return; }
+    }
+    const uint32_t o = atomicAdd(&fix[0], 1u);
+    if (o < cap) fix[2 + o] = (uint32_t) i; else fix[1] = 1u;
+}
+
 // the same from the 32-byte records written by kmerhash_kernel: one sector per tuple
 __global__ void __launch_bounds__(256) tuple_gather_aos_kernel(const uint64_t *sval, const ulonglong4 *tup, uint64_t *socc, uint64_t *ssmer, uint64_t *sfp, uint64_t n)
 {
@@ -310,6 +382,30 @@ __global__ void __launch_bounds__(256) key_tally_kernel(const uint64_t *keys, ui
         table_add_warp(tk, tv, nslot_mask, base + lane < n ? keys[base + lane] : EMPTY_KEY, lane);
 }
 
+// the same in a table sized for FEW distinct keys (it then stays in L2): gives up when a key finds no slot nearby
+__global__ void __launch_bounds__(256) key_tally_small_kernel(const uint64_t *keys, uint64_t n, uint64_t *tk, uint32_t *tv, uint64_t nslot_mask,
+        unsigned int *full)
+{
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp0 = ((uint64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nwarp = ((uint64_t) gridDim.x * blockDim.x) >> 5;
+    for (uint64_t base = warp0 * 32; base < n; base += nwarp * 32) {
+        unsigned int gave_up = 0;
+        if (lane == 0) gave_up = *((volatile unsigned int *) full);
+        if (__shfl_sync(SG_FULL, gave_up, 0)) return;           // somebody gave up: the result will be thrown away
+        const uint64_t key = base + lane < n ? keys[base + lane] : EMPTY_KEY;
+        const uint32_t peers = __match_any_sync(SG_FULL, key);
+        const bool leader = key != EMPTY_KEY && lane == __ffs(peers) - 1;
+        const uint32_t cnt = __popc(peers);
+        uint32_t work = __ballot_sync(SG_FULL, leader);
+        while (work) {
+            const int src = __ffs(work) - 1;
+            work &= work - 1;
+            table_add_bounded(tk, tv, nslot_mask, __shfl_sync(SG_FULL, key, src), __shfl_sync(SG_FULL, cnt, src), lane, 4, full);
+        }
+    }
+}
+
 // multiplicity-of-multiplicity histogram over the occupied slots; hist[1001] counts the distinct keys
 __global__ void __launch_bounds__(256) slot_hist_kernel(const uint64_t *tk, const uint32_t *tv, uint64_t nslots, unsigned long long *hist)
 {
@@ -403,6 +499,42 @@ static int ensure_sorted(sg_batch *b)
     RS(b->sort_fix, (SORT_FIX_CAP + 2) * 4);
     const int SORT_LOW_BITS = b->keys_are_ids ? 0 : b->sort_low_bits;   // 24 unless a test moves it (multiple of 8); dense ids: all bits
     bool full = b->hash_bits < 64 || SORT_LOW_BITS == 0;     // truncated hashes (tests) collide by design
+    // the ordinary case: whole hashes, records of this batch's own extract, fewer than 2^32 tuples (the index shares a word
+    // with the top half of the hash)
+    if (!full && SORT_LOW_BITS == 24 && b->tup_valid && !b->adopted && !b->keys_are_ids && N < (1ull << 32) && !getenv("SG_SORT_PAIRS")) {
+        const uint32_t cap = (uint32_t) std::min<uint64_t>(N / 64 + SORT_FIX_CAP, 1u << 26);
+        RS(b->sort_fix, ((size_t) cap + 2) * 4);
+        uint64_t *pk = (uint64_t *) b->skey_alt.p, *pk_alt = (uint64_t *) b->sval_alt.p;
+        const int plow = 64 - b->pack_bits;                   // hash bits the packed sort leaves to the repair (32 unless a test moves it)
+        pack_init_kernel<<<nblk(N, 256), 256, 0, st>>>((const ulonglong4 *) b->tup.p, pk, N, plow);
+        ctx->count_launch(SG_T_SORT, 1);
+        LAUNCHED(SG_T_SORT, launch_sort_keys(pk, pk_alt, N, 32, 32 + b->pack_bits, (uint32_t *) b->sort_tmp.p, st));
+        pack_gather_kernel<<<nblk(N, 256), 256, 0, st>>>(pk, (const ulonglong4 *) b->tup.p, (uint64_t *) b->skey.p, (uint64_t *) b->sval.p,
+                (uint64_t *) b->socc.p, (uint64_t *) b->ssmer.p, (uint64_t *) b->sfp.p, N);
+        CK(cudaMemsetAsync(b->sort_fix.p, 0, 8, st));
+        sort_detect_cap_kernel<<<nblk(N, 256), 256, 0, st>>>((const uint64_t *) b->skey.p, N, plow, cap, (uint32_t *) b->sort_fix.p);
+        // one warp per listed run (their number is known on the device only: a grid for a full list, warps without a run leave at once);
+        // scratch: the two word buffers of the sort and three arrays that are filled later in the step
+        RS(b->ids, (N + 2) * 8); RS(b->starts, (N + 2) * 8); RS(b->kid, (N + 1) * 8);
+        Repair5 R5 = {(uint64_t *) b->skey.p, (uint64_t *) b->sval.p, (uint64_t *) b->socc.p, (uint64_t *) b->ssmer.p, (uint64_t *) b->sfp.p,
+                      pk, pk_alt, (uint64_t *) b->ids.p, (uint64_t *) b->starts.p, (uint64_t *) b->kid.p};
+        sort_repair5_kernel<<<std::min<unsigned>(nblk((uint64_t) cap * 32, 128), 148u * 16u), 128, 0, st>>>(R5, N, plow, cap, (uint32_t *) b->sort_fix.p);
+        sort_check_kernel<<<nblk(N, 256), 256, 0, st>>>((const uint64_t *) b->skey.p, N, plow, (uint32_t *) b->sort_fix.p);
+        ctx->count_launch(SG_T_SORT, 4);
+        uint32_t hf[2];
+        CK(cudaMemcpyAsync(hf, b->sort_fix.p, sizeof(hf), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        b->n_sort_repairs = hf[0];
+        b->sort_fell_back = false;
+        if (hf[1] == 0 && hf[0] <= cap) {
+            ctx->t_end(SG_T_SORT);
+            CK(cudaGetLastError());
+            b->sorted = true;
+            return SG_OK;
+        }
+        b->sort_fell_back = true;                             // too many or too long runs: the pair sort on all 64 bits below
+        full = true;
+    }
     for (int attempt = 0; attempt < 2; ++attempt) {
         tuple_init_kernel<<<nblk(N, 256), 256, 0, st>>>(b->t_key(), (uint64_t *) b->skey.p, (uint64_t *) b->sval.p, N, hmask);
         ctx->count_launch(SG_T_SORT, 1);
@@ -476,6 +608,14 @@ int sg_debug_set_sort_low_bits(sg_batch *b, int bits)
     return SG_OK;
 }
 
+int sg_debug_set_pack_bits(sg_batch *b, int bits)
+{
+    if (!b || bits < 8 || bits > 32 || (bits & 7)) return SG_E_ARG;
+    b->pack_bits = bits;
+    b->sorted = b->counted = false;
+    return SG_OK;
+}
+
 int sg_debug_sort_info(sg_batch *b, uint64_t *repairs, int *fell_back)
 {
     if (!b) return SG_E_ARG;
@@ -516,21 +656,48 @@ int sg_stat(sg_batch *b, sg_stat_t *out)
     // s-mer codes: no order is needed, only how often each distinct code occurs -> hash table
     // (the reference sorts all syncmers a second time for this, syncmer.c:916-926)
     if (N) {
-        uint64_t nslots = 1024;
-        while (nslots < 2 * N) nslots <<= 1;
-        RS(b->arc_keys, nslots * 8); RS(b->arc_vals, nslots * 4);
-        RS(b->stat_dev2, 1002 * 8);
-        b->smer_slots = nslots;
-        CK(cudaMemsetAsync(b->arc_keys.p, 0xff, nslots * 8, st));
-        CK(cudaMemsetAsync(b->arc_vals.p, 0, nslots * 4, st));
-        CK(cudaMemsetAsync(b->stat_dev2.p, 0, 1002 * 8, st));
-        // in k-mer hash order the occurrences of one k-mer (hence of its s-mer code) are neighbours: the warps merge
-        // them with one match_any before touching the table
-        key_tally_kernel<<<std::min<unsigned>(nblk(N, 256), 148u * 16u), 256, 0, st>>>((const uint64_t *) b->ssmer.p, N, (uint64_t *) b->arc_keys.p,
-                (uint32_t *) b->arc_vals.p, nslots - 1);
-        slot_hist_kernel<<<std::min<unsigned>(nblk(nslots, 256), 148u * 16u), 256, 0, st>>>((const uint64_t *) b->arc_keys.p,
-                (const uint32_t *) b->arc_vals.p, nslots, (unsigned long long *) b->stat_dev2.p);
-        ctx->count_launch(SG_T_STAT, 2);
+        // Syncmers of one genome share few s-mers (the minimum of a window survives most sequencing errors in it), so
+        // the table is first cut for N / 16 distinct codes: 48 MB at 21 M syncmers, resident in L2, where a table for
+        // the worst case (every code distinct) is 768 MB of DRAM probes. A tally that finds the small table crowded
+        // (a key without a free slot within four groups, or more than half of the slots taken) is repeated in the large one.
+        uint64_t nslots = 1024, nfull = 1024;
+        while (nfull < 2 * N) nfull <<= 1;
+        while (nslots < N / 8) nslots <<= 1;
+        if (nslots > nfull) nslots = nfull;
+        RS(b->stat_dev2, 1004 * 8);
+        bool tallied = false;
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            RS(b->arc_keys, nslots * 8); RS(b->arc_vals, nslots * 4);
+            b->smer_slots = nslots;
+            CK(cudaMemsetAsync(b->arc_keys.p, 0xff, nslots * 8, st));
+            CK(cudaMemsetAsync(b->arc_vals.p, 0, nslots * 4, st));
+            CK(cudaMemsetAsync(b->stat_dev2.p, 0, 1004 * 8, st));
+            // in k-mer hash order the occurrences of one k-mer (hence of its s-mer code) are neighbours: the warps merge
+            // them with one match_any before touching the table
+            if (nslots == nfull) {
+                key_tally_kernel<<<std::min<unsigned>(nblk(N, 256), 148u * 16u), 256, 0, st>>>((const uint64_t *) b->ssmer.p, N, (uint64_t *) b->arc_keys.p,
+                        (uint32_t *) b->arc_vals.p, nslots - 1);
+                ctx->count_launch(SG_T_STAT, 1);
+                break;
+            }
+            unsigned long long *flag = (unsigned long long *) b->stat_dev2.p + 1002;      // [1002] a key found no slot (low word)
+            key_tally_small_kernel<<<std::min<unsigned>(nblk(N, 256), 148u * 16u), 256, 0, st>>>((const uint64_t *) b->ssmer.p, N, (uint64_t *) b->arc_keys.p,
+                    (uint32_t *) b->arc_vals.p, nslots - 1, (unsigned int *) flag);
+            // the histogram pass counts the keys in the table as well ([1001]): no counter is hammered during the tally
+            slot_hist_kernel<<<std::min<unsigned>(nblk(nslots, 256), 148u * 16u), 256, 0, st>>>((const uint64_t *) b->arc_keys.p,
+                    (const uint32_t *) b->arc_vals.p, nslots, (unsigned long long *) b->stat_dev2.p);
+            ctx->count_launch(SG_T_STAT, 2);
+            unsigned long long hf[2];
+            CK(cudaMemcpyAsync(hf, (unsigned long long *) b->stat_dev2.p + 1001, sizeof(hf), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            if ((hf[1] & 0xffffffffull) == 0 && hf[0] <= nslots / 2) { tallied = true; break; }
+            nslots = nfull;
+        }
+        if (!tallied) {
+            slot_hist_kernel<<<std::min<unsigned>(nblk(nslots, 256), 148u * 16u), 256, 0, st>>>((const uint64_t *) b->arc_keys.p,
+                    (const uint32_t *) b->arc_vals.p, nslots, (unsigned long long *) b->stat_dev2.p);
+            ctx->count_launch(SG_T_STAT, 1);
+        }
         CK(cudaMemcpyAsync(d, b->stat_dev2.p, 1001 * 8, cudaMemcpyDeviceToDevice, st));
         CK(cudaMemcpyAsync(&gs, (unsigned long long *) b->stat_dev2.p + 1001, 8, cudaMemcpyDeviceToHost, st));
     }

@@ -62,6 +62,7 @@ struct sg_batch {
     sg::DevBuf kid;                              // read order: id << 1
     sg::DevBuf skey, sval, skey_alt, sval_alt, sort_tmp, sort_fix;
     int sort_low_bits = 24;                      // radix passes skip these low hash bits, a repair pass handles them (0: full sort)
+    int pack_bits = 32;                          // hash bits the packed (hash-top | index) sort orders; a repair pass handles the rest
     bool sort_fell_back = false;
     bool keys_are_ids = false;                   // sg_batch_set_lists_host: key[] holds id << 1 | corrected, not hashes
     uint64_t n_sort_repairs = 0;                 // out-of-order pairs the repair pass saw

@@ -214,6 +214,68 @@ __global__ void __launch_bounds__(RS_NT) rs_scatter_kernel(const uint64_t *key, 
     }
 }
 
+// keys only (the value rides in the low bits of the key word): same stable scatter, half the traffic
+__global__ void __launch_bounds__(RS_NT) rs_scatter_keys_kernel(const uint64_t *key, uint64_t *okey, uint64_t n, int shift, const uint32_t *offsets, uint32_t ntiles)
+{
+    __shared__ uint32_t wc[RS_NW][RS_BINS];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < RS_NW * RS_BINS; i += RS_NT) (&wc[0][0])[i] = 0;
+    __syncthreads();
+    const uint64_t wbase = (uint64_t) blockIdx.x * RS_TILE + (uint64_t) wid * 32 * RS_IPT;
+    uint64_t kreg[RS_IPT];
+    uint32_t rank[RS_IPT];
+#pragma unroll
+    for (int j = 0; j < RS_IPT; ++j) {
+        const uint64_t i = wbase + (uint64_t) j * 32 + lane;
+        const bool ok = i < n;
+        kreg[j] = ok ? key[i] : 0;
+        const uint32_t d = ok ? (uint32_t) ((kreg[j] >> shift) & 0xFFu) : 0x100u;
+        const uint32_t peers = __match_any_sync(SG_FULL, d);
+        const uint32_t before = __popc(peers & ((1u << lane) - 1u));
+        uint32_t base = 0;
+        if (ok) base = wc[wid][d];
+        __syncwarp();
+        if (ok && before == 0) wc[wid][d] = base + __popc(peers);
+        __syncwarp();
+        rank[j] = base + before;
+    }
+    __syncthreads();
+    {
+        uint32_t run = offsets[(uint64_t) threadIdx.x * ntiles + blockIdx.x];
+#pragma unroll
+        for (int w = 0; w < RS_NW; ++w) { uint32_t t = wc[w][threadIdx.x]; wc[w][threadIdx.x] = run; run += t; }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < RS_IPT; ++j) {
+        const uint64_t i = wbase + (uint64_t) j * 32 + lane;
+        if (i < n) okey[(uint64_t) wc[wid][(uint32_t) ((kreg[j] >> shift) & 0xFFu)] + rank[j]] = kreg[j];
+    }
+}
+
+// stable LSD radix sort of 64-bit words on bits [begin_bit, end_bit); the result ends in `key`
+int launch_sort_keys(uint64_t *key, uint64_t *key_alt, uint64_t n, int begin_bit, int end_bit, uint32_t *tmp, cudaStream_t st)
+{
+    if (n == 0) return 0;
+    const uint32_t ntiles = (uint32_t) ((n + RS_TILE - 1) / RS_TILE);
+    const uint64_t m = (uint64_t) ntiles * RS_BINS;
+    const uint64_t nb = (m + SCAN_TILE - 1) / SCAN_TILE;
+    uint32_t *counts = tmp, *sums = tmp + m;
+    int launches = 0, passes = 0;
+    uint64_t *k0 = key, *k1 = key_alt;
+    for (int shift = begin_bit; shift < end_bit; shift += 8, ++passes) {
+        rs_hist_kernel<<<ntiles, RS_NT, 0, st>>>(k0, n, shift, counts, ntiles);
+        rs_scan_reduce<<<(unsigned) nb, SCAN_NT, 0, st>>>(counts, m, sums);
+        rs_scan_sums<<<1, 1024, 0, st>>>(sums, nb);
+        rs_scan_apply<<<(unsigned) nb, SCAN_NT, 0, st>>>(counts, m, sums);
+        rs_scatter_keys_kernel<<<ntiles, RS_NT, 0, st>>>(k0, k1, n, shift, counts, ntiles);
+        launches += 5;
+        uint64_t *t = k0; k0 = k1; k1 = t;
+    }
+    if (passes & 1) cudaMemcpyAsync(key, k0, n * sizeof(uint64_t), cudaMemcpyDeviceToDevice, st);
+    return launches;
+}
+
 size_t sort_tmp_words(uint64_t n)
 {
     const uint64_t ntiles = (n + RS_TILE - 1) / RS_TILE;

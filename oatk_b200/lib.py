@@ -60,7 +60,7 @@ SYMBOLS = [
     "sg_batch_create", "sg_batch_destroy", "sg_batch_set_reads_host", "sg_batch_set_reads_device",
     "sg_batch_set_sid_base", "sg_extract", "sg_extract_sizes", "sg_extract_download",
     "sg_stat", "sg_stat_multiplicities", "sg_count", "sg_count_sizes", "sg_count_download", "sg_arcs", "sg_arcs_download",
-    "sg_tuples_partition", "sg_tuples_adopt", "sg_debug_set_hash_bits", "sg_debug_set_sort_low_bits", "sg_debug_sort_info", "sg_debug_scan_info", "sg_batch_buffer",
+    "sg_tuples_partition", "sg_tuples_adopt", "sg_debug_set_hash_bits", "sg_debug_set_sort_low_bits", "sg_debug_sort_info", "sg_debug_set_pack_bits", "sg_debug_scan_info", "sg_batch_buffer",
     "sg_ids_pack", "sg_ids_scatter", "sg_batch_set_exact_verify", "sg_smer_counts_pack", "sg_smer_counts_merge", "sg_batch_set_lists_host",
     "sg_comm_unique_id", "sg_comm_init_rank", "sg_comm_init_all", "sg_comm_destroy", "sg_comm_rank", "sg_comm_world", "sg_comm_bytes_sent",
     "sg_comm_exchange_tuples", "sg_comm_global_stat", "sg_comm_return_ids", "sg_comm_arcs",
@@ -105,7 +105,7 @@ def _lib():
                        ("sg_arcs", [vp, C.c_uint32, C.c_double, C.POINTER(u64)]), ("sg_arcs_download", [vp, vp]),
                        ("sg_tuples_partition", [vp, i32, vp, C.POINTER(vp)]), ("sg_tuples_adopt", [vp, vp, u64]),
                        ("sg_debug_set_hash_bits", [vp, i32]), ("sg_debug_set_sort_low_bits", [vp, i32]),
-                       ("sg_debug_sort_info", [vp, C.POINTER(u64), C.POINTER(i32)]), ("sg_debug_scan_info", [vp, C.POINTER(u64)]), ("sg_batch_buffer", [vp, i32, C.POINTER(vp), C.POINTER(u64)]),
+                       ("sg_debug_sort_info", [vp, C.POINTER(u64), C.POINTER(i32)]), ("sg_debug_set_pack_bits", [vp, i32]), ("sg_debug_scan_info", [vp, C.POINTER(u64)]), ("sg_batch_buffer", [vp, i32, C.POINTER(vp), C.POINTER(u64)]),
                        ("sg_ids_pack", [vp, u64, C.POINTER(vp), C.POINTER(u64)]), ("sg_smer_counts_pack", [vp, C.POINTER(vp), C.POINTER(u64)]),
                        ("sg_smer_counts_merge", [vp, vp, u64, vp]), ("sg_ids_scatter", [vp, vp, u64]), ("sg_batch_set_exact_verify", [vp, i32])):
         if hasattr(L, name):
@@ -327,6 +327,9 @@ class Batch:
 
     def debug_set_sort_low_bits(self, bits):
         _ck(self.ctx.h, _lib().sg_debug_set_sort_low_bits(self.h, bits), "sg_debug_set_sort_low_bits")
+
+    def debug_set_pack_bits(self, bits):
+        _ck(self.ctx.h, _lib().sg_debug_set_pack_bits(self.h, bits), "sg_debug_set_pack_bits")
 
     def debug_sort_info(self):
         r, f = C.c_uint64(0), C.c_int(0)

@@ -133,3 +133,29 @@ def test_partial_sort_and_repair(gpu_ctx, oracle, low_bits, expect):
         assert fell_back
     oracle.free(db, exp)
     b.close()
+
+
+@pytest.mark.parametrize("bits,expect", [(32, "none"), (16, "repair"), (8, "repair")])
+def test_packed_sort_and_repair(gpu_ctx, oracle, bits, expect):
+    """the default sort orders (top hash bits | tuple index) words and repairs the runs that differ below; with 16 or 8
+    bits in the word nearly every tuple sits in such a run, so the five-array repair does real work. The order, ids and
+    occurrence lists must not depend on where the split is."""
+    reads = synth.hifi_reads(12, 100000, 300, 15000, 0.001) + synth.adversarial_reads(5, 101, 11)
+    bases, off = pack_reads(reads)
+    db, _ = oracle.extract(bases, off, 101, 11)
+    exp = oracle.collect(db, len(reads), 64)
+    b = gpu_batch(gpu_ctx, bases, off, 101, 11)
+    b.debug_set_pack_bits(bits)
+    st = b.stat()
+    b.count()
+    got = b.count_download()
+    repairs, fell_back = b.debug_sort_info()
+    d = parity.diff(got, exp, parity.SCM_FIELDS)
+    assert not d, "\n".join(d)
+    rc, dd, ii, sc, kc = oracle.stat(db)
+    assert np.array_equal(np.array(st.kmer_cnts[:]), kc) and np.array_equal(np.array(st.smer_cnts[:]), sc)
+    assert not fell_back
+    if expect == "repair":
+        assert repairs > 0
+    oracle.free(db, exp)
+    b.close()
