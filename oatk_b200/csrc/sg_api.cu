@@ -143,6 +143,7 @@ static void reset_state(sg_batch *b)
     b->lrl_sorted = false;
     b->keys_are_ids = false;
     b->tup_valid = false;
+    b->atup_valid = false;
     b->k = b->s = 0;
     b->n_syncmers = 0;
 }

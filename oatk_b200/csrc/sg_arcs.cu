@@ -112,11 +112,13 @@ __global__ void __launch_bounds__(256) part_gather_kernel(const uint64_t *pkey, 
     if (i == n - 1 || pkey[i + 1] != pkey[i]) atomicMax(counts + pkey[i], (unsigned long long) (i + 1));   // end offset of this part
 }
 
-__global__ void __launch_bounds__(256) adopt_kernel(const uint64_t *tuples, uint64_t n, uint64_t *key, uint64_t *occ, uint64_t *smer, uint64_t *fp)
+__global__ void __launch_bounds__(256) adopt_kernel(const uint64_t *tuples, uint64_t n, uint64_t *key, uint64_t *occ, uint64_t *smer, uint64_t *fp, ulonglong4 *rec)
 {
     const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    key[i] = tuples[4 * i]; occ[i] = tuples[4 * i + 1]; smer[i] = tuples[4 * i + 2]; fp[i] = tuples[4 * i + 3];
+    const uint64_t h = tuples[4 * i], o = tuples[4 * i + 1], sm = tuples[4 * i + 2], f = tuples[4 * i + 3];   // (hash, occurrence, s-mer code, fingerprint)
+    key[i] = h; occ[i] = o; smer[i] = sm; fp[i] = f;
+    rec[i] = make_ulonglong4(o, sm, f, h);                             // the record layout of kmerhash_kernel: the packed sort of sg_count gathers from it
 }
 
 // ids coming back from the GPU that owns the hash range: pairs (occ, id << 1) for occurrences on local reads
@@ -351,11 +353,15 @@ int sg_tuples_adopt(sg_batch *b, const void *d_tuples, uint64_t n)
     CK(cudaSetDevice(ctx->device));
     // keep the local read-order arrays for the id write-back; the tuple set being counted is replaced
     RS(b->akey, (n + 1) * 8); RS(b->aocc, (n + 1) * 8); RS(b->asmer, (n + 1) * 8); RS(b->afp, (n + 1) * 8);
+    RS(b->tup, (n + 1) * 32);                                      // the records of the local extract are not needed again before the next one
+    b->tup_valid = false;
     if (n) {
-        adopt_kernel<<<nblk(n, 256), 256, 0, st>>>((const uint64_t *) d_tuples, n, (uint64_t *) b->akey.p, (uint64_t *) b->aocc.p, (uint64_t *) b->asmer.p, (uint64_t *) b->afp.p);
+        adopt_kernel<<<nblk(n, 256), 256, 0, st>>>((const uint64_t *) d_tuples, n, (uint64_t *) b->akey.p, (uint64_t *) b->aocc.p, (uint64_t *) b->asmer.p,
+                (uint64_t *) b->afp.p, (ulonglong4 *) b->tup.p);
         ctx->count_launch(SG_T_SORT, 1);
     }
     CK(cudaGetLastError());
+    b->atup_valid = true;
     b->adopted = true;
     b->n_adopted = n;
     b->sorted = b->counted = false;

@@ -501,7 +501,7 @@ static int ensure_sorted(sg_batch *b)
     bool full = b->hash_bits < 64 || SORT_LOW_BITS == 0;     // truncated hashes (tests) collide by design
     // the ordinary case: whole hashes, records of this batch's own extract, fewer than 2^32 tuples (the index shares a word
     // with the top half of the hash)
-    if (!full && SORT_LOW_BITS == 24 && b->tup_valid && !b->adopted && !b->keys_are_ids && N < (1ull << 32) && !getenv("SG_SORT_PAIRS")) {
+    if (!full && SORT_LOW_BITS == 24 && (b->adopted ? b->atup_valid : b->tup_valid) && !b->keys_are_ids && N < (1ull << 32) && !getenv("SG_SORT_PAIRS")) {
         const uint32_t cap = (uint32_t) std::min<uint64_t>(N / 64 + SORT_FIX_CAP, 1u << 26);
         RS(b->sort_fix, ((size_t) cap + 2) * 4);
         uint64_t *pk = (uint64_t *) b->skey_alt.p, *pk_alt = (uint64_t *) b->sval_alt.p;
