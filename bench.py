@@ -205,6 +205,7 @@ def main():
     ap.add_argument("--no-config3", action="store_true", help="skip the configs[3] line (10 M reads over 8 GPUs; runs only at 8 GPUs)")
     ap.add_argument("--no-whole", action="store_true", help="skip the configs[2] line (whole syncasm command on 200 k reads; one GPU only)")
     ap.add_argument("--whole-reads", type=int, default=200000)
+    ap.add_argument("--config3-reads", type=int, default=0, help="run the configs[3] line with this many reads in all at any N > 1 (default: 10 M, at 8 GPUs only)")
     args = ap.parse_args()
     globals()["K"], globals()["ERR"] = args.k, args.err
     if args.impl == "reference":
@@ -350,12 +351,13 @@ def main():
 
     # configs[3]: ONE read set of 10 M x 15 kb reads in contiguous blocks over 8 GPUs, global ids checked on a sample
     config3 = None
-    if not args.no_config3 and world == 8 and args.workload == "uniform":
-        n3 = 10_000_000 // world
+    if not args.no_config3 and args.workload == "uniform" and ((world == 8 and not args.config3_reads) or (world > 1 and args.config3_reads)):
+        n3 = (args.config3_reads or 10_000_000) // world
         b3, o3 = synth_gpu.hifi_reads_gpu(3000 + rank, 500_000_000, n3, READ_LEN, ERR, dev, genome_seed=3)
         batch.set_sid_base(rank * n3)
         config3 = timed(None, (b3, o3, n3, n3 * READ_LEN), 2)
-        config3["workload"] = "BASELINE.json configs[3]: 10 M x %d b reads of a 500 Mb genome, %d per GPU in contiguous blocks, tuple exchange + id return over NCCL" % (READ_LEN, n3)
+        config3["workload"] = "BASELINE.json configs[3]: %d x %d b reads of a 500 Mb genome, %d per GPU in contiguous blocks, tuple exchange + id return over NCCL" % (
+            n3 * world, READ_LEN, n3)
         config3["global_ids_sample_check"] = check_global_ids(torch, dist, batch, comm, rank, world, dev, n3)
         batch.set_sid_base(rank * n_reads)
         del b3, o3
