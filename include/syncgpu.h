@@ -150,6 +150,20 @@ typedef struct {
 } sg_ec_result_t;
 int sg_ec_correct(sg_batch *b, const sg_ec_graph_t *g, double max_edist, sg_ec_result_t *res);
 void sg_ec_result_free(sg_ec_result_t *res);
+/* The error filter of read error correction on the device (reference find_error_syncmers, syncerr.c:679-757): runs
+ * sg_arcs(b, 0, 0) -- the arcs of the all-syncmer graph, which never have to become a host graph -- flags the suspect
+ * syncmers (coverage below err_mer_c, or below max_err_c with a side whose arcs are all unreliable) and returns the arcs
+ * both of whose ends survive, in the list's (v, w, comp) order. del_prev: syncmer_t.del on entry, or NULL for none. */
+typedef struct {
+    uint64_t n_syncmers;            /* entries of err */
+    uint8_t *err;                   /* 1: suspect (malloc'ed) */
+    uint64_t n_arcs_all;            /* arcs before the filter */
+    uint64_t n_live;                /* arcs left */
+    uint64_t *arcs4;                /* v, w, cov, comp per live arc (malloc'ed) */
+} sg_ec_filter_out_t;
+int sg_ec_filter(sg_batch *b, const uint8_t *del_prev, uint32_t err_mer_c, uint32_t max_err_c, uint32_t err_arc_c, double max_arc_f,
+        sg_ec_filter_out_t *out);
+void sg_ec_filter_free(sg_ec_filter_out_t *out);
 /* test hook: vertices per path and stacked wavefront entries of the first-pass search arena (default 256 / 16384) */
 int sg_debug_set_ec_arena(uint32_t path, uint32_t stash);
 

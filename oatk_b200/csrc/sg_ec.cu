@@ -37,6 +37,9 @@
 #include <vector>
 #include <algorithm>
 #include <cmath>
+#include <ctime>
+#include <cstdio>
+#include <cstdlib>
 #include "sg_common.cuh"
 #include "sg_internal.h"
 #include "sg_host.h"
@@ -468,6 +471,59 @@ __global__ void __launch_bounds__(32 * EC_WARPS) ec_read_kernel(EcArgs A)
     if (lane == 0) for (int i = 0; i < 11; ++i) if (st[i]) atomicAdd(A.stats + i, (unsigned long long) st[i]);
 }
 
+// ---- the error filter (syncerr.c:679-757) over the device-resident arc list -------------------------------------------
+// A syncmer is suspect when its coverage is below err_mer_c, or -- below max_err_c -- when one of its two sides has arcs
+// but none with coverage >= err_arc_c and >= max_arc_f * min(cov, cov') (the product in double precision, as the
+// reference writes it). Arcs are the (v, w, cov, comp) records sg_arcs leaves sorted by (v, w, comp): the arcs of an
+// oriented vertex are found by bisection. One thread per syncmer; most leave at the first test.
+__device__ __forceinline__ uint64_t arc4_lower(const uint64_t *arcs4, uint64_t n, uint64_t v)
+{
+    uint64_t lo = 0, hi = n;
+    while (lo < hi) { const uint64_t mid = (lo + hi) >> 1; if (arcs4[4 * mid] < v) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+__global__ void __launch_bounds__(256) ec_filter_kernel(const uint64_t *arcs4, uint64_t n_arc, const uint32_t *cov, const uint8_t *del_prev, uint64_t n_scm,
+        uint32_t err_mer_c, uint32_t max_err_c, uint32_t err_arc_c, double max_arc_f, uint8_t *err)
+{
+    const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_scm) return;
+    uint8_t e = 0;
+    const uint32_t cv = cov[i];
+    if (!(del_prev && del_prev[i]) && cv < max_err_c) {
+        if (cv < err_mer_c) e = 1;
+        else {
+            int side_ok[2] = {-1, -1};
+            for (int side = 0; side < 2; ++side) {
+                const uint64_t v = i << 1 | (uint64_t) side;
+                uint64_t a = arc4_lower(arcs4, n_arc, v);
+                if (a >= n_arc || arcs4[4 * a] != v) continue;                 // no arc on that side
+                side_ok[side] = 0;
+                for (; a < n_arc && arcs4[4 * a] == v; ++a) {
+                    const uint32_t ac = (uint32_t) arcs4[4 * a + 2], cw = cov[arcs4[4 * a + 1] >> 1];
+                    if (ac >= err_arc_c && (double) ac >= (double) (cv < cw ? cv : cw) * max_arc_f) { side_ok[side] = 1; break; }
+                }
+            }
+            if (!side_ok[0] || !side_ok[1]) e = 1;
+        }
+    }
+    err[i] = e;
+}
+// an arc survives when neither end is suspect or was deleted before
+__global__ void __launch_bounds__(256) ec_live_flag_kernel(const uint64_t *arcs4, uint64_t n_arc, const uint8_t *err, const uint8_t *del_prev, uint32_t *flag)
+{
+    const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_arc) return;
+    const uint64_t v = arcs4[4 * i] >> 1, w = arcs4[4 * i + 1] >> 1;
+    flag[i] = (err[v] || err[w] || (del_prev && (del_prev[v] || del_prev[w]))) ? 0u : 1u;
+}
+__global__ void __launch_bounds__(256) ec_live_pack_kernel(const uint64_t *arcs4, uint64_t n_arc, const uint32_t *flag, const uint64_t *ex, uint64_t *out4)
+{
+    const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_arc || !flag[i]) return;
+    const uint64_t o = ex[i];
+    out4[4 * o] = arcs4[4 * i]; out4[4 * o + 1] = arcs4[4 * i + 1]; out4[4 * o + 2] = arcs4[4 * i + 2]; out4[4 * o + 3] = arcs4[4 * i + 3];
+}
+
 } // namespace sg
 
 using namespace sg;
@@ -509,7 +565,8 @@ extern "C" int sg_ec_correct(sg_batch *b, const sg_ec_graph_t *g, double max_edi
     const int k = b->k;
     const int bw_max = std::max<int>(EC_MIN_BAND, (int) std::ceil(max_l * max_edist));
 
-    sg::DevBuf d_del, d_av, d_aw, d_at, d_al, d_arena, d_outk, d_outp, d_off, d_n, d_misc, d_over;
+    sg::DevBuf &d_del = b->ec_del, &d_av = b->ec_av, &d_aw = b->ec_aw, &d_at = b->ec_at, &d_al = b->ec_al, &d_arena = b->ec_arena, &d_outk = b->ec_outk,
+        &d_outp = b->ec_outp, &d_off = b->ec_off, &d_n = b->ec_n, &d_misc = b->ec_misc, &d_over = b->ec_over;
 #define RSV(buf, bytes) do { if ((buf).reserve(bytes)) { ctx->err = "device allocation failed in sg_ec_correct"; return SG_E_NOMEM; } } while (0)
     RSV(d_del, g->n_syncmers + 16); RSV(d_av, g->n_arcs * 8 + 16); RSV(d_aw, g->n_arcs * 8 + 16); RSV(d_at, g->n_arcs * 8 + 16); RSV(d_al, g->n_arcs * 4 + 16);
     CK(cudaMemcpyAsync(d_del.p, g->del, g->n_syncmers, cudaMemcpyHostToDevice, st));
@@ -620,6 +677,74 @@ extern "C" int sg_ec_correct(sg_batch *b, const sg_ec_graph_t *g, double max_edi
     CK(cudaStreamSynchronize(st));
     b->d2h_bytes += n_reads * 12 + n_out * 12;
     return SG_OK;
+}
+
+
+// The error filter on the device: sg_arcs(b, 0, 0) (the all-syncmer graph's arcs) must be what the batch holds, which
+// this call makes sure of itself. Returns the suspect flags and what is left of the arc list, in the list's order.
+extern "C" int sg_ec_filter(sg_batch *b, const uint8_t *del_prev, uint32_t err_mer_c, uint32_t max_err_c, uint32_t err_arc_c, double max_arc_f,
+        sg_ec_filter_out_t *out)
+{
+    if (!b || !out) return SG_E_ARG;
+    if (!b->counted || b->adopted) return SG_E_STATE;
+    sg_ctx *ctx = b->ctx;
+    cudaStream_t st = ctx->stream;
+    CK(cudaSetDevice(ctx->device));
+    memset(out, 0, sizeof(*out));
+    uint64_t na = 0;
+    const bool dbg = getenv("SG_EC_TIMING") != nullptr;
+    auto now = []() { timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec + 1e-9 * t.tv_nsec; };
+    double t0 = now();
+    int rc = sg_arcs(b, 0, 0.0, &na);
+    if (rc) return rc;
+    if (dbg) { fprintf(stderr, "[sg_ec_filter] sg_arcs %.3f s (%llu arcs)\n", now() - t0, (unsigned long long) na); t0 = now(); }
+    const uint64_t U = b->n_unique;
+    out->n_syncmers = U;
+    sg::DevBuf &d_err = b->ec_err, &d_prev = b->ec_prev, &d_flag = b->ec_flag, &d_ex = b->ec_ex, &d_tmp = b->ec_tmp, &d_live = b->ec_live;
+    if (d_err.reserve(U + 16) || d_flag.reserve((na + 1) * 4) || d_ex.reserve((na + 2) * 8) || d_tmp.reserve(scan_tmp_words(na) * 8) || (del_prev && d_prev.reserve(U + 16))) {
+        ctx->err = "device allocation failed in sg_ec_filter"; return SG_E_NOMEM;
+    }
+    if (del_prev) CK(cudaMemcpyAsync(d_prev.p, del_prev, U, cudaMemcpyHostToDevice, st));
+    if (dbg) { fprintf(stderr, "[sg_ec_filter] allocations %.3f s\n", now() - t0); t0 = now(); }
+    ctx->t_begin(SG_T_EC);
+    if (U) ec_filter_kernel<<<(unsigned) ((U + 255) / 256), 256, 0, st>>>((const uint64_t *) b->arc_out.p, na, (const uint32_t *) b->scm_cov.p,
+            del_prev ? (const uint8_t *) d_prev.p : nullptr, U, err_mer_c, max_err_c, err_arc_c, max_arc_f, (uint8_t *) d_err.p);
+    uint64_t n_live = 0;
+    if (na) {
+        ec_live_flag_kernel<<<(unsigned) ((na + 255) / 256), 256, 0, st>>>((const uint64_t *) b->arc_out.p, na, (const uint8_t *) d_err.p,
+                del_prev ? (const uint8_t *) d_prev.p : nullptr, (uint32_t *) d_flag.p);
+        int nl = launch_scan_u32_u64((const uint32_t *) d_flag.p, (uint64_t *) d_ex.p, na, (uint64_t *) d_tmp.p, st);
+        if (nl < 0) return nl;
+        ctx->count_launch(SG_T_EC, nl + 1);
+        CK(cudaMemcpyAsync(&n_live, (uint64_t *) d_ex.p + na, 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (d_live.reserve((n_live + 1) * 32)) { ctx->err = "device allocation failed in sg_ec_filter"; return SG_E_NOMEM; }
+        ec_live_pack_kernel<<<(unsigned) ((na + 255) / 256), 256, 0, st>>>((const uint64_t *) b->arc_out.p, na, (const uint32_t *) d_flag.p,
+                (const uint64_t *) d_ex.p, (uint64_t *) d_live.p);
+        ctx->count_launch(SG_T_EC, 1);
+    }
+    ctx->count_launch(SG_T_EC, 1);
+    ctx->t_end(SG_T_EC);
+    out->err = (uint8_t *) malloc(U ? U : 1);
+    out->arcs4 = (uint64_t *) malloc((n_live + 1) * 32);
+    if (!out->err || !out->arcs4) { sg_ec_filter_free(out); return SG_E_NOMEM; }
+    if (U) CK(cudaMemcpyAsync(out->err, d_err.p, U, cudaMemcpyDeviceToHost, st));
+    if (n_live) CK(cudaMemcpyAsync(out->arcs4, d_live.p, n_live * 32, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    if (dbg) { fprintf(stderr, "[sg_ec_filter] kernels + download %.3f s\n", now() - t0); t0 = now(); }
+    out->n_arcs_all = na;
+    out->n_live = n_live;
+    b->h2d_bytes += del_prev ? U : 0;
+    b->d2h_bytes += U + n_live * 32;
+    return SG_OK;
+}
+
+extern "C" void sg_ec_filter_free(sg_ec_filter_out_t *o)
+{
+    if (!o) return;
+    free(o->err); free(o->arcs4);
+    o->err = 0; o->arcs4 = 0;
 }
 
 extern "C" void sg_ec_result_free(sg_ec_result_t *r)

@@ -86,6 +86,8 @@ struct sg_batch {
     bool rl_resident = false;                    // ho_rl (capacity layout) and the long-run side list are on the device: sg_runlen_sums works
     bool lrl_sorted = false;                     // lrl_key / lrl_sval hold the side list ordered by (read, hoco index)
     sg::DevBuf lrl_key, lrl_sval, lrl_key_alt, lrl_val_alt, rq_off, rq_occ, rq_out;
+    // f2 (sg_ec_filter / sg_ec_correct): kept with the batch, because cudaMalloc / cudaFree per call cost more than the kernels
+    sg::DevBuf ec_del, ec_av, ec_aw, ec_at, ec_al, ec_arena, ec_outk, ec_outp, ec_off, ec_n, ec_misc, ec_over, ec_err, ec_prev, ec_flag, ec_ex, ec_tmp, ec_live;
     uint64_t n_adopted = 0;
     // the tuple set a5/a6 work on
     const uint64_t *t_key() const { return (const uint64_t *) (adopted ? akey.p : key.p); }

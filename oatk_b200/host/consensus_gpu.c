@@ -482,6 +482,59 @@ static void cons_run(cons_job_t *J, int phase, uint64_t n_items)
     for (long i = 0; i < nt; ++i) pthread_join(th[i], 0);
 }
 
+/* run-length sums already fetched from the device for the syncmers of one read database (see scg_consensus) */
+static struct { const sr_db_t *db; size_t n_scm; int64_t *row_of; uint64_t *sums; uint32_t *copies; uint64_t n_rows; } g_rl;
+void oatk_cons_cache_drop(const sr_db_t *db)
+{
+    if (db && g_rl.db != db) return;
+    free(g_rl.row_of); free(g_rl.sums); free(g_rl.copies);
+    memset(&g_rl, 0, sizeof(g_rl));
+}
+
+/* Overlaps (asmg_arc_t.ls) of a list of arcs between single-syncmer vertices in homopolymer-compressed space, exactly as
+ * scg_consensus(sr_db, scg, 1, ...) leaves them on the all-syncmer graph: for every arc that is not flagged as a
+ * complement the most frequent start distance l of the two syncmers over the reads that carry both (neighbour_offset),
+ * overlap = k - l when l < k, else 0, clipped to k; the value also goes to the FIRST arc (w^1, v^1) of the list -- in
+ * list order, so that arcs nobody points at (a palindromic pair's second entry) keep 0 like they do there. The arcs must
+ * be sorted by (v, w). Used by the graph-free form of read error correction (syncerr_gpu.c). */
+typedef struct { const sr_db_t *db; const syncmer_t *scm; const uint64_t *arcs4; int64_t *l; } ovl_job_t;
+static void ovl_range(uint64_t lo, uint64_t hi, void *arg)
+{
+    ovl_job_t *J = (ovl_job_t *) arg;
+    const int w = J->db->k;
+    ovl_tab_t tab;
+    memset(&tab, 0, sizeof(tab));
+    for (uint64_t i = lo; i < hi; ++i) {
+        const uint64_t x = J->arcs4[4 * i], y = J->arcs4[4 * i + 1];
+        if (J->arcs4[4 * i + 3]) { J->l[i] = -1; continue; }        /* complement */
+        int64_t l = neighbour_offset(J->db, &J->scm[x >> 1], x & 1, &J->scm[y >> 1], y & 1, &tab, 0);
+        if (l < w) l = syncmer_text(J->db, &J->scm[x >> 1], (int) (x & 1), l, 0, 1, 0, x >> 1);
+        else l = 0;
+        if (l > w) l = w;
+        J->l[i] = l;
+    }
+    ot_free(&tab);
+}
+
+void oatk_syncmer_arc_overlaps(sr_db_t *sr_db, syncmer_db_t *scm_db, uint64_t n, const uint64_t *arcs4, uint32_t *ls)
+{
+    ovl_job_t J = {sr_db, scm_db->a, arcs4, (int64_t *) malloc(sizeof(int64_t) * (n ? n : 1))};
+    oatk_parallel_for(n, ovl_range, &J);
+    for (uint64_t i = 0; i < n; ++i) ls[i] = 0;
+    for (uint64_t i = 0; i < n; ++i) {
+        if (J.l[i] < 0) continue;
+        ls[i] = (uint32_t) J.l[i];
+        const uint64_t mv = arcs4[4 * i + 1] ^ 1, mw = arcs4[4 * i] ^ 1;
+        uint64_t lo = 0, hi = n;
+        while (lo < hi) {                                            /* first arc with (v, w) >= (mv, mw) */
+            const uint64_t mid = (lo + hi) >> 1;
+            if (arcs4[4 * mid] < mv || (arcs4[4 * mid] == mv && arcs4[4 * mid + 1] < mw)) lo = mid + 1; else hi = mid;
+        }
+        if (lo < n && arcs4[4 * lo] == mv && arcs4[4 * lo + 1] == mw) ls[lo] = (uint32_t) J.l[i];
+    }
+    free(J.l);
+}
+
 void scg_consensus(sr_db_t *sr_db, scg_t *scg, int hoco_seq, int save_seq, FILE *fo)
 {
     asmg_t *G = scg->utg_asmg;
@@ -498,48 +551,68 @@ void scg_consensus(sr_db_t *sr_db, scg_t *scg, int hoco_seq, int save_seq, FILE 
     J.cov = (double *) calloc(G->n_vtx ? G->n_vtx : 1, sizeof(double));
     J.ovl = (int64_t *) calloc(G->n_arc ? G->n_arc : 1, sizeof(int64_t));
 
-    /* run lengths that stayed on the device: one request for every syncmer on a live unitig, answered by sg_runlen_sums */
+    /* run lengths that stayed on the device: one request for every syncmer on a live unitig that was not asked for before,
+     * answered by sg_runlen_sums. The sums of a syncmer depend on the reads' lists only, and syncasm() calls this function
+     * three times on graphs made of the same syncmers (.utg.gfa, after unzipping, .utg.final.gfa), so the answers are kept
+     * until the lists change (g_rl: dropped by oatk_cons_cache_drop from read_error_correction and sr_db_clean). */
     rl_table_t rlt;
-    int64_t *row_of = 0;
-    uint64_t *sums = 0;
-    uint32_t *copies = 0;
     if (!hoco_seq && oatk_gpu_run_lengths_on_device(sr_db)) {
         const syncmer_t *scm = scg->scm_db->a;
-        uint64_t n_req = 0, n_occ = 0, j, *ids, *occ_off, *occ;
-        row_of = (int64_t *) malloc(sizeof(int64_t) * (scg->scm_db->n ? scg->scm_db->n : 1));
-        for (j = 0; j < scg->scm_db->n; ++j) row_of[j] = -1;
+        const size_t n_scm = scg->scm_db->n;
+        uint64_t n_new = 0, n_occ = 0, j, *ids, *occ_off, *occ;
+        if (g_rl.db != sr_db || g_rl.n_scm != n_scm) {
+            oatk_cons_cache_drop(0);
+            g_rl.db = sr_db; g_rl.n_scm = n_scm;
+            g_rl.row_of = (int64_t *) malloc(sizeof(int64_t) * (n_scm ? n_scm : 1));
+            for (j = 0; j < n_scm; ++j) g_rl.row_of[j] = -1;
+        }
+        const uint64_t row0 = g_rl.n_rows;
+        ids = 0;
+        uint64_t m_ids = 0;
         for (i = 0; i < G->n_vtx; ++i) {
             const asmg_vtx_t *u = &G->vtx[i];
             if (u->del) continue;
-            for (j = 0; j < u->n; ++j) if (row_of[u->a[j] >> 1] < 0) { row_of[u->a[j] >> 1] = (int64_t) n_req++; n_occ += scm[u->a[j] >> 1].cov; }
-        }
-        ids = (uint64_t *) malloc(sizeof(uint64_t) * (n_req ? n_req : 1));
-        for (j = 0; j < scg->scm_db->n; ++j) if (row_of[j] >= 0) ids[row_of[j]] = j;
-        occ_off = (uint64_t *) malloc(sizeof(uint64_t) * (n_req + 1));
-        occ = (uint64_t *) malloc(sizeof(uint64_t) * (n_occ ? n_occ : 1));
-        copies = (uint32_t *) malloc(sizeof(uint32_t) * (n_req ? n_req : 1));
-        n_occ = 0;
-        for (j = 0; j < n_req; ++j) {
-            const syncmer_t *m = &scm[ids[j]];
-            occ_off[j] = n_occ;
-            for (uint32_t c = 0; c < m->cov; ++c) {
-                if (occ_is_corrected(sr_db, m->m_pos[c])) continue;
-                occ[n_occ++] = (m->m_pos[c] >> 32) << 32 | sr_db->a[m->m_pos[c] >> 32].m_pos[m->m_pos[c] >> 1 & MAX_RD_SCM];
+            for (j = 0; j < u->n; ++j) {
+                const uint64_t id = u->a[j] >> 1;
+                if (g_rl.row_of[id] >= 0) continue;
+                g_rl.row_of[id] = (int64_t) (row0 + n_new);
+                if (n_new == m_ids) { m_ids = m_ids ? m_ids * 2 : 1024; ids = (uint64_t *) realloc(ids, sizeof(uint64_t) * m_ids); }
+                ids[n_new++] = id;
+                n_occ += scm[id].cov;
             }
-            copies[j] = (uint32_t) (n_occ - occ_off[j]);
         }
-        occ_off[n_req] = n_occ;
-        sums = (uint64_t *) malloc(sizeof(uint64_t) * (n_req ? n_req : 1) * (size_t) sr_db->k);
-        if (oatk_gpu_runlen_sums(sr_db, n_req, occ_off, occ, sums) != 0) {
-            fprintf(stderr, "[E::%s] the run lengths could not be read from the device\n", __func__);
-            exit(EXIT_FAILURE);
+        if (n_new) {
+            occ_off = (uint64_t *) malloc(sizeof(uint64_t) * (n_new + 1));
+            occ = (uint64_t *) malloc(sizeof(uint64_t) * (n_occ ? n_occ : 1));
+            g_rl.copies = (uint32_t *) realloc(g_rl.copies, sizeof(uint32_t) * (row0 + n_new));
+            g_rl.sums = (uint64_t *) realloc(g_rl.sums, sizeof(uint64_t) * (row0 + n_new) * (size_t) sr_db->k);
+            n_occ = 0;
+            for (j = 0; j < n_new; ++j) {
+                const syncmer_t *m = &scm[ids[j]];
+                occ_off[j] = n_occ;
+                for (uint32_t c = 0; c < m->cov; ++c) {
+                    if (occ_is_corrected(sr_db, m->m_pos[c])) continue;
+                    occ[n_occ++] = (m->m_pos[c] >> 32) << 32 | sr_db->a[m->m_pos[c] >> 32].m_pos[m->m_pos[c] >> 1 & MAX_RD_SCM];
+                }
+                g_rl.copies[row0 + j] = (uint32_t) (n_occ - occ_off[j]);
+            }
+            occ_off[n_new] = n_occ;
+            oatk_tick("cons: run-length requests");
+            if (oatk_gpu_runlen_sums(sr_db, n_new, occ_off, occ, g_rl.sums + row0 * (size_t) sr_db->k) != 0) {
+                fprintf(stderr, "[E::%s] the run lengths could not be read from the device\n", __func__);
+                exit(EXIT_FAILURE);
+            }
+            g_rl.n_rows = row0 + n_new;
+            free(occ_off); free(occ);
+            oatk_tick("cons: run-length sums from the device");
         }
-        free(ids); free(occ_off); free(occ);
-        rlt.row_of = row_of; rlt.sums = sums; rlt.copies = copies;
+        free(ids);
+        rlt.row_of = g_rl.row_of; rlt.sums = g_rl.sums; rlt.copies = g_rl.copies;
         J.rlt = &rlt;
     }
 
     cons_run(&J, 0, G->n_vtx);
+    oatk_tick("cons: unitig texts");
     if (fo) fprintf(fo, "H\tVN:Z:1.0\n");
     for (i = 0; i < G->n_vtx; ++i) {
         asmg_vtx_t *u = &G->vtx[i];
@@ -551,8 +624,10 @@ void scg_consensus(sr_db_t *sr_db, scg_t *scg, int hoco_seq, int save_seq, FILE 
         if (fo) fprintf(fo, "S\tu%lu\t%.*s\tLN:i:%ld\tKC:i:%ld\tSC:f:%.3f\n", (unsigned long) i, (int) l, J.text[i], (long) l, (long) (int64_t) (l * cov), cov);
         if (save_seq) u->seq = J.text[i]; else free(J.text[i]);
     }
+    oatk_tick("cons: S lines");
     /* overlaps are clipped to the unitig lengths, which are all known now */
     cons_run(&J, 1, G->n_arc);
+    oatk_tick("cons: arc overlaps");
     for (i = 0; i < G->n_arc; ++i) {
         asmg_arc_t *a = &G->arc[i];
         if (a->del || a->comp) continue;
@@ -567,5 +642,4 @@ void scg_consensus(sr_db_t *sr_db, scg_t *scg, int hoco_seq, int save_seq, FILE 
         }
     }
     free(J.text); free(J.len); free(J.cov); free(J.ovl);
-    free(row_of); free(sums); free(copies);
 }

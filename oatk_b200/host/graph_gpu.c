@@ -438,11 +438,14 @@ scg_t *make_syncmer_graph(sr_db_t *sr_db, syncmer_db_t *scm_db, uint32_t min_k_c
     for (i = 0; i < n; ++i) {
         syncmer_t *m = &scm_db->a[i];
         m->del |= m->cov < min_k_cov;
-        g->vtx[i].a = (uint64_t *) malloc(8);
         g->vtx[i].n = 1;
-        g->vtx[i].a[0] = i << 1;
         g->vtx[i].cov = m->cov;
         g->vtx[i].del = m->del;
+        /* a deleted vertex is dropped by asmg_finalize below before anybody can look at its syncmer list: with a coverage
+         * threshold that is nearly all of them, and 10^6 eight-byte blocks they would be */
+        if (m->del) continue;
+        g->vtx[i].a = (uint64_t *) malloc(8);
+        g->vtx[i].a[0] = i << 1;
     }
     oatk_tick("graph: vertices");
     /* arcs: counted, filtered and paired with their complements on the device */

@@ -79,7 +79,12 @@ typedef struct {
 } scg_meta_t;
 #endif
 
-int oatk_ec_last_run(uint64_t *overflow_reads);   /* 1: the last read_error_correction searched on the device */
+int oatk_ec_last_run(uint64_t *overflow_reads);
+/* read error correction without the all-syncmer graph on the host (filter, search on the device; syncerr_gpu.c): 0 when it ran,
+ * anything else when the caller has to take make_syncmer_graph + read_error_correction */
+int read_error_correction_device(sr_db_t *sr_db, syncmer_db_t *scm_db, double max_edist, uint32_t err_mer_c, uint32_t max_err_c,
+        uint32_t err_arc_c, double max_arc_f, int n_threads, int verbose);
+void oatk_syncmer_arc_overlaps(sr_db_t *sr_db, syncmer_db_t *scm_db, uint64_t n, const uint64_t *arcs4, uint32_t *ls);   /* 1: the last read_error_correction searched on the device */
 void asmg_destroy(asmg_t *g);
 /* graphutil_gpu.c / cleaning_gpu.c: the queries of graph.h:72-96 that callers beyond syncasm() use */
 int asmg_arc_is_sorted(asmg_t *g);

@@ -181,11 +181,17 @@ int syncasm(char **file_in, int n_file, size_t m_data, int k, int s, int bubble_
     if (do_ec) {
         /* the graph of ALL syncmers; the reads are corrected against its consensus in homopolymer-compressed space, which
          * read_error_correction computes itself for the part of the graph that survives its error filter */
-        scg = make_syncmer_graph(sr_db, scm_db, 0, 0.);
-        if (scg) {
-            read_error_correction(sr_db, scg, 0.02, min_k_cov, min_k_cov * 10, min_k_cov, min_a_cov_f, n_threads, 0, VERBOSE);
+        /* ... unless the reads live on the device: then that graph is never built on the host -- the device tallies its
+         * arcs, filters them and searches, and only what survives the filter comes down (read_error_correction_device) */
+        if (read_error_correction_device(sr_db, scm_db, 0.02, min_k_cov, min_k_cov * 10, min_k_cov, min_a_cov_f, n_threads, VERBOSE) == 0) {
             sr_db_stat(sr_db, stderr, VERBOSE);
-            scg_destroy(scg); scg = 0;
+        } else {
+            scg = make_syncmer_graph(sr_db, scm_db, 0, 0.);
+            if (scg) {
+                read_error_correction(sr_db, scg, 0.02, min_k_cov, min_k_cov * 10, min_k_cov, min_a_cov_f, n_threads, 0, VERBOSE);
+                sr_db_stat(sr_db, stderr, VERBOSE);
+                scg_destroy(scg); scg = 0;
+            }
         }
     }
 

@@ -528,6 +528,27 @@ static void ec_apply_range(uint64_t lo, uint64_t hi, void *arg)
     }
 }
 
+/* upload, search, and the rewritten lists back into the reads */
+static int ec_device_run(sr_db_t *db, const syncmer_db_t *S, const uint8_t *del, uint64_t n_live, const uint64_t *av, const uint64_t *aw,
+        const uint32_t *al, const uint64_t *at, double max_edist, long stats[11])
+{
+    sg_ec_graph_t E;
+    memset(&E, 0, sizeof(E));
+    E.n_syncmers = S->n; E.del = del; E.n_arcs = n_live; E.arc_v = av; E.arc_w = aw; E.arc_ls = al; E.arc_txt = at;
+    sg_ec_result_t R;
+    int rc = oatk_gpu_ec_correct(db, &E, max_edist, &R);
+    oatk_tick("ec/device: upload, search kernel, download");
+    if (rc == 0) {
+        ec_apply_t A = {db, S->a, &R};
+        oatk_parallel_for(db->n, ec_apply_range, &A);
+        for (int q = 0; q < 11; ++q) stats[q] = (long) R.stats[q];
+        g_last_overflow = R.n_overflow_reads;
+        sg_ec_result_free(&R);
+        oatk_tick("ec/device: lists back into the reads");
+    }
+    return rc;
+}
+
 static int cmp_part(const void *a, const void *b) { const ec_part_t *x = (const ec_part_t *) a, *y = (const ec_part_t *) b; return x->lo < y->lo ? -1 : x->lo > y->lo; }
 
 static int correct_reads_on_device(sr_db_t *db, scg_t *g, double max_edist, long stats[11])
@@ -553,20 +574,7 @@ static int correct_reads_on_device(sr_db_t *db, scg_t *g, double max_edist, long
         oatk_parallel_for(G->n_arc, ec_pack_range, &P);             /* same n, same ranges */
         for (uint64_t i = 0; i < S->n; ++i) del[i] = (uint8_t) scm[i].del;
         oatk_tick("ec/device: arrays of the filtered graph");
-        sg_ec_graph_t E;
-        memset(&E, 0, sizeof(E));
-        E.n_syncmers = S->n; E.del = del; E.n_arcs = n_live; E.arc_v = P.av; E.arc_w = P.aw; E.arc_ls = P.al; E.arc_txt = P.at;
-        sg_ec_result_t R;
-        rc = oatk_gpu_ec_correct(db, &E, max_edist, &R);
-        oatk_tick("ec/device: upload, search kernel, download");
-        if (rc == 0) {
-            ec_apply_t A = {db, scm, &R};
-            oatk_parallel_for(db->n, ec_apply_range, &A);
-            for (int q = 0; q < 11; ++q) stats[q] = (long) R.stats[q];
-            g_last_overflow = R.n_overflow_reads;
-            sg_ec_result_free(&R);
-            oatk_tick("ec/device: lists back into the reads");
-        }
+        rc = ec_device_run(db, S, del, n_live, P.av, P.aw, P.al, P.at, max_edist, stats);
         free(del); free(P.av); free(P.aw); free(P.at); free(P.al);
     }
     pthread_mutex_destroy(&P.lock);
@@ -574,33 +582,172 @@ static int correct_reads_on_device(sr_db_t *db, scg_t *g, double max_edist, long
 }
 
 /* ---------------------------------------------------------------- database after the rewrite */
-static void rebuild_syncmer_db(sr_db_t *db, syncmer_db_t *S)
+/* The occurrence lists are rebuilt by worker threads that each own a range of syncmer ids and walk all reads: a list
+ * is then filled by one thread, in read order, as the reference's single loop fills it (syncerr.c:769-817). */
+typedef struct { sr_db_t *db; syncmer_db_t *S; uint32_t *cnt, *fwd; int pass; } rebuild_t;
+static void rebuild_range(uint64_t lo, uint64_t hi, void *arg)
 {
-    syncmer_t *scm = S->a;
-    uint32_t *cnt = (uint32_t *) calloc(S->n ? S->n : 1, sizeof(uint32_t)), *fwd = (uint32_t *) calloc(S->n ? S->n : 1, sizeof(uint32_t));
-    free(S->c); S->c = 0;
-    free(S->h); S->h = 0;
-    for (size_t r = 0; r < db->n; ++r)
-        for (uint32_t j = 0; j < db->a[r].n; ++j) ++cnt[db->a[r].k_mer[j] >> 1];
-    /* the occurrence lists are one malloc block per syncmer (syncmer.c:1359); a block that is large enough is kept --
-     * nearly all syncmers are sequencing errors whose list only shrinks */
-    for (size_t i = 0; i < S->n; ++i) {
-        if (cnt[i] > scm[i].cov || !scm[i].m_pos) {
-            free(scm[i].m_pos);
-            scm[i].m_pos = (uint64_t *) malloc((cnt[i] ? cnt[i] : 1) * sizeof(uint64_t));
+    rebuild_t *R = (rebuild_t *) arg;
+    sr_db_t *db = R->db;
+    syncmer_t *scm = R->S->a;
+    if (R->pass == 0) {
+        for (size_t r = 0; r < db->n; ++r) {
+            const sr_t *sr = &db->a[r];
+            for (uint32_t j = 0; j < sr->n; ++j) { const uint64_t id = sr->k_mer[j] >> 1; if (id >= lo && id < hi) ++R->cnt[id]; }
         }
-        scm[i].cov = 0;
+        /* the lists are one malloc block per syncmer (syncmer.c:1359); a block that is large enough is kept -- nearly all
+         * syncmers are sequencing errors whose list only shrinks */
+        for (uint64_t i = lo; i < hi; ++i) {
+            if (R->cnt[i] > scm[i].cov || !scm[i].m_pos) {
+                free(scm[i].m_pos);
+                scm[i].m_pos = (uint64_t *) malloc((R->cnt[i] ? R->cnt[i] : 1) * sizeof(uint64_t));
+            }
+            scm[i].cov = 0;
+        }
+        return;
     }
     for (size_t r = 0; r < db->n; ++r) {
         const sr_t *sr = &db->a[r];
         for (uint32_t j = 0; j < sr->n; ++j) {
             const uint64_t id = sr->k_mer[j] >> 1;
+            if (id < lo || id >= hi) continue;
             scm[id].m_pos[scm[id].cov++] = sr->sid << 32 | (uint64_t) j << 1 | (sr->m_pos[j] & 1);
-            if (!(sr->m_pos[j] & 1)) ++fwd[id];
+            if (!(sr->m_pos[j] & 1)) ++R->fwd[id];
         }
     }
-    for (size_t i = 0; i < S->n; ++i) scm[i].del = !fwd[i];   /* syncerr.c:805-812 */
-    free(fwd); free(cnt);
+    for (uint64_t i = lo; i < hi; ++i) scm[i].del = !R->fwd[i];       /* syncerr.c:805-812 */
+}
+
+static void rebuild_syncmer_db(sr_db_t *db, syncmer_db_t *S)
+{
+    rebuild_t R = {db, S, (uint32_t *) calloc(S->n ? S->n : 1, sizeof(uint32_t)), (uint32_t *) calloc(S->n ? S->n : 1, sizeof(uint32_t)), 0};
+    free(S->c); S->c = 0;
+    free(S->h); S->h = 0;
+    oatk_parallel_for(S->n, rebuild_range, &R);
+    R.pass = 1;
+    oatk_parallel_for(S->n, rebuild_range, &R);
+    free(R.fwd); free(R.cnt);
+}
+
+static void rebuild_syncmer_db(sr_db_t *db, syncmer_db_t *S);
+/* the closing lines of read_error_correction (syncerr.c:899-923); they carry that function's name whichever form ran */
+static void ec_print_summary(const long stats[11], int verbose, double cpu_at_entry, double wall_at_entry)
+{
+    const char *fn = "read_error_correction";
+    fprintf(stderr, "[M::%s] Error Correction Summary Results\n", fn);
+    fprintf(stderr, "[M::%s] total number of error blocks : %ld\n", fn, stats[0] + stats[5] + stats[10]);
+    fprintf(stderr, "[M::%s]                - uncorrected : %ld\n", fn, stats[1] + stats[6]);
+    fprintf(stderr, "[M::%s]                  - corrected : %ld\n", fn, stats[2] + stats[7]);
+    fprintf(stderr, "[M::%s]             - ambiguous seqs : %ld\n", fn, stats[3] + stats[8]);
+    fprintf(stderr, "[M::%s]             - ambiguous path : %ld\n", fn, stats[4] + stats[9]);
+    if (verbose) {
+        fprintf(stderr, "[M::%s] error blocks in the tail end : %ld\n", fn, stats[0]);
+        fprintf(stderr, "[M::%s]                - uncorrected : %ld\n", fn, stats[1]);
+        fprintf(stderr, "[M::%s]                  - corrected : %ld\n", fn, stats[2]);
+        fprintf(stderr, "[M::%s]             - ambiguous seqs : %ld\n", fn, stats[3]);
+        fprintf(stderr, "[M::%s]             - ambiguous path : %ld\n", fn, stats[4]);
+        fprintf(stderr, "[M::%s]   error blocks in the middle : %ld\n", fn, stats[5]);
+        fprintf(stderr, "[M::%s]                - uncorrected : %ld\n", fn, stats[6]);
+        fprintf(stderr, "[M::%s]                  - corrected : %ld\n", fn, stats[7]);
+        fprintf(stderr, "[M::%s]             - ambiguous seqs : %ld\n", fn, stats[8]);
+        fprintf(stderr, "[M::%s]             - ambiguous path : %ld\n", fn, stats[9]);
+        fprintf(stderr, "[M::%s]      error blocks overlapped : %ld\n", fn, stats[10]);
+        {   /* syncerr.c:921-922: the step's own clocks */
+            struct rusage ru;
+            struct timeval tv;
+            getrusage(RUSAGE_SELF, &ru);
+            gettimeofday(&tv, 0);
+            fprintf(stderr, "[M::%s]   error correction  CPU time : %.3f sec\n", fn,
+                    ru.ru_utime.tv_sec + ru.ru_stime.tv_sec + 1e-6 * (ru.ru_utime.tv_usec + ru.ru_stime.tv_usec) - cpu_at_entry);
+            fprintf(stderr, "[M::%s]   error correction real time : %.3f sec\n", fn, tv.tv_sec + 1e-6 * tv.tv_usec - wall_at_entry);
+        }
+    }
+}
+
+static void ec_clocks(double *cpu, double *wall)
+{
+    struct rusage ru;
+    struct timeval tv;
+    getrusage(RUSAGE_SELF, &ru);
+    gettimeofday(&tv, 0);
+    *cpu = ru.ru_utime.tv_sec + ru.ru_stime.tv_sec + 1e-6 * (ru.ru_utime.tv_usec + ru.ru_stime.tv_usec);
+    *wall = tv.tv_sec + 1e-6 * tv.tv_usec;
+}
+
+/* ---------------------------------------------------------------- the whole step without a host graph
+ * What syncasm() does for its error-correction step when the reads live on the device: the all-syncmer graph (one
+ * vertex per distinct k-mer, ~10^7 arcs at 200 k reads) exists only to be filtered down to the ~2 % of it the search can
+ * walk, so it is never built here. The device tallies the arcs (sg_arcs with no thresholds: exactly the arcs
+ * make_syncmer_graph(sr_db, scm_db, 0, 0.) would receive, in the order asmg_finalize leaves them), flags the suspects
+ * (sg_ec_filter) and sends back the flags and the surviving arcs; the host computes those arcs' overlaps the way
+ * scg_consensus does in hoco space (oatk_syncmer_arc_overlaps), the search runs on the device (sg_ec_correct), and the
+ * database is rebuilt as in read_error_correction. Same messages, same results (tests/test_gpu_ec.py compares the two
+ * forms; the CLI tests compare stderr and both GFA files with the reference binary). Returns non-zero, having changed
+ * nothing, when the conditions do not hold: no device batch behind sr_db, or syncmers already flagged deleted (the graph
+ * the reference builds would then be renumbered by asmg_finalize). */
+typedef struct { sr_db_t *db; const syncmer_t *scm; const uint64_t *arcs4; uint64_t *at; } ec_txt_t;
+static void ec_txt_range(uint64_t lo, uint64_t hi, void *arg)
+{
+    ec_txt_t *T = (ec_txt_t *) arg;
+    for (uint64_t i = lo; i < hi; ++i) {
+        const syncmer_t *m = &T->scm[T->arcs4[4 * i + 1] >> 1];
+        uint64_t ref = UINT64_MAX;
+        for (uint32_t c = 0; c < m->cov; ++c) {
+            const uint64_t occ = m->m_pos[c];
+            const sr_t *r = &T->db->a[occ >> 32];
+            const uint64_t idx = occ >> 1 & MAX_RD_SCM;
+            if (r->k_mer[idx] & 1) continue;
+            ref = (occ >> 32) << 32 | (uint64_t) (r->m_pos[idx] >> 1) << 1 | (r->m_pos[idx] & 1);
+            break;
+        }
+        T->at[i] = ref;
+    }
+}
+
+int read_error_correction_device(sr_db_t *sr_db, syncmer_db_t *scm_db, double max_edist, uint32_t err_mer_c, uint32_t max_err_c,
+        uint32_t err_arc_c, double max_arc_f, int n_threads, int verbose)
+{
+    (void) n_threads;
+    const char *force_host = getenv("OATK_EC_HOST"), *force_graph = getenv("OATK_EC_GRAPH");
+    if ((force_host && atoi(force_host) > 0) || (force_graph && atoi(force_graph) > 0)) return -1;
+    if (!oatk_gpu_ec_available(sr_db) || scm_db->n == 0) return -1;
+    syncmer_t *scm = scm_db->a;
+    for (size_t i = 0; i < scm_db->n; ++i) if (scm[i].del) return -1;
+    double cpu_at_entry, wall_at_entry;
+    ec_clocks(&cpu_at_entry, &wall_at_entry);
+    oatk_tick(0);
+    sg_ec_filter_out_t F;
+    if (oatk_gpu_ec_filter(sr_db, err_mer_c, max_err_c, err_arc_c, max_arc_f, &F) != 0) return -1;
+    oatk_tick("ec/graph-free: arc tally + error filter (device), flags and surviving arcs down");
+    /* nothing has been changed so far; from here on the step is committed */
+    int64_t n_err = 0;
+    uint32_t max_c = 0;
+    for (size_t i = 0; i < scm_db->n; ++i)
+        if (F.err[i]) { scm[i].del = 1; if (scm[i].cov > max_c) max_c = scm[i].cov; ++n_err; }
+    fprintf(stderr, "[M::%s] error syncmer candidates: num = %ld, max_c = %u\n", "find_error_syncmers", (long) n_err, max_c);
+    const uint64_t n = F.n_live;
+    uint64_t *av = (uint64_t *) malloc(8 * (n + 1)), *aw = (uint64_t *) malloc(8 * (n + 1)), *at = (uint64_t *) malloc(8 * (n + 1));
+    uint32_t *al = (uint32_t *) malloc(4 * (n + 1));
+    for (uint64_t i = 0; i < n; ++i) { av[i] = F.arcs4[4 * i]; aw[i] = F.arcs4[4 * i + 1]; }
+    oatk_syncmer_arc_overlaps(sr_db, scm_db, n, F.arcs4, al);
+    ec_txt_t T = {sr_db, scm, F.arcs4, at};
+    oatk_parallel_for(n, ec_txt_range, &T);
+    oatk_tick("ec/graph-free: overlaps and text sources of the surviving arcs");
+    long stats[11] = {0};
+    const int rc = ec_device_run(sr_db, scm_db, F.err, n, av, aw, al, at, max_edist, stats);
+    free(av); free(aw); free(at); free(al);
+    sg_ec_filter_free(&F);
+    if (rc != 0) {
+        fprintf(stderr, "[E::%s] the device search failed after the error filter had been applied\n", __func__);
+        exit(EXIT_FAILURE);
+    }
+    g_last_on_device = 2;
+    rebuild_syncmer_db(sr_db, scm_db);
+    oatk_tick("ec: rebuild database");
+    oatk_gpu_update_lists(sr_db, scm_db);
+    oatk_tick("ec: refresh device lists");
+    ec_print_summary(stats, verbose, cpu_at_entry, wall_at_entry);
+    return 0;
 }
 
 /* ---------------------------------------------------------------- driver */
@@ -668,34 +815,7 @@ void read_error_correction(sr_db_t *sr_db, scg_t *g, double max_edist, uint32_t 
     oatk_gpu_update_lists(sr_db, g->scm_db);            /* the device-resident lists follow the host's */
     oatk_tick("ec: refresh device lists");
 
-    fprintf(stderr, "[M::%s] Error Correction Summary Results\n", __func__);
-    fprintf(stderr, "[M::%s] total number of error blocks : %ld\n", __func__, stats[0] + stats[5] + stats[10]);
-    fprintf(stderr, "[M::%s]                - uncorrected : %ld\n", __func__, stats[1] + stats[6]);
-    fprintf(stderr, "[M::%s]                  - corrected : %ld\n", __func__, stats[2] + stats[7]);
-    fprintf(stderr, "[M::%s]             - ambiguous seqs : %ld\n", __func__, stats[3] + stats[8]);
-    fprintf(stderr, "[M::%s]             - ambiguous path : %ld\n", __func__, stats[4] + stats[9]);
-    if (verbose) {
-        fprintf(stderr, "[M::%s] error blocks in the tail end : %ld\n", __func__, stats[0]);
-        fprintf(stderr, "[M::%s]                - uncorrected : %ld\n", __func__, stats[1]);
-        fprintf(stderr, "[M::%s]                  - corrected : %ld\n", __func__, stats[2]);
-        fprintf(stderr, "[M::%s]             - ambiguous seqs : %ld\n", __func__, stats[3]);
-        fprintf(stderr, "[M::%s]             - ambiguous path : %ld\n", __func__, stats[4]);
-        fprintf(stderr, "[M::%s]   error blocks in the middle : %ld\n", __func__, stats[5]);
-        fprintf(stderr, "[M::%s]                - uncorrected : %ld\n", __func__, stats[6]);
-        fprintf(stderr, "[M::%s]                  - corrected : %ld\n", __func__, stats[7]);
-        fprintf(stderr, "[M::%s]             - ambiguous seqs : %ld\n", __func__, stats[8]);
-        fprintf(stderr, "[M::%s]             - ambiguous path : %ld\n", __func__, stats[9]);
-        fprintf(stderr, "[M::%s]      error blocks overlapped : %ld\n", __func__, stats[10]);
-        {   /* syncerr.c:921-922: the step's own clocks */
-            struct rusage ru;
-            struct timeval tv;
-            getrusage(RUSAGE_SELF, &ru);
-            gettimeofday(&tv, 0);
-            fprintf(stderr, "[M::%s]   error correction  CPU time : %.3f sec\n", __func__,
-                    ru.ru_utime.tv_sec + ru.ru_stime.tv_sec + 1e-6 * (ru.ru_utime.tv_usec + ru.ru_stime.tv_usec) - cpu_at_entry);
-            fprintf(stderr, "[M::%s]   error correction real time : %.3f sec\n", __func__, tv.tv_sec + 1e-6 * tv.tv_usec - wall_at_entry);
-        }
-    }
+    ec_print_summary(stats, verbose, cpu_at_entry, wall_at_entry);
     for (int t = 0; t < n_threads; ++t) {
         ec_worker_t *W = &J[t].W;
         wave_free(&W->w); free(W->S.cand.s); free(W->S.best_seq.s); free(W->S.path.a); free(W->S.best_path.a); free(W->S.stash);

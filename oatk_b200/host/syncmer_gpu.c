@@ -610,6 +610,17 @@ int oatk_gpu_ec_correct(sr_db_t *sr_db, const void *graph, double max_edist, voi
     return rc;
 }
 
+/* the error filter on the device (sg_ec_filter); result is an sg_ec_filter_out_t */
+int oatk_gpu_ec_filter(sr_db_t *sr_db, uint32_t err_mer_c, uint32_t max_err_c, uint32_t err_arc_c, double max_arc_f, void *result)
+{
+    sg_batch *b = batch_of(sr_db, 0);
+    int rc;
+    if (!b) return SG_E_STATE;
+    rc = sg_ec_filter(b, 0, err_mer_c, max_err_c, err_arc_c, max_arc_f, (sg_ec_filter_out_t *) result);
+    if (rc != SG_OK) fprintf(stderr, "[E::%s] %s: %s\n", __func__, sg_strerror(rc), sg_last_error(ctx_of(sr_db)));
+    return rc;
+}
+
 int syncmer_graph_arcs(sr_db_t *sr_db, syncmer_db_t *scm_db, uint32_t min_k_cov, double min_a_cov_f, uint64_t **arcs4, uint64_t *n_arcs)
 {
     sg_batch *b = batch_of(sr_db, 0);
@@ -660,6 +671,7 @@ void oatk_tick(const char *what)
 
 int oatk_gpu_update_lists(sr_db_t *sr_db, syncmer_db_t *scm_db)
 {
+    oatk_cons_cache_drop(sr_db);                       /* the lists changed: run-length sums kept for them are stale */
     sg_batch *b = batch_of(sr_db, 0);
     uint64_t i, N = 0, *off, *km, *sm;
     uint32_t *mp, *cov;
@@ -699,6 +711,7 @@ void sr_db_clean(sr_db_t *sr_db)
     free(sr_db->a);
     free(sr_db->stats);
     sr_db->a = 0; sr_db->stats = 0; sr_db->n = sr_db->m = 0;
+    oatk_cons_cache_drop(sr_db);
     batch_drop(sr_db);
 }
 

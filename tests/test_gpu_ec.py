@@ -48,15 +48,35 @@ def host():
     L.read_error_correction.restype = None
     L.read_error_correction.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_uint32, C.c_uint32, C.c_uint32, C.c_double, C.c_int, C.c_void_p, C.c_int]
     L.oatk_ec_last_run.argtypes = [C.POINTER(C.c_uint64)]
+    L.read_error_correction_device.restype = C.c_int
+    L.read_error_correction_device.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_uint32, C.c_uint32, C.c_uint32, C.c_double, C.c_int, C.c_int]
     return L
 
 
-def run_ec(host, reads, k, s, mkc, on_host, up_front_consensus):
+def run_ec(host, reads, k, s, mkc, on_host, up_front_consensus, graph_free=False):
     bases, off = pack_reads(reads)
     db = SrDb()
     host.sr_db_init(C.byref(db), k, s)
     assert host.sr_read_mem(C.byref(db), bases.ctypes.data, off.ctypes.data, None, len(reads)) == 0
     scm = host.collect_syncmer_from_reads(C.byref(db))
+    if graph_free:
+        # what syncasm() does: no all-syncmer graph on the host at all
+        os.environ.pop("OATK_EC_HOST", None)
+        assert host.read_error_correction_device(C.byref(db), scm, 0.02, mkc, mkc * 10, mkc, 0.35, 4, 1) == 0
+        over = C.c_uint64(0)
+        where = host.oatk_ec_last_run(C.byref(over))
+        lists = []
+        for r in range(db.n):
+            a = db.a[r]
+            n = a.n
+            lists.append((np.ctypeslib.as_array(a.k_mer, (n,)).copy() if n else np.zeros(0, np.uint64),
+                          np.ctypeslib.as_array(a.m_pos, (n,)).copy() if n else np.zeros(0, np.uint32),
+                          np.ctypeslib.as_array(a.s_mer, (n,)).copy() if n else np.zeros(0, np.uint64)))
+        S = C.cast(scm, C.POINTER(ScmDb)).contents
+        covdel = np.array([S.a[i].covdel for i in range(S.n)], dtype=np.uint32)
+        host.syncmer_db_destroy(scm)
+        host.sr_db_clean(C.byref(db))
+        return where, int(over.value), lists, covdel
     g = host.make_syncmer_graph(C.byref(db), scm, 0, 0.0)
     if up_front_consensus:
         host.scg_consensus(C.byref(db), g, 1, 1, None)      # what run_syncasm.c:118 does; without it the texts follow the filter
@@ -103,6 +123,11 @@ def test_device_search_equals_host_search(host, k, s, G, n, L, err, mkc, front):
     assert np.array_equal(ch, cd)
     corrected = sum(int((x[0] & 1).sum()) for x in ld)
     assert corrected > 0, "no block was corrected: the test does not exercise the search"
+    # the graph-free form of syncasm(): filter on the device, overlaps of the surviving arcs only
+    wf, _, lf, cf = run_ec(host, reads, k, s, mkc, False, front, graph_free=True)
+    assert wf == 2
+    same(lh, lf)
+    assert np.array_equal(ch, cf)
 
 
 def test_repeats_and_haplotypes(host):
@@ -129,6 +154,10 @@ def test_repeats_and_haplotypes(host):
         assert wh == 0 and wd == 1
         same(lh, ld)
         assert np.array_equal(ch, cd)
+        wf, _, lf, cf = run_ec(host, reads, k, s, mkc, False, 0, graph_free=True)
+        assert wf == 2
+        same(lh, lf)
+        assert np.array_equal(ch, cf)
 
 
 def test_worst_case_arena_pass(host):

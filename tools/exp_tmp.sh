@@ -1,7 +1,3 @@
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29611 bench.py --gpus 2 --steps 2 --warmup 3 --no-e2e --reads 200000 --config3-reads 600000 > gpurun_out/exp_n2.json 2> gpurun_out/exp_n2.err; echo rc=$?; tail -3 gpurun_out/exp_n2.err
-python - <<PY
-import json
-d=json.loads([l for l in open("gpurun_out/exp_n2.json") if l.startswith("{")][-1])
-print("value", d["value"]/1e9, "ms", d["ms_per_step"], d["multi_gpu_parity"]["ok"], d["global_ids_sample_check"]["ok"])
-print(json.dumps(d["config3"])[:1500])
-PY
+python -m pytest tests/test_gpu_syncasm.py tests/test_cli.py tests/test_gpu_golden_pipeline.py tests/test_host_layer.py tests/test_gpu_runlen.py -m gpu -x -q 2>&1 | tail -5
+OATK_TIMING=1 python tools/syncasm_run.py --reads 200000 --genome 10000000 --c 30 2> gpurun_out/whole_stages.err | tail -1 | cut -c1-200
+grep -n "T::" gpurun_out/whole_stages.err | tail -42
