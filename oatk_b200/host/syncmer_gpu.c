@@ -521,6 +521,28 @@ void sr_db_stat(sr_db_t *sr_db, FILE *fo, int verbose)
     if (verbose > 1) print_verbose_tables(sr_db, fo, verbose - 1 > 0);
 }
 
+typedef struct { syncmer_db_t *db; const uint64_t *h, *s; const uint32_t *cov; const uint64_t *off, *occ; } collect_fill_t;
+static void collect_fill(uint64_t lo, uint64_t hi, void *arg)
+{
+    const collect_fill_t *F = (const collect_fill_t *) arg;
+    for (uint64_t i = lo; i < hi; ++i) {
+        syncmer_t *m = &F->db->a[i];
+        m->h = F->h[i]; m->s = F->s[i]; m->cov = F->cov[i]; m->del = 0;
+        m->m_pos = (uint64_t *) malloc(8 * (size_t) F->cov[i]);
+        memcpy(m->m_pos, F->occ + F->off[i], 8 * (size_t) F->cov[i]);
+        F->db->c[i] = 1;                                        /* syncmer.c:1443 */
+    }
+}
+typedef struct { sr_db_t *db; const uint64_t *kid, *first; } collect_ids_t;
+static void collect_ids(uint64_t lo, uint64_t hi, void *arg)
+{
+    const collect_ids_t *K = (const collect_ids_t *) arg;
+    for (uint64_t i = lo; i < hi; ++i) {
+        sr_t *r = &K->db->a[i];
+        if (r->n) memcpy(r->k_mer, K->kid + K->first[i], 8 * (size_t) r->n);
+    }
+}
+
 syncmer_db_t *collect_syncmer_from_reads(sr_db_t *sr_db)
 {
     sg_batch *b = batch_of(sr_db, 0);
@@ -554,18 +576,16 @@ syncmer_db_t *collect_syncmer_from_reads(sr_db_t *sr_db)
     db->a = (syncmer_t *) malloc(sizeof(syncmer_t) * (z.n_unique ? z.n_unique : 1));
     db->c = (uint16_t *) malloc(sizeof(uint16_t) * (z.n_unique ? z.n_unique : 1));
     db->h = 0;
-    for (i = 0; i < z.n_unique; ++i) {
-        syncmer_t *m = &db->a[i];
-        m->h = h[i]; m->s = s[i]; m->cov = cov[i]; m->del = 0;
-        m->m_pos = (uint64_t *) malloc(8 * (size_t) cov[i]);
-        memcpy(m->m_pos, occ + off[i], 8 * (size_t) cov[i]);
-        db->c[i] = 1;                                           /* syncmer.c:1443 */
-    }
+    /* one malloc block per occurrence list (syncmer.c:1359; freed one by one, syncmer.c:1099): 10^6 small blocks, built
+     * by worker threads over ranges of ids */
+    { collect_fill_t F = {db, h, s, cov, off, occ}; oatk_parallel_for(z.n_unique, collect_fill, &F); }
     /* k_mer[] now carries id << 1 (syncmer.c:1378) */
-    for (i = 0, p = 0; i < sr_db->n; ++i) {
-        sr_t *r = &sr_db->a[i];
-        if (r->n) memcpy(r->k_mer, kid + p, 8 * (size_t) r->n);
-        p += r->n;
+    {
+        uint64_t *first = (uint64_t *) malloc(8 * (sr_db->n + 1));
+        for (i = 0, p = 0; i < sr_db->n; ++i) { first[i] = p; p += sr_db->a[i].n; }
+        collect_ids_t K = {sr_db, kid, first};
+        oatk_parallel_for(sr_db->n, collect_ids, &K);
+        free(first);
     }
     free(h); free(s); free(cov); free(off); free(occ); free(kid);
     return db;

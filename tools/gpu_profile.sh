@@ -11,7 +11,7 @@ d=json.load(open("gpurun_out/${TAG}_bench_n1.json"))
 print("value", d["value"]/1e9, "ms", d["ms_per_step"], "e2e", d["e2e"] and d["e2e"]["value"]/1e9)
 print(d["roofline"]["stage_ms"], d["roofline"]["frac"])
 PY
-ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:"^(?!.*(at::|unnamed|cub::|thrust::|elementwise)).*" -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu > gpurun_out/${TAG}_launches.log 2>&1; echo "launch list rc=$?"
-ncu --set full --clock-control none --import-source on -k regex:"scan_kernel|encode_kernel|kmerhash_kernel" -s 3 -c 3 -o gpurun_out/${TAG}_extract -f python bench.py --reads 50000 --steps 1 --warmup 0 --no-e2e --no-cpu > gpurun_out/${TAG}_ncu_extract.log 2>&1; echo "ncu extract rc=$?"
+ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:"^(?!.*(at::|unnamed|cub::|thrust::|elementwise)).*" -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu --no-sweep --no-whole > gpurun_out/${TAG}_launches.log 2>&1; echo "launch list rc=$?"
+ncu --set full --clock-control none --import-source on -k regex:"scan_kernel|encode_kernel|kmerhash_kernel" -s 3 -c 3 -o gpurun_out/${TAG}_extract -f python bench.py --reads 50000 --steps 1 --warmup 0 --no-e2e --no-cpu --no-sweep --no-whole > gpurun_out/${TAG}_ncu_extract.log 2>&1; echo "ncu extract rc=$?"
 ncu -i gpurun_out/${TAG}_extract.ncu-rep --page raw --csv > gpurun_out/${TAG}_extract_raw.csv 2>/dev/null
 ls -la gpurun_out | tail -12
