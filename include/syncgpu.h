@@ -258,6 +258,12 @@ uint64_t sg_pipe_launches(sg_pipe *p);
  * being downloaded; sg_runlen_sums then serves the one consumer they have, the run-length consensus. sg_pipe_run_host does the
  * same on its own when the caller passes no ho_rl buffer. */
 int sg_pipe_keep_run_lengths(sg_pipe *p, int on);
+/* Callback form: the master batch has room for `factor` times the expected number of syncmers (2 per window of k - s + 1
+ * bases; default 16, never more than one per base). Low-complexity input (short tandem repeats tie at every position) can
+ * exceed that: the run then ends with SG_E_NOMEM and sg_pipe_syncmer_overflow() = 1, and the caller repeats it with a
+ * larger factor (sr_read_mem does). */
+int sg_pipe_set_capacity_factor(sg_pipe *p, unsigned factor);
+int sg_pipe_syncmer_overflow(sg_pipe *p);
 /* multi-GPU: global index of this pipe's first read (sid of read i = sid_base + i); default 0 */
 int sg_pipe_set_sid_base(sg_pipe *p, uint64_t sid_base);
 

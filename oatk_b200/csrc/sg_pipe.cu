@@ -72,6 +72,8 @@ struct sg_pipe {
     sg_batch *master = nullptr;
     std::string err;
     uint64_t sid_base = 0;       // global index of the first read (multi-GPU: this GPU's block of the read set)
+    unsigned cap_factor = 16;    // callback form: room for this many times the expected number of syncmers in the master batch
+    bool overflowed = false;     // the last run ended because that room was not enough (sg_pipe_syncmer_overflow)
     bool keep_rl = false;        // ho_rl stays on the device (master batch) instead of travelling to the host: sg_runlen_sums serves the consensus
 };
 
@@ -137,6 +139,14 @@ sg_batch *sg_pipe_master(sg_pipe *p) { return p ? p->master : nullptr; }
 sg_ctx *sg_pipe_ctx(sg_pipe *p) { return p ? p->mctx : nullptr; }
 const char *sg_pipe_last_error(sg_pipe *p) { return p ? p->err.c_str() : "no pipe"; }
 
+int sg_pipe_set_capacity_factor(sg_pipe *p, unsigned factor)
+{
+    if (!p || factor < 1) return SG_E_ARG;
+    p->cap_factor = factor;
+    return SG_OK;
+}
+int sg_pipe_syncmer_overflow(sg_pipe *p) { return p && p->overflowed ? 1 : 0; }
+
 int sg_pipe_keep_run_lengths(sg_pipe *p, int on) { if (!p) return SG_E_ARG; p->keep_rl = on != 0; return SG_OK; }
 
 int sg_pipe_set_sid_base(sg_pipe *p, uint64_t sid_base) { if (!p) return SG_E_ARG; p->sid_base = sid_base; return SG_OK; }
@@ -174,7 +184,8 @@ static int pipe_run(sg_pipe *p, const char *bases, const uint64_t *off, uint64_t
     // (callback form: 2 closed syncmers per window is the expectation; room for 16, never more than one per base)
     const uint64_t qwin = (uint64_t) (k - s + 1);
     const uint64_t cap_pos = total + 64 * n_reads + 64;
-    const uint64_t capN = cb ? std::min<uint64_t>(total + n_reads, 16 * (total / qwin + n_reads)) + 1024 : caps->max_syncmers;
+    const uint64_t capN = cb ? std::min<uint64_t>(total + n_reads, (uint64_t) p->cap_factor * (total / qwin + n_reads)) + 1024 : caps->max_syncmers;
+    p->overflowed = false;
     // run lengths stay on the device when asked to (sg_pipe_keep_run_lengths) or when the caller gave no buffer for them
     const bool keep_rl = p->keep_rl || (!cb && out && !out->ho_rl_buf);
     const uint64_t cap_lrl = total / 256 + 1024;             // a listed run is at least 256 bases long
@@ -276,6 +287,7 @@ static int pipe_run(sg_pipe *p, const char *bases, const uint64_t *off, uint64_t
                             (out->ho_rl_buf && tot.rl + z.ho_rl_bytes > caps->ho_rl_bytes) || tot.amb + z.n_ambiguous > caps->max_ambiguous ||
                             tot.lrl + z.n_long_runs > caps->max_long_runs))) {
                         rc = SG_E_NOMEM; msg = "caller capacities too small";
+                        if (cb) p->overflowed = true;
                     }
                 }
                 if (!rc && !first_err) {

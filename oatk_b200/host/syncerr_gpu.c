@@ -193,17 +193,17 @@ static inline void str_room(str_t *s, size_t extra)
 }
 static inline void str_add(str_t *s, const char *p, size_t l) { str_room(s, l); memcpy(s->s + s->l, p, l); s->l += l; s->s[s->l] = 0; }
 /* complement by table; the graph's strings hold ACGT (and N for syncmers without a copy), anything else stays as it is */
+static char comp_tab[256];
+static pthread_once_t comp_once = PTHREAD_ONCE_INIT;
+static void comp_init(void)
+{
+    for (int c = 0; c < 256; ++c) comp_tab[c] = (char) c;
+    comp_tab['A'] = 'T'; comp_tab['C'] = 'G'; comp_tab['G'] = 'C'; comp_tab['T'] = 'A';
+}
 static const char *comp_table(void)
 {
-    static char t[256];
-    static volatile int ready;
-    if (!ready) {
-        for (int c = 0; c < 256; ++c) t[c] = (char) c;
-        t['A'] = 'T'; t['C'] = 'G'; t['G'] = 'C'; t['T'] = 'A';
-        __sync_synchronize();
-        ready = 1;
-    }
-    return t;
+    pthread_once(&comp_once, comp_init);               /* worker threads call this: built exactly once */
+    return comp_tab;
 }
 static inline void str_add_rc(str_t *s, const char *p, size_t l)
 {

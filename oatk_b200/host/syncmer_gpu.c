@@ -174,7 +174,17 @@ int sr_read_mem(sr_db_t *sr_db, const char *bases, const uint64_t *off, char **n
     sr_db->n = sr_db->m = n_reads;
     f.db = sr_db; f.names = names;
     sg_pipe_keep_run_lengths(pipe, g_keep_rl);
-    rc = sg_pipe_run_host_cb(pipe, bases, off, n_reads, k, s, SR_READ_CHUNK, fill_chunk, &f, &z);
+    /* the pipeline's master batch is cut for 16 times the expected number of syncmers; low-complexity reads (a
+     * dinucleotide repeat ties at every position: one syncmer per base) can need more, where the reference simply goes on:
+     * the run is repeated with more room until there is one slot per base */
+    for (unsigned factor = 16; ; factor *= 8) {
+        sg_pipe_set_capacity_factor(pipe, factor);
+        rc = sg_pipe_run_host_cb(pipe, bases, off, n_reads, k, s, SR_READ_CHUNK, fill_chunk, &f, &z);
+        if (!(rc == SG_E_NOMEM && sg_pipe_syncmer_overflow(pipe)) || factor > (unsigned) (k - s + 1)) break;
+        for (uint64_t i = 0; i < n_reads; ++i) sr_destroy(&sr_db->a[i]);        /* what the chunks before the overflow built */
+        memset(sr_db->a, 0, (n_reads ? n_reads : 1) * sizeof(sr_t));
+    }
+    sg_pipe_set_capacity_factor(pipe, 16);
     if (rc != SG_OK) fprintf(stderr, "[E::%s] %s: %s\n", __func__, sg_strerror(rc), sg_pipe_last_error(pipe));
     return rc;
 }
@@ -773,21 +783,22 @@ void get_kmer_seq(uint8_t *hoco_s, uint32_t pos, int l, uint32_t rev, uint8_t *k
 
 /* l bases from hoco position pos as text, reverse-complemented when rev. Whole packed bytes go through a table of
  * four characters per byte (the error correction unpacks every block of every read with this). */
+static uint32_t fwd4[256], rc4[256];
+static pthread_once_t dna4_once = PTHREAD_ONCE_INIT;
+static void dna4_init(void)
+{
+    int b, j;
+    for (b = 0; b < 256; ++b) {
+        char f[4], r[4];
+        for (j = 0; j < 4; ++j) { const int c = (b >> ((3 - j) * 2)) & 3; f[j] = char_nt4_table[c]; r[3 - j] = char_nt4_table[3 - c]; }
+        memcpy(&fwd4[b], f, 4); memcpy(&rc4[b], r, 4);
+    }
+}
+
 void get_kmer_dna_seq(uint8_t *hoco_s, uint32_t pos, int l, uint32_t rev, char *dna_seq)
 {
-    static uint32_t fwd4[256], rc4[256];
-    static volatile int ready;
     int i = 0;
-    if (!ready) {
-        int b, j;
-        for (b = 0; b < 256; ++b) {
-            char f[4], r[4];
-            for (j = 0; j < 4; ++j) { const int c = (b >> ((3 - j) * 2)) & 3; f[j] = char_nt4_table[c]; r[3 - j] = char_nt4_table[3 - c]; }
-            memcpy(&fwd4[b], f, 4); memcpy(&rc4[b], r, 4);
-        }
-        __sync_synchronize();
-        ready = 1;
-    }
+    pthread_once(&dna4_once, dna4_init);                   /* called from worker threads: the tables are built exactly once */
     if (!rev) {
         uint32_t p = pos;
         for (; i < l && (p & 3); ++i, ++p) dna_seq[i] = char_nt4_table[hoco_base(hoco_s, p)];

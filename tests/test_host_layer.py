@@ -197,6 +197,26 @@ def test_graph_layer_matches_reference(host, ref, k, s, mkc):
     ref.free(rdb, rscm)
 
 
+def test_low_complexity_reads_need_more_room(host, ref):
+    """reads that are nothing but short tandem repeats: every position ties for the window minimum, so there is close to
+    one syncmer per base where the pipeline's master batch is cut for 16 times two per window. sr_read_mem repeats the run
+    with more room and the result is the reference's"""
+    k, s = 301, 15
+    reads = [b"AC" * 4000, b"ACG" * 2500, b"TTAGGG" * 1500, b"AC" * 3000 + b"ACGT" * 800] * 12
+    bases, off = pack_reads(reads)
+    n = len(reads)
+    db = SrDb()
+    host.sr_db_init(C.byref(db), k, s)
+    assert host.sr_read_mem(C.byref(db), bases.ctypes.data, off.ctypes.data, None, n) == 0
+    mine = ref._flat(C.addressof(db), n, count_ambiguous(bases, off))
+    rdb, theirs = ref.extract(bases, off, k, s)
+    assert parity.diff(mine, theirs, parity.EXTRACT_FIELDS) == []
+    total = int(off[-1])
+    assert len(theirs["m_pos"]) > 16 * (total // (k - s + 1) + n) + 1024, "the set does not overflow the first capacity"
+    host.sr_db_clean(C.byref(db))
+    ref.free(rdb)
+
+
 def test_empty_collection(host):
     bases, off = pack_reads([b"ACGTTGCA", b"NNNN", b""])
     db = SrDb()

@@ -1,1 +1,1 @@
-ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:"^(?!.*(at::|unnamed|cub::|thrust::|elementwise)).*" -c 400 --csv --log-file gpurun_out/r02c_launches.csv python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu --no-whole --no-sweep > gpurun_out/r02c_launches.log 2>&1; echo "launch list rc=$?"
+python -m pytest tests/test_host_layer.py -m gpu -x -q 2>&1 | tail -12
