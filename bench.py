@@ -564,8 +564,10 @@ def run_e2e(torch, lib, ctx, batch, bases, off, n_reads, total, sizes, csz, step
     upload, kernels and download overlap) -> sg_stat -> sg_count -> sg_count_download on the master batch.
     Every input byte crosses PCIe inside the timed region and every result array lands in pinned host memory.
     full=False (the headline, what syncasm() does): the run lengths (ho_rl, 1 B per hoco base, whose one consumer -- the
-    run-length consensus -- is served on the device by sg_runlen_sums) stay in HBM; everything else is downloaded.
-    full=True: ho_rl travels too, i.e. every field of the reference's sr_t lands on the host (the round-1 e2e)."""
+    run-length consensus -- is served on the device by sg_runlen_sums) and the packed bases (hoco_s, 1/4 B per hoco base:
+    read error correction and the consensus texts are served by sg_ec_correct / sg_kmer_codes) stay in HBM; the syncmer
+    lists of every read, the syncmer database and the ids are downloaded.
+    full=True: both travel too, i.e. every field of the reference's sr_t lands on the host (the round-1 e2e)."""
     pin = lambda n, dt: torch.empty(max(int(n), 1), dtype=dt, pin_memory=True)
     # pinned host memory: ~31 KB per read (input + every output array). All ranks of a node share the
     # host RAM, so the e2e batch is capped to what fits in half of what is available now.
@@ -592,7 +594,7 @@ def run_e2e(torch, lib, ctx, batch, bases, off, n_reads, total, sizes, csz, step
     bufs = {
         "hoco_l": pin(n_reads, torch.int32), "n_scm": pin(n_reads, torch.int32),
         "hoco_s_off": pin(n_reads + 1, torch.int64), "ho_rl_off": pin(n_reads + 1, torch.int64), "scm_off": pin(n_reads + 1, torch.int64),
-        "hoco_s_buf": pin(sizes.hoco_s_bytes * slack + 4096, torch.uint8),
+        "hoco_s_buf": pin(sizes.hoco_s_bytes * slack + 4096 if full else 16, torch.uint8),
         "ho_rl_buf": pin(sizes.ho_rl_bytes * slack + 4096 if full else 16, torch.uint8),
         "m_pos": pin(N * slack, torch.int32), "s_mer": pin(N * slack, torch.int64), "k_mer": pin(N * slack, torch.int64),
         "amb_sid": pin(1024, torch.int32), "amb_pos": pin(1024, torch.int32),
@@ -603,6 +605,7 @@ def run_e2e(torch, lib, ctx, batch, bases, off, n_reads, total, sizes, csz, step
     o.k_mer = None     # k_mer[] is delivered once, as ids, by sg_count_download (the reference overwrites the hashes too, syncmer.c:1378)
     if not full:
         o.ho_rl_buf = None                         # stays on the device (sg_pipe keeps it in the master batch)
+        o.hoco_s_buf = None                        # and so do the packed bases: their consumers are served there (sg_kmer_codes, sg_ec_correct)
     caps = lib.PipeCaps(int(N * slack), bufs["hoco_s_buf"].numel(), bufs["ho_rl_buf"].numel(), 1024, 1024)
     co = lib.CountOut()
     cb = {"h": pin(U * slack, torch.int64), "s": pin(U * slack, torch.int64), "cov": pin(U * slack, torch.int32),
@@ -654,10 +657,10 @@ def run_e2e(torch, lib, ctx, batch, bases, off, n_reads, total, sizes, csz, step
     U = int(pipe.master.count_sizes().n_unique)
     h2d = total + 8 * (n_reads + n_reads // chunk + 1)
     NA = int(pipe.master.count_sizes().n_syncmers)          # tuples of this rank's hash range (== N on one GPU)
-    d2h = int(z.hoco_s_bytes + (z.ho_rl_bytes if full else 0) + 12 * N + 8 * n_reads + 28 * U + 16 * NA + (8 * N if world > 1 else 0))
+    d2h = int((z.hoco_s_bytes + z.ho_rl_bytes if full else 0) + 12 * N + 8 * n_reads + 28 * U + 16 * NA + (8 * N if world > 1 else 0))
     res = {"value": world * total / sec, "unit": "bases/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": d2h,
            "ms_per_step": sec * 1e3, "steps": steps, "reads_per_gpu": n_reads, "gpu_launches_per_step": int(launches), "chunk_reads": chunk, "streams": n_slots,
-           "run_lengths": "downloaded (every sr_t field on the host)" if full else "resident in HBM, served by sg_runlen_sums (what syncasm() does)",
+           "run_lengths": "downloaded with the packed bases (every sr_t field on the host)" if full else "resident in HBM with the packed bases, served by sg_runlen_sums / sg_kmer_codes / sg_ec_correct (what syncasm() does)",
            "path": "sg_pipe_run_host (chunks of %d reads over several streams) -> sg_stat -> sg_count -> sg_count_download; pinned host buffers; "
                    "%s" % (chunk, "one GPU" if world == 1 else "with the tuple exchange and the id return over NCCL (sg_comm_*) between extract and count; "
                                   "each rank downloads its hash range of the database and the global ids of its reads")}

@@ -59,7 +59,7 @@ const char *sg_last_error(sg_ctx *ctx);
 /* number of kernels launched by this context since creation (bench.py's gpu_launches) */
 uint64_t sg_ctx_launches(sg_ctx *ctx);
 /* per-stage device time of the most recent call, CUDA events on the context's stream */
-enum { SG_T_ENCODE = 0, SG_T_SCAN, SG_T_KMERHASH, SG_T_PLACE, SG_T_SORT, SG_T_GROUP, SG_T_STAT, SG_T_ARCS, SG_T_PACK, SG_T_EC, SG_T_N };
+enum { SG_T_ENCODE = 0, SG_T_SCAN, SG_T_KMERHASH, SG_T_PLACE, SG_T_SORT, SG_T_GROUP, SG_T_STAT, SG_T_ARCS, SG_T_PACK, SG_T_EC, SG_T_EXCH, SG_T_IDS, SG_T_N };
 int sg_ctx_enable_timing(sg_ctx *ctx, int on);
 int sg_ctx_timings(sg_ctx *ctx, float *ms /* SG_T_N */, uint32_t *launches /* SG_T_N */);
 
@@ -123,6 +123,10 @@ int sg_extract_download(sg_batch *b, const sg_extract_out_t *out);
  * on the device: a batch after sg_extract, or a pipe's master batch with sg_pipe_keep_run_lengths. Synchronises. */
 int sg_runlen_sums(sg_batch *b, uint64_t n_req, const uint64_t *occ_off, const uint64_t *occ, uint64_t *sums /* host, n_req * k */);
 int sg_runlen_resident(sg_batch *b);                          /* 1 when sg_runlen_sums can be served */
+/* hoco bases of n_req stretches of `len` positions, one code 0..3 per byte (n_req x len), read from the device-resident
+ * packed bases: refs[i] = read << 32 | first hoco position. What get_kmer_seq (syncmer.c:1105-1125) reads from sr_t.hoco_s,
+ * for read databases whose packed bases stayed on the device (sg_pipe_keep_packed_bases). */
+int sg_kmer_codes(sg_batch *b, uint64_t n_req, const uint64_t *refs, int len, uint8_t *codes);
 
 /* ---- f2: the per-read pass of read error correction on the device ----
  * Replaces the kt_for over reads inside read_error_correction (reference syncerr.c:342-612 per read, :144-288 dfs_search,
@@ -258,6 +262,9 @@ uint64_t sg_pipe_launches(sg_pipe *p);
  * being downloaded; sg_runlen_sums then serves the one consumer they have, the run-length consensus. sg_pipe_run_host does the
  * same on its own when the caller passes no ho_rl buffer. */
 int sg_pipe_keep_run_lengths(sg_pipe *p, int on);
+/* 1: the packed bases (hoco_s, a quarter byte per hoco base) are not downloaded either; sg_kmer_codes serves the consensus.
+ * sg_pipe_run_host does the same on its own when the caller passes no hoco_s buffer. */
+int sg_pipe_keep_packed_bases(sg_pipe *p, int on);
 /* Callback form: the master batch has room for `factor` times the expected number of syncmers (2 per window of k - s + 1
  * bases; default 16, never more than one per base). Low-complexity input (short tandem repeats tie at every position) can
  * exceed that: the run then ends with SG_E_NOMEM and sg_pipe_syncmer_overflow() = 1, and the caller repeats it with a

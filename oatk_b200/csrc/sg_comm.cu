@@ -285,6 +285,7 @@ int sg_comm_exchange_tuples(sg_comm *c, sg_batch *b)
     cudaStream_t st = ctx->stream;
     CK(cudaSetDevice(ctx->device));
     const int W = c->world;
+    ctx->t_begin(SG_T_EXCH);
     int rc = tuples_partition_device(b, W);                 // b->tuples grouped by destination, b->part_counts = end offsets
     if (rc) return rc;
     RS(c->cnt_dev, (size_t) W * 8);
@@ -302,7 +303,9 @@ int sg_comm_exchange_tuples(sg_comm *c, sg_batch *b)
     RS(c->recv, (total + 1) * 32);
     rc = all_to_all_v(c, (const uint64_t *) b->tuples.p, c->send_counts, (uint64_t *) c->recv.p, c->recv_counts, 4);
     if (rc) return rc;
-    return sg_tuples_adopt(b, c->recv.p, total);
+    rc = sg_tuples_adopt(b, c->recv.p, total);
+    ctx->t_end(SG_T_EXCH);
+    return rc;
 }
 
 int sg_comm_return_ids(sg_comm *c, sg_batch *b, uint64_t *id_base, uint64_t *n_unique_total)
@@ -316,6 +319,7 @@ int sg_comm_return_ids(sg_comm *c, sg_batch *b, uint64_t *id_base, uint64_t *n_u
     CK(cudaSetDevice(ctx->device));
     const int W = c->world;
     RS(c->uniq_dev, (size_t) (W + 1) * 8);
+    ctx->t_begin(SG_T_IDS);
     uint64_t *mine = c->mat_host + (size_t) W * W + W;       // pinned scratch word
     *mine = b->n_unique;
     CK(cudaMemcpyAsync((uint64_t *) c->uniq_dev.p + W, mine, 8, cudaMemcpyHostToDevice, st));
@@ -332,6 +336,7 @@ int sg_comm_return_ids(sg_comm *c, sg_batch *b, uint64_t *id_base, uint64_t *n_u
     if (rc) return rc;
     CK(cudaMemcpyAsync(c->mat_host + (size_t) W * W, c->uniq_dev.p, (size_t) W * 8, cudaMemcpyDeviceToHost, st));
     rc = sg_ids_scatter(b, c->back.p, b->n_syncmers);       // synchronises
+    ctx->t_end(SG_T_IDS);
     if (rc) return rc;
     c->uniq.assign(c->mat_host + (size_t) W * W, c->mat_host + (size_t) W * W + W);
     uint64_t base = 0, tot = 0;

@@ -74,6 +74,7 @@ struct sg_pipe {
     uint64_t sid_base = 0;       // global index of the first read (multi-GPU: this GPU's block of the read set)
     unsigned cap_factor = 16;    // callback form: room for this many times the expected number of syncmers in the master batch
     bool overflowed = false;     // the last run ended because that room was not enough (sg_pipe_syncmer_overflow)
+    bool keep_hs = false;        // hoco_s is not downloaded either (it is in the master batch anyway): sg_kmer_codes serves the consensus
     bool keep_rl = false;        // ho_rl stays on the device (master batch) instead of travelling to the host: sg_runlen_sums serves the consensus
 };
 
@@ -148,6 +149,7 @@ int sg_pipe_set_capacity_factor(sg_pipe *p, unsigned factor)
 int sg_pipe_syncmer_overflow(sg_pipe *p) { return p && p->overflowed ? 1 : 0; }
 
 int sg_pipe_keep_run_lengths(sg_pipe *p, int on) { if (!p) return SG_E_ARG; p->keep_rl = on != 0; return SG_OK; }
+int sg_pipe_keep_packed_bases(sg_pipe *p, int on) { if (!p) return SG_E_ARG; p->keep_hs = on != 0; return SG_OK; }
 
 int sg_pipe_set_sid_base(sg_pipe *p, uint64_t sid_base) { if (!p) return SG_E_ARG; p->sid_base = sid_base; return SG_OK; }
 
@@ -283,7 +285,7 @@ static int pipe_run(sg_pipe *p, const char *bases, const uint64_t *off, uint64_t
                 cv.wait(g, [&] { return next_chunk == c; });
                 base = tot;
                 if (!rc && !first_err) {
-                    if (tot.scm + z.n_syncmers > capN || (!cb && (tot.hs + z.hoco_s_bytes > caps->hoco_s_bytes ||
+                    if (tot.scm + z.n_syncmers > capN || (!cb && ((out->hoco_s_buf && tot.hs + z.hoco_s_bytes > caps->hoco_s_bytes) ||
                             (out->ho_rl_buf && tot.rl + z.ho_rl_bytes > caps->ho_rl_bytes) || tot.amb + z.n_ambiguous > caps->max_ambiguous ||
                             tot.lrl + z.n_long_runs > caps->max_long_runs))) {
                         rc = SG_E_NOMEM; msg = "caller capacities too small";
@@ -341,6 +343,7 @@ static int pipe_run(sg_pipe *p, const char *bases, const uint64_t *off, uint64_t
                 for (int j = 0; j < 15; ++j) ok = ok && in->stage[j];
                 double t3 = now(); tp[2] += t3 - t2;
                 if (keep_rl) o.ho_rl_buf = nullptr;        // stays on the device
+                if (p->keep_hs) o.hoco_s_buf = nullptr;
                 rc = ok ? sg_extract_download(b, &o) : SG_E_NOMEM;
                 double t4 = now(); tp[3] += t4 - t3;
                 if (!rc) rc = cb(cb_user, r0, nr, &o, &z);

@@ -99,6 +99,27 @@ __global__ void __launch_bounds__(256) runlen_sum_kernel(RunlenArgs A)
     }
 }
 
+// hoco bases of requested stretches, one code (0..3) per byte: what get_kmer_seq reads from sr_t.hoco_s when the packed
+// bases stayed on the device. One warp per request.
+__global__ void __launch_bounds__(256) kmer_codes_kernel(const uint64_t *hoff, const uint8_t *hoco_s, const uint32_t *hoco_l, uint64_t sid_base, uint64_t n_reads,
+        const uint64_t *refs, uint64_t n_req, int len, uint8_t *out, unsigned long long *bad)
+{
+    const int lane = threadIdx.x & 31;
+    const uint64_t w0 = ((uint64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((uint64_t) gridDim.x * blockDim.x) >> 5;
+    for (uint64_t rq = w0; rq < n_req; rq += nw) {
+        const uint64_t e = refs[rq];
+        const uint64_t sid = (e >> 32) - sid_base;
+        const uint32_t start = (uint32_t) e;
+        const bool ok = sid < n_reads && (uint64_t) start + (uint64_t) len <= (uint64_t) hoco_l[sid < n_reads ? sid : 0];
+        if (!ok) { if (lane == 0) atomicAdd(bad, 1ull); continue; }
+        const uint8_t *hs = hoco_s + hoff[sid] / 4;
+        for (int i = lane; i < len; i += 32) {
+            const uint32_t p = start + (uint32_t) i;
+            out[rq * (uint64_t) len + i] = (uint8_t) ((hs[p >> 2] >> ((3 - (p & 3)) << 1)) & 3);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) lrl_key_kernel(const uint32_t *sid, const uint32_t *idx, const uint32_t *val, uint64_t n, uint64_t sid_base,
         uint64_t *key, uint64_t *v)
 {
@@ -119,6 +140,33 @@ static inline unsigned nblk(uint64_t n, unsigned t) { return (unsigned) ((n + t 
 extern "C" {
 
 int sg_runlen_resident(sg_batch *b) { return b && b->extracted && b->rl_resident ? 1 : 0; }
+
+int sg_kmer_codes(sg_batch *b, uint64_t n_req, const uint64_t *refs, int len, uint8_t *codes)
+{
+    if (!b || len < 1 || (n_req && (!refs || !codes))) return SG_E_ARG;
+    if (!b->extracted) return SG_E_STATE;
+    sg_ctx *ctx = b->ctx;
+    cudaStream_t st = ctx->stream;
+    CK(cudaSetDevice(ctx->device));
+    if (n_req == 0) return SG_OK;
+    RS(b->rq_occ, (n_req + 1) * 8); RS(b->rq_out, n_req * (uint64_t) len + 16); RS(b->status, 4 * 8);
+    CK(cudaMemsetAsync(b->status.p, 0, 8, st));
+    CK(cudaMemcpyAsync(b->rq_occ.p, refs, n_req * 8, cudaMemcpyHostToDevice, st));
+    ctx->t_begin(SG_T_PACK);
+    kmer_codes_kernel<<<(unsigned) std::min<uint64_t>((n_req + 7) / 8, 148ull * 16ull), 256, 0, st>>>((const uint64_t *) b->hoff.p, (const uint8_t *) b->hoco_s.p,
+            (const uint32_t *) b->hoco_l.p, b->sid_base, b->n_reads, (const uint64_t *) b->rq_occ.p, n_req, len, (uint8_t *) b->rq_out.p, (unsigned long long *) b->status.p);
+    ctx->count_launch(SG_T_PACK, 1);
+    ctx->t_end(SG_T_PACK);
+    unsigned long long bad = 0;
+    CK(cudaMemcpyAsync(codes, b->rq_out.p, n_req * (uint64_t) len, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&bad, b->status.p, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    b->h2d_bytes += n_req * 8;
+    b->d2h_bytes += n_req * (uint64_t) len;
+    if (bad) { ctx->err = std::to_string(bad) + " requested stretches lie outside their read"; return SG_E_ARG; }
+    return SG_OK;
+}
 
 int sg_runlen_sums(sg_batch *b, uint64_t n_req, const uint64_t *occ_off, const uint64_t *occ, uint64_t *sums)
 {

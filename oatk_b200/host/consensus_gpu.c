@@ -206,9 +206,16 @@ __attribute__((optimize("O3"))) static void lane_add_rev(uint16_t *restrict lane
  * syncmer ids[i] in its own orientation, sum over the uncorrected copies of (run length - 1) per hoco position. */
 typedef struct {
     const int64_t *row_of;        /* per syncmer id: row, or -1 */
-    const uint64_t *sums;         /* rows x w */
+    const uint64_t *sums;         /* rows x w, or NULL when the reads carry ho_rl */
     const uint32_t *copies;       /* per row: uncorrected copies */
+    const uint8_t *codes;         /* rows x w hoco codes of the row's first uncorrected occurrence as it lies on its read, or NULL
+                                     when the reads carry hoco_s */
 } rl_table_t;
+/* l codes from position p of a k-mer whose w codes (as on the read) are `fwd`: forwards, or reverse-complemented like get_kmer_seq */
+static void codes_from_row(const uint8_t *fwd, uint64_t p, uint64_t l, uint64_t r, uint8_t *out)
+{
+    for (uint64_t i = 0; i < l; ++i) out[i] = (uint8_t) (r ? 3 - fwd[p + l - 1 - i] : fwd[p + i]);
+}
 
 /* out == NULL: only the length is wanted (arc overlaps) */
 static int64_t syncmer_text(const sr_db_t *db, const syncmer_t *m, int rev, int64_t from, txt_t *out, int hoco_only, const rl_table_t *rlt, uint64_t id)
@@ -239,9 +246,20 @@ static int64_t syncmer_text(const sr_db_t *db, const syncmer_t *m, int rev, int6
         return written;
     }
     if (!r) p += (uint64_t) from;
+    /* the occurrence's bases: from the read, or -- for reads whose packed bases stayed on the device -- from the row the
+     * device sent for this syncmer (its w codes as they lie on the read, from the occurrence's start) */
+    const uint8_t *row_codes = 0;
+    if (!s->hoco_s) {
+        assert(rlt && rlt->codes && rlt->row_of[id] >= 0);
+        row_codes = rlt->codes + (size_t) rlt->row_of[id] * (size_t) w;
+    }
     if (hoco_only) {
         txt_room(out, l);
-        get_kmer_dna_seq(s->hoco_s, (uint32_t) p, (int) l, (uint32_t) r, out->s + out->l);
+        if (row_codes) {
+            uint8_t *dst = (uint8_t *) out->s + out->l;
+            codes_from_row(row_codes, r ? 0 : (uint64_t) from, l, r, dst);
+            for (uint64_t j = 0; j < l; ++j) dst[j] = (uint8_t) char_nt4_table[dst[j]];
+        } else get_kmer_dna_seq(s->hoco_s, (uint32_t) p, (int) l, (uint32_t) r, out->s + out->l);
         out->l += l;
         return written;
     }
@@ -251,7 +269,7 @@ static int64_t syncmer_text(const sr_db_t *db, const syncmer_t *m, int rev, int6
      * rare runs of 255 or more, kept in a side list per read, are patched in on top */
     uint64_t *tot = (uint64_t *) calloc(l, sizeof(uint64_t));
     uint32_t copies = 0, pending = 0;
-    if (rlt) {
+    if (rlt && rlt->sums) {
         /* the device summed the copies in the syncmer's forward frame F[0..w): position j of this view is F[from + j]
          * on the forward strand and F[w - 1 - from - j] on the reverse one */
         const int64_t row = rlt->row_of[id];
@@ -304,7 +322,8 @@ static int64_t syncmer_text(const sr_db_t *db, const syncmer_t *m, int rev, int6
         return written;
     }
     uint8_t *code = (uint8_t *) malloc(l);
-    get_kmer_seq(s->hoco_s, (uint32_t) p, (int) l, (uint32_t) r, code);
+    if (row_codes) codes_from_row(row_codes, r ? 0 : (uint64_t) from, l, r, code);
+    else get_kmer_seq(s->hoco_s, (uint32_t) p, (int) l, (uint32_t) r, code);
     for (uint64_t j = 0; j < l; ++j) {
         const long extra = lround((double) tot[j] / copies);
         const char c = char_nt4_table[code[j]];
@@ -483,11 +502,11 @@ static void cons_run(cons_job_t *J, int phase, uint64_t n_items)
 }
 
 /* run-length sums already fetched from the device for the syncmers of one read database (see scg_consensus) */
-static struct { const sr_db_t *db; size_t n_scm; int64_t *row_of; uint64_t *sums; uint32_t *copies; uint64_t n_rows; } g_rl;
+static struct { const sr_db_t *db; size_t n_scm; int64_t *row_of; uint64_t *sums; uint32_t *copies; uint8_t *codes; uint64_t n_rows; int with_sums, with_codes; } g_rl;
 void oatk_cons_cache_drop(const sr_db_t *db)
 {
     if (db && g_rl.db != db) return;
-    free(g_rl.row_of); free(g_rl.sums); free(g_rl.copies);
+    free(g_rl.row_of); free(g_rl.sums); free(g_rl.copies); free(g_rl.codes);
     memset(&g_rl, 0, sizeof(g_rl));
 }
 
@@ -556,13 +575,16 @@ void scg_consensus(sr_db_t *sr_db, scg_t *scg, int hoco_seq, int save_seq, FILE 
      * three times on graphs made of the same syncmers (.utg.gfa, after unzipping, .utg.final.gfa), so the answers are kept
      * until the lists change (g_rl: dropped by oatk_cons_cache_drop from read_error_correction and sr_db_clean). */
     rl_table_t rlt;
-    if (!hoco_seq && oatk_gpu_run_lengths_on_device(sr_db)) {
+    const int need_sums = !hoco_seq && oatk_gpu_run_lengths_on_device(sr_db);
+    const int need_codes = oatk_gpu_bases_on_device(sr_db);                 /* sr_t.hoco_s == NULL: the bases come from the device too */
+    if (need_sums || need_codes) {
         const syncmer_t *scm = scg->scm_db->a;
         const size_t n_scm = scg->scm_db->n;
-        uint64_t n_new = 0, n_occ = 0, j, *ids, *occ_off, *occ;
-        if (g_rl.db != sr_db || g_rl.n_scm != n_scm) {
+        const size_t w = (size_t) sr_db->k;
+        uint64_t n_new = 0, n_occ = 0, j, *ids, *occ_off, *occ, *refs;
+        if (g_rl.db != sr_db || g_rl.n_scm != n_scm || (need_sums && !g_rl.with_sums) || (need_codes && !g_rl.with_codes)) {
             oatk_cons_cache_drop(0);
-            g_rl.db = sr_db; g_rl.n_scm = n_scm;
+            g_rl.db = sr_db; g_rl.n_scm = n_scm; g_rl.with_sums = need_sums; g_rl.with_codes = need_codes;
             g_rl.row_of = (int64_t *) malloc(sizeof(int64_t) * (n_scm ? n_scm : 1));
             for (j = 0; j < n_scm; ++j) g_rl.row_of[j] = -1;
         }
@@ -584,30 +606,49 @@ void scg_consensus(sr_db_t *sr_db, scg_t *scg, int hoco_seq, int save_seq, FILE 
         if (n_new) {
             occ_off = (uint64_t *) malloc(sizeof(uint64_t) * (n_new + 1));
             occ = (uint64_t *) malloc(sizeof(uint64_t) * (n_occ ? n_occ : 1));
+            refs = (uint64_t *) malloc(sizeof(uint64_t) * n_new);
             g_rl.copies = (uint32_t *) realloc(g_rl.copies, sizeof(uint32_t) * (row0 + n_new));
-            g_rl.sums = (uint64_t *) realloc(g_rl.sums, sizeof(uint64_t) * (row0 + n_new) * (size_t) sr_db->k);
+            if (g_rl.with_sums) g_rl.sums = (uint64_t *) realloc(g_rl.sums, sizeof(uint64_t) * (row0 + n_new) * w);
+            if (g_rl.with_codes) g_rl.codes = (uint8_t *) realloc(g_rl.codes, (row0 + n_new) * w);
             n_occ = 0;
             for (j = 0; j < n_new; ++j) {
                 const syncmer_t *m = &scm[ids[j]];
                 occ_off[j] = n_occ;
+                refs[j] = UINT64_MAX;
                 for (uint32_t c = 0; c < m->cov; ++c) {
                     if (occ_is_corrected(sr_db, m->m_pos[c])) continue;
-                    occ[n_occ++] = (m->m_pos[c] >> 32) << 32 | sr_db->a[m->m_pos[c] >> 32].m_pos[m->m_pos[c] >> 1 & MAX_RD_SCM];
+                    const uint64_t mp = sr_db->a[m->m_pos[c] >> 32].m_pos[m->m_pos[c] >> 1 & MAX_RD_SCM];
+                    if (refs[j] == UINT64_MAX) refs[j] = (m->m_pos[c] >> 32) << 32 | (mp >> 1);    /* the first one supplies the bases */
+                    occ[n_occ++] = (m->m_pos[c] >> 32) << 32 | mp;
                 }
                 g_rl.copies[row0 + j] = (uint32_t) (n_occ - occ_off[j]);
             }
             occ_off[n_new] = n_occ;
-            oatk_tick("cons: run-length requests");
-            if (oatk_gpu_runlen_sums(sr_db, n_new, occ_off, occ, g_rl.sums + row0 * (size_t) sr_db->k) != 0) {
+            oatk_tick("cons: run-length / base requests");
+            if (g_rl.with_sums && oatk_gpu_runlen_sums(sr_db, n_new, occ_off, occ, g_rl.sums + row0 * w) != 0) {
                 fprintf(stderr, "[E::%s] the run lengths could not be read from the device\n", __func__);
                 exit(EXIT_FAILURE);
             }
+            if (g_rl.with_codes) {
+                /* syncmers every copy of which was corrected away have no text (N): they ask for nothing */
+                uint64_t n_ref = 0, *pack = (uint64_t *) malloc(sizeof(uint64_t) * n_new);
+                for (j = 0; j < n_new; ++j) if (refs[j] != UINT64_MAX) pack[n_ref++] = refs[j];
+                uint8_t *tmp = (uint8_t *) malloc((n_ref ? n_ref : 1) * w);
+                if (oatk_gpu_kmer_codes(sr_db, n_ref, pack, (int) w, tmp) != 0) {
+                    fprintf(stderr, "[E::%s] the bases could not be read from the device\n", __func__);
+                    exit(EXIT_FAILURE);
+                }
+                for (j = 0, n_ref = 0; j < n_new; ++j)
+                    if (refs[j] != UINT64_MAX) memcpy(g_rl.codes + (row0 + j) * w, tmp + (n_ref++) * w, w);
+                    else memset(g_rl.codes + (row0 + j) * w, 0, w);
+                free(tmp); free(pack);
+            }
             g_rl.n_rows = row0 + n_new;
-            free(occ_off); free(occ);
-            oatk_tick("cons: run-length sums from the device");
+            free(occ_off); free(occ); free(refs);
+            oatk_tick("cons: run-length sums / bases from the device");
         }
         free(ids);
-        rlt.row_of = g_rl.row_of; rlt.sums = g_rl.sums; rlt.copies = g_rl.copies;
+        rlt.row_of = g_rl.row_of; rlt.sums = g_rl.with_sums ? g_rl.sums : 0; rlt.copies = g_rl.copies; rlt.codes = g_rl.with_codes ? g_rl.codes : 0;
         J.rlt = &rlt;
     }
 

@@ -149,9 +149,14 @@ int syncasm(char **file_in, int n_file, size_t m_data, int k, int s, int bubble_
          * consumer, the run-length consensus, is served on the device: the array -- as large as the input -- is not
          * downloaded. OATK_FULL_READS=1 keeps the full records; a caller with meta always gets them. */
         const char *full = getenv("OATK_FULL_READS");
-        const int was = oatk_gpu_keep_run_lengths(!meta && !(full && atoi(full) > 0));
+        const int lean = !meta && !(full && atoi(full) > 0);
+        const int was = oatk_gpu_keep_run_lengths(lean);
+        /* ... and the packed bases (sr_t.hoco_s) with them when the reads are going to be corrected on the device: their
+         * other consumer, the consensus, asks the device for the few k-mers it writes out */
+        const int was_hs = oatk_gpu_keep_packed_bases(lean && !getenv("OATK_EC_HOST"));
         rc = sr_read_files(sr_db, (const char *const *) file_in, n_file, m_data);
         oatk_gpu_keep_run_lengths(was);
+        oatk_gpu_keep_packed_bases(was_hs);
     }
     if (rc != 0) {
         fprintf(stderr, "[E::%s] failed to read the input files (%d)\n", __func__, rc);

@@ -798,6 +798,10 @@ void read_error_correction(sr_db_t *sr_db, scg_t *g, double max_edist, uint32_t 
     int on_device = 0;
     if (!(force_host && atoi(force_host) > 0)) on_device = correct_reads_on_device(sr_db, g, max_edist, stats) == 0;
     g_last_on_device = on_device;
+    if (!on_device && oatk_gpu_bases_on_device(sr_db)) {
+        fprintf(stderr, "[E::%s] the packed bases of the reads are on the device only and the device search did not run\n", __func__);
+        exit(EXIT_FAILURE);
+    }
     if (!on_device) {
         uint64_t next = 0;
         for (int t = 0; t < n_threads; ++t) { J[t].db = sr_db; J[t].g = g; J[t].max_edist = max_edist; J[t].next = &next; }

@@ -36,8 +36,11 @@ int oatk_gpu_set_device(int device) { g_device = device; return 0; }
 /* 1: sr_read_mem / sr_read_files / sr_read leave the run lengths (sr_t.ho_rl, one byte per hoco base: as large as the input)
  * on the device; sr_t.ho_rl is NULL and scg_consensus gets its run-length sums from there (oatk_gpu_runlen_sums). syncasm()
  * switches it on; callers of the API get the full read records unless they ask. */
-static int g_keep_rl;
+static int g_keep_rl, g_keep_hs;
 int oatk_gpu_keep_run_lengths(int on) { const int was = g_keep_rl; g_keep_rl = on != 0; return was; }
+/* the same for the packed bases (sr_t.hoco_s == NULL): their consumers under syncasm() -- the consensus texts and the
+ * read error correction -- are served on the device (oatk_gpu_kmer_codes, sg_ec_correct) */
+int oatk_gpu_keep_packed_bases(int on) { const int was = g_keep_hs; g_keep_hs = on != 0; return was; }
 
 static sg_batch *batch_of(sr_db_t *db, int create)
 {
@@ -128,7 +131,7 @@ static int fill_chunk(void *user, uint64_t r0, uint64_t nr, const sg_extract_out
         if (f->names && f->names[r0 + i]) r->sname = strdup(f->names[r0 + i]);
         else { snprintf(nm, sizeof(nm), "r%lu", (unsigned long) (r0 + i)); r->sname = strdup(nm); }
         r->hoco_l = c->hoco_l[i];
-        r->hoco_s = (uint8_t *) dup_block(c->hoco_s_buf + c->hoco_s_off[i], (c->hoco_l[i] + 3) / 4);
+        r->hoco_s = c->hoco_s_buf ? (uint8_t *) dup_block(c->hoco_s_buf + c->hoco_s_off[i], (c->hoco_l[i] + 3) / 4) : 0;   /* NULL: resident on the device */
         r->ho_rl = c->ho_rl_buf ? (uint8_t *) dup_block(c->ho_rl_buf + c->ho_rl_off[i], c->hoco_l[i]) : 0;   /* NULL: resident on the device */
         while (ia < z->n_ambiguous && c->amb_sid[ia] == i) ++ia;
         r->n_nucl = (uint32_t *) dup_block(c->amb_pos + a0, 4 * (ia - a0));
@@ -174,6 +177,7 @@ int sr_read_mem(sr_db_t *sr_db, const char *bases, const uint64_t *off, char **n
     sr_db->n = sr_db->m = n_reads;
     f.db = sr_db; f.names = names;
     sg_pipe_keep_run_lengths(pipe, g_keep_rl);
+    sg_pipe_keep_packed_bases(pipe, g_keep_hs);
     /* the pipeline's master batch is cut for 16 times the expected number of syncmers; low-complexity reads (a
      * dinucleotide repeat ties at every position: one syncmer per base) can need more, where the reference simply goes on:
      * the run is repeated with more room until there is one slot per base */
@@ -609,6 +613,26 @@ int oatk_gpu_run_lengths_on_device(sr_db_t *sr_db)
     if (!b || !sg_runlen_resident(b)) return 0;
     for (i = 0; i < sr_db->n; ++i) if (sr_db->a[i].hoco_l) return sr_db->a[i].ho_rl == 0;
     return 0;
+}
+
+/* 1 when the packed bases of this read database live on the device only (see oatk_gpu_keep_packed_bases) */
+int oatk_gpu_bases_on_device(sr_db_t *sr_db)
+{
+    uint64_t i;
+    if (!batch_of(sr_db, 0)) return 0;
+    for (i = 0; i < sr_db->n; ++i) if (sr_db->a[i].hoco_l) return sr_db->a[i].hoco_s == 0;
+    return 0;
+}
+
+/* hoco bases (codes 0..3, one per byte) of n stretches of len positions: refs[i] = read << 32 | first position (sg_kmer_codes) */
+int oatk_gpu_kmer_codes(sr_db_t *sr_db, uint64_t n, const uint64_t *refs, int len, uint8_t *codes)
+{
+    sg_batch *b = batch_of(sr_db, 0);
+    int rc;
+    if (!b) return SG_E_STATE;
+    rc = sg_kmer_codes(b, n, refs, len, codes);
+    if (rc != SG_OK) fprintf(stderr, "[E::%s] %s: %s\n", __func__, sg_strerror(rc), sg_last_error(ctx_of(sr_db)));
+    return rc;
 }
 
 /* sums of (run length - 1) per hoco position for n_req syncmers over the listed occurrences (sg_runlen_sums) */

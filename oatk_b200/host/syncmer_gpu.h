@@ -129,6 +129,9 @@ int oatk_gpu_set_device(int device);
 /* run lengths stay on the device (sr_t.ho_rl == NULL) for the read databases made from now on; returns the previous setting */
 int oatk_gpu_keep_run_lengths(int on);
 int oatk_gpu_run_lengths_on_device(sr_db_t *sr_db);
+int oatk_gpu_keep_packed_bases(int on);          /* sr_t.hoco_s stays on the device as well (NULL on the host) */
+int oatk_gpu_bases_on_device(sr_db_t *sr_db);
+int oatk_gpu_kmer_codes(sr_db_t *sr_db, uint64_t n, const uint64_t *refs, int len, uint8_t *codes);
 int oatk_gpu_runlen_sums(sr_db_t *sr_db, uint64_t n_req, const uint64_t *occ_off, const uint64_t *occ, uint64_t *sums);
 /* the per-read pass of read error correction on the device (syncerr_gpu.c builds the arguments) */
 int oatk_gpu_ec_available(sr_db_t *sr_db);

@@ -108,3 +108,39 @@ def test_pipe_master_keeps_run_lengths(gpu_ctx):
     assert np.array_equal(got, exp)
     pipe.close()
     ref.close()
+
+
+@pytest.mark.parametrize("k,s", [(301, 15), (1001, 31)])
+def test_kmer_codes_match_the_packed_bases(gpu_ctx, k, s):
+    """sg_kmer_codes (the bases behind get_kmer_seq for read databases whose hoco_s stayed on the device) against the
+    downloaded packed bases of the same reads: stretches at the start, in the middle and at the very end of reads, and a
+    request outside its read must be refused"""
+    from oatk_b200 import lib
+    rng = np.random.default_rng(k + 1)
+    reads = [synth._rand(rng, int(n)) for n in rng.integers(2 * k, 6 * k, 40)]
+    bases, off = pack_reads(reads)
+    b = lib.Batch(gpu_ctx)
+    b.set_reads_host(bases, off)
+    b.extract(k, s)
+    f = b.extract_download()
+    hoco_l = f["hoco_l"].astype(np.int64)
+    hs_off = np.concatenate([[0], np.cumsum((hoco_l + 3) // 4)])      # extract_download hands the packed bases over unpadded, read after read
+    L = lib.library()
+    L.sg_kmer_codes.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_int, C.c_void_p]
+    refs, exp = [], []
+    for sid in range(len(reads)):
+        # unpack the read's bases from the compact download (4 per byte, first in the top bits)
+        o0 = int(hs_off[sid])
+        nb = (hoco_l[sid] + 3) // 4
+        packed = f["hoco_s"][o0:o0 + nb]
+        codes = np.stack([(packed >> 6) & 3, (packed >> 4) & 3, (packed >> 2) & 3, packed & 3], axis=1).reshape(-1)[:hoco_l[sid]]
+        for start in (0, int(hoco_l[sid] - k) // 2, int(hoco_l[sid] - k)):
+            refs.append((sid << 32) | start)
+            exp.append(codes[start:start + k])
+    refs = np.array(refs, np.uint64)
+    out = np.zeros((len(refs), k), np.uint8)
+    assert L.sg_kmer_codes(b.h, len(refs), refs.ctypes.data, k, out.ctypes.data) == 0
+    assert np.array_equal(out, np.stack(exp).astype(np.uint8))
+    bad = np.array([(0 << 32) | int(hoco_l[0] - k + 1)], np.uint64)
+    assert L.sg_kmer_codes(b.h, 1, bad.ctypes.data, k, out.ctypes.data) != 0
+    b.close()
