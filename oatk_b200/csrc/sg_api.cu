@@ -144,6 +144,7 @@ static void reset_state(sg_batch *b)
     b->keys_are_ids = false;
     b->tup_valid = false;
     b->atup_valid = false;
+    b->asoa_valid = true;
     b->k = b->s = 0;
     b->n_syncmers = 0;
 }

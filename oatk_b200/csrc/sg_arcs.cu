@@ -254,6 +254,31 @@ int arcs_sort_unpack(sg_batch *b, uint64_t na)
 
 // this batch's tuples grouped by hash range (b->tuples, 4 words each, (sid, idx) order kept inside a part);
 // b->part_counts[p] = end offset of part p, 0 for an empty part. No host synchronisation.
+// records (occ, s_mer, fp, hash) of the adopted set -> the four arrays the pair sort and sg_ids_pack read
+__global__ void __launch_bounds__(256) unrecord_kernel(const ulonglong4 *rec, uint64_t n, uint64_t *key, uint64_t *occ, uint64_t *smer, uint64_t *fp)
+{
+    const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const ulonglong4 t = rec[i];
+    occ[i] = t.x; smer[i] = t.y; fp[i] = t.z; key[i] = t.w;
+}
+
+int ensure_adopted_soa(sg_batch *b)
+{
+    if (!b->adopted || b->asoa_valid) return SG_OK;
+    sg_ctx *ctx = b->ctx;
+    cudaStream_t st = ctx->stream;
+    const uint64_t n = b->n_adopted;
+    RS(b->akey, (n + 1) * 8); RS(b->aocc, (n + 1) * 8); RS(b->asmer, (n + 1) * 8); RS(b->afp, (n + 1) * 8);
+    if (n) {
+        unrecord_kernel<<<nblk(n, 256), 256, 0, st>>>((const ulonglong4 *) b->tup.p, n, (uint64_t *) b->akey.p, (uint64_t *) b->aocc.p,
+                (uint64_t *) b->asmer.p, (uint64_t *) b->afp.p);
+        ctx->count_launch(SG_T_SORT, 1);
+    }
+    b->asoa_valid = true;
+    return SG_OK;
+}
+
 int tuples_partition_device(sg_batch *b, int n_parts)
 {
     sg_ctx *ctx = b->ctx;
@@ -362,6 +387,7 @@ int sg_tuples_adopt(sg_batch *b, const void *d_tuples, uint64_t n)
     }
     CK(cudaGetLastError());
     b->atup_valid = true;
+    b->asoa_valid = true;
     b->adopted = true;
     b->n_adopted = n;
     b->sorted = b->counted = false;
@@ -376,6 +402,7 @@ int sg_ids_pack(sg_batch *b, uint64_t id_base, void **d_pairs, uint64_t *n)
     cudaStream_t st = ctx->stream;
     CK(cudaSetDevice(ctx->device));
     const uint64_t N = b->n_adopted;
+    { const int rc_ = ensure_adopted_soa(b); if (rc_) return rc_; }
     RS(b->tuples, (N + 1) * 32);
     if (N) {
         pair_pack_kernel<<<nblk(N, 256), 256, 0, st>>>((const uint64_t *) b->aocc.p, (const uint64_t *) b->kid.p, N, id_base, (uint64_t *) b->tuples.p);

@@ -83,7 +83,8 @@ struct sg_comm {
     sg_ctx *ctx = nullptr;
     ncclComm_t comm = nullptr;
     int world = 1, rank = 0;
-    DevBuf cnt_dev, mat_dev, uniq_dev, recv, back, gather, covs, scratch, pcount, pcursor, ppairs;
+    DevBuf cnt_dev, mat_dev, uniq_dev, recv, back, gather, covs, scratch, pcount, pcursor, ppairs, split_counts, split_sums, perm, sent_dev;
+    bool fast = false;                       // the last exchange split the extract's records directly (perm holds where each sent record came from)
     uint64_t *mat_host = nullptr;            // pinned, world x world (+ world for the distinct counts)
     std::vector<uint64_t> send_counts, recv_counts;   // of the last tuple exchange
     std::vector<uint64_t> uniq;              // distinct k-mers per rank after sg_comm_return_ids
@@ -98,6 +99,96 @@ struct sg_comm {
 static inline unsigned nblk(uint64_t n, unsigned t) { return (unsigned) ((n + t - 1) / t); }
 
 namespace sg {
+
+// ---- the exchange without detours: the 32-byte records kmerhash_kernel wrote are split by destination in one stable
+// pass (per-tile counts, one scan, ranked scatter as in the radix sort) straight into the send buffer, together with the
+// index each record came from; what comes back after counting is then just the id of every sent record, in the order it
+// was sent, and the saved indices put the ids into read order. No (key, value) sort, no gather, no (occ, id) pairs.
+constexpr int SP_NT = 256, SP_NW = SP_NT / 32, SP_IPT = 8, SP_TILE = SP_NT * SP_IPT;
+__device__ __forceinline__ uint32_t part_of(uint64_t h, uint32_t world) { return (uint32_t) __umul64hi((h >> 1) << 1, (uint64_t) world); }
+
+__global__ void __launch_bounds__(SP_NT) split_hist_kernel(const uint64_t *key, uint64_t n, uint32_t world, uint32_t *counts, uint32_t ntiles)
+{
+    __shared__ uint32_t h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    const uint64_t base = (uint64_t) blockIdx.x * SP_TILE;
+#pragma unroll
+    for (int j = 0; j < SP_IPT; ++j) {
+        const uint64_t i = base + (uint64_t) j * SP_NT + threadIdx.x;
+        if (i < n) atomicAdd(&h[part_of(key[i], world)], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < world) counts[(uint64_t) threadIdx.x * ntiles + blockIdx.x] = h[threadIdx.x];
+}
+
+// counts[] holds exclusive offsets now; part p starts at counts[p * ntiles]
+__global__ void split_counts_kernel(const uint32_t *offsets, uint32_t ntiles, int world, uint64_t n, uint64_t *cnt)
+{
+    const int p = threadIdx.x;
+    if (p >= world) return;
+    const uint64_t a = offsets[(uint64_t) p * ntiles], b = p + 1 < world ? offsets[(uint64_t) (p + 1) * ntiles] : n;
+    cnt[p] = b - a;
+}
+
+__global__ void __launch_bounds__(SP_NT) split_scatter_kernel(const uint64_t *key, const ulonglong4 *rec, uint64_t n, uint32_t world,
+        const uint32_t *offsets, uint32_t ntiles, ulonglong4 *out, uint32_t *perm)
+{
+    __shared__ uint32_t wc[SP_NW][256];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < SP_NW * 256; i += SP_NT) (&wc[0][0])[i] = 0;
+    __syncthreads();
+    const uint64_t wbase = (uint64_t) blockIdx.x * SP_TILE + (uint64_t) wid * 32 * SP_IPT;
+    uint32_t rank[SP_IPT], dig[SP_IPT];
+#pragma unroll
+    for (int j = 0; j < SP_IPT; ++j) {
+        const uint64_t i = wbase + (uint64_t) j * 32 + lane;
+        const bool ok = i < n;
+        const uint32_t d = ok ? part_of(key[i], world) : 0x100u;
+        const uint32_t peers = __match_any_sync(SG_FULL, d);
+        const uint32_t before = __popc(peers & ((1u << lane) - 1u));
+        uint32_t base = 0;
+        if (ok) base = wc[wid][d];
+        __syncwarp();
+        if (ok && before == 0) wc[wid][d] = base + __popc(peers);
+        __syncwarp();
+        rank[j] = base + before;
+        dig[j] = d;
+    }
+    __syncthreads();
+    if (threadIdx.x < world) {
+        uint32_t run = offsets[(uint64_t) threadIdx.x * ntiles + blockIdx.x];
+#pragma unroll
+        for (int w = 0; w < SP_NW; ++w) { const uint32_t t = wc[w][threadIdx.x]; wc[w][threadIdx.x] = run; run += t; }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < SP_IPT; ++j) {
+        const uint64_t i = wbase + (uint64_t) j * 32 + lane;
+        if (i < n) {
+            const uint64_t o = (uint64_t) wc[wid][dig[j]] + rank[j];
+            out[o] = rec[i];
+            perm[o] = (uint32_t) i;
+        }
+    }
+}
+
+// ids of the records this rank sent, back in the order they were sent (part after part): kid_local[perm[j]] = id + base of the owner
+__global__ void __launch_bounds__(256) ids_unpermute_kernel(const uint64_t *back, const uint32_t *perm, uint64_t n, const uint64_t *sent /* world counts */,
+        const uint64_t *uniq /* world */, int world, uint64_t *kid_local)
+{
+    __shared__ uint64_t s_end[256], s_base[256];
+    if (threadIdx.x == 0) {
+        uint64_t e = 0, b = 0;
+        for (int p = 0; p < world; ++p) { e += sent[p]; s_end[p] = e; s_base[p] = b; b += uniq[p]; }
+    }
+    __syncthreads();
+    const uint64_t j = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    int lo = 0, hi = world - 1;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (s_end[mid] <= j) lo = mid + 1; else hi = mid; }
+    kid_local[perm[j]] = back[j] + (s_base[lo] << 1);
+}
 
 // end offsets of the parts (0 = the part is empty) -> counts
 __global__ void ends_to_counts_kernel(const unsigned long long *ends, int n_parts, uint64_t *counts)
@@ -286,11 +377,29 @@ int sg_comm_exchange_tuples(sg_comm *c, sg_batch *b)
     CK(cudaSetDevice(ctx->device));
     const int W = c->world;
     ctx->t_begin(SG_T_EXCH);
-    int rc = tuples_partition_device(b, W);                 // b->tuples grouped by destination, b->part_counts = end offsets
-    if (rc) return rc;
+    int rc;
+    const uint64_t N = b->n_syncmers;
+    c->fast = b->tup_valid && N < (1ull << 32) && !getenv("SG_COMM_PAIRS");
     RS(c->cnt_dev, (size_t) W * 8);
-    ends_to_counts_kernel<<<1, 32, 0, st>>>((const unsigned long long *) b->part_counts.p, W, (uint64_t *) c->cnt_dev.p);
-    ctx->count_launch(SG_T_SORT, 1);
+    if (c->fast) {
+        const uint32_t ntiles = (uint32_t) ((N + SP_TILE - 1) / SP_TILE);
+        const uint64_t m = (uint64_t) std::max<uint32_t>(ntiles, 1) * W;
+        RS(c->split_counts, (m + 8) * 4); RS(c->split_sums, (m / 2048 + 16) * 4); RS(c->perm, (N + 1) * 4); RS(b->tuples, (N + 1) * 32);
+        if (N) {
+            split_hist_kernel<<<ntiles, SP_NT, 0, st>>>((const uint64_t *) b->key.p, N, (uint32_t) W, (uint32_t *) c->split_counts.p, ntiles);
+            const int nl = launch_exscan_u32((uint32_t *) c->split_counts.p, m, (uint32_t *) c->split_sums.p, st);
+            split_counts_kernel<<<1, 256, 0, st>>>((const uint32_t *) c->split_counts.p, ntiles, W, N, (uint64_t *) c->cnt_dev.p);
+            split_scatter_kernel<<<ntiles, SP_NT, 0, st>>>((const uint64_t *) b->key.p, (const ulonglong4 *) b->tup.p, N, (uint32_t) W,
+                    (const uint32_t *) c->split_counts.p, ntiles, (ulonglong4 *) b->tuples.p, (uint32_t *) c->perm.p);
+            ctx->count_launch(SG_T_EXCH, 3 + nl);
+        } else CK(cudaMemsetAsync(c->cnt_dev.p, 0, (size_t) W * 8, st));
+        b->sorted = false;
+    } else {
+        rc = tuples_partition_device(b, W);                 // b->tuples grouped by destination, b->part_counts = end offsets
+        if (rc) return rc;
+        ends_to_counts_kernel<<<1, 32, 0, st>>>((const unsigned long long *) b->part_counts.p, W, (uint64_t *) c->cnt_dev.p);
+        ctx->count_launch(SG_T_SORT, 1);
+    }
     rc = gather_count_matrix(c, (const uint64_t *) c->cnt_dev.p);
     if (rc) return rc;
     c->send_counts.assign(W, 0); c->recv_counts.assign(W, 0);
@@ -299,6 +408,21 @@ int sg_comm_exchange_tuples(sg_comm *c, sg_batch *b)
         c->send_counts[p] = c->mat_host[(size_t) c->rank * W + p];
         c->recv_counts[p] = c->mat_host[(size_t) p * W + c->rank];
         total += c->recv_counts[p];
+    }
+    if (c->fast) {
+        RS(c->sent_dev, (size_t) W * 8);                     // how many records went to each rank: the id return needs it after mat_dev has been reused
+        CK(cudaMemcpyAsync(c->sent_dev.p, c->cnt_dev.p, (size_t) W * 8, cudaMemcpyDeviceToDevice, st));
+        // the records arrive in the layout the packed sort of sg_count gathers from: they land where it looks for them.
+        // (The extract's own records were consumed by the split; room for a quarter more than a fair share, grow-only.)
+        RS(b->tup, (std::max<uint64_t>(total, N) + std::max<uint64_t>(total, N) / 4 + 1024) * 32);
+        b->tup_valid = false;
+        rc = all_to_all_v(c, (const uint64_t *) b->tuples.p, c->send_counts, (uint64_t *) b->tup.p, c->recv_counts, 4);
+        if (rc) return rc;
+        b->atup_valid = true; b->asoa_valid = false;
+        b->adopted = true; b->n_adopted = total;
+        b->sorted = b->counted = false;
+        ctx->t_end(SG_T_EXCH);
+        return SG_OK;
     }
     RS(c->recv, (total + 1) * 32);
     rc = all_to_all_v(c, (const uint64_t *) b->tuples.p, c->send_counts, (uint64_t *) c->recv.p, c->recv_counts, 4);
@@ -325,19 +449,39 @@ int sg_comm_return_ids(sg_comm *c, sg_batch *b, uint64_t *id_base, uint64_t *n_u
     CK(cudaMemcpyAsync((uint64_t *) c->uniq_dev.p + W, mine, 8, cudaMemcpyHostToDevice, st));
     NK(N->AllGather((const uint64_t *) c->uniq_dev.p + W, c->uniq_dev.p, 1, ncclUint64, c->comm, st));
     const uint64_t n = b->n_adopted;
+    int rc;
+    if (c->fast) {
+        // ids of the adopted records, in the order they arrived, go back as they are (8 bytes each)
+        RS(c->back, (b->n_syncmers + 1) * 8);
+        rc = all_to_all_v(c, (const uint64_t *) b->kid.p, c->recv_counts, (uint64_t *) c->back.p, c->send_counts, 1);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(c->mat_host + (size_t) W * W, c->uniq_dev.p, (size_t) W * 8, cudaMemcpyDeviceToHost, st));
+        RS(b->kid_local, (b->n_syncmers + 1) * 8);
+        if (b->n_syncmers) {
+            ids_unpermute_kernel<<<nblk(b->n_syncmers, 256), 256, 0, st>>>((const uint64_t *) c->back.p, (const uint32_t *) c->perm.p, b->n_syncmers,
+                    (const uint64_t *) c->sent_dev.p, (const uint64_t *) c->uniq_dev.p, W, (uint64_t *) b->kid_local.p);
+            ctx->count_launch(SG_T_IDS, 1);
+        }
+        CK(cudaStreamSynchronize(st));
+        CK(cudaGetLastError());
+        b->have_kid_local = true;
+        ctx->t_end(SG_T_IDS);
+    } else {
     RS(b->tuples, (n + 1) * 32);
     if (n) {
+        { const int rc_ = sg::ensure_adopted_soa(b); if (rc_) return rc_; }
         pair_pack_base_kernel<<<nblk(n, 256), 256, 0, st>>>((const uint64_t *) b->aocc.p, (const uint64_t *) b->kid.p, n,
                 (const uint64_t *) c->uniq_dev.p, c->rank, (uint64_t *) b->tuples.p);
         ctx->count_launch(SG_T_GROUP, 1);
     }
     RS(c->back, (b->n_syncmers + 1) * 16);
-    int rc = all_to_all_v(c, (const uint64_t *) b->tuples.p, c->recv_counts, (uint64_t *) c->back.p, c->send_counts, 2);
+    rc = all_to_all_v(c, (const uint64_t *) b->tuples.p, c->recv_counts, (uint64_t *) c->back.p, c->send_counts, 2);
     if (rc) return rc;
     CK(cudaMemcpyAsync(c->mat_host + (size_t) W * W, c->uniq_dev.p, (size_t) W * 8, cudaMemcpyDeviceToHost, st));
     rc = sg_ids_scatter(b, c->back.p, b->n_syncmers);       // synchronises
     ctx->t_end(SG_T_IDS);
     if (rc) return rc;
+    }
     c->uniq.assign(c->mat_host + (size_t) W * W, c->mat_host + (size_t) W * W + W);
     uint64_t base = 0, tot = 0;
     for (int r = 0; r < W; ++r) { if (r < c->rank) base += c->uniq[r]; tot += c->uniq[r]; }

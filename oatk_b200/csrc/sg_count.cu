@@ -535,6 +535,7 @@ static int ensure_sorted(sg_batch *b)
         b->sort_fell_back = true;                             // too many or too long runs: the pair sort on all 64 bits below
         full = true;
     }
+    { const int rc_ = sg::ensure_adopted_soa(b); if (rc_) return rc_; }       // the pair sort reads the four arrays
     for (int attempt = 0; attempt < 2; ++attempt) {
         tuple_init_kernel<<<nblk(N, 256), 256, 0, st>>>(b->t_key(), (uint64_t *) b->skey.p, (uint64_t *) b->sval.p, N, hmask);
         ctx->count_launch(SG_T_SORT, 1);
@@ -964,7 +965,7 @@ int sg_batch_buffer(sg_batch *b, int which, void **ptr, uint64_t *n)
         case SG_BUF_SORTED_OCC: *ptr = b->socc.p; *n = b->sorted ? b->t_n() : 0; break;
         case SG_BUF_SCM_H: *ptr = b->scm_h.p; *n = b->counted ? b->n_unique : 0; break;
         case SG_BUF_SCM_COV: *ptr = b->scm_cov.p; *n = b->counted ? b->n_unique : 0; break;
-        case SG_BUF_ADOPTED_OCC: *ptr = b->aocc.p; *n = b->n_adopted; break;
+        case SG_BUF_ADOPTED_OCC: { const int rc_ = sg::ensure_adopted_soa(b); if (rc_) return rc_; *ptr = b->aocc.p; *n = b->n_adopted; break; }
         default: return SG_E_ARG;
     }
     return SG_OK;

@@ -54,7 +54,8 @@ struct sg_batch {
     sg::DevBuf key, occ, m_pos, s_mer, fp;      // read order, one entry per syncmer (fp: second hash)
     sg::DevBuf tup;                              // read order: (occ, s_mer, fp, key) as 32-byte records (sg_extract only)
     bool tup_valid = false;
-    bool atup_valid = false;                     // tup holds the records of the ADOPTED tuple set (sg_tuples_adopt)
+    bool atup_valid = false;
+    bool asoa_valid = true;                      // akey / aocc / asmer / afp hold the adopted tuples (false: only the records in tup do; sg::ensure_adopted_soa)                     // tup holds the records of the ADOPTED tuple set (sg_tuples_adopt)
     // download staging
     sg::DevBuf pk_hs, pk_rl, pk_hs_off, pk_rl_off;
     std::vector<uint32_t> h_hoco_l, h_n_scm;
@@ -98,5 +99,6 @@ struct sg_batch {
 };
 
 namespace sg {
+int ensure_adopted_soa(sg_batch *b);
 int launch_pack(sg_batch *b, cudaStream_t st, bool want_hs, bool want_rl);
 }

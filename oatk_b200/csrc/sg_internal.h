@@ -80,6 +80,7 @@ int launch_capacity_offsets(const uint64_t *off, uint64_t *hoff, uint64_t n, uin
 size_t sort_tmp_words(uint64_t n);
 int launch_sort_pairs(uint64_t *key, uint64_t *val, uint64_t *key_alt, uint64_t *val_alt, uint64_t n,
         int begin_bit, int end_bit, uint32_t *tmp, cudaStream_t st);
+int launch_exscan_u32(uint32_t *a, uint64_t n, uint32_t *sums, cudaStream_t st);
 // the same for bare 64-bit words (a payload can ride in the bits below begin_bit); result in key
 int launch_sort_keys(uint64_t *key, uint64_t *key_alt, uint64_t n, int begin_bit, int end_bit, uint32_t *tmp, cudaStream_t st);
 

@@ -214,6 +214,17 @@ __global__ void __launch_bounds__(RS_NT) rs_scatter_kernel(const uint64_t *key, 
     }
 }
 
+// in-place exclusive scan of n uint32 (total < 2^32); sums must hold n / 2048 + 8 words
+int launch_exscan_u32(uint32_t *a, uint64_t n, uint32_t *sums, cudaStream_t st)
+{
+    if (n == 0) return 0;
+    const uint64_t nb = (n + SCAN_TILE - 1) / SCAN_TILE;
+    rs_scan_reduce<<<(unsigned) nb, SCAN_NT, 0, st>>>(a, n, sums);
+    rs_scan_sums<<<1, 1024, 0, st>>>(sums, nb);
+    rs_scan_apply<<<(unsigned) nb, SCAN_NT, 0, st>>>(a, n, sums);
+    return 3;
+}
+
 // keys only (the value rides in the low bits of the key word): same stable scatter, half the traffic
 __global__ void __launch_bounds__(RS_NT) rs_scatter_keys_kernel(const uint64_t *key, uint64_t *okey, uint64_t n, int shift, const uint32_t *offsets, uint32_t ntiles)
 {
