@@ -17,6 +17,12 @@ READS10K = dict(seed=42, G=500000, N=10000, L=15000, err=0.001,
                 after_ec=("number syncmers collected: 210358", "number uniqe kmer: 37977"),
                 final=("number unitigs  : 17", "number syncmers : 664", "number arcs     : 0"))
 
+READS80K = dict(seed=7, G=4000000, N=80000, L=15000, err=0.001,
+                fasta_md5="36af7ad79e85c7fc6bbffae19a8928d0", fasta_bytes=1200708868,
+                hoco_total=900590458, syncmers=1714278, distinct_kmers=1001918,
+                dump_md5="756ca5945129d97276a62781a17a51cb",
+                utg_gfa_md5="725ac164ab47eb550ecc0b16c18daf38", final_gfa_md5="72255ff76991504777e34831a7372b2e")   # syncasm -k 1001 -s 31 -c 30
+
 
 def generate(seed, G, N, L, err):
     """list of reads (bytes) and the FASTA text, exactly as SURVEY.md A.1 writes them"""
