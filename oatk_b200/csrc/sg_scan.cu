@@ -72,7 +72,7 @@ __device__ __noinline__ bool settle_tie(const uint16_t *ring, int RCH, const uin
     return mp <= mo && (mp <= e64 || mp < mo || m64_at(p - q + 1) == mp);
 }
 
-template <int S_FIXED, int RCH_FIXED, int LOGB_FIXED>
+template <int S_FIXED, int RCH_FIXED, int LOGB_FIXED, int OSP>
 __global__ void __launch_bounds__(32 * SYNC_SCAN_WARPS, 6) scan_kernel(ScanArgs A, ScanGeom G)
 {
     extern __shared__ __align__(16) uint32_t smem[];
@@ -80,10 +80,17 @@ __global__ void __launch_bounds__(32 * SYNC_SCAN_WARPS, 6) scan_kernel(ScanArgs 
     // (two columns) then fall into distinct banks, like the 32 chunks of a tile (one row)
     const int RCH = RCH_FIXED ? RCH_FIXED : G.rch, RM = RCH - 1, RS = RCH + 4;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    uint32_t *wbase = smem + (size_t) wid * (8 * RS + 2 * RCH + 2 * LISTCAP + 64);
+    constexpr int NLV = OSP < 0 ? 1 : 2;               // arrays of chunk minima: one without the split
+    uint32_t *wbase = smem + (size_t) wid * (8 * RS + (NLV + 1) * RCH + 2 * LISTCAP + 64);
     uint16_t *ring = reinterpret_cast<uint16_t *>(wbase);   // [16][RS] 15-bit keys of m[]
-    uint32_t *Lv0 = wbase + 8 * RS;                    // [RCH] chunk minima (32-bit)
-    uint32_t *sfxA = Lv0 + RCH;                        // [RCH] suffix minimum of the chunk's block from the chunk on
+    // The elements e(p) = m[p - q] that leave the windows of a chunk's 16 positions are the positions of offset >= osp in
+    // one chunk and those of offset < osp in the next (osp = -q mod 16, the same for every chunk): the minimum of a chunk
+    // is kept in these two halves, so that the OPEN flag of step 3 looks at exactly the 16 leaving elements. With the
+    // offset known at compile time (OSP >= 0: the shapes of the benchmark sweep) the split costs nothing in the hash loop;
+    // otherwise both halves hold the whole chunk's minimum (the looser test of the two chunks).
+    uint32_t *LvHi = wbase + 8 * RS;                   // [RCH] minimum over the chunk's positions of offset >= osp (32-bit)
+    uint32_t *LvLo = OSP < 0 ? LvHi : LvHi + RCH;      // [RCH] ... of offset < osp
+    uint32_t *sfxA = LvHi + NLV * RCH;                       // [RCH] suffix minimum of the chunk's block from the chunk on
     uint32_t *list_c = sfxA + RCH;                     // [LISTCAP] chunk index
     uint32_t *list_e = list_c + LISTCAP;               // [LISTCAP] E | Om << 16
     uint32_t *wbuf = list_e + LISTCAP;                 // [2][32] packed words of the next tile, filled by cp.async
@@ -119,7 +126,7 @@ __global__ void __launch_bounds__(32 * SYNC_SCAN_WARPS, 6) scan_kernel(ScanArgs 
 
         // chunk minima in front of the read must say "no hash"; the position ring needs no clearing: every
         // position a window can reach (>= 0) is written, hash or NONE, by the tile that holds it
-        for (int i = lane; i < 2 * RCH; i += 32) Lv0[i] = HNONE;                 // Lv0, sfxA
+        for (int i = lane; i < (NLV + 1) * RCH; i += 32) LvHi[i] = HNONE;        // LvHi, (LvLo,) sfxA
         __syncwarp();
 
         uint32_t n_emitted = 0, carryC = 0;
@@ -220,7 +227,7 @@ __global__ void __launch_bounds__(32 * SYNC_SCAN_WARPS, 6) scan_kernel(ScanArgs 
             }
 
             // 1. keys of my 16 positions
-            uint32_t cmin = HNONE;
+            uint32_t cmin = HNONE, cmLo = HNONE;           // minimum of the offsets >= OSP (all of them without a split) / < OSP
             uint16_t *own = ring + cs;
             if (vm && S_FIXED == 31) {
                 // s = 31: every position is extracted straight from the three words around it (no rolling
@@ -230,7 +237,10 @@ __global__ void __launch_bounds__(32 * SYNC_SCAN_WARPS, 6) scan_kernel(ScanArgs 
                 if (vm == 0xffffu) {
 #define SG_H31_PAIR(J) { uint32_t hi, lo, hi2, lo2; h31_canon<J>(wa, wb, w0, ra, rb, rc, hi, lo); h31_canon<(J) + 1>(wa, wb, w0, ra, rb, rc, hi2, lo2); \
                         const uint32_t hv = h31_hash_top(hi, lo, G.h31), hv2 = h31_hash_top(hi2, lo2, G.h31); \
-                        own[(J) * RS] = (uint16_t) (hv >> 17); own[((J) + 1) * RS] = (uint16_t) (hv2 >> 17); cmin = min(cmin, min(hv, hv2)); }
+                        own[(J) * RS] = (uint16_t) (hv >> 17); own[((J) + 1) * RS] = (uint16_t) (hv2 >> 17); \
+                        if (OSP < 0 || (J) >= OSP) cmin = min(cmin, min(hv, hv2)); \
+                        else if ((J) + 1 < OSP) cmLo = min(cmLo, min(hv, hv2)); \
+                        else { cmLo = min(cmLo, hv); cmin = min(cmin, hv2); } }
                     SG_H31_PAIR(0) SG_H31_PAIR(2) SG_H31_PAIR(4) SG_H31_PAIR(6) SG_H31_PAIR(8) SG_H31_PAIR(10) SG_H31_PAIR(12) SG_H31_PAIR(14)
 #undef SG_H31_PAIR
                 } else {
@@ -241,7 +251,7 @@ __global__ void __launch_bounds__(32 * SYNC_SCAN_WARPS, 6) scan_kernel(ScanArgs 
                         const bool ok = (vm >> j) & 1u;
                         const uint32_t hv = h31_hash_top(hi, lo, G.h31);
                         own[j * RS] = (uint16_t) (ok ? hv >> 17 : KNONE);
-                        if (ok) cmin = min(cmin, hv);
+                        if (ok) { if (OSP < 0 || j >= OSP) cmin = min(cmin, hv); else cmLo = min(cmLo, hv); }
                     }
                 }
             } else if (vm) {
@@ -267,6 +277,8 @@ __global__ void __launch_bounds__(32 * SYNC_SCAN_WARPS, 6) scan_kernel(ScanArgs 
             }
 
             // 2. minimum over the n_full whole chunks in front of mine: prefix / suffix minima inside blocks of B lanes
+            const uint32_t cmHi = cmin;
+            cmin = min(cmin, cmLo);
             uint32_t pfx = cmin, sfx = cmin;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
@@ -276,7 +288,8 @@ __global__ void __launch_bounds__(32 * SYNC_SCAN_WARPS, 6) scan_kernel(ScanArgs 
                     if (lb + d < B) sfx = min(sfx, dn);
                 }
             }
-            Lv0[cs] = cmin;
+            LvHi[cs] = cmHi;
+            if (OSP >= 0) LvLo[cs] = cmLo;
             sfxA[cs] = sfx;
             uint32_t pex = __shfl_up_sync(SG_FULL, pfx, 1);                // my block's chunks in front of me
             if (lb == 0) pex = HNONE;
@@ -301,7 +314,7 @@ __global__ void __launch_bounds__(32 * SYNC_SCAN_WARPS, 6) scan_kernel(ScanArgs 
             if (small_q) flagged = (mC | mO) != 0;
             else {
                 const int cA = (P - q) >> 4;
-                const uint32_t emin = min(Lv0[cA & RM], Lv0[(cA + 1) & RM]);
+                const uint32_t emin = min(LvHi[cA & RM], LvLo[(cA + 1) & RM]);
                 flagged = (mC && cmin <= r0) || (mO && emin <= r0);
             }
 
@@ -691,10 +704,10 @@ int scan_geometry(int k, int s, ScanGeom *g, size_t *smem_per_warp)
     return *smem_per_warp <= 227 * 1024 ? 0 : SG_E_KSIZE;
 }
 
-template <int S_FIXED, int RCH_FIXED, int LOGB_FIXED>
+template <int S_FIXED, int RCH_FIXED, int LOGB_FIXED, int OSP>
 static int launch_scan_t(const ScanArgs &A, const ScanGeom &g, size_t smem_per_warp, cudaStream_t st)
 {
-    auto kern = scan_kernel<S_FIXED, RCH_FIXED, LOGB_FIXED>;
+    auto kern = scan_kernel<S_FIXED, RCH_FIXED, LOGB_FIXED, OSP>;
     static int ctas_per_sm = 0, n_sm = 0;
     static size_t smem_set = 0;
     int warps = SYNC_SCAN_WARPS;
@@ -724,11 +737,17 @@ int launch_scan(const ScanArgs &A, cudaStream_t st)
     int rc;
     if (A.s == 31) {
         // the shapes of the benchmark sweep (k = 501, 1001, 2001) get compile-time ring and block sizes
-        if (g.rch == 64 && g.logB == 4) rc = launch_scan_t<31, 64, 4>(A, g, spw, st);
-        else if (g.rch == 128 && g.logB == 5) rc = launch_scan_t<31, 128, 5>(A, g, spw, st);
-        else if (g.rch == 256 && g.logB == 5) rc = launch_scan_t<31, 256, 5>(A, g, spw, st);
-        else rc = launch_scan_t<31, 0, -1>(A, g, spw, st);
-    } else rc = launch_scan_t<0, 0, -1>(A, g, spw, st);
+        // ... and a compile-time split of the chunk minima at -q mod 16 (k = 501: 9, k = 1001: 5, k = 2001: 13)
+        const int osp = (int) ((16u - ((unsigned) (A.k - A.s + 1) & 15u)) & 15u);
+        // (one more array of chunk minima: taken where the shared memory it costs does not cost a resident CTA)
+        const size_t spw_split = spw + sizeof(uint32_t) * (size_t) g.rch;
+        if (g.rch == 64 && g.logB == 4 && osp == 9) rc = launch_scan_t<31, 64, 4, 9>(A, g, spw_split, st);
+        else if (g.rch == 128 && g.logB == 5 && osp == 5) rc = launch_scan_t<31, 128, 5, 5>(A, g, spw_split, st);
+        else if (g.rch == 64 && g.logB == 4) rc = launch_scan_t<31, 64, 4, -1>(A, g, spw, st);
+        else if (g.rch == 128 && g.logB == 5) rc = launch_scan_t<31, 128, 5, -1>(A, g, spw, st);
+        else if (g.rch == 256 && g.logB == 5) rc = launch_scan_t<31, 256, 5, -1>(A, g, spw, st);
+        else rc = launch_scan_t<31, 0, -1, -1>(A, g, spw, st);
+    } else rc = launch_scan_t<0, 0, -1, -1>(A, g, spw, st);
     if (rc < 0) return rc;
     // the reads scan_kernel deferred (none on ordinary sequence: the kernel then finds an empty list and returns)
     const int rc2 = launch_scan_exact(A, st);
