@@ -57,13 +57,19 @@ __device__ __forceinline__ uint64_t kmer_murmur_interior(const uint32_t *hs, int
     const uint32_t *w = hs + (p0 >> 4);
     uint32_t a = bswap32(__ldg(w)), b = bswap32(__ldg(w + 1)), c = bswap32(__ldg(w + 2));
     const uint32_t nall = nblk + ((nbytes & 7u) ? 1u : 0u);
+    // the strands of the k-mers of a warp are a coin toss each: both directions go through the same instructions
+    // (selects, no branches), or every iteration would run twice
+    const int step = rev ? -2 : 2, o1 = rev ? 0 : 1;
     for (uint32_t j = 0; j < nall; ++j) {
         uint64_t be = (uint64_t) __funnelshift_l(b, a, sh) << 32 | __funnelshift_l(c, b, sh);
-        if (rev) be = rc64(be);
+        const uint64_t rcbe = rc64(be);
+        be = rev ? rcbe : be;
         // next window: two words on (forward) or two words back (reverse); one word is shared
         if (j + 1 < nall) {
-            if (!rev) { w += 2; a = c; b = bswap32(__ldg(w + 1)); c = bswap32(__ldg(w + 2)); }
-            else { w -= 2; c = a; a = bswap32(__ldg(w)); b = bswap32(__ldg(w + 1)); }
+            w += step;
+            const uint32_t x = bswap32(__ldg(w + o1)), y = bswap32(__ldg(w + o1 + 1));
+            const uint32_t na = rev ? x : c, nb = rev ? y : x, nc = rev ? a : y;
+            a = na; b = nb; c = nc;
         }
         const int left = k - 32 * (int) j;                            // bases of the k-mer in this block
         if (left < 32) be &= ~0ull << (64 - 2 * left);

@@ -108,6 +108,7 @@ __global__ void __launch_bounds__(32 * SYNC_SCAN_WARPS, 6) scan_kernel(ScanArgs 
     // block that holds the first chunk of my window (c - n_full) and my own block
     const int lb = lane & (B - 1);
     const int n_between = n_full > 0 ? ((lane >> logB) - ((lane - n_full) >> logB) - 1) : 0;
+    const int nb_common = __reduce_min_sync(SG_FULL, n_between);
     auto ring_at = [&](int x) -> uint32_t { return ring[(x & 15) * RS + ((x >> 4) & RM)]; };
 
     for (;;) {
@@ -299,7 +300,10 @@ __global__ void __launch_bounds__(32 * SYNC_SCAN_WARPS, 6) scan_kernel(ScanArgs 
                 int sl = (c - n_full) & RM;                                  // first chunk of my window
                 r0 = min(pex, sfxA[sl]);
                 sl &= ~(B - 1);                                              // its block; block totals sit at block starts
-                for (int j = 0; j < n_between; ++j) { sl = (sl + B) & RM; r0 = min(r0, sfxA[sl]); }
+                // the lanes of a warp differ by at most one in the number of whole blocks between (it steps once where the
+                // window start crosses a block boundary): the common part runs unpredicated, the extra block is a select
+                for (int j = 0; j < nb_common; ++j) { sl = (sl + B) & RM; r0 = min(r0, sfxA[sl]); }
+                { const uint32_t t = sfxA[(sl + B) & RM]; r0 = n_between > nb_common ? min(r0, t) : r0; }
             }
 
             // 3. which chunks can hold a candidate at all
@@ -347,7 +351,8 @@ __global__ void __launch_bounds__(32 * SYNC_SCAN_WARPS, 6) scan_kernel(ScanArgs 
                         // minimum of the keys over m[p-q+1 .. p-1]: Rex covers [fc, p), the rest is scanned
                         uint32_t m = __shfl_sync(SG_FULL, Rex, bit);
                         if (small_q) m = KNONE;
-                        for (int x = p - q + 1 + lane; x < min(fc, p); x += 32) m = min(m, ring_at(x));
+                        // (at most q mod 16 + 15 positions: one per lane)
+                        { const int x = p - q + 1 + lane; if (x < min(fc, p)) m = min(m, ring_at(x)); }
                         const uint32_t Mhi = __reduce_min_sync(SG_FULL, m);
                         const uint32_t tgt = __shfl_sync(SG_FULL, mine, bit);
                         bool yes = tgt < Mhi;
