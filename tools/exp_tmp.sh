@@ -1,6 +1,4 @@
-python -m pytest tests/test_gpu_extract.py tests/test_gpu_scale.py tests/test_gpu_survey_kat.py -x -q -k "not reads80k" 2>&1 | tail -4
-python bench.py --steps 5 --warmup 3 --no-cpu --no-e2e --no-whole 2>gpurun_out/exp_bench.err | python -c "
-import json,sys
-d=json.loads(sys.stdin.readline())
-print('value', d['value']/1e9, 'ms', d['ms_per_step']); print(d['roofline']['stage_ms'])
-for e in d['k_sweep']: print(e['k'], e['value']/1e9, e['stage_ms']['scan'])"
+ncu --set full --clock-control none --import-source on -k regex:"scan_kernel" -s 1 -c 1 -o gpurun_out/r02e_scan -f python bench.py --reads 50000 --steps 1 --warmup 0 --no-e2e --no-cpu --no-sweep --no-whole > gpurun_out/r02e_ncu.log 2>&1; echo rc=$?
+ncu -i gpurun_out/r02e_scan.ncu-rep --page source --print-source cuda,sass --csv > gpurun_out/r02e_scan_cs.csv 2>/dev/null
+ncu -i gpurun_out/r02e_scan.ncu-rep --page raw --csv > gpurun_out/r02e_scan_raw.csv 2>/dev/null
+ls -la gpurun_out/r02e*
