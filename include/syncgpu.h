@@ -168,6 +168,12 @@ typedef struct {
 int sg_ec_filter(sg_batch *b, const uint8_t *del_prev, uint32_t err_mer_c, uint32_t max_err_c, uint32_t err_arc_c, double max_arc_f,
         sg_ec_filter_out_t *out);
 void sg_ec_filter_free(sg_ec_filter_out_t *out);
+/* f1: the votes of calc_syncmer_overlap (reference syncasm.c:477-582) for n arcs between single syncmers (v, w, cov, comp
+ * records as sg_ec_filter returns them), over the occurrence lists of the last sg_count: dist[i] = the most frequent
+ * difference of the two syncmers' start positions over the reads that carry them as neighbours (0 when there is none);
+ * flag[i] = 1 when two values share the highest count (the reference breaks the tie in the slot order of its hash table: the
+ * caller decides those on the host), 2 for a complement arc (no vote: it takes its mirror's value), else 0. */
+int sg_arc_votes(sg_batch *b, uint64_t n, const uint64_t *arcs4, int32_t *dist, uint8_t *flag);
 /* test hook: vertices per path and stacked wavefront entries of the first-pass search arena (default 256 / 16384) */
 int sg_debug_set_ec_arena(uint32_t path, uint32_t stash);
 

@@ -524,6 +524,72 @@ __global__ void __launch_bounds__(256) ec_live_pack_kernel(const uint64_t *arcs4
     out4[4 * o] = arcs4[4 * i]; out4[4 * o + 1] = arcs4[4 * i + 1]; out4[4 * o + 2] = arcs4[4 * i + 2]; out4[4 * o + 3] = arcs4[4 * i + 3];
 }
 
+// ---- f1: the votes of calc_syncmer_overlap (syncasm.c:477-582) for a list of arcs between single syncmers ----------------
+// The distance between two neighbouring syncmers is the most frequent difference of their hoco start positions over the
+// reads that carry both next to each other on the asked strands. One WARP per arc: a lane takes one occurrence of the first
+// syncmer, looks at the entry in front of it and the one behind it on its read, and votes when that entry is the second
+// syncmer (entries an earlier correction touched do not vote). Equal votes are merged with ballots into a table of four
+// values; more than four, or two values with the same highest count, are left to the host, which breaks the tie in the
+// slot order of the reference's hash table. No votes: 0, like the empty table there.
+struct VoteArgs {
+    const uint64_t *arcs4; uint64_t n;
+    const uint64_t *socc, *occ_off;           // occurrences of every syncmer, (sid, idx) order
+    const uint64_t *scm_off, *kid; const uint32_t *m_pos;
+    uint64_t sid_base, n_reads;
+    int32_t *dist; uint8_t *flag;             // flag 1: the host decides
+};
+__global__ void __launch_bounds__(128) arc_vote_kernel(VoteArgs A)
+{
+    const int lane = threadIdx.x & 31;
+    const uint64_t w0 = ((uint64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((uint64_t) gridDim.x * blockDim.x) >> 5;
+    for (uint64_t a = w0; a < A.n; a += nw) {
+        if (A.arcs4[4 * a + 3]) { if (lane == 0) { A.dist[a] = 0; A.flag[a] = 2; } continue; }     // a complement: takes its mirror's value
+        const uint64_t x = A.arcs4[4 * a], y = A.arcs4[4 * a + 1];
+        const uint64_t id1 = x >> 1, id2 = y >> 1, rc1 = x & 1, rc2 = y & 1;
+        const uint64_t o0 = A.occ_off[id1], o1 = A.occ_off[id1 + 1];
+        int tv[4] = {0, 0, 0, 0}, tc[4] = {0, 0, 0, 0}, nt = 0;
+        bool over = false;
+        for (uint64_t ob = o0; ob < o1; ob += 32) {
+            bool valid = false;
+            int vote = 0;
+            if (ob + lane < o1) {
+                const uint64_t oc = A.socc[ob + lane];
+                const uint64_t rd = (oc >> 32) - A.sid_base, i1 = (oc >> 1) & 0x7FFFFFFFull, s1 = oc & 1;
+                const uint64_t e0 = A.scm_off[rd], e1 = A.scm_off[rd + 1];
+                const uint64_t e = e0 + i1;
+                if (rd < A.n_reads && e < e1 && !(A.kid[e] & 1)) {
+                    const int p1 = (int) (A.m_pos[e] >> 1);
+                    if (s1 != rc1) {
+                        if (i1 >= 1) { const uint64_t kk = A.kid[e - 1]; const uint32_t mp = A.m_pos[e - 1];
+                            if ((kk >> 1) == id2 && !(kk & 1) && (uint64_t) (mp & 1) != rc2) { valid = true; vote = p1 - (int) (mp >> 1); } }
+                    } else {
+                        if (e + 1 < e1) { const uint64_t kk = A.kid[e + 1]; const uint32_t mp = A.m_pos[e + 1];
+                            if ((kk >> 1) == id2 && !(kk & 1) && (uint64_t) (mp & 1) == rc2) { valid = true; vote = (int) (mp >> 1) - p1; } }
+                    }
+                }
+            }
+            uint32_t left = __ballot_sync(SG_FULL, valid);
+            while (left) {
+                const int src = __ffs(left) - 1;
+                const int v = __shfl_sync(SG_FULL, vote, src);
+                const uint32_t same = __ballot_sync(SG_FULL, valid && vote == v);
+                left &= ~same;
+                int t = 0;
+                for (; t < nt; ++t) if (tv[t] == v) break;
+                if (t == nt) { if (nt < 4) { tv[nt] = v; tc[nt] = 0; ++nt; } else { over = true; t = 3; } }
+                tc[t] += __popc(same);
+            }
+        }
+        int best = 0, best_n = 0;
+        bool tied = false;
+        for (int t = 0; t < nt; ++t) {
+            if (tc[t] > best_n) { best_n = tc[t]; best = tv[t]; tied = false; }
+            else if (tc[t] == best_n) tied = true;
+        }
+        if (lane == 0) { A.dist[a] = best; A.flag[a] = (over || tied) ? 1 : 0; }
+    }
+}
+
 } // namespace sg
 
 using namespace sg;
@@ -737,6 +803,35 @@ extern "C" int sg_ec_filter(sg_batch *b, const uint8_t *del_prev, uint32_t err_m
     out->n_live = n_live;
     b->h2d_bytes += del_prev ? U : 0;
     b->d2h_bytes += U + n_live * 32;
+    return SG_OK;
+}
+
+
+extern "C" int sg_arc_votes(sg_batch *b, uint64_t n, const uint64_t *arcs4, int32_t *dist, uint8_t *flag)
+{
+    if (!b || (n && (!arcs4 || !dist || !flag))) return SG_E_ARG;
+    if (!b->counted || b->adopted || b->keys_are_ids || !b->sorted) return SG_E_STATE;     // the occurrence lists of the last sg_count
+    sg_ctx *ctx = b->ctx;
+    cudaStream_t st = ctx->stream;
+    CK(cudaSetDevice(ctx->device));
+    if (n == 0) return SG_OK;
+    if (b->ec_live.reserve(n * 32 + 32) || b->ec_flag.reserve(n * 4 + 16) || b->ec_err.reserve(n + 16)) { ctx->err = "device allocation failed in sg_arc_votes"; return SG_E_NOMEM; }
+    CK(cudaMemcpyAsync(b->ec_live.p, arcs4, n * 32, cudaMemcpyHostToDevice, st));
+    VoteArgs A;
+    A.arcs4 = (const uint64_t *) b->ec_live.p; A.n = n;
+    A.socc = (const uint64_t *) b->socc.p; A.occ_off = (const uint64_t *) b->scm_occ_off.p;
+    A.scm_off = (const uint64_t *) b->scm_off.p; A.kid = (const uint64_t *) b->kid.p; A.m_pos = (const uint32_t *) b->m_pos.p;
+    A.sid_base = b->sid_base; A.n_reads = b->n_reads;
+    A.dist = (int32_t *) b->ec_flag.p; A.flag = (uint8_t *) b->ec_err.p;
+    ctx->t_begin(SG_T_EC);
+    arc_vote_kernel<<<(unsigned) std::min<uint64_t>((n + 3) / 4, 148ull * 16ull), 128, 0, st>>>(A);
+    ctx->count_launch(SG_T_EC, 1);
+    ctx->t_end(SG_T_EC);
+    CK(cudaMemcpyAsync(dist, b->ec_flag.p, n * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(flag, b->ec_err.p, n, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    b->h2d_bytes += n * 32; b->d2h_bytes += n * 5;
     return SG_OK;
 }
 

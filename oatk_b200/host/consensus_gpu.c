@@ -516,7 +516,7 @@ void oatk_cons_cache_drop(const sr_db_t *db)
  * overlap = k - l when l < k, else 0, clipped to k; the value also goes to the FIRST arc (w^1, v^1) of the list -- in
  * list order, so that arcs nobody points at (a palindromic pair's second entry) keep 0 like they do there. The arcs must
  * be sorted by (v, w). Used by the graph-free form of read error correction (syncerr_gpu.c). */
-typedef struct { const sr_db_t *db; const syncmer_t *scm; const uint64_t *arcs4; int64_t *l; } ovl_job_t;
+typedef struct { const sr_db_t *db; const syncmer_t *scm; const uint64_t *arcs4; int64_t *l; const int32_t *dist; const uint8_t *flag; } ovl_job_t;
 static void ovl_range(uint64_t lo, uint64_t hi, void *arg)
 {
     ovl_job_t *J = (ovl_job_t *) arg;
@@ -526,7 +526,10 @@ static void ovl_range(uint64_t lo, uint64_t hi, void *arg)
     for (uint64_t i = lo; i < hi; ++i) {
         const uint64_t x = J->arcs4[4 * i], y = J->arcs4[4 * i + 1];
         if (J->arcs4[4 * i + 3]) { J->l[i] = -1; continue; }        /* complement */
-        int64_t l = neighbour_offset(J->db, &J->scm[x >> 1], x & 1, &J->scm[y >> 1], y & 1, &tab, 0);
+        /* the votes were counted on the device (sg_arc_votes) unless two distances tied there: the reference's answer
+         * then depends on the slot order of its hash table, which only the table below reproduces */
+        int64_t l = (J->flag && J->flag[i] == 0) ? J->dist[i]
+                  : neighbour_offset(J->db, &J->scm[x >> 1], x & 1, &J->scm[y >> 1], y & 1, &tab, 0);
         if (l < w) l = syncmer_text(J->db, &J->scm[x >> 1], (int) (x & 1), l, 0, 1, 0, x >> 1);
         else l = 0;
         if (l > w) l = w;
@@ -537,8 +540,12 @@ static void ovl_range(uint64_t lo, uint64_t hi, void *arg)
 
 void oatk_syncmer_arc_overlaps(sr_db_t *sr_db, syncmer_db_t *scm_db, uint64_t n, const uint64_t *arcs4, uint32_t *ls)
 {
-    ovl_job_t J = {sr_db, scm_db->a, arcs4, (int64_t *) malloc(sizeof(int64_t) * (n ? n : 1))};
+    ovl_job_t J = {sr_db, scm_db->a, arcs4, (int64_t *) malloc(sizeof(int64_t) * (n ? n : 1)), 0, 0};
+    int32_t *dist = (int32_t *) malloc(sizeof(int32_t) * (n ? n : 1));
+    uint8_t *flag = (uint8_t *) malloc(n ? n : 1);
+    if (n && !getenv("OATK_VOTES_HOST") && oatk_gpu_arc_votes(sr_db, n, arcs4, dist, flag) == 0) { J.dist = dist; J.flag = flag; }
     oatk_parallel_for(n, ovl_range, &J);
+    free(dist); free(flag);
     for (uint64_t i = 0; i < n; ++i) ls[i] = 0;
     for (uint64_t i = 0; i < n; ++i) {
         if (J.l[i] < 0) continue;

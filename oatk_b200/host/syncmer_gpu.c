@@ -664,6 +664,14 @@ int oatk_gpu_ec_correct(sr_db_t *sr_db, const void *graph, double max_edist, voi
     return rc;
 }
 
+/* the distance votes of a list of arcs on the device (sg_arc_votes); non-zero: count them on the host */
+int oatk_gpu_arc_votes(sr_db_t *sr_db, uint64_t n, const uint64_t *arcs4, int32_t *dist, uint8_t *flag)
+{
+    sg_batch *b = batch_of(sr_db, 0);
+    if (!b) return SG_E_STATE;
+    return sg_arc_votes(b, n, arcs4, dist, flag);          /* a state error (lists replaced since sg_count) is not an error here */
+}
+
 /* the error filter on the device (sg_ec_filter); result is an sg_ec_filter_out_t */
 int oatk_gpu_ec_filter(sr_db_t *sr_db, uint32_t err_mer_c, uint32_t max_err_c, uint32_t err_arc_c, double max_arc_f, void *result)
 {

@@ -136,6 +136,7 @@ int oatk_gpu_runlen_sums(sr_db_t *sr_db, uint64_t n_req, const uint64_t *occ_off
 /* the per-read pass of read error correction on the device (syncerr_gpu.c builds the arguments) */
 int oatk_gpu_ec_available(sr_db_t *sr_db);
 int oatk_gpu_ec_correct(sr_db_t *sr_db, const void *graph, double max_edist, void *result);
+int oatk_gpu_arc_votes(sr_db_t *sr_db, uint64_t n, const uint64_t *arcs4, int32_t *dist, uint8_t *flag);
 int oatk_gpu_ec_filter(sr_db_t *sr_db, uint32_t err_mer_c, uint32_t max_err_c, uint32_t err_arc_c, double max_arc_f, void *result);
 void oatk_cons_cache_drop(const sr_db_t *db);   /* consensus_gpu.c: forget the run-length sums kept for db (NULL: whatever is kept) */
 void oatk_gpu_shutdown(void);

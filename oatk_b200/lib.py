@@ -65,7 +65,7 @@ SYMBOLS = [
     "sg_comm_unique_id", "sg_comm_init_rank", "sg_comm_init_all", "sg_comm_destroy", "sg_comm_rank", "sg_comm_world", "sg_comm_bytes_sent",
     "sg_comm_exchange_tuples", "sg_comm_global_stat", "sg_comm_return_ids", "sg_comm_arcs",
     "sg_pipe_create", "sg_pipe_destroy", "sg_pipe_run_host", "sg_pipe_run_host_cb", "sg_pipe_master", "sg_pipe_ctx", "sg_pipe_last_error", "sg_pipe_launches", "sg_pipe_set_sid_base", "sg_pipe_keep_run_lengths", "sg_pipe_keep_packed_bases", "sg_kmer_codes", "sg_pipe_set_capacity_factor", "sg_pipe_syncmer_overflow", "sg_runlen_sums", "sg_runlen_resident",
-    "sg_ec_correct", "sg_ec_result_free", "sg_debug_set_ec_arena", "sg_ec_filter", "sg_ec_filter_free",
+    "sg_ec_correct", "sg_ec_result_free", "sg_debug_set_ec_arena", "sg_ec_filter", "sg_ec_filter_free", "sg_arc_votes",
 ]
 
 

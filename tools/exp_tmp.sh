@@ -1,4 +1,3 @@
-ncu --set full --clock-control none --import-source on -k regex:"scan_kernel" -s 1 -c 1 -o gpurun_out/r02e_scan -f python bench.py --reads 50000 --steps 1 --warmup 0 --no-e2e --no-cpu --no-sweep --no-whole > gpurun_out/r02e_ncu.log 2>&1; echo rc=$?
-ncu -i gpurun_out/r02e_scan.ncu-rep --page source --print-source cuda,sass --csv > gpurun_out/r02e_scan_cs.csv 2>/dev/null
-ncu -i gpurun_out/r02e_scan.ncu-rep --page raw --csv > gpurun_out/r02e_scan_raw.csv 2>/dev/null
-ls -la gpurun_out/r02e*
+python -m pytest tests/test_gpu_ec.py tests/test_gpu_syncasm.py tests/test_cli.py tests/test_gpu_survey_kat.py -m gpu -x -q 2>&1 | tail -6
+OATK_TIMING=1 python tools/syncasm_run.py --reads 200000 --genome 10000000 --c 30 2> gpurun_out/whole_stages.err | tail -1 | cut -c1-200
+grep -n "T::ec" gpurun_out/whole_stages.err | tail -7
