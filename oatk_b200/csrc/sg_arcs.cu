@@ -388,6 +388,7 @@ int sg_tuples_adopt(sg_batch *b, const void *d_tuples, uint64_t n)
     CK(cudaGetLastError());
     b->atup_valid = true;
     b->asoa_valid = true;
+    b->range_lo = 0; b->range_lsh = 0;                             // the caller's parts are its own business: the whole hash orders the sort
     b->adopted = true;
     b->n_adopted = n;
     b->sorted = b->counted = false;

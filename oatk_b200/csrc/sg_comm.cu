@@ -420,6 +420,15 @@ int sg_comm_exchange_tuples(sg_comm *c, sg_batch *b)
         if (rc) return rc;
         b->atup_valid = true; b->asoa_valid = false;
         b->adopted = true; b->n_adopted = total;
+        {
+            // this rank's hash range starts at ceil(rank * 2^64 / W) and is at most 2^64 / W + 1 long: inside it the hashes can be
+            // moved up by floor(log2 W) - 1 bits, which is what the packed sort of sg_count orders them by
+            const unsigned __int128 lo = (((unsigned __int128) c->rank << 64) + (unsigned) W - 1) / (unsigned) W;
+            int lg = 0;
+            while ((2 << lg) <= W) ++lg;
+            b->range_lo = (uint64_t) lo;
+            b->range_lsh = lg > 0 ? lg - 1 : 0;
+        }
         b->sorted = b->counted = false;
         ctx->t_end(SG_T_EXCH);
         return SG_OK;

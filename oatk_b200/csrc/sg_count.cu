@@ -96,10 +96,24 @@ __global__ void __launch_bounds__(128) sort_repair_kernel(uint64_t *k, uint64_t 
 // 16-byte pairs -- leaves every tuple in its final place except inside the runs that agree on 32 hash bits
 // (N^2 / 2^33 pairs: a few 10^4 at 21 M tuples). The gather then brings the whole 32-byte record (hash, occurrence,
 // s-mer code, fingerprint) of every word in, and the detect / repair pair below puts the few runs right.
-__global__ void __launch_bounds__(256) pack_init_kernel(const ulonglong4 *tup, uint64_t *pk, uint64_t n, int low_bits)
+// Which hash bits the packed sort orders: the top ones -- of the hash itself, or, for tuples adopted from other GPUs, of the
+// hash's place inside this GPU's hash range ((h - sub) << lsh: every hash of the range shares its leading bits, which
+// would otherwise use up the word's 32 bits and leave eight times as many runs to the repair at eight GPUs).
+struct RunKey { uint64_t sub; int lsh, low_bits; };
+__device__ __forceinline__ uint64_t run_of(const RunKey &K, uint64_t h) { return ((h - K.sub) << K.lsh) >> K.low_bits; }
+
+__global__ void __launch_bounds__(256) pack_init_kernel(const ulonglong4 *tup, uint64_t *pk, uint64_t n, RunKey K)
 {
     const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) pk[i] = (tup[i].w >> low_bits) << 32 | i;       // low_bits = 32: the top half of the hash stays where it is
+    if (i < n) pk[i] = run_of(K, tup[i].w) << 32 | i;            // low_bits = 32: the top half stays where it is
+}
+
+__global__ void __launch_bounds__(256) sort_check_rk_kernel(const uint64_t *k, uint64_t n, RunKey K, uint32_t *fix)
+{
+    const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i + 1 >= n) return;
+    const uint64_t a = k[i], b = k[i + 1];
+    if (run_of(K, a) == run_of(K, b) && a > b) fix[1] = 1u;
 }
 
 __global__ void __launch_bounds__(256) pack_gather_kernel(const uint64_t *pk, const ulonglong4 *tup, uint64_t *skey, uint64_t *sval, uint64_t *socc,
@@ -121,17 +135,17 @@ __global__ void __launch_bounds__(256) pack_gather_kernel(const uint64_t *pk, co
 // the same hash and an earlier position (stable) -- with the run's hashes read by all lanes together, is parked there
 // in scratch arrays, and the run is copied back. Runs were listed by sort_detect_cap_kernel.
 struct Repair5 { uint64_t *k, *v, *o, *sm, *fp, *tk, *tv, *to, *tsm, *tfp; };
-__global__ void __launch_bounds__(128) sort_repair5_kernel(Repair5 R, uint64_t n, int low_bits, uint32_t cap, uint32_t *fix)
+__global__ void __launch_bounds__(128) sort_repair5_kernel(Repair5 R, uint64_t n, RunKey K, uint32_t cap, uint32_t *fix)
 {
     const uint32_t cnt = min(fix[0], cap);
     const int lane = threadIdx.x & 31;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = (gridDim.x * blockDim.x) >> 5;
     for (uint32_t e = warp; e < cnt; e += nwarp) {
         const uint64_t i = fix[2 + e];
-        const uint64_t top = R.k[i] >> low_bits;
+        const uint64_t top = run_of(K, R.k[i]);
         uint64_t s0 = i, s1 = i + 1;
-        while (s0 > 0 && (R.k[s0 - 1] >> low_bits) == top) --s0;
-        while (s1 + 1 < n && (R.k[s1 + 1] >> low_bits) == top) ++s1;
+        while (s0 > 0 && run_of(K, R.k[s0 - 1]) == top) --s0;
+        while (s1 + 1 < n && run_of(K, R.k[s1 + 1]) == top) ++s1;
         if (s1 - s0 > SORT_FIX_MAXRUN) { if (lane == 0) fix[1] = 1u; continue; }
         for (uint64_t a = s0 + lane; a <= s1; a += 32) {
             const uint64_t ka = R.k[a];
@@ -147,14 +161,14 @@ __global__ void __launch_bounds__(128) sort_repair5_kernel(Repair5 R, uint64_t n
 }
 
 // sort_detect_kernel with a caller-sized list
-__global__ void __launch_bounds__(256) sort_detect_cap_kernel(const uint64_t *k, uint64_t n, int low_bits, uint32_t cap, uint32_t *fix)
+__global__ void __launch_bounds__(256) sort_detect_cap_kernel(const uint64_t *k, uint64_t n, RunKey K, uint32_t cap, uint32_t *fix)
 {
     const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (i + 1 >= n) return;
     const uint64_t a = k[i], b = k[i + 1];
-    if ((a >> low_bits) != (b >> low_bits) || a <= b) return;
-    const uint64_t top = a >> low_bits;
-    for (uint64_t j = i; j > 0 && (k[j - 1] >> low_bits) == top; --j) {
+    if (run_of(K, a) != run_of(K, b) || a <= b) return;
+    const uint64_t top = run_of(K, a);
+    for (uint64_t j = i; j > 0 && run_of(K, k[j - 1]) == top; --j) {
         if (k[j - 1] > k[j]) return;                       // an earlier inversion owns the run
         if (i - j > SORT_FIX_MAXRUN) { fix[1] = 1u; return; }
     }
@@ -506,20 +520,21 @@ static int ensure_sorted(sg_batch *b)
         RS(b->sort_fix, ((size_t) cap + 2) * 4);
         uint64_t *pk = (uint64_t *) b->skey_alt.p, *pk_alt = (uint64_t *) b->sval_alt.p;
         const int plow = 64 - b->pack_bits;                   // hash bits the packed sort leaves to the repair (32 unless a test moves it)
-        pack_init_kernel<<<nblk(N, 256), 256, 0, st>>>((const ulonglong4 *) b->tup.p, pk, N, plow);
+        const RunKey RK = {b->adopted ? b->range_lo : 0ull, b->adopted ? b->range_lsh : 0, plow};
+        pack_init_kernel<<<nblk(N, 256), 256, 0, st>>>((const ulonglong4 *) b->tup.p, pk, N, RK);
         ctx->count_launch(SG_T_SORT, 1);
         LAUNCHED(SG_T_SORT, launch_sort_keys(pk, pk_alt, N, 32, 32 + b->pack_bits, (uint32_t *) b->sort_tmp.p, st));
         pack_gather_kernel<<<nblk(N, 256), 256, 0, st>>>(pk, (const ulonglong4 *) b->tup.p, (uint64_t *) b->skey.p, (uint64_t *) b->sval.p,
                 (uint64_t *) b->socc.p, (uint64_t *) b->ssmer.p, (uint64_t *) b->sfp.p, N);
         CK(cudaMemsetAsync(b->sort_fix.p, 0, 8, st));
-        sort_detect_cap_kernel<<<nblk(N, 256), 256, 0, st>>>((const uint64_t *) b->skey.p, N, plow, cap, (uint32_t *) b->sort_fix.p);
+        sort_detect_cap_kernel<<<nblk(N, 256), 256, 0, st>>>((const uint64_t *) b->skey.p, N, RK, cap, (uint32_t *) b->sort_fix.p);
         // one warp per listed run (their number is known on the device only: a grid for a full list, warps without a run leave at once);
         // scratch: the two word buffers of the sort and three arrays that are filled later in the step
         RS(b->ids, (N + 2) * 8); RS(b->starts, (N + 2) * 8); RS(b->kid, (N + 1) * 8);
         Repair5 R5 = {(uint64_t *) b->skey.p, (uint64_t *) b->sval.p, (uint64_t *) b->socc.p, (uint64_t *) b->ssmer.p, (uint64_t *) b->sfp.p,
                       pk, pk_alt, (uint64_t *) b->ids.p, (uint64_t *) b->starts.p, (uint64_t *) b->kid.p};
-        sort_repair5_kernel<<<std::min<unsigned>(nblk((uint64_t) cap * 32, 128), 148u * 16u), 128, 0, st>>>(R5, N, plow, cap, (uint32_t *) b->sort_fix.p);
-        sort_check_kernel<<<nblk(N, 256), 256, 0, st>>>((const uint64_t *) b->skey.p, N, plow, (uint32_t *) b->sort_fix.p);
+        sort_repair5_kernel<<<std::min<unsigned>(nblk((uint64_t) cap * 32, 128), 148u * 16u), 128, 0, st>>>(R5, N, RK, cap, (uint32_t *) b->sort_fix.p);
+        sort_check_rk_kernel<<<nblk(N, 256), 256, 0, st>>>((const uint64_t *) b->skey.p, N, RK, (uint32_t *) b->sort_fix.p);
         ctx->count_launch(SG_T_SORT, 4);
         uint32_t hf[2];
         CK(cudaMemcpyAsync(hf, b->sort_fix.p, sizeof(hf), cudaMemcpyDeviceToHost, st));

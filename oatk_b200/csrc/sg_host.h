@@ -55,6 +55,8 @@ struct sg_batch {
     sg::DevBuf tup;                              // read order: (occ, s_mer, fp, key) as 32-byte records (sg_extract only)
     bool tup_valid = false;
     bool atup_valid = false;
+    uint64_t range_lo = 0;                       // adopted tuples: first hash of this GPU's range and how far (h - range_lo) can be shifted up
+    int range_lsh = 0;                           // without overflow (set by the exchange; 0 / 0 otherwise)
     bool asoa_valid = true;                      // akey / aocc / asmer / afp hold the adopted tuples (false: only the records in tup do; sg::ensure_adopted_soa)                     // tup holds the records of the ADOPTED tuple set (sg_tuples_adopt)
     // download staging
     sg::DevBuf pk_hs, pk_rl, pk_hs_off, pk_rl_off;
