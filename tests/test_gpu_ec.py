@@ -176,3 +176,34 @@ def test_worst_case_arena_pass(host):
     assert wd == 1 and over > 0, "no read took the worst-case pass (%d)" % over
     same(lh, ld)
     assert np.array_equal(ch, cd)
+
+
+def test_votes_on_the_device_equal_the_host_votes(host):
+    """sg_arc_votes (the distance votes of calc_syncmer_overlap on the device) against the host's vote table: the graph-free
+    error-correction step run twice, once with the votes counted on the host (OATK_VOTES_HOST=1), on reads with tandem
+    repeats of varying copy number -- where the same pair of syncmers sits at several distances and votes tie"""
+    rng = np.random.default_rng(9)
+    unit = synth._nohp(rng, 90)
+    reads = []
+    for copies in (3, 4, 5):
+        g = synth._rand(rng, 9000) + unit * copies + synth._rand(rng, 9000)
+        for _ in range(50):
+            st = int(rng.integers(0, len(g) - 8000))
+            r = bytearray(g[st:st + 8000])
+            for p in rng.integers(0, len(r), rng.binomial(len(r), 0.003)):
+                r[p] = ord("ACGT"[(b"ACGT".index(r[p]) + 1 + int(rng.integers(0, 3))) % 4])
+            r = bytes(r)
+            reads.append(synth.revcomp(r) if rng.integers(0, 2) else r)
+    reads += synth.hifi_reads(21, 30000, 200, 8000, 0.003)
+    for k, s, mkc in ((201, 15, 6), (301, 31, 8)):
+        os.environ["OATK_VOTES_HOST"] = "1"
+        try:
+            w0, _, l0, c0 = run_ec(host, reads, k, s, mkc, False, 0, graph_free=True)
+        finally:
+            os.environ.pop("OATK_VOTES_HOST", None)
+        w1, _, l1, c1 = run_ec(host, reads, k, s, mkc, False, 0, graph_free=True)
+        wh, _, lh, ch = run_ec(host, reads, k, s, mkc, True, 0)
+        assert w0 == 2 and w1 == 2 and wh == 0
+        same(l0, l1)
+        same(lh, l1)
+        assert np.array_equal(c0, c1) and np.array_equal(ch, c1)
