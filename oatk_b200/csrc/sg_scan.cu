@@ -229,13 +229,14 @@ __global__ void __launch_bounds__(32 * SYNC_SCAN_WARPS, 6) scan_kernel(ScanArgs 
 
             // 1. keys of my 16 positions
             uint32_t cmin = HNONE, cmLo = HNONE;           // minimum of the offsets >= OSP (all of them without a split) / < OSP
+            uint32_t scan_up = 0;                          // see the partial chunks below: what the minimum may be short of
             uint16_t *own = ring + cs;
             if (vm && S_FIXED == 31) {
                 // s = 31: every position is extracted straight from the three words around it (no rolling
                 // dependency between positions) and hashed in the left-aligned frame of sg_hash31.cuh.
                 // An odd s-mer cannot be its own reverse complement.
                 const uint32_t ra = rev2(~w0), rb = rev2(~wb), rc = rev2(~wa);
-                if (vm == 0xffffu) {
+                {
 #define SG_H31_PAIR(J) { uint32_t hi, lo, hi2, lo2; h31_canon<J>(wa, wb, w0, ra, rb, rc, hi, lo); h31_canon<(J) + 1>(wa, wb, w0, ra, rb, rc, hi2, lo2); \
                         const uint32_t hv = h31_hash_top(hi, lo, G.h31), hv2 = h31_hash_top(hi2, lo2, G.h31); \
                         own[(J) * RS] = (uint16_t) (hv >> 17); own[((J) + 1) * RS] = (uint16_t) (hv2 >> 17); \
@@ -244,16 +245,27 @@ __global__ void __launch_bounds__(32 * SYNC_SCAN_WARPS, 6) scan_kernel(ScanArgs 
                         else { cmLo = min(cmLo, hv); cmin = min(cmin, hv2); } }
                     SG_H31_PAIR(0) SG_H31_PAIR(2) SG_H31_PAIR(4) SG_H31_PAIR(6) SG_H31_PAIR(8) SG_H31_PAIR(10) SG_H31_PAIR(12) SG_H31_PAIR(14)
 #undef SG_H31_PAIR
-                } else {
+                }
+                if (vm != 0xffffu) {
+                    // A chunk at either end of the read, or next to an ambiguous base: some of its positions carry no hash.
+                    // It went through the same sixteen hashes as everybody else (a separate loop for it would make the
+                    // other 31 lanes wait: two tiles of every read paid for both paths); the keys of the positions that
+                    // do not count are now overwritten, and the chunk's minima are rebuilt from the KEYS of the others.
+                    // A minimum known to 15 bits stands for a range of hashes: as the chunk's own value in the flag tests of
+                    // step 3 the bottom of the range is used, as part of the window minimum of later chunks the top
+                    // (scan_up), so that both tests can only flag more, never less; the decisions themselves are taken
+                    // on keys, with ties settled exactly, whatever the flags were computed from.
+                    uint32_t kh = KNONE, kl = KNONE;
 #pragma unroll 1
                     for (int j = 0; j < 16; ++j) {
-                        uint32_t hi, lo;
-                        h31_canon_rt(j, wa, wb, w0, ra, rb, rc, hi, lo);
                         const bool ok = (vm >> j) & 1u;
-                        const uint32_t hv = h31_hash_top(hi, lo, G.h31);
-                        own[j * RS] = (uint16_t) (ok ? hv >> 17 : KNONE);
-                        if (ok) { if (OSP < 0 || j >= OSP) cmin = min(cmin, hv); else cmLo = min(cmLo, hv); }
+                        uint32_t kj = own[j * RS];
+                        if (!ok) { own[j * RS] = (uint16_t) KNONE; kj = KNONE; }
+                        if (OSP < 0 || j >= OSP) kh = min(kh, kj); else kl = min(kl, kj);
                     }
+                    cmin = kh == KNONE ? HNONE : kh << 17;
+                    cmLo = kl == KNONE ? HNONE : kl << 17;
+                    scan_up = 0x1ffffu;
                 }
             } else if (vm) {
                 uint32_t ww = w0;
@@ -280,7 +292,8 @@ __global__ void __launch_bounds__(32 * SYNC_SCAN_WARPS, 6) scan_kernel(ScanArgs 
             // 2. minimum over the n_full whole chunks in front of mine: prefix / suffix minima inside blocks of B lanes
             const uint32_t cmHi = cmin;
             cmin = min(cmin, cmLo);
-            uint32_t pfx = cmin, sfx = cmin;
+            const uint32_t cscan = cmin == HNONE ? HNONE : cmin | scan_up;
+            uint32_t pfx = cscan, sfx = cscan;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
                 if (d < B) {

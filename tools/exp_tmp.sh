@@ -1,2 +1,6 @@
-timeout 1200 python tools/fuzz_syncasm_gpu.py --seeds 0:60 > gpurun_out/fuzz_gpu_a.log 2> gpurun_out/fuzz_gpu_a.err; echo rc=$?; tail -1 gpurun_out/fuzz_gpu_a.log | cut -c1-600; grep -c "^ok" gpurun_out/fuzz_gpu_a.log; grep "^BAD" gpurun_out/fuzz_gpu_a.log | head -5
-timeout 900 python tools/fuzz_syncasm_gpu.py --hifi --seeds 300:320 > gpurun_out/fuzz_gpu_b.log 2> gpurun_out/fuzz_gpu_b.err; echo rc=$?; tail -1 gpurun_out/fuzz_gpu_b.log | cut -c1-600
+python -m pytest tests/test_gpu_extract.py tests/test_gpu_scale.py tests/test_gpu_survey_kat.py tests/test_gpu_pipe.py -x -q -k "not reads80k" 2>&1 | tail -4
+python bench.py --steps 5 --warmup 3 --no-cpu --no-e2e --no-whole 2>gpurun_out/exp_bench.err | python -c "
+import json,sys
+d=json.loads(sys.stdin.readline())
+print('value', d['value']/1e9, 'ms', d['ms_per_step']); print(d['roofline']['stage_ms'])
+for e in d['k_sweep']: print(e['k'], e['value']/1e9, e['stage_ms']['scan'])"
