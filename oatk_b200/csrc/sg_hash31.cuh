@@ -95,19 +95,4 @@ __device__ __forceinline__ void h31_canon(uint32_t a, uint32_t b, uint32_t w0, u
     lo = (lt ? fl : rl) & 0xfffffffcu;
 }
 
-// run-time position (the slow, checked path): same as h31_canon<J>
-__device__ __forceinline__ void h31_canon_rt(int j, uint32_t a, uint32_t b, uint32_t w0, uint32_t ra, uint32_t rb, uint32_t rc,
-        uint32_t &hi, uint32_t &lo)
-{
-    const uint32_t n = 2u * j + 4u;                            // 4..34
-    const bool far = n >= 32u;
-    const uint32_t x0 = far ? b : a, x1 = far ? w0 : b, x2 = far ? 0u : w0;
-    const uint32_t fh = h31_shf_l(x1, x0, n & 31u), fl = h31_shf_l(x2, x1, n & 31u);
-    const uint32_t m = 30u - 2u * j;                           // 30..0
-    const uint32_t rh = h31_shf_l(rb, ra, m), rl = h31_shf_l(rc, rb, m);
-    const bool lt = fh < rh;
-    hi = lt ? fh : rh;
-    lo = (lt ? fl : rl) & 0xfffffffcu;
-}
-
 } // namespace sg

@@ -21,41 +21,19 @@ namespace sg {
 // Besides the reference's MurmurHash64A, a second, independent 64-bit hash of the same oriented
 // words (multiply-xorshift chain with other constants, over the big-endian blocks). Hash and
 // fingerprint together decide "same k-mer" in sg_count's default mode; see DESIGN.md section 8.
-__device__ __forceinline__ uint64_t kmer_murmur(const uint32_t *hs, int64_t nwords, int64_t start, int k, int rev, uint64_t *fp_out)
-{
-    const uint64_t M = 0xc6a4a7935bd1e995ull, F = 0x9e3779b97f4a7c15ull;
-    const uint32_t nbytes = (uint32_t) (k + 3) >> 2, nblk = nbytes >> 3;
-    uint64_t h = 1234ull ^ ((uint64_t) nbytes * M), f = 0x243f6a8885a308d3ull ^ (uint64_t) k;
-    for (uint32_t j = 0; j < nblk; ++j) {
-        const uint64_t be = oriented_block(hs, nwords, start, k, rev, (int) j);
-        uint64_t w = bswap64(be);
-        w *= M; w ^= w >> 47; w *= M;
-        h = (h ^ w) * M;
-        f = (f ^ be) * F; f ^= f >> 32;
-    }
-    if (nbytes & 7u) {
-        const uint64_t be = oriented_block(hs, nwords, start, k, rev, (int) nblk);
-        h = (h ^ bswap64(be)) * M;
-        f = (f ^ be) * F; f ^= f >> 32;
-    }
-    h ^= h >> 47; h *= M; h ^= h >> 47;
-    f *= 0xd6e8feb86659fd93ull; f ^= f >> 29;
-    *fp_out = f;
-    return h;
-}
-
-// The same for a k-mer whose 32-base windows all lie inside the read's words (every k-mer but those within two
-// words of a read end): the three-word window slides by two words per block, so each block costs two loads, no
-// bounds checks and no re-conversion of the word it shares with its neighbour.
-__device__ __forceinline__ uint64_t kmer_murmur_interior(const uint32_t *hs, int64_t start, int k, int rev, uint64_t *fp_out)
+// MurmurHash64A over the oriented k-mer with a three-word window that slides by two words per block (each block costs two
+// loads and no re-conversion of the word it shares with its neighbour). Every load is bounds-checked like hoco_word: the first and the last syncmer of
+// a read reach past its words, and with 21 syncmers per read nearly every warp holds one of them -- a separate unchecked
+// path for the others made those warps run both.
+__device__ __forceinline__ uint64_t kmer_murmur_sliding(const uint32_t *hs, int64_t nwords, int64_t start, int k, int rev, uint64_t *fp_out)
 {
     const uint64_t M = 0xc6a4a7935bd1e995ull, F = 0x9e3779b97f4a7c15ull;
     const uint32_t nbytes = (uint32_t) (k + 3) >> 2, nblk = nbytes >> 3;
     uint64_t h = 1234ull ^ ((uint64_t) nbytes * M), f = 0x243f6a8885a308d3ull ^ (uint64_t) k;
     const int64_t p0 = rev ? start + k - 32 : start;                // first window; later ones are 32 bases further on / back
     const int sh = (int) (p0 & 15) * 2;
-    const uint32_t *w = hs + (p0 >> 4);
-    uint32_t a = bswap32(__ldg(w)), b = bswap32(__ldg(w + 1)), c = bswap32(__ldg(w + 2));
+    int64_t wi = p0 >> 4;                                           // arithmetic shift: floor, the last reverse window may start before the read
+    uint32_t a = hoco_word(hs, wi, nwords), b = hoco_word(hs, wi + 1, nwords), c = hoco_word(hs, wi + 2, nwords);
     const uint32_t nall = nblk + ((nbytes & 7u) ? 1u : 0u);
     // the strands of the k-mers of a warp are a coin toss each: both directions go through the same instructions
     // (selects, no branches), or every iteration would run twice
@@ -66,8 +44,8 @@ __device__ __forceinline__ uint64_t kmer_murmur_interior(const uint32_t *hs, int
         be = rev ? rcbe : be;
         // next window: two words on (forward) or two words back (reverse); one word is shared
         if (j + 1 < nall) {
-            w += step;
-            const uint32_t x = bswap32(__ldg(w + o1)), y = bswap32(__ldg(w + o1 + 1));
+            wi += step;
+            const uint32_t x = hoco_word(hs, wi + o1, nwords), y = hoco_word(hs, wi + o1 + 1, nwords);
             const uint32_t na = rev ? x : c, nb = rev ? y : x, nc = rev ? a : y;
             a = na; b = nb; c = nc;
         }
@@ -102,10 +80,7 @@ __global__ void __launch_bounds__(256) kmerhash_kernel(KmerArgs A)
     const uint64_t raw = smer_code_at(hs32, open ? t + A.s - 1 : t + A.k - 1, A.s, nwords);
     const uint32_t mp = (uint32_t) t << 1 | (uint32_t) (raw & 1ull);
     uint64_t fp;
-    // windows reach from word (start - 32) >> 4 (reverse, last block) to word ((start + k + 31) >> 4) + 2 at most
-    const bool interior = t >= 32 && ((t + A.k + 31) >> 4) + 3 <= nwords;
-    const uint64_t h = interior ? kmer_murmur_interior(hs32, t, A.k, (int) (mp & 1u), &fp)
-                                : kmer_murmur(hs32, nwords, mp >> 1, A.k, mp & 1u, &fp);
+    const uint64_t h = kmer_murmur_sliding(hs32, nwords, t, A.k, (int) (mp & 1u), &fp);
     const uint64_t o = A.scm_off[sid] + idx;
     A.key[o] = h;
     A.fp[o] = fp;
