@@ -134,15 +134,17 @@ __global__ void __launch_bounds__(32 * ENC_WARPS) encode_kernel(EncodeArgs A)
 
         // tile t of this read into the stage it will be consumed from (lane 0 only). The copy ends at the 16-byte
         // boundary after the read's last base (the input buffer is readable up to there, include/syncgpu.h).
-        const uint64_t raw_end = (raw1 + 15ull) & ~15ull;
-        auto issue_tile = [&](int t, uint32_t use) {
-            const uint64_t g = a0 + (uint64_t) t * ENC_TILE;
-            const uint32_t bytes = (uint32_t) min((uint64_t) ENC_TILE, raw_end - g);
+        // (One lane issues it, so every instruction here costs the warp a whole issue slot: the sizes are 32-bit and come
+        // from one subtraction per read.)
+        const uint32_t span = (uint32_t) (((raw1 + 15ull) & ~15ull) - a0);     // bytes from the first tile's start to the end of the last copy
+        const uint8_t *src0 = A.bases + a0;
+        auto issue_tile = [&](int t, uint32_t use, bool dirty) {
+            const uint32_t at = (uint32_t) t * ENC_TILE, bytes = min((uint32_t) ENC_TILE, span - at);
             const uint32_t st = use % ENC_STAGES;
-            // the slow path may have written codes over the stage with ordinary stores: order them before the unit's writes
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            // the slow path writes codes over the stage with ordinary stores: they are ordered before the unit's writes
+            if (dirty) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_arrive_expect(bar_s + 8 * st, bytes);
-            bulk_load(raw_s + st * ENC_TILE, A.bases + g, bytes, bar_s + 8 * st);
+            bulk_load(raw_s + st * ENC_TILE, src0 + at, bytes, bar_s + 8 * st);
         };
         // a run of 256 or more saturates ho_rl and goes to the side list (syncmer.c:301-304)
         auto side_list = [&](uint32_t idx, uint32_t rl1) {
@@ -151,7 +153,7 @@ __global__ void __launch_bounds__(32 * ENC_WARPS) encode_kernel(EncodeArgs A)
         };
 
         if (lane == 0)
-            for (int t = 0; t < ENC_STAGES && t < ntiles; ++t) issue_tile(t, n_used + t);
+            for (int t = 0; t < ENC_STAGES && t < ntiles; ++t) issue_tile(t, n_used + t, true);
         for (int t = 0; t < ntiles; ++t, ++n_used) {
             const uint32_t st = n_used % ENC_STAGES;
             mbar_wait(bar_s + 8 * st, (n_used / ENC_STAGES) & 1u);
@@ -181,6 +183,7 @@ __global__ void __launch_bounds__(32 * ENC_WARPS) encode_kernel(EncodeArgs A)
                     bad |= invalid4(w[j]) & bm;
                 }
             }
+            const bool slow = bad != 0;
             if (bad) {
                 // exact per-byte codes (also fixes U, raw 0..3) for the valid bytes; everything else becomes 0. The words
                 // are taken from the staged tile and the codes written back over them, so that no register array is
@@ -208,9 +211,10 @@ __global__ void __launch_bounds__(32 * ENC_WARPS) encode_kernel(EncodeArgs A)
                 const uint4 c0 = reinterpret_cast<const uint4 *>(mine)[0], c1 = reinterpret_cast<const uint4 *>(mine)[1];
                 cc[0] = c0.x; cc[1] = c0.y; cc[2] = c0.z; cc[3] = c0.w; cc[4] = c1.x; cc[5] = c1.y; cc[6] = c1.z; cc[7] = c1.w;
             }
-            if (__any_sync(SG_FULL, (NM0 | NM1) != 0)) any_n = true;
-            // every lane is done with the staged bytes (the vote above is the warp's rendezvous): refill the stage
-            if (lane == 0 && t + ENC_STAGES < ntiles) issue_tile(t + ENC_STAGES, n_used + ENC_STAGES);
+            // every lane is done with the staged bytes (the vote is the warp's rendezvous): refill the stage
+            const bool dirty = __any_sync(SG_FULL, slow);
+            if (dirty && __any_sync(SG_FULL, (NM0 | NM1) != 0)) any_n = true;
+            if (lane == 0 && t + ENC_STAGES < ntiles) issue_tile(t + ENC_STAGES, n_used + ENC_STAGES, dirty);
 
             // packed codes: positions 0..15 in P0, 16..31 in P1, first position in bits 31:30
             const uint32_t P0 = pack4(cc[0]) << 24 | pack4(cc[1]) << 16 | pack4(cc[2]) << 8 | pack4(cc[3]);
@@ -327,13 +331,17 @@ __global__ void __launch_bounds__(32 * ENC_WARPS) encode_kernel(EncodeArgs A)
                 const uint32_t left = fin - 16 * gi;       // entries of this group that exist (>= 16 except in the last group of a read)
                 if (left < 16) {
                     // keep the unused tail of the last word clean: bases beyond hoco_l read as zero
-                    uint32_t keepc = 0;
-                    for (uint32_t i = 0; i < left; ++i) keepc |= 3u << (2 * (3 - (i & 3)) + 8 * (i >> 2));
+                    // (entry i sits in bits 7:6 >> 2 (i & 3) of byte i >> 2: whole bytes for the first left / 4, the top
+                    // 2 (left & 3) bits of the next)
+                    const uint32_t fullb = left >> 2, part = left & 3u;
+                    const uint32_t keepc = ((1u << (8 * fullb)) - 1u) | (((0xff00u >> (2 * part)) & 0xffu) << (8 * fullb));
                     code &= keepc;
                     nflag &= (1u << left) - 1u;
 #pragma unroll
-                    for (int m = 0; m < 4; ++m)
-                        for (int b = 0; b < 4; ++b) if ((uint32_t) (4 * m + b) >= left) R[m] &= ~(0xffu << (8 * b));
+                    for (int m = 0; m < 4; ++m) {
+                        const int nb_ = min(4, max(0, (int) left - 4 * m));        // run lengths of this word that exist
+                        R[m] &= nb_ == 4 ? 0xffffffffu : (1u << (8 * nb_)) - 1u;
+                    }
                 }
                 const uint32_t go = (g_done >> 4) + gi;
                 hs32[go] = code;
