@@ -256,11 +256,11 @@ __global__ void __launch_bounds__(32 * SYNC_SCAN_WARPS, 6) scan_kernel(ScanArgs 
                     // (scan_up), so that both tests can only flag more, never less; the decisions themselves are taken
                     // on keys, with ties settled exactly, whatever the flags were computed from.
                     uint32_t kh = KNONE, kl = KNONE;
-#pragma unroll 1
-                    for (int j = 0; j < 16; ++j) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {                 // unrolled: one lane runs this while 31 wait
                         const bool ok = (vm >> j) & 1u;
-                        uint32_t kj = own[j * RS];
-                        if (!ok) { own[j * RS] = (uint16_t) KNONE; kj = KNONE; }
+                        const uint32_t kj = ok ? (uint32_t) own[j * RS] : KNONE;
+                        if (!ok) own[j * RS] = (uint16_t) KNONE;
                         if (OSP < 0 || j >= OSP) kh = min(kh, kj); else kl = min(kl, kj);
                     }
                     cmin = kh == KNONE ? HNONE : kh << 17;
