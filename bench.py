@@ -205,6 +205,8 @@ def main():
     ap.add_argument("--no-config3", action="store_true", help="skip the configs[3] line (10 M reads over 8 GPUs; runs only at 8 GPUs)")
     ap.add_argument("--no-whole", action="store_true", help="skip the configs[2] line (whole syncasm command on 200 k reads; one GPU only)")
     ap.add_argument("--whole-reads", type=int, default=200000)
+    ap.add_argument("--no-numa-bind", action="store_true", help="leave the process where the launcher put it (default: the CPUs and the "
+                    "memory node next to this rank's GPU at N > 1, the memory node only at N = 1, where the CPU baseline needs every core)")
     ap.add_argument("--config3-reads", type=int, default=0, help="run the configs[3] line with this many reads in all at any N > 1 (default: 10 M, at 8 GPUs only)")
     args = ap.parse_args()
     globals()["K"], globals()["ERR"] = args.k, args.err
@@ -220,6 +222,11 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: libsyncgpu has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = None
+    if not args.no_numa_bind:
+        # one process per GPU: pinned host buffers on the GPU's own NUMA node (sg_host_bind_near_device), before any is allocated
+        node, ncpu = lib.bind_host_near_device(local, cpus=world > 1, memory=True)
+        numa = {"node": node, "cpus_bound": ncpu}
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -294,9 +301,17 @@ def main():
     ex_bytes = None if comm is None else comm.bytes_sent() // max(1, W + args.steps)
     clocks = sampler.stop() if sampler else None
     ms_step = e0.elapsed_time(e1) / args.steps
+    by_rank = None
     if dist is not None:
         t = torch.tensor([ms_step], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        # every rank's own stage times (the JSON line carries rank 0's): the spread shows where ranks wait for each other
+        names = sorted(stage_ms)
+        mine = torch.tensor([stage_ms[n_] / args.steps for n_ in names] + [ms_step], device=dev, dtype=torch.float64)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        by_rank = {n_: [round(float(r_[i]), 3) for r_ in allr] for i, n_ in enumerate(names) if float(max(r_[i] for r_ in allr)) > 0.05}
+        by_rank["step"] = [round(float(r_[-1]), 3) for r_ in allr]
         ms_step = float(t.item())
     ctx.enable_timing(False)
     value = world * total / (ms_step * 1e-3)
@@ -383,6 +398,7 @@ def main():
                 "bytes_per_raw_base": ext_bytes / total, "ms_per_launch": ext_ms,
                 "stage_ms": {k_: v / args.steps for k_, v in stage_ms.items()},
                 "stage_launches": {k_: v // args.steps for k_, v in stage_launch.items()},
+                "stage_ms_by_rank": by_rank,
                 "note": "integer-issue bound, not HBM bound: see DESIGN.md section 5"}
 
     cpu = None
@@ -410,7 +426,7 @@ def main():
     line = {"metric": "HiFi bases/sec syncmer-extract+count", "value": value, "unit": "bases/s", "n_gpus": world,
             "steps": args.steps, "warmup": W, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": workload_config(world, n_reads, args.workload, n_planted),
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+            "clocks": clocks, "numa": numa, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
             "k_sweep": sweep, "config3": config3, "whole_command": whole,
             "multi_gpu_parity": mgpu, "global_ids_sample_check": ids_check,
             "exchange": None if comm is None else {"transport": "sg_comm_* in C: grouped ncclSend/ncclRecv, counts on the device",

@@ -50,6 +50,10 @@ typedef struct sg_batch sg_batch;
 
 /* ---- context ---- */
 int sg_ctx_create(int device, sg_ctx **out);
+/* One process per GPU: pin the calling thread to the CPUs next to `device` and prefer its NUMA node for pages touched from
+ * now on (call before allocating pinned host buffers). numa_node: the node, -1 unknown, < -1 policy refused; n_cpus: CPUs
+ * bound, 0 = affinity left alone. Never fails for lack of sysfs. (The reference has no counterpart: it is host-only.) */
+int sg_host_bind_near_device(int device, int flags, int *numa_node, int *n_cpus);   /* flags: 1 = CPUs, 2 = memory */
 void sg_ctx_destroy(sg_ctx *ctx);
 /* launch everything on this cudaStream_t (NULL = the legacy default stream) */
 int sg_ctx_set_stream(sg_ctx *ctx, void *cuda_stream);

@@ -3,6 +3,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <cctype>
+#include <sched.h>
+#include <unistd.h>
+#include <sys/syscall.h>
 #include <string>
 #include <vector>
 #include <algorithm>
@@ -54,6 +58,30 @@ void sg_ctx::t_end(int stage)
     ev_used[stage] = true;
 }
 
+void sg_ctx::lap(const char *name)
+{
+    if (laps_on < 0) { const char *e = getenv("SG_LAPS"); laps_on = e && *e && *e != '0'; }
+    if (!laps_on || !timing) return;
+    if (lap_n == lap_ev.size()) { cudaEvent_t e; cudaEventCreate(&e); lap_ev.push_back(e); lap_name.push_back(name); }
+    lap_name[lap_n] = name;
+    cudaEventRecord(lap_ev[lap_n++], stream);
+}
+void sg_ctx::laps_print(const char *tag)
+{
+    if (laps_on <= 0 || lap_n < 2) { lap_n = 0; return; }
+    cudaEventSynchronize(lap_ev[lap_n - 1]);
+    std::string line = std::string("[sg laps dev ") + std::to_string(device) + "] " + tag + ":";
+    for (size_t i = 1; i < lap_n; ++i) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, lap_ev[i - 1], lap_ev[i]);
+        char buf[96];
+        snprintf(buf, sizeof(buf), " %s=%.3f", lap_name[i], ms);
+        line += buf;
+    }
+    fprintf(stderr, "%s\n", line.c_str());
+    lap_n = 0;
+}
+
 extern "C" {
 
 const char *sg_strerror(int code)
@@ -94,6 +122,51 @@ void sg_ctx_destroy(sg_ctx *ctx)
     cudaSetDevice(ctx->device);
     for (int i = 0; i < SG_T_N; ++i) { cudaEventDestroy(ctx->ev[i][0]); cudaEventDestroy(ctx->ev[i][1]); }
     delete ctx;
+}
+
+// Host placement for one process per GPU: run the calling thread (and the threads it starts later) on the CPUs next to the device and
+// prefer that NUMA node for the pages it touches from now on, so that pinned buffers allocated afterwards are read by the copy
+// engines without crossing the socket link. Everything comes from sysfs; a container that hides it leaves the process as it was.
+int sg_host_bind_near_device(int device, int flags, int *numa_node, int *n_cpus)
+{
+    if (numa_node) *numa_node = -1;
+    if (n_cpus) *n_cpus = 0;
+    char bus[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus, (int) sizeof(bus), device) != cudaSuccess) { cudaGetLastError(); return SG_E_CUDA; }
+    for (char *c = bus; *c; ++c) *c = (char) tolower((unsigned char) *c);
+    char path[160];
+    int node = -1;
+    snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/numa_node", bus);
+    if (FILE *f = fopen(path, "r")) { if (fscanf(f, "%d", &node) != 1) node = -1; fclose(f); }
+    cpu_set_t now, want;
+    CPU_ZERO(&want);
+    int bound = 0;
+    snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/local_cpulist", bus);
+    FILE *fl = (flags & 1) ? fopen(path, "r") : nullptr;
+    if (FILE *f = fl) {
+        if (sched_getaffinity(0, sizeof(now), &now) == 0) {
+            int a, b2;
+            // "0-15,32-47": ranges and single numbers separated by commas
+            while (fscanf(f, "%d", &a) == 1) {
+                b2 = a;
+                int ch = fgetc(f);
+                if (ch == '-') { if (fscanf(f, "%d", &b2) != 1) break; ch = fgetc(f); }
+                for (int c = a; c <= b2 && c < CPU_SETSIZE; ++c) if (c >= 0 && CPU_ISSET(c, &now)) { CPU_SET(c, &want); ++bound; }
+                if (ch != ',') break;
+            }
+            if (bound > 0 && sched_setaffinity(0, sizeof(want), &want) != 0) bound = 0;
+        }
+        fclose(f);
+    }
+    if ((flags & 2) && node >= 0 && node < 1024) {
+        unsigned long mask[16] = {0};
+        mask[node / (8 * sizeof(unsigned long))] = 1ul << (node % (8 * sizeof(unsigned long)));
+        // MPOL_PREFERRED = 1: fall back to other nodes rather than fail when the node is full or not allowed
+        if (syscall(SYS_set_mempolicy, 1, mask, (unsigned long) (sizeof(mask) * 8)) != 0) node = -1 - node;
+    }
+    if (numa_node) *numa_node = node;
+    if (n_cpus) *n_cpus = bound;
+    return SG_OK;
 }
 
 int sg_ctx_set_stream(sg_ctx *ctx, void *s) { if (!ctx) return SG_E_ARG; ctx->stream = (cudaStream_t) s; return SG_OK; }

@@ -377,6 +377,7 @@ int sg_comm_exchange_tuples(sg_comm *c, sg_batch *b)
     CK(cudaSetDevice(ctx->device));
     const int W = c->world;
     ctx->t_begin(SG_T_EXCH);
+    ctx->lap("begin");
     int rc;
     const uint64_t N = b->n_syncmers;
     c->fast = b->tup_valid && N < (1ull << 32) && !getenv("SG_COMM_PAIRS");
@@ -400,8 +401,10 @@ int sg_comm_exchange_tuples(sg_comm *c, sg_batch *b)
         ends_to_counts_kernel<<<1, 32, 0, st>>>((const unsigned long long *) b->part_counts.p, W, (uint64_t *) c->cnt_dev.p);
         ctx->count_launch(SG_T_SORT, 1);
     }
+    ctx->lap("split");
     rc = gather_count_matrix(c, (const uint64_t *) c->cnt_dev.p);
     if (rc) return rc;
+    ctx->lap("counts");
     c->send_counts.assign(W, 0); c->recv_counts.assign(W, 0);
     uint64_t total = 0;
     for (int p = 0; p < W; ++p) {
@@ -430,7 +433,9 @@ int sg_comm_exchange_tuples(sg_comm *c, sg_batch *b)
             b->range_lsh = lg > 0 ? lg - 1 : 0;
         }
         b->sorted = b->counted = false;
+        ctx->lap("all_to_all");
         ctx->t_end(SG_T_EXCH);
+        ctx->laps_print("exchange");
         return SG_OK;
     }
     RS(c->recv, (total + 1) * 32);
@@ -453,10 +458,12 @@ int sg_comm_return_ids(sg_comm *c, sg_batch *b, uint64_t *id_base, uint64_t *n_u
     const int W = c->world;
     RS(c->uniq_dev, (size_t) (W + 1) * 8);
     ctx->t_begin(SG_T_IDS);
+    ctx->lap("begin");
     uint64_t *mine = c->mat_host + (size_t) W * W + W;       // pinned scratch word
     *mine = b->n_unique;
     CK(cudaMemcpyAsync((uint64_t *) c->uniq_dev.p + W, mine, 8, cudaMemcpyHostToDevice, st));
     NK(N->AllGather((const uint64_t *) c->uniq_dev.p + W, c->uniq_dev.p, 1, ncclUint64, c->comm, st));
+    ctx->lap("allgather");
     const uint64_t n = b->n_adopted;
     int rc;
     if (c->fast) {
@@ -464,6 +471,7 @@ int sg_comm_return_ids(sg_comm *c, sg_batch *b, uint64_t *id_base, uint64_t *n_u
         RS(c->back, (b->n_syncmers + 1) * 8);
         rc = all_to_all_v(c, (const uint64_t *) b->kid.p, c->recv_counts, (uint64_t *) c->back.p, c->send_counts, 1);
         if (rc) return rc;
+        ctx->lap("all_to_all");
         CK(cudaMemcpyAsync(c->mat_host + (size_t) W * W, c->uniq_dev.p, (size_t) W * 8, cudaMemcpyDeviceToHost, st));
         RS(b->kid_local, (b->n_syncmers + 1) * 8);
         if (b->n_syncmers) {
@@ -471,10 +479,12 @@ int sg_comm_return_ids(sg_comm *c, sg_batch *b, uint64_t *id_base, uint64_t *n_u
                     (const uint64_t *) c->sent_dev.p, (const uint64_t *) c->uniq_dev.p, W, (uint64_t *) b->kid_local.p);
             ctx->count_launch(SG_T_IDS, 1);
         }
+        ctx->lap("unpermute");
         CK(cudaStreamSynchronize(st));
         CK(cudaGetLastError());
         b->have_kid_local = true;
         ctx->t_end(SG_T_IDS);
+        ctx->laps_print("ids");
     } else {
     RS(b->tuples, (n + 1) * 32);
     if (n) {

@@ -521,26 +521,35 @@ static int ensure_sorted(sg_batch *b)
         uint64_t *pk = (uint64_t *) b->skey_alt.p, *pk_alt = (uint64_t *) b->sval_alt.p;
         const int plow = 64 - b->pack_bits;                   // hash bits the packed sort leaves to the repair (32 unless a test moves it)
         const RunKey RK = {b->adopted ? b->range_lo : 0ull, b->adopted ? b->range_lsh : 0, plow};
+        ctx->lap("begin");
         pack_init_kernel<<<nblk(N, 256), 256, 0, st>>>((const ulonglong4 *) b->tup.p, pk, N, RK);
         ctx->count_launch(SG_T_SORT, 1);
+        ctx->lap("pack_init");
         LAUNCHED(SG_T_SORT, launch_sort_keys(pk, pk_alt, N, 32, 32 + b->pack_bits, (uint32_t *) b->sort_tmp.p, st));
+        ctx->lap("sort_keys");
         pack_gather_kernel<<<nblk(N, 256), 256, 0, st>>>(pk, (const ulonglong4 *) b->tup.p, (uint64_t *) b->skey.p, (uint64_t *) b->sval.p,
                 (uint64_t *) b->socc.p, (uint64_t *) b->ssmer.p, (uint64_t *) b->sfp.p, N);
+        ctx->lap("gather");
         CK(cudaMemsetAsync(b->sort_fix.p, 0, 8, st));
         sort_detect_cap_kernel<<<nblk(N, 256), 256, 0, st>>>((const uint64_t *) b->skey.p, N, RK, cap, (uint32_t *) b->sort_fix.p);
         // one warp per listed run (their number is known on the device only: a grid for a full list, warps without a run leave at once);
         // scratch: the two word buffers of the sort and three arrays that are filled later in the step
         RS(b->ids, (N + 2) * 8); RS(b->starts, (N + 2) * 8); RS(b->kid, (N + 1) * 8);
+        ctx->lap("detect");
         Repair5 R5 = {(uint64_t *) b->skey.p, (uint64_t *) b->sval.p, (uint64_t *) b->socc.p, (uint64_t *) b->ssmer.p, (uint64_t *) b->sfp.p,
                       pk, pk_alt, (uint64_t *) b->ids.p, (uint64_t *) b->starts.p, (uint64_t *) b->kid.p};
         sort_repair5_kernel<<<std::min<unsigned>(nblk((uint64_t) cap * 32, 128), 148u * 16u), 128, 0, st>>>(R5, N, RK, cap, (uint32_t *) b->sort_fix.p);
+        ctx->lap("repair");
         sort_check_rk_kernel<<<nblk(N, 256), 256, 0, st>>>((const uint64_t *) b->skey.p, N, RK, (uint32_t *) b->sort_fix.p);
         ctx->count_launch(SG_T_SORT, 4);
+        ctx->lap("check");
         uint32_t hf[2];
         CK(cudaMemcpyAsync(hf, b->sort_fix.p, sizeof(hf), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         b->n_sort_repairs = hf[0];
         b->sort_fell_back = false;
+        if (ctx->laps_on > 0) fprintf(stderr, "[sg laps dev %d] sort: N=%llu runs=%u bad=%u cap=%u\n", ctx->device, (unsigned long long) N, hf[0], hf[1], cap);
+        ctx->laps_print("sort");
         if (hf[1] == 0 && hf[0] <= cap) {
             ctx->t_end(SG_T_SORT);
             CK(cudaGetLastError());

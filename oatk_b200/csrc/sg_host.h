@@ -30,6 +30,13 @@ struct sg_ctx {
     void count_launch(int stage, int n);
     void t_begin(int stage);
     void t_end(int stage);
+    // SG_LAPS=1 in the environment: event-timed laps inside a stage, printed to stderr when the stage closes (diagnostics only)
+    int laps_on = -1;
+    std::vector<cudaEvent_t> lap_ev;
+    std::vector<const char *> lap_name;
+    size_t lap_n = 0;
+    void lap(const char *name);
+    void laps_print(const char *tag);
 };
 
 struct sg_batch {

@@ -55,7 +55,7 @@ _LIB = None
 
 # every symbol include/syncgpu.h declares; tests check that the library exports all of them
 SYMBOLS = [
-    "sg_ctx_create", "sg_ctx_destroy", "sg_ctx_set_stream", "sg_ctx_sync", "sg_strerror", "sg_last_error",
+    "sg_ctx_create", "sg_host_bind_near_device", "sg_ctx_destroy", "sg_ctx_set_stream", "sg_ctx_sync", "sg_strerror", "sg_last_error",
     "sg_ctx_launches", "sg_ctx_enable_timing", "sg_ctx_timings",
     "sg_batch_create", "sg_batch_destroy", "sg_batch_set_reads_host", "sg_batch_set_reads_device",
     "sg_batch_set_sid_base", "sg_extract", "sg_extract_sizes", "sg_extract_download",
@@ -83,6 +83,7 @@ def _lib():
     L.sg_last_error.restype = C.c_char_p
     L.sg_last_error.argtypes = [vp]
     L.sg_ctx_create.argtypes = [i32, C.POINTER(vp)]
+    L.sg_host_bind_near_device.argtypes = [i32, i32, C.POINTER(i32), C.POINTER(i32)]
     L.sg_ctx_destroy.argtypes = [vp]
     L.sg_ctx_destroy.restype = None
     L.sg_ctx_set_stream.argtypes = [vp, vp]
@@ -139,6 +140,15 @@ def _lib():
 
 def library():
     return _lib()
+
+
+def bind_host_near_device(device, cpus=True, memory=True):
+    """sg_host_bind_near_device: CPUs and / or NUMA node next to the GPU for this process; returns (numa_node, n_cpus)."""
+    node, ncpu = C.c_int32(-1), C.c_int32(0)
+    rc = _lib().sg_host_bind_near_device(int(device), (1 if cpus else 0) | (2 if memory else 0), C.byref(node), C.byref(ncpu))
+    if rc != 0:
+        raise SgError(rc, "sg_host_bind_near_device", "")
+    return node.value, ncpu.value
 
 
 def _ck(ctx, rc, what):
