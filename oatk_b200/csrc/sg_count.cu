@@ -128,52 +128,114 @@ __global__ void __launch_bounds__(256) pack_gather_kernel(const uint64_t *pk, co
     }
 }
 
-// The listed runs, put right over all five gathered arrays: one WARP per run. A run holds the occurrences of the few
+// The runs that need it, put right over all five gathered arrays: one WARP per run. A run holds the occurrences of the few
 // distinct k-mers that share their top hash bits, each k-mer's occurrences already in tuple order but interleaved with
-// the others' (a genomic k-mer brings its whole coverage along), so an insertion sort would shift hundreds of elements
-// again and again. Every element instead computes its final place -- the number of elements with a smaller hash, or
-// the same hash and an earlier position (stable) -- with the run's hashes read by all lanes together, is parked there
-// in scratch arrays, and the run is copied back. Runs were listed by sort_detect_cap_kernel.
+// the others' -- and a genomic k-mer brings its whole coverage along: hundreds of copies on one GPU, eight times that when
+// eight GPUs send theirs, so nothing here may walk a run one element at a time. Three launches:
+//   sort_detect_all_kernel   lists EVERY adjacent out-of-order pair inside a run;
+//   sort_owner_kernel        keeps, of the pairs of one run, the first (a warp looks back 32 tuples at a time for an earlier
+//                            pair or the start of the run); it only reads, so ownership never depends on a repair in flight;
+//   sort_repair5_kernel      finds the run's ends 32 tuples at a time, then takes the distinct hashes in increasing order:
+//                            one pass for the next smallest hash, one that moves its tuples (ballot + prefix count: stable)
+//                            behind those already placed, in scratch arrays; the run is copied back at the end.
 struct Repair5 { uint64_t *k, *v, *o, *sm, *fp, *tk, *tv, *to, *tsm, *tfp; };
-__global__ void __launch_bounds__(128) sort_repair5_kernel(Repair5 R, uint64_t n, RunKey K, uint32_t cap, uint32_t *fix)
+constexpr uint32_t NOT_OWNER = 0xffffffffu;                 // a listed index is below 2^32 - 1
+
+__global__ void __launch_bounds__(256) sort_detect_all_kernel(const uint64_t *k, uint64_t n, RunKey K, uint32_t cap, uint32_t *fix)
+{
+    const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i + 1 >= n) return;
+    const uint64_t a = k[i], b = k[i + 1];
+    if (run_of(K, a) != run_of(K, b) || a <= b) return;
+    const uint32_t o = atomicAdd(&fix[0], 1u);
+    if (o < cap) fix[2 + o] = (uint32_t) i; else fix[1] = 1u;
+}
+
+// how many of the tuples before `hi` (exclusive, going down) belong to the run `top`, 32 at a time; *stop: an out-of-order pair
+// was seen among them (only looked for when find_pair)
+__device__ __forceinline__ uint64_t run_back(const uint64_t *k, RunKey K, uint64_t top, uint64_t hi, int lane, bool find_pair, bool *pair)
+{
+    uint64_t cnt = 0;
+    *pair = false;
+    for (;;) {
+        const bool ok = hi - cnt > (uint64_t) lane;             // j = hi - cnt - 1 - lane exists
+        const uint64_t j = hi - cnt - 1 - lane;
+        const uint64_t kj = ok ? k[j] : 0;
+        const bool in = ok && run_of(K, kj) == top;
+        const unsigned m = __ballot_sync(SG_FULL, in);
+        const int t = m == SG_FULL ? 32 : __ffs(~m) - 1;         // the run reaches this far back
+        if (find_pair) {
+            const bool inv = lane < t && kj > k[j + 1];
+            if (__any_sync(SG_FULL, inv)) { *pair = true; return cnt; }
+        }
+        cnt += t;
+        if (t < 32 || cnt > SORT_FIX_MAXRUN) return cnt;
+    }
+}
+
+__global__ void __launch_bounds__(128) sort_owner_kernel(const uint64_t *k, RunKey K, uint32_t cap, uint32_t *fix)
 {
     const uint32_t cnt = min(fix[0], cap);
     const int lane = threadIdx.x & 31;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = (gridDim.x * blockDim.x) >> 5;
     for (uint32_t e = warp; e < cnt; e += nwarp) {
         const uint64_t i = fix[2 + e];
+        bool pair;
+        const uint64_t back = run_back(k, K, run_of(K, k[i]), i, lane, true, &pair);
+        if (lane == 0) {
+            if (pair) fix[2 + e] = NOT_OWNER;
+            else if (back > SORT_FIX_MAXRUN) fix[1] = 1u;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) sort_repair5_kernel(Repair5 R, uint64_t n, RunKey K, uint32_t cap, uint32_t *fix)
+{
+    const uint32_t cnt = min(fix[0], cap);
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t e = warp; e < cnt; e += nwarp) {
+        const uint32_t ent = fix[2 + e];
+        if (ent == NOT_OWNER) continue;
+        const uint64_t i = ent;
         const uint64_t top = run_of(K, R.k[i]);
-        uint64_t s0 = i, s1 = i + 1;
-        while (s0 > 0 && run_of(K, R.k[s0 - 1]) == top) --s0;
-        while (s1 + 1 < n && run_of(K, R.k[s1 + 1]) == top) ++s1;
+        bool unused;
+        const uint64_t s0 = i - run_back(R.k, K, top, i, lane, false, &unused);
+        uint64_t s1 = i + 1;
+        for (;;) {                                              // forward, 32 at a time
+            const uint64_t j = s1 + 1 + lane;
+            const bool in = j < n && run_of(K, R.k[j]) == top;
+            const unsigned m = __ballot_sync(SG_FULL, in);
+            const int t = m == SG_FULL ? 32 : __ffs(~m) - 1;
+            s1 += t;
+            if (t < 32 || s1 - s0 > SORT_FIX_MAXRUN) break;
+        }
         if (s1 - s0 > SORT_FIX_MAXRUN) { if (lane == 0) fix[1] = 1u; continue; }
-        for (uint64_t a = s0 + lane; a <= s1; a += 32) {
-            const uint64_t ka = R.k[a];
-            uint64_t r = 0;
-            for (uint64_t b = s0; b <= s1; ++b) { const uint64_t kb = R.k[b]; r += (kb < ka || (kb == ka && b < a)) ? 1u : 0u; }
-            const uint64_t d = s0 + r;
-            R.tk[d] = ka; R.tv[d] = R.v[a]; R.to[d] = R.o[a]; R.tsm[d] = R.sm[a]; R.tfp[d] = R.fp[a];
+        uint64_t placed = s0, prev = 0;
+        bool first = true;
+        while (placed <= s1) {
+            uint64_t cur = ~0ull;                               // the smallest hash not placed yet
+            for (uint64_t a0 = s0; a0 <= s1; a0 += 32) {
+                const uint64_t a = a0 + lane;
+                if (a <= s1) { const uint64_t ka = R.k[a]; if (first || ka > prev) cur = min(cur, ka); }
+            }
+            for (int d = 16; d; d >>= 1) cur = min(cur, __shfl_xor_sync(SG_FULL, cur, d));
+            for (uint64_t a0 = s0; a0 <= s1; a0 += 32) {       // its tuples, in the order they stand
+                const uint64_t a = a0 + lane;
+                const bool eq = a <= s1 && R.k[a] == cur;
+                const unsigned m = __ballot_sync(SG_FULL, eq);
+                if (eq) {
+                    const uint64_t d = placed + __popc(m & ((1u << lane) - 1u));
+                    R.tk[d] = cur; R.tv[d] = R.v[a]; R.to[d] = R.o[a]; R.tsm[d] = R.sm[a]; R.tfp[d] = R.fp[a];
+                }
+                placed += __popc(m);
+            }
+            prev = cur; first = false;
         }
         __syncwarp();
         for (uint64_t a = s0 + lane; a <= s1; a += 32) { R.k[a] = R.tk[a]; R.v[a] = R.tv[a]; R.o[a] = R.to[a]; R.sm[a] = R.tsm[a]; R.fp[a] = R.tfp[a]; }
         __syncwarp();
     }
-}
-
-// sort_detect_kernel with a caller-sized list
-__global__ void __launch_bounds__(256) sort_detect_cap_kernel(const uint64_t *k, uint64_t n, RunKey K, uint32_t cap, uint32_t *fix)
-{
-    const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
-    if (i + 1 >= n) return;
-    const uint64_t a = k[i], b = k[i + 1];
-    if (run_of(K, a) != run_of(K, b) || a <= b) return;
-    const uint64_t top = run_of(K, a);
-    for (uint64_t j = i; j > 0 && run_of(K, k[j - 1]) == top; --j) {
-        if (k[j - 1] > k[j]) return;                       // an earlier inversion owns the run
-        if (i - j > SORT_FIX_MAXRUN) { fix[1] = 1u; return; }
-    }
-    const uint32_t o = atomicAdd(&fix[0], 1u);
-    if (o < cap) fix[2 + o] = (uint32_t) i; else fix[1] = 1u;
 }
 
 // the same from the 32-byte records written by kmerhash_kernel: one sector per tuple
@@ -516,7 +578,7 @@ static int ensure_sorted(sg_batch *b)
     // the ordinary case: whole hashes, records of this batch's own extract, fewer than 2^32 tuples (the index shares a word
     // with the top half of the hash)
     if (!full && SORT_LOW_BITS == 24 && (b->adopted ? b->atup_valid : b->tup_valid) && !b->keys_are_ids && N < (1ull << 32) && !getenv("SG_SORT_PAIRS")) {
-        const uint32_t cap = (uint32_t) std::min<uint64_t>(N / 64 + SORT_FIX_CAP, 1u << 26);
+        const uint32_t cap = (uint32_t) std::min<uint64_t>(N + 2, 0xfffffff0u);   // every out-of-order pair inside a run is listed: fewer than N
         RS(b->sort_fix, ((size_t) cap + 2) * 4);
         uint64_t *pk = (uint64_t *) b->skey_alt.p, *pk_alt = (uint64_t *) b->sval_alt.p;
         const int plow = 64 - b->pack_bits;                   // hash bits the packed sort leaves to the repair (32 unless a test moves it)
@@ -531,7 +593,8 @@ static int ensure_sorted(sg_batch *b)
                 (uint64_t *) b->socc.p, (uint64_t *) b->ssmer.p, (uint64_t *) b->sfp.p, N);
         ctx->lap("gather");
         CK(cudaMemsetAsync(b->sort_fix.p, 0, 8, st));
-        sort_detect_cap_kernel<<<nblk(N, 256), 256, 0, st>>>((const uint64_t *) b->skey.p, N, RK, cap, (uint32_t *) b->sort_fix.p);
+        sort_detect_all_kernel<<<nblk(N, 256), 256, 0, st>>>((const uint64_t *) b->skey.p, N, RK, cap, (uint32_t *) b->sort_fix.p);
+        sort_owner_kernel<<<std::min<unsigned>(nblk((uint64_t) cap * 32, 128), 148u * 16u), 128, 0, st>>>((const uint64_t *) b->skey.p, RK, cap, (uint32_t *) b->sort_fix.p);
         // one warp per listed run (their number is known on the device only: a grid for a full list, warps without a run leave at once);
         // scratch: the two word buffers of the sort and three arrays that are filled later in the step
         RS(b->ids, (N + 2) * 8); RS(b->starts, (N + 2) * 8); RS(b->kid, (N + 1) * 8);
@@ -541,7 +604,7 @@ static int ensure_sorted(sg_batch *b)
         sort_repair5_kernel<<<std::min<unsigned>(nblk((uint64_t) cap * 32, 128), 148u * 16u), 128, 0, st>>>(R5, N, RK, cap, (uint32_t *) b->sort_fix.p);
         ctx->lap("repair");
         sort_check_rk_kernel<<<nblk(N, 256), 256, 0, st>>>((const uint64_t *) b->skey.p, N, RK, (uint32_t *) b->sort_fix.p);
-        ctx->count_launch(SG_T_SORT, 4);
+        ctx->count_launch(SG_T_SORT, 5);
         ctx->lap("check");
         uint32_t hf[2];
         CK(cudaMemcpyAsync(hf, b->sort_fix.p, sizeof(hf), cudaMemcpyDeviceToHost, st));

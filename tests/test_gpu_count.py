@@ -135,12 +135,15 @@ def test_partial_sort_and_repair(gpu_ctx, oracle, low_bits, expect):
     b.close()
 
 
-@pytest.mark.parametrize("bits,expect", [(32, "none"), (16, "repair"), (8, "repair")])
-def test_packed_sort_and_repair(gpu_ctx, oracle, bits, expect):
+@pytest.mark.parametrize("bits,expect,deep", [(32, "none", False), (16, "repair", False), (8, "repair", False), (16, "repair", True), (8, "repair", True)])
+def test_packed_sort_and_repair(gpu_ctx, oracle, bits, expect, deep):
     """the default sort orders (top hash bits | tuple index) words and repairs the runs that differ below; with 16 or 8
     bits in the word nearly every tuple sits in such a run, so the five-array repair does real work. The order, ids and
     occurrence lists must not depend on where the split is."""
-    reads = synth.hifi_reads(12, 100000, 300, 15000, 0.001) + synth.adversarial_reads(5, 101, 11)
+    if deep:   # few distinct k-mers, each several hundred copies deep (what one GPU of eight adopts): long runs, few hashes per run
+        reads = synth.hifi_reads(13, 12000, 1500, 4000, 0.0002)
+    else:
+        reads = synth.hifi_reads(12, 100000, 300, 15000, 0.001) + synth.adversarial_reads(5, 101, 11)
     bases, off = pack_reads(reads)
     db, _ = oracle.extract(bases, off, 101, 11)
     exp = oracle.collect(db, len(reads), 64)
