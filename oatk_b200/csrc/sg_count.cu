@@ -458,7 +458,8 @@ __global__ void __launch_bounds__(256) key_tally_kernel(const uint64_t *keys, ui
         table_add_warp(tk, tv, nslot_mask, base + lane < n ? keys[base + lane] : EMPTY_KEY, lane);
 }
 
-// the same in a table sized for FEW distinct keys (it then stays in L2): gives up when a key finds no slot nearby
+// the same in a table sized for FEW distinct keys (it then stays in L2): the lanes of a warp merge equal keys (match), then every
+// leader probes for itself (slot_add_bounded); gives up when a key finds no slot nearby
 __global__ void __launch_bounds__(256) key_tally_small_kernel(const uint64_t *keys, uint64_t n, uint64_t *tk, uint32_t *tv, uint64_t nslot_mask,
         unsigned int *full)
 {
@@ -466,19 +467,13 @@ __global__ void __launch_bounds__(256) key_tally_small_kernel(const uint64_t *ke
     const uint64_t warp0 = ((uint64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t nwarp = ((uint64_t) gridDim.x * blockDim.x) >> 5;
     for (uint64_t base = warp0 * 32; base < n; base += nwarp * 32) {
-        unsigned int gave_up = 0;
-        if (lane == 0) gave_up = *((volatile unsigned int *) full);
-        if (__shfl_sync(SG_FULL, gave_up, 0)) return;           // somebody gave up: the result will be thrown away
         const uint64_t key = base + lane < n ? keys[base + lane] : EMPTY_KEY;
+        const unsigned int gave_up = lane == 0 ? *((volatile unsigned int *) full) : 0u;
         const uint32_t peers = __match_any_sync(SG_FULL, key);
         const bool leader = key != EMPTY_KEY && lane == __ffs(peers) - 1;
-        const uint32_t cnt = __popc(peers);
-        uint32_t work = __ballot_sync(SG_FULL, leader);
-        while (work) {
-            const int src = __ffs(work) - 1;
-            work &= work - 1;
-            table_add_bounded(tk, tv, nslot_mask, __shfl_sync(SG_FULL, key, src), __shfl_sync(SG_FULL, cnt, src), lane, 4, full);
-        }
+        if (__any_sync(SG_FULL, gave_up != 0)) return;          // somebody gave up: the result will be thrown away
+        const bool lost = leader && !slot_add_bounded(tk, tv, nslot_mask, key, __popc(peers), 128);
+        if (__any_sync(SG_FULL, lost)) { if (lane == 0) *full = 1u; return; }
     }
 }
 
@@ -747,7 +742,7 @@ int sg_stat(sg_batch *b, sg_stat_t *out)
         // Syncmers of one genome share few s-mers (the minimum of a window survives most sequencing errors in it), so
         // the table is first cut for N / 16 distinct codes: 48 MB at 21 M syncmers, resident in L2, where a table for
         // the worst case (every code distinct) is 768 MB of DRAM probes. A tally that finds the small table crowded
-        // (a key without a free slot within four groups, or more than half of the slots taken) is repeated in the large one.
+        // (a key without a free slot within 128 probes, or more than half of the slots taken) is repeated in the large one.
         uint64_t nslots = 1024, nfull = 1024;
         while (nfull < 2 * N) nfull <<= 1;
         while (nslots < N / 8) nslots <<= 1;

@@ -46,35 +46,22 @@ __device__ __forceinline__ void table_add(uint64_t *tk, uint32_t *tv, uint64_t n
 }
 
 
-// the same for a table that may be too small: gives up after `max_groups` groups without a free slot and reports it
-// through *full (the caller then repeats the tally in a larger table)
-__device__ __forceinline__ void table_add_bounded(uint64_t *tk, uint32_t *tv, uint64_t nslot_mask, uint64_t key, uint32_t cnt, int lane,
-        int max_groups, unsigned int *full)
+// One lane, one key, in a table that is mostly empty and resident in L2: plain linear probing, a slot at a time. Every lane of a
+// warp is on its own probe sequence, so 32 reads are in flight where the group probe above has one (the s-mer tally of sg_stat
+// is bound by that latency, not by bytes). false: no slot within max_probes.
+__device__ __forceinline__ bool slot_add_bounded(uint64_t *tk, uint32_t *tv, uint64_t nslot_mask, uint64_t key, uint32_t cnt, int max_probes)
 {
-    uint64_t g = (mix64(key) << 5) & nslot_mask;
-    for (int tries = 0; tries < max_groups; ) {
-        const uint64_t cur = *((volatile uint64_t *) (tk + g + lane));
-        const uint32_t hit = __ballot_sync(SG_FULL, cur == key);
-        if (hit) {
-            if (lane == __ffs(hit) - 1) atomicAdd(tv + g + lane, cnt);
-            return;
+    uint64_t g = mix64(key) & nslot_mask;
+    for (int t = 0; t < max_probes; ++t) {
+        uint64_t cur = *((volatile uint64_t *) (tk + g));
+        if (cur == EMPTY_KEY) {
+            cur = atomicCAS((unsigned long long *) (tk + g), (unsigned long long) EMPTY_KEY, (unsigned long long) key);
+            if (cur == EMPTY_KEY) cur = key;
         }
-        const uint32_t emp = __ballot_sync(SG_FULL, cur == EMPTY_KEY);
-        if (emp) {
-            const int e = __ffs(emp) - 1;
-            uint64_t old = 0;
-            if (lane == e) old = atomicCAS((unsigned long long *) (tk + g + lane), (unsigned long long) EMPTY_KEY, (unsigned long long) key);
-            old = __shfl_sync(SG_FULL, old, e);
-            if (old == EMPTY_KEY || old == key) {
-                if (lane == e) atomicAdd(tv + g + lane, cnt);
-                return;
-            }
-            continue;
-        }
-        g = (g + 32) & nslot_mask;
-        ++tries;
+        if (cur == key) { atomicAdd(tv + g, cnt); return true; }
+        g = (g + 1) & nslot_mask;
     }
-    if (lane == 0) *full = 1u;
+    return false;
 }
 
 // one key per lane (EMPTY_KEY = nothing): add 1 for every lane's key; the whole warp must call
