@@ -206,6 +206,10 @@ int sg_stat_multiplicities(sg_batch *b, int which, uint32_t **host_out, uint64_t
  * k-mer (splitting it like process_kmer_cluster when it does not), assigns
  * dense ids in hash order and rewrites k_mer[] to id << 1. */
 int sg_count(sg_batch *b);
+/* After sg_count returned SG_E_SMER_CONFLICT: what the reference prints before it exits (syncmer.c:1371-1374), for the first
+ * class in hash order that holds two s-mer codes: out[0] the k-mer hash, out[1] / out[2] the s-mer code and the read of the
+ * class's first tuple, out[3] / out[4] the code and the read of the first tuple that disagrees. SG_E_STATE otherwise. */
+int sg_count_conflict(sg_batch *b, uint64_t out[5]);
 /* How sg_count decides that two tuples of equal hash are the same k-mer. 0 (default): equal hash and
  * equal 64-bit fingerprint (a second, independent hash of the same packed k-mer, computed by
  * sg_extract); a group with differing fingerprints is then split by exact sequence comparison like

@@ -398,7 +398,7 @@ struct FillArgs {
     uint64_t n;
     uint64_t *kid;                       // read order: id << 1
     uint64_t *scm_h, *scm_s, *occ_off;
-    unsigned long long *status;          // [0] |= s-mer conflict
+    unsigned long long *status;          // [0] |= s-mer conflict, [3] = n - (first tuple in hash order that disagrees with its class)
 };
 
 __global__ void __launch_bounds__(256) fill_kernel(FillArgs A)
@@ -409,8 +409,17 @@ __global__ void __launch_bounds__(256) fill_kernel(FillArgs A)
     const uint64_t id = A.ex[i] + head - 1;
     A.kid[A.sval[i]] = id << 1;                                  // syncmer.c:1378
     if (head) { A.scm_h[id] = A.skey[i]; A.scm_s[id] = A.ssmer[i]; A.occ_off[id] = i; }
-    else if (A.ssmer[i] != A.ssmer[i - 1]) atomicOr(A.status, 1ull);   // syncmer.c:1370-1376
+    else if (A.ssmer[i] != A.ssmer[i - 1]) { atomicOr(A.status, 1ull); atomicMax(A.status + 3, (unsigned long long) (A.n - i)); }   // syncmer.c:1370-1376
     if (i == A.n - 1) A.occ_off[id + 1] = A.n;
+}
+
+// what the reference prints before it gives up (syncmer.c:1371-1374): the class's hash, the s-mer code and read of its first
+// tuple, the code and read of the first tuple that disagrees
+__global__ void conflict_info_kernel(const uint64_t *skey, const uint64_t *ssmer, const uint64_t *socc, const uint32_t *newid, uint64_t i, unsigned long long *out)
+{
+    uint64_t h = i;
+    while (h > 0 && !newid[h]) --h;
+    out[0] = skey[i]; out[1] = ssmer[h]; out[2] = socc[h] >> 32; out[3] = ssmer[i]; out[4] = socc[i] >> 32;
 }
 
 __global__ void __launch_bounds__(256) cov_kernel(const uint64_t *occ_off, uint32_t *cov, uint64_t u)
@@ -966,7 +975,8 @@ int sg_count(sg_batch *b)
     if (rc) return rc;
     ctx->t_begin(SG_T_GROUP);
     RS(b->flags, (N + 1) * 4); RS(b->differs, N + 1); RS(b->ids, (N + 2) * 8); RS(b->ids_tmp, scan_tmp_words(N) * 8);
-    RS(b->status, 4 * 8); RS(b->kid, (N + 1) * 8);
+    RS(b->status, 16 * 8); RS(b->kid, (N + 1) * 8);
+    b->has_conflict = false;
     unsigned long long *status = (unsigned long long *) b->status.p;
     CK(cudaMemsetAsync(status, 0, 4 * 8, st));
     CK(cudaMemsetAsync(b->differs.p, 0, N + 1, st));
@@ -1031,7 +1041,25 @@ int sg_count(sg_batch *b)
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
     b->counted = true;
-    if (hs[0]) { ctx->err = "identical kmers have different smers"; return SG_E_SMER_CONFLICT; }
+    if (hs[0]) {
+        conflict_info_kernel<<<1, 1, 0, st>>>((const uint64_t *) b->skey.p, (const uint64_t *) b->ssmer.p, (const uint64_t *) b->socc.p,
+                (const uint32_t *) b->flags.p, N - hs[3], status + 8);
+        unsigned long long ci[5];
+        CK(cudaMemcpyAsync(ci, status + 8, sizeof(ci), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        for (int j = 0; j < 5; ++j) b->conflict[j] = ci[j];
+        b->has_conflict = true;
+        ctx->err = "identical kmers have different smers";
+        return SG_E_SMER_CONFLICT;
+    }
+    return SG_OK;
+}
+
+int sg_count_conflict(sg_batch *b, uint64_t out[5])
+{
+    if (!b || !out) return SG_E_ARG;
+    if (!b->has_conflict) return SG_E_STATE;
+    for (int j = 0; j < 5; ++j) out[j] = b->conflict[j];
     return SG_OK;
 }
 

@@ -83,6 +83,8 @@ struct sg_batch {
     int hash_bits = 64;                          // < 64 only through sg_debug_set_hash_bits (tests)
     sg::DevBuf scm_h, scm_s, scm_cov, scm_occ_off, status;
     uint64_t n_unique = 0, n_collisions = 0;
+    bool has_conflict = false;                   // the last sg_count ended with SG_E_SMER_CONFLICT: what the reference would have printed
+    uint64_t conflict[5] = {};                   // k-mer hash, first s-mer code, its read, disagreeing code, its read
     sg::DevBuf smer_pairs;                       // multi-GPU: (s-mer code, local count) pairs of the last sg_stat
     uint64_t smer_slots = 0;                     // slots of the s-mer tally table left by sg_stat (0: none)
     // a7

@@ -196,6 +196,7 @@ int main(int argc, char *argv[])
 
     ret = syncasm(argv + z.first_file, argc - z.first_file, m_data, k, s, bubble, tip, min_k_cov, min_a_cov_f, weak_cross,
                   do_ec, unzip, n_threads, out, 0, verbose);
+    if (ret == 2) exit(EXIT_FAILURE);              /* the reference left from inside process_kmer_cluster: nothing more is printed */
     if (ret) {
         fprintf(stderr, "[E::%s] failed to constrcut assembly\n", __func__);
         exit(EXIT_FAILURE);

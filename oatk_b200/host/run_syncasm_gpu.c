@@ -10,7 +10,8 @@
  *   clean-up          asmg_pop_bubble / asmg_remove_weak_crosslink / asmg_drop_tip until nothing changes (cleaning_gpu.c)
  *   unzipping         scg_read_alignment / scg_update_utg_cov / scg_multiplex rounds, scg_demultiplex (f3, unzip_gpu.c)
  *   final coverages   scg_read_alignment -> scg_ra_utg_coverage -> scg_ra_arc_coverage -> scg_consensus -> .utg.final.gfa
- * Errors come back as 1 after an [E::syncasm] line, as in the reference; nothing here calls exit().
+ * Errors come back as 1 after an [E::syncasm] line, as in the reference (2: the reference would have left the process from
+ * inside process_kmer_cluster, its lines are printed); nothing here calls exit().
  */
 #include <stdlib.h>
 #include <string.h>
@@ -177,7 +178,10 @@ int syncasm(char **file_in, int n_file, size_t m_data, int k, int s, int bubble_
     }
 
     scm_db = collect_syncmer_from_reads(sr_db);
-    if (!scm_db) {                                    /* the reference dereferences NULL here (syncasm.c:205) */
+    if (!scm_db) {
+        /* an empty database: the reference dereferences NULL here (syncasm.c:205). Identical k-mers with different s-mers: the
+         * reference has printed its four lines and left the process with EXIT_FAILURE; the lines are out, 2 tells main */
+        if (oatk_collect_conflict()) { ret = 2; goto done; }
         fprintf(stderr, "[E::%s] empty syncmer graph\n", __func__);
         ret = 1;
         goto done;

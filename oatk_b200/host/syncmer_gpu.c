@@ -557,6 +557,9 @@ static void collect_ids(uint64_t lo, uint64_t hi, void *arg)
     }
 }
 
+static int oatk_collect_conflict_flag = 0;
+int oatk_collect_conflict(void) { return oatk_collect_conflict_flag; }
+
 syncmer_db_t *collect_syncmer_from_reads(sr_db_t *sr_db)
 {
     sg_batch *b = batch_of(sr_db, 0);
@@ -569,8 +572,17 @@ syncmer_db_t *collect_syncmer_from_reads(sr_db_t *sr_db)
     if (!b) { fprintf(stderr, "[E::%s] the read database was not produced by sr_read_mem\n", __func__); return 0; }
     rc = sg_count(b);
     if (rc == SG_E_EMPTY) return 0;                            /* syncmer.c:1414-1417 */
+    oatk_collect_conflict_flag = 0;
     if (rc == SG_E_SMER_CONFLICT) {
-        fprintf(stderr, "[E::%s] identical kmers have different smers\n", __func__);   /* the reference exits here */
+        /* the reference prints these four lines from process_kmer_cluster and exits (syncmer.c:1370-1376); this layer returns
+         * NULL and leaves the decision to the caller (oatk_collect_conflict() tells it apart from an empty database) */
+        uint64_t c[5] = {0, 0, 0, 0, 0};
+        sg_count_conflict(b, c);
+        fprintf(stderr, "[E::process_kmer_cluster] identical kmers have different smers\n");
+        fprintf(stderr, "[E::process_kmer_cluster] kmer hash  : %lu\n", (unsigned long) c[0]);
+        fprintf(stderr, "[E::process_kmer_cluster] smer code 0: %lu; read id: %lu\n", (unsigned long) c[1], (unsigned long) c[2]);
+        fprintf(stderr, "[E::process_kmer_cluster] smer code 1: %lu; read id: %lu\n", (unsigned long) c[3], (unsigned long) c[4]);
+        oatk_collect_conflict_flag = 1;
         return 0;
     }
     if (rc != SG_OK || (rc = sg_count_sizes(b, &z)) != SG_OK) {

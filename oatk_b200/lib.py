@@ -59,7 +59,7 @@ SYMBOLS = [
     "sg_ctx_launches", "sg_ctx_enable_timing", "sg_ctx_timings",
     "sg_batch_create", "sg_batch_destroy", "sg_batch_set_reads_host", "sg_batch_set_reads_device",
     "sg_batch_set_sid_base", "sg_extract", "sg_extract_sizes", "sg_extract_download",
-    "sg_stat", "sg_stat_multiplicities", "sg_count", "sg_count_sizes", "sg_count_download", "sg_arcs", "sg_arcs_download",
+    "sg_stat", "sg_stat_multiplicities", "sg_count", "sg_count_conflict", "sg_count_sizes", "sg_count_download", "sg_arcs", "sg_arcs_download",
     "sg_tuples_partition", "sg_tuples_adopt", "sg_debug_set_hash_bits", "sg_debug_set_sort_low_bits", "sg_debug_sort_info", "sg_debug_set_pack_bits", "sg_debug_scan_info", "sg_batch_buffer",
     "sg_ids_pack", "sg_ids_scatter", "sg_batch_set_exact_verify", "sg_smer_counts_pack", "sg_smer_counts_merge", "sg_batch_set_lists_host",
     "sg_comm_unique_id", "sg_comm_init_rank", "sg_comm_init_all", "sg_comm_destroy", "sg_comm_rank", "sg_comm_world", "sg_comm_bytes_sent",
@@ -101,7 +101,7 @@ def _lib():
     L.sg_extract.argtypes = [vp, i32, i32]
     L.sg_extract_sizes.argtypes = [vp, C.POINTER(ExtractSizes)]
     L.sg_extract_download.argtypes = [vp, C.POINTER(ExtractOut)]
-    for name, args in (("sg_stat", [vp, C.POINTER(StatOut)]), ("sg_count", [vp]),
+    for name, args in (("sg_stat", [vp, C.POINTER(StatOut)]), ("sg_count", [vp]), ("sg_count_conflict", [vp, C.POINTER(u64)]),
                        ("sg_count_sizes", [vp, C.POINTER(CountSizes)]), ("sg_count_download", [vp, C.POINTER(CountOut)]),
                        ("sg_arcs", [vp, C.c_uint32, C.c_double, C.POINTER(u64)]), ("sg_arcs_download", [vp, vp]),
                        ("sg_tuples_partition", [vp, i32, vp, C.POINTER(vp)]), ("sg_tuples_adopt", [vp, vp, u64]),
@@ -268,6 +268,12 @@ class Batch:
 
     def count(self):
         _ck(self.ctx.h, _lib().sg_count(self.h), "sg_count")
+
+    def count_conflict(self):
+        """after count() raised SG_E_SMER_CONFLICT: (k-mer hash, s-mer code 0, read 0, s-mer code 1, read 1)"""
+        out = (C.c_uint64 * 5)()
+        _ck(self.ctx.h, _lib().sg_count_conflict(self.h, out), "sg_count_conflict")
+        return tuple(int(x) for x in out)
 
     def count_sizes(self):
         z = CountSizes()

@@ -11,7 +11,7 @@ def hifi_reads(seed, genome_len, n_reads, read_len, err):
     random strand, per-base error rate `err` split evenly over sub/ins/del."""
     rng = np.random.default_rng(seed)
     genome = rng.integers(0, 4, genome_len, dtype=np.uint8)
-    g2 = np.concatenate([genome, genome[:read_len]])
+    g2 = np.concatenate([genome, genome[:read_len]]) if read_len <= genome_len else np.tile(genome, read_len // genome_len + 2)[:genome_len + read_len]
     out = []
     for _ in range(n_reads):
         p = int(rng.integers(0, genome_len))

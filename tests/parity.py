@@ -43,3 +43,37 @@ def per_read_report(got, exp, max_reads=5):
             if len(out) >= max_reads:
                 break
     return out
+
+
+# ---- the one input class on which the reference gives up ------------------------------------------------------
+# (GC)n broken by two ambiguous bases in opposite phase: the k-mers behind them are the same k-mer on opposite strands, each
+# is a syncmer through the same s-mer, but the stored s-mer code carries the other strand bit -- "identical kmers have
+# different smers" (syncmer.c:1370-1376), four [E::process_kmer_cluster] lines and exit(EXIT_FAILURE). (Found by
+# tools/fuzz_oracle_vs_reference.py on a read whose homopolymer-compressed form is (GC)n.)
+CONFLICT_K, CONFLICT_S = 129, 29
+CONFLICT_READ = bytearray(b"GC" * 400)
+CONFLICT_READ[200] = CONFLICT_READ[501] = ord("N")
+CONFLICT_READ = bytes(CONFLICT_READ)
+
+_REF_CONFLICT_SCRIPT = r"""
+import os, sys
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+from pyoracle import Ref, pack_reads
+import parity
+reads = [parity.CONFLICT_READ] if %d == 0 else eval(open(%r).read())
+bases, off = pack_reads(reads)
+ref = Ref()
+db, _ = ref.extract(bases, off, parity.CONFLICT_K, parity.CONFLICT_S)
+ref.collect(db)
+print("survived")
+"""
+
+
+def reference_on_conflict(reads_file=None):
+    """runs the unmodified reference (oracle/_ref/libref.so) on CONFLICT_READ (or the python list literal in reads_file) in
+    a process of its own, because it exits; returns (exit code, [E::...] lines)"""
+    import os, subprocess, sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    script = _REF_CONFLICT_SCRIPT % (os.path.join(os.path.dirname(here), "oracle"), here, 1 if reads_file else 0, reads_file or "")
+    p = subprocess.run([sys.executable, "-c", script], stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300)
+    return p.returncode, [l for l in p.stderr.decode().splitlines() if l.startswith("[E::")], p.stdout.decode()

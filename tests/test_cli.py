@@ -118,3 +118,27 @@ def test_failed_run_exit_code(binaries):
     for f in os.listdir(tmp):
         os.unlink(os.path.join(tmp, f))
     os.rmdir(tmp)
+
+
+@pytest.mark.gpu
+def test_smer_conflict_ends_the_run_like_the_reference(binaries):
+    """identical k-mers with different s-mer codes (tests/parity.py): the reference prints four [E::process_kmer_cluster]
+    lines and leaves with EXIT_FAILURE from inside collect_syncmer_from_reads; same lines, same exit code, nothing after"""
+    import parity
+    import make_golden_syncasm as G
+    ours, ref = binaries
+    tmp = tempfile.mkdtemp()
+    fa = os.path.join(tmp, "reads.fa")
+    G.write_fasta("repeats_default", fa)
+    with open(fa, "ab") as f:
+        f.write(b">conflict\n" + parity.CONFLICT_READ + b"\n")
+    opts = ["-k", str(parity.CONFLICT_K), "-s", str(parity.CONFLICT_S), "-c", "3", "-t", "2"]
+    a = run(ours, opts + ["-o", os.path.join(tmp, "ours"), fa])
+    b = run(ref, [fa] + opts + ["-o", os.path.join(tmp, "ref")])
+    assert a[0] == b[0] == 1
+    la, lb = norm_stderr(a[2], ours), norm_stderr(b[2], ref)
+    assert [l for l in lb if l.startswith("[E::")][0] == "[E::process_kmer_cluster] identical kmers have different smers"
+    assert la == lb
+    for f in os.listdir(tmp):
+        os.unlink(os.path.join(tmp, f))
+    os.rmdir(tmp)

@@ -172,3 +172,32 @@ def test_host_binding_reports_and_never_fails(gpu_ctx):
     assert isinstance(node, int) and ncpu == 0
     node2, ncpu2 = lib.bind_host_near_device(0, cpus=False, memory=True)
     assert ncpu2 == 0 and (node2 == node or node2 < -1)
+
+
+def test_smer_conflict_is_reported_like_the_reference(gpu_ctx, oracle, ref):
+    """the one input class on which the reference exits (identical k-mers, different s-mer codes; tests/parity.py): sg_count
+    returns SG_E_SMER_CONFLICT and sg_count_conflict the figures of the reference's four lines; with other reads around it,
+    the FIRST conflicting class in hash order is the one reported"""
+    from oatk_b200 import lib
+    k, s = parity.CONFLICT_K, parity.CONFLICT_S
+    other = synth.hifi_reads(21, 30000, 40, 3000, 0.001)
+    for reads, rid in (([parity.CONFLICT_READ], 0), (other[:20] + [parity.CONFLICT_READ] + other[20:], 20)):
+        bases, off = pack_reads(reads)
+        b = gpu_batch(gpu_ctx, bases, off, k, s)
+        with pytest.raises(lib.SgError) as e:
+            b.count()
+        assert e.value.code == -6
+        got = b.count_conflict()
+        rc, lines, _ = parity.reference_on_conflict()
+        assert rc == 1
+        assert lines[1].endswith(": %d" % got[0])
+        assert lines[2] == "[E::process_kmer_cluster] smer code 0: %d; read id: 0" % got[1] and got[2] == rid
+        assert lines[3] == "[E::process_kmer_cluster] smer code 1: %d; read id: 0" % got[3] and got[4] == rid
+        b.close()
+    # a batch without a conflict has nothing to report
+    bases, off = pack_reads(other)
+    b = gpu_batch(gpu_ctx, bases, off, k, s)
+    b.count()
+    with pytest.raises(lib.SgError):
+        b.count_conflict()
+    b.close()

@@ -119,3 +119,19 @@ def test_peak_finder(oracle):
     flat = np.zeros(1001, np.int64)
     flat[1] = 10
     assert oracle.analyze_count(flat)[0] == -1     # low coverage: no rise after the first minimum
+
+
+def test_smer_conflict_is_where_the_reference_gives_up(oracle, ref):
+    """identical k-mers with different s-mer codes: the reference prints four lines from process_kmer_cluster and exits
+    (syncmer.c:1370-1376); the oracle flags the same input (and nothing else in the suites does)"""
+    bases, off = pack_reads([parity.CONFLICT_READ])
+    db, f = oracle.extract(bases, off, parity.CONFLICT_K, parity.CONFLICT_S)
+    c = oracle.collect(db, 1)
+    assert f["n_scm"].tolist() == [2] and c["smer_conflict"] == 1 and len(c["h"]) == 1
+    rc, lines, out = parity.reference_on_conflict()
+    assert rc == 1 and out == ""
+    assert lines[0] == "[E::process_kmer_cluster] identical kmers have different smers"
+    assert lines[1] == "[E::process_kmer_cluster] kmer hash  : %d" % int(c["h"][0])
+    assert lines[2] == "[E::process_kmer_cluster] smer code 0: %d; read id: 0" % int(c["s"][0])
+    assert lines[3] == "[E::process_kmer_cluster] smer code 1: %d; read id: 0" % (int(c["s"][0]) ^ 1)
+    oracle.free(db, c)
