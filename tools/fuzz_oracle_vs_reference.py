@@ -2,7 +2,8 @@
 """Randomised check of the oracle (oracle/sync_oracle.c, the CPU restatement the GPU tests compare with) against the
 unmodified reference compiled in place (oracle/_ref/libref.so): random k in (s, s + 2500], random s in [1, 31] (odd and
 even), mixtures of HiFi-like reads (error rates up to 2 %), the adversarial set, short-period tandem arrays with
-ambiguous bases; every sr_t field, the sr_db_stat figures and the syncmer database must be equal. Each case runs in a
+ambiguous bases; every sr_t field, the sr_db_stat figures, the syncmer database and the arc list of make_syncmer_graph (random
+coverage thresholds) must be equal. Each case runs in a
 forked child because the reference calls exit() on inputs it rejects ("identical kmers have different smers").
 Test infrastructure, CPU only.
 
@@ -53,6 +54,25 @@ def one(seed, note=None):
     elif oc is not None:
         dd = parity.diff(oc, rc, parity.SCM_FIELDS)
         if dd: why.append(("collect", dd[:3]))
+        # a7: the arc list of make_syncmer_graph for a random (minimum k-mer coverage, arc coverage fraction)
+        rng = np.random.default_rng(seed + 7)
+        mkc, af = int(rng.choice([0, 1, 2, 3, 5])), float(rng.choice([0.0, 0.05, 0.35, 1.0]))
+        g = ref.graph(rdb, rc, mkc, af)
+        gd = ref.graph_dump(g)
+        first = gd["vtx_lists"][np.concatenate([[0], np.cumsum(gd["vtx_n"])[:-1]]).astype(np.int64)] if len(gd["vtx_n"]) else np.zeros(0, np.uint64)
+        ra = gd["arcs"]
+        if len(ra):
+            v = first[(ra[:, 0] >> 1).astype(np.int64)] | (ra[:, 0] & 1)
+            w = first[(ra[:, 1] >> 1).astype(np.int64)] | (ra[:, 1] & 1)
+            a = np.stack([v, w, ra[:, 4] & 0x3FFFFFFF, (ra[:, 4] >> 31) & 1], axis=1).astype(np.uint64)
+            a[(a[:, 1] ^ 1) == a[:, 0], 3] = 0          # asmg_arc_fix_symm flips comp of v+ -> v- (tests/golden_util.py)
+            a = a[np.lexsort((a[:, 2], a[:, 3], a[:, 1], a[:, 0]))]
+        else:
+            a = np.zeros((0, 4), np.uint64)
+        oa = oracle.arcs(odb, oc, mkc, af)
+        oa = oa[np.lexsort((oa[:, 2], oa[:, 3], oa[:, 1], oa[:, 0]))] if len(oa) else oa
+        if oa.shape != a.shape or not np.array_equal(oa, a): why.append(("arcs", mkc, af, oa.shape, a.shape))
+        ref.free(g=g)
     return k, s, len(reads), why
 
 
