@@ -20,7 +20,9 @@
 // it and single-GPU users never touch it. Two ways to form the communicator:
 //   sg_comm_init_rank  one process per GPU (bench.py under torchrun): rank 0 makes the unique id with
 //                      sg_comm_unique_id and hands it to the others by whatever means the launcher has
-//   sg_comm_init_all   one process, one thread per GPU (the host layer's syncasm() with OATK_GPUS=n)
+//   sg_comm_init_all   one process, one host thread per GPU (every data call below blocks until its peers have made it too, so
+//                      the calls for different GPUs must come from different threads); nothing in this repository uses it yet:
+//                      the host layer's syncasm() runs on one GPU
 // Every sg_comm_* data call is collective: all ranks (or all threads) make the same calls in the same order.
 #include <dlfcn.h>
 #include <cstdio>
