@@ -321,9 +321,9 @@ int fastx_load(const char *const *files, int n_files, uint64_t max_bases, fastx_
     for (int f = 0; f < n_files && !x->limit_reached; ++f) {
         blob_t b;
         if (blob_open(files[f], &b) != 0) {
-            fprintf(stderr, "[E::%s] fail to open file \"%s\"\n", __func__, files[f]);   /* the reference exits here, sstream.c:46-49 */
+            fprintf(stderr, "[E::%s] fail to open file \"%s\"\n", "make_kseq_stream", files[f]);   /* the reference exits here, sstream.c:46-49 */
             fastx_free(x);
-            return -1;
+            return FASTX_E_OPEN;
         }
         /* kseq learns about the end of file from a short read of its 16 KB buffer: when the size is a multiple of
          * that, one more (empty) read happens before "end of file" is known. Only visible in corner cases. */
@@ -372,7 +372,7 @@ int sr_read_files(sr_db_t *sr_db, const char *const *files, int n_files, size_t 
 {
     fastx_t x;
     oatk_tick(0);
-    if (fastx_load(files, n_files, max_bases, &x) != 0) return -1;
+    { const int lrc = fastx_load(files, n_files, max_bases, &x); if (lrc != 0) return lrc; }
     oatk_tick("reads: parse files");
     if (x.limit_reached)
         fprintf(stderr, "[M::%s] data limit (%lu) reached. Discard the remaining sequences...\n", "sr_read", (unsigned long) max_bases);

@@ -11,7 +11,7 @@
  *   unzipping         scg_read_alignment / scg_update_utg_cov / scg_multiplex rounds, scg_demultiplex (f3, unzip_gpu.c)
  *   final coverages   scg_read_alignment -> scg_ra_utg_coverage -> scg_ra_arc_coverage -> scg_consensus -> .utg.final.gfa
  * Errors come back as 1 after an [E::syncasm] line, as in the reference (2: the reference would have left the process from
- * inside process_kmer_cluster, its lines are printed); nothing here calls exit().
+ * inside -- a file that cannot be opened, identical k-mers with different s-mers -- and its lines are printed); nothing here calls exit().
  */
 #include <stdlib.h>
 #include <string.h>
@@ -159,6 +159,7 @@ int syncasm(char **file_in, int n_file, size_t m_data, int k, int s, int bubble_
         oatk_gpu_keep_run_lengths(was);
         oatk_gpu_keep_packed_bases(was_hs);
     }
+    if (rc == FASTX_E_OPEN) { ret = 2; goto done; }   /* the reference has printed its line and left from inside sstream (sstream.c:46-49) */
     if (rc != 0) {
         fprintf(stderr, "[E::%s] failed to read the input files (%d)\n", __func__, rc);
         ret = 1;

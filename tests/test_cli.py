@@ -142,3 +142,22 @@ def test_smer_conflict_ends_the_run_like_the_reference(binaries):
     for f in os.listdir(tmp):
         os.unlink(os.path.join(tmp, f))
     os.rmdir(tmp)
+
+
+@pytest.mark.parametrize("which", ["first", "second"])
+def test_unopenable_input_ends_like_the_reference(binaries, which):
+    """a file that cannot be opened: the reference prints one line from make_kseq_stream and exits (sstream.c:46-49), at once
+    for the first file, after reading the first file for a later one; same line, same exit code, nothing else (no GPU needed:
+    the files are read before the device is touched)"""
+    ours, ref = binaries
+    tmp = tempfile.mkdtemp()
+    good = os.path.join(tmp, "good.fa")
+    open(good, "wb").write(b">a\n" + b"ACGTTGCA" * 40 + b"\n")
+    files = [os.path.join(tmp, "missing.fa")] if which == "first" else [good, os.path.join(tmp, "missing.fa")]
+    a = run(ours, ["-k", "101", "-s", "11", "-o", os.path.join(tmp, "o")] + files)
+    b = run(ref, files + ["-k", "101", "-s", "11", "-o", os.path.join(tmp, "r")])
+    assert a[0] == b[0] == 1
+    assert norm_stderr(a[2], ours) == norm_stderr(b[2], ref) == ['[E::make_kseq_stream] fail to open file "%s"' % files[-1]]
+    for f in os.listdir(tmp):
+        os.unlink(os.path.join(tmp, f))
+    os.rmdir(tmp)
