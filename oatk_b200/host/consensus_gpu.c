@@ -491,10 +491,9 @@ static void *cons_worker(void *arg)
 
 static void cons_run(cons_job_t *J, int phase, uint64_t n_items)
 {
-    long nt = sysconf(_SC_NPROCESSORS_ONLN);
+    long nt = oatk_host_threads();
     pthread_t th[16];
-    if (nt > 16) nt = 16;
-    if (nt < 1 || n_items < 4) nt = 1;
+    if (n_items < 4) nt = 1;
     J->phase = phase; J->next = 0;
     if (nt == 1) { cons_worker(J); return; }
     for (long i = 0; i < nt; ++i) pthread_create(&th[i], 0, cons_worker, J);

@@ -314,7 +314,7 @@ int fastx_load(const char *const *files, int n_files, uint64_t max_bases, fastx_
     x->off = (uint64_t *) malloc((x->m + 1) * sizeof(uint64_t));
     x->off[0] = 0;
     x->names = (char **) malloc(x->m * sizeof(char *));
-    long nt = sysconf(_SC_NPROCESSORS_ONLN);
+    long nt = oatk_host_threads();
     if (getenv("OATK_FASTX_THREADS")) nt = atol(getenv("OATK_FASTX_THREADS"));      /* tests: force a thread count */
     if (nt > 16) nt = 16;
     uint64_t total = 0;

@@ -183,8 +183,9 @@ static int finalize_symmetric(asmg_t *g)
     sym_t S = {g, 0, 0};
     const uint64_t PENDING = 0x8000000000000000ULL;
     uint64_t i, next = 0;
-    static long min_arcs = -1;                           /* small graphs have nothing to gain; OATK_PF_MIN (tests) overrides */
-    if (min_arcs < 0) { const char *e = getenv("OATK_PF_MIN"); min_arcs = e ? atol(e) : 1000000; }
+    static long min_arcs_cached = -1;                    /* small graphs have nothing to gain; OATK_PF_MIN (tests) overrides */
+    long min_arcs = __atomic_load_n(&min_arcs_cached, __ATOMIC_RELAXED);
+    if (min_arcs < 0) { const char *e = getenv("OATK_PF_MIN"); min_arcs = e ? atol(e) : 1000000; __atomic_store_n(&min_arcs_cached, min_arcs, __ATOMIC_RELAXED); }
     if (g->n_arc < (uint64_t) min_arcs || g->n_arc == 0) return 0;
     S.comp = (uint64_t *) malloc(sizeof(uint64_t) * g->n_arc);
     oatk_parallel_for(g->n_arc, sym_scan, &S);

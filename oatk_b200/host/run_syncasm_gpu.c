@@ -143,6 +143,7 @@ int syncasm(char **file_in, int n_file, size_t m_data, int k, int s, int bubble_
     scg_ra_v *ra_db = 0;
     int ret = 0, rc;
 
+    oatk_set_host_threads(n_threads);                 /* -t bounds the helper pools of this layer too */
     sr_db = (sr_db_t *) malloc(sizeof(sr_db_t));
     sr_db_init(sr_db, k, s);
     {

@@ -714,15 +714,28 @@ int syncmer_graph_arcs(sr_db_t *sr_db, syncmer_db_t *scm_db, uint32_t min_k_cov,
 /* fn(lo, hi, arg) over [0, n) cut into contiguous ranges, on up to 16 threads (the caller's included) */
 typedef struct { void (*fn)(uint64_t, uint64_t, void *); void *arg; uint64_t lo, hi; } pf_job_t;
 static void *pf_run(void *p) { pf_job_t *j = (pf_job_t *) p; j->fn(j->lo, j->hi, j->arg); return 0; }
+/* how many host threads the helper pools of this layer may use: the cores of the machine, at most 16, at most what the
+ * caller of syncasm() asked for with -t (0: no wish) */
+static int g_host_threads = 0;
+void oatk_set_host_threads(int n) { __atomic_store_n(&g_host_threads, n > 0 ? n : 0, __ATOMIC_RELAXED); }
+long oatk_host_threads(void)
+{
+    long nt = sysconf(_SC_NPROCESSORS_ONLN);
+    const int cap = __atomic_load_n(&g_host_threads, __ATOMIC_RELAXED);
+    if (nt > 16) nt = 16;
+    if (cap > 0 && nt > cap) nt = cap;
+    return nt < 1 ? 1 : nt;
+}
+
 void oatk_parallel_for(uint64_t n, void (*fn)(uint64_t lo, uint64_t hi, void *arg), void *arg)
 {
-    long nt = sysconf(_SC_NPROCESSORS_ONLN), t;
+    long nt = oatk_host_threads(), t;
     pf_job_t job[16];
     pthread_t th[16];
-    static long min_n = -1;                            /* OATK_PF_MIN: smallest n worth threads (tests lower it) */
-    if (min_n < 0) { const char *e = getenv("OATK_PF_MIN"); min_n = e ? atol(e) : 65536; }
-    if (nt > 16) nt = 16;
-    if (nt < 1 || n < (uint64_t) min_n) nt = 1;
+    static long min_n_cached = -1;                     /* OATK_PF_MIN: smallest n worth threads (tests lower it) */
+    long min_n = __atomic_load_n(&min_n_cached, __ATOMIC_RELAXED);
+    if (min_n < 0) { const char *e = getenv("OATK_PF_MIN"); min_n = e ? atol(e) : 65536; __atomic_store_n(&min_n_cached, min_n, __ATOMIC_RELAXED); }
+    if (n < (uint64_t) min_n) nt = 1;
     if (nt == 1 && min_n <= 1 && n > 1) nt = 4;        /* ... and force threads even on a one-core box */
     for (t = 0; t < nt; ++t) { job[t].fn = fn; job[t].arg = arg; job[t].lo = n * (uint64_t) t / (uint64_t) nt; job[t].hi = n * (uint64_t) (t + 1) / (uint64_t) nt; }
     for (t = 1; t < nt; ++t) pthread_create(&th[t], 0, pf_run, &job[t]);

@@ -126,6 +126,8 @@ int oatk_gpu_update_lists(sr_db_t *sr_db, syncmer_db_t *scm_db);
 void oatk_parallel_for(uint64_t n, void (*fn)(uint64_t lo, uint64_t hi, void *arg), void *arg);
 void oatk_tick(const char *what);      /* OATK_TIMING=1: stage times on stderr */
 int oatk_collect_conflict(void);                /* 1: the last collect_syncmer_from_reads returned NULL because identical k-mers had different s-mers (the reference exits there) */
+void oatk_set_host_threads(int n);              /* the helper thread pools of this layer use at most n threads (0: the cores, up to 16); syncasm() passes -t */
+long oatk_host_threads(void);
 int oatk_gpu_set_device(int device);
 /* run lengths stay on the device (sr_t.ho_rl == NULL) for the read databases made from now on; returns the previous setting */
 int oatk_gpu_keep_run_lengths(int on);
