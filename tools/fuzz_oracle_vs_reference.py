@@ -7,7 +7,7 @@ coverage thresholds) must be equal. Each case runs in a
 forked child because the reference calls exit() on inputs it rejects ("identical kmers have different smers").
 Test infrastructure, CPU only.
 
-  python tools/fuzz_oracle_vs_reference.py <first seed> <last seed + 1>"""
+  python tools/fuzz_oracle_vs_reference.py <first seed> <last seed + 1> [mean]"""
 import sys, os
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
@@ -17,6 +17,10 @@ from oatk_b200 import synth
 import parity
 from pyoracle import Oracle, Ref, pack_reads
 oracle, ref = Oracle(), Ref()
+
+MEAN = False          # third argument `mean`: also long homopolymers (past 255 and past 65535 bases), runs of N, lower case and
+                      # IUPAC codes, empty and one-base reads
+
 
 def make(seed):
     rng = np.random.default_rng(seed)
@@ -31,6 +35,17 @@ def make(seed):
         r = bytearray(unit * int(rng.integers(5, 400)))
         for p in rng.integers(0, len(r), int(rng.integers(0, 5))): r[p] = ord("N")
         reads.append(bytes(r))
+    if MEAN:
+        for _ in range(int(rng.integers(0, 4))):
+            parts = []
+            for _ in range(int(rng.integers(1, 12))):
+                c = rng.random()
+                if c < 0.25: parts.append(bytes([rng.choice(list(b"ACGTacgtN"))]) * int(rng.choice([1, 2, 254, 255, 256, 257, 300, 1000, 65535, 65536, 70000])))
+                elif c < 0.5: parts.append(bytes(rng.choice(list(b"ACGTacgtNRYKMSWBDHVn-*"), int(rng.integers(1, 600))).tolist()))
+                else: parts.append(bytes(rng.choice(list(b"ACGT"), int(rng.integers(1, 3000))).tolist()))
+            reads.append(b"".join(parts))
+        if rng.random() < 0.3: reads.insert(int(rng.integers(0, len(reads) + 1)), b"")
+        if rng.random() < 0.3: reads.append(b"A")
     return k, s, reads
 
 def one(seed, note=None):
@@ -78,6 +93,7 @@ def one(seed, note=None):
 
 if __name__ == "__main__":
     lo, hi = int(sys.argv[1]), int(sys.argv[2])
+    MEAN = len(sys.argv) > 3 and sys.argv[3] == "mean"
     bad = conflicts = 0
     for seed in range(lo, hi):
         r, w = os.pipe()
