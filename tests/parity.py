@@ -49,7 +49,7 @@ def per_read_report(got, exp, max_reads=5):
 # (GC)n broken by two ambiguous bases in opposite phase: the k-mers behind them are the same k-mer on opposite strands, each
 # is a syncmer through the same s-mer, but the stored s-mer code carries the other strand bit -- "identical kmers have
 # different smers" (syncmer.c:1370-1376), four [E::process_kmer_cluster] lines and exit(EXIT_FAILURE). (Found by
-# tools/fuzz_oracle_vs_reference.py on a read whose homopolymer-compressed form is (GC)n.)
+# tests/tools/fuzz_oracle_vs_reference.py on a read whose homopolymer-compressed form is (GC)n.)
 CONFLICT_K, CONFLICT_S = 129, 29
 CONFLICT_READ = bytearray(b"GC" * 400)
 CONFLICT_READ[200] = CONFLICT_READ[501] = ord("N")

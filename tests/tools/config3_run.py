@@ -3,7 +3,7 @@
 (-c, -a) -> unitigs -> GFA, once through the host layer over libsyncgpu (GPU) and once through the unmodified
 reference on the host cores; the two GFA files must be byte-identical. Prints one JSON line with the stage times.
 
-  python tools/config3_run.py [--reads 20000] [--genome 1000000] [--c 30] [--k 1001] [--threads N]
+  python tests/tools/config3_run.py [--reads 20000] [--genome 1000000] [--c 30] [--k 1001] [--threads N]
 
 Needs a CUDA device and oracle/_ref/libref.so (test infrastructure: it is the checker and the CPU baseline)."""
 import argparse
@@ -15,7 +15,7 @@ import sys
 import tempfile
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 for p in (ROOT, os.path.join(ROOT, "oracle")):
     sys.path.insert(0, p)
 import numpy as np                                   # noqa: E402

@@ -5,10 +5,10 @@ no run starts. Exit code, stdout and stderr must be equal. CPU only (everything 
 touched). Round 2: 1500 command lines, equal -- after it found that a file that cannot be opened ended our command with
 three lines where the reference prints one.
 
-  python tools/fuzz_cli_options.py <seed> <number of command lines>"""
+  python tests/tools/fuzz_cli_options.py <seed> <number of command lines>"""
 import os
 import random, subprocess, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 OURS = os.path.join(ROOT, "oatk_b200", "host", "syncasm"); REF = os.path.join(ROOT, "oracle", "_ref", "syncasm")
 opts = ["-k", "-s", "-c", "-a", "-D", "-t", "-o", "-v", "-V", "-h", "--max-bubble", "--max-tip", "--weak-cross", "--unzip-round",
         "--no-read-ec", "--version", "--help", "--verbose", "--threads", "--max", "--m", "--un", "--no", "--we", "--ve", "--he", "--v", "--t",

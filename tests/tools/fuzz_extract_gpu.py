@@ -1,16 +1,16 @@
 #!/usr/bin/env python
 """Random-parameter hunt on the GPU: the device path (sg_extract, sg_stat, sg_count, sg_arcs through the C ABI) against the
-CPU oracle on the read sets and (k, s) pairs of tools/fuzz_oracle_vs_reference.py (k - s in [1, 2500], s in [1, 31] odd and
+CPU oracle on the read sets and (k, s) pairs of tests/tools/fuzz_oracle_vs_reference.py (k - s in [1, 2500], s in [1, 31] odd and
 even, HiFi-like reads, the adversarial set, short-period tandem arrays with ambiguous bases); every sr_t field, the
 multiplicity tables, the syncmer database and the arc list must be equal, an s-mer conflict must be reported as one.
 Needs a CUDA device; the oracle is the checker (test infrastructure).
 
-  python tools/fuzz_extract_gpu.py <first seed> <last seed + 1> [seconds]"""
+  python tests/tools/fuzz_extract_gpu.py <first seed> <last seed + 1> [seconds]"""
 import os
 import sys
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
     sys.path.insert(0, p)
 import numpy as np                                   # noqa: E402
@@ -19,7 +19,7 @@ from oatk_b200 import lib, synth                     # noqa: E402
 from pyoracle import Oracle, pack_reads              # noqa: E402
 
 
-def make(seed):                                      # the generator of tools/fuzz_oracle_vs_reference.py
+def make(seed):                                      # the generator of tests/tools/fuzz_oracle_vs_reference.py
     rng = np.random.default_rng(seed)
     s = int(rng.integers(1, 32))
     k = int(s + rng.integers(1, 400)) if rng.random() < 0.7 else int(s + rng.integers(1, 2500))

@@ -4,7 +4,7 @@ haplotypes, rare molecules and recombinants, random k / coverage thresholds / cl
 command against this layer's read error correction and graph stage, fed with the reference's extraction, database and
 graph construction (the device rows, which have their own GPU tests); both GFA files compared.
 
-  python tools/fuzz_graph_stage.py [--seeds 0:40] [--threads 3]
+  python tests/tools/fuzz_graph_stage.py [--seeds 0:40] [--threads 3]
 
 Needs oracle/_ref/libref.so (test infrastructure)."""
 import argparse
@@ -13,7 +13,7 @@ import os
 import sys
 import tempfile
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
     sys.path.insert(0, p)
 os.environ.setdefault("OATK_PF_MIN", "1")

@@ -7,9 +7,9 @@ coverage thresholds) must be equal. Each case runs in a
 forked child because the reference calls exit() on inputs it rejects ("identical kmers have different smers").
 Test infrastructure, CPU only.
 
-  python tools/fuzz_oracle_vs_reference.py <first seed> <last seed + 1> [mean]"""
+  python tests/tools/fuzz_oracle_vs_reference.py <first seed> <last seed + 1> [mean]"""
 import sys, os
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
     sys.path.insert(0, p)
 import numpy as np

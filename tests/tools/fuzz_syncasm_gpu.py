@@ -1,11 +1,11 @@
 #!/usr/bin/env python
-"""Randomised hunt for divergences in the WHOLE command on the GPU: the scenarios of tools/fuzz_graph_stage.py (random
+"""Randomised hunt for divergences in the WHOLE command on the GPU: the scenarios of tests/tools/fuzz_graph_stage.py (random
 mixtures of repeats, haplotypes, rare molecules, recombinants and tandem arrays; random k / s, coverage thresholds, clean-up
 limits, with and without read error correction and unzipping) through this repository's syncasm() -- device extraction,
 counting, arc tally, error filter, graph search, votes, run-length sums -- against the unmodified reference's syncasm() on the
 host; both GFA files must be byte-identical. Prints one line per seed and a JSON summary.
 
-  python tools/fuzz_syncasm_gpu.py [--seeds 0:40] [--hifi]
+  python tests/tools/fuzz_syncasm_gpu.py [--seeds 0:40] [--hifi]
 
 Needs a CUDA device and oracle/_ref/libref.so (test infrastructure: the checker)."""
 import argparse
@@ -15,8 +15,8 @@ import os
 import sys
 import tempfile
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests"), os.path.join(ROOT, "tools")):
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests"), os.path.join(ROOT, "tests", "tools")):
     sys.path.insert(0, p)
 import numpy as np                                   # noqa: E402
 from oatk_b200.host import build_host                # noqa: E402

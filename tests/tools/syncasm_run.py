@@ -4,7 +4,7 @@ layer's syncasm() (device rows on the GPU) and once by the unmodified reference'
 arguments (the reference's defaults: -k 1001 -s 31 -a 0.35, read error correction, 3 unzip rounds, --max-bubble 100000
 --max-tip 10000 --weak-cross 0.3). Both files must be byte-identical. Prints one JSON line.
 
-  python tools/syncasm_run.py [--reads 20000] [--genome 1000000] [--c 30] [--threads N]
+  python tests/tools/syncasm_run.py [--reads 20000] [--genome 1000000] [--c 30] [--threads N]
 
 Needs a CUDA device and oracle/_ref/libref.so (test infrastructure: the checker and the CPU baseline)."""
 import argparse
@@ -16,7 +16,7 @@ import sys
 import tempfile
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests", "golden"), os.path.join(ROOT, "tests")):
     sys.path.insert(0, p)
 from oatk_b200 import synth                          # noqa: E402
