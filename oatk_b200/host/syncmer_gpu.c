@@ -560,6 +560,9 @@ static void collect_ids(uint64_t lo, uint64_t hi, void *arg)
 static int oatk_collect_conflict_flag = 0;
 int oatk_collect_conflict(void) { return oatk_collect_conflict_flag; }
 
+/* the peak finder alone, for the tests that compare it with the reference's ha_analyze_count on histograms of their own */
+int oatk_find_peaks(int n, int first_bin, const int64_t *cnt, int *peak_het) { return find_peaks(n, first_bin, cnt, peak_het, 0); }
+
 syncmer_db_t *collect_syncmer_from_reads(sr_db_t *sr_db)
 {
     sg_batch *b = batch_of(sr_db, 0);

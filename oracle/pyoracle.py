@@ -256,6 +256,14 @@ class Ref:
             f["n_nucl"] = nn[:-1]
         return f
 
+    def analyze_count(self, cnt, start_cnt=5):
+        cnt = np.ascontiguousarray(cnt, dtype=np.int64)
+        het = C.c_int(0)
+        self.L.ref_analyze_count.restype = C.c_int
+        self.L.ref_analyze_count.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        hom = self.L.ref_analyze_count(len(cnt), start_cnt, cnt.ctypes.data, C.byref(het))
+        return hom, het.value
+
     def stat(self, db, verbose=0):
         d = np.zeros(5, np.float64)
         i = np.zeros(8, np.int32)

@@ -24,6 +24,8 @@ static double now_s(void)
 
 /* ---- unit functions (SURVEY appendix A.4 vectors come from these) ---- */
 uint64_t ref_hash64(uint64_t key, uint64_t mask) { return hash64(key, mask); }
+/* the peak finder behind sr_db_stat's peak_hom / peak_het lines (syncmer.c:775-865), quiet */
+int ref_analyze_count(int n_cnt, int start_cnt, const int64_t *cnt, int *peak_het) { return ha_analyze_count(n_cnt, start_cnt, cnt, peak_het, 0); }
 uint64_t ref_murmur64a(const void *p, uint32_t len, uint64_t seed) { return MurmurHash64A(p, len, seed); }
 uint64_t ref_kmer_hash64(uint8_t *hoco_s, uint32_t pos_rev, int k)
 {

@@ -135,3 +135,30 @@ def test_smer_conflict_is_where_the_reference_gives_up(oracle, ref):
     assert lines[2] == "[E::process_kmer_cluster] smer code 0: %d; read id: 0" % int(c["s"][0])
     assert lines[3] == "[E::process_kmer_cluster] smer code 1: %d; read id: 0" % (int(c["s"][0]) ^ 1)
     oracle.free(db, c)
+
+
+def test_peak_finder_three_ways(oracle, ref):
+    """the peak finder behind sr_db_stat's peak_hom / peak_het (and behind the automatic -c): the reference's
+    ha_analyze_count (syncmer.c:775-865), the oracle's restatement and the host layer's find_peaks on 3000 synthetic
+    multiplicity histograms (error spike, up to three coverage peaks, Poisson noise, truncated / flat / tiny tables)"""
+    import ctypes as C
+    from oatk_b200.host import build_host
+    host = C.CDLL(build_host.build())
+    host.oatk_find_peaks.restype = C.c_int
+    host.oatk_find_peaks.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    rng = np.random.default_rng(5)
+    x = np.arange(1001, dtype=np.float64)
+    for it in range(3000):
+        cnt = rng.choice([0, 1e3, 1e5, 1e7]) * np.exp(-x / rng.uniform(0.5, 3))
+        for _ in range(int(rng.integers(0, 4))):
+            mu, sd, amp = rng.uniform(6, 400), rng.uniform(1, 40), rng.choice([10, 1e3, 1e5])
+            cnt += amp * np.exp(-0.5 * ((x - mu) / sd) ** 2)
+        if rng.random() < 0.5: cnt = rng.poisson(np.maximum(cnt, 0)).astype(np.float64)
+        if rng.random() < 0.2: cnt[int(rng.integers(0, 1001)):] = 0
+        if rng.random() < 0.1: cnt[:] = rng.integers(0, 3, 1001)
+        if rng.random() < 0.3: cnt[1000] = rng.choice([0, 5, 1e6])
+        cnt[0] = 0
+        c = np.ascontiguousarray(cnt.astype(np.int64))
+        het = C.c_int(0)
+        ours = (host.oatk_find_peaks(len(c), 5, c.ctypes.data, C.byref(het)), het.value)
+        assert ours == ref.analyze_count(c) == oracle.analyze_count(c), (it, c[:40].tolist())
